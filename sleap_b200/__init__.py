@@ -1,0 +1,13 @@
+"""sleap_b200: B200-native (sm_100a) batched-frame pose inference path with the
+``sleap.nn.inference`` surface.  All device work goes through ``libsleapb200.so`` (C-ABI);
+there is no CPU fallback: using any op without a CUDA device raises."""
+__version__ = "0.1.0"
+
+from sleap_b200 import _lib  # noqa: F401
+
+
+def load_model(*args, **kwargs):
+    """Mirror of ``sleap.load_model`` (sleap/nn/inference.py:4865)."""
+    from sleap_b200.nn.inference import load_model as _lm
+
+    return _lm(*args, **kwargs)

@@ -1,0 +1,600 @@
+// Model engine: executes the flat op-list compiled from the reference's backbone + heads graph,
+// and the fused predictors (bottom-up / single-instance / centered-instance / centroid) on top.
+//
+// Reference: sleap/nn/model.py:312-364 (graph topology), sleap/nn/inference.py:2864-3003
+// (BottomUpInferenceLayer), :1319-1380 (SingleInstanceInferenceLayer), :1747-1966 (CentroidCrop),
+// :2059-2200 (FindInstancePeaks).
+#include <algorithm>
+
+#include "sb_common.cuh"
+#include "sb_kernels_direct.cuh"
+#include "sb_model.h"
+
+using namespace sbd;
+
+namespace {
+
+template <typename T> T* buf_ptr(const SbBuffer& b) { return (T*)b.dev; }
+
+size_t elem_size(const SbModel* m, const SbBuffer& b) { return (b.f32 || m->precision == 1) ? 4 : 2; }
+
+int grid_for(size_t total, int sm) {
+  size_t g = (total + 255) / 256;
+  size_t cap = (size_t)sm * 16;
+  return (int)std::max<size_t>(1, std::min(g, cap));
+}
+
+}  // namespace
+
+void sb_models_free(sb_handle_s* h) {
+  for (SbModel* m : h->models) {
+    if (!m) continue;
+    for (auto& b : m->buffers) if (b.dev) cudaFree(b.dev);
+    if (m->weights_dev) cudaFree(m->weights_dev);
+    if (m->weights_tc_dev) cudaFree(m->weights_tc_dev);
+    if (m->frames_dev) cudaFree(m->frames_dev);
+    if (m->crop_off_dev) cudaFree(m->crop_off_dev);
+    if (m->gpart) cudaFree(m->gpart);
+    if (m->gpoints) cudaFree(m->gpoints);
+    if (m->gvals) cudaFree(m->gvals);
+    sb_post_ws_free(m->ws);
+    sb_conv_tc_release(m);
+    delete m;
+  }
+  h->models.clear();
+}
+
+static SbModel* get_model(sb_handle_s* h, int id) {
+  if (!h || id < 0 || id >= (int)h->models.size()) return nullptr;
+  return h->models[id];
+}
+
+extern "C" {
+
+int sb_load_model(sb_handle_t h, const int32_t* ops, int n_ops, const float* weights, int64_t n_weights,
+                  int precision, int* out_model_id) {
+  if (!h) return sb_fail(nullptr, SB_ERR_INVALID, "null handle");
+  if (!ops || n_ops <= 0 || !weights || n_weights <= 0 || !out_model_id)
+    return sb_fail(h, SB_ERR_INVALID, "sb_load_model: bad arguments");
+  if (precision != 0 && precision != 1) return sb_fail(h, SB_ERR_INVALID, "precision must be 0 (fp16) or 1 (fp32)");
+  SB_CUDA(h, cudaSetDevice(h->device));
+  SbModel* m = new SbModel();
+  m->precision = precision;
+  m->n_weights = n_weights;
+  for (int i = 0; i < n_ops; ++i) {
+    const int32_t* w = ops + (size_t)i * SB_OP_WORDS;
+    if (w[0] == SB_OPK_BUFFER) {
+      SbBuffer b;
+      b.id = w[1]; b.stride_den = w[2]; b.C = w[3]; b.f32 = w[4]; b.is_input = w[5];
+      if (b.id != (int)m->buffers.size()) { delete m; return sb_fail(h, SB_ERR_INVALID, "buffer ids must be dense and ordered"); }
+      if (b.stride_den <= 0 || b.C <= 0) { delete m; return sb_fail(h, SB_ERR_INVALID, "bad buffer record"); }
+      m->buffers.push_back(b);
+    } else {
+      SbOp op;
+      memcpy(op.w, w, sizeof(op.w));
+      const int nb = (int)m->buffers.size();
+      auto okbuf = [&](int id) { return id >= 0 && id < nb; };
+      if (op.kind() < SB_OPK_CONV || op.kind() > SB_OPK_COPY) { delete m; return sb_fail(h, SB_ERR_INVALID, "op %d: unknown kind %d", i, op.kind()); }
+      if (!okbuf(op.out_buf()) || (op.kind() != SB_OPK_PREPROCESS && !okbuf(op.in_buf()))) { delete m; return sb_fail(h, SB_ERR_INVALID, "op %d: bad buffer id", i); }
+      if (op.kind() == SB_OPK_ADD && !okbuf(op.in2_buf())) { delete m; return sb_fail(h, SB_ERR_INVALID, "op %d: bad second input", i); }
+      auto okoff = [&](int off, int64_t n) { return off < 0 ? true : (int64_t)off + n <= n_weights; };
+      if (op.kind() == SB_OPK_CONV || op.kind() == SB_OPK_TCONV) {
+        const int64_t nw = (int64_t)op.k() * op.k() * op.in_C() * op.out_C();
+        if (op.w_off() < 0 || !okoff(op.w_off(), nw) || !okoff(op.b_off(), op.out_C()) ||
+            !okoff(op.bn_scale_off(), op.out_C()) || !okoff(op.bn_shift_off(), op.out_C())) {
+          delete m; return sb_fail(h, SB_ERR_INVALID, "op %d: weight offsets out of range", i);
+        }
+      }
+      m->ops.push_back(op);
+    }
+  }
+  if (m->buffers.empty() || m->ops.empty()) { delete m; return sb_fail(h, SB_ERR_INVALID, "empty model"); }
+  cudaError_t e = cudaMalloc((void**)&m->weights_dev, (size_t)n_weights * sizeof(float));
+  if (e != cudaSuccess) { delete m; return sb_fail(h, SB_ERR_CUDA, "cudaMalloc weights: %s", cudaGetErrorString(e)); }
+  e = cudaMemcpy(m->weights_dev, weights, (size_t)n_weights * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(m->weights_dev); delete m; return sb_fail(h, SB_ERR_CUDA, "copy weights: %s", cudaGetErrorString(e)); }
+  m->weights_host.assign(weights, weights + n_weights);
+  h->models.push_back(m);
+  *out_model_id = (int)h->models.size() - 1;
+  return SB_OK;
+}
+
+int sb_model_configure(sb_handle_t h, int model_id, int max_batch, int H, int W, int C_in) {
+  SbModel* m = get_model(h, model_id);
+  if (!m) return sb_fail(h, SB_ERR_INVALID, "bad model id");
+  if (max_batch <= 0 || H <= 0 || W <= 0 || (C_in != 1 && C_in != 3)) return sb_fail(h, SB_ERR_INVALID, "sb_model_configure: bad shape");
+  SB_CUDA(h, cudaSetDevice(h->device));
+  // preprocess op defines the net input size
+  const SbOp* pre = nullptr;
+  for (auto& op : m->ops) if (op.kind() == SB_OPK_PREPROCESS) { pre = &op; break; }
+  if (!pre) return sb_fail(h, SB_ERR_INVALID, "model has no preprocess op");
+  const float input_scale = pre->input_scale();
+  const int pad_stride = std::max(1, pre->pad_stride());
+  int Hres = H, Wres = W;
+  if (input_scale != 1.0f) { Wres = (int)((float)W * input_scale); Hres = (int)((float)H * input_scale); }
+  const int Hnet = ((Hres + pad_stride - 1) / pad_stride) * pad_stride;
+  const int Wnet = ((Wres + pad_stride - 1) / pad_stride) * pad_stride;
+  for (auto& b : m->buffers) {
+    if (Hnet % b.stride_den || Wnet % b.stride_den)
+      return sb_fail(h, SB_ERR_INVALID, "net input %dx%d not divisible by stride %d (pad_to_stride too small)", Hnet, Wnet, b.stride_den);
+  }
+  for (auto& b : m->buffers) { if (b.dev) { cudaFree(b.dev); b.dev = nullptr; } }
+  if (m->frames_dev) { cudaFree(m->frames_dev); m->frames_dev = nullptr; }
+  sb_conv_tc_release(m);
+  m->B = max_batch; m->Hin = H; m->Win = W; m->Cin = C_in; m->Hres = Hres; m->Wres = Wres; m->Hnet = Hnet; m->Wnet = Wnet;
+  size_t total = 0;
+  for (auto& b : m->buffers) {
+    b.H = Hnet / b.stride_den; b.W = Wnet / b.stride_den;
+    const size_t bytes = (size_t)max_batch * b.H * b.W * b.C * elem_size(m, b);
+    cudaError_t e = cudaMalloc(&b.dev, bytes + 256);
+    if (e != cudaSuccess) return sb_fail(h, SB_ERR_CUDA, "cudaMalloc buffer %d (%zu B): %s", b.id, bytes, cudaGetErrorString(e));
+    total += bytes;
+  }
+  m->act_bytes = total;
+  SB_CUDA(h, cudaMalloc(&m->frames_dev, (size_t)max_batch * H * W * C_in * sizeof(float)));
+  int rc = sb_conv_tc_prepare(h, m);
+  if (rc) return rc;
+  m->configured = true;
+  return SB_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+template <typename T>
+static int run_ops_t(sb_handle_s* h, SbModel* m, const void* frames_dev, int frames_are_u8, int B) {
+  cudaStream_t s = h->stream;
+  for (size_t oi = 0; oi < m->ops.size(); ++oi) {
+    const SbOp& op = m->ops[oi];
+    SbBuffer& ob = m->buffers[op.out_buf()];
+    switch (op.kind()) {
+      case SB_OPK_PREPROCESS: {
+        const size_t total = (size_t)B * ob.H * ob.W * ob.C;
+        const int resize = op.input_scale() != 1.0f;
+        int mode_ch = 0;
+        if (m->Cin == 3 && ob.C == 1) mode_ch = 1;
+        if (m->Cin == 1 && ob.C == 3) mode_ch = 2;
+        if (frames_are_u8)
+          k_preprocess<unsigned char, T><<<grid_for(total, h->sm_count), 256, 0, s>>>(
+              (const unsigned char*)frames_dev, m->Hin, m->Win, m->Cin, (T*)ob.dev, ob.H, ob.W, ob.C, m->Hres, m->Wres, resize, mode_ch, 1, total);
+        else
+          k_preprocess<float, T><<<grid_for(total, h->sm_count), 256, 0, s>>>(
+              (const float*)frames_dev, m->Hin, m->Win, m->Cin, (T*)ob.dev, ob.H, ob.W, ob.C, m->Hres, m->Wres, resize, mode_ch, 0, total);
+        SB_CHECK_LAUNCH(h);
+        break;
+      }
+      case SB_OPK_CONV: {
+        SbBuffer& ib = m->buffers[op.in_buf()];
+        if (m->precision == 0 && sb_conv_tc_can(m, (int)oi)) {
+          int rc = sb_conv_tc_launch(h, m, (int)oi, B);
+          if (rc) return rc;
+          break;
+        }
+        const int k = op.k(), st = op.stride();
+        const int Hout = ob.H, Wout = ob.W;
+        const int tot_h = std::max((Hout - 1) * st + k - ib.H, 0), tot_w = std::max((Wout - 1) * st + k - ib.W, 0);
+        const int pad_top = tot_h / 2, pad_left = tot_w / 2;
+        const float* W = m->weights_dev + op.w_off();
+        const float* bias = op.b_off() >= 0 ? m->weights_dev + op.b_off() : nullptr;
+        const float* bs = (op.flags() & SB_OPF_BN) ? m->weights_dev + op.bn_scale_off() : nullptr;
+        const float* bh = (op.flags() & SB_OPF_BN) ? m->weights_dev + op.bn_shift_off() : nullptr;
+        const int in_tile = (DC_TILE - 1) * st + k;
+        const size_t sm = ((size_t)in_tile * in_tile * DC_CK + (size_t)k * k * DC_CK * DC_CO) * sizeof(float);
+        dim3 g(((Wout + DC_TILE - 1) / DC_TILE) * ((Hout + DC_TILE - 1) / DC_TILE), (op.out_C() + DC_CO - 1) / DC_CO, B);
+        const int relu = (op.flags() & SB_OPF_RELU) ? 1 : 0;
+        if (ob.f32 && sizeof(T) == 2) {
+          auto kern = k_conv_direct<T, float>;
+          if (sm > 48 * 1024) SB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+          kern<<<g, 256, sm, s>>>((const T*)ib.dev, ib.H, ib.W, ib.C, op.in_coff(), op.in_C(), (float*)ob.dev, Hout, Wout,
+                                  ob.C, op.out_coff(), op.out_C(), W, bias, bs, bh, k, st, pad_top, pad_left, relu);
+        } else {
+          auto kern = k_conv_direct<T, T>;
+          if (sm > 48 * 1024) SB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+          kern<<<g, 256, sm, s>>>((const T*)ib.dev, ib.H, ib.W, ib.C, op.in_coff(), op.in_C(), (T*)ob.dev, Hout, Wout,
+                                  ob.C, op.out_coff(), op.out_C(), W, bias, bs, bh, k, st, pad_top, pad_left, relu);
+        }
+        SB_CHECK_LAUNCH(h);
+        break;
+      }
+      case SB_OPK_TCONV: {
+        SbBuffer& ib = m->buffers[op.in_buf()];
+        if (m->precision == 0 && sb_conv_tc_can(m, (int)oi)) {
+          int rc = sb_conv_tc_launch(h, m, (int)oi, B);
+          if (rc) return rc;
+          break;
+        }
+        const float* W = m->weights_dev + op.w_off();
+        const float* bias = op.b_off() >= 0 ? m->weights_dev + op.b_off() : nullptr;
+        dim3 g((ob.H * ob.W + 255) / 256, (op.out_C() + DC_CO - 1) / DC_CO, B);
+        k_tconv_direct<T, T><<<g, 256, 0, s>>>((const T*)ib.dev, ib.H, ib.W, ib.C, op.in_coff(), op.in_C(), (T*)ob.dev, ob.C,
+                                               op.out_coff(), op.out_C(), W, bias, (op.flags() & SB_OPF_RELU) ? 1 : 0);
+        SB_CHECK_LAUNCH(h);
+        break;
+      }
+      case SB_OPK_POOL: {
+        SbBuffer& ib = m->buffers[op.in_buf()];
+        const size_t total = (size_t)B * ob.H * ob.W * op.in_C();
+        k_maxpool2<T><<<grid_for(total, h->sm_count), 256, 0, s>>>((const T*)ib.dev, ib.H, ib.W, ib.C, op.in_coff(), op.in_C(),
+                                                                   (T*)ob.dev, ob.H, ob.W, ob.C, op.out_coff(), total);
+        SB_CHECK_LAUNCH(h);
+        break;
+      }
+      case SB_OPK_UPSAMPLE: {
+        SbBuffer& ib = m->buffers[op.in_buf()];
+        const size_t total = (size_t)B * ob.H * ob.W * op.in_C();
+        k_upsample2<T><<<grid_for(total, h->sm_count), 256, 0, s>>>((const T*)ib.dev, ib.H, ib.W, ib.C, op.in_coff(), op.in_C(),
+                                                                    (T*)ob.dev, ob.C, op.out_coff(),
+                                                                    (op.flags() & SB_OPF_BILINEAR) ? 1 : 0, total);
+        SB_CHECK_LAUNCH(h);
+        break;
+      }
+      case SB_OPK_ADD: {
+        SbBuffer& ib = m->buffers[op.in_buf()];
+        SbBuffer& ib2 = m->buffers[op.in2_buf()];
+        const size_t npix = (size_t)B * ob.H * ob.W;
+        k_add<T><<<grid_for(npix * op.in_C(), h->sm_count), 256, 0, s>>>((const T*)ib.dev, ib.C, op.in_coff(), (const T*)ib2.dev, ib2.C,
+                                                                         op.in2_coff(), (T*)ob.dev, ob.C, op.out_coff(), op.in_C(), npix);
+        SB_CHECK_LAUNCH(h);
+        break;
+      }
+      case SB_OPK_COPY: {
+        SbBuffer& ib = m->buffers[op.in_buf()];
+        const size_t npix = (size_t)B * ob.H * ob.W;
+        k_copy<T><<<grid_for(npix * op.in_C(), h->sm_count), 256, 0, s>>>((const T*)ib.dev, ib.C, op.in_coff(), (T*)ob.dev, ob.C,
+                                                                          op.out_coff(), op.in_C(), npix);
+        SB_CHECK_LAUNCH(h);
+        break;
+      }
+      default:
+        return sb_fail(h, SB_ERR_INVALID, "unknown op kind %d", op.kind());
+    }
+  }
+  return 0;
+}
+
+int sb_run_ops(sb_handle_s* h, SbModel* m, const void* frames_dev, int frames_are_u8, int B) {
+  if (!m->configured) return sb_fail(h, SB_ERR_INVALID, "model not configured");
+  if (B <= 0 || B > m->B) return sb_fail(h, SB_ERR_INVALID, "batch %d exceeds configured max %d", B, m->B);
+  if (m->precision == 1) return run_ops_t<float>(h, m, frames_dev, frames_are_u8, B);
+  return run_ops_t<__half>(h, m, frames_dev, frames_are_u8, B);
+}
+
+__global__ void k_half_to_float(const __half* __restrict__ in, float* __restrict__ out, size_t n) {
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x)
+    out[t] = __half2float(in[t]);
+}
+
+static int upload_frames(sb_handle_s* h, SbModel* m, const void* images_host, int is_u8, int B) {
+  const size_t bytes = (size_t)B * m->Hin * m->Win * m->Cin * (is_u8 ? 1 : 4);
+  SB_CUDA(h, cudaMemcpyAsync(m->frames_dev, images_host, bytes, cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+
+extern "C" {
+
+int sb_model_forward(sb_handle_t h, int model_id, const void* images_host, int images_are_u8, int B,
+                     int n_outputs, const int32_t* output_buffer_ids, float** out_host_ptrs) {
+  SbModel* m = get_model(h, model_id);
+  if (!m) return sb_fail(h, SB_ERR_INVALID, "bad model id");
+  SB_CUDA(h, cudaSetDevice(h->device));
+  if (!m->configured) return sb_fail(h, SB_ERR_INVALID, "model not configured");
+  if (B <= 0 || B > m->B) return sb_fail(h, SB_ERR_INVALID, "bad batch");
+  int rc = upload_frames(h, m, images_host, images_are_u8, B);
+  if (rc) return rc;
+  if ((rc = sb_run_ops(h, m, m->frames_dev, images_are_u8, B))) return rc;
+  for (int i = 0; i < n_outputs; ++i) {
+    const int id = output_buffer_ids[i];
+    if (id < 0 || id >= (int)m->buffers.size()) return sb_fail(h, SB_ERR_INVALID, "bad output buffer id %d", id);
+    SbBuffer& b = m->buffers[id];
+    const size_t n = (size_t)B * b.H * b.W * b.C;
+    if (elem_size(m, b) == 4) {
+      SB_CUDA(h, cudaMemcpyAsync(out_host_ptrs[i], b.dev, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    } else {
+      float* tmp = nullptr;
+      SB_CUDA(h, cudaMalloc((void**)&tmp, n * 4));
+      k_half_to_float<<<grid_for(n, h->sm_count), 256, 0, h->stream>>>((const __half*)b.dev, tmp, n);
+      h->gpu_launches++;
+      cudaError_t e = cudaMemcpyAsync(out_host_ptrs[i], tmp, n * 4, cudaMemcpyDeviceToHost, h->stream);
+      cudaStreamSynchronize(h->stream);
+      cudaFree(tmp);
+      if (e != cudaSuccess) return sb_fail(h, SB_ERR_CUDA, "copy out: %s", cudaGetErrorString(e));
+    }
+  }
+  SB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return SB_OK;
+}
+
+// ---------------------------------- bottom-up ------------------------------------------------
+int sb_bottomup_configure(sb_handle_t h, int model_id, const sb_bottomup_params* p) {
+  SbModel* m = get_model(h, model_id);
+  if (!m || !p) return sb_fail(h, SB_ERR_INVALID, "bad model id / params");
+  if (!m->configured) return sb_fail(h, SB_ERR_INVALID, "call sb_model_configure first");
+  SB_CUDA(h, cudaSetDevice(h->device));
+  const int nb = (int)m->buffers.size();
+  if (p->cms_buffer < 0 || p->cms_buffer >= nb || p->pafs_buffer < 0 || p->pafs_buffer >= nb)
+    return sb_fail(h, SB_ERR_INVALID, "cms/pafs buffer ids out of range");
+  SbBuffer& cb = m->buffers[p->cms_buffer];
+  SbBuffer& pb = m->buffers[p->pafs_buffer];
+  if (!cb.f32 || !pb.f32) return sb_fail(h, SB_ERR_INVALID, "cms / pafs buffers must be f32 head outputs");
+  if (cb.C != p->n_nodes || pb.C != 2 * p->n_edges) return sb_fail(h, SB_ERR_INVALID, "head channels do not match skeleton");
+  if (p->offsets_buffer >= 0 && (p->offsets_buffer >= nb || !m->buffers[p->offsets_buffer].f32 || m->buffers[p->offsets_buffer].C != 2 * p->n_nodes))
+    return sb_fail(h, SB_ERR_INVALID, "bad offsets buffer");
+  if (p->n_sorted > p->n_edges || p->max_peaks_per_sample <= 0 || p->max_node_peaks <= 0 || p->max_instances <= 0)
+    return sb_fail(h, SB_ERR_INVALID, "bad capacities");
+  for (int e = 0; e < 2 * p->n_edges; ++e)
+    if (p->edges[e] < 0 || p->edges[e] >= p->n_nodes) return sb_fail(h, SB_ERR_INVALID, "edge node index out of range");
+  sb_post_ws_free(m->ws);
+  int rc = sb_post_ws_alloc(h, m->ws, m->B, cb.H, cb.W, cb.C, p->max_peaks_per_sample, p->max_node_peaks, p->max_instances, p->n_edges);
+  if (rc) return rc;
+  SB_CUDA(h, cudaMemcpy(m->ws.edges_dev, p->edges, (size_t)p->n_edges * 2 * sizeof(int), cudaMemcpyHostToDevice));
+  if (p->n_sorted > 0)
+    SB_CUDA(h, cudaMemcpy(m->ws.sorted_edges_dev, p->sorted_edge_inds, (size_t)p->n_sorted * sizeof(int), cudaMemcpyHostToDevice));
+  m->ws.n_sorted = p->n_sorted;
+  m->bu = *p;
+  m->bu.edges = nullptr; m->bu.sorted_edge_inds = nullptr;
+  m->bu_edges.assign(p->edges, p->edges + 2 * p->n_edges);
+  m->bu_configured = true;
+  return SB_OK;
+}
+
+static int bottomup_post(sb_handle_s* h, SbModel* m, int B) {
+  const sb_bottomup_params& p = m->bu;
+  SbBuffer& cb = m->buffers[p.cms_buffer];
+  SbBuffer& pb = m->buffers[p.pafs_buffer];
+  const float* off = p.offsets_buffer >= 0 ? (const float*)m->buffers[p.offsets_buffer].dev : nullptr;
+  SbPeakParams pp{p.peak_threshold, p.refinement, p.integral_patch_size, (float)p.cm_output_stride, 1.0f};
+  int rc = sbk_local_peaks(h, cb.dev, 0, off, B, cb.H, cb.W, cb.C, pp, m->ws);
+  if (rc) return rc;
+  const float max_len = p.max_edge_length_ratio * (float)std::max(std::max(pb.H, pb.W), pb.C) * (float)p.paf_output_stride;
+  if ((rc = sbk_score_match(h, (const float*)pb.dev, B, pb.H, pb.W, pb.C, p.n_line_points, p.paf_output_stride, max_len,
+                            p.dist_penalty_weight, m->ws))) return rc;
+  return sbk_group(h, B, p.n_nodes, p.min_instance_peaks, p.min_line_scores, p.input_scale, m->ws);
+}
+
+int sb_infer_bottomup_dev(sb_handle_t h, int model_id, const uint8_t* frames_dev, int B) {
+  SbModel* m = get_model(h, model_id);
+  if (!m || !m->bu_configured) return sb_fail(h, SB_ERR_INVALID, "bottom-up predictor not configured");
+  SB_CUDA(h, cudaSetDevice(h->device));
+  int rc = sb_run_ops(h, m, frames_dev, 1, B);
+  if (rc) return rc;
+  return bottomup_post(h, m, B);
+}
+
+int sb_infer_bottomup(sb_handle_t h, int model_id, const uint8_t* frames_host, int B, float* out_instance_peaks,
+                      float* out_instance_peak_vals, float* out_instance_scores, int32_t* out_n_valid,
+                      int32_t* out_flags) {
+  SbModel* m = get_model(h, model_id);
+  if (!m || !m->bu_configured) return sb_fail(h, SB_ERR_INVALID, "bottom-up predictor not configured");
+  SB_CUDA(h, cudaSetDevice(h->device));
+  if (B <= 0 || B > m->B) return sb_fail(h, SB_ERR_INVALID, "bad batch");
+  int rc = upload_frames(h, m, frames_host, 1, B);
+  if (rc) return rc;
+  if ((rc = sb_run_ops(h, m, m->frames_dev, 1, B))) return rc;
+  if ((rc = bottomup_post(h, m, B))) return rc;
+  const sb_bottomup_params& p = m->bu;
+  const size_t I = p.max_instances, C = p.n_nodes;
+  SB_CUDA(h, cudaMemcpyAsync(out_instance_peaks, m->ws.inst_peaks, (size_t)B * I * C * 2 * 4, cudaMemcpyDeviceToHost, h->stream));
+  SB_CUDA(h, cudaMemcpyAsync(out_instance_peak_vals, m->ws.inst_vals, (size_t)B * I * C * 4, cudaMemcpyDeviceToHost, h->stream));
+  SB_CUDA(h, cudaMemcpyAsync(out_instance_scores, m->ws.inst_scores, (size_t)B * I * 4, cudaMemcpyDeviceToHost, h->stream));
+  SB_CUDA(h, cudaMemcpyAsync(out_n_valid, m->ws.n_inst, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (out_flags) SB_CUDA(h, cudaMemcpyAsync(out_flags, m->ws.flags, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+  SB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return SB_OK;
+}
+
+int sb_bottomup_device_outputs(sb_handle_t h, int model_id, float** instance_peaks_dev, float** instance_peak_vals_dev,
+                               float** instance_scores_dev, int32_t** n_valid_dev, int32_t** flags_dev) {
+  SbModel* m = get_model(h, model_id);
+  if (!m || !m->bu_configured) return sb_fail(h, SB_ERR_INVALID, "bottom-up predictor not configured");
+  if (instance_peaks_dev) *instance_peaks_dev = m->ws.inst_peaks;
+  if (instance_peak_vals_dev) *instance_peak_vals_dev = m->ws.inst_vals;
+  if (instance_scores_dev) *instance_scores_dev = m->ws.inst_scores;
+  if (n_valid_dev) *n_valid_dev = m->ws.n_inst;
+  if (flags_dev) *flags_dev = m->ws.flags;
+  return SB_OK;
+}
+
+static int fetch_graph_ws(sb_handle_s* h, SbPostWs& ws, const int* edges_host, int B, int cap_peaks, float* peaks,
+                          float* peak_vals, int32_t* peak_channel_inds, int32_t* peak_offsets, int cap_cands,
+                          int32_t* edge_inds, int32_t* edge_peak_inds, float* line_scores, int32_t* cand_offsets) {
+  const int C = ws.C, K = ws.max_node_peaks, E = ws.n_edges, MP = ws.max_peaks;
+  std::vector<int> np(B), ncnt((size_t)B * C), nlist((size_t)B * C * K);
+  std::vector<float> mat((size_t)B * E * K * K);
+  SB_CUDA(h, cudaStreamSynchronize(h->stream));
+  SB_CUDA(h, cudaMemcpy(np.data(), ws.n_peaks, (size_t)B * 4, cudaMemcpyDeviceToHost));
+  SB_CUDA(h, cudaMemcpy(ncnt.data(), ws.node_cnt, ncnt.size() * 4, cudaMemcpyDeviceToHost));
+  SB_CUDA(h, cudaMemcpy(nlist.data(), ws.node_peaks, nlist.size() * 4, cudaMemcpyDeviceToHost));
+  SB_CUDA(h, cudaMemcpy(mat.data(), ws.score_mat, mat.size() * 4, cudaMemcpyDeviceToHost));
+  int tp = 0, tc = 0;
+  for (int b = 0; b < B; ++b) {
+    peak_offsets[b] = tp;
+    cand_offsets[b] = tc;
+    if (tp + np[b] > cap_peaks) return sb_fail(h, SB_ERR_INVALID, "peak capacity exceeded");
+    if (np[b] > 0) {
+      SB_CUDA(h, cudaMemcpy(peaks + 2 * (size_t)tp, ws.peaks + (size_t)b * MP * 2, (size_t)np[b] * 8, cudaMemcpyDeviceToHost));
+      SB_CUDA(h, cudaMemcpy(peak_vals + tp, ws.peak_vals + (size_t)b * MP, (size_t)np[b] * 4, cudaMemcpyDeviceToHost));
+      SB_CUDA(h, cudaMemcpy(peak_channel_inds + tp, ws.peak_ch + (size_t)b * MP, (size_t)np[b] * 4, cudaMemcpyDeviceToHost));
+    }
+    tp += np[b];
+    for (int e = 0; e < E; ++e) {
+      const int sn = edges_host[2 * e], dn = edges_host[2 * e + 1];
+      const int ns = std::min(ncnt[(size_t)b * C + sn], K), nd = std::min(ncnt[(size_t)b * C + dn], K);
+      for (int i = 0; i < ns; ++i)
+        for (int j = 0; j < nd; ++j) {
+          if (tc >= cap_cands) return sb_fail(h, SB_ERR_INVALID, "candidate capacity exceeded");
+          edge_inds[tc] = e;
+          edge_peak_inds[2 * tc] = nlist[((size_t)b * C + sn) * K + i];
+          edge_peak_inds[2 * tc + 1] = nlist[((size_t)b * C + dn) * K + j];
+          line_scores[tc] = mat[((size_t)b * E + e) * K * K + (size_t)i * nd + j];
+          ++tc;
+        }
+    }
+  }
+  peak_offsets[B] = tp;
+  cand_offsets[B] = tc;
+  return SB_OK;
+}
+
+int sb_bottomup_fetch_graph(sb_handle_t h, int model_id, int B, int cap_peaks, float* peaks, float* peak_vals,
+                            int32_t* peak_channel_inds, int32_t* peak_offsets, int cap_cands, int32_t* edge_inds,
+                            int32_t* edge_peak_inds, float* line_scores, int32_t* cand_offsets) {
+  SbModel* m = get_model(h, model_id);
+  if (!m || !m->bu_configured) return sb_fail(h, SB_ERR_INVALID, "bottom-up predictor not configured");
+  SB_CUDA(h, cudaSetDevice(h->device));
+  return fetch_graph_ws(h, m->ws, m->bu_edges.data(), B, cap_peaks, peaks, peak_vals, peak_channel_inds, peak_offsets,
+                        cap_cands, edge_inds, edge_peak_inds, line_scores, cand_offsets);
+}
+
+int sb_bottomup_from_maps(sb_handle_t h, const sb_bottomup_params* p, const float* cms_host, int B, int H, int W,
+                          const float* pafs_host, int Hp, int Wp, const float* offsets_host,
+                          float* out_instance_peaks, float* out_instance_peak_vals, float* out_instance_scores,
+                          int32_t* out_n_valid, int32_t* out_flags, int cap_peaks, float* peaks, float* peak_vals,
+                          int32_t* peak_channel_inds, int32_t* peak_offsets, int cap_cands, int32_t* edge_inds,
+                          int32_t* edge_peak_inds, float* line_scores, int32_t* cand_offsets) {
+  if (!h || !p) return sb_fail(h, SB_ERR_INVALID, "null handle / params");
+  if (B <= 0 || H <= 0 || W <= 0 || Hp <= 0 || Wp <= 0 || p->n_nodes <= 0 || p->n_edges <= 0)
+    return sb_fail(h, SB_ERR_INVALID, "sb_bottomup_from_maps: bad shape");
+  SB_CUDA(h, cudaSetDevice(h->device));
+  const int C = p->n_nodes, C2 = 2 * p->n_edges;
+  SbPostWs ws;
+  struct Guard { SbPostWs& w; std::vector<void*> bufs; ~Guard() { sb_post_ws_free(w); for (void* q : bufs) cudaFree(q); } } guard{ws, {}};
+  int rc = sb_post_ws_alloc(h, ws, B, H, W, C, p->max_peaks_per_sample, p->max_node_peaks, p->max_instances, p->n_edges);
+  if (rc) return rc;
+  auto dalloc = [&](void** q, size_t bytes) -> int {
+    cudaError_t e = cudaMalloc(q, bytes + 16);
+    if (e != cudaSuccess) return sb_fail(h, SB_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e));
+    guard.bufs.push_back(*q);
+    return 0;
+  };
+  void *d_cms = nullptr, *d_pafs = nullptr, *d_off = nullptr;
+  const size_t ncm = (size_t)B * H * W * C, npf = (size_t)B * Hp * Wp * C2;
+  if ((rc = dalloc(&d_cms, ncm * 4)) || (rc = dalloc(&d_pafs, npf * 4))) return rc;
+  SB_CUDA(h, cudaMemcpyAsync(d_cms, cms_host, ncm * 4, cudaMemcpyHostToDevice, h->stream));
+  SB_CUDA(h, cudaMemcpyAsync(d_pafs, pafs_host, npf * 4, cudaMemcpyHostToDevice, h->stream));
+  if (offsets_host) {
+    if ((rc = dalloc(&d_off, 2 * ncm * 4))) return rc;
+    SB_CUDA(h, cudaMemcpyAsync(d_off, offsets_host, 2 * ncm * 4, cudaMemcpyHostToDevice, h->stream));
+  }
+  SB_CUDA(h, cudaMemcpyAsync(ws.edges_dev, p->edges, (size_t)p->n_edges * 8, cudaMemcpyHostToDevice, h->stream));
+  if (p->n_sorted > 0) SB_CUDA(h, cudaMemcpyAsync(ws.sorted_edges_dev, p->sorted_edge_inds, (size_t)p->n_sorted * 4, cudaMemcpyHostToDevice, h->stream));
+  ws.n_sorted = p->n_sorted;
+  SbPeakParams pp{p->peak_threshold, p->refinement, p->integral_patch_size, (float)p->cm_output_stride, 1.0f};
+  if ((rc = sbk_local_peaks(h, d_cms, 0, (const float*)d_off, B, H, W, C, pp, ws))) return rc;
+  const float max_len = p->max_edge_length_ratio * (float)std::max(std::max(Hp, Wp), C2) * (float)p->paf_output_stride;
+  if ((rc = sbk_score_match(h, (const float*)d_pafs, B, Hp, Wp, C2, p->n_line_points, p->paf_output_stride, max_len,
+                            p->dist_penalty_weight, ws))) return rc;
+  if ((rc = sbk_group(h, B, C, p->min_instance_peaks, p->min_line_scores, p->input_scale, ws))) return rc;
+  const size_t I = p->max_instances;
+  SB_CUDA(h, cudaMemcpyAsync(out_instance_peaks, ws.inst_peaks, (size_t)B * I * C * 8, cudaMemcpyDeviceToHost, h->stream));
+  SB_CUDA(h, cudaMemcpyAsync(out_instance_peak_vals, ws.inst_vals, (size_t)B * I * C * 4, cudaMemcpyDeviceToHost, h->stream));
+  SB_CUDA(h, cudaMemcpyAsync(out_instance_scores, ws.inst_scores, (size_t)B * I * 4, cudaMemcpyDeviceToHost, h->stream));
+  SB_CUDA(h, cudaMemcpyAsync(out_n_valid, ws.n_inst, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (out_flags) SB_CUDA(h, cudaMemcpyAsync(out_flags, ws.flags, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+  SB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (peaks)
+    return fetch_graph_ws(h, ws, p->edges, B, cap_peaks, peaks, peak_vals, peak_channel_inds, peak_offsets, cap_cands,
+                          edge_inds, edge_peak_inds, line_scores, cand_offsets);
+  return SB_OK;
+}
+
+// ---------------------------------- global peaks (single / centered instance) ----------------
+int sb_global_configure(sb_handle_t h, int model_id, const sb_global_params* p) {
+  SbModel* m = get_model(h, model_id);
+  if (!m || !p) return sb_fail(h, SB_ERR_INVALID, "bad model id / params");
+  if (!m->configured) return sb_fail(h, SB_ERR_INVALID, "call sb_model_configure first");
+  SB_CUDA(h, cudaSetDevice(h->device));
+  const int nb = (int)m->buffers.size();
+  if (p->cms_buffer < 0 || p->cms_buffer >= nb || !m->buffers[p->cms_buffer].f32) return sb_fail(h, SB_ERR_INVALID, "bad cms buffer");
+  if (p->offsets_buffer >= nb) return sb_fail(h, SB_ERR_INVALID, "bad offsets buffer");
+  SbBuffer& cb = m->buffers[p->cms_buffer];
+  if (cb.C > 256) return sb_fail(h, SB_ERR_UNSUPPORTED, "more than 256 confidence-map channels");
+  int target = (2 * h->sm_count + m->B - 1) / m->B;
+  m->g_rpc = std::max(1, (cb.H + target - 1) / target);
+  m->g_chunks = (cb.H + m->g_rpc - 1) / m->g_rpc;
+  if (m->gpart) cudaFree(m->gpart);
+  if (m->gpoints) cudaFree(m->gpoints);
+  if (m->gvals) cudaFree(m->gvals);
+  if (m->crop_off_dev) cudaFree(m->crop_off_dev);
+  SB_CUDA(h, cudaMalloc((void**)&m->gpart, (size_t)m->B * m->g_chunks * cb.C * 3 * 4));
+  SB_CUDA(h, cudaMalloc((void**)&m->gpoints, (size_t)m->B * cb.C * 2 * 4));
+  SB_CUDA(h, cudaMalloc((void**)&m->gvals, (size_t)m->B * cb.C * 4));
+  SB_CUDA(h, cudaMalloc((void**)&m->crop_off_dev, (size_t)m->B * 2 * 4));
+  m->gl = *p;
+  m->gl_configured = true;
+  return SB_OK;
+}
+
+int sb_infer_global(sb_handle_t h, int model_id, const void* images_host, int images_are_u8, int B,
+                    const float* crop_offsets_host, float* out_points, float* out_vals) {
+  SbModel* m = get_model(h, model_id);
+  if (!m || !m->gl_configured) return sb_fail(h, SB_ERR_INVALID, "global-peak predictor not configured");
+  SB_CUDA(h, cudaSetDevice(h->device));
+  if (B <= 0 || B > m->B) return sb_fail(h, SB_ERR_INVALID, "bad batch");
+  int rc = upload_frames(h, m, images_host, images_are_u8, B);
+  if (rc) return rc;
+  if (crop_offsets_host) SB_CUDA(h, cudaMemcpyAsync(m->crop_off_dev, crop_offsets_host, (size_t)B * 8, cudaMemcpyHostToDevice, h->stream));
+  if ((rc = sb_run_ops(h, m, m->frames_dev, images_are_u8, B))) return rc;
+  const sb_global_params& p = m->gl;
+  SbBuffer& cb = m->buffers[p.cms_buffer];
+  const float* off = p.offsets_buffer >= 0 ? (const float*)m->buffers[p.offsets_buffer].dev : nullptr;
+  SbPeakParams pp{p.peak_threshold, p.refinement, p.integral_patch_size, (float)p.output_stride, p.input_scale};
+  if ((rc = sbk_global_peaks(h, cb.dev, 0, off, B, cb.H, cb.W, cb.C, pp, crop_offsets_host ? m->crop_off_dev : nullptr,
+                             m->gpart, m->g_chunks, m->g_rpc, m->gpoints, m->gvals))) return rc;
+  SB_CUDA(h, cudaMemcpyAsync(out_points, m->gpoints, (size_t)B * cb.C * 8, cudaMemcpyDeviceToHost, h->stream));
+  SB_CUDA(h, cudaMemcpyAsync(out_vals, m->gvals, (size_t)B * cb.C * 4, cudaMemcpyDeviceToHost, h->stream));
+  SB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return SB_OK;
+}
+
+// ---------------------------------- centroids (top-down stage 1) ------------------------------
+int sb_centroid_configure(sb_handle_t h, int model_id, const sb_centroid_params* p) {
+  SbModel* m = get_model(h, model_id);
+  if (!m || !p) return sb_fail(h, SB_ERR_INVALID, "bad model id / params");
+  if (!m->configured) return sb_fail(h, SB_ERR_INVALID, "call sb_model_configure first");
+  SB_CUDA(h, cudaSetDevice(h->device));
+  const int nb = (int)m->buffers.size();
+  if (p->cms_buffer < 0 || p->cms_buffer >= nb || !m->buffers[p->cms_buffer].f32) return sb_fail(h, SB_ERR_INVALID, "bad cms buffer");
+  SbBuffer& cb = m->buffers[p->cms_buffer];
+  sb_post_ws_free(m->ws);
+  int rc = sb_post_ws_alloc(h, m->ws, m->B, cb.H, cb.W, cb.C, p->max_peaks_per_sample, 1, 1, 0);
+  if (rc) return rc;
+  m->ce = *p;
+  m->ce_configured = true;
+  return SB_OK;
+}
+
+int sb_infer_centroids(sb_handle_t h, int model_id, const void* images_host, int images_are_u8, int B,
+                       float* out_centroids, float* out_vals, int32_t* out_sample_inds, int32_t* out_n,
+                       int32_t* out_flags) {
+  SbModel* m = get_model(h, model_id);
+  if (!m || !m->ce_configured) return sb_fail(h, SB_ERR_INVALID, "centroid predictor not configured");
+  SB_CUDA(h, cudaSetDevice(h->device));
+  if (B <= 0 || B > m->B) return sb_fail(h, SB_ERR_INVALID, "bad batch");
+  int rc = upload_frames(h, m, images_host, images_are_u8, B);
+  if (rc) return rc;
+  if ((rc = sb_run_ops(h, m, m->frames_dev, images_are_u8, B))) return rc;
+  const sb_centroid_params& p = m->ce;
+  SbBuffer& cb = m->buffers[p.cms_buffer];
+  const float* off = p.offsets_buffer >= 0 ? (const float*)m->buffers[p.offsets_buffer].dev : nullptr;
+  SbPeakParams pp{p.peak_threshold, p.refinement, p.integral_patch_size, (float)p.output_stride, p.input_scale};
+  if ((rc = sbk_local_peaks(h, cb.dev, 0, off, B, cb.H, cb.W, cb.C, pp, m->ws))) return rc;
+  std::vector<int> cnt(B), fl(B);
+  SB_CUDA(h, cudaMemcpyAsync(cnt.data(), m->ws.n_peaks, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+  SB_CUDA(h, cudaMemcpyAsync(fl.data(), m->ws.flags, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
+  SB_CUDA(h, cudaStreamSynchronize(h->stream));
+  int total = 0;
+  for (int b = 0; b < B; ++b) {
+    if (cnt[b] > 0) {
+      SB_CUDA(h, cudaMemcpyAsync(out_centroids + 2 * (size_t)total, m->ws.peaks + (size_t)b * m->ws.max_peaks * 2, (size_t)cnt[b] * 8, cudaMemcpyDeviceToHost, h->stream));
+      SB_CUDA(h, cudaMemcpyAsync(out_vals + total, m->ws.peak_vals + (size_t)b * m->ws.max_peaks, (size_t)cnt[b] * 4, cudaMemcpyDeviceToHost, h->stream));
+      for (int i = 0; i < cnt[b]; ++i) out_sample_inds[total + i] = b;
+    }
+    total += cnt[b];
+    if (out_flags) out_flags[b] = fl[b];
+  }
+  SB_CUDA(h, cudaStreamSynchronize(h->stream));
+  *out_n = total;
+  return SB_OK;
+}
+
+}  // extern "C"

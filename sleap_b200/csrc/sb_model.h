@@ -1,0 +1,83 @@
+// Internal model structures (op-list, buffers) shared by sb_model.cu and sb_conv_tc.cu.
+// The int32 record layout must match sleap_b200/nn/oplist.py.
+#pragma once
+#include <vector>
+
+#include "sb_common.cuh"
+
+enum {
+  SB_OPK_BUFFER = 0,
+  SB_OPK_CONV = 1,
+  SB_OPK_TCONV = 2,
+  SB_OPK_POOL = 3,
+  SB_OPK_UPSAMPLE = 4,
+  SB_OPK_ADD = 5,
+  SB_OPK_PREPROCESS = 6,
+  SB_OPK_COPY = 7,
+};
+enum { SB_OPF_RELU = 1, SB_OPF_BN = 2, SB_OPF_BILINEAR = 8 };
+
+struct SbOp {
+  int32_t w[SB_OP_WORDS];
+  int kind() const { return w[0]; }
+  int in_buf() const { return w[1]; }
+  int in_coff() const { return w[2]; }
+  int in_C() const { return w[3]; }
+  int in2_buf() const { return w[4]; }
+  int in2_coff() const { return w[5]; }
+  int out_buf() const { return w[6]; }
+  int out_coff() const { return w[7]; }
+  int out_C() const { return w[8]; }
+  int k() const { return w[9]; }
+  int stride() const { return w[10]; }
+  int flags() const { return w[11]; }
+  int w_off() const { return w[12]; }
+  int b_off() const { return w[13]; }
+  int bn_scale_off() const { return w[14]; }
+  int bn_shift_off() const { return w[15]; }
+  // PREPROCESS: w[16] = float bits of input_scale, w[17] = pad_to_stride
+  float input_scale() const { float f; memcpy(&f, &w[16], 4); return f; }
+  int pad_stride() const { return w[17]; }
+};
+
+struct SbBuffer {
+  int id = 0, stride_den = 1, C = 0, f32 = 0, is_input = 0;
+  int H = 0, W = 0;
+  void* dev = nullptr;
+};
+
+struct SbConvTcPlan;  // sb_conv_tc.cu
+
+struct SbModel {
+  int precision = 0;  // 0: fp16 activations + tensor-core convs; 1: fp32 CUDA-core path
+  std::vector<SbOp> ops;
+  std::vector<SbBuffer> buffers;
+  std::vector<float> weights_host;
+  float* weights_dev = nullptr;
+  void* weights_tc_dev = nullptr;   // fp16 [tap][Cout][Cin] copies for the tensor-core path
+  int64_t n_weights = 0;
+  bool configured = false;
+  int B = 0, Hin = 0, Win = 0, Cin = 0, Hres = 0, Wres = 0, Hnet = 0, Wnet = 0;
+  size_t act_bytes = 0;
+  void* frames_dev = nullptr;
+  std::vector<SbConvTcPlan*> tc_plans;  // per op (nullptr = direct path)
+  // predictors
+  SbPostWs ws;
+  sb_bottomup_params bu{};
+  std::vector<int> bu_edges;
+  bool bu_configured = false;
+  sb_global_params gl{};
+  bool gl_configured = false;
+  float *gpart = nullptr, *gpoints = nullptr, *gvals = nullptr, *crop_off_dev = nullptr;
+  int g_rpc = 1, g_chunks = 1;
+  sb_centroid_params ce{};
+  bool ce_configured = false;
+};
+
+int sb_run_ops(sb_handle_s* h, SbModel* m, const void* frames_dev, int frames_are_u8, int B);
+
+// tensor-core conv path (sb_conv_tc.cu)
+int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m);      // after buffers are allocated
+void sb_conv_tc_release(SbModel* m);
+bool sb_conv_tc_can(const SbModel* m, int op_index);
+int sb_conv_tc_launch(sb_handle_s* h, SbModel* m, int op_index, int B);

@@ -1,0 +1,1020 @@
+// Post-processing kernels of the SLEAP inference path for sm_100a: local / global peak finding
+// with sub-pixel refinement, PAF line scoring, per-edge assignment and greedy instance grouping.
+//
+// Compiled with -fmad=false: the reference computes these quantities in float32 with separately
+// rounded TensorFlow ops, and peak indices / instance assignments must match bit for bit, so no
+// multiply-add may be contracted here.  All of this is HBM/L2-bound scan + gather work.
+//
+// Reference semantics restated per kernel (file:line under /root/reference):
+//   k_local_scan / k_local_emit : sleap/nn/peak_finding.py:249-308 (rough NMS peaks),
+//                                 :451-532 (refinement), :646-707 (learned offsets),
+//                                 :135-190 crop_bboxes, :311-334 integral_regression, :78-132 local
+//                                 sleap/nn/data/instance_cropping.py:58-90,124-166 (bboxes)
+//   k_global_partial / k_global_final : sleap/nn/peak_finding.py:193-246, :337-420, :566-643
+//   k_score_match : sleap/nn/paf_grouping.py:82-142, :145-275, :278-403, :406-550 (scoring),
+//                   :553-670 (matching) + SciPy rectangular LSAP (sleap/nn/utils.py:79-98)
+//   k_group       : sleap/nn/paf_grouping.py:799-914, :917-981, :984-1112
+#include "sb_common.cuh"
+
+#include <math_constants.h>
+
+namespace {
+
+__device__ __forceinline__ float ldf(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ldf(const __half* p) { return __half2float(__ldg(p)); }
+
+// ------------------------------------------------------------------------------------------
+// tf.image.crop_and_resize(bilinear) of a p x p patch centred on integer pixel (px, py) of one
+// channel plane of an NHWC map, followed by integral regression or the local-direction offset.
+// Restates, op for op in f32: make_centered_bboxes -> normalize_bboxes -> crop_and_resize.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__device__ void refine_offset(const T* __restrict__ plane /* &cms[b][0][0][c] */, int H, int W,
+                              int C, float px, float py, int mode, int p, float* dx, float* dy) {
+  const float Hm1 = (float)(H - 1), Wm1 = (float)(W - 1);
+  const float half = (float)(p - 1) * 0.5f;
+  // bbox = (y,x,y,x) + 0.5*(-p+1, -p+1, p-1, p-1); normalised by (H-1, W-1).
+  const float y1 = (py + (float)(-p + 1) * 0.5f) / Hm1;
+  const float x1 = (px + (float)(-p + 1) * 0.5f) / Wm1;
+  const float y2 = (py + (float)(p - 1) * 0.5f) / Hm1;
+  const float x2 = (px + (float)(p - 1) * 0.5f) / Wm1;
+  const float hs = (p > 1) ? ((y2 - y1) * Hm1) / (float)(p - 1) : 0.f;
+  const float wsx = (p > 1) ? ((x2 - x1) * Wm1) / (float)(p - 1) : 0.f;
+  float z = 0.f, sx = 0.f, sy = 0.f;
+  float left = 0.f, right = 0.f, top = 0.f, bottom = 0.f;  // for the 3x3 local mode
+  for (int i = 0; i < p; ++i) {
+    const float in_y = (p > 1) ? (y1 * Hm1 + (float)i * hs) : (0.5f * (y1 + y2) * Hm1);
+    const bool yok = !(in_y < 0.f || in_y > Hm1);
+    int ty = 0, by = 0;
+    float ly = 0.f;
+    if (yok) {
+      ty = (int)floorf(in_y);
+      by = (int)ceilf(in_y);
+      ly = in_y - (float)ty;
+    }
+    for (int j = 0; j < p; ++j) {
+      float v = 0.f;
+      if (yok) {
+        const float in_x = (p > 1) ? (x1 * Wm1 + (float)j * wsx) : (0.5f * (x1 + x2) * Wm1);
+        if (!(in_x < 0.f || in_x > Wm1)) {
+          const int lx = (int)floorf(in_x), rx = (int)ceilf(in_x);
+          const float xl = in_x - (float)lx;
+          const float tl = ldf(plane + ((size_t)ty * W + lx) * C);
+          const float tr = ldf(plane + ((size_t)ty * W + rx) * C);
+          const float bl = ldf(plane + ((size_t)by * W + lx) * C);
+          const float br = ldf(plane + ((size_t)by * W + rx) * C);
+          const float t = tl + (tr - tl) * xl;
+          const float bt = bl + (br - bl) * xl;
+          v = t + (bt - t) * ly;
+        }
+      }
+      if (mode == SB_REFINE_INTEGRAL) {
+        z += v;
+        sx += ((float)j - half) * v;
+        sy += ((float)i - half) * v;
+      } else {
+        if (i == 1 && j == 0) left = v;
+        if (i == 1 && j == 2) right = v;
+        if (i == 0 && j == 1) top = v;
+        if (i == 2 && j == 1) bottom = v;
+      }
+    }
+  }
+  if (mode == SB_REFINE_INTEGRAL) {
+    *dx = sx / z;
+    *dy = sy / z;
+  } else {
+    const float gx = right - left, gy = bottom - top;
+    *dx = (gx > 0.f ? 0.25f : (gx < 0.f ? -0.25f : gx * 0.f));  // sign(x)*0.25 (NaN stays NaN)
+    *dy = (gy > 0.f ? 0.25f : (gy < 0.f ? -0.25f : gy * 0.f));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Local peaks, pass A: one CTA per (row chunk, sample); flat, coalesced walk over the NHWC map;
+// strict 8-neighbour NMS (out-of-image taps skipped, centre-1 tap) + strict threshold; ordered
+// compaction of (flat index, value) into the chunk's list.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_local_scan(const T* __restrict__ cms, int H, int W, int C,
+                                                    int rows_per_chunk, int chunk_cap,
+                                                    float threshold, int* __restrict__ chunk_cnt,
+                                                    uint2* __restrict__ chunk_items) {
+  const int chunk = blockIdx.x, b = blockIdx.y, n_chunks = gridDim.x;
+  const int y0 = chunk * rows_per_chunk;
+  const int y1 = min(H, y0 + rows_per_chunk);
+  const int rowlen = W * C;
+  const T* base = cms + (size_t)b * H * rowlen;
+  const int f0 = y0 * rowlen, f1 = y1 * rowlen;
+  uint2* items = chunk_items + ((size_t)b * n_chunks + chunk) * chunk_cap;
+  __shared__ int warp_tot[8];
+  __shared__ int running;
+  if (threadIdx.x == 0) running = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int fbase = f0; fbase < f1; fbase += 256) {
+    const int f = fbase + threadIdx.x;
+    bool is_peak = false;
+    float v = 0.f;
+    if (f < f1) {
+      v = ldf(base + f);
+      if (v > threshold) {
+        const int y = f / rowlen;
+        const int r = f - y * rowlen;
+        const int x = r / C;
+        float m = v - 1.0f;  // centre tap: v + (-1)
+        const bool up = y > 0, dn = y < H - 1, lf = x > 0, rt = x < W - 1;
+        const T* q = base + f;
+        if (up) {
+          if (lf) m = fmaxf(m, ldf(q - rowlen - C));
+          m = fmaxf(m, ldf(q - rowlen));
+          if (rt) m = fmaxf(m, ldf(q - rowlen + C));
+        }
+        if (lf) m = fmaxf(m, ldf(q - C));
+        if (rt) m = fmaxf(m, ldf(q + C));
+        if (dn) {
+          if (lf) m = fmaxf(m, ldf(q + rowlen - C));
+          m = fmaxf(m, ldf(q + rowlen));
+          if (rt) m = fmaxf(m, ldf(q + rowlen + C));
+        }
+        is_peak = v > m;
+      }
+    }
+    const int any = __syncthreads_count(is_peak);
+    if (any == 0) continue;
+    const unsigned bal = __ballot_sync(0xffffffffu, is_peak);
+    const int rank = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) warp_tot[wid] = __popc(bal);
+    __syncthreads();
+    int off = running;
+    for (int w = 0; w < wid; ++w) off += warp_tot[w];
+    if (is_peak) {
+      const int pos = off + rank;
+      if (pos < chunk_cap) items[pos] = make_uint2((unsigned)f, __float_as_uint(v));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) running += any;
+    // next iteration's first barrier (__syncthreads_count) orders this write before its read
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) chunk_cnt[b * n_chunks + chunk] = running;
+}
+
+// ------------------------------------------------------------------------------------------
+// Local peaks, pass B: one CTA per sample.  Concatenates the chunk lists in order (= tf.where
+// order), refines each peak, scales it, and builds the per-node (channel) ascending peak lists
+// that PAF candidate enumeration needs (stable argsort by channel, paf_grouping.py:106-109).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_local_emit(
+    const T* __restrict__ cms, const float* __restrict__ offsets, int H, int W, int C, int n_chunks,
+    int chunk_cap, int refinement, int patch, float scale, float input_scale, int max_peaks,
+    int max_node_peaks, const int* __restrict__ chunk_cnt, const uint2* __restrict__ chunk_items,
+    float* __restrict__ peaks, float* __restrict__ peak_vals, int* __restrict__ peak_ch,
+    int* __restrict__ n_peaks, int* __restrict__ total_peaks, int* __restrict__ node_cnt,
+    int* __restrict__ node_peaks, int* __restrict__ flags) {
+  extern __shared__ int s_prefix[];  // n_chunks + 1
+  const int b = blockIdx.x;
+  __shared__ int warp_tot[8];
+  __shared__ int running;
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int k = 0; k < n_chunks; ++k) {
+      s_prefix[k] = acc;
+      acc += min(chunk_cnt[b * n_chunks + k], chunk_cap);
+    }
+    s_prefix[n_chunks] = acc;
+  }
+  __syncthreads();
+  const int total = s_prefix[n_chunks];
+  const int n = min(total, max_peaks);
+  int flag = (total > max_peaks) ? SB_FLAG_PEAKS_TRUNCATED : 0;
+  const int rowlen = W * C;
+  const T* base = cms + (size_t)b * H * rowlen;
+  float* pk = peaks + (size_t)b * max_peaks * 2;
+  float* pv = peak_vals + (size_t)b * max_peaks;
+  int* pc = peak_ch + (size_t)b * max_peaks;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    int lo = 0, hi = n_chunks - 1;  // largest k with prefix[k] <= i
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (s_prefix[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    const uint2 it = chunk_items[((size_t)b * n_chunks + lo) * chunk_cap + (i - s_prefix[lo])];
+    const int f = (int)it.x;
+    const int y = f / rowlen;
+    const int r = f - y * rowlen;
+    const int x = r / C;
+    const int c = r - x * C;
+    float fx = (float)x, fy = (float)y;
+    if (offsets != nullptr) {
+      // learned offsets (B,H,W,C,2): refined = rough + offsets[b, y, x, c, :]
+      const float* o = offsets + (((size_t)b * H + y) * W + x) * (size_t)(2 * C) + 2 * c;
+      fx = fx + o[0];
+      fy = fy + o[1];
+    } else if (refinement != SB_REFINE_NONE) {
+      float dx, dy;
+      refine_offset<T>(base + c, H, W, C, fx, fy, refinement,
+                       refinement == SB_REFINE_INTEGRAL ? patch : 3, &dx, &dy);
+      fx = fx + dx;
+      fy = fy + dy;
+    }
+    fx = fx * scale;
+    fy = fy * scale;
+    if (input_scale != 1.0f) {  // CentroidCrop: /input_scale + 0.5 (inference.py:1828-1833)
+      fx = fx / input_scale + 0.5f;
+      fy = fy / input_scale + 0.5f;
+    }
+    pk[2 * i] = fx;
+    pk[2 * i + 1] = fy;
+    pv[i] = __uint_as_float(it.y);
+    pc[i] = c;
+  }
+  __syncthreads();  // peak_ch written by this CTA is visible to it
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (node_cnt != nullptr) {
+    for (int c = 0; c < C; ++c) {
+      if (threadIdx.x == 0) running = 0;
+      __syncthreads();
+      int* lst = node_peaks + ((size_t)b * C + c) * max_node_peaks;
+      for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        const bool hit = (i < n) && (pc[i] == c);
+        const int any = __syncthreads_count(hit);
+        if (any == 0) continue;
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        const int rank = __popc(bal & ((1u << lane) - 1u));
+        if (lane == 0) warp_tot[wid] = __popc(bal);
+        __syncthreads();
+        int off = running;
+        for (int w = 0; w < wid; ++w) off += warp_tot[w];
+        if (hit && off + rank < max_node_peaks) lst[off + rank] = i;
+        __syncthreads();
+        if (threadIdx.x == 0) running += any;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        node_cnt[b * C + c] = running;
+        if (running > max_node_peaks) flag |= SB_FLAG_NODE_PEAKS_TRUNCATED;
+      }
+    }
+  }
+  if (threadIdx.x == 0) {
+    n_peaks[b] = n;
+    total_peaks[b] = total;
+    flags[b] = flag;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Global peaks.  argmax_y(max_x) / argmax_x(max_y) with first-index ties == (first row, first
+// column) that contain the global maximum, so one lexicographic (max, min y, min x) reduction.
+// Pass 1: CTA per (row chunk, sample); each thread owns one channel (stride multiple of C) and
+// walks the chunk coalesced.  Pass 2: CTA per sample finishes, thresholds, refines, fixes up.
+// ------------------------------------------------------------------------------------------
+struct GMax {
+  float v;
+  int y, x;
+};
+__device__ __forceinline__ void gmax_merge(GMax& a, float v, int y, int x) {
+  if (v > a.v) {
+    a.v = v; a.y = y; a.x = x;
+  } else if (v == a.v) {
+    a.y = min(a.y, y);
+    a.x = min(a.x, x);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_global_partial(const T* __restrict__ cms, int H, int W,
+                                                        int C, int rows_per_chunk,
+                                                        float* __restrict__ part /*[B][chunks][C][3]*/) {
+  const int chunk = blockIdx.x, b = blockIdx.y, n_chunks = gridDim.x;
+  const int y0 = chunk * rows_per_chunk, y1 = min(H, y0 + rows_per_chunk);
+  const int rowlen = W * C;
+  const T* base = cms + (size_t)b * H * rowlen;
+  const int per = max(1, 256 / C);           // pixels handled per sweep
+  const int active = per * C;                // threads that own a (pixel slot, channel)
+  extern __shared__ float s_red[];           // [active][3]
+  GMax g;
+  g.v = -CUDART_INF_F; g.y = 0x7fffffff; g.x = 0x7fffffff;
+  if (threadIdx.x < active && C <= 256) {
+    const int c = threadIdx.x % C;
+    const int f0 = y0 * rowlen, f1 = y1 * rowlen;
+    for (int f = f0 + threadIdx.x; f < f1; f += active) {
+      const float v = ldf(base + f);
+      const int y = f / rowlen;
+      const int x = (f - y * rowlen) / C;
+      gmax_merge(g, v, y, x);
+      (void)c;
+    }
+    s_red[threadIdx.x * 3 + 0] = g.v;
+    s_red[threadIdx.x * 3 + 1] = __int_as_float(g.y);
+    s_red[threadIdx.x * 3 + 2] = __int_as_float(g.x);
+  }
+  __syncthreads();
+  if (threadIdx.x < C && C <= 256) {
+    GMax a;
+    a.v = -CUDART_INF_F; a.y = 0x7fffffff; a.x = 0x7fffffff;
+    for (int s = 0; s < per; ++s) {
+      const int t = s * C + threadIdx.x;
+      gmax_merge(a, s_red[t * 3], __float_as_int(s_red[t * 3 + 1]), __float_as_int(s_red[t * 3 + 2]));
+    }
+    float* o = part + (((size_t)b * n_chunks + chunk) * C + threadIdx.x) * 3;
+    o[0] = a.v; o[1] = __int_as_float(a.y); o[2] = __int_as_float(a.x);
+  }
+}
+
+struct GlobalFix {
+  float scale;        // output stride
+  float input_scale;  // != 1 -> /input_scale + 0.5
+  int has_crop_off;   // + crop_offsets[b] / input_scale
+};
+
+template <typename T>
+__global__ void k_global_final(const T* __restrict__ cms, const float* __restrict__ offsets, int H,
+                               int W, int C, int n_chunks, const float* __restrict__ part,
+                               float threshold, int refinement, int patch, GlobalFix fix,
+                               const float* __restrict__ crop_off, float* __restrict__ out_points,
+                               float* __restrict__ out_vals) {
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    GMax a;
+    a.v = -CUDART_INF_F; a.y = 0x7fffffff; a.x = 0x7fffffff;
+    for (int k = 0; k < n_chunks; ++k) {
+      const float* o = part + (((size_t)b * n_chunks + k) * C + c) * 3;
+      gmax_merge(a, o[0], __float_as_int(o[1]), __float_as_int(o[2]));
+    }
+    const int row = min(max(a.y, 0), H - 1), col = min(max(a.x, 0), W - 1);
+    const T* plane = cms + (size_t)b * H * W * C + c;
+    const float val = ldf(plane + ((size_t)row * W + col) * C);
+    float fx = (float)col, fy = (float)row;
+    if (val < threshold) {
+      fx = CUDART_NAN_F; fy = CUDART_NAN_F;
+    } else {
+      if (offsets != nullptr) {
+        const float* o = offsets + (((size_t)b * H + row) * W + col) * (size_t)(2 * C) + 2 * c;
+        fx = fx + o[0]; fy = fy + o[1];
+      } else if (refinement != SB_REFINE_NONE) {
+        float dx, dy;
+        refine_offset<T>(plane, H, W, C, fx, fy, refinement,
+                         refinement == SB_REFINE_INTEGRAL ? patch : 3, &dx, &dy);
+        fx = fx + dx; fy = fy + dy;
+      }
+      fx = fx * fix.scale; fy = fy * fix.scale;
+      if (fix.input_scale != 1.0f) {
+        fx = fx / fix.input_scale + 0.5f; fy = fy / fix.input_scale + 0.5f;
+      }
+      if (fix.has_crop_off) {
+        fx = fx + crop_off[2 * b] / fix.input_scale;
+        fy = fy + crop_off[2 * b + 1] / fix.input_scale;
+      }
+    }
+    out_points[((size_t)b * C + c) * 2] = fx;
+    out_points[((size_t)b * C + c) * 2 + 1] = fy;
+    out_vals[(size_t)b * C + c] = val;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// SciPy rectangular linear-sum-assignment (Crouse's shortest augmenting path), restated for one
+// thread.  score(i,j) -> cost = isnan ? +inf : -score, in double as SciPy does.
+// Returns number of assignments (0 when infeasible); rows ascending.
+// ------------------------------------------------------------------------------------------
+struct LsapScratch {
+  double* u; double* v; double* spc;
+  int* path; int* col4row; int* row4col; int* remaining;
+  unsigned char* SR; unsigned char* SC;
+};
+
+__device__ int lsap_solve(const float* __restrict__ scores, int n_src, int n_dst, LsapScratch s,
+                          int* out_rows, int* out_cols) {
+  if (n_src == 0 || n_dst == 0) return 0;
+  const bool transpose = n_dst < n_src;
+  const int nr = transpose ? n_dst : n_src, nc = transpose ? n_src : n_dst;
+  auto cost = [&](int i, int j) -> double {
+    const float sc = transpose ? scores[j * n_dst + i] : scores[i * n_dst + j];
+    return (sc != sc) ? (double)CUDART_INF_F : -(double)sc;
+  };
+  for (int i = 0; i < nr; ++i)
+    for (int j = 0; j < nc; ++j)
+      if (cost(i, j) == -(double)CUDART_INF_F) return 0;  // SciPy: invalid (-inf) entries raise
+  for (int i = 0; i < nr; ++i) { s.u[i] = 0.0; s.col4row[i] = -1; }
+  for (int j = 0; j < nc; ++j) { s.v[j] = 0.0; s.path[j] = -1; s.row4col[j] = -1; }
+  for (int cur = 0; cur < nr; ++cur) {
+    double minVal = 0.0;
+    int i = cur;
+    int num_remaining = nc;
+    for (int it = 0; it < nc; ++it) s.remaining[it] = nc - it - 1;
+    for (int k = 0; k < nr; ++k) s.SR[k] = 0;
+    for (int k = 0; k < nc; ++k) { s.SC[k] = 0; s.spc[k] = (double)CUDART_INF_F; }
+    int sink = -1;
+    while (sink == -1) {
+      int index = -1;
+      double lowest = (double)CUDART_INF_F;
+      s.SR[i] = 1;
+      for (int it = 0; it < num_remaining; ++it) {
+        const int j = s.remaining[it];
+        const double r = minVal + cost(i, j) - s.u[i] - s.v[j];
+        if (r < s.spc[j]) { s.path[j] = i; s.spc[j] = r; }
+        if (s.spc[j] < lowest || (s.spc[j] == lowest && s.row4col[j] == -1)) {
+          lowest = s.spc[j];
+          index = it;
+        }
+      }
+      minVal = lowest;
+      if (minVal == (double)CUDART_INF_F) return 0;  // infeasible
+      const int j = s.remaining[index];
+      if (s.row4col[j] == -1) sink = j; else i = s.row4col[j];
+      s.SC[j] = 1;
+      s.remaining[index] = s.remaining[--num_remaining];
+    }
+    s.u[cur] += minVal;
+    for (int k = 0; k < nr; ++k)
+      if (s.SR[k] && k != cur) s.u[k] += minVal - s.spc[s.col4row[k]];
+    for (int k = 0; k < nc; ++k)
+      if (s.SC[k]) s.v[k] -= minVal - s.spc[k];
+    int j = sink;
+    while (true) {
+      const int ii = s.path[j];
+      s.row4col[j] = ii;
+      const int tmp = s.col4row[ii];
+      s.col4row[ii] = j;
+      j = tmp;
+      if (ii == cur) break;
+    }
+  }
+  if (!transpose) {
+    for (int i = 0; i < nr; ++i) { out_rows[i] = i; out_cols[i] = s.col4row[i]; }
+  } else {
+    // rows of the transposed problem are dst; emit sorted by src (= col4row value), stable
+    // argsort by insertion (values are distinct).
+    int cnt = 0;
+    for (int srci = 0; srci < nc; ++srci) {
+      const int d = s.row4col[srci];
+      if (d >= 0) { out_rows[cnt] = srci; out_cols[cnt] = d; ++cnt; }
+    }
+  }
+  return nr;
+}
+
+__device__ __forceinline__ LsapScratch carve_lsap(unsigned char* raw, int K) {
+  LsapScratch s;
+  double* d = reinterpret_cast<double*>(raw);
+  s.u = d; s.v = d + K; s.spc = d + 2 * K;
+  int* ip = reinterpret_cast<int*>(d + 3 * K);
+  s.path = ip; s.col4row = ip + K; s.row4col = ip + 2 * K; s.remaining = ip + 3 * K;
+  s.SR = reinterpret_cast<unsigned char*>(ip + 4 * K);
+  s.SC = s.SR + K;
+  return s;
+}
+__host__ __device__ inline size_t lsap_scratch_bytes(int K) {
+  return (size_t)K * (3 * sizeof(double) + 4 * sizeof(int) + 2) + 16;
+}
+
+// ------------------------------------------------------------------------------------------
+// PAF line scoring + matching: one CTA per (edge, sample).  One warp per candidate pair, lanes
+// over the line points (warp-shuffle reduction of the dot products); then thread 0 solves the
+// assignment for this edge.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_score_match(
+    const float* __restrict__ pafs, int Hp, int Wp, int C2, int C, int K, int max_peaks,
+    const int* __restrict__ edges, const float* __restrict__ peaks, const int* __restrict__ node_cnt,
+    const int* __restrict__ node_peaks, int n_points, float pafs_stride, float max_edge_length,
+    float dist_w, float* __restrict__ score_mat, int* __restrict__ match_cnt,
+    int* __restrict__ match_src, int* __restrict__ match_dst, float* __restrict__ match_score) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int e = blockIdx.x, b = blockIdx.y, E = gridDim.x;
+  const int src_node = edges[2 * e], dst_node = edges[2 * e + 1];
+  const int ns = min(node_cnt[b * C + src_node], K), nd = min(node_cnt[b * C + dst_node], K);
+  float* s_scores = reinterpret_cast<float*>(smem_raw);                 // K*K
+  unsigned char* s_lsap = smem_raw + (size_t)K * K * sizeof(float);
+  const int* src_list = node_peaks + ((size_t)b * C + src_node) * K;
+  const int* dst_list = node_peaks + ((size_t)b * C + dst_node) * K;
+  const float* pk = peaks + (size_t)b * max_peaks * 2;
+  const float* paf_b = pafs + (size_t)b * Hp * Wp * C2;
+  float* gmat = score_mat + ((size_t)b * E + e) * K * K;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int p = wid; p < ns * nd; p += nw) {
+    const int i = p / nd, j = p - i * nd;
+    const int si = src_list[i], di = dst_list[j];
+    const float sx = pk[2 * si], sy = pk[2 * si + 1];
+    const float dx = pk[2 * di], dy = pk[2 * di + 1];
+    const float vx = dx - sx, vy = dy - sy;
+    const float len = sqrtf(vx * vx + vy * vy);
+    const float ux = vx / len, uy = vy / len;
+    const float stepx = (n_points > 1) ? (dx - sx) / (float)(n_points - 1) : 0.f;
+    const float stepy = (n_points > 1) ? (dy - sy) / (float)(n_points - 1) : 0.f;
+    float acc = 0.f;
+    for (int q = lane; q < n_points; q += 32) {
+      float X, Y;
+      if (q == n_points - 1 && n_points > 1) { X = dx; Y = dy; }
+      else { X = sx + stepx * (float)q; Y = sy + stepy * (float)q; }
+      const int col = (int)rintf(X / pafs_stride);   // tf.round: half to even
+      const int row = (int)rintf(Y / pafs_stride);
+      float px = 0.f, py = 0.f;
+      if (row >= 0 && row < Hp && col >= 0 && col < Wp) {
+        const float2 pv = *reinterpret_cast<const float2*>(paf_b + ((size_t)row * Wp + col) * C2 + 2 * e);
+        px = pv.x; py = pv.y;
+      }
+      acc += px * ux + py * uy;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      const float mean = acc / (float)n_points;
+      const float pen = fminf(max_edge_length / len - 1.0f, 0.f) * dist_w;
+      const float sc = mean + pen;
+      s_scores[p] = sc;
+      gmat[p] = sc;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    LsapScratch s = carve_lsap(s_lsap, K);
+    int* rows = match_src + ((size_t)b * E + e) * K;
+    int* cols = match_dst + ((size_t)b * E + e) * K;
+    const int n = lsap_solve(s_scores, ns, nd, s, rows, cols);
+    float* ms = match_score + ((size_t)b * E + e) * K;
+    for (int k = 0; k < n; ++k) ms[k] = s_scores[rows[k] * nd + cols[k]];
+    match_cnt[b * E + e] = n;
+  }
+}
+
+// Generic batched LSAP (stage-level API): one CTA (thread 0) per problem.
+__global__ void k_lsap_batch(const float* __restrict__ scores, const int* __restrict__ n_src,
+                             const int* __restrict__ n_dst, const int* __restrict__ offsets, int K,
+                             int* __restrict__ out_rows, int* __restrict__ out_cols,
+                             float* __restrict__ out_scores, int* __restrict__ out_counts) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int p = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  LsapScratch s = carve_lsap(smem_raw, K);
+  const int ns = n_src[p], nd = n_dst[p];
+  const float* sc = scores + offsets[p];
+  int n = 0;
+  if (ns <= K && nd <= K) n = lsap_solve(sc, ns, nd, s, out_rows + (size_t)p * K, out_cols + (size_t)p * K);
+  for (int k = 0; k < n; ++k)
+    out_scores[(size_t)p * K + k] = sc[out_rows[(size_t)p * K + k] * nd + out_cols[(size_t)p * K + k]];
+  out_counts[p] = n;
+}
+
+// ------------------------------------------------------------------------------------------
+// Greedy instance grouping: one CTA per sample; thread 0 replays the reference's sequential
+// dict algorithm on an array (node, local peak) -> instance id; the CTA fills outputs.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_group(
+    int C, int E, int K, int max_peaks, int max_inst, const int* __restrict__ edges,
+    const int* __restrict__ sorted_edges, int n_sorted, const float* __restrict__ peaks,
+    const float* __restrict__ peak_vals, const int* __restrict__ node_cnt,
+    const int* __restrict__ node_peaks, const int* __restrict__ match_cnt,
+    const int* __restrict__ match_src, const int* __restrict__ match_dst,
+    const float* __restrict__ match_score, int min_instance_peaks, float min_line_scores,
+    float input_scale, float* __restrict__ inst_peaks, float* __restrict__ inst_vals,
+    float* __restrict__ inst_scores, int* __restrict__ n_inst, int* __restrict__ flags) {
+  extern __shared__ int s_assign[];  // [C*K] instance id or -1; then [C*K] rank map scratch
+  const int b = blockIdx.x;
+  int* assign = s_assign;
+  int* idrank = s_assign + C * K;    // instance id -> rank (ids < C*K)
+  __shared__ int s_ninst;
+  for (int t = threadIdx.x; t < C * K; t += blockDim.x) { assign[t] = -1; idrank[t] = -1; }
+  float* op = inst_peaks + (size_t)b * max_inst * C * 2;
+  float* ov = inst_vals + (size_t)b * max_inst * C;
+  float* os = inst_scores + (size_t)b * max_inst;
+  for (int t = threadIdx.x; t < max_inst * C * 2; t += blockDim.x) op[t] = CUDART_NAN_F;
+  for (int t = threadIdx.x; t < max_inst * C; t += blockDim.x) ov[t] = CUDART_NAN_F;
+  for (int t = threadIdx.x; t < max_inst; t += blockDim.x) os[t] = CUDART_NAN_F;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int n_slots = C * K;
+    for (int se = 0; se < n_sorted; ++se) {
+      const int e = sorted_edges[se];
+      const int sn = edges[2 * e], dn = edges[2 * e + 1];
+      const int cnt = match_cnt[b * E + e];
+      const size_t mo = ((size_t)b * E + e) * K;
+      for (int m = 0; m < cnt; ++m) {
+        if (!(match_score[mo + m] >= min_line_scores)) continue;
+        const int sid = sn * K + match_src[mo + m], did = dn * K + match_dst[mo + m];
+        const int si = assign[sid], di = assign[did];
+        if (si < 0 && di < 0) {
+          int mx = -1;
+          for (int t = 0; t < n_slots; ++t) mx = max(mx, assign[t]);
+          assign[sid] = mx + 1;
+          assign[did] = mx + 1;
+        } else if (si >= 0 && di < 0) {
+          assign[did] = si;
+        } else if (si >= 0 && di >= 0) {
+          assign[did] = si;
+          // node-type sets of both instances AFTER the re-assignment of dst
+          bool share = false;
+          for (int node = 0; node < C && !share; ++node) {
+            bool in_s = false, in_d = false;
+            for (int k = 0; k < K; ++k) {
+              const int a = assign[node * K + k];
+              in_s |= (a == si);
+              in_d |= (a == di);
+            }
+            share = in_s && in_d;
+          }
+          if (!share)
+            for (int t = 0; t < n_slots; ++t)
+              if (assign[t] == di) assign[t] = si;
+        }
+      }
+    }
+    if (min_instance_peaks > 0) {
+      // instance ids are < n_slots; count peaks per id in idrank (reused as counter)
+      for (int t = 0; t < n_slots; ++t) idrank[t] = 0;
+      for (int t = 0; t < n_slots; ++t) if (assign[t] >= 0) idrank[assign[t]]++;
+      for (int t = 0; t < n_slots; ++t)
+        if (assign[t] >= 0 && idrank[assign[t]] < min_instance_peaks) assign[t] = -2;  // removed
+      for (int t = 0; t < n_slots; ++t) { if (assign[t] == -2) assign[t] = -1; }
+      for (int t = 0; t < n_slots; ++t) idrank[t] = -1;
+    }
+    // np.unique(return_inverse): rank of each id among the sorted unique ids
+    for (int t = 0; t < n_slots; ++t) if (assign[t] >= 0) idrank[assign[t]] = 0;
+    int r = 0;
+    for (int t = 0; t < n_slots; ++t) if (idrank[t] == 0) idrank[t] = r++;
+    s_ninst = r;
+    int fl = 0;
+    if (r > max_inst) fl = SB_FLAG_INSTANCES_TRUNCATED;
+    const int keep = min(r, max_inst);
+    for (int t = 0; t < keep; ++t) os[t] = 0.f;
+    for (int se = 0; se < n_sorted; ++se) {
+      const int e = sorted_edges[se];
+      const int sn = edges[2 * e];
+      const int cnt = match_cnt[b * E + e];
+      const size_t mo = ((size_t)b * E + e) * K;
+      for (int m = 0; m < cnt; ++m) {
+        const float sc = match_score[mo + m];
+        if (!(sc >= min_line_scores)) continue;
+        const int a = assign[sn * K + match_src[mo + m]];
+        if (a >= 0) {
+          const int rk = idrank[a];
+          if (rk < keep) os[rk] = os[rk] + sc;
+        }
+      }
+    }
+    n_inst[b] = keep;
+    if (fl) flags[b] |= fl;
+  }
+  __syncthreads();
+  const int keep = min(s_ninst, max_inst);
+  const float* pk = peaks + (size_t)b * max_peaks * 2;
+  const float* pv = peak_vals + (size_t)b * max_peaks;
+  for (int t = threadIdx.x; t < C * K; t += blockDim.x) {
+    const int a = assign[t];
+    if (a < 0) continue;
+    const int rk = idrank[a];
+    if (rk >= keep) continue;
+    const int node = t / K, k = t - node * K;
+    if (k >= min(node_cnt[b * C + node], K)) continue;
+    const int pi = node_peaks[((size_t)b * C + node) * K + k];
+    float x = pk[2 * pi], y = pk[2 * pi + 1];
+    if (input_scale != 1.0f) {  // inference.py:2980-2984
+      x = x / input_scale + 0.5f;
+      y = y / input_scale + 0.5f;
+    }
+    op[((size_t)rk * C + node) * 2] = x;
+    op[((size_t)rk * C + node) * 2 + 1] = y;
+    ov[(size_t)rk * C + node] = pv[pi];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Centred bilinear crops (top-down): crop_bboxes(make_centered_bboxes(centroid, h, w)).
+// ------------------------------------------------------------------------------------------
+template <typename TI, typename TO, bool TRUNC_U8>
+__global__ void k_crop(const TI* __restrict__ images, int H, int W, int C,
+                       const float* __restrict__ centroids, const int* __restrict__ sample_inds,
+                       int crop_h, int crop_w, TO* __restrict__ out) {
+  const int n = blockIdx.y;
+  const float cx = centroids[2 * n], cy = centroids[2 * n + 1];
+  const int b = sample_inds[n];
+  const float Hm1 = (float)(H - 1), Wm1 = (float)(W - 1);
+  const float y1 = (cy + (float)(-crop_h + 1) * 0.5f) / Hm1;
+  const float x1 = (cx + (float)(-crop_w + 1) * 0.5f) / Wm1;
+  const float y2 = (cy + (float)(crop_h - 1) * 0.5f) / Hm1;
+  const float x2 = (cx + (float)(crop_w - 1) * 0.5f) / Wm1;
+  const float hs = (crop_h > 1) ? ((y2 - y1) * Hm1) / (float)(crop_h - 1) : 0.f;
+  const float wsx = (crop_w > 1) ? ((x2 - x1) * Wm1) / (float)(crop_w - 1) : 0.f;
+  const TI* img = images + (size_t)b * H * W * C;
+  const int total = crop_h * crop_w * C;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int c = t % C;
+    const int j = (t / C) % crop_w;
+    const int i = t / (C * crop_w);
+    const float in_y = (crop_h > 1) ? (y1 * Hm1 + (float)i * hs) : (0.5f * (y1 + y2) * Hm1);
+    const float in_x = (crop_w > 1) ? (x1 * Wm1 + (float)j * wsx) : (0.5f * (x1 + x2) * Wm1);
+    float v = 0.f;
+    if (!(in_y < 0.f || in_y > Hm1) && !(in_x < 0.f || in_x > Wm1)) {
+      const int ty = (int)floorf(in_y), by = (int)ceilf(in_y);
+      const int lx = (int)floorf(in_x), rx = (int)ceilf(in_x);
+      const float ly = in_y - (float)ty, xl = in_x - (float)lx;
+      const float tl = (float)img[((size_t)ty * W + lx) * C + c];
+      const float tr = (float)img[((size_t)ty * W + rx) * C + c];
+      const float bl = (float)img[((size_t)by * W + lx) * C + c];
+      const float br = (float)img[((size_t)by * W + rx) * C + c];
+      const float tp = tl + (tr - tl) * xl;
+      const float bt = bl + (br - bl) * xl;
+      v = tp + (bt - tp) * ly;
+    }
+    if (TRUNC_U8) out[(size_t)n * total + t] = (TO)(unsigned char)truncf(fminf(fmaxf(v, 0.f), 255.f));
+    else out[(size_t)n * total + t] = (TO)v;
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Function-level helpers kept for the reference's unit-test surface:
+//   k_lines     : make_line_subs + get_paf_lines + score_paf_lines for explicit candidate lists
+//                 (paf_grouping.py:145-222, :225-275, :325-403); one warp per candidate.
+//   k_integral  : integral_regression (peak_finding.py:311-334); one warp per (sample, channel).
+//   k_local_dir : find_offsets_local_direction (peak_finding.py:78-132).
+// ------------------------------------------------------------------------------------------
+__global__ void k_lines(const float* __restrict__ pafs /*(Hp,Wp,C2) or null*/, int Hp, int Wp, int C2,
+                        const float* __restrict__ lines_in /*(n,P,2) or null*/,
+                        const float* __restrict__ peaks, const int* __restrict__ edge_peak_inds,
+                        const int* __restrict__ edge_inds, int n, int P, float pafs_stride,
+                        float max_edge_length, float dist_w, int* __restrict__ out_subs /*(n,P,2)*/,
+                        float* __restrict__ out_lines /*(n,P,2)*/, float* __restrict__ out_scores) {
+  const int lane = threadIdx.x & 31;
+  const int cand = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (cand >= n) return;
+  const int si = edge_peak_inds[2 * cand], di = edge_peak_inds[2 * cand + 1];
+  const int e = edge_inds ? edge_inds[cand] : 0;
+  const float sx = peaks[2 * si], sy = peaks[2 * si + 1];
+  const float dx = peaks[2 * di], dy = peaks[2 * di + 1];
+  const float vx = dx - sx, vy = dy - sy;
+  const float len = sqrtf(vx * vx + vy * vy);
+  const float ux = vx / len, uy = vy / len;
+  const float stepx = (P > 1) ? (dx - sx) / (float)(P - 1) : 0.f;
+  const float stepy = (P > 1) ? (dy - sy) / (float)(P - 1) : 0.f;
+  float acc = 0.f;
+  for (int q = lane; q < P; q += 32) {
+    float px = 0.f, py = 0.f;
+    if (lines_in != nullptr) {
+      px = lines_in[((size_t)cand * P + q) * 2];
+      py = lines_in[((size_t)cand * P + q) * 2 + 1];
+    } else {
+      float X, Y;
+      if (q == P - 1 && P > 1) { X = dx; Y = dy; }
+      else { X = sx + stepx * (float)q; Y = sy + stepy * (float)q; }
+      const int col = (int)rintf(X / pafs_stride);
+      const int row = (int)rintf(Y / pafs_stride);
+      if (out_subs) {
+        out_subs[((size_t)cand * P + q) * 2] = row;
+        out_subs[((size_t)cand * P + q) * 2 + 1] = col;
+      }
+      if (pafs != nullptr && row >= 0 && row < Hp && col >= 0 && col < Wp && 2 * e + 1 < C2) {
+        px = pafs[((size_t)row * Wp + col) * C2 + 2 * e];
+        py = pafs[((size_t)row * Wp + col) * C2 + 2 * e + 1];
+      }
+    }
+    if (out_lines) {
+      out_lines[((size_t)cand * P + q) * 2] = px;
+      out_lines[((size_t)cand * P + q) * 2 + 1] = py;
+    }
+    acc += px * ux + py * uy;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0 && out_scores) {
+    const float mean = acc / (float)P;
+    const float pen = fminf(max_edge_length / len - 1.0f, 0.f) * dist_w;
+    out_scores[cand] = mean + pen;
+  }
+}
+
+__global__ void k_integral(const float* __restrict__ cms, int N, int Hh, int Ww, int C,
+                           const float* __restrict__ xv, const float* __restrict__ yv,
+                           float* __restrict__ x_hat, float* __restrict__ y_hat) {
+  const int lane = threadIdx.x & 31;
+  const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (item >= N * C) return;
+  const int nidx = item / C, c = item - nidx * C;
+  const float* base = cms + (size_t)nidx * Hh * Ww * C + c;
+  float z = 0.f, sx = 0.f, sy = 0.f;
+  for (int t = lane; t < Hh * Ww; t += 32) {
+    const int i = t / Ww, j = t - i * Ww;
+    const float v = base[(size_t)t * C];
+    z += v; sx += xv[j] * v; sy += yv[i] * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    z += __shfl_xor_sync(0xffffffffu, z, o);
+    sx += __shfl_xor_sync(0xffffffffu, sx, o);
+    sy += __shfl_xor_sync(0xffffffffu, sy, o);
+  }
+  if (lane == 0) { x_hat[item] = sx / z; y_hat[item] = sy / z; }
+}
+
+__global__ void k_local_dir(const float* __restrict__ patches /*(N,3,3,1)*/, int N, float delta,
+                            float* __restrict__ out /*(N,2)*/) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float* p = patches + (size_t)i * 9;
+  const float gx = p[5] - p[3], gy = p[7] - p[1];
+  out[2 * i] = (gx > 0.f ? 1.f : (gx < 0.f ? -1.f : gx * 0.f)) * delta;
+  out[2 * i + 1] = (gy > 0.f ? 1.f : (gy < 0.f ? -1.f : gy * 0.f)) * delta;
+}
+
+}  // namespace
+
+// =================================== host launchers =========================================
+
+int sb_post_ws_alloc(sb_handle_s* h, SbPostWs& ws, int B, int H, int W, int C, int max_peaks,
+                     int max_node_peaks, int max_instances, int n_edges) {
+  ws.B = B; ws.H = H; ws.W = W; ws.C = C;
+  ws.max_peaks = max_peaks; ws.max_node_peaks = max_node_peaks; ws.max_instances = max_instances;
+  ws.n_edges = n_edges;
+  int target_chunks = (2 * h->sm_count + B - 1) / B;          // >= 2 CTAs per SM over the batch
+  int rpc = (H + target_chunks - 1) / target_chunks;
+  if (rpc < 1) rpc = 1;
+  while ((long long)rpc * W * C > 65536 && rpc > 1) rpc = (rpc + 1) / 2;
+  ws.rows_per_chunk = rpc;
+  ws.n_chunks = (H + rpc - 1) / rpc;
+  ws.chunk_cap = ((rpc + 1) / 2) * ((W + 1) / 2) * C;
+  const int E = n_edges > 0 ? n_edges : 1, K = max_node_peaks > 0 ? max_node_peaks : 1;
+  int rc = 0;
+#define A(ptr, n) do { if ((rc = sb_dev_alloc(h, &ptr, (size_t)(n))) != 0) return rc; ws.bytes += sizeof(*ptr) * (size_t)(n); } while (0)
+  A(ws.chunk_cnt, (size_t)B * ws.n_chunks);
+  A(ws.chunk_items, (size_t)B * ws.n_chunks * ws.chunk_cap);
+  A(ws.peaks, (size_t)B * max_peaks * 2);
+  A(ws.peak_vals, (size_t)B * max_peaks);
+  A(ws.peak_ch, (size_t)B * max_peaks);
+  A(ws.n_peaks, B); A(ws.total_peaks, B); A(ws.flags, B);
+  A(ws.node_cnt, (size_t)B * C);
+  A(ws.node_peaks, (size_t)B * C * K);
+  if (n_edges > 0) {
+    A(ws.score_mat, (size_t)B * E * K * K);
+    A(ws.match_cnt, (size_t)B * E);
+    A(ws.match_src, (size_t)B * E * K);
+    A(ws.match_dst, (size_t)B * E * K);
+    A(ws.match_score, (size_t)B * E * K);
+    A(ws.inst_peaks, (size_t)B * max_instances * C * 2);
+    A(ws.inst_vals, (size_t)B * max_instances * C);
+    A(ws.inst_scores, (size_t)B * max_instances);
+    A(ws.n_inst, B);
+    A(ws.edges_dev, (size_t)E * 2);
+    A(ws.sorted_edges_dev, (size_t)E);
+  }
+#undef A
+  return 0;
+}
+
+void sb_post_ws_free(SbPostWs& ws) {
+  void* ptrs[] = {ws.chunk_cnt, ws.chunk_items, ws.peaks, ws.peak_vals, ws.peak_ch, ws.n_peaks,
+                  ws.total_peaks, ws.flags, ws.node_cnt, ws.node_peaks, ws.score_mat, ws.match_cnt,
+                  ws.match_src, ws.match_dst, ws.match_score, ws.inst_peaks, ws.inst_vals,
+                  ws.inst_scores, ws.n_inst, ws.edges_dev, ws.sorted_edges_dev};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  ws = SbPostWs();
+}
+
+int sbk_local_peaks(sb_handle_s* h, const void* cms, int cms_is_half, const float* offsets, int B,
+                    int H, int W, int C, const SbPeakParams& p, SbPostWs& ws) {
+  if (B > ws.B || H != ws.H || W != ws.W || C != ws.C)
+    return sb_fail(h, SB_ERR_INVALID, "local peaks: workspace shape mismatch");
+  dim3 g(ws.n_chunks, B);
+  if (cms_is_half)
+    k_local_scan<__half><<<g, 256, 0, h->stream>>>((const __half*)cms, H, W, C, ws.rows_per_chunk,
+                                                   ws.chunk_cap, p.threshold, ws.chunk_cnt, ws.chunk_items);
+  else
+    k_local_scan<float><<<g, 256, 0, h->stream>>>((const float*)cms, H, W, C, ws.rows_per_chunk,
+                                                  ws.chunk_cap, p.threshold, ws.chunk_cnt, ws.chunk_items);
+  SB_CHECK_LAUNCH(h);
+  const size_t sm = (size_t)(ws.n_chunks + 1) * sizeof(int);
+  int* ncnt = ws.n_edges > 0 ? ws.node_cnt : nullptr;
+  if (cms_is_half)
+    k_local_emit<__half><<<B, 256, sm, h->stream>>>(
+        (const __half*)cms, offsets, H, W, C, ws.n_chunks, ws.chunk_cap, p.refinement, p.patch,
+        p.scale, p.input_scale, ws.max_peaks, ws.max_node_peaks, ws.chunk_cnt, ws.chunk_items, ws.peaks,
+        ws.peak_vals, ws.peak_ch, ws.n_peaks, ws.total_peaks, ncnt, ws.node_peaks, ws.flags);
+  else
+    k_local_emit<float><<<B, 256, sm, h->stream>>>(
+        (const float*)cms, offsets, H, W, C, ws.n_chunks, ws.chunk_cap, p.refinement, p.patch,
+        p.scale, p.input_scale, ws.max_peaks, ws.max_node_peaks, ws.chunk_cnt, ws.chunk_items, ws.peaks,
+        ws.peak_vals, ws.peak_ch, ws.n_peaks, ws.total_peaks, ncnt, ws.node_peaks, ws.flags);
+  SB_CHECK_LAUNCH(h);
+  return 0;
+}
+
+int sbk_global_peaks(sb_handle_s* h, const void* cms, int cms_is_half, const float* offsets,
+                     int B, int H, int W, int C, const SbPeakParams& p,
+                     const float* crop_off_dev, float* part_buf, int n_chunks, int rows_per_chunk,
+                     float* out_points, float* out_vals) {
+  if (C > 256) return sb_fail(h, SB_ERR_UNSUPPORTED, "global peaks: C > 256");
+  dim3 g(n_chunks, B);
+  const int per = 256 / C > 0 ? 256 / C : 1;
+  const size_t sm = (size_t)per * C * 3 * sizeof(float);
+  GlobalFix fix;
+  fix.scale = p.scale; fix.input_scale = p.input_scale; fix.has_crop_off = crop_off_dev != nullptr;
+  if (cms_is_half) {
+    k_global_partial<__half><<<g, 256, sm, h->stream>>>((const __half*)cms, H, W, C, rows_per_chunk, part_buf);
+    SB_CHECK_LAUNCH(h);
+    k_global_final<__half><<<B, 64, 0, h->stream>>>((const __half*)cms, offsets, H, W, C, n_chunks, part_buf,
+                                                    p.threshold, p.refinement, p.patch, fix, crop_off_dev,
+                                                    out_points, out_vals);
+  } else {
+    k_global_partial<float><<<g, 256, sm, h->stream>>>((const float*)cms, H, W, C, rows_per_chunk, part_buf);
+    SB_CHECK_LAUNCH(h);
+    k_global_final<float><<<B, 64, 0, h->stream>>>((const float*)cms, offsets, H, W, C, n_chunks, part_buf,
+                                                   p.threshold, p.refinement, p.patch, fix, crop_off_dev,
+                                                   out_points, out_vals);
+  }
+  SB_CHECK_LAUNCH(h);
+  return 0;
+}
+
+int sbk_score_match(sb_handle_s* h, const float* pafs, int B, int Hp, int Wp, int C2, int n_points,
+                    int pafs_stride, float max_edge_length, float dist_penalty_weight, SbPostWs& ws) {
+  const int K = ws.max_node_peaks, E = ws.n_edges;
+  const size_t sm = (size_t)K * K * sizeof(float) + lsap_scratch_bytes(K);
+  if (sm > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_score_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return sb_fail(h, SB_ERR_CUDA, "score_match smem %zu: %s", sm, cudaGetErrorString(e));
+  }
+  dim3 g(E, B);
+  k_score_match<<<g, 128, sm, h->stream>>>(pafs, Hp, Wp, C2, ws.C, K, ws.max_peaks, ws.edges_dev, ws.peaks,
+                                           ws.node_cnt, ws.node_peaks, n_points, (float)pafs_stride,
+                                           max_edge_length, dist_penalty_weight, ws.score_mat, ws.match_cnt,
+                                           ws.match_src, ws.match_dst, ws.match_score);
+  SB_CHECK_LAUNCH(h);
+  return 0;
+}
+
+int sbk_group(sb_handle_s* h, int B, int n_nodes, int min_instance_peaks, float min_line_scores,
+              float input_scale, SbPostWs& ws) {
+  const int K = ws.max_node_peaks;
+  const size_t sm = (size_t)2 * n_nodes * K * sizeof(int);
+  if (sm > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return sb_fail(h, SB_ERR_CUDA, "group smem %zu: %s", sm, cudaGetErrorString(e));
+  }
+  k_group<<<B, 128, sm, h->stream>>>(n_nodes, ws.n_edges, K, ws.max_peaks, ws.max_instances, ws.edges_dev,
+                                     ws.sorted_edges_dev, ws.n_sorted, ws.peaks, ws.peak_vals, ws.node_cnt,
+                                     ws.node_peaks, ws.match_cnt, ws.match_src, ws.match_dst, ws.match_score,
+                                     min_instance_peaks, min_line_scores, input_scale, ws.inst_peaks,
+                                     ws.inst_vals, ws.inst_scores, ws.n_inst, ws.flags);
+  SB_CHECK_LAUNCH(h);
+  return 0;
+}
+
+int sbk_lsap_batch(sb_handle_s* h, const float* scores, const int* n_src, const int* n_dst,
+                   const int* offsets, int n_problems, int max_k, int* out_rows, int* out_cols,
+                   float* out_scores, int* out_counts) {
+  if (n_problems <= 0) return 0;
+  const size_t sm = lsap_scratch_bytes(max_k);
+  if (sm > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_lsap_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return sb_fail(h, SB_ERR_CUDA, "lsap smem %zu: %s", sm, cudaGetErrorString(e));
+  }
+  k_lsap_batch<<<n_problems, 32, sm, h->stream>>>(scores, n_src, n_dst, offsets, max_k, out_rows, out_cols,
+                                                  out_scores, out_counts);
+  SB_CHECK_LAUNCH(h);
+  return 0;
+}
+
+int sbk_crop(sb_handle_s* h, const void* images, int img_is_u8, int B, int H, int W, int C,
+             const float* centroids, const int* sample_inds, int n, int crop_h, int crop_w, void* out,
+             int out_is_u8_trunc) {
+  if (n <= 0) return 0;
+  const int total = crop_h * crop_w * C;
+  dim3 g((total + 255) / 256, n);
+  if (g.x > 64) g.x = 64;
+  if (img_is_u8)
+    k_crop<unsigned char, unsigned char, true><<<g, 256, 0, h->stream>>>(
+        (const unsigned char*)images, H, W, C, centroids, sample_inds, crop_h, crop_w, (unsigned char*)out);
+  else
+    k_crop<float, float, false><<<g, 256, 0, h->stream>>>((const float*)images, H, W, C, centroids,
+                                                           sample_inds, crop_h, crop_w, (float*)out);
+  SB_CHECK_LAUNCH(h);
+  return 0;
+}
+
+int sbk_lines(sb_handle_s* h, const float* pafs, int Hp, int Wp, int C2, const float* lines_in,
+              const float* peaks, const int* edge_peak_inds, const int* edge_inds, int n, int P,
+              float pafs_stride, float max_edge_length, float dist_w, int* out_subs, float* out_lines,
+              float* out_scores) {
+  if (n <= 0) return 0;
+  k_lines<<<(n + 3) / 4, 128, 0, h->stream>>>(pafs, Hp, Wp, C2, lines_in, peaks, edge_peak_inds, edge_inds, n, P,
+                                              pafs_stride, max_edge_length, dist_w, out_subs, out_lines, out_scores);
+  SB_CHECK_LAUNCH(h);
+  return 0;
+}
+
+int sbk_integral(sb_handle_s* h, const float* cms, int N, int Hh, int Ww, int C, const float* xv,
+                 const float* yv, float* x_hat, float* y_hat) {
+  if (N * C <= 0) return 0;
+  k_integral<<<(N * C + 3) / 4, 128, 0, h->stream>>>(cms, N, Hh, Ww, C, xv, yv, x_hat, y_hat);
+  SB_CHECK_LAUNCH(h);
+  return 0;
+}
+
+int sbk_local_dir(sb_handle_s* h, const float* patches, int N, float delta, float* out) {
+  if (N <= 0) return 0;
+  k_local_dir<<<(N + 127) / 128, 128, 0, h->stream>>>(patches, N, delta, out);
+  SB_CHECK_LAUNCH(h);
+  return 0;
+}

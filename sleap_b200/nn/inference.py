@@ -1,0 +1,747 @@
+"""Drop-in for the inference side of ``sleap.nn.inference`` (reference: sleap/nn/inference.py).
+
+Kept surface (same names / attributes / dict contract, NumPy in and out):
+  Predictor (:158-590), InferenceModel.predict / predict_on_batch (:989-1090),
+  SingleInstanceInferenceLayer/Model/Predictor (:1229-1636),
+  CentroidCrop (:1638-1967), FindInstancePeaks (:1969-2201), TopDownInferenceModel (:2246-2311),
+  TopDownPredictor (:2314-2735), BottomUpInferenceLayer/Model (:2737-3053),
+  BottomUpPredictor (:3055-3349), load_model (:4865).
+All tensor work runs on the GPU through libsleapb200 (C-ABI); this file is orchestration only.
+"""
+import ctypes
+import json
+import os
+import queue
+import threading
+from ctypes import c_int32, byref
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from sleap_b200 import _lib
+from sleap_b200._lib import BottomUpParams, CentroidParams, GlobalParams, f32, i32, ptr
+from sleap_b200.nn import architectures as arch
+from sleap_b200.nn import paf_grouping, peak_finding
+from sleap_b200.nn.model import DeviceModel, PRECISION_FP16, PRECISION_FP32, load_weights_npz
+
+REFINE = peak_finding.REFINE
+
+
+def _images_of(data):
+    if isinstance(data, dict):
+        return data["image"]
+    return data
+
+
+def _ragged_to_dense(rows: List[np.ndarray], inner_shape, dtype=np.float32):
+    """RaggedTensor.to_tensor(default=NaN) to the bounding shape + row lengths (data/utils.py:118-146)."""
+    n = max([len(r) for r in rows] + [0])
+    out = np.full((len(rows), n) + tuple(inner_shape), np.nan, dtype)
+    for i, r in enumerate(rows):
+        if len(r):
+            out[i, :len(r)] = r
+    return out, np.asarray([len(r) for r in rows], np.int64)
+
+
+class InferenceModel:
+    """sleap/nn/inference.py:969-1171 (predict / predict_on_batch contract)."""
+
+    def call(self, data):
+        raise NotImplementedError
+
+    def __call__(self, data):
+        return self.call(data)
+
+    def predict_on_batch(self, data, numpy: bool = True, **kwargs):
+        """:1047-1090.  Ragged outputs come back NaN-padded with an ``n_valid`` key."""
+        outs = self.call(data)
+        if isinstance(data, dict):
+            for k in ("video_ind", "frame_ind", "scale", "offset_x", "offset_y"):
+                if k in data and k not in outs:
+                    outs[k] = data[k]
+        return outs
+
+    def predict(self, data, numpy: bool = True, batch_size: int = 4, **kwargs):
+        """:989-1045: iterate batches and concatenate (NaN-padding to the widest batch)."""
+        imgs = np.asarray(_images_of(data))
+        chunks = [self.predict_on_batch(imgs[i:i + batch_size]) for i in range(0, len(imgs), batch_size)]
+        return _merge_batches(chunks)
+
+
+def _merge_batches(chunks):
+    out = {}
+    if not chunks:
+        return out
+    for k in chunks[0]:
+        arrs = [np.asarray(c[k]) for c in chunks]
+        if arrs[0].ndim >= 2 and np.issubdtype(arrs[0].dtype, np.floating):
+            n = max(a.shape[1] for a in arrs)
+            padded = []
+            for a in arrs:
+                if a.shape[1] < n:
+                    pad = np.full((a.shape[0], n - a.shape[1]) + a.shape[2:], np.nan, a.dtype)
+                    a = np.concatenate([a, pad], axis=1)
+                padded.append(a)
+            out[k] = np.concatenate(padded, axis=0)
+        else:
+            out[k] = np.concatenate(arrs, axis=0)
+    return out
+
+
+class InferenceLayer:
+    """sleap/nn/inference.py:897-967: owns the device model and the preprocessing parameters.
+    (uint8 -> float, gray/rgb, resize by input_scale and pad_to_stride run inside the device op-list.)"""
+
+    def __init__(self, keras_model: DeviceModel, input_scale: float = 1.0, pad_to_stride: int = 1,
+                 ensure_grayscale: Optional[bool] = None, ensure_float: bool = True):
+        self.keras_model = keras_model      # attribute name kept from the reference
+        self.input_scale = input_scale
+        self.pad_to_stride = pad_to_stride
+        if ensure_grayscale is None:
+            ensure_grayscale = keras_model.cm.input_channels == 1
+        self.ensure_grayscale = ensure_grayscale
+        self.ensure_float = ensure_float
+
+    @staticmethod
+    def _prep(imgs):
+        imgs = np.ascontiguousarray(imgs)
+        if imgs.ndim == 3:
+            imgs = imgs[..., None]
+        if imgs.dtype != np.uint8:
+            imgs = np.ascontiguousarray(imgs, dtype=np.float32)
+        return imgs
+
+
+def _find_head(model: DeviceModel, name: str):
+    if name not in model.cm.head_buffers:
+        return None
+    return model.cm.head_buffers[name]
+
+
+# ------------------------------------------------------------------------------------------
+class SingleInstanceInferenceLayer(InferenceLayer):
+    """sleap/nn/inference.py:1229-1380."""
+
+    HEAD = "SingleInstanceConfmapsHead"
+
+    def __init__(self, keras_model, input_scale=1.0, pad_to_stride=1, output_stride=None, peak_threshold=0.2,
+                 refinement="local", integral_patch_size=5, return_confmaps=False, confmaps_ind=None,
+                 offsets_ind=None, **kwargs):
+        super().__init__(keras_model, input_scale=input_scale, pad_to_stride=pad_to_stride, **kwargs)
+        self.confmaps_buffer = _find_head(keras_model, self.HEAD)
+        if self.confmaps_buffer is None:
+            raise ValueError(f"Index of the confidence maps output tensor must be specified if not named '{self.HEAD}'.")
+        self.offsets_buffer = _find_head(keras_model, "OffsetRefinementHead")
+        if output_stride is None:
+            output_stride = keras_model.cm.head_strides[self.HEAD]
+        self.output_stride = output_stride
+        self.peak_threshold = peak_threshold
+        self.refinement = refinement
+        self.integral_patch_size = integral_patch_size
+        self.return_confmaps = return_confmaps
+        self._cfg_key = None
+
+    def _configure(self, B, H, W, C):
+        m = self.keras_model
+        if not (m.configured_for and m.configured_for[0] >= B and m.configured_for[1:] == (H, W, C)):
+            m.configure(B, H, W, C)
+            self._cfg_key = None
+        key = (m.configured_for, self.peak_threshold, self.refinement, self.integral_patch_size, self.input_scale)
+        if self._cfg_key != key:
+            p = GlobalParams(self.confmaps_buffer, -1 if self.offsets_buffer is None else self.offsets_buffer,
+                             int(self.output_stride), float(self.peak_threshold), REFINE.get(self.refinement, 0),
+                             int(self.integral_patch_size), float(self.input_scale))
+            m.handle.call("sb_global_configure", m.model_id, byref(p))
+            self._cfg_key = key
+
+    def call(self, data, crop_offsets=None):
+        imgs = self._prep(_images_of(data))
+        B, H, W, C = imgs.shape
+        self._configure(B, H, W, C)
+        m = self.keras_model
+        n_nodes = next(h["channels"] for h in m.spec["heads"] if h["name"] == self.HEAD)
+        pts = np.zeros((B, n_nodes, 2), np.float32)
+        vals = np.zeros((B, n_nodes), np.float32)
+        co = None if crop_offsets is None else f32(crop_offsets).reshape(B, 2)
+        m.handle.call("sb_infer_global", m.model_id, ptr(imgs), int(imgs.dtype == np.uint8), B, ptr(co), ptr(pts), ptr(vals))
+        out = {"instance_peaks": pts[:, None], "instance_peak_vals": vals[:, None]}
+        if self.return_confmaps:
+            out["confmaps"] = m.forward(imgs, [self.HEAD])[0]
+        return out
+
+
+class SingleInstanceInferenceModel(InferenceModel):
+    """sleap/nn/inference.py:1383-1415."""
+
+    def __init__(self, single_instance_layer: SingleInstanceInferenceLayer):
+        self.single_instance_layer = single_instance_layer
+
+    def call(self, example):
+        return self.single_instance_layer.call(example)
+
+
+# ------------------------------------------------------------------------------------------
+class CentroidCrop(InferenceLayer):
+    """sleap/nn/inference.py:1638-1967: centroid net -> local peaks -> crops of the raw frames."""
+
+    HEAD = "CentroidConfmapsHead"
+
+    def __init__(self, keras_model, crop_size, input_scale=1.0, pad_to_stride=1, output_stride=None,
+                 peak_threshold=0.2, refinement="local", integral_patch_size=5, return_confmaps=False,
+                 return_crops=True, confmaps_ind=None, offsets_ind=None, max_instances=None,
+                 precrop_resize=1.0, max_peaks_per_sample=256, **kwargs):
+        super().__init__(keras_model, input_scale=input_scale, pad_to_stride=pad_to_stride, **kwargs)
+        self.crop_size = crop_size
+        self.confmaps_buffer = _find_head(keras_model, self.HEAD)
+        if self.confmaps_buffer is None:
+            raise ValueError(f"Index of the confidence maps output tensor must be specified if not named '{self.HEAD}'.")
+        self.offsets_buffer = _find_head(keras_model, "OffsetRefinementHead")
+        self.output_stride = output_stride or keras_model.cm.head_strides[self.HEAD]
+        self.peak_threshold = peak_threshold
+        self.refinement = refinement
+        self.integral_patch_size = integral_patch_size
+        self.return_confmaps = return_confmaps
+        self.return_crops = return_crops
+        self.max_instances = max_instances
+        self.precrop_resize = precrop_resize
+        self.max_peaks_per_sample = max_peaks_per_sample
+        self._cfg_key = None
+
+    def call(self, inputs):
+        full_imgs = self._prep(_images_of(inputs))
+        B, H, W, C = full_imgs.shape
+        m = self.keras_model
+        m.configure(B, H, W, C)
+        key = (m.configured_for, self.peak_threshold, self.refinement, self.integral_patch_size, self.input_scale)
+        if self._cfg_key != key:
+            p = CentroidParams(self.confmaps_buffer, -1 if self.offsets_buffer is None else self.offsets_buffer,
+                               int(self.output_stride), float(self.peak_threshold), REFINE.get(self.refinement, 0),
+                               int(self.integral_patch_size), float(self.input_scale), int(self.max_peaks_per_sample))
+            m.handle.call("sb_centroid_configure", m.model_id, byref(p))
+            self._cfg_key = key
+        cap = B * self.max_peaks_per_sample
+        pts = np.zeros((cap, 2), np.float32)
+        vals = np.zeros((cap,), np.float32)
+        sinds = np.zeros((cap,), np.int32)
+        n = c_int32(0)
+        flags = np.zeros((B,), np.int32)
+        m.handle.call("sb_infer_centroids", m.model_id, ptr(full_imgs), int(full_imgs.dtype == np.uint8), B, ptr(pts),
+                      ptr(vals), ptr(sinds), byref(n), ptr(flags))
+        k = n.value
+        pts, vals, sinds = pts[:k].copy(), vals[:k].copy(), sinds[:k].copy()
+        if self.precrop_resize != 1.0:
+            raise NotImplementedError("precrop_resize != 1 (centered-instance input_scaling) is not built yet")
+        if k > 0 and self.max_instances is not None:
+            keep = []
+            for s in range(B):   # tf.math.top_k: descending score, ties keep the lower index (:1879-1894)
+                idx = np.nonzero(sinds == s)[0]
+                if self.max_instances < len(idx):
+                    order = np.argsort(-vals[idx], kind="stable")[: self.max_instances]
+                    idx = idx[order]
+                keep.append(idx)
+            keep = np.concatenate(keep) if keep else np.zeros((0,), np.int64)
+            pts, vals, sinds = pts[keep], vals[keep], sinds[keep]
+            k = len(keep)
+        crop_offsets = (pts - np.float32(self.crop_size / 2)).astype(np.float32)
+        out = dict(centroids=[pts[sinds == s] for s in range(B)], centroid_vals=[vals[sinds == s] for s in range(B)])
+        if self.return_crops:
+            if k > 0:
+                crops = np.zeros((k, self.crop_size, self.crop_size, C), full_imgs.dtype)
+                m.handle.call("sb_crop_centered", ptr(full_imgs), int(full_imgs.dtype == np.uint8), B, H, W, C,
+                              ptr(f32(pts)), ptr(i32(sinds)), k, self.crop_size, self.crop_size, ptr(crops))
+            else:
+                crops = np.zeros((0, self.crop_size, self.crop_size, C), full_imgs.dtype)
+            out["crops"] = crops
+            out["crop_offsets"] = crop_offsets
+            out["crop_sample_inds"] = sinds
+            out["samples"] = B
+        return out
+
+
+class FindInstancePeaks(SingleInstanceInferenceLayer):
+    """sleap/nn/inference.py:1969-2201: centered-instance net on crops -> global peaks (+ crop offsets)."""
+
+    HEAD = "CenteredInstanceConfmapsHead"
+
+    def __init__(self, keras_model, max_crops_per_call=64, **kwargs):
+        super().__init__(keras_model, **kwargs)
+        self.max_crops_per_call = max_crops_per_call
+
+    def call(self, inputs):
+        if isinstance(inputs, dict):
+            crops = inputs["crops"]
+        else:
+            crops, inputs = inputs, {}
+        crops = self._prep(crops)
+        n = crops.shape[0]
+        if "crop_sample_inds" in inputs:
+            samples, sinds = inputs["samples"], np.asarray(inputs["crop_sample_inds"])
+        else:
+            samples, sinds = n, np.arange(n)
+        co = inputs.get("crop_offsets")
+        m = self.keras_model
+        n_nodes = next(h["channels"] for h in m.spec["heads"] if h["name"] == self.HEAD)
+        pts = np.zeros((n, n_nodes, 2), np.float32)
+        vals = np.zeros((n, n_nodes), np.float32)
+        for i in range(0, n, self.max_crops_per_call):
+            sl = slice(i, min(n, i + self.max_crops_per_call))
+            sub = np.ascontiguousarray(crops[sl])
+            # keep one device configuration for all chunk sizes
+            self._configure(self.max_crops_per_call, *sub.shape[1:])
+            o = super().call(sub, crop_offsets=None if co is None else np.asarray(co)[sl])
+            pts[sl], vals[sl] = o["instance_peaks"][:, 0], o["instance_peak_vals"][:, 0]
+        out = {"instance_peaks": [pts[sinds == s] for s in range(samples)],
+               "instance_peak_vals": [vals[sinds == s] for s in range(samples)]}
+        for k in ("centroids", "centroid_vals"):
+            if k in inputs:
+                out[k] = inputs[k]
+        return out
+
+
+class TopDownInferenceModel(InferenceModel):
+    """sleap/nn/inference.py:2246-2311."""
+
+    def __init__(self, centroid_crop, instance_peaks):
+        self.centroid_crop = centroid_crop
+        self.instance_peaks = instance_peaks
+
+    def call(self, example):
+        crop_out = self.centroid_crop.call(example)
+        peaks_out = self.instance_peaks.call(crop_out)
+        n_nodes = peaks_out["instance_peaks"][0].shape[1] if peaks_out["instance_peaks"] and peaks_out["instance_peaks"][0].ndim == 3 else \
+            next(h["channels"] for h in self.instance_peaks.keras_model.spec["heads"] if h["name"] == self.instance_peaks.HEAD)
+        ip, nv = _ragged_to_dense(peaks_out["instance_peaks"], (n_nodes, 2))
+        iv, _ = _ragged_to_dense(peaks_out["instance_peak_vals"], (n_nodes,))
+        ce, _ = _ragged_to_dense(peaks_out["centroids"], (2,))
+        cv, _ = _ragged_to_dense(peaks_out["centroid_vals"], ())
+        return {"centroids": ce, "centroid_vals": cv, "instance_peaks": ip, "instance_peak_vals": iv, "n_valid": nv}
+
+
+# ------------------------------------------------------------------------------------------
+class BottomUpInferenceLayer(InferenceLayer):
+    """sleap/nn/inference.py:2737-3003: net -> local peaks -> PAF scoring -> matching -> grouping,
+    executed as one device pipeline (``sb_infer_bottomup``)."""
+
+    def __init__(self, keras_model, paf_scorer, input_scale=1.0, pad_to_stride=1, cm_output_stride=None,
+                 paf_output_stride=None, peak_threshold=0.2, refinement="local", integral_patch_size=5,
+                 return_confmaps=False, return_pafs=False, return_paf_graph=False, confmaps_ind=None,
+                 pafs_ind=None, offsets_ind=None, max_peaks_per_sample=1024, max_node_peaks=32,
+                 max_instances=64, **kwargs):
+        super().__init__(keras_model, input_scale=input_scale, pad_to_stride=pad_to_stride, **kwargs)
+        self.paf_scorer = paf_scorer
+        self.confmaps_buffer = _find_head(keras_model, "MultiInstanceConfmapsHead")
+        self.pafs_buffer = _find_head(keras_model, "PartAffinityFieldsHead")
+        self.offsets_buffer = _find_head(keras_model, "OffsetRefinementHead")
+        if self.confmaps_buffer is None:
+            raise ValueError("Index of the confidence maps output tensor must be specified if not named 'MultiInstanceConfmapsHead'.")
+        if self.pafs_buffer is None:
+            raise ValueError("Index of the part affinity fields output tensor must be specified if not named 'PartAffinityFieldsHead'.")
+        self.cm_output_stride = cm_output_stride or keras_model.cm.head_strides["MultiInstanceConfmapsHead"]
+        self.paf_output_stride = paf_output_stride or keras_model.cm.head_strides["PartAffinityFieldsHead"]
+        self.peak_threshold = peak_threshold
+        self.refinement = refinement
+        self.integral_patch_size = integral_patch_size
+        self.return_confmaps = return_confmaps
+        self.return_pafs = return_pafs
+        self.return_paf_graph = return_paf_graph
+        self.max_peaks_per_sample = max_peaks_per_sample
+        self.max_node_peaks = max_node_peaks
+        self.max_instances = max_instances
+        self._cfg_key = None
+        self._keep = None
+
+    def params(self) -> BottomUpParams:
+        ps = self.paf_scorer
+        edges = i32(ps.edge_inds).reshape(-1, 2)
+        sorted_e = i32(list(ps.sorted_edge_inds))
+        mip = ps.min_instance_peaks
+        if isinstance(mip, float):
+            mip = int(mip * ps.n_nodes)
+        self._keep = (edges, sorted_e)
+        return BottomUpParams(
+            self.confmaps_buffer, self.pafs_buffer, -1 if self.offsets_buffer is None else self.offsets_buffer,
+            int(self.cm_output_stride), int(self.paf_output_stride), float(self.peak_threshold),
+            REFINE.get(self.refinement, 0), int(self.integral_patch_size), ps.n_nodes, ps.n_edges,
+            edges.ctypes.data, sorted_e.ctypes.data, len(sorted_e), int(ps.n_points), float(ps.max_edge_length_ratio),
+            float(ps.dist_penalty_weight), float(ps.min_line_scores), int(mip), float(self.input_scale),
+            int(self.max_peaks_per_sample), int(self.max_node_peaks), int(self.max_instances))
+
+    def _configure(self, B, H, W, C):
+        m = self.keras_model
+        if not (m.configured_for and m.configured_for[0] >= B and m.configured_for[1:] == (H, W, C)):
+            m.configure(B, H, W, C)
+            self._cfg_key = None
+        ps = self.paf_scorer
+        key = (m.configured_for, self.peak_threshold, self.refinement, self.integral_patch_size, self.input_scale,
+               ps.n_points, ps.max_edge_length_ratio, ps.dist_penalty_weight, ps.min_line_scores, ps.min_instance_peaks,
+               self.max_peaks_per_sample, self.max_node_peaks, self.max_instances)
+        if self._cfg_key != key:
+            p = self.params()
+            m.handle.call("sb_bottomup_configure", m.model_id, byref(p))
+            self._cfg_key = key
+
+    def call(self, data):
+        imgs = self._prep(_images_of(data))
+        if imgs.dtype != np.uint8:
+            raise ValueError("BottomUpInferenceLayer expects uint8 frames (the fused path reads raw frames).")
+        B, H, W, C = imgs.shape
+        self._configure(B, H, W, C)
+        m = self.keras_model
+        I, N = self.max_instances, self.paf_scorer.n_nodes
+        ip = np.zeros((B, I, N, 2), np.float32)
+        iv = np.zeros((B, I, N), np.float32)
+        isc = np.zeros((B, I), np.float32)
+        nv = np.zeros((B,), np.int32)
+        fl = np.zeros((B,), np.int32)
+        m.handle.call("sb_infer_bottomup", m.model_id, ptr(imgs), B, ptr(ip), ptr(iv), ptr(isc), ptr(nv), ptr(fl))
+        n = int(nv.max()) if B else 0
+        out = {"instance_peaks": ip[:, :n].copy(), "instance_peak_vals": iv[:, :n].copy(),
+               "instance_scores": isc[:, :n].copy(), "n_valid": nv.astype(np.int64), "flags": fl}
+        if self.return_confmaps or self.return_pafs:
+            cms, pafs = m.forward(imgs, ["MultiInstanceConfmapsHead", "PartAffinityFieldsHead"])
+            if self.return_confmaps:
+                out["confmaps"] = cms
+            if self.return_pafs:
+                out["part_affinity_fields"] = pafs
+        if self.return_paf_graph:
+            out.update(self.fetch_graph(B))
+        return out
+
+    def fetch_graph(self, B):
+        m = self.keras_model
+        cp = B * self.max_peaks_per_sample
+        cc = B * self.paf_scorer.n_edges * self.max_node_peaks ** 2
+        peaks = np.zeros((cp, 2), np.float32); pv = np.zeros((cp,), np.float32); pc = np.zeros((cp,), np.int32)
+        po = np.zeros((B + 1,), np.int32)
+        ei = np.zeros((cc,), np.int32); epi = np.zeros((cc, 2), np.int32); ls = np.zeros((cc,), np.float32)
+        co = np.zeros((B + 1,), np.int32)
+        m.handle.call("sb_bottomup_fetch_graph", m.model_id, B, cp, ptr(peaks), ptr(pv), ptr(pc), ptr(po), cc, ptr(ei),
+                      ptr(epi), ptr(ls), ptr(co))
+        rows = lambda a, o: [a[o[b]:o[b + 1]].copy() for b in range(B)]
+        return {"peaks": rows(peaks, po), "peak_vals": rows(pv, po), "peak_channel_inds": rows(pc, po),
+                "edge_inds": rows(ei, co), "edge_peak_inds": rows(epi, co), "line_scores": rows(ls, co)}
+
+
+def bottomup_from_maps(cms, pafs, paf_scorer, cm_output_stride, peak_threshold=0.2, refinement="integral",
+                       integral_patch_size=5, offsets=None, input_scale=1.0, max_peaks_per_sample=1024,
+                       max_node_peaks=32, max_instances=64, return_paf_graph=True, handle=None):
+    """The BottomUpInferenceLayer post-processing chain (inference.py:2892-3003) on caller-supplied
+    confidence maps / PAFs -- the parity entry point (identical maps in, bit-exact instances out)."""
+    h = handle or _lib.default_handle()
+    cms, pafs = f32(cms), f32(pafs)
+    B, H, W, C = cms.shape
+    _, Hp, Wp, C2 = pafs.shape
+    ps = paf_scorer
+    edges = i32(ps.edge_inds).reshape(-1, 2)
+    sorted_e = i32(list(ps.sorted_edge_inds))
+    mip = ps.min_instance_peaks
+    if isinstance(mip, float):
+        mip = int(mip * ps.n_nodes)
+    p = BottomUpParams(-1, -1, -1, int(cm_output_stride), int(ps.pafs_stride), float(peak_threshold),
+                       REFINE.get(refinement, 0), int(integral_patch_size), ps.n_nodes, ps.n_edges, edges.ctypes.data,
+                       sorted_e.ctypes.data, len(sorted_e), int(ps.n_points), float(ps.max_edge_length_ratio),
+                       float(ps.dist_penalty_weight), float(ps.min_line_scores), int(mip), float(input_scale),
+                       int(max_peaks_per_sample), int(max_node_peaks), int(max_instances))
+    I, N = max_instances, ps.n_nodes
+    ip = np.zeros((B, I, N, 2), np.float32); iv = np.zeros((B, I, N), np.float32); isc = np.zeros((B, I), np.float32)
+    nv = np.zeros((B,), np.int32); fl = np.zeros((B,), np.int32)
+    cp = B * max_peaks_per_sample
+    cc = B * ps.n_edges * max_node_peaks ** 2
+    peaks = np.zeros((cp, 2), np.float32); pv = np.zeros((cp,), np.float32); pc = np.zeros((cp,), np.int32)
+    po = np.zeros((B + 1,), np.int32)
+    ei = np.zeros((cc,), np.int32); epi = np.zeros((cc, 2), np.int32); ls = np.zeros((cc,), np.float32)
+    co = np.zeros((B + 1,), np.int32)
+    off = None if offsets is None else f32(offsets)
+    h.call("sb_bottomup_from_maps", byref(p), ptr(cms), B, H, W, ptr(pafs), Hp, Wp, ptr(off), ptr(ip), ptr(iv), ptr(isc),
+           ptr(nv), ptr(fl), cp, ptr(peaks) if return_paf_graph else None, ptr(pv), ptr(pc), ptr(po), cc, ptr(ei),
+           ptr(epi), ptr(ls), ptr(co))
+    out = {"instance_peaks": [ip[b, :nv[b]].copy() for b in range(B)],
+           "instance_peak_vals": [iv[b, :nv[b]].copy() for b in range(B)],
+           "instance_scores": [isc[b, :nv[b]].copy() for b in range(B)], "n_valid": nv, "flags": fl}
+    if return_paf_graph:
+        rows = lambda a, o: [a[o[b]:o[b + 1]].copy() for b in range(B)]
+        out.update({"peaks": rows(peaks, po), "peak_vals": rows(pv, po), "peak_channel_inds": rows(pc, po),
+                    "edge_inds": rows(ei, co), "edge_peak_inds": rows(epi, co), "line_scores": rows(ls, co)})
+    return out
+
+
+class BottomUpInferenceModel(InferenceModel):
+    """sleap/nn/inference.py:3006-3052."""
+
+    def __init__(self, bottomup_layer: BottomUpInferenceLayer):
+        self.bottomup_layer = bottomup_layer
+
+    def call(self, example):
+        return self.bottomup_layer.call(example)
+
+
+# ------------------------------------------------------------------------------------------
+class PredictedInstance:
+    """Array contract of ``sleap.PredictedInstance.from_numpy`` (sleap/instance.py:1164)."""
+
+    def __init__(self, points, point_confidences, instance_score, skeleton=None, track=None):
+        self.points = np.asarray(points)
+        self.point_confidences = np.asarray(point_confidences)
+        self.score = float(instance_score)
+        self.skeleton = skeleton
+        self.track = track
+
+    @classmethod
+    def from_numpy(cls, points, point_confidences, instance_score, skeleton=None, track=None):
+        return cls(points, point_confidences, instance_score, skeleton, track)
+
+    def numpy(self):
+        return self.points
+
+
+class LabeledFrame:
+    def __init__(self, video, frame_idx, instances):
+        self.video, self.frame_idx, self.instances = video, frame_idx, instances
+
+
+class Predictor:
+    """sleap/nn/inference.py:158-590."""
+
+    verbosity = "none"
+    report_rate = 2.0
+    model_paths: List[str] = []
+
+    def __init__(self, batch_size=4):
+        self.batch_size = batch_size
+        self.inference_model = None
+
+    @classmethod
+    def from_model_paths(cls, model_paths, peak_threshold=0.2, integral_refinement=True, integral_patch_size=5,
+                         batch_size=4, resize_input_layer=True, max_instances=None, precision=PRECISION_FP16,
+                         handle=None):
+        """:176-311: dispatch on the head type found in each model's training_config.json."""
+        if isinstance(model_paths, str):
+            model_paths = [model_paths]
+        if not model_paths:
+            raise ValueError("Must specify at least one model path.")   # :2479
+        cfgs = {}
+        for p in model_paths:
+            cfg_path = p if p.endswith(".json") else os.path.join(p, "training_config.json")
+            with open(cfg_path) as f:
+                cfg = json.load(f)
+            heads = {k: v for k, v in cfg["model"]["heads"].items() if v is not None}
+            cfgs[next(iter(heads))] = (cfg, os.path.dirname(cfg_path))
+        kw = dict(peak_threshold=peak_threshold, integral_refinement=integral_refinement,
+                  integral_patch_size=integral_patch_size, batch_size=batch_size, precision=precision, handle=handle)
+        if "single_instance" in cfgs:
+            return SingleInstancePredictor.from_trained_models(cfgs["single_instance"], **kw)
+        if "centroid" in cfgs or "centered_instance" in cfgs:
+            return TopDownPredictor.from_trained_models(cfgs.get("centroid"), cfgs.get("centered_instance"),
+                                                        max_instances=max_instances, **kw)
+        if "multi_instance" in cfgs:
+            return BottomUpPredictor.from_trained_models(cfgs["multi_instance"], max_instances=max_instances, **kw)
+        raise ValueError("Could not create predictor from model paths:" + "\n".join(model_paths))
+
+    # -- shared helpers ---------------------------------------------------------------------
+    @staticmethod
+    def _load(cfg_and_dir, precision, handle):
+        cfg, d = cfg_and_dir
+        spec = arch.spec_from_config(cfg["model"], *_skeleton_from_cfg(cfg))
+        wpath = os.path.join(d, "best_model.npz")
+        if not os.path.exists(wpath):
+            raise FileNotFoundError(
+                f"{wpath} not found.  Keras best_model.h5 files must be exported to .npz first "
+                "(see INTEGRATION.md: h5py is not available in this environment).")
+        pre = cfg["data"]["preprocessing"]
+        in_ch = 1 if pre.get("ensure_grayscale") else (3 if pre.get("ensure_rgb") else int(cfg.get("_input_channels", 1)))
+        model = DeviceModel(spec, load_weights_npz(wpath), input_channels=in_ch,
+                            input_scale=pre.get("input_scaling", 1.0) or 1.0, pad_to_stride=pre.get("pad_to_stride"),
+                            precision=precision, handle=handle)
+        return cfg, spec, model
+
+    def _batches(self, data):
+        imgs = _images_of(data)
+        n = len(imgs)
+        for i in range(0, n, self.batch_size):
+            batch = np.stack([np.asarray(imgs[j]) for j in range(i, min(n, i + self.batch_size))])
+            yield i, batch
+
+    def _predict_generator(self, data):
+        """:377-420: one predict_on_batch per batch (+ frame indices)."""
+        for i0, batch in self._batches(data):
+            ex = self.inference_model.predict_on_batch(batch)
+            ex["frame_ind"] = np.arange(i0, i0 + len(batch))
+            ex["video_ind"] = np.zeros(len(batch), np.int64)
+            yield ex
+
+    def predict(self, data, make_labels: bool = True):
+        """:496-531."""
+        gen = self._predict_generator(data)
+        if make_labels:
+            return self._make_labeled_frames_from_generator(gen, data)
+        return list(gen)
+
+    def _make_labeled_frames_from_generator(self, generator, data):
+        """:3230-3343 pattern: a consumer thread builds the objects while the batch loop runs."""
+        q: "queue.Queue" = queue.Queue()
+        frames: List[LabeledFrame] = []
+
+        def worker():
+            while True:
+                ex = q.get()
+                if ex is None:
+                    return
+                frames.extend(self._frames_from_example(ex))
+
+        t = threading.Thread(target=worker)
+        t.start()
+        try:
+            for ex in generator:
+                q.put(ex)
+        finally:
+            q.put(None)
+            t.join()
+        return frames
+
+    def _frames_from_example(self, ex):
+        out = []
+        scores = ex.get("instance_scores")
+        for i in range(len(ex["instance_peaks"])):
+            insts = []
+            for j in range(ex["instance_peaks"].shape[1]):
+                pts = ex["instance_peaks"][i, j]
+                if np.all(np.isnan(pts)):
+                    continue   # :3285
+                sc = float(scores[i, j]) if scores is not None else float(np.nansum(ex["instance_peak_vals"][i, j]))
+                insts.append(PredictedInstance.from_numpy(pts, ex["instance_peak_vals"][i, j], sc))
+            mi = getattr(self, "max_instances", None)
+            if mi is not None and len(insts) > mi:   # :3297
+                insts = sorted(insts, key=lambda x: x.score, reverse=True)[:mi]
+            out.append(LabeledFrame(int(ex["video_ind"][i]), int(ex["frame_ind"][i]), insts))
+        return out
+
+
+def _skeleton_from_cfg(cfg):
+    sk = (cfg.get("data", {}).get("labels", {}).get("skeletons") or [None])[0]
+    if not sk or "nodes" not in sk:
+        return None, None
+    try:
+        names = [n["id"]["py/state"]["py/tuple"][0] if "py/state" in n["id"] else None for n in sk["nodes"]]
+        if all(names):
+            return names, None
+    except Exception:
+        pass
+    return None, None
+
+
+class SingleInstancePredictor(Predictor):
+    """sleap/nn/inference.py:1418-1636."""
+
+    def __init__(self, confmap_model, peak_threshold=0.2, integral_refinement=True, integral_patch_size=5,
+                 batch_size=4):
+        super().__init__(batch_size)
+        self.confmap_model = confmap_model
+        self.peak_threshold = peak_threshold
+        self.integral_refinement = integral_refinement
+        self.integral_patch_size = integral_patch_size
+        self._initialize_inference_model()
+
+    def _initialize_inference_model(self):
+        """:1456-1478."""
+        m = self.confmap_model
+        self.inference_model = SingleInstanceInferenceModel(SingleInstanceInferenceLayer(
+            keras_model=m, input_scale=m.input_scale, pad_to_stride=m.cm.max_stride,
+            peak_threshold=self.peak_threshold, refinement="integral" if self.integral_refinement else "local",
+            integral_patch_size=self.integral_patch_size))
+
+    @classmethod
+    def from_trained_models(cls, cfg_and_dir, peak_threshold=0.2, integral_refinement=True, integral_patch_size=5,
+                            batch_size=4, precision=PRECISION_FP16, handle=None, **_):
+        _, _, model = cls._load(cfg_and_dir, precision, handle)
+        return cls(model, peak_threshold, integral_refinement, integral_patch_size, batch_size)
+
+
+class TopDownPredictor(Predictor):
+    """sleap/nn/inference.py:2314-2735."""
+
+    def __init__(self, centroid_model=None, confmap_model=None, crop_size=160, peak_threshold=0.2,
+                 integral_refinement=True, integral_patch_size=5, batch_size=4, max_instances=None):
+        super().__init__(batch_size)
+        if centroid_model is None or confmap_model is None:
+            raise ValueError("This build needs both a centroid and a centered-instance model "
+                             "(ground-truth stand-in layers are out of scope).")
+        self.centroid_model, self.confmap_model = centroid_model, confmap_model
+        self.crop_size = crop_size
+        self.peak_threshold = peak_threshold
+        self.integral_refinement = integral_refinement
+        self.integral_patch_size = integral_patch_size
+        self.max_instances = max_instances
+        self._initialize_inference_model()
+
+    def _initialize_inference_model(self):
+        """:2373-2433."""
+        ref = "integral" if self.integral_refinement else "local"
+        cm, im = self.centroid_model, self.confmap_model
+        cc = CentroidCrop(keras_model=cm, crop_size=self.crop_size, input_scale=cm.input_scale,
+                          pad_to_stride=cm.cm.max_stride, peak_threshold=self.peak_threshold, refinement=ref,
+                          integral_patch_size=self.integral_patch_size, max_instances=self.max_instances)
+        fp = FindInstancePeaks(keras_model=im, input_scale=im.input_scale, peak_threshold=self.peak_threshold,
+                               refinement=ref, integral_patch_size=self.integral_patch_size)
+        self.inference_model = TopDownInferenceModel(cc, fp)
+
+    @classmethod
+    def from_trained_models(cls, centroid_cfg, confmap_cfg, peak_threshold=0.2, integral_refinement=True,
+                            integral_patch_size=5, batch_size=4, max_instances=None, precision=PRECISION_FP16,
+                            handle=None, **_):
+        if centroid_cfg is None and confmap_cfg is None:
+            raise ValueError("Either the centroid or topdown confidence map model must be provided.")  # :2479
+        if centroid_cfg is None or confmap_cfg is None:
+            raise ValueError("This build needs both a centroid and a centered-instance model.")
+        _, _, cmodel = cls._load(centroid_cfg, precision, handle)
+        icfg, _, imodel = cls._load(confmap_cfg, precision, handle)
+        crop = icfg["data"]["instance_cropping"]["crop_size"]
+        return cls(cmodel, imodel, crop, peak_threshold, integral_refinement, integral_patch_size, batch_size, max_instances)
+
+
+class BottomUpPredictor(Predictor):
+    """sleap/nn/inference.py:3055-3349 (attrs :3104-3117)."""
+
+    def __init__(self, bottomup_model, part_names, edges, peak_threshold=0.2, batch_size=4, max_edge_length_ratio=0.25,
+                 dist_penalty_weight=1.0, paf_line_points=10, min_line_scores=0.25, integral_refinement=True,
+                 integral_patch_size=5, max_instances=None, max_peaks_per_sample=1024, max_node_peaks=32,
+                 max_instances_per_frame=64):
+        super().__init__(batch_size)
+        self.bottomup_model = bottomup_model
+        self.part_names, self.edges = list(part_names), [tuple(e) for e in edges]
+        self.peak_threshold = peak_threshold
+        self.max_edge_length_ratio = max_edge_length_ratio
+        self.dist_penalty_weight = dist_penalty_weight
+        self.paf_line_points = paf_line_points
+        self.min_line_scores = min_line_scores
+        self.integral_refinement = integral_refinement
+        self.integral_patch_size = integral_patch_size
+        self.max_instances = max_instances
+        self._caps = (max_peaks_per_sample, max_node_peaks, max_instances_per_frame)
+        self._initialize_inference_model()
+
+    def _initialize_inference_model(self):
+        """:3119-3150."""
+        m = self.bottomup_model
+        scorer = paf_grouping.PAFScorer(
+            part_names=self.part_names, edges=self.edges, pafs_stride=m.cm.head_strides["PartAffinityFieldsHead"],
+            max_edge_length_ratio=self.max_edge_length_ratio, dist_penalty_weight=self.dist_penalty_weight,
+            n_points=self.paf_line_points, min_instance_peaks=0, min_line_scores=self.min_line_scores)
+        self.inference_model = BottomUpInferenceModel(BottomUpInferenceLayer(
+            keras_model=m, paf_scorer=scorer, input_scale=m.input_scale, pad_to_stride=m.cm.max_stride,
+            peak_threshold=self.peak_threshold, refinement="integral" if self.integral_refinement else "local",
+            integral_patch_size=self.integral_patch_size, max_peaks_per_sample=self._caps[0],
+            max_node_peaks=self._caps[1], max_instances=self._caps[2]))
+
+    @classmethod
+    def from_trained_models(cls, cfg_and_dir, peak_threshold=0.2, integral_refinement=True, integral_patch_size=5,
+                            batch_size=4, max_instances=None, precision=PRECISION_FP16, handle=None, **_):
+        _, spec, model = cls._load(cfg_and_dir, precision, handle)
+        return cls(model, spec["part_names"], spec["edges"], peak_threshold=peak_threshold, batch_size=batch_size,
+                   integral_refinement=integral_refinement, integral_patch_size=integral_patch_size,
+                   max_instances=max_instances)
+
+
+def load_model(model_path, batch_size=4, peak_threshold=0.2, refinement="integral", **kwargs):
+    """sleap/nn/inference.py:4865-5005 (``sleap.load_model``)."""
+    return Predictor.from_model_paths(model_path, peak_threshold=peak_threshold,
+                                      integral_refinement=(refinement == "integral"), batch_size=batch_size, **kwargs)

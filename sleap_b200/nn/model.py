@@ -1,0 +1,87 @@
+"""Device model: compiled op-list + weights resident on one GPU (replaces the Keras model of
+sleap/nn/model.py:312-364 and ``tf.keras.models.load_model`` at sleap/nn/inference.py:3203-3213)."""
+import ctypes
+import json
+import os
+from ctypes import c_int, c_void_p
+
+import numpy as np
+
+from sleap_b200 import _lib
+from sleap_b200._lib import ptr
+from sleap_b200.nn import architectures as arch
+
+PRECISION_FP16 = 0   # fp16 activations, tensor-core convs, fp32 accumulate, fp32 head outputs
+PRECISION_FP32 = 1   # fp32 CUDA-core path (strict parity with the fp32 reference)
+
+
+class DeviceModel:
+    def __init__(self, spec, weights, input_channels=1, input_scale=1.0, pad_to_stride=None,
+                 precision=PRECISION_FP16, handle=None):
+        self.handle = handle or _lib.default_handle()
+        self.spec = spec
+        self.precision = precision
+        self.input_scale = float(input_scale)
+        self.cm = arch.compile_model(spec, input_channels, input_scale, pad_to_stride)
+        blob = self.cm.pack_weights(weights)
+        ops = self.cm.ops_array()
+        mid = c_int(-1)
+        self.handle.call("sb_load_model", ptr(ops), ops.shape[0], ptr(blob), int(blob.size), int(precision),
+                         ctypes.byref(mid))
+        self.model_id = mid.value
+        self.configured_for = None
+
+    def head_buffer(self, name):
+        return self.cm.head_buffers[name]
+
+    def configure(self, max_batch, H, W, C_in):
+        key = (int(max_batch), int(H), int(W), int(C_in))
+        if self.configured_for != key:
+            self.handle.call("sb_model_configure", self.model_id, *key)
+            self.configured_for = key
+            self._post_cfg = None
+        return self
+
+    def net_hw(self, H, W):
+        """Network input size after resize + pad (resizing.py:71-106, :34-68)."""
+        if self.input_scale != 1.0:
+            W, H = int(np.float32(W) * np.float32(self.input_scale)), int(np.float32(H) * np.float32(self.input_scale))
+        ms = self.cm.max_stride
+        return -(-H // ms) * ms, -(-W // ms) * ms
+
+    def forward(self, images, head_names=None):
+        """images (B,H,W,C) uint8 or float32 in [0,1] -> list of head outputs (NHWC float32)."""
+        images = np.ascontiguousarray(images)
+        is_u8 = images.dtype == np.uint8
+        if not is_u8:
+            images = np.ascontiguousarray(images, dtype=np.float32)
+        B, H, W, C = images.shape
+        if self.configured_for is None or self.configured_for[0] < B or self.configured_for[1:] != (H, W, C):
+            self.configure(B, H, W, C)
+        head_names = head_names or [h["name"] for h in self.spec["heads"]]
+        nh, nw = self.net_hw(H, W)
+        outs, ids = [], []
+        for n in head_names:
+            st = self.cm.head_strides[n]
+            ch = next(h["channels"] for h in self.spec["heads"] if h["name"] == n)
+            outs.append(np.zeros((B, nh // st, nw // st, ch), np.float32))
+            ids.append(self.cm.head_buffers[n])
+        ids_a = np.asarray(ids, np.int32)
+        ptrs = (c_void_p * len(outs))(*[o.ctypes.data for o in outs])
+        self.handle.call("sb_model_forward", self.model_id, ptr(images), int(is_u8), B, len(outs), ptr(ids_a), ptrs)
+        return outs
+
+
+def load_weights_npz(path):
+    """``{layer}/{param}`` arrays exported from a Keras ``best_model.h5``."""
+    z = np.load(path)
+    w = {}
+    for k in z.files:
+        layer, param = k.rsplit("/", 1)
+        w.setdefault(layer, {})[param] = z[k]
+    return w
+
+
+def save_weights_npz(path, weights):
+    flat = {f"{layer}/{param}": arr for layer, p in weights.items() for param, arr in p.items()}
+    np.savez(path, **flat)
