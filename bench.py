@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""Benchmark of the north-star path: bottom-up UNet+PAF pose inference on 1024x1024x1 frames
+(BASELINE.json config C4: 13 nodes / 12 edges, 8 frames per GPU per step, frames sharded over
+the GPUs of one node, one gather of detected instances).
+
+One "step" = one batch of 8 synthetic uint8 frames per GPU through
+preprocess -> UNet (tconv variant, 92.32 GFLOP/frame) -> local peaks + integral refinement ->
+PAF line scoring -> per-edge assignment -> greedy grouping (-> all_gather of instances, N > 1).
+
+  python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, C-ABI)
+  python bench.py --impl reference --steps K --warmup W    # CPU restatement of the reference path
+
+Prints ONE JSON line (rank 0).  `value` = frames/s with frames resident in HBM; `e2e` = the same
+metric through the public `predict_on_batch` call with pinned host frames (H2D + D2H inside).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H = W = 1024
+NODES = ["head", "thorax", "abdomen", "wingL", "wingR", "forelegL", "forelegR", "midlegL", "midlegR",
+         "hindlegL", "hindlegR", "eyeL", "eyeR"]
+EDGES = [("thorax", "head"), ("thorax", "abdomen"), ("thorax", "wingL"), ("thorax", "wingR"),
+         ("thorax", "forelegL"), ("thorax", "forelegR"), ("thorax", "midlegL"), ("thorax", "midlegR"),
+         ("thorax", "hindlegL"), ("thorax", "hindlegR"), ("head", "eyeL"), ("head", "eyeR")]
+UNET_CFG = dict(filters=16, filters_rate=2, max_stride=32, output_stride=4, middle_block=True,
+                up_interpolate=False, stacks=1)          # baseline_medium_rf.bottomup, tconv variant
+SEED = 1004
+FRAMES_PER_GPU = 8
+GFLOP_PER_FRAME = 92.32
+TARGET_PEAKS_PER_CHANNEL = 5
+
+
+def c4_spec():
+    return dict(backbone="unet", backbone_cfg=dict(UNET_CFG), head_type="multi_instance",
+                heads=[dict(name="MultiInstanceConfmapsHead", channels=13, output_stride=4),
+                       dict(name="PartAffinityFieldsHead", channels=24, output_stride=8)],
+                part_names=NODES, edges=EDGES)
+
+
+def make_frames(n, seed0=0):
+    return np.stack([np.random.default_rng(SEED * 1000 + seed0 + i).integers(0, 256, size=(H, W, 1), dtype=np.uint8)
+                     for i in range(n)])
+
+
+def local_max_values(cm):
+    """Values of the strict 8-neighbour maxima of one (H, W) map (workload calibration only)."""
+    p = np.pad(cm, 1, constant_values=-np.inf)
+    nb = np.max(np.stack([p[dy:dy + cm.shape[0], dx:dx + cm.shape[1]] for dy in range(3) for dx in range(3)
+                          if not (dy == 1 and dx == 1)]), axis=0)
+    return cm[cm > nb]
+
+
+def calibrate_heads(weights, cms, pafs, n_frames):
+    """Random-init weights give arbitrary maps.  To make the post-processing load look like a trained
+    model's (~5 peaks per channel, ~65 peaks and ~300 candidates per frame) the two 1x1
+    heads get a per-channel affine: the (5*n_frames+1)-th largest local maximum of each confidence
+    channel is moved to the 0.2 threshold and the largest to 1.0; PAFs are scaled to unit std.
+    This only rescales head weights/biases (setup time, not timed)."""
+    k = np.asarray(weights["MultiInstanceConfmapsHead"]["kernel"]).copy()
+    b = np.asarray(weights["MultiInstanceConfmapsHead"]["bias"]).copy()
+    for c in range(cms.shape[-1]):
+        vals = np.sort(np.concatenate([local_max_values(cms[i, :, :, c]) for i in range(cms.shape[0])]))[::-1]
+        kth = min(len(vals) - 1, TARGET_PEAKS_PER_CHANNEL * n_frames)
+        t, top = float(vals[kth]), float(vals[0])
+        g = 0.8 / max(top - t, 1e-6)
+        k[..., c] *= g
+        b[c] = (b[c] - t) * g + 0.2
+    weights["MultiInstanceConfmapsHead"] = dict(kernel=k, bias=b)
+    s = 1.0 / max(float(pafs.std()), 1e-6)
+    weights["PartAffinityFieldsHead"] = dict(kernel=np.asarray(weights["PartAffinityFieldsHead"]["kernel"]) * s,
+                                             bias=np.asarray(weights["PartAffinityFieldsHead"]["bias"]) * s)
+    return weights
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu_index, self.rows, self.proc = gpu_index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        busy = [s for s in sm if s > 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks_file():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# --------------------------------------------------------------------------------------------
+def cpu_oracle_fps(n_frames, weights, threads=None):
+    """The reference path restated on the CPU (oracle/): torch-CPU fp32 UNet + NumPy peak finding +
+    PAF grouping (SciPy LSAP), on `n_frames` frames of the same workload."""
+    import torch
+    from oracle import convnet, paf_grouping as opg, peak_finding as opf, preprocess as opre
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    frames = make_frames(n_frames, 900)
+    scorer = opg.PAFScorer(NODES, EDGES, pafs_stride=8)
+    t0 = time.perf_counter()
+    for i in range(n_frames):
+        x = opre.preprocess(frames[i:i + 1], ensure_gray=True, input_scale=1.0, pad_stride=32)
+        cms, pafs = convnet.model_forward(x, c4_spec(), weights)
+        p, v, si, ci = opf.find_local_peaks(cms, 0.2, "integral", 5)
+        p = (p * np.float32(4)).astype(np.float32)
+        scorer.predict(pafs, [p], [v], [ci])
+    dt = time.perf_counter() - t0
+    return n_frames / dt, threads
+
+
+def run_reference(args):
+    """--impl reference: TensorFlow (the reference's engine) is not installable offline, so the
+    reference arm is the CPU restatement of its algorithm (oracle/), on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from sleap_b200.nn import architectures as A
+    cm = A.compile_model(c4_spec(), 1)
+    weights = A.make_synthetic_weights(cm, SEED)
+    threads = os.cpu_count()
+    import torch
+    from oracle import convnet, preprocess as opre
+    torch.set_num_threads(threads)
+    calib = make_frames(2, 500)
+    cms0, pafs0 = convnet.model_forward(opre.preprocess(calib, True, 1.0, 32), c4_spec(), weights)
+    weights = calibrate_heads(weights, cms0, pafs0, len(calib))      # same workload shaping as the CUDA arm
+    for _ in range(min(args.warmup, 1)):
+        cpu_oracle_fps(1, weights, threads)
+    times = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        cpu_oracle_fps(1, weights, threads)
+        times.append(time.perf_counter() - t0)
+    fps = len(times) / sum(times)
+    line = {"impl": "reference", "metric": "frames/sec (1024x1024 bottom-up UNet+PAF)", "value": fps, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C4 bottom-up UNet(f16,ms32,os4,tconv)+PAF 1024x1024x1, 13 nodes/12 edges",
+                       "step": "1 frame per step (bounded sample of the 8-frame batch)"},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                             "sample": f"{args.steps} steps x 1 frame, torch-CPU fp32 UNet + NumPy/SciPy post-processing"},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from ctypes import byref, c_int32, c_void_p
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from sleap_b200 import _lib
+    from sleap_b200.nn import architectures as A
+    from sleap_b200.nn.inference import BottomUpPredictor
+    from sleap_b200.nn.model import DeviceModel
+
+    handle = _lib.default_handle(local_rank)
+    stream = torch.cuda.Stream()
+    handle.set_stream(stream.cuda_stream)
+    B = args.frames_per_gpu
+    prec = 0 if args.precision == "fp16" else 1
+
+    spec = c4_spec()
+    cm = A.compile_model(spec, 1)
+    weights = A.make_synthetic_weights(cm, SEED)
+    calib = make_frames(2, 500)
+    m0 = DeviceModel(spec, weights, input_channels=1, precision=prec, handle=handle)
+    cms0, pafs0 = m0.forward(calib)
+    weights = calibrate_heads(weights, cms0, pafs0, len(calib))
+    del m0
+    model = DeviceModel(spec, weights, input_channels=1, precision=prec, handle=handle)
+    pred = BottomUpPredictor(model, NODES, EDGES, peak_threshold=0.2, batch_size=B, integral_refinement=True,
+                             max_peaks_per_sample=1024, max_node_peaks=32, max_instances_per_frame=32)
+    layer = pred.inference_model.bottomup_layer
+    n_sets = 3
+    host = [torch.from_numpy(make_frames(B, 10000 * rank + 100 * s)).pin_memory() for s in range(n_sets)]
+    dev = [h.cuda(non_blocking=True) for h in host]
+    torch.cuda.synchronize()
+    out0 = pred.inference_model.predict_on_batch(host[0].numpy())          # configures everything
+    n_inst_mean = float(np.mean(out0["n_valid"]))
+    I, C = layer.max_instances, 13
+    ptrs = [c_void_p() for _ in range(5)]
+    handle.call("sb_bottomup_device_outputs", model.model_id, *[byref(p) for p in ptrs])
+    rec_elems = B * (I * C * 3 + I + 1)
+    gather_in = torch.empty(rec_elems, dtype=torch.float32, device="cuda")
+    gather_out = torch.empty(world * rec_elems, dtype=torch.float32, device="cuda") if world > 1 else None
+
+    def as_tensor(p, n, dtype):
+        """torch view of a library-owned device buffer (plain pointer -> __cuda_array_interface__)."""
+        class _V:
+            pass
+        v = _V()
+        v.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4" if dtype == torch.float32 else "<i4",
+                                      "data": (p.value, False), "version": 2}
+        return torch.as_tensor(v, device="cuda")
+
+    t_peaks = as_tensor(ptrs[0], B * I * C * 2, torch.float32)
+    t_vals = as_tensor(ptrs[1], B * I * C, torch.float32)
+    t_scores = as_tensor(ptrs[2], B * I, torch.float32)
+    t_nvalid = as_tensor(ptrs[3], B, torch.int32)
+
+    def step_device(i):
+        with torch.cuda.stream(stream):
+            handle.call("sb_infer_bottomup_dev", model.model_id, c_void_p(dev[i % n_sets].data_ptr()), B)
+            if world > 1:   # the path's one exchange step: fixed-size instance records to every rank
+                o = 0
+                for t in (t_peaks, t_vals, t_scores):
+                    gather_in[o:o + t.numel()].copy_(t, non_blocking=True)
+                    o += t.numel()
+                gather_in[o:o + B].copy_(t_nvalid.to(torch.float32), non_blocking=True)
+                dist.all_gather_into_tensor(gather_out, gather_in)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput ("value") ----------------
+    for i in range(args.warmup):
+        step_device(i)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.25)
+    l0 = handle.gpu_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+    for i in range(args.steps):
+        step_device(i)
+    with torch.cuda.stream(stream):
+        ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = handle.gpu_launches() - l0
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * args.steps / (ms_max / 1e3)
+
+    # ---------------- end to end through the public API ("e2e") ----------------
+    for i in range(min(args.warmup, 3)):
+        pred.inference_model.predict_on_batch(host[i % n_sets].numpy())
+    barrier()
+    d2h = 0
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        o = pred.inference_model.predict_on_batch(host[i % n_sets].numpy())
+        if world > 1:
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(gather_out, gather_in)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    d2h = B * (I * C * 2 + I * C + I + 2) * 4
+    te = torch.tensor([e2e_s], device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = world * B * args.steps / float(te.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel (k_conv_tc) ----------------
+    n_ops = c_int32(0)
+    cap = 256
+    op_ms = np.zeros(cap, np.float32); op_kind = np.zeros(cap, np.int32); op_fl = np.zeros(cap, np.float64)
+    reps = []
+    for r in range(3):
+        handle.call("sb_model_profile_ops", model.model_id, c_void_p(dev[r % n_sets].data_ptr()), B, cap,
+                    _lib.ptr(op_ms), _lib.ptr(op_kind), _lib.ptr(op_fl), byref(n_ops))
+        reps.append((op_ms[:n_ops.value].copy(), op_kind[:n_ops.value].copy(), op_fl[:n_ops.value].copy()))
+    op_ms_m = np.median(np.stack([r[0] for r in reps]), axis=0)
+    kind, fl = reps[0][1], reps[0][2]
+    tc = kind == 1
+    tc_ms, tc_flops = float(op_ms_m[tc].sum()), float(fl[tc].sum())
+    peaks, peaks_src = peaks_file()
+    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+    achieved_tf = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    step_ms = ms_max / args.steps
+    roofline = {"bound": "tensor", "kernel": "k_conv_tc (tcgen05 implicit-GEMM conv, all %d launches of a step)" % int(tc.sum()),
+                "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                "peak_source": f"{peaks_src} bf16_tflops_sustained", "traffic": None,
+                "kernel_ms_per_step": tc_ms, "kernel_share_of_step": tc_ms / step_ms if step_ms else None,
+                "algorithmic_flops_per_step": tc_flops,
+                "hbm_model": {"unfused_activation_bytes_per_frame": 357e6,
+                              "achieved_gbs": 357e6 * B / (float(op_ms_m.sum()) * 1e-3) / 1e9,
+                              "peak_gbs": float(peaks["hbm_gbs"])}}
+
+    # ---------------- CPU baseline (oracle port) on a bounded sample ----------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        fps, threads = cpu_oracle_fps(args.cpu_frames, weights)
+        cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+               "sample": f"{args.cpu_frames} frames of the same workload: torch-CPU fp32 UNet + NumPy/SciPy post-processing "
+                         "(tf-cpu is not installable offline)"}
+
+    line = {"metric": "frames/sec (1024x1024 bottom-up UNet+PAF)", "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16" if prec == 0 else "f32", "data": "synthetic",
+            "config": {"workload": "C4 bottom-up UNet(f16,r2,ms32,os4,tconv)+PAF 1024x1024x1, 13 nodes/12 edges (flies13)",
+                       "frames_per_gpu_per_step": B, "global_batch": world * B, "parallelism": f"frame-shard x{world}",
+                       "gflop_per_frame": GFLOP_PER_FRAME,
+                       "l2": "3 rotating input batches; per-step activation working set ~2.9 GB >> 126 MB L2",
+                       "accumulate": "fp32", "head_outputs": "fp32", "mean_instances_per_frame": n_inst_mean,
+                       "heads_calibrated_to_peaks_per_channel": TARGET_PEAKS_PER_CHANNEL},
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * H * W, "d2h_bytes_per_step": d2h,
+                    "api": "BottomUpInferenceModel.predict_on_batch(pinned uint8 batch)"},
+            "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames-per-gpu", type=int, default=FRAMES_PER_GPU)
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32"])
+    ap.add_argument("--cpu-frames", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -156,6 +156,11 @@ int sb_model_forward(sb_handle_t h, int model_id, const void* images_host, int i
                      int B, int n_outputs, const int32_t* output_buffer_ids,
                      float** out_host_ptrs);
 
+/* Device-side timing of one forward pass, op by op (CUDA events on the launching stream).
+ * out_kind: 0 other, 1 tensor-core conv, 2 CUDA-core conv; out_flops: 2*MACs for the batch. */
+int sb_model_profile_ops(sb_handle_t h, int model_id, const uint8_t* frames_dev, int B, int cap,
+                         float* out_ms, int32_t* out_kind, double* out_flops, int32_t* out_n_ops);
+
 /* ---- fused predictors ------------------------------------------------------------------------
  * sleap/nn/inference.py:2737-3003 BottomUpInferenceLayer.call: preprocess -> net -> local peaks
  * -> * cm_output_stride -> PAFScorer.predict -> (/input_scale + 0.5). */

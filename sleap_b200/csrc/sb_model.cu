@@ -146,6 +146,7 @@ static int run_ops_t(sb_handle_s* h, SbModel* m, const void* frames_dev, int fra
   cudaStream_t s = h->stream;
   for (size_t oi = 0; oi < m->ops.size(); ++oi) {
     const SbOp& op = m->ops[oi];
+    if (!m->prof_events.empty()) cudaEventRecord(m->prof_events[oi], s);
     SbBuffer& ob = m->buffers[op.out_buf()];
     switch (op.kind()) {
       case SB_OPK_PREPROCESS: {
@@ -249,6 +250,7 @@ static int run_ops_t(sb_handle_s* h, SbModel* m, const void* frames_dev, int fra
         return sb_fail(h, SB_ERR_INVALID, "unknown op kind %d", op.kind());
     }
   }
+  if (!m->prof_events.empty()) cudaEventRecord(m->prof_events[m->ops.size()], s);
   return 0;
 }
 
@@ -302,6 +304,38 @@ int sb_model_forward(sb_handle_t h, int model_id, const void* images_host, int i
   }
   SB_CUDA(h, cudaStreamSynchronize(h->stream));
   return SB_OK;
+}
+
+// Per-op device timing of one forward pass (CUDA events on the launching stream); used by
+// bench.py for the roofline of the conv kernels.  out_ms[i] = duration of op i; out_kind[i] =
+// 0 other, 1 tensor-core conv, 2 CUDA-core conv; out_flops[i] = 2*MACs of the op for batch B.
+int sb_model_profile_ops(sb_handle_t h, int model_id, const uint8_t* frames_dev, int B, int cap, float* out_ms,
+                         int32_t* out_kind, double* out_flops, int32_t* out_n_ops) {
+  SbModel* m = get_model(h, model_id);
+  if (!m || !m->configured) return sb_fail(h, SB_ERR_INVALID, "model not configured");
+  SB_CUDA(h, cudaSetDevice(h->device));
+  const int n = (int)m->ops.size();
+  if (cap < n) return sb_fail(h, SB_ERR_INVALID, "capacity %d < n_ops %d", cap, n);
+  m->prof_events.resize(n + 1);
+  for (auto& e : m->prof_events) SB_CUDA(h, cudaEventCreate(&e));
+  int rc = sb_run_ops(h, m, frames_dev, 1, B);
+  cudaStreamSynchronize(h->stream);
+  for (int i = 0; i < n && !rc; ++i) {
+    cudaEventElapsedTime(&out_ms[i], m->prof_events[i], m->prof_events[i + 1]);
+    const SbOp& op = m->ops[i];
+    out_kind[i] = 0; out_flops[i] = 0.0;
+    if (op.kind() == SB_OPK_CONV || op.kind() == SB_OPK_TCONV) {
+      out_kind[i] = sb_conv_tc_can(m, i) ? 1 : 2;
+      const SbBuffer& ib = m->buffers[op.in_buf()];
+      const SbBuffer& ob = m->buffers[op.out_buf()];
+      const double pix = op.kind() == SB_OPK_TCONV ? (double)ib.H * ib.W : (double)ob.H * ob.W;
+      out_flops[i] = 2.0 * op.k() * op.k() * op.in_C() * op.out_C() * pix * B;
+    }
+  }
+  for (auto& e : m->prof_events) cudaEventDestroy(e);
+  m->prof_events.clear();
+  *out_n_ops = n;
+  return rc;
 }
 
 // ---------------------------------- bottom-up ------------------------------------------------

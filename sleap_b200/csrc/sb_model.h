@@ -61,6 +61,7 @@ struct SbModel {
   size_t act_bytes = 0;
   void* frames_dev = nullptr;
   std::vector<SbConvTcPlan*> tc_plans;  // per op (nullptr = direct path)
+  std::vector<cudaEvent_t> prof_events; // non-empty only inside sb_model_profile_ops
   // predictors
   SbPostWs ws;
   sb_bottomup_params bu{};

@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(128) k_score_match(
   const int src_node = edges[2 * e], dst_node = edges[2 * e + 1];
   const int ns = min(node_cnt[b * C + src_node], K), nd = min(node_cnt[b * C + dst_node], K);
   float* s_scores = reinterpret_cast<float*>(smem_raw);                 // K*K
-  unsigned char* s_lsap = smem_raw + (size_t)K * K * sizeof(float);
+  unsigned char* s_lsap = smem_raw + (((size_t)K * K * sizeof(float) + 15) & ~(size_t)15);
   const int* src_list = node_peaks + ((size_t)b * C + src_node) * K;
   const int* dst_list = node_peaks + ((size_t)b * C + dst_node) * K;
   const float* pk = peaks + (size_t)b * max_peaks * 2;
@@ -930,7 +930,7 @@ int sbk_global_peaks(sb_handle_s* h, const void* cms, int cms_is_half, const flo
 int sbk_score_match(sb_handle_s* h, const float* pafs, int B, int Hp, int Wp, int C2, int n_points,
                     int pafs_stride, float max_edge_length, float dist_penalty_weight, SbPostWs& ws) {
   const int K = ws.max_node_peaks, E = ws.n_edges;
-  const size_t sm = (size_t)K * K * sizeof(float) + lsap_scratch_bytes(K);
+  const size_t sm = (((size_t)K * K * sizeof(float) + 15) & ~(size_t)15) + lsap_scratch_bytes(K);
   if (sm > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k_score_match, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return sb_fail(h, SB_ERR_CUDA, "score_match smem %zu: %s", sm, cudaGetErrorString(e));

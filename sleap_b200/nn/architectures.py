@@ -196,7 +196,7 @@ def build_hourglass(g: GraphBuilder, x: _T, cfg):
         feats = []
         for b in range(down_blocks):
             x = g.pool(x, f"stack{s}_enc{b}_pool")
-            x = cbn(x, filters + b * inc, f"stack{s}_enc{b}")
+            x = cbn(x, filters + b * inc, f"stack{s}_enc{b}_conv")
             if x.stride not in [f.stride for f in feats]:
                 feats.append(x)
         skips = stem_output + feats[:-1]
@@ -207,7 +207,7 @@ def build_hourglass(g: GraphBuilder, x: _T, cfg):
             f = filters + (down_blocks - b - 1) * inc
             prefix = f"stack{s}_dec{b}"
             skip = next(t for t in skips if t.stride == nxt)
-            x = cbn(x, f, prefix)
+            x = cbn(x, f, prefix + "_conv")
             x = g.upsample(x, False, prefix + "_nearest")
             xs = cbn(skip, f, prefix + "_skip")
             x = g.add(x, xs, prefix + "_skip_add")

@@ -32,7 +32,7 @@ def _random_cms(seed, B, H, W, C, n_inst=4, sigma=2.0, noise=0.02):
     for b in range(B):
         pts = rng.uniform(-1, [W + 1, H + 1], size=(n_inst, C, 2)).astype(np.float32)   # some near / past the border
         pts[0, 0] = [0.3, 0.2]                 # border peaks (crop_and_resize extrapolation cases)
-        pts[1, min(1, C - 1)] = [W - 1.2, H - 1.1]
+        pts[n_inst - 1, min(1, C - 1)] = [W - 1.2, H - 1.1]
         cm = np.zeros((H, W, C), np.float32)
         for p in pts:
             cm = np.maximum(cm, synth.make_confmaps(p, xv, yv, sigma))
