@@ -132,7 +132,7 @@ def cpu_oracle_fps(n_frames, weights, threads=None):
     PAF grouping (SciPy LSAP), on `n_frames` frames of the same workload."""
     import torch
     from oracle import convnet, paf_grouping as opg, peak_finding as opf, preprocess as opre
-    threads = threads or os.cpu_count()
+    threads = threads or best_threads(weights)
     torch.set_num_threads(threads)
     frames = make_frames(n_frames, 900)
     scorer = opg.PAFScorer(NODES, EDGES, pafs_stride=8)
@@ -147,6 +147,35 @@ def cpu_oracle_fps(n_frames, weights, threads=None):
     return n_frames / dt, threads
 
 
+_BEST_THREADS = None
+
+
+def best_threads(weights):
+    """All the host threads the CPU path can *use*: torch-CPU convs stop scaling (and regress) well
+    before 128 threads, so pick the fastest count among a few candidates (one forward each)."""
+    global _BEST_THREADS
+    if _BEST_THREADS is not None:
+        return _BEST_THREADS
+    import torch
+    from oracle import convnet, preprocess as opre
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count()
+    x = opre.preprocess(make_frames(1, 700), True, 1.0, 32)
+    best, best_t = None, None
+    for t in sorted({c for c in (8, 16, 32, 64, avail) if c <= avail}):
+        torch.set_num_threads(t)
+        convnet.model_forward(x, c4_spec(), weights)
+        t0 = time.perf_counter()
+        convnet.model_forward(x, c4_spec(), weights)
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best, best_t = t, dt
+    _BEST_THREADS = best
+    return best
+
+
 def run_reference(args):
     """--impl reference: TensorFlow (the reference's engine) is not installable offline, so the
     reference arm is the CPU restatement of its algorithm (oracle/), on all host cores."""
@@ -156,9 +185,9 @@ def run_reference(args):
     from sleap_b200.nn import architectures as A
     cm = A.compile_model(c4_spec(), 1)
     weights = A.make_synthetic_weights(cm, SEED)
-    threads = os.cpu_count()
     import torch
     from oracle import convnet, preprocess as opre
+    threads = best_threads(weights)
     torch.set_num_threads(threads)
     calib = make_frames(2, 500)
     cms0, pafs0 = convnet.model_forward(opre.preprocess(calib, True, 1.0, 32), c4_spec(), weights)

@@ -49,6 +49,8 @@ struct TcParams {
   const float* bn_scale;
   const float* bn_shift;
   int relu;
+  void* pool_out;               // optional fused MaxPool2D(2,2) output (same dtype as out)
+  int pool_H, pool_W, pool_Ctot, pool_coff;
   int a_slot_bytes, b_slot_bytes, n_a_slots, n_b_slots;
   int a_tx_bytes, b_tx_bytes;
   int layout_type;             // UMMA LayoutType: 2 = SW128, 4 = SW64, 6 = SW32
@@ -239,6 +241,28 @@ __global__ void __launch_bounds__(128) k_conv_tc(const __grid_constant__ CUtenso
       }
       v[j] = x;
     }
+    if (P.pool_out != nullptr) {
+      // fused MaxPool2D(2, strides=2): lanes hold pixels (ty = 2*warp + lane/16, tx = lane%16) of the
+      // tile, so the 2x2 partners are lane^1 (x) and lane^16 (y); even-x lanes of the upper row store.
+      float pv[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float a = v[j];
+        a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 1));
+        a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 16));
+        pv[j] = a;
+      }
+      if (valid && lane < 16 && (lane & 1) == 0 && n0 + c0 + 16 <= P.Cout) {
+        const int py = (y0 >> 1) + warp, px = (x0 >> 1) + (lane >> 1);
+        __half* pp = reinterpret_cast<__half*>(P.pool_out) + (((size_t)b * P.pool_H + py) * P.pool_W + px) * P.pool_Ctot +
+                     P.pool_coff + n0 + c0;
+        __half2 h[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(pv[2 * j], pv[2 * j + 1]);
+        reinterpret_cast<uint4*>(pp)[0] = *reinterpret_cast<uint4*>(&h[0]);
+        reinterpret_cast<uint4*>(pp)[1] = *reinterpret_cast<uint4*>(&h[4]);
+      }
+    }
     if (valid) {
       if (P.out_f32) {
         float* po = reinterpret_cast<float*>(P.out) + pix * P.out_Ctot + P.out_coff + n0 + c0;
@@ -365,6 +389,12 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
   P.bn_scale = (op.flags() & SB_OPF_BN) ? m->weights_dev + op.bn_scale_off() : nullptr;
   P.bn_shift = (op.flags() & SB_OPF_BN) ? m->weights_dev + op.bn_shift_off() : nullptr;
   P.relu = (op.flags() & SB_OPF_RELU) ? 1 : 0;
+  P.pool_out = nullptr;
+  if (op.kind() == SB_OPK_CONV && op.pool_buf() >= 0 && !ob.f32 && Cout % 16 == 0 &&
+      m->buffers[op.pool_buf()].C % 8 == 0 && op.pool_coff() % 8 == 0 && ib.H % 2 == 0 && ib.W % 2 == 0) {
+    const SbBuffer& pb = m->buffers[op.pool_buf()];
+    P.pool_out = pb.dev; P.pool_H = pb.H; P.pool_W = pb.W; P.pool_Ctot = pb.C; P.pool_coff = op.pool_coff();
+  }
   P.row_bytes = KC * 2;
   P.layout_type = KC == 64 ? 2 : (KC == 32 ? 4 : 6);
   P.a_tx_bytes = P.box_rows * TW * KC * 2;
@@ -408,6 +438,7 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
 
 int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m) {
   m->tc_plans.assign(m->ops.size(), nullptr);
+  m->skip_op.assign(m->ops.size(), 0);
   if (m->precision != 0) return 0;
   static bool attr_set = false;
   if (!attr_set) {
@@ -471,6 +502,9 @@ int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m) {
     }
     if (rc) { cudaFree(plan->w16); delete plan; return rc; }
     m->tc_plans[oi] = plan;
+    if (op.kind() == SB_OPK_CONV && op.pool_buf() >= 0 && oi + 1 < m->ops.size() &&
+        m->ops[oi + 1].kind() == SB_OPK_POOL && (m->ops[oi + 1].flags() & SB_OPF_FUSED_POOL))
+      if (plan->launches[0].P.pool_out != nullptr) m->skip_op[oi + 1] = 1;
   }
   return 0;
 }

@@ -140,16 +140,68 @@ int sb_model_configure(sb_handle_t h, int model_id, int max_batch, int H, int W,
 
 }  // extern "C"
 
+// First conv fused with preprocessing (fp16 path): returns the conv op index or -1.
+static int first_fusion_op(const SbModel* m, size_t pre_index) {
+  if (m->precision != 0 || getenv("SB_DISABLE_FIRST_FUSION")) return -1;
+  if (pre_index + 1 >= m->ops.size()) return -1;
+  const SbOp& pre = m->ops[pre_index];
+  const SbOp& cv = m->ops[pre_index + 1];
+  if (cv.kind() != SB_OPK_CONV || cv.in_buf() != pre.out_buf() || cv.k() != 3 || cv.stride() != 1) return -1;
+  if (pre.input_scale() != 1.0f) return -1;
+  const SbBuffer& ib = m->buffers[pre.out_buf()];
+  const SbBuffer& ob = m->buffers[cv.out_buf()];
+  if (m->Cin != ib.C || (ib.C != 1 && ib.C != 3) || cv.in_C() != ib.C) return -1;
+  if (ob.f32 || (cv.flags() & SB_OPF_BN) || ob.C % 8 || cv.out_coff() % 8) return -1;
+  const int co = cv.out_C();
+  if (!(co == 8 || co == 16 || co == 24 || co == 32 || co == 64)) return -1;
+  for (size_t i = pre_index + 2; i < m->ops.size(); ++i)      // nobody else may read the preprocessed frame
+    if (m->ops[i].kind() != SB_OPK_PREPROCESS && (m->ops[i].in_buf() == pre.out_buf() ||
+        (m->ops[i].kind() == SB_OPK_ADD && m->ops[i].in2_buf() == pre.out_buf()))) return -1;
+  return (int)pre_index + 1;
+}
+
+template <typename TI, int CIN>
+static void launch_first(int co, dim3 g, cudaStream_t s, const TI* img, int Hin, int Win, int Hnet, int Wnet, __half* out,
+                         int Ctot, int coff, const float* w, const float* b, int relu, int is_u8) {
+  dim3 blk(32, 8);
+  switch (co) {
+    case 8: k_conv_first<TI, CIN, 8><<<g, blk, 0, s>>>(img, Hin, Win, Hnet, Wnet, out, Ctot, coff, w, b, relu, is_u8); break;
+    case 16: k_conv_first<TI, CIN, 16><<<g, blk, 0, s>>>(img, Hin, Win, Hnet, Wnet, out, Ctot, coff, w, b, relu, is_u8); break;
+    case 24: k_conv_first<TI, CIN, 24><<<g, blk, 0, s>>>(img, Hin, Win, Hnet, Wnet, out, Ctot, coff, w, b, relu, is_u8); break;
+    case 32: k_conv_first<TI, CIN, 32><<<g, blk, 0, s>>>(img, Hin, Win, Hnet, Wnet, out, Ctot, coff, w, b, relu, is_u8); break;
+    default: k_conv_first<TI, CIN, 64><<<g, blk, 0, s>>>(img, Hin, Win, Hnet, Wnet, out, Ctot, coff, w, b, relu, is_u8); break;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 template <typename T>
 static int run_ops_t(sb_handle_s* h, SbModel* m, const void* frames_dev, int frames_are_u8, int B) {
   cudaStream_t s = h->stream;
+  int fused_first = -1;
   for (size_t oi = 0; oi < m->ops.size(); ++oi) {
     const SbOp& op = m->ops[oi];
     if (!m->prof_events.empty()) cudaEventRecord(m->prof_events[oi], s);
     SbBuffer& ob = m->buffers[op.out_buf()];
+    if (oi < m->skip_op.size() && m->skip_op[oi]) continue;     // 2x2 max-pool fused into the producing conv
+    if ((int)oi == fused_first) {
+      const float* Wt = m->weights_dev + op.w_off();
+      const float* bias = op.b_off() >= 0 ? m->weights_dev + op.b_off() : nullptr;
+      dim3 g((ob.W + 31) / 32, (ob.H + 7) / 8, B);
+      const int relu = (op.flags() & SB_OPF_RELU) ? 1 : 0;
+      // rows/cols beyond the resized frame (Hres, Wres) are the bottom/right zero padding
+      if (frames_are_u8) {
+        if (m->Cin == 1) launch_first<unsigned char, 1>(op.out_C(), g, s, (const unsigned char*)frames_dev, m->Hin, m->Win, ob.H, ob.W, (__half*)ob.dev, ob.C, op.out_coff(), Wt, bias, relu, 1);
+        else launch_first<unsigned char, 3>(op.out_C(), g, s, (const unsigned char*)frames_dev, m->Hin, m->Win, ob.H, ob.W, (__half*)ob.dev, ob.C, op.out_coff(), Wt, bias, relu, 1);
+      } else {
+        if (m->Cin == 1) launch_first<float, 1>(op.out_C(), g, s, (const float*)frames_dev, m->Hin, m->Win, ob.H, ob.W, (__half*)ob.dev, ob.C, op.out_coff(), Wt, bias, relu, 0);
+        else launch_first<float, 3>(op.out_C(), g, s, (const float*)frames_dev, m->Hin, m->Win, ob.H, ob.W, (__half*)ob.dev, ob.C, op.out_coff(), Wt, bias, relu, 0);
+      }
+      SB_CHECK_LAUNCH(h);
+      continue;
+    }
     switch (op.kind()) {
       case SB_OPK_PREPROCESS: {
+        if (sizeof(T) == 2 && (fused_first = first_fusion_op(m, oi)) >= 0) break;
         const size_t total = (size_t)B * ob.H * ob.W * ob.C;
         const int resize = op.input_scale() != 1.0f;
         int mode_ch = 0;

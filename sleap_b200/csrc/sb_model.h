@@ -15,7 +15,7 @@ enum {
   SB_OPK_PREPROCESS = 6,
   SB_OPK_COPY = 7,
 };
-enum { SB_OPF_RELU = 1, SB_OPF_BN = 2, SB_OPF_BILINEAR = 8 };
+enum { SB_OPF_RELU = 1, SB_OPF_BN = 2, SB_OPF_BILINEAR = 8, SB_OPF_FUSED_POOL = 16 };
 
 struct SbOp {
   int32_t w[SB_OP_WORDS];
@@ -35,6 +35,11 @@ struct SbOp {
   int b_off() const { return w[13]; }
   int bn_scale_off() const { return w[14]; }
   int bn_shift_off() const { return w[15]; }
+  // CONV: w[18] = buffer of a fused 2x2 max-pool output (-1: none), w[19] = its channel offset;
+  //       the POOL op that follows carries flag SB_OPF_FUSED_POOL and is skipped when the conv
+  //       ran on the tensor-core path.
+  int pool_buf() const { return w[18]; }
+  int pool_coff() const { return w[19]; }
   // PREPROCESS: w[16] = float bits of input_scale, w[17] = pad_to_stride
   float input_scale() const { float f; memcpy(&f, &w[16], 4); return f; }
   int pad_stride() const { return w[17]; }
@@ -61,6 +66,7 @@ struct SbModel {
   size_t act_bytes = 0;
   void* frames_dev = nullptr;
   std::vector<SbConvTcPlan*> tc_plans;  // per op (nullptr = direct path)
+  std::vector<char> skip_op;            // POOL ops fused into the producing tensor-core conv
   std::vector<cudaEvent_t> prof_events; // non-empty only inside sb_model_profile_ops
   // predictors
   SbPostWs ws;

@@ -379,6 +379,7 @@ def compile_model(spec: dict, input_channels: int, input_scale: float = 1.0, pad
     cm.layers = g.layers
 
     flops = 0.0
+    fused_pools = set()
     for idx, (kind, o) in enumerate(g.sym_ops):
         for (src, dbuf, dcoff) in copies_before.get(idx, []):
             cm.records.append(ol.copy_record(src.buf, src.coff, src.C, dbuf, dcoff))
@@ -386,9 +387,18 @@ def compile_model(spec: dict, input_channels: int, input_scale: float = 1.0, pad
             x, y = o["x"], o["y"]
             slot = cm._w_slots[o["name"]]
             bn = cm._w_slots[o["bn"]] if o["bn"] else None
+            # a 2x2 max-pool that directly follows is offered to the conv's epilogue (the POOL record
+            # stays in the list, flagged, and only runs when the conv took the CUDA-core path)
+            pool_buf, pool_coff = -1, 0
+            if idx + 1 < len(g.sym_ops) and g.sym_ops[idx + 1][0] == "pool" and g.sym_ops[idx + 1][1]["x"] is y \
+                    and not copies_before.get(idx + 1) and o["stride"] == 1 and not y.f32:
+                py = g.sym_ops[idx + 1][1]["y"]
+                pool_buf, pool_coff = py.buf, py.coff
+                fused_pools.add(idx + 1)
             cm.records.append(ol.conv_record(x.buf, x.coff, x.C, y.buf, y.coff, y.C, o["k"], o["stride"],
                                              relu=o["relu"], w_off=slot["w"], b_off=slot["b"],
-                                             bn_scale_off=bn["scale"] if bn else -1, bn_shift_off=bn["shift"] if bn else -1))
+                                             bn_scale_off=bn["scale"] if bn else -1, bn_shift_off=bn["shift"] if bn else -1,
+                                             pool_buf=pool_buf, pool_coff=pool_coff))
             flops += 2.0 * o["k"] * o["k"] * x.C * y.C / (y.stride ** 2)
         elif kind == "tconv":
             x, y = o["x"], o["y"]
@@ -396,7 +406,8 @@ def compile_model(spec: dict, input_channels: int, input_scale: float = 1.0, pad
             cm.records.append(ol.tconv_record(x.buf, x.coff, x.C, y.buf, y.coff, y.C, w_off=slot["w"], b_off=slot["b"]))
             flops += 2.0 * 9 * x.C * y.C / (x.stride ** 2)     # 2*9*Cin*Cout MACs per *input* pixel (Keras count)
         elif kind == "pool":
-            cm.records.append(ol.pool_record(o["x"].buf, o["x"].coff, o["x"].C, o["y"].buf, o["y"].coff))
+            cm.records.append(ol.pool_record(o["x"].buf, o["x"].coff, o["x"].C, o["y"].buf, o["y"].coff,
+                                             fused=idx in fused_pools))
         elif kind == "up":
             cm.records.append(ol.upsample_record(o["x"].buf, o["x"].coff, o["x"].C, o["y"].buf, o["y"].coff, o["bilinear"]))
         elif kind == "add":

@@ -142,4 +142,7 @@ def test_greedy_merge_semantics(pg):
         for mip in (0, 2):
             w = opg.group_instances_sample(*args, mip, 0.25)
             g = pg.group_instances_sample(*args, mip, 0.25)
-            assert_array_equal(g[0], w[0]); assert_array_equal(g[1], w[1]); assert_allclose(g[2], w[2], atol=1e-6)
+            ctx = f"trial={trial} mip={mip} counts={counts} ch={ch} me={me} ms={ms} md={md} msc={np.round(msc, 3)}\nGOT={g[0]}\nWANT={w[0]}"
+            assert g[0].shape == w[0].shape, ctx
+            assert np.array_equal(np.nan_to_num(g[0], nan=-1), np.nan_to_num(w[0], nan=-1)), ctx
+            assert_array_equal(g[1], w[1]); assert_allclose(g[2], w[2], atol=1e-6)
