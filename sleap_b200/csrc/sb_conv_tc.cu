@@ -55,6 +55,11 @@ struct TcParams {
   int a_tx_bytes, b_tx_bytes;
   int layout_type;             // UMMA LayoutType: 2 = SW128, 4 = SW64, 6 = SW32
   int row_bytes;               // KC * 2
+  // persistent variant (weights resident in shared memory, double-buffered TMEM accumulators)
+  int persistent;
+  int tiles_per_img, n_tiles_total;
+  int n_used_taps, used_taps[9], slot_of_tap[9];
+  int w_slot_bytes;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -125,6 +130,94 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int row_bytes, int
   return d;
 }
 
+// bias / BN scale / BN shift of output channels [n0, n0 + N) -> shared memory (zeros / ones beyond Cout)
+__device__ __forceinline__ void stage_params(const TcParams& P, float* s_par, int n0) {
+  for (int i = threadIdx.x; i < P.N; i += blockDim.x) {
+    const int co = n0 + i;
+    const bool ok = co < P.Cout;
+    s_par[i] = (ok && P.bias) ? P.bias[co] : 0.f;
+    s_par[P.N + i] = (ok && P.bn_scale) ? P.bn_scale[co] : 1.f;
+    s_par[2 * P.N + i] = (ok && P.bn_shift) ? P.bn_shift[co] : 0.f;
+  }
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Shared epilogue: 16 accumulator columns of this thread's pixel -> bias / ReLU / BN -> stores
+// (+ fused 2x2 max-pool).  q = TMEM lane quadrant of the warp (rows 32q .. 32q+31 of the tile).
+__device__ __forceinline__ void tc_epilogue_cols(const TcParams& P, const float* __restrict__ s_par, const uint32_t (&r)[16],
+                                                 int n0, int c0, bool valid, size_t pix, int b, int x0, int y0, int q, int lane) {
+  // s_par: [3][N] = bias | bn_scale | bn_shift of this N tile, staged in shared memory once per CTA
+  float v[16];
+  const float4* pb = reinterpret_cast<const float4*>(s_par + c0);
+  const float4* ps = reinterpret_cast<const float4*>(s_par + P.N + c0);
+  const float4* ph = reinterpret_cast<const float4*>(s_par + 2 * P.N + c0);
+#pragma unroll
+  for (int j4 = 0; j4 < 4; ++j4) {
+    const float4 bb = pb[j4];
+    v[4 * j4 + 0] = __uint_as_float(r[4 * j4 + 0]) + bb.x;
+    v[4 * j4 + 1] = __uint_as_float(r[4 * j4 + 1]) + bb.y;
+    v[4 * j4 + 2] = __uint_as_float(r[4 * j4 + 2]) + bb.z;
+    v[4 * j4 + 3] = __uint_as_float(r[4 * j4 + 3]) + bb.w;
+  }
+  if (P.relu) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  if (P.bn_scale != nullptr) {
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) {
+      const float4 sc = ps[j4], sh = ph[j4];
+      v[4 * j4 + 0] = v[4 * j4 + 0] * sc.x + sh.x;
+      v[4 * j4 + 1] = v[4 * j4 + 1] * sc.y + sh.y;
+      v[4 * j4 + 2] = v[4 * j4 + 2] * sc.z + sh.z;
+      v[4 * j4 + 3] = v[4 * j4 + 3] * sc.w + sh.w;
+    }
+  }
+  if (P.pool_out != nullptr) {
+    float pv[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float a = v[j];
+      a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 1));
+      a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 16));
+      pv[j] = a;
+    }
+    if (valid && lane < 16 && (lane & 1) == 0 && n0 + c0 + 16 <= P.Cout) {
+      const int py = (y0 >> 1) + q, px = (x0 >> 1) + (lane >> 1);
+      __half* pp = reinterpret_cast<__half*>(P.pool_out) + (((size_t)b * P.pool_H + py) * P.pool_W + px) * P.pool_Ctot +
+                   P.pool_coff + n0 + c0;
+      __half2 h[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(pv[2 * j], pv[2 * j + 1]);
+      reinterpret_cast<uint4*>(pp)[0] = *reinterpret_cast<uint4*>(&h[0]);
+      reinterpret_cast<uint4*>(pp)[1] = *reinterpret_cast<uint4*>(&h[4]);
+    }
+  }
+  if (!valid) return;
+  if (P.out_f32) {
+    float* po = reinterpret_cast<float*>(P.out) + pix * P.out_Ctot + P.out_coff + n0 + c0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (n0 + c0 + j < P.Cout) po[j] = v[j];
+  } else {
+    __half* po = reinterpret_cast<__half*>(P.out) + pix * P.out_Ctot + P.out_coff + n0 + c0;
+    if (n0 + c0 + 16 <= P.Cout) {
+      __half2 h[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+      reinterpret_cast<uint4*>(po)[0] = *reinterpret_cast<uint4*>(&h[0]);
+      reinterpret_cast<uint4*>(po)[1] = *reinterpret_cast<uint4*>(&h[4]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (n0 + c0 + j < P.Cout) po[j] = __float2half_rn(v[j]);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(128) k_conv_tc(const __grid_constant__ CUtensorMap mapA,
                                                  const __grid_constant__ CUtensorMap mapB,
                                                  const __grid_constant__ TcParams P) {
@@ -140,12 +233,14 @@ __global__ void __launch_bounds__(128) k_conv_tc(const __grid_constant__ CUtenso
   uint64_t* emptyB = fullB + P.n_b_slots;
   uint64_t* accum = emptyB + P.n_b_slots;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+  float* s_par = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~(uintptr_t)15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x;
   const int x0 = (tile % P.tiles_x) * TW, y0 = (tile / P.tiles_x) * TH;
   const int n0 = blockIdx.y * P.N;
   const int b = blockIdx.z;
+  stage_params(P, s_par, n0);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < P.n_a_slots; ++i) { mbar_init(smem_u32(fullA + i), 1); mbar_init(smem_u32(emptyA + i), 1); }
@@ -229,65 +324,139 @@ __global__ void __launch_bounds__(128) k_conv_tc(const __grid_constant__ CUtenso
     uint32_t r[16];
     tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    float v[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int co = n0 + c0 + j;
-      float x = __uint_as_float(r[j]);
-      if (co < P.Cout) {
-        if (P.bias) x += P.bias[co];
-        if (P.relu) x = fmaxf(x, 0.f);
-        if (P.bn_scale) x = x * P.bn_scale[co] + P.bn_shift[co];
-      }
-      v[j] = x;
-    }
-    if (P.pool_out != nullptr) {
-      // fused MaxPool2D(2, strides=2): lanes hold pixels (ty = 2*warp + lane/16, tx = lane%16) of the
-      // tile, so the 2x2 partners are lane^1 (x) and lane^16 (y); even-x lanes of the upper row store.
-      float pv[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float a = v[j];
-        a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 1));
-        a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 16));
-        pv[j] = a;
-      }
-      if (valid && lane < 16 && (lane & 1) == 0 && n0 + c0 + 16 <= P.Cout) {
-        const int py = (y0 >> 1) + warp, px = (x0 >> 1) + (lane >> 1);
-        __half* pp = reinterpret_cast<__half*>(P.pool_out) + (((size_t)b * P.pool_H + py) * P.pool_W + px) * P.pool_Ctot +
-                     P.pool_coff + n0 + c0;
-        __half2 h[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(pv[2 * j], pv[2 * j + 1]);
-        reinterpret_cast<uint4*>(pp)[0] = *reinterpret_cast<uint4*>(&h[0]);
-        reinterpret_cast<uint4*>(pp)[1] = *reinterpret_cast<uint4*>(&h[4]);
-      }
-    }
-    if (valid) {
-      if (P.out_f32) {
-        float* po = reinterpret_cast<float*>(P.out) + pix * P.out_Ctot + P.out_coff + n0 + c0;
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (n0 + c0 + j < P.Cout) po[j] = v[j];
-      } else {
-        __half* po = reinterpret_cast<__half*>(P.out) + pix * P.out_Ctot + P.out_coff + n0 + c0;
-        if (n0 + c0 + 16 <= P.Cout) {
-          uint4 q0, q1;
-          __half2 h[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-          q0 = *reinterpret_cast<uint4*>(&h[0]);
-          q1 = *reinterpret_cast<uint4*>(&h[4]);
-          reinterpret_cast<uint4*>(po)[0] = q0;
-          reinterpret_cast<uint4*>(po)[1] = q1;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (n0 + c0 + j < P.Cout) po[j] = __float2half_rn(v[j]);
+    tc_epilogue_cols(P, s_par, r, n0, c0, valid, pix, b, x0, y0, warp, lane);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P.tmem_cols) : "memory");
+  }
+}
+
+
+// Persistent, warp-specialised variant for layers whose whole filter bank fits in shared memory:
+// each CTA loads the weights once, then walks output tiles; warp 0 = TMA producer (activation
+// halo tiles), warp 1 = MMA issuer, warps 2..5 = epilogue.  Two TMEM accumulator stages let the
+// epilogue of tile i overlap the MMAs of tile i+1 and the TMA loads of tile i+2.
+__global__ void __launch_bounds__(192) k_conv_tc_persist(const __grid_constant__ CUtensorMap mapA,
+                                                         const __grid_constant__ CUtensorMap mapB,
+                                                         const __grid_constant__ TcParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int n_wslots = P.n_chunks * P.n_used_taps;
+  uint8_t* w_res = base;
+  uint8_t* a_ring = w_res + (size_t)n_wslots * P.w_slot_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(a_ring + (size_t)P.n_a_slots * P.a_slot_bytes);
+  uint64_t* fullA = bars;
+  uint64_t* emptyA = fullA + P.n_a_slots;
+  uint64_t* tfull = emptyA + P.n_a_slots;     // [2]
+  uint64_t* tempty = tfull + 2;               // [2]
+  uint64_t* wbar = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+  float* s_par = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~(uintptr_t)15);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  stage_params(P, s_par, 0);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < P.n_a_slots; ++i) { mbar_init(smem_u32(fullA + i), 1); mbar_init(smem_u32(emptyA + i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(tfull + i), 1); mbar_init(smem_u32(tempty + i), 4); }
+    mbar_init(smem_u32(wbar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(P.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    mbar_expect_tx(smem_u32(wbar), (uint32_t)(n_wslots * P.b_tx_bytes));
+    for (int ch = 0; ch < P.n_chunks; ++ch)
+      for (int u = 0; u < P.n_used_taps; ++u)
+        tma_load_3d(smem_u32(w_res + (size_t)(ch * P.n_used_taps + u) * P.w_slot_bytes), &mapB, smem_u32(wbar), ch * P.KC, 0,
+                    P.used_taps[u]);
+    int sa = 0;
+    uint32_t pha = 0;
+    for (int t = blockIdx.x; t < P.n_tiles_total; t += gridDim.x) {
+      const int b = t / P.tiles_per_img, r = t - b * P.tiles_per_img;
+      const int y0 = (r / P.tiles_x) * TH, x0 = (r % P.tiles_x) * TW;
+      for (int ch = 0; ch < P.n_chunks; ++ch)
+        for (int g = 0; g < P.n_groups; ++g) {
+          mbar_wait(smem_u32(emptyA + sa), pha ^ 1, 11);
+          mbar_expect_tx(smem_u32(fullA + sa), (uint32_t)P.a_tx_bytes);
+          tma_load_4d(smem_u32(a_ring + (size_t)sa * P.a_slot_bytes), &mapA, smem_u32(fullA + sa), ch * P.KC,
+                      x0 + P.groups[g].dx, y0 + P.dy0, b);
+          if (++sa == P.n_a_slots) { sa = 0; pha ^= 1; }
         }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------ MMA issuer --------------------------------
+    mbar_wait(smem_u32(wbar), 0, 12);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    int sa = 0, stage = 0;
+    uint32_t pha = 0, eph[2] = {0, 0};
+    const int ksteps = P.KC / 16;
+    for (int t = blockIdx.x; t < P.n_tiles_total; t += gridDim.x) {
+      mbar_wait(smem_u32(tempty + stage), eph[stage] ^ 1, 13);
+      eph[stage] ^= 1;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d_tmem = tmem_base + (uint32_t)(stage * P.N);
+      uint32_t first = 1;
+      for (int ch = 0; ch < P.n_chunks; ++ch)
+        for (int g = 0; g < P.n_groups; ++g) {
+          mbar_wait(smem_u32(fullA + sa), pha, 14);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_base = smem_u32(a_ring + (size_t)sa * P.a_slot_bytes);
+          for (int tp = 0; tp < P.groups[g].n_taps; ++tp) {
+            const int slot = ch * P.n_used_taps + P.slot_of_tap[P.groups[g].taps[tp].w_tap];
+            const uint32_t b_base = smem_u32(w_res + (size_t)slot * P.w_slot_bytes);
+            const uint32_t a_tap = a_base + (uint32_t)(P.groups[g].taps[tp].row_off * TW * P.row_bytes);
+            for (int k = 0; k < ksteps; ++k) {
+              tc_mma_f16(d_tmem, make_desc(a_tap + k * 32, P.row_bytes, P.layout_type),
+                         make_desc(b_base + k * 32, P.row_bytes, P.layout_type), P.idesc, first ? 0u : 1u);
+              first = 0;
+            }
+          }
+          tc_commit(smem_u32(emptyA + sa));
+          if (++sa == P.n_a_slots) { sa = 0; pha ^= 1; }
+        }
+      tc_commit(smem_u32(tfull + stage));
+      stage ^= 1;
+    }
+  } else if (warp >= 2) {
+    // ------------------------------ epilogue warps ----------------------------
+    const int q = warp & 3;                       // TMEM lane quadrant this warp may access
+    int stage = 0;
+    uint32_t fph[2] = {0, 0};
+    for (int t = blockIdx.x; t < P.n_tiles_total; t += gridDim.x) {
+      const int b = t / P.tiles_per_img, r = t - b * P.tiles_per_img;
+      const int y0 = (r / P.tiles_x) * TH, x0 = (r % P.tiles_x) * TW;
+      mbar_wait(smem_u32(tfull + stage), fph[stage], 15);
+      fph[stage] ^= 1;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int m = q * 32 + lane;
+      const int iy = y0 + m / TW, ix = x0 + m % TW;
+      const bool valid = (iy < P.H) && (ix < P.W);
+      const size_t pix = ((size_t)b * P.out_H + (iy * P.oy_mul + P.oy_add)) * P.out_W + (ix * P.ox_mul + P.ox_add);
+      for (int c0 = 0; c0 < P.N; c0 += 16) {
+        uint32_t r16[16];
+        tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(stage * P.N + c0), r16);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tc_epilogue_cols(P, s_par, r16, 0, c0, valid, pix, b, x0, y0, q, lane);
       }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(tempty + stage));
+      stage ^= 1;
     }
   }
+  __syncwarp();
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) {
@@ -314,9 +483,14 @@ EncodeTiledFn get_encode() {
 
 struct TcLaunch {
   CUtensorMap mapA, mapB;
-  TcParams P;
+  TcParams P;          // streaming variant (one CTA per tile, weights streamed through a TMA ring)
   dim3 grid;
   size_t smem;
+  bool has_persist;    // persistent variant available (filter bank resident in shared memory)
+  TcParams PP;
+  size_t smem_p;
+  int occ;
+  int use_persist;     // chosen at configure time by timing both variants on the device
 };
 
 }  // namespace
@@ -408,9 +582,49 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
   while ((size_t)P.n_a_slots * P.a_slot_bytes + (size_t)P.n_b_slots * P.b_slot_bytes > 200 * 1024 && P.n_b_slots > 2) P.n_b_slots--;
   while ((size_t)P.n_a_slots * P.a_slot_bytes + (size_t)P.n_b_slots * P.b_slot_bytes > 200 * 1024 && P.n_a_slots > 2) P.n_a_slots--;
   L.smem = (size_t)P.n_a_slots * P.a_slot_bytes + (size_t)P.n_b_slots * P.b_slot_bytes + 1024 /*align slack*/ +
-           (size_t)(2 * P.n_a_slots + 2 * P.n_b_slots + 1) * 8 + 16;
+           (size_t)(2 * P.n_a_slots + 2 * P.n_b_slots + 1) * 8 + 64 + 3 * 256 * sizeof(float);
   L.grid = dim3(P.tiles_x * tiles_y, plan->Cout_pad / N, 1 /* z = batch, set at launch */);
-
+  // persistent variant when the whole filter bank of this launch fits in shared memory
+  P.persistent = 0;
+  P.tiles_per_img = P.tiles_x * tiles_y;
+  L.has_persist = false;
+  {
+    int used[9], n_used = 0, slot_of[9];
+    for (int i = 0; i < 9; ++i) slot_of[i] = -1;
+    for (int g = 0; g < n_groups; ++g)
+      for (int t = 0; t < groups[g].n_taps; ++t) {
+        const int wt = groups[g].taps[t].w_tap;
+        if (slot_of[wt] < 0) { slot_of[wt] = n_used; used[n_used++] = wt; }
+      }
+    const size_t w_bytes = (size_t)P.n_chunks * n_used * P.b_slot_bytes;
+    const size_t budget = 196 * 1024;
+    if (!getenv("SB_DISABLE_PERSISTENT") && plan->Cout_pad == N && 2 * N <= 512 &&
+        w_bytes + 2 * (size_t)P.a_slot_bytes <= budget) {
+      TcParams& Q = L.PP;
+      Q = P;
+      Q.persistent = 1;
+      Q.n_used_taps = n_used;
+      for (int i = 0; i < 9; ++i) { Q.used_taps[i] = i < n_used ? used[i] : 0; Q.slot_of_tap[i] = slot_of[i]; }
+      Q.w_slot_bytes = P.b_slot_bytes;
+      // activation ring: two tiles of look-ahead (2 x n_groups halo tiles per chunk) when it fits
+      int na = (int)((budget - w_bytes) / P.a_slot_bytes);
+      Q.n_a_slots = std::max(2, std::min(na, std::max(6, 2 * n_groups)));
+      int c2 = 32;
+      while (c2 < 2 * N) c2 <<= 1;
+      Q.tmem_cols = c2;
+      L.smem_p = w_bytes + (size_t)Q.n_a_slots * P.a_slot_bytes + 1024 + (size_t)(2 * Q.n_a_slots + 5) * 8 + 64 + 3 * 256 * sizeof(float);
+      cudaFuncAttributes fa;
+      int occ = 1;
+      if (cudaFuncGetAttributes(&fa, k_conv_tc_persist) == cudaSuccess) {
+        const int by_regs = 65536 / std::max(1, fa.numRegs * 192);
+        const int by_smem = (int)((227 * 1024) / (L.smem_p + fa.sharedSizeBytes + 1024));
+        occ = std::max(1, std::min(std::min(by_regs, by_smem), std::min(512 / c2, 8)));
+      }
+      L.occ = occ;
+      L.has_persist = true;
+    }
+  }
+  L.use_persist = 0;
   // A: NHWC view (slice channels, W, H, batch)
   {
     cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)ib.W, (cuuint64_t)ib.H, (cuuint64_t)m->B};
@@ -436,6 +650,8 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
   return 0;
 }
 
+int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m);
+
 int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m) {
   m->tc_plans.assign(m->ops.size(), nullptr);
   m->skip_op.assign(m->ops.size(), 0);
@@ -443,6 +659,7 @@ int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m) {
   static bool attr_set = false;
   if (!attr_set) {
     SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     attr_set = true;
   }
   for (size_t oi = 0; oi < m->ops.size(); ++oi) {
@@ -506,15 +723,67 @@ int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m) {
         m->ops[oi + 1].kind() == SB_OPK_POOL && (m->ops[oi + 1].flags() & SB_OPF_FUSED_POOL))
       if (plan->launches[0].P.pool_out != nullptr) m->skip_op[oi + 1] = 1;
   }
+  return sb_conv_tc_autotune(h, m);
+}
+
+static void launch_variant(sb_handle_s* h, TcLaunch& L, int B, bool persist) {
+  if (persist) {
+    TcParams P = L.PP;
+    P.n_tiles_total = P.tiles_per_img * B;
+    const int grid = std::max(1, std::min(P.n_tiles_total, h->sm_count * L.occ));
+    k_conv_tc_persist<<<grid, 192, L.smem_p, h->stream>>>(L.mapA, L.mapB, P);
+  } else {
+    dim3 g = L.grid;
+    g.z = B;
+    k_conv_tc<<<g, 128, L.smem, h->stream>>>(L.mapA, L.mapB, L.P);
+  }
+}
+
+// Pick, per launch, the faster of the two kernel variants by timing them on the device (buffers
+// are already allocated; their contents do not matter for timing).
+int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
+  if (getenv("SB_DISABLE_AUTOTUNE")) {
+    for (SbConvTcPlan* plan : m->tc_plans)
+      if (plan) for (TcLaunch& L : plan->launches) L.use_persist = L.has_persist ? 1 : 0;
+    return 0;
+  }
+  cudaEvent_t e0, e1;
+  SB_CUDA(h, cudaEventCreate(&e0));
+  SB_CUDA(h, cudaEventCreate(&e1));
+  const bool dbg = getenv("SB_DEBUG") != nullptr;
+  for (size_t oi = 0; oi < m->tc_plans.size(); ++oi) {
+    SbConvTcPlan* plan = m->tc_plans[oi];
+    if (!plan) continue;
+    for (TcLaunch& L : plan->launches) {
+      if (!L.has_persist) continue;
+      float best[2] = {1e30f, 1e30f};
+      for (int v = 0; v < 2; ++v)
+        for (int rep = 0; rep < 3; ++rep) {
+          cudaEventRecord(e0, h->stream);
+          launch_variant(h, L, m->B, v == 1);
+          cudaEventRecord(e1, h->stream);
+          cudaError_t e = cudaStreamSynchronize(h->stream);
+          if (e != cudaSuccess) return sb_fail(h, SB_ERR_CUDA, "autotune launch failed: %s", cudaGetErrorString(e));
+          float ms = 0.f;
+          cudaEventElapsedTime(&ms, e0, e1);
+          if (rep > 0) best[v] = std::min(best[v], ms);
+        }
+      L.use_persist = best[1] < best[0] ? 1 : 0;
+      if (dbg)
+        fprintf(stderr, "[sb_conv_tc] op %zu Cin=%d N=%d %dx%d: stream %.1f us, persist %.1f us (occ %d, %d A slots) -> %s\n", oi,
+                L.P.n_chunks * L.P.KC, L.P.N, L.P.H, L.P.W, best[0] * 1e3f, best[1] * 1e3f, L.occ, L.PP.n_a_slots,
+                L.use_persist ? "persist" : "stream");
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
   return 0;
 }
 
 int sb_conv_tc_launch(sb_handle_s* h, SbModel* m, int op_index, int B) {
   SbConvTcPlan* plan = m->tc_plans[op_index];
   for (TcLaunch& L : plan->launches) {
-    dim3 g = L.grid;
-    g.z = B;
-    k_conv_tc<<<g, 128, L.smem, h->stream>>>(L.mapA, L.mapB, L.P);
+    launch_variant(h, L, B, L.use_persist != 0);
     SB_CHECK_LAUNCH(h);
   }
   return 0;

@@ -576,8 +576,9 @@ __global__ void __launch_bounds__(128) k_group(
   const int b = blockIdx.x;
   int* assign = s_assign;
   int* idrank = s_assign + C * K;    // instance id -> rank (ids < C*K)
+  int* order = s_assign + 2 * C * K; // dict insertion sequence of each (node, peak) key
   __shared__ int s_ninst;
-  for (int t = threadIdx.x; t < C * K; t += blockDim.x) { assign[t] = -1; idrank[t] = -1; }
+  for (int t = threadIdx.x; t < C * K; t += blockDim.x) { assign[t] = -1; idrank[t] = -1; order[t] = -1; }
   float* op = inst_peaks + (size_t)b * max_inst * C * 2;
   float* ov = inst_vals + (size_t)b * max_inst * C;
   float* os = inst_scores + (size_t)b * max_inst;
@@ -587,6 +588,7 @@ __global__ void __launch_bounds__(128) k_group(
   __syncthreads();
   if (threadIdx.x == 0) {
     const int n_slots = C * K;
+    int seq = 0;
     for (int se = 0; se < n_sorted; ++se) {
       const int e = sorted_edges[se];
       const int sn = edges[2 * e], dn = edges[2 * e + 1];
@@ -601,8 +603,11 @@ __global__ void __launch_bounds__(128) k_group(
           for (int t = 0; t < n_slots; ++t) mx = max(mx, assign[t]);
           assign[sid] = mx + 1;
           assign[did] = mx + 1;
+          order[sid] = seq++;                 // src key is inserted before dst (paf_grouping.py:853-854)
+          order[did] = seq++;
         } else if (si >= 0 && di < 0) {
           assign[did] = si;
+          order[did] = seq++;
         } else if (si >= 0 && di >= 0) {
           assign[did] = si;
           // node-type sets of both instances AFTER the re-assignment of dst
@@ -669,6 +674,13 @@ __global__ void __launch_bounds__(128) k_group(
     if (rk >= keep) continue;
     const int node = t / K, k = t - node * K;
     if (k >= min(node_cnt[b * C + node], K)) continue;
+    // two peaks of one node type can land in the same instance (skeletons where a node is the
+    // destination of several edges); the reference fills the output in dict insertion order, so the
+    // key inserted last wins (paf_grouping.py:973-979)
+    bool later = false;
+    for (int k2 = 0; k2 < K; ++k2)
+      later |= (assign[node * K + k2] == a && order[node * K + k2] > order[t]);
+    if (later) continue;
     const int pi = node_peaks[((size_t)b * C + node) * K + k];
     float x = pk[2 * pi], y = pk[2 * pi + 1];
     if (input_scale != 1.0f) {  // inference.py:2980-2984
@@ -947,7 +959,7 @@ int sbk_score_match(sb_handle_s* h, const float* pafs, int B, int Hp, int Wp, in
 int sbk_group(sb_handle_s* h, int B, int n_nodes, int min_instance_peaks, float min_line_scores,
               float input_scale, SbPostWs& ws) {
   const int K = ws.max_node_peaks;
-  const size_t sm = (size_t)2 * n_nodes * K * sizeof(int);
+  const size_t sm = (size_t)3 * n_nodes * K * sizeof(int);
   if (sm > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return sb_fail(h, SB_ERR_CUDA, "group smem %zu: %s", sm, cudaGetErrorString(e));
