@@ -218,6 +218,7 @@ __device__ __forceinline__ void tc_epilogue_cols(const TcParams& P, const float*
   }
 }
 
+template <int KSTEPS>
 __global__ void __launch_bounds__(128) k_conv_tc(const __grid_constant__ CUtensorMap mapA,
                                                  const __grid_constant__ CUtensorMap mapB,
                                                  const __grid_constant__ TcParams P) {
@@ -279,36 +280,43 @@ __global__ void __launch_bounds__(128) k_conv_tc(const __grid_constant__ CUtenso
         if (++sa == P.n_a_slots) { sa = 0; pha ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
+    // The whole warp walks the loop (all values are warp-uniform, so descriptors live in uniform
+    // registers); only lane 0 issues tcgen05.mma / tcgen05.commit.
     int sa = 0, sb = 0;
     uint32_t pha = 0, phb = 0;
-    uint32_t first = 1;
-    const int ksteps = P.KC / 16;
+    const uint64_t desc_hi = make_desc(0, P.row_bytes, P.layout_type);
     for (int ch = 0; ch < P.n_chunks; ++ch) {
-      for (int g = 0; g < P.n_groups; ++g) {
+#pragma unroll
+      for (int g = 0; g < MAX_GROUPS; ++g) {
+        if (g >= P.n_groups) break;
         mbar_wait(smem_u32(fullA + sa), pha, 3);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a_base = smem_u32(a_ring + (size_t)sa * P.a_slot_bytes);
-        for (int t = 0; t < P.groups[g].n_taps; ++t) {
+#pragma unroll
+        for (int t = 0; t < MAX_TAPS; ++t) {
+          if (t >= P.groups[g].n_taps) break;
           mbar_wait(smem_u32(fullB + sb), phb, 4);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t b_base = smem_u32(b_ring + (size_t)sb * P.b_slot_bytes);
-          const uint32_t a_tap = a_base + (uint32_t)(P.groups[g].taps[t].row_off * TW * P.row_bytes);
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t da = make_desc(a_tap + k * 32, P.row_bytes, P.layout_type);
-            const uint64_t db = make_desc(b_base + k * 32, P.row_bytes, P.layout_type);
-            tc_mma_f16(tmem_base, da, db, P.idesc, first ? 0u : 1u);
-            first = 0;
+          const uint64_t da = desc_hi + (uint64_t)((a_base + (uint32_t)(P.groups[g].taps[t].row_off * TW * P.row_bytes)) >> 4);
+          const uint64_t db = desc_hi + (uint64_t)(b_base >> 4);
+          if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < KSTEPS; ++k)
+              tc_mma_f16(tmem_base, da + 2 * k, db + 2 * k, P.idesc, (ch | g | t | k) ? 1u : 0u);
+            tc_commit(smem_u32(emptyB + sb));
           }
-          tc_commit(smem_u32(emptyB + sb));
+          __syncwarp();
           if (++sb == P.n_b_slots) { sb = 0; phb ^= 1; }
         }
-        tc_commit(smem_u32(emptyA + sa));
+        if (lane == 0) tc_commit(smem_u32(emptyA + sa));
+        __syncwarp();
         if (++sa == P.n_a_slots) { sa = 0; pha ^= 1; }
       }
     }
-    tc_commit(smem_u32(accum));
+    if (lane == 0) tc_commit(smem_u32(accum));
   }
   __syncwarp();
 
@@ -338,6 +346,7 @@ __global__ void __launch_bounds__(128) k_conv_tc(const __grid_constant__ CUtenso
 // each CTA loads the weights once, then walks output tiles; warp 0 = TMA producer (activation
 // halo tiles), warp 1 = MMA issuer, warps 2..5 = epilogue.  Two TMEM accumulator stages let the
 // epilogue of tile i overlap the MMAs of tile i+1 and the TMA loads of tile i+2.
+template <int KSTEPS>
 __global__ void __launch_bounds__(192) k_conv_tc_persist(const __grid_constant__ CUtensorMap mapA,
                                                          const __grid_constant__ CUtensorMap mapB,
                                                          const __grid_constant__ TcParams P) {
@@ -395,38 +404,47 @@ __global__ void __launch_bounds__(192) k_conv_tc_persist(const __grid_constant__
           if (++sa == P.n_a_slots) { sa = 0; pha ^= 1; }
         }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
+    // warp-uniform loop (descriptors in uniform registers); lane 0 issues the tcgen05 instructions
     mbar_wait(smem_u32(wbar), 0, 12);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     int sa = 0, stage = 0;
-    uint32_t pha = 0, eph[2] = {0, 0};
-    const int ksteps = P.KC / 16;
+    uint32_t pha = 0, eph0 = 0, eph1 = 0;
+    const uint64_t desc_hi = make_desc(0, P.row_bytes, P.layout_type);
+    const uint32_t w_base = smem_u32(w_res);
     for (int t = blockIdx.x; t < P.n_tiles_total; t += gridDim.x) {
-      mbar_wait(smem_u32(tempty + stage), eph[stage] ^ 1, 13);
-      eph[stage] ^= 1;
+      const uint32_t eph = stage ? eph1 : eph0;
+      mbar_wait(smem_u32(tempty + stage), eph ^ 1, 13);
+      if (stage) eph1 ^= 1; else eph0 ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t d_tmem = tmem_base + (uint32_t)(stage * P.N);
-      uint32_t first = 1;
-      for (int ch = 0; ch < P.n_chunks; ++ch)
-        for (int g = 0; g < P.n_groups; ++g) {
+      for (int ch = 0; ch < P.n_chunks; ++ch) {
+#pragma unroll
+        for (int g = 0; g < MAX_GROUPS; ++g) {
+          if (g >= P.n_groups) break;
           mbar_wait(smem_u32(fullA + sa), pha, 14);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_base = smem_u32(a_ring + (size_t)sa * P.a_slot_bytes);
-          for (int tp = 0; tp < P.groups[g].n_taps; ++tp) {
+#pragma unroll
+          for (int tp = 0; tp < MAX_TAPS; ++tp) {
+            if (tp >= P.groups[g].n_taps) break;
             const int slot = ch * P.n_used_taps + P.slot_of_tap[P.groups[g].taps[tp].w_tap];
-            const uint32_t b_base = smem_u32(w_res + (size_t)slot * P.w_slot_bytes);
-            const uint32_t a_tap = a_base + (uint32_t)(P.groups[g].taps[tp].row_off * TW * P.row_bytes);
-            for (int k = 0; k < ksteps; ++k) {
-              tc_mma_f16(d_tmem, make_desc(a_tap + k * 32, P.row_bytes, P.layout_type),
-                         make_desc(b_base + k * 32, P.row_bytes, P.layout_type), P.idesc, first ? 0u : 1u);
-              first = 0;
+            const uint64_t da = desc_hi + (uint64_t)((a_base + (uint32_t)(P.groups[g].taps[tp].row_off * TW * P.row_bytes)) >> 4);
+            const uint64_t db = desc_hi + (uint64_t)((w_base + (uint32_t)(slot * P.w_slot_bytes)) >> 4);
+            if (lane == 0) {
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k)
+                tc_mma_f16(d_tmem, da + 2 * k, db + 2 * k, P.idesc, (ch | g | tp | k) ? 1u : 0u);
             }
           }
-          tc_commit(smem_u32(emptyA + sa));
+          if (lane == 0) tc_commit(smem_u32(emptyA + sa));
+          __syncwarp();
           if (++sa == P.n_a_slots) { sa = 0; pha ^= 1; }
         }
-      tc_commit(smem_u32(tfull + stage));
+      }
+      if (lane == 0) tc_commit(smem_u32(tfull + stage));
+      __syncwarp();
       stage ^= 1;
     }
   } else if (warp >= 2) {
@@ -615,7 +633,7 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
       L.smem_p = w_bytes + (size_t)Q.n_a_slots * P.a_slot_bytes + 1024 + (size_t)(2 * Q.n_a_slots + 5) * 8 + 64 + 3 * 256 * sizeof(float);
       cudaFuncAttributes fa;
       int occ = 1;
-      if (cudaFuncGetAttributes(&fa, k_conv_tc_persist) == cudaSuccess) {
+      if (cudaFuncGetAttributes(&fa, k_conv_tc_persist<4>) == cudaSuccess) {
         const int by_regs = 65536 / std::max(1, fa.numRegs * 192);
         const int by_smem = (int)((227 * 1024) / (L.smem_p + fa.sharedSizeBytes + 1024));
         occ = std::max(1, std::min(std::min(by_regs, by_smem), std::min(512 / c2, 8)));
@@ -658,8 +676,12 @@ int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m) {
   if (m->precision != 0) return 0;
   static bool attr_set = false;
   if (!attr_set) {
-    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_persist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_persist<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_persist<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     attr_set = true;
   }
   for (size_t oi = 0; oi < m->ops.size(); ++oi) {
@@ -731,11 +753,19 @@ static void launch_variant(sb_handle_s* h, TcLaunch& L, int B, bool persist) {
     TcParams P = L.PP;
     P.n_tiles_total = P.tiles_per_img * B;
     const int grid = std::max(1, std::min(P.n_tiles_total, h->sm_count * L.occ));
-    k_conv_tc_persist<<<grid, 192, L.smem_p, h->stream>>>(L.mapA, L.mapB, P);
+    switch (P.KC) {
+      case 16: k_conv_tc_persist<1><<<grid, 192, L.smem_p, h->stream>>>(L.mapA, L.mapB, P); break;
+      case 32: k_conv_tc_persist<2><<<grid, 192, L.smem_p, h->stream>>>(L.mapA, L.mapB, P); break;
+      default: k_conv_tc_persist<4><<<grid, 192, L.smem_p, h->stream>>>(L.mapA, L.mapB, P); break;
+    }
   } else {
     dim3 g = L.grid;
     g.z = B;
-    k_conv_tc<<<g, 128, L.smem, h->stream>>>(L.mapA, L.mapB, L.P);
+    switch (L.P.KC) {
+      case 16: k_conv_tc<1><<<g, 128, L.smem, h->stream>>>(L.mapA, L.mapB, L.P); break;
+      case 32: k_conv_tc<2><<<g, 128, L.smem, h->stream>>>(L.mapA, L.mapB, L.P); break;
+      default: k_conv_tc<4><<<g, 128, L.smem, h->stream>>>(L.mapA, L.mapB, L.P); break;
+    }
   }
 }
 
