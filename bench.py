@@ -356,6 +356,9 @@ def run_ours(args):
     op_ms_m = np.median(np.stack([r[0] for r in reps]), axis=0)
     kind, fl = reps[0][1], reps[0][2]
     tc = kind == 1
+    if os.environ.get("BENCH_VERBOSE"):
+        for i in range(len(kind)):
+            sys.stderr.write(f"[op {i:2d}] kind={int(kind[i])} {op_ms_m[i]*1e3:8.1f} us  {fl[i]/1e9:7.2f} GF  {(fl[i]/max(op_ms_m[i],1e-6)/1e9):8.1f} TF/s\n")
     tc_ms, tc_flops = float(op_ms_m[tc].sum()), float(fl[tc].sum())
     peaks, peaks_src = peaks_file()
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))

@@ -44,6 +44,11 @@ int sb_create(int device_id, sb_handle_t* out_handle) {
             device_id, prop.major, prop.minor);
   SB_CUDA(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->stream = h->own_stream;
+  for (int i = 0; i < 3; ++i) {
+    SB_CUDA(h, cudaStreamCreateWithFlags(&h->aux_stream[i], cudaStreamNonBlocking));
+    SB_CUDA(h, cudaEventCreateWithFlags(&h->join_ev[i], cudaEventDisableTiming));
+  }
+  SB_CUDA(h, cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
   *out_handle = h;
   return SB_OK;
 }
@@ -54,6 +59,8 @@ int sb_destroy(sb_handle_t h) {
   cudaDeviceSynchronize();
   sb_models_free(h);
   for (void* p : h->owned) cudaFree(p);
+  for (int i = 0; i < 3; ++i) { if (h->aux_stream[i]) cudaStreamDestroy(h->aux_stream[i]); if (h->join_ev[i]) cudaEventDestroy(h->join_ev[i]); }
+  if (h->fork_ev) cudaEventDestroy(h->fork_ev);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return SB_OK;

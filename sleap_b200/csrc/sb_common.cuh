@@ -50,6 +50,8 @@ struct sb_handle_s {
   int device = 0;
   cudaStream_t stream = nullptr;       // stream all work is issued on
   cudaStream_t own_stream = nullptr;   // created by sb_create
+  cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr};  // fork/join branches (tconv phases)
+  cudaEvent_t fork_ev = nullptr, join_ev[3] = {nullptr, nullptr, nullptr};
   std::string last_error;
   std::vector<void*> owned;                 // generic device allocations freed at destroy
   std::vector<SbModel*> models;

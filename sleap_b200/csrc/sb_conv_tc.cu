@@ -748,23 +748,23 @@ int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m) {
   return sb_conv_tc_autotune(h, m);
 }
 
-static void launch_variant(sb_handle_s* h, TcLaunch& L, int B, bool persist) {
+static void launch_variant(sb_handle_s* h, TcLaunch& L, int B, bool persist, cudaStream_t stream) {
   if (persist) {
     TcParams P = L.PP;
     P.n_tiles_total = P.tiles_per_img * B;
     const int grid = std::max(1, std::min(P.n_tiles_total, h->sm_count * L.occ));
     switch (P.KC) {
-      case 16: k_conv_tc_persist<1><<<grid, 192, L.smem_p, h->stream>>>(L.mapA, L.mapB, P); break;
-      case 32: k_conv_tc_persist<2><<<grid, 192, L.smem_p, h->stream>>>(L.mapA, L.mapB, P); break;
-      default: k_conv_tc_persist<4><<<grid, 192, L.smem_p, h->stream>>>(L.mapA, L.mapB, P); break;
+      case 16: k_conv_tc_persist<1><<<grid, 192, L.smem_p, stream>>>(L.mapA, L.mapB, P); break;
+      case 32: k_conv_tc_persist<2><<<grid, 192, L.smem_p, stream>>>(L.mapA, L.mapB, P); break;
+      default: k_conv_tc_persist<4><<<grid, 192, L.smem_p, stream>>>(L.mapA, L.mapB, P); break;
     }
   } else {
     dim3 g = L.grid;
     g.z = B;
     switch (L.P.KC) {
-      case 16: k_conv_tc<1><<<g, 128, L.smem, h->stream>>>(L.mapA, L.mapB, L.P); break;
-      case 32: k_conv_tc<2><<<g, 128, L.smem, h->stream>>>(L.mapA, L.mapB, L.P); break;
-      default: k_conv_tc<4><<<g, 128, L.smem, h->stream>>>(L.mapA, L.mapB, L.P); break;
+      case 16: k_conv_tc<1><<<g, 128, L.smem, stream>>>(L.mapA, L.mapB, L.P); break;
+      case 32: k_conv_tc<2><<<g, 128, L.smem, stream>>>(L.mapA, L.mapB, L.P); break;
+      default: k_conv_tc<4><<<g, 128, L.smem, stream>>>(L.mapA, L.mapB, L.P); break;
     }
   }
 }
@@ -790,7 +790,7 @@ int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
       for (int v = 0; v < 2; ++v)
         for (int rep = 0; rep < 3; ++rep) {
           cudaEventRecord(e0, h->stream);
-          launch_variant(h, L, m->B, v == 1);
+          launch_variant(h, L, m->B, v == 1, h->stream);
           cudaEventRecord(e1, h->stream);
           cudaError_t e = cudaStreamSynchronize(h->stream);
           if (e != cudaSuccess) return sb_fail(h, SB_ERR_CUDA, "autotune launch failed: %s", cudaGetErrorString(e));
@@ -812,9 +812,24 @@ int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
 
 int sb_conv_tc_launch(sb_handle_s* h, SbModel* m, int op_index, int B) {
   SbConvTcPlan* plan = m->tc_plans[op_index];
-  for (TcLaunch& L : plan->launches) {
-    launch_variant(h, L, B, L.use_persist != 0);
-    SB_CHECK_LAUNCH(h);
+  const size_t n = plan->launches.size();
+  if (n == 1 || getenv("SB_DISABLE_FORK")) {
+    for (TcLaunch& L : plan->launches) {
+      launch_variant(h, L, B, L.use_persist != 0, h->stream);
+      SB_CHECK_LAUNCH(h);
+    }
+    return 0;
   }
+  // the sub-pixel phases of a transposed conv are independent: fork them onto side streams so that
+  // their (individually small) grids fill the GPU together, then join
+  SB_CUDA(h, cudaEventRecord(h->fork_ev, h->stream));
+  for (size_t i = 0; i < n; ++i) {
+    cudaStream_t st = (i == 0) ? h->stream : h->aux_stream[(i - 1) % 3];
+    if (i > 0) SB_CUDA(h, cudaStreamWaitEvent(st, h->fork_ev, 0));
+    launch_variant(h, plan->launches[i], B, plan->launches[i].use_persist != 0, st);
+    SB_CHECK_LAUNCH(h);
+    if (i > 0) SB_CUDA(h, cudaEventRecord(h->join_ev[(i - 1) % 3], st));
+  }
+  for (size_t i = 1; i < n; ++i) SB_CUDA(h, cudaStreamWaitEvent(h->stream, h->join_ev[(i - 1) % 3], 0));
   return 0;
 }

@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(128) k_group(
   __syncthreads();
   if (threadIdx.x == 0) {
     const int n_slots = C * K;
-    int seq = 0;
+    int seq = 0, cur_max = -1;
     for (int se = 0; se < n_sorted; ++se) {
       const int e = sorted_edges[se];
       const int sn = edges[2 * e], dn = edges[2 * e + 1];
@@ -599,10 +599,9 @@ __global__ void __launch_bounds__(128) k_group(
         const int sid = sn * K + match_src[mo + m], did = dn * K + match_dst[mo + m];
         const int si = assign[sid], di = assign[did];
         if (si < 0 && di < 0) {
-          int mx = -1;
-          for (int t = 0; t < n_slots; ++t) mx = max(mx, assign[t]);
-          assign[sid] = mx + 1;
-          assign[did] = mx + 1;
+          assign[sid] = cur_max + 1;          // max(instance_assignments.values()) + 1, tracked incrementally
+          assign[did] = cur_max + 1;
+          ++cur_max;
           order[sid] = seq++;                 // src key is inserted before dst (paf_grouping.py:853-854)
           order[did] = seq++;
         } else if (si >= 0 && di < 0) {
@@ -614,7 +613,8 @@ __global__ void __launch_bounds__(128) k_group(
           bool share = false;
           for (int node = 0; node < C && !share; ++node) {
             bool in_s = false, in_d = false;
-            for (int k = 0; k < K; ++k) {
+            const int kn = min(node_cnt[b * C + node], K);
+            for (int k = 0; k < kn; ++k) {
               const int a = assign[node * K + k];
               in_s |= (a == si);
               in_d |= (a == di);
@@ -622,8 +622,17 @@ __global__ void __launch_bounds__(128) k_group(
             share = in_s && in_d;
           }
           if (!share)
-            for (int t = 0; t < n_slots; ++t)
-              if (assign[t] == di) assign[t] = si;
+            for (int node = 0; node < C; ++node) {
+              const int kn = min(node_cnt[b * C + node], K);
+              for (int k = 0; k < kn; ++k)
+                if (assign[node * K + k] == di) assign[node * K + k] = si;
+            }
+          // instance ids can disappear through merges / steals: recompute the running maximum
+          cur_max = -1;
+          for (int node = 0; node < C; ++node) {
+            const int kn = min(node_cnt[b * C + node], K);
+            for (int k = 0; k < kn; ++k) cur_max = max(cur_max, assign[node * K + k]);
+          }
         }
       }
     }
