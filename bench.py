@@ -258,34 +258,33 @@ def run_ours(args):
     I, C = layer.max_instances, 13
     ptrs = [c_void_p() for _ in range(5)]
     handle.call("sb_bottomup_device_outputs", model.model_id, *[byref(p) for p in ptrs])
-    rec_elems = B * (I * C * 3 + I + 1)
-    gather_in = torch.empty(rec_elems, dtype=torch.float32, device="cuda")
-    gather_out = torch.empty(world * rec_elems, dtype=torch.float32, device="cuda") if world > 1 else None
+    from sleap_b200 import parallel
+    gather_out = (torch.empty((world * B, parallel.record_width(I, C)), dtype=torch.float32, device="cuda")
+                  if world > 1 else None)
 
-    def as_tensor(p, n, dtype):
+    def as_tensor(p, shape, typestr):
         """torch view of a library-owned device buffer (plain pointer -> __cuda_array_interface__)."""
         class _V:
             pass
         v = _V()
-        v.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4" if dtype == torch.float32 else "<i4",
-                                      "data": (p.value, False), "version": 2}
+        v.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (p.value, False), "version": 2}
         return torch.as_tensor(v, device="cuda")
 
-    t_peaks = as_tensor(ptrs[0], B * I * C * 2, torch.float32)
-    t_vals = as_tensor(ptrs[1], B * I * C, torch.float32)
-    t_scores = as_tensor(ptrs[2], B * I, torch.float32)
-    t_nvalid = as_tensor(ptrs[3], B, torch.int32)
+    t_peaks = as_tensor(ptrs[0], (B, I, C, 2), "<f4")
+    t_vals = as_tensor(ptrs[1], (B, I, C), "<f4")
+    t_scores = as_tensor(ptrs[2], (B, I), "<f4")
+    t_nvalid = as_tensor(ptrs[3], (B,), "<i4")
+
+    def gather_step():
+        # the path's one exchange step: fixed-size instance records of every frame to every rank
+        rec = parallel.pack_records(t_peaks, t_vals, t_scores, t_nvalid)
+        parallel.all_gather_records(rec, gather_out)
 
     def step_device(i):
         with torch.cuda.stream(stream):
             handle.call("sb_infer_bottomup_dev", model.model_id, c_void_p(dev[i % n_sets].data_ptr()), B)
-            if world > 1:   # the path's one exchange step: fixed-size instance records to every rank
-                o = 0
-                for t in (t_peaks, t_vals, t_scores):
-                    gather_in[o:o + t.numel()].copy_(t, non_blocking=True)
-                    o += t.numel()
-                gather_in[o:o + B].copy_(t_nvalid.to(torch.float32), non_blocking=True)
-                dist.all_gather_into_tensor(gather_out, gather_in)
+            if world > 1:
+                gather_step()
 
     def barrier():
         torch.cuda.synchronize()
@@ -330,7 +329,7 @@ def run_ours(args):
         o = pred.inference_model.predict_on_batch(host[i % n_sets].numpy())
         if world > 1:
             with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(gather_out, gather_in)
+                gather_step()
     barrier()
     e2e_s = time.perf_counter() - t0
     d2h = B * (I * C * 2 + I * C + I + 2) * 4
