@@ -409,6 +409,20 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # keep stdout clean for the ONE JSON line (NCCL / torchrun print banners on stdout)
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    import builtins
+    _print = builtins.print
+
+    def print_json(*a, **k):
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        _print(*a, **k)
+        sys.stdout.flush()
+        os.dup2(2, 1)
+
+    globals()["print"] = print_json
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -64,6 +64,18 @@ struct TcParams {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// one elected lane of a converged warp (elect.sync): lets ptxas predicate the tcgen05 instructions
+// directly instead of building a per-lane uniformisation loop around them
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -302,7 +314,7 @@ __global__ void __launch_bounds__(128) k_conv_tc(const __grid_constant__ CUtenso
           const uint32_t b_base = smem_u32(b_ring + (size_t)sb * P.b_slot_bytes);
           const uint64_t da = desc_hi + (uint64_t)((a_base + (uint32_t)(P.groups[g].taps[t].row_off * TW * P.row_bytes)) >> 4);
           const uint64_t db = desc_hi + (uint64_t)(b_base >> 4);
-          if (lane == 0) {
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < KSTEPS; ++k)
               tc_mma_f16(tmem_base, da + 2 * k, db + 2 * k, P.idesc, (ch | g | t | k) ? 1u : 0u);
@@ -311,12 +323,12 @@ __global__ void __launch_bounds__(128) k_conv_tc(const __grid_constant__ CUtenso
           __syncwarp();
           if (++sb == P.n_b_slots) { sb = 0; phb ^= 1; }
         }
-        if (lane == 0) tc_commit(smem_u32(emptyA + sa));
+        if (elect_one()) tc_commit(smem_u32(emptyA + sa));
         __syncwarp();
         if (++sa == P.n_a_slots) { sa = 0; pha ^= 1; }
       }
     }
-    if (lane == 0) tc_commit(smem_u32(accum));
+    if (elect_one()) tc_commit(smem_u32(accum));
   }
   __syncwarp();
 
@@ -432,18 +444,19 @@ __global__ void __launch_bounds__(192) k_conv_tc_persist(const __grid_constant__
             const int slot = ch * P.n_used_taps + P.slot_of_tap[P.groups[g].taps[tp].w_tap];
             const uint64_t da = desc_hi + (uint64_t)((a_base + (uint32_t)(P.groups[g].taps[tp].row_off * TW * P.row_bytes)) >> 4);
             const uint64_t db = desc_hi + (uint64_t)((w_base + (uint32_t)(slot * P.w_slot_bytes)) >> 4);
-            if (lane == 0) {
+            if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < KSTEPS; ++k)
                 tc_mma_f16(d_tmem, da + 2 * k, db + 2 * k, P.idesc, (ch | g | tp | k) ? 1u : 0u);
             }
+            __syncwarp();
           }
-          if (lane == 0) tc_commit(smem_u32(emptyA + sa));
+          if (elect_one()) tc_commit(smem_u32(emptyA + sa));
           __syncwarp();
           if (++sa == P.n_a_slots) { sa = 0; pha ^= 1; }
         }
       }
-      if (lane == 0) tc_commit(smem_u32(tfull + stage));
+      if (elect_one()) tc_commit(smem_u32(tfull + stage));
       __syncwarp();
       stage ^= 1;
     }

@@ -113,57 +113,74 @@ __global__ void __launch_bounds__(256) k_conv_direct(
 // net size -> 3x3 SAME conv + bias + ReLU -> fp16 NHWC.  One output pixel per thread, all COUT
 // channels in registers; the frame is read once from HBM (neighbour re-reads hit L1), the output
 // is written once, so the kernel runs at HBM speed instead of paying a separate preprocess pass.
-template <typename TI, int CIN, int COUT>
+template <typename TI, int CIN, int COUT, int PX>
 __global__ void __launch_bounds__(256) k_conv_first(const TI* __restrict__ img, int Hin, int Win, int Hnet, int Wnet,
                                                     __half* __restrict__ out, int out_Ctot, int out_coff,
                                                     const float* __restrict__ w /*[9][CIN][COUT]*/,
                                                     const float* __restrict__ bias, int relu, int in_is_u8) {
-  __shared__ float s_w[9 * CIN * COUT];
+  // each thread: PX horizontally adjacent output pixels x COUT channels (weights read once from
+  // shared memory per PX pixels; the thread's PX*COUT fp16 outputs are contiguous in NHWC)
+  __shared__ __align__(16) float s_w[9 * CIN * COUT];
   __shared__ float s_b[COUT];
   for (int t = threadIdx.y * 32 + threadIdx.x; t < 9 * CIN * COUT; t += 256) s_w[t] = w[t];
-  if (threadIdx.y == 0 && threadIdx.x < COUT) s_b[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
-  if (COUT > 32 && threadIdx.y == 1 && threadIdx.x + 32 < COUT) s_b[threadIdx.x + 32] = bias ? bias[threadIdx.x + 32] : 0.f;
+  for (int t = threadIdx.y * 32 + threadIdx.x; t < COUT; t += 256) s_b[t] = bias ? bias[t] : 0.f;
   __syncthreads();
-  const int ox = blockIdx.x * 32 + threadIdx.x, oy = blockIdx.y * 8 + threadIdx.y, b = blockIdx.z;
-  if (ox >= Wnet || oy >= Hnet) return;
+  const int ox0 = (blockIdx.x * 32 + threadIdx.x) * PX, oy = blockIdx.y * 8 + threadIdx.y, b = blockIdx.z;
+  if (ox0 >= Wnet || oy >= Hnet) return;
   const TI* im = img + (size_t)b * Hin * Win * CIN;
   const float sc = in_is_u8 ? (1.0f / 255.0f) : 1.0f;
-  float acc[COUT];
+  float acc[PX][COUT];
 #pragma unroll
-  for (int c = 0; c < COUT; ++c) acc[c] = s_b[c];
+  for (int p = 0; p < PX; ++p)
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[p][c] = s_b[c];
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
     const int iy = oy + ky - 1;
+    if (iy < 0 || iy >= Hin) continue;                       // SAME padding / bottom zero pad
+    float in[PX + 2][CIN];
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      const int ix = ox + kx - 1;
-      if (iy < 0 || iy >= Hin || ix < 0 || ix >= Win) continue;   // SAME padding and bottom/right zero pad
+    for (int j = 0; j < PX + 2; ++j) {
+      const int ix = ox0 + j - 1;
+      const bool ok = ix >= 0 && ix < Win;
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci)
+        in[j][ci] = ok ? __fmul_rn((float)im[((size_t)iy * Win + ix) * CIN + ci], sc) : 0.f;
+    }
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
       for (int ci = 0; ci < CIN; ++ci) {
-        const float v = __fmul_rn((float)im[((size_t)iy * Win + ix) * CIN + ci], sc);
         const float4* w4 = reinterpret_cast<const float4*>(s_w + ((ky * 3 + kx) * CIN + ci) * COUT);
 #pragma unroll
         for (int q = 0; q < COUT / 4; ++q) {
           const float4 ww = w4[q];
-          acc[4 * q + 0] = fmaf(v, ww.x, acc[4 * q + 0]);
-          acc[4 * q + 1] = fmaf(v, ww.y, acc[4 * q + 1]);
-          acc[4 * q + 2] = fmaf(v, ww.z, acc[4 * q + 2]);
-          acc[4 * q + 3] = fmaf(v, ww.w, acc[4 * q + 3]);
+#pragma unroll
+          for (int p = 0; p < PX; ++p) {
+            const float v = in[p + kx][ci];
+            acc[p][4 * q + 0] = fmaf(v, ww.x, acc[p][4 * q + 0]);
+            acc[p][4 * q + 1] = fmaf(v, ww.y, acc[p][4 * q + 1]);
+            acc[p][4 * q + 2] = fmaf(v, ww.z, acc[p][4 * q + 2]);
+            acc[p][4 * q + 3] = fmaf(v, ww.w, acc[p][4 * q + 3]);
+          }
         }
       }
-    }
   }
-  __half* po = out + (((size_t)b * Hnet + oy) * Wnet + ox) * out_Ctot + out_coff;
 #pragma unroll
-  for (int q = 0; q < COUT / 8; ++q) {
-    __half2 h[4];
+  for (int p = 0; p < PX; ++p) {
+    if (ox0 + p >= Wnet) break;
+    __half* po = out + (((size_t)b * Hnet + oy) * Wnet + ox0 + p) * out_Ctot + out_coff;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float a = acc[8 * q + 2 * j], c2 = acc[8 * q + 2 * j + 1];
-      if (relu) { a = fmaxf(a, 0.f); c2 = fmaxf(c2, 0.f); }
-      h[j] = __floats2half2_rn(a, c2);
+    for (int q = 0; q < COUT / 8; ++q) {
+      __half2 h[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a = acc[p][8 * q + 2 * j], c2 = acc[p][8 * q + 2 * j + 1];
+        if (relu) { a = fmaxf(a, 0.f); c2 = fmaxf(c2, 0.f); }
+        h[j] = __floats2half2_rn(a, c2);
+      }
+      reinterpret_cast<uint4*>(po)[q] = *reinterpret_cast<uint4*>(h);
     }
-    reinterpret_cast<uint4*>(po)[q] = *reinterpret_cast<uint4*>(h);
   }
 }
 

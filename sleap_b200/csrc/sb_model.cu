@@ -161,15 +161,16 @@ static int first_fusion_op(const SbModel* m, size_t pre_index) {
 }
 
 template <typename TI, int CIN>
-static void launch_first(int co, dim3 g, cudaStream_t s, const TI* img, int Hin, int Win, int Hnet, int Wnet, __half* out,
+static void launch_first(int co, int B, cudaStream_t s, const TI* img, int Hin, int Win, int Hnet, int Wnet, __half* out,
                          int Ctot, int coff, const float* w, const float* b, int relu, int is_u8) {
   dim3 blk(32, 8);
+  auto grid = [&](int px) { return dim3((Wnet + 32 * px - 1) / (32 * px), (Hnet + 7) / 8, B); };
   switch (co) {
-    case 8: k_conv_first<TI, CIN, 8><<<g, blk, 0, s>>>(img, Hin, Win, Hnet, Wnet, out, Ctot, coff, w, b, relu, is_u8); break;
-    case 16: k_conv_first<TI, CIN, 16><<<g, blk, 0, s>>>(img, Hin, Win, Hnet, Wnet, out, Ctot, coff, w, b, relu, is_u8); break;
-    case 24: k_conv_first<TI, CIN, 24><<<g, blk, 0, s>>>(img, Hin, Win, Hnet, Wnet, out, Ctot, coff, w, b, relu, is_u8); break;
-    case 32: k_conv_first<TI, CIN, 32><<<g, blk, 0, s>>>(img, Hin, Win, Hnet, Wnet, out, Ctot, coff, w, b, relu, is_u8); break;
-    default: k_conv_first<TI, CIN, 64><<<g, blk, 0, s>>>(img, Hin, Win, Hnet, Wnet, out, Ctot, coff, w, b, relu, is_u8); break;
+    case 8: k_conv_first<TI, CIN, 8, 4><<<grid(4), blk, 0, s>>>(img, Hin, Win, Hnet, Wnet, out, Ctot, coff, w, b, relu, is_u8); break;
+    case 16: k_conv_first<TI, CIN, 16, 4><<<grid(4), blk, 0, s>>>(img, Hin, Win, Hnet, Wnet, out, Ctot, coff, w, b, relu, is_u8); break;
+    case 24: k_conv_first<TI, CIN, 24, 2><<<grid(2), blk, 0, s>>>(img, Hin, Win, Hnet, Wnet, out, Ctot, coff, w, b, relu, is_u8); break;
+    case 32: k_conv_first<TI, CIN, 32, 2><<<grid(2), blk, 0, s>>>(img, Hin, Win, Hnet, Wnet, out, Ctot, coff, w, b, relu, is_u8); break;
+    default: k_conv_first<TI, CIN, 64, 1><<<grid(1), blk, 0, s>>>(img, Hin, Win, Hnet, Wnet, out, Ctot, coff, w, b, relu, is_u8); break;
   }
 }
 
@@ -186,7 +187,7 @@ static int run_ops_t(sb_handle_s* h, SbModel* m, const void* frames_dev, int fra
     if ((int)oi == fused_first) {
       const float* Wt = m->weights_dev + op.w_off();
       const float* bias = op.b_off() >= 0 ? m->weights_dev + op.b_off() : nullptr;
-      dim3 g((ob.W + 31) / 32, (ob.H + 7) / 8, B);
+      const int g = B;
       const int relu = (op.flags() & SB_OPF_RELU) ? 1 : 0;
       // rows/cols beyond the resized frame (Hres, Wres) are the bottom/right zero padding
       if (frames_are_u8) {

@@ -90,6 +90,21 @@ def test_hourglass_forward_fp32():
         assert_allclose(g, x, atol=1e-4 * max(1.0, np.abs(x).max()), rtol=1e-4)
 
 
+def test_hourglass_forward_fp16():
+    """conv -> ReLU -> BN affine epilogue of the tensor-core path (hourglass), additive skips, nearest x2."""
+    spec = dict(backbone="hourglass", head_type="multi_instance", part_names=None, edges=None,
+                backbone_cfg=dict(stem_stride=4, max_stride=32, output_stride=4, stem_filters=16, filters=32, filter_increase=32, stacks=2),
+                heads=[dict(name="MultiInstanceConfmapsHead", channels=6, output_stride=4),
+                       dict(name="PartAffinityFieldsHead", channels=10, output_stride=4)])
+    model, w, cm = _mk(spec, 3, 17, precision=0)
+    imgs = np.random.default_rng(2).integers(0, 256, size=(2, 512, 640, 3), dtype=np.uint8)
+    got = model.forward(imgs)
+    want = _oracle_forward(imgs, spec, w, 3, 1.0, 32)
+    for g, x in zip(got, want):
+        err = np.abs(g - x).max() / max(1e-6, np.abs(x).max())
+        assert err < 2e-2, err
+
+
 @pytest.mark.parametrize("name", ["tconv", "interp"])
 def test_unet_forward_fp16(name):
     cfg = dict(UNET_CASES[name], filters=16, max_stride=16)
