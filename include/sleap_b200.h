@@ -191,6 +191,12 @@ int sb_infer_bottomup(sb_handle_t h, int model_id, const uint8_t* frames_host, i
                       float* out_instance_peaks, float* out_instance_peak_vals,
                       float* out_instance_scores, int32_t* out_n_valid, int32_t* out_flags);
 int sb_infer_bottomup_dev(sb_handle_t h, int model_id, const uint8_t* frames_dev, int B);
+/* sb_infer_bottomup_dev returns as soon as the work is queued: the network runs on the handle's
+ * stream and the post-processing on a second stream, so that it overlaps the network of the next
+ * call.  sb_bottomup_wait_results makes the handle's stream wait (device side) for the results of
+ * the last call; sb_get_post_stream exposes the post-processing stream; sb_synchronize joins both. */
+int sb_bottomup_wait_results(sb_handle_t h, int model_id);
+int sb_get_post_stream(sb_handle_t h, void** out_stream);
 int sb_bottomup_device_outputs(sb_handle_t h, int model_id, float** instance_peaks_dev,
                                float** instance_peak_vals_dev, float** instance_scores_dev,
                                int32_t** n_valid_dev, int32_t** flags_dev);

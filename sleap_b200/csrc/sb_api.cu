@@ -49,6 +49,9 @@ int sb_create(int device_id, sb_handle_t* out_handle) {
     SB_CUDA(h, cudaEventCreateWithFlags(&h->join_ev[i], cudaEventDisableTiming));
   }
   SB_CUDA(h, cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
+  SB_CUDA(h, cudaStreamCreateWithFlags(&h->post_stream, cudaStreamNonBlocking));
+  SB_CUDA(h, cudaEventCreateWithFlags(&h->fwd_done_ev, cudaEventDisableTiming));
+  SB_CUDA(h, cudaEventCreateWithFlags(&h->post_done_ev, cudaEventDisableTiming));
   *out_handle = h;
   return SB_OK;
 }
@@ -61,6 +64,9 @@ int sb_destroy(sb_handle_t h) {
   for (void* p : h->owned) cudaFree(p);
   for (int i = 0; i < 3; ++i) { if (h->aux_stream[i]) cudaStreamDestroy(h->aux_stream[i]); if (h->join_ev[i]) cudaEventDestroy(h->join_ev[i]); }
   if (h->fork_ev) cudaEventDestroy(h->fork_ev);
+  if (h->post_stream) cudaStreamDestroy(h->post_stream);
+  if (h->fwd_done_ev) cudaEventDestroy(h->fwd_done_ev);
+  if (h->post_done_ev) cudaEventDestroy(h->post_done_ev);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
   return SB_OK;
@@ -74,6 +80,8 @@ const char* sb_last_error(sb_handle_t h) {
 int sb_synchronize(sb_handle_t h) {
   if (!h) return sb_fail(nullptr, SB_ERR_INVALID, "null handle");
   SB_CUDA(h, cudaStreamSynchronize(h->stream));
+  SB_CUDA(h, cudaStreamSynchronize(h->post_stream));
+  h->post_pending = false;
   return SB_OK;
 }
 

@@ -52,6 +52,10 @@ struct sb_handle_s {
   cudaStream_t own_stream = nullptr;   // created by sb_create
   cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr};  // fork/join branches (tconv phases)
   cudaEvent_t fork_ev = nullptr, join_ev[3] = {nullptr, nullptr, nullptr};
+  // post-processing of step i runs on its own stream so that it overlaps the network of step i+1
+  cudaStream_t post_stream = nullptr;
+  cudaEvent_t fwd_done_ev = nullptr, post_done_ev = nullptr;
+  bool post_pending = false;
   std::string last_error;
   std::vector<void*> owned;                 // generic device allocations freed at destroy
   std::vector<SbModel*> models;

@@ -60,6 +60,14 @@ struct TcParams {
   int tiles_per_img, n_tiles_total;
   int n_used_taps, used_taps[9], slot_of_tap[9];
   int w_slot_bytes;
+  // geometry of the output tile: tw x (128/tw) pixels (16x8 for the per-dx staging, 8x16 for halo staging)
+  int tw;
+  // halo variant: ONE staged tile [KC, tw+2, th+2] per chunk; every tap is a start-address offset
+  int n_htaps;
+  int htap_off_rows[9];        // (tap_dy - dy0) * (tw + 2) + (tap_dx - dx0)   [rows of row_bytes]
+  int htap_w[9];               // weight tap index
+  int dx0;
+  int halo_base_offset;        // 1: put (addr >> 7) & 7 into the descriptor's base-offset field
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -189,16 +197,19 @@ __device__ __forceinline__ void tc_epilogue_cols(const TcParams& P, const float*
     }
   }
   if (P.pool_out != nullptr) {
+    // fused MaxPool2D(2, strides=2): lanes of a warp hold tile pixels (ty = q*(32/tw) + lane/tw, tx = lane%tw);
+    // the 2x2 partners are lane^1 (x) and lane^tw (y); lanes with even tx and even ty store.
     float pv[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       float a = v[j];
       a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 1));
-      a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 16));
+      a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, P.tw));
       pv[j] = a;
     }
-    if (valid && lane < 16 && (lane & 1) == 0 && n0 + c0 + 16 <= P.Cout) {
-      const int py = (y0 >> 1) + q, px = (x0 >> 1) + (lane >> 1);
+    const int lr = lane / P.tw, lc = lane % P.tw;
+    if (valid && (lc & 1) == 0 && (lr & 1) == 0 && n0 + c0 + 16 <= P.Cout) {
+      const int py = (y0 >> 1) + ((q * (32 / P.tw) + lr) >> 1), px = (x0 >> 1) + (lc >> 1);
       __half* pp = reinterpret_cast<__half*>(P.pool_out) + (((size_t)b * P.pool_H + py) * P.pool_W + px) * P.pool_Ctot +
                    P.pool_coff + n0 + c0;
       __half2 h[8];
@@ -495,6 +506,155 @@ __global__ void __launch_bounds__(192) k_conv_tc_persist(const __grid_constant__
   }
 }
 
+
+// K-major swizzled descriptor whose start address is NOT aligned to the swizzle repeat (8 rows):
+// the matrix base offset field (bits [49,52)) carries the phase (address >> 7) & 7.
+__device__ __forceinline__ uint64_t make_desc_unaligned(uint32_t saddr, int sbo_bytes, int layout_type, int use_base_offset) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  if (use_base_offset) d |= (uint64_t)((saddr >> 7) & 7) << 49;
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+
+// Halo variant of the persistent kernel: output tile 8 px wide x 16 rows (one 8-row swizzle group
+// per tile row), ONE TMA load of the [KC, 10, 18] halo tile per input-channel chunk; the nine
+// taps are pure start-address offsets ((ky*10 + kx) rows) with stride-byte-offset = 10 rows.
+// Cuts the L2->SM traffic of the activation operand from 3.75x to 1.4x of the tile.
+template <int KSTEPS>
+__global__ void __launch_bounds__(192) k_conv_tc_halo(const __grid_constant__ CUtensorMap mapA,
+                                                      const __grid_constant__ CUtensorMap mapB,
+                                                      const __grid_constant__ TcParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int n_wslots = P.n_chunks * P.n_used_taps;
+  uint8_t* w_res = base;
+  uint8_t* a_ring = w_res + (size_t)n_wslots * P.w_slot_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(a_ring + (size_t)P.n_a_slots * P.a_slot_bytes);
+  uint64_t* fullA = bars;
+  uint64_t* emptyA = fullA + P.n_a_slots;
+  uint64_t* tfull = emptyA + P.n_a_slots;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* wbar = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+  float* s_par = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~(uintptr_t)15);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int TWH = 8, THH = 16, PITCH = TWH + 2;
+  stage_params(P, s_par, 0);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < P.n_a_slots; ++i) { mbar_init(smem_u32(fullA + i), 1); mbar_init(smem_u32(emptyA + i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(tfull + i), 1); mbar_init(smem_u32(tempty + i), 4); }
+    mbar_init(smem_u32(wbar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(P.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    mbar_expect_tx(smem_u32(wbar), (uint32_t)(n_wslots * P.b_tx_bytes));
+    for (int ch = 0; ch < P.n_chunks; ++ch)
+      for (int u = 0; u < P.n_used_taps; ++u)
+        tma_load_3d(smem_u32(w_res + (size_t)(ch * P.n_used_taps + u) * P.w_slot_bytes), &mapB, smem_u32(wbar), ch * P.KC, 0,
+                    P.used_taps[u]);
+    int sa = 0;
+    uint32_t pha = 0;
+    for (int t = blockIdx.x; t < P.n_tiles_total; t += gridDim.x) {
+      const int b = t / P.tiles_per_img, r = t - b * P.tiles_per_img;
+      const int y0 = (r / P.tiles_x) * THH, x0 = (r % P.tiles_x) * TWH;
+      for (int ch = 0; ch < P.n_chunks; ++ch) {
+        mbar_wait(smem_u32(emptyA + sa), pha ^ 1, 21);
+        mbar_expect_tx(smem_u32(fullA + sa), (uint32_t)P.a_tx_bytes);
+        tma_load_4d(smem_u32(a_ring + (size_t)sa * P.a_slot_bytes), &mapA, smem_u32(fullA + sa), ch * P.KC, x0 + P.dx0,
+                    y0 + P.dy0, b);
+        if (++sa == P.n_a_slots) { sa = 0; pha ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    mbar_wait(smem_u32(wbar), 0, 22);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    int sa = 0, stage = 0;
+    uint32_t pha = 0, eph0 = 0, eph1 = 0;
+    const uint64_t descb_hi = make_desc(0, P.row_bytes, P.layout_type);
+    const uint32_t w_base = smem_u32(w_res);
+    const int sbo = PITCH * P.row_bytes;
+    for (int t = blockIdx.x; t < P.n_tiles_total; t += gridDim.x) {
+      const uint32_t eph = stage ? eph1 : eph0;
+      mbar_wait(smem_u32(tempty + stage), eph ^ 1, 23);
+      if (stage) eph1 ^= 1; else eph0 ^= 1;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d_tmem = tmem_base + (uint32_t)(stage * P.N);
+      for (int ch = 0; ch < P.n_chunks; ++ch) {
+        mbar_wait(smem_u32(fullA + sa), pha, 24);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_base = smem_u32(a_ring + (size_t)sa * P.a_slot_bytes);
+#pragma unroll
+        for (int tp = 0; tp < 9; ++tp) {
+          if (tp >= P.n_htaps) break;
+          const int slot = ch * P.n_used_taps + P.slot_of_tap[P.htap_w[tp]];
+          const uint32_t a_addr = a_base + (uint32_t)(P.htap_off_rows[tp] * P.row_bytes);
+          const uint64_t da = make_desc_unaligned(a_addr, sbo, P.layout_type, P.halo_base_offset);
+          const uint64_t db = descb_hi + (uint64_t)((w_base + (uint32_t)(slot * P.w_slot_bytes)) >> 4);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < KSTEPS; ++k)
+              tc_mma_f16(d_tmem, da + 2 * k, db + 2 * k, P.idesc, (ch | tp | k) ? 1u : 0u);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) tc_commit(smem_u32(emptyA + sa));
+        __syncwarp();
+        if (++sa == P.n_a_slots) { sa = 0; pha ^= 1; }
+      }
+      if (elect_one()) tc_commit(smem_u32(tfull + stage));
+      __syncwarp();
+      stage ^= 1;
+    }
+  } else if (warp >= 2) {
+    const int q = warp & 3;
+    int stage = 0;
+    uint32_t fph[2] = {0, 0};
+    for (int t = blockIdx.x; t < P.n_tiles_total; t += gridDim.x) {
+      const int b = t / P.tiles_per_img, r = t - b * P.tiles_per_img;
+      const int y0 = (r / P.tiles_x) * THH, x0 = (r % P.tiles_x) * TWH;
+      mbar_wait(smem_u32(tfull + stage), fph[stage], 25);
+      fph[stage] ^= 1;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int m = q * 32 + lane;
+      const int iy = y0 + m / TWH, ix = x0 + m % TWH;
+      const bool valid = (iy < P.H) && (ix < P.W);
+      const size_t pix = ((size_t)b * P.out_H + (iy * P.oy_mul + P.oy_add)) * P.out_W + (ix * P.ox_mul + P.ox_add);
+      for (int c0 = 0; c0 < P.N; c0 += 16) {
+        uint32_t r16[16];
+        tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(stage * P.N + c0), r16);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tc_epilogue_cols(P, s_par, r16, 0, c0, valid, pix, b, x0, y0, q, lane);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(tempty + stage));
+      stage ^= 1;
+    }
+  }
+  __syncwarp();
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P.tmem_cols) : "memory");
+  }
+}
+
 // ------------------------------- host side ---------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -521,7 +681,12 @@ struct TcLaunch {
   TcParams PP;
   size_t smem_p;
   int occ;
-  int use_persist;     // chosen at configure time by timing both variants on the device
+  int use_persist;     // variant chosen at configure time by timing them on the device: 0 stream, 1 persist, 2 halo
+  bool has_halo;
+  CUtensorMap mapAH;   // box [KC, 10, 18, 1]
+  TcParams PH;
+  size_t smem_h;
+  int occ_h;
 };
 
 }  // namespace
@@ -617,8 +782,10 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
   L.grid = dim3(P.tiles_x * tiles_y, plan->Cout_pad / N, 1 /* z = batch, set at launch */);
   // persistent variant when the whole filter bank of this launch fits in shared memory
   P.persistent = 0;
+  P.tw = TW;
   P.tiles_per_img = P.tiles_x * tiles_y;
   L.has_persist = false;
+  L.has_halo = false;
   {
     int used[9], n_used = 0, slot_of[9];
     for (int i = 0; i < 9; ++i) slot_of[i] = -1;
@@ -653,6 +820,50 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
       }
       L.occ = occ;
       L.has_persist = true;
+    }
+  }
+  if (L.has_persist && ib.W >= 10 && ib.H >= 18 && !getenv("SB_DISABLE_HALO")) {
+    TcParams& Hp = L.PH;
+    Hp = L.PP;
+    Hp.tw = 8;
+    Hp.tiles_x = (ib.W + 7) / 8;
+    Hp.tiles_per_img = Hp.tiles_x * ((ib.H + 15) / 16);
+    int dxmin = 0;
+    for (int g = 0; g < n_groups; ++g) dxmin = std::min(dxmin, groups[g].dx);
+    Hp.dx0 = dxmin;
+    Hp.halo_base_offset = getenv("SB_HALO_BASEOFF") ? atoi(getenv("SB_HALO_BASEOFF")) : 0;
+    Hp.n_htaps = 0;
+    for (int g = 0; g < n_groups; ++g)
+      for (int t = 0; t < groups[g].n_taps; ++t) {
+        Hp.htap_off_rows[Hp.n_htaps] = groups[g].taps[t].row_off * 10 + (groups[g].dx - dxmin);
+        Hp.htap_w[Hp.n_htaps] = groups[g].taps[t].w_tap;
+        ++Hp.n_htaps;
+      }
+    Hp.a_tx_bytes = 18 * 10 * KC * 2;
+    Hp.a_slot_bytes = (Hp.a_tx_bytes + 1023) / 1024 * 1024;
+    const size_t w_bytes = (size_t)Hp.n_chunks * Hp.n_used_taps * Hp.w_slot_bytes;
+    const size_t budget = 196 * 1024;
+    if (w_bytes + 2 * (size_t)Hp.a_slot_bytes <= budget) {
+      int na = (int)((budget - w_bytes) / Hp.a_slot_bytes);
+      Hp.n_a_slots = std::max(2, std::min(na, 6));
+      L.smem_h = w_bytes + (size_t)Hp.n_a_slots * Hp.a_slot_bytes + 1024 + (size_t)(2 * Hp.n_a_slots + 5) * 8 + 64 + 3 * 256 * sizeof(float);
+      cudaFuncAttributes fa;
+      int occ = 1;
+      if (cudaFuncGetAttributes(&fa, k_conv_tc_halo<4>) == cudaSuccess) {
+        const int by_regs = 65536 / std::max(1, fa.numRegs * 192);
+        const int by_smem = (int)((227 * 1024) / (L.smem_h + fa.sharedSizeBytes + 1024));
+        occ = std::max(1, std::min(std::min(by_regs, by_smem), std::min(512 / Hp.tmem_cols, 8)));
+      }
+      L.occ_h = occ;
+      cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)ib.W, (cuuint64_t)ib.H, (cuuint64_t)m->B};
+      cuuint64_t strides[3] = {(cuuint64_t)ib.C * 2, (cuuint64_t)ib.W * ib.C * 2, (cuuint64_t)ib.H * ib.W * ib.C * 2};
+      cuuint32_t box[4] = {(cuuint32_t)KC, 10, 18, 1};
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      void* gptr = (void*)((__half*)ib.dev + op.in_coff());
+      CUresult r = enc(&L.mapAH, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, gptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       swz_for(KC), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return sb_fail(h, SB_ERR_CUDA, "cuTensorMapEncodeTiled(A halo) failed: %d", (int)r);
+      L.has_halo = true;
     }
   }
   L.use_persist = 0;
@@ -695,6 +906,9 @@ int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m) {
     SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_persist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_persist<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_persist<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_halo<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_halo<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_halo<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     attr_set = true;
   }
   for (size_t oi = 0; oi < m->ops.size(); ++oi) {
@@ -761,8 +975,17 @@ int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m) {
   return sb_conv_tc_autotune(h, m);
 }
 
-static void launch_variant(sb_handle_s* h, TcLaunch& L, int B, bool persist, cudaStream_t stream) {
-  if (persist) {
+static void launch_variant(sb_handle_s* h, TcLaunch& L, int B, int variant, cudaStream_t stream) {
+  if (variant == 2) {
+    TcParams P = L.PH;
+    P.n_tiles_total = P.tiles_per_img * B;
+    const int grid = std::max(1, std::min(P.n_tiles_total, h->sm_count * L.occ_h));
+    switch (P.KC) {
+      case 16: k_conv_tc_halo<1><<<grid, 192, L.smem_h, stream>>>(L.mapAH, L.mapB, P); break;
+      case 32: k_conv_tc_halo<2><<<grid, 192, L.smem_h, stream>>>(L.mapAH, L.mapB, P); break;
+      default: k_conv_tc_halo<4><<<grid, 192, L.smem_h, stream>>>(L.mapAH, L.mapB, P); break;
+    }
+  } else if (variant == 1) {
     TcParams P = L.PP;
     P.n_tiles_total = P.tiles_per_img * B;
     const int grid = std::max(1, std::min(P.n_tiles_total, h->sm_count * L.occ));
@@ -785,9 +1008,13 @@ static void launch_variant(sb_handle_s* h, TcLaunch& L, int B, bool persist, cud
 // Pick, per launch, the faster of the two kernel variants by timing them on the device (buffers
 // are already allocated; their contents do not matter for timing).
 int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
-  if (getenv("SB_DISABLE_AUTOTUNE")) {
+  const char* force = getenv("SB_FORCE_VARIANT");
+  const bool halo_ok = !getenv("SB_DISABLE_HALO");
+  auto avail = [&](const TcLaunch& L, int v) { return v == 0 || (v == 1 && L.has_persist) || (v == 2 && L.has_halo && halo_ok); };
+  if (force || getenv("SB_DISABLE_AUTOTUNE")) {
+    const int want = force ? atoi(force) : 1;
     for (SbConvTcPlan* plan : m->tc_plans)
-      if (plan) for (TcLaunch& L : plan->launches) L.use_persist = L.has_persist ? 1 : 0;
+      if (plan) for (TcLaunch& L : plan->launches) L.use_persist = avail(L, want) ? want : (avail(L, 1) && !force ? 1 : 0);
     return 0;
   }
   cudaEvent_t e0, e1;
@@ -799,23 +1026,27 @@ int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
     if (!plan) continue;
     for (TcLaunch& L : plan->launches) {
       if (!L.has_persist) continue;
-      float best[2] = {1e30f, 1e30f};
-      for (int v = 0; v < 2; ++v)
+      float best[3] = {1e30f, 1e30f, 1e30f};
+      for (int v = 0; v < 3; ++v) {
+        if (!avail(L, v)) continue;
         for (int rep = 0; rep < 3; ++rep) {
           cudaEventRecord(e0, h->stream);
-          launch_variant(h, L, m->B, v == 1, h->stream);
+          launch_variant(h, L, m->B, v, h->stream);
           cudaEventRecord(e1, h->stream);
           cudaError_t e = cudaStreamSynchronize(h->stream);
-          if (e != cudaSuccess) return sb_fail(h, SB_ERR_CUDA, "autotune launch failed: %s", cudaGetErrorString(e));
+          if (e != cudaSuccess) return sb_fail(h, SB_ERR_CUDA, "autotune launch (variant %d) failed: %s", v, cudaGetErrorString(e));
           float ms = 0.f;
           cudaEventElapsedTime(&ms, e0, e1);
           if (rep > 0) best[v] = std::min(best[v], ms);
         }
-      L.use_persist = best[1] < best[0] ? 1 : 0;
+      }
+      int pick = 0;
+      for (int v = 1; v < 3; ++v) if (best[v] < best[pick]) pick = v;
+      L.use_persist = pick;
       if (dbg)
-        fprintf(stderr, "[sb_conv_tc] op %zu Cin=%d N=%d %dx%d: stream %.1f us, persist %.1f us (occ %d, %d A slots) -> %s\n", oi,
-                L.P.n_chunks * L.P.KC, L.P.N, L.P.H, L.P.W, best[0] * 1e3f, best[1] * 1e3f, L.occ, L.PP.n_a_slots,
-                L.use_persist ? "persist" : "stream");
+        fprintf(stderr, "[sb_conv_tc] op %zu Cin=%d N=%d %dx%d: stream %.1f, persist %.1f (occ %d, %d slots), halo %.1f (occ %d, %d slots) us -> %d\n",
+                oi, L.P.n_chunks * L.P.KC, L.P.N, L.P.H, L.P.W, best[0] * 1e3f, best[1] * 1e3f, L.occ, L.PP.n_a_slots,
+                best[2] * 1e3f, L.occ_h, L.has_halo ? L.PH.n_a_slots : 0, pick);
     }
   }
   cudaEventDestroy(e0);
@@ -828,7 +1059,7 @@ int sb_conv_tc_launch(sb_handle_s* h, SbModel* m, int op_index, int B) {
   const size_t n = plan->launches.size();
   if (n == 1 || getenv("SB_DISABLE_FORK")) {
     for (TcLaunch& L : plan->launches) {
-      launch_variant(h, L, B, L.use_persist != 0, h->stream);
+      launch_variant(h, L, B, L.use_persist, h->stream);
       SB_CHECK_LAUNCH(h);
     }
     return 0;
@@ -839,7 +1070,7 @@ int sb_conv_tc_launch(sb_handle_s* h, SbModel* m, int op_index, int B) {
   for (size_t i = 0; i < n; ++i) {
     cudaStream_t st = (i == 0) ? h->stream : h->aux_stream[(i - 1) % 3];
     if (i > 0) SB_CUDA(h, cudaStreamWaitEvent(st, h->fork_ev, 0));
-    launch_variant(h, plan->launches[i], B, plan->launches[i].use_persist != 0, st);
+    launch_variant(h, plan->launches[i], B, plan->launches[i].use_persist, st);
     SB_CHECK_LAUNCH(h);
     if (i > 0) SB_CUDA(h, cudaEventRecord(h->join_ev[(i - 1) % 3], st));
   }

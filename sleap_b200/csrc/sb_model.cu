@@ -183,6 +183,7 @@ static int run_ops_t(sb_handle_s* h, SbModel* m, const void* frames_dev, int fra
     const SbOp& op = m->ops[oi];
     if (!m->prof_events.empty()) cudaEventRecord(m->prof_events[oi], s);
     SbBuffer& ob = m->buffers[op.out_buf()];
+    if ((int)oi == m->guard_op && h->post_pending) SB_CUDA(h, cudaStreamWaitEvent(s, h->post_done_ev, 0));
     if (oi < m->skip_op.size() && m->skip_op[oi]) continue;     // 2x2 max-pool fused into the producing conv
     if ((int)oi == fused_first) {
       const float* Wt = m->weights_dev + op.w_off();
@@ -420,11 +421,17 @@ int sb_bottomup_configure(sb_handle_t h, int model_id, const sb_bottomup_params*
   m->bu = *p;
   m->bu.edges = nullptr; m->bu.sorted_edge_inds = nullptr;
   m->bu_edges.assign(p->edges, p->edges + 2 * p->n_edges);
+  m->guard_op = -1;
+  if (!getenv("SB_DISABLE_POST_OVERLAP"))
+    for (size_t i = 0; i < m->ops.size(); ++i) {
+      const int ob = m->ops[i].out_buf();
+      if (ob == p->cms_buffer || ob == p->pafs_buffer || (p->offsets_buffer >= 0 && ob == p->offsets_buffer)) { m->guard_op = (int)i; break; }
+    }
   m->bu_configured = true;
   return SB_OK;
 }
 
-static int bottomup_post(sb_handle_s* h, SbModel* m, int B) {
+static int bottomup_post_kernels(sb_handle_s* h, SbModel* m, int B) {
   const sb_bottomup_params& p = m->bu;
   SbBuffer& cb = m->buffers[p.cms_buffer];
   SbBuffer& pb = m->buffers[p.pafs_buffer];
@@ -436,6 +443,24 @@ static int bottomup_post(sb_handle_s* h, SbModel* m, int B) {
   if ((rc = sbk_score_match(h, (const float*)pb.dev, B, pb.H, pb.W, pb.C, p.n_line_points, p.paf_output_stride, max_len,
                             p.dist_penalty_weight, m->ws))) return rc;
   return sbk_group(h, B, p.n_nodes, p.min_instance_peaks, p.min_line_scores, p.input_scale, m->ws);
+}
+
+// Peak finding / PAF scoring / matching / grouping of this batch on the handle's post-processing
+// stream: it only depends on the head outputs, so it overlaps the network of the next batch
+// (run_ops waits on post_done_ev right before it overwrites a head buffer).
+static int bottomup_post(sb_handle_s* h, SbModel* m, int B) {
+  if (m->guard_op < 0) return bottomup_post_kernels(h, m, B);
+  cudaStream_t main_stream = h->stream;
+  SB_CUDA(h, cudaEventRecord(h->fwd_done_ev, main_stream));
+  SB_CUDA(h, cudaStreamWaitEvent(h->post_stream, h->fwd_done_ev, 0));
+  h->stream = h->post_stream;
+  int rc = bottomup_post_kernels(h, m, B);
+  cudaError_t e = cudaEventRecord(h->post_done_ev, h->post_stream);
+  h->stream = main_stream;
+  if (rc) return rc;
+  if (e != cudaSuccess) return sb_fail(h, SB_ERR_CUDA, "event record: %s", cudaGetErrorString(e));
+  h->post_pending = true;
+  return 0;
 }
 
 int sb_infer_bottomup_dev(sb_handle_t h, int model_id, const uint8_t* frames_dev, int B) {
@@ -460,12 +485,30 @@ int sb_infer_bottomup(sb_handle_t h, int model_id, const uint8_t* frames_host, i
   if ((rc = bottomup_post(h, m, B))) return rc;
   const sb_bottomup_params& p = m->bu;
   const size_t I = p.max_instances, C = p.n_nodes;
-  SB_CUDA(h, cudaMemcpyAsync(out_instance_peaks, m->ws.inst_peaks, (size_t)B * I * C * 2 * 4, cudaMemcpyDeviceToHost, h->stream));
-  SB_CUDA(h, cudaMemcpyAsync(out_instance_peak_vals, m->ws.inst_vals, (size_t)B * I * C * 4, cudaMemcpyDeviceToHost, h->stream));
-  SB_CUDA(h, cudaMemcpyAsync(out_instance_scores, m->ws.inst_scores, (size_t)B * I * 4, cudaMemcpyDeviceToHost, h->stream));
-  SB_CUDA(h, cudaMemcpyAsync(out_n_valid, m->ws.n_inst, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
-  if (out_flags) SB_CUDA(h, cudaMemcpyAsync(out_flags, m->ws.flags, (size_t)B * 4, cudaMemcpyDeviceToHost, h->stream));
-  SB_CUDA(h, cudaStreamSynchronize(h->stream));
+  cudaStream_t rs = h->post_pending ? h->post_stream : h->stream;
+  SB_CUDA(h, cudaMemcpyAsync(out_instance_peaks, m->ws.inst_peaks, (size_t)B * I * C * 2 * 4, cudaMemcpyDeviceToHost, rs));
+  SB_CUDA(h, cudaMemcpyAsync(out_instance_peak_vals, m->ws.inst_vals, (size_t)B * I * C * 4, cudaMemcpyDeviceToHost, rs));
+  SB_CUDA(h, cudaMemcpyAsync(out_instance_scores, m->ws.inst_scores, (size_t)B * I * 4, cudaMemcpyDeviceToHost, rs));
+  SB_CUDA(h, cudaMemcpyAsync(out_n_valid, m->ws.n_inst, (size_t)B * 4, cudaMemcpyDeviceToHost, rs));
+  if (out_flags) SB_CUDA(h, cudaMemcpyAsync(out_flags, m->ws.flags, (size_t)B * 4, cudaMemcpyDeviceToHost, rs));
+  SB_CUDA(h, cudaStreamSynchronize(rs));
+  h->post_pending = false;
+  return SB_OK;
+}
+
+// Makes the handle's main stream wait (on the device, no host sync) for the post-processing of the
+// last sb_infer_bottomup_dev call, e.g. before recording an end-of-work event or reading the results.
+int sb_bottomup_wait_results(sb_handle_t h, int model_id) {
+  SbModel* m = get_model(h, model_id);
+  if (!m || !m->bu_configured) return sb_fail(h, SB_ERR_INVALID, "bottom-up predictor not configured");
+  if (h->post_pending) SB_CUDA(h, cudaStreamWaitEvent(h->stream, h->post_done_ev, 0));
+  return SB_OK;
+}
+
+// The stream post-processing runs on (consumers such as the NCCL gather can be queued behind it).
+int sb_get_post_stream(sb_handle_t h, void** out_stream) {
+  if (!h || !out_stream) return sb_fail(h, SB_ERR_INVALID, "null argument");
+  *out_stream = (void*)h->post_stream;
   return SB_OK;
 }
 
@@ -488,6 +531,7 @@ static int fetch_graph_ws(sb_handle_s* h, SbPostWs& ws, const int* edges_host, i
   std::vector<int> np(B), ncnt((size_t)B * C), nlist((size_t)B * C * K);
   std::vector<float> mat((size_t)B * E * K * K);
   SB_CUDA(h, cudaStreamSynchronize(h->stream));
+  SB_CUDA(h, cudaStreamSynchronize(h->post_stream));
   SB_CUDA(h, cudaMemcpy(np.data(), ws.n_peaks, (size_t)B * 4, cudaMemcpyDeviceToHost));
   SB_CUDA(h, cudaMemcpy(ncnt.data(), ws.node_cnt, ncnt.size() * 4, cudaMemcpyDeviceToHost));
   SB_CUDA(h, cudaMemcpy(nlist.data(), ws.node_peaks, nlist.size() * 4, cudaMemcpyDeviceToHost));

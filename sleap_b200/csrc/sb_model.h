@@ -73,6 +73,7 @@ struct SbModel {
   sb_bottomup_params bu{};
   std::vector<int> bu_edges;
   bool bu_configured = false;
+  int guard_op = -1;      // first op that overwrites a head buffer the post-processing stream may still read
   sb_global_params gl{};
   bool gl_configured = false;
   float *gpart = nullptr, *gpoints = nullptr, *gvals = nullptr, *crop_off_dev = nullptr;
