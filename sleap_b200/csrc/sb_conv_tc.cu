@@ -68,6 +68,8 @@ struct TcParams {
   int htap_w[9];               // weight tap index
   int dx0;
   int halo_base_offset;        // 1: put (addr >> 7) & 7 into the descriptor's base-offset field
+  int n_stages;                // TMEM accumulator stages of the persistent kernels (2..8)
+  int ablate;                  // profiling only (SB_ABLATE): 1 no TMA, 2 no MMA, 4 no stores, 8 no TMEM loads
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -212,7 +214,7 @@ __device__ __forceinline__ void tc_epilogue_cols(const TcParams& P, const float*
       const int py = (y0 >> 1) + ((q * (32 / P.tw) + lr) >> 1), px = (x0 >> 1) + (lc >> 1);
       __half* pp = reinterpret_cast<__half*>(P.pool_out) + (((size_t)b * P.pool_H + py) * P.pool_W + px) * P.pool_Ctot +
                    P.pool_coff + n0 + c0;
-      __half2 h[8];
+      __align__(16) __half2 h[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(pv[2 * j], pv[2 * j + 1]);
       reinterpret_cast<uint4*>(pp)[0] = *reinterpret_cast<uint4*>(&h[0]);
@@ -228,7 +230,7 @@ __device__ __forceinline__ void tc_epilogue_cols(const TcParams& P, const float*
   } else {
     __half* po = reinterpret_cast<__half*>(P.out) + pix * P.out_Ctot + P.out_coff + n0 + c0;
     if (n0 + c0 + 16 <= P.Cout) {
-      __half2 h[8];
+      __align__(16) __half2 h[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
       reinterpret_cast<uint4*>(po)[0] = *reinterpret_cast<uint4*>(&h[0]);
@@ -381,9 +383,9 @@ __global__ void __launch_bounds__(192) k_conv_tc_persist(const __grid_constant__
   uint64_t* bars = reinterpret_cast<uint64_t*>(a_ring + (size_t)P.n_a_slots * P.a_slot_bytes);
   uint64_t* fullA = bars;
   uint64_t* emptyA = fullA + P.n_a_slots;
-  uint64_t* tfull = emptyA + P.n_a_slots;     // [2]
-  uint64_t* tempty = tfull + 2;               // [2]
-  uint64_t* wbar = tempty + 2;
+  uint64_t* tfull = emptyA + P.n_a_slots;     // [n_stages]
+  uint64_t* tempty = tfull + P.n_stages;      // [n_stages]
+  uint64_t* wbar = tempty + P.n_stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
   float* s_par = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~(uintptr_t)15);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -391,7 +393,7 @@ __global__ void __launch_bounds__(192) k_conv_tc_persist(const __grid_constant__
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < P.n_a_slots; ++i) { mbar_init(smem_u32(fullA + i), 1); mbar_init(smem_u32(emptyA + i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(tfull + i), 1); mbar_init(smem_u32(tempty + i), 4); }
+    for (int i = 0; i < P.n_stages; ++i) { mbar_init(smem_u32(tfull + i), 1); mbar_init(smem_u32(tempty + i), 4); }
     mbar_init(smem_u32(wbar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -433,13 +435,11 @@ __global__ void __launch_bounds__(192) k_conv_tc_persist(const __grid_constant__
     mbar_wait(smem_u32(wbar), 0, 12);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     int sa = 0, stage = 0;
-    uint32_t pha = 0, eph0 = 0, eph1 = 0;
+    uint32_t pha = 0, eph = 0;
     const uint64_t desc_hi = make_desc(0, P.row_bytes, P.layout_type);
     const uint32_t w_base = smem_u32(w_res);
     for (int t = blockIdx.x; t < P.n_tiles_total; t += gridDim.x) {
-      const uint32_t eph = stage ? eph1 : eph0;
       mbar_wait(smem_u32(tempty + stage), eph ^ 1, 13);
-      if (stage) eph1 ^= 1; else eph0 ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t d_tmem = tmem_base + (uint32_t)(stage * P.N);
       for (int ch = 0; ch < P.n_chunks; ++ch) {
@@ -469,18 +469,17 @@ __global__ void __launch_bounds__(192) k_conv_tc_persist(const __grid_constant__
       }
       if (elect_one()) tc_commit(smem_u32(tfull + stage));
       __syncwarp();
-      stage ^= 1;
+      if (++stage == P.n_stages) { stage = 0; eph ^= 1; }
     }
   } else if (warp >= 2) {
     // ------------------------------ epilogue warps ----------------------------
     const int q = warp & 3;                       // TMEM lane quadrant this warp may access
     int stage = 0;
-    uint32_t fph[2] = {0, 0};
+    uint32_t fph = 0;
     for (int t = blockIdx.x; t < P.n_tiles_total; t += gridDim.x) {
       const int b = t / P.tiles_per_img, r = t - b * P.tiles_per_img;
       const int y0 = (r / P.tiles_x) * TH, x0 = (r % P.tiles_x) * TW;
-      mbar_wait(smem_u32(tfull + stage), fph[stage], 15);
-      fph[stage] ^= 1;
+      mbar_wait(smem_u32(tfull + stage), fph, 15);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int m = q * 32 + lane;
       const int iy = y0 + m / TW, ix = x0 + m % TW;
@@ -495,7 +494,7 @@ __global__ void __launch_bounds__(192) k_conv_tc_persist(const __grid_constant__
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(tempty + stage));
-      stage ^= 1;
+      if (++stage == P.n_stages) { stage = 0; fph ^= 1; }
     }
   }
   __syncwarp();
@@ -506,6 +505,28 @@ __global__ void __launch_bounds__(192) k_conv_tc_persist(const __grid_constant__
   }
 }
 
+
+
+// Walks the tiles t = first, first + stride, ... of a (batch, tiles_y, tiles_x) grid without
+// integer divisions in the loop (each role warp of the persistent kernels keeps one of these).
+struct TileIter {
+  int b, ty, tx;            // current tile
+  int sb, sy, sx;           // stride decomposed into (batch, tile row, tile col) steps
+  int tiles_x, tiles_y;
+  __device__ __forceinline__ void init(int first, int stride, int tx_n, int ty_n) {
+    tiles_x = tx_n; tiles_y = ty_n;
+    const int per = tx_n * ty_n;
+    b = first / per; int r = first - b * per; ty = r / tx_n; tx = r - ty * tx_n;
+    sb = stride / per; r = stride - sb * per; sy = r / tx_n; sx = r - sy * tx_n;
+  }
+  __device__ __forceinline__ void next() {
+    tx += sx;
+    if (tx >= tiles_x) { tx -= tiles_x; ++ty; }
+    ty += sy;
+    if (ty >= tiles_y) { ty -= tiles_y; ++b; }
+    b += sb;
+  }
+};
 
 // K-major swizzled descriptor whose start address is NOT aligned to the swizzle repeat (8 rows):
 // the matrix base offset field (bits [49,52)) carries the phase (address >> 7) & 7.
@@ -537,8 +558,8 @@ __global__ void __launch_bounds__(192) k_conv_tc_halo(const __grid_constant__ CU
   uint64_t* fullA = bars;
   uint64_t* emptyA = fullA + P.n_a_slots;
   uint64_t* tfull = emptyA + P.n_a_slots;
-  uint64_t* tempty = tfull + 2;
-  uint64_t* wbar = tempty + 2;
+  uint64_t* tempty = tfull + P.n_stages;
+  uint64_t* wbar = tempty + P.n_stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
   float* s_par = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~(uintptr_t)15);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -547,7 +568,7 @@ __global__ void __launch_bounds__(192) k_conv_tc_halo(const __grid_constant__ CU
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < P.n_a_slots; ++i) { mbar_init(smem_u32(fullA + i), 1); mbar_init(smem_u32(emptyA + i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(tfull + i), 1); mbar_init(smem_u32(tempty + i), 4); }
+    for (int i = 0; i < P.n_stages; ++i) { mbar_init(smem_u32(tfull + i), 1); mbar_init(smem_u32(tempty + i), 4); }
     mbar_init(smem_u32(wbar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -570,14 +591,18 @@ __global__ void __launch_bounds__(192) k_conv_tc_halo(const __grid_constant__ CU
                     P.used_taps[u]);
     int sa = 0;
     uint32_t pha = 0;
-    for (int t = blockIdx.x; t < P.n_tiles_total; t += gridDim.x) {
-      const int b = t / P.tiles_per_img, r = t - b * P.tiles_per_img;
-      const int y0 = (r / P.tiles_x) * THH, x0 = (r % P.tiles_x) * TWH;
+    TileIter it;
+    it.init(blockIdx.x, gridDim.x, P.tiles_x, P.tiles_per_img / P.tiles_x);
+    for (int t = blockIdx.x; t < P.n_tiles_total; t += gridDim.x, it.next()) {
+      const int b = it.b, y0 = it.ty * THH, x0 = it.tx * TWH;
       for (int ch = 0; ch < P.n_chunks; ++ch) {
         mbar_wait(smem_u32(emptyA + sa), pha ^ 1, 21);
-        mbar_expect_tx(smem_u32(fullA + sa), (uint32_t)P.a_tx_bytes);
-        tma_load_4d(smem_u32(a_ring + (size_t)sa * P.a_slot_bytes), &mapA, smem_u32(fullA + sa), ch * P.KC, x0 + P.dx0,
-                    y0 + P.dy0, b);
+        if (P.ablate & 1) { mbar_arrive(smem_u32(fullA + sa)); }
+        else {
+          mbar_expect_tx(smem_u32(fullA + sa), (uint32_t)P.a_tx_bytes);
+          tma_load_4d(smem_u32(a_ring + (size_t)sa * P.a_slot_bytes), &mapA, smem_u32(fullA + sa), ch * P.KC, x0 + P.dx0,
+                      y0 + P.dy0, b);
+        }
         if (++sa == P.n_a_slots) { sa = 0; pha ^= 1; }
       }
     }
@@ -585,51 +610,58 @@ __global__ void __launch_bounds__(192) k_conv_tc_halo(const __grid_constant__ CU
     mbar_wait(smem_u32(wbar), 0, 22);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     int sa = 0, stage = 0;
-    uint32_t pha = 0, eph0 = 0, eph1 = 0;
-    const uint64_t descb_hi = make_desc(0, P.row_bytes, P.layout_type);
+    uint32_t pha = 0, eph = 0;
     const uint32_t w_base = smem_u32(w_res);
     const int sbo = PITCH * P.row_bytes;
+    // per-tap constants, computed once per CTA (fully unrolled -> registers)
+    const uint64_t desca_hi = make_desc_unaligned(0, sbo, P.layout_type, 0);
+    uint32_t tap_aoff[9];      // (start-address offset of the tap inside the halo tile) >> 4
+    uint64_t tap_db[9];        // B descriptor of the tap for chunk 0
+#pragma unroll
+    for (int tp = 0; tp < 9; ++tp) {
+      const int tq = tp < P.n_htaps ? tp : 0;
+      tap_aoff[tp] = (uint32_t)(P.htap_off_rows[tq] * P.row_bytes) >> 4;
+      tap_db[tp] = make_desc(w_base + (uint32_t)(P.slot_of_tap[P.htap_w[tq]] * P.w_slot_bytes), P.row_bytes, P.layout_type);
+    }
+    const uint32_t chunk_db_step = (uint32_t)(P.n_used_taps * P.w_slot_bytes) >> 4;
     for (int t = blockIdx.x; t < P.n_tiles_total; t += gridDim.x) {
-      const uint32_t eph = stage ? eph1 : eph0;
       mbar_wait(smem_u32(tempty + stage), eph ^ 1, 23);
-      if (stage) eph1 ^= 1; else eph0 ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t d_tmem = tmem_base + (uint32_t)(stage * P.N);
       for (int ch = 0; ch < P.n_chunks; ++ch) {
         mbar_wait(smem_u32(fullA + sa), pha, 24);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_base = smem_u32(a_ring + (size_t)sa * P.a_slot_bytes);
+        const uint64_t da0 = desca_hi + (uint64_t)(smem_u32(a_ring + (size_t)sa * P.a_slot_bytes) >> 4);
+        const uint32_t dbo = (uint32_t)ch * chunk_db_step;
+        if (elect_one()) {
 #pragma unroll
-        for (int tp = 0; tp < 9; ++tp) {
-          if (tp >= P.n_htaps) break;
-          const int slot = ch * P.n_used_taps + P.slot_of_tap[P.htap_w[tp]];
-          const uint32_t a_addr = a_base + (uint32_t)(P.htap_off_rows[tp] * P.row_bytes);
-          const uint64_t da = make_desc_unaligned(a_addr, sbo, P.layout_type, P.halo_base_offset);
-          const uint64_t db = descb_hi + (uint64_t)((w_base + (uint32_t)(slot * P.w_slot_bytes)) >> 4);
-          if (elect_one()) {
+          for (int tp = 0; tp < 9; ++tp) {
+            if (tp < P.n_htaps && !(P.ablate & 2)) {
+              const uint64_t da = da0 + tap_aoff[tp];
+              const uint64_t db = tap_db[tp] + dbo;
 #pragma unroll
-            for (int k = 0; k < KSTEPS; ++k)
-              tc_mma_f16(d_tmem, da + 2 * k, db + 2 * k, P.idesc, (ch | tp | k) ? 1u : 0u);
+              for (int k = 0; k < KSTEPS; ++k)
+                tc_mma_f16(d_tmem, da + 2 * k, db + 2 * k, P.idesc, (ch | tp | k) ? 1u : 0u);
+            }
           }
-          __syncwarp();
+          tc_commit(smem_u32(emptyA + sa));
         }
-        if (elect_one()) tc_commit(smem_u32(emptyA + sa));
         __syncwarp();
         if (++sa == P.n_a_slots) { sa = 0; pha ^= 1; }
       }
       if (elect_one()) tc_commit(smem_u32(tfull + stage));
       __syncwarp();
-      stage ^= 1;
+      if (++stage == P.n_stages) { stage = 0; eph ^= 1; }
     }
   } else if (warp >= 2) {
     const int q = warp & 3;
     int stage = 0;
-    uint32_t fph[2] = {0, 0};
-    for (int t = blockIdx.x; t < P.n_tiles_total; t += gridDim.x) {
-      const int b = t / P.tiles_per_img, r = t - b * P.tiles_per_img;
-      const int y0 = (r / P.tiles_x) * THH, x0 = (r % P.tiles_x) * TWH;
-      mbar_wait(smem_u32(tfull + stage), fph[stage], 25);
-      fph[stage] ^= 1;
+    uint32_t fph = 0;
+    TileIter it;
+    it.init(blockIdx.x, gridDim.x, P.tiles_x, P.tiles_per_img / P.tiles_x);
+    for (int t = blockIdx.x; t < P.n_tiles_total; t += gridDim.x, it.next()) {
+      const int b = it.b, y0 = it.ty * THH, x0 = it.tx * TWH;
+      mbar_wait(smem_u32(tfull + stage), fph, 25);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int m = q * 32 + lane;
       const int iy = y0 + m / TWH, ix = x0 + m % TWH;
@@ -637,14 +669,19 @@ __global__ void __launch_bounds__(192) k_conv_tc_halo(const __grid_constant__ CU
       const size_t pix = ((size_t)b * P.out_H + (iy * P.oy_mul + P.oy_add)) * P.out_W + (ix * P.ox_mul + P.ox_add);
       for (int c0 = 0; c0 < P.N; c0 += 16) {
         uint32_t r16[16];
-        tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(stage * P.N + c0), r16);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        tc_epilogue_cols(P, s_par, r16, 0, c0, valid, pix, b, x0, y0, q, lane);
+        if (P.ablate & 8) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) r16[j] = (uint32_t)(lane + j);
+        } else {
+          tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(stage * P.N + c0), r16);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
+        tc_epilogue_cols(P, s_par, r16, 0, c0, valid && !(P.ablate & 4), pix, b, x0, y0, q, lane);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(tempty + stage));
-      stage ^= 1;
+      if (++stage == P.n_stages) { stage = 0; fph ^= 1; }
     }
   }
   __syncwarp();
@@ -780,6 +817,18 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
   L.smem = (size_t)P.n_a_slots * P.a_slot_bytes + (size_t)P.n_b_slots * P.b_slot_bytes + 1024 /*align slack*/ +
            (size_t)(2 * P.n_a_slots + 2 * P.n_b_slots + 1) * 8 + 64 + 3 * 256 * sizeof(float);
   L.grid = dim3(P.tiles_x * tiles_y, plan->Cout_pad / N, 1 /* z = batch, set at launch */);
+  {
+    // never let more CTAs become co-resident than TMEM can serve without waiting inside tcgen05.alloc
+    cudaFuncAttributes fa;
+    const void* fn = KC == 16 ? (const void*)k_conv_tc<1> : (KC == 32 ? (const void*)k_conv_tc<2> : (const void*)k_conv_tc<4>);
+    if (cudaFuncGetAttributes(&fa, fn) == cudaSuccess) {
+      const int by_regs = 65536 / std::max(1, ((fa.numRegs + 7) / 8 * 8) * 128);
+      const int by_smem = (int)((227 * 1024) / (L.smem + fa.sharedSizeBytes + 1024));
+      const int hw_occ = std::max(1, std::min(std::min(by_regs, by_smem), 32));
+      const int tmem_occ = 512 / P.tmem_cols;
+      if (hw_occ > tmem_occ) L.smem = std::max(L.smem, (size_t)(227 * 1024) / tmem_occ - 2048);
+    }
+  }
   // persistent variant when the whole filter bank of this launch fits in shared memory
   P.persistent = 0;
   P.tw = TW;
@@ -807,16 +856,29 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
       // activation ring: two tiles of look-ahead (2 x n_groups halo tiles per chunk) when it fits
       int na = (int)((budget - w_bytes) / P.a_slot_bytes);
       Q.n_a_slots = std::max(2, std::min(na, std::max(6, 2 * n_groups)));
+      // accumulator stages: as many as TMEM allows (the mbarrier hand-offs between the MMA and the
+      // epilogue warps cost ~0.5 us each; a deep ring keeps both sides from ever sleeping)
+      int ns = getenv("SB_TMEM_STAGES") ? atoi(getenv("SB_TMEM_STAGES")) : 8;
+      while (ns > 2 && ns * N > 512) ns >>= 1;
+      Q.n_stages = ns;
       int c2 = 32;
-      while (c2 < 2 * N) c2 <<= 1;
+      while (c2 < ns * N) c2 <<= 1;
       Q.tmem_cols = c2;
-      L.smem_p = w_bytes + (size_t)Q.n_a_slots * P.a_slot_bytes + 1024 + (size_t)(2 * Q.n_a_slots + 5) * 8 + 64 + 3 * 256 * sizeof(float);
+      L.smem_p = w_bytes + (size_t)Q.n_a_slots * P.a_slot_bytes + 1024 + (size_t)(2 * Q.n_a_slots + 2 * 8 + 1) * 8 + 64 + 3 * 256 * sizeof(float);
+      // co-residency the hardware may reach (registers / shared memory); the TMEM demand of that many
+      // CTAs must fit the 512 columns of the SM outright, because a CTA that has to wait inside
+      // tcgen05.alloc for a neighbour to exit was observed to fault on sm_100a
       cudaFuncAttributes fa;
       int occ = 1;
-      if (cudaFuncGetAttributes(&fa, k_conv_tc_persist<4>) == cudaSuccess) {
-        const int by_regs = 65536 / std::max(1, fa.numRegs * 192);
+      const void* fn = KC == 16 ? (const void*)k_conv_tc_persist<1> : (KC == 32 ? (const void*)k_conv_tc_persist<2> : (const void*)k_conv_tc_persist<4>);
+      if (cudaFuncGetAttributes(&fa, fn) == cudaSuccess) {
+        const int by_regs = 65536 / std::max(1, ((fa.numRegs + 7) / 8 * 8) * 192);
         const int by_smem = (int)((227 * 1024) / (L.smem_p + fa.sharedSizeBytes + 1024));
-        occ = std::max(1, std::min(std::min(by_regs, by_smem), std::min(512 / c2, 8)));
+        occ = std::max(1, std::min(std::min(by_regs, by_smem), 16));
+        auto cols_for = [&](int nst) { int c = 32; while (c < nst * N) c <<= 1; return c; };
+        while (occ * Q.tmem_cols > 512 && Q.n_stages > 2) { Q.n_stages >>= 1; Q.tmem_cols = cols_for(Q.n_stages); }
+        if (occ * Q.tmem_cols > 512) { Q.n_stages = 1; Q.tmem_cols = cols_for(1); }        // last resort: single stage
+        if (occ * Q.tmem_cols > 512) { L.smem_p = std::max(L.smem_p, (size_t)(227 * 1024) / (512 / Q.tmem_cols) - 2048); occ = 512 / Q.tmem_cols; }
       }
       L.occ = occ;
       L.has_persist = true;
@@ -832,6 +894,7 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
     for (int g = 0; g < n_groups; ++g) dxmin = std::min(dxmin, groups[g].dx);
     Hp.dx0 = dxmin;
     Hp.halo_base_offset = getenv("SB_HALO_BASEOFF") ? atoi(getenv("SB_HALO_BASEOFF")) : 0;
+    Hp.ablate = getenv("SB_ABLATE") ? atoi(getenv("SB_ABLATE")) : 0;
     Hp.n_htaps = 0;
     for (int g = 0; g < n_groups; ++g)
       for (int t = 0; t < groups[g].n_taps; ++t) {
@@ -846,13 +909,21 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
     if (w_bytes + 2 * (size_t)Hp.a_slot_bytes <= budget) {
       int na = (int)((budget - w_bytes) / Hp.a_slot_bytes);
       Hp.n_a_slots = std::max(2, std::min(na, 6));
-      L.smem_h = w_bytes + (size_t)Hp.n_a_slots * Hp.a_slot_bytes + 1024 + (size_t)(2 * Hp.n_a_slots + 5) * 8 + 64 + 3 * 256 * sizeof(float);
+      L.smem_h = w_bytes + (size_t)Hp.n_a_slots * Hp.a_slot_bytes + 1024 + (size_t)(2 * Hp.n_a_slots + 2 * 8 + 1) * 8 + 64 + 3 * 256 * sizeof(float);
       cudaFuncAttributes fa;
       int occ = 1;
-      if (cudaFuncGetAttributes(&fa, k_conv_tc_halo<4>) == cudaSuccess) {
-        const int by_regs = 65536 / std::max(1, fa.numRegs * 192);
+      const void* fn = KC == 16 ? (const void*)k_conv_tc_halo<1> : (KC == 32 ? (const void*)k_conv_tc_halo<2> : (const void*)k_conv_tc_halo<4>);
+      if (cudaFuncGetAttributes(&fa, fn) == cudaSuccess) {
+        const int by_regs = 65536 / std::max(1, ((fa.numRegs + 7) / 8 * 8) * 192);
         const int by_smem = (int)((227 * 1024) / (L.smem_h + fa.sharedSizeBytes + 1024));
-        occ = std::max(1, std::min(std::min(by_regs, by_smem), std::min(512 / Hp.tmem_cols, 8)));
+        occ = std::max(1, std::min(std::min(by_regs, by_smem), 16));
+        auto cols_for = [&](int nst) { int c = 32; while (c < nst * N) c <<= 1; return c; };
+        Hp.n_stages = getenv("SB_TMEM_STAGES") ? atoi(getenv("SB_TMEM_STAGES")) : 8;
+        while (Hp.n_stages > 2 && Hp.n_stages * N > 512) Hp.n_stages >>= 1;
+        Hp.tmem_cols = cols_for(Hp.n_stages);
+        while (occ * Hp.tmem_cols > 512 && Hp.n_stages > 2) { Hp.n_stages >>= 1; Hp.tmem_cols = cols_for(Hp.n_stages); }
+        if (occ * Hp.tmem_cols > 512) { Hp.n_stages = 1; Hp.tmem_cols = cols_for(1); }
+        if (occ * Hp.tmem_cols > 512) { L.smem_h = std::max(L.smem_h, (size_t)(227 * 1024) / (512 / Hp.tmem_cols) - 2048); occ = 512 / Hp.tmem_cols; }
       }
       L.occ_h = occ;
       cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)ib.W, (cuuint64_t)ib.H, (cuuint64_t)m->B};
@@ -989,6 +1060,7 @@ static void launch_variant(sb_handle_s* h, TcLaunch& L, int B, int variant, cuda
     TcParams P = L.PP;
     P.n_tiles_total = P.tiles_per_img * B;
     const int grid = std::max(1, std::min(P.n_tiles_total, h->sm_count * L.occ));
+    if (getenv("SB_DEBUG_LAUNCH")) fprintf(stderr, "[persist] KC=%d N=%d stages=%d cols=%d occ=%d grid=%d slots=%d smem=%zu tiles=%d\n", P.KC, P.N, P.n_stages, P.tmem_cols, L.occ, grid, P.n_a_slots, L.smem_p, P.n_tiles_total);
     switch (P.KC) {
       case 16: k_conv_tc_persist<1><<<grid, 192, L.smem_p, stream>>>(L.mapA, L.mapB, P); break;
       case 32: k_conv_tc_persist<2><<<grid, 192, L.smem_p, stream>>>(L.mapA, L.mapB, P); break;

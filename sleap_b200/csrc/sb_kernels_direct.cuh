@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256) k_conv_first(const TI* __restrict__ img, 
     __half* po = out + (((size_t)b * Hnet + oy) * Wnet + ox0 + p) * out_Ctot + out_coff;
 #pragma unroll
     for (int q = 0; q < COUT / 8; ++q) {
-      __half2 h[4];
+      __align__(16) __half2 h[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float a = acc[p][8 * q + 2 * j], c2 = acc[p][8 * q + 2 * j + 1];
