@@ -191,6 +191,16 @@ int sb_infer_bottomup(sb_handle_t h, int model_id, const uint8_t* frames_host, i
                       float* out_instance_peaks, float* out_instance_peak_vals,
                       float* out_instance_scores, int32_t* out_n_valid, int32_t* out_flags);
 int sb_infer_bottomup_dev(sb_handle_t h, int model_id, const uint8_t* frames_dev, int B);
+/* Streaming form of sb_infer_bottomup for many batches (sleap/nn/inference.py:377-420, the
+ * Predictor batch loop): sb_bottomup_submit queues the H2D copy (copy stream), the network and the
+ * post-processing of one batch into slot 0/1 and returns; sb_bottomup_collect blocks until that
+ * slot's results are in host memory.  Submitting batch i+1 before collecting batch i overlaps its
+ * upload with the compute of batch i.  frames_host should be pinned for a truly asynchronous copy. */
+int sb_bottomup_submit(sb_handle_t h, int model_id, const uint8_t* frames_host, int B, int slot);
+int sb_bottomup_collect(sb_handle_t h, int model_id, int slot, int B, float* out_instance_peaks,
+                        float* out_instance_peak_vals, float* out_instance_scores,
+                        int32_t* out_n_valid, int32_t* out_flags);
+
 /* sb_infer_bottomup_dev returns as soon as the work is queued: the network runs on the handle's
  * stream and the post-processing on a second stream, so that it overlaps the network of the next
  * call.  sb_bottomup_wait_results makes the handle's stream wait (device side) for the results of

@@ -90,6 +90,8 @@ _SIGS = {
     "sb_bottomup_configure": [c_void_p, c_int, POINTER(BottomUpParams)],
     "sb_infer_bottomup": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "sb_infer_bottomup_dev": [c_void_p, c_int, c_void_p, c_int],
+    "sb_bottomup_submit": [c_void_p, c_int, c_void_p, c_int, c_int],
+    "sb_bottomup_collect": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "sb_bottomup_wait_results": [c_void_p, c_int],
     "sb_get_post_stream": [c_void_p, POINTER(c_void_p)],
     "sb_bottomup_device_outputs": [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),

@@ -37,6 +37,14 @@ void sb_models_free(sb_handle_s* h) {
     if (m->gpart) cudaFree(m->gpart);
     if (m->gpoints) cudaFree(m->gpoints);
     if (m->gvals) cudaFree(m->gvals);
+    for (int i = 0; i < 2; ++i) {
+      if (m->frames_slot[i]) cudaFree(m->frames_slot[i]);
+      if (m->stage_host[i]) cudaFreeHost(m->stage_host[i]);
+      if (m->h2d_done_ev[i]) cudaEventDestroy(m->h2d_done_ev[i]);
+      if (m->frames_free_ev[i]) cudaEventDestroy(m->frames_free_ev[i]);
+      if (m->result_ev[i]) cudaEventDestroy(m->result_ev[i]);
+    }
+    if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     sb_post_ws_free(m->ws);
     sb_conv_tc_release(m);
     delete m;
@@ -509,6 +517,75 @@ int sb_bottomup_wait_results(sb_handle_t h, int model_id) {
 int sb_get_post_stream(sb_handle_t h, void** out_stream) {
   if (!h || !out_stream) return sb_fail(h, SB_ERR_INVALID, "null argument");
   *out_stream = (void*)h->post_stream;
+  return SB_OK;
+}
+
+// Asynchronous, double-buffered variant of sb_infer_bottomup for streaming many batches: submit
+// batch i+1 (its H2D copy runs on a copy stream) while batch i computes, then collect batch i.
+// Layout of the pinned staging record per slot: peaks | vals | scores | n_valid | flags.
+static size_t stage_floats(const SbModel* m) {
+  const size_t I = m->bu.max_instances, C = m->bu.n_nodes;
+  return (size_t)m->B * (I * C * 3 + I + 2);
+}
+
+int sb_bottomup_submit(sb_handle_t h, int model_id, const uint8_t* frames_host, int B, int slot) {
+  SbModel* m = get_model(h, model_id);
+  if (!m || !m->bu_configured) return sb_fail(h, SB_ERR_INVALID, "bottom-up predictor not configured");
+  if (slot < 0 || slot > 1 || B <= 0 || B > m->B) return sb_fail(h, SB_ERR_INVALID, "bad slot / batch");
+  SB_CUDA(h, cudaSetDevice(h->device));
+  if (!m->copy_stream) {
+    SB_CUDA(h, cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      SB_CUDA(h, cudaEventCreateWithFlags(&m->h2d_done_ev[i], cudaEventDisableTiming));
+      SB_CUDA(h, cudaEventCreateWithFlags(&m->frames_free_ev[i], cudaEventDisableTiming));
+      SB_CUDA(h, cudaEventCreateWithFlags(&m->result_ev[i], cudaEventDisableTiming));
+    }
+  }
+  const size_t fbytes = (size_t)m->B * m->Hin * m->Win * m->Cin;
+  for (int i = 0; i < 2; ++i) {
+    if (!m->frames_slot[i]) SB_CUDA(h, cudaMalloc(&m->frames_slot[i], fbytes));
+    if (!m->stage_host[i]) SB_CUDA(h, cudaHostAlloc((void**)&m->stage_host[i], stage_floats(m) * sizeof(float), cudaHostAllocDefault));
+  }
+  // H2D on the copy stream (after the network that last read this slot's frames has finished)
+  if (m->slot_used[slot]) SB_CUDA(h, cudaStreamWaitEvent(m->copy_stream, m->frames_free_ev[slot], 0));
+  SB_CUDA(h, cudaMemcpyAsync(m->frames_slot[slot], frames_host, (size_t)B * m->Hin * m->Win * m->Cin, cudaMemcpyHostToDevice, m->copy_stream));
+  SB_CUDA(h, cudaEventRecord(m->h2d_done_ev[slot], m->copy_stream));
+  SB_CUDA(h, cudaStreamWaitEvent(h->stream, m->h2d_done_ev[slot], 0));
+  int rc = sb_run_ops(h, m, m->frames_slot[slot], 1, B);
+  if (rc) return rc;
+  SB_CUDA(h, cudaEventRecord(m->frames_free_ev[slot], h->stream));
+  if ((rc = bottomup_post(h, m, B))) return rc;
+  cudaStream_t rs = h->post_pending ? h->post_stream : h->stream;
+  const size_t I = m->bu.max_instances, C = m->bu.n_nodes;
+  float* st = m->stage_host[slot];
+  SB_CUDA(h, cudaMemcpyAsync(st, m->ws.inst_peaks, (size_t)B * I * C * 2 * 4, cudaMemcpyDeviceToHost, rs));
+  st += (size_t)m->B * I * C * 2;
+  SB_CUDA(h, cudaMemcpyAsync(st, m->ws.inst_vals, (size_t)B * I * C * 4, cudaMemcpyDeviceToHost, rs));
+  st += (size_t)m->B * I * C;
+  SB_CUDA(h, cudaMemcpyAsync(st, m->ws.inst_scores, (size_t)B * I * 4, cudaMemcpyDeviceToHost, rs));
+  st += (size_t)m->B * I;
+  SB_CUDA(h, cudaMemcpyAsync(st, m->ws.n_inst, (size_t)B * 4, cudaMemcpyDeviceToHost, rs));
+  st += m->B;
+  SB_CUDA(h, cudaMemcpyAsync(st, m->ws.flags, (size_t)B * 4, cudaMemcpyDeviceToHost, rs));
+  SB_CUDA(h, cudaEventRecord(m->result_ev[slot], rs));
+  m->slot_used[slot] = true;
+  return SB_OK;
+}
+
+int sb_bottomup_collect(sb_handle_t h, int model_id, int slot, int B, float* out_instance_peaks,
+                        float* out_instance_peak_vals, float* out_instance_scores, int32_t* out_n_valid,
+                        int32_t* out_flags) {
+  SbModel* m = get_model(h, model_id);
+  if (!m || !m->bu_configured) return sb_fail(h, SB_ERR_INVALID, "bottom-up predictor not configured");
+  if (slot < 0 || slot > 1 || !m->slot_used[slot] || B <= 0 || B > m->B) return sb_fail(h, SB_ERR_INVALID, "bad slot / batch");
+  SB_CUDA(h, cudaEventSynchronize(m->result_ev[slot]));
+  const size_t I = m->bu.max_instances, C = m->bu.n_nodes;
+  const float* st = m->stage_host[slot];
+  memcpy(out_instance_peaks, st, (size_t)B * I * C * 2 * 4); st += (size_t)m->B * I * C * 2;
+  memcpy(out_instance_peak_vals, st, (size_t)B * I * C * 4); st += (size_t)m->B * I * C;
+  memcpy(out_instance_scores, st, (size_t)B * I * 4); st += (size_t)m->B * I;
+  memcpy(out_n_valid, st, (size_t)B * 4); st += m->B;
+  if (out_flags) memcpy(out_flags, st, (size_t)B * 4);
   return SB_OK;
 }
 

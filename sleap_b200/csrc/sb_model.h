@@ -73,7 +73,13 @@ struct SbModel {
   sb_bottomup_params bu{};
   std::vector<int> bu_edges;
   bool bu_configured = false;
-  int guard_op = -1;      // first op that overwrites a head buffer the post-processing stream may still read
+  int guard_op = -1;
+  // double-buffered asynchronous pipeline (sb_bottomup_submit / sb_bottomup_collect)
+  void* frames_slot[2] = {nullptr, nullptr};
+  float* stage_host[2] = {nullptr, nullptr};     // pinned result staging
+  cudaEvent_t h2d_done_ev[2] = {nullptr, nullptr}, frames_free_ev[2] = {nullptr, nullptr}, result_ev[2] = {nullptr, nullptr};
+  bool slot_used[2] = {false, false};
+  cudaStream_t copy_stream = nullptr;      // first op that overwrites a head buffer the post-processing stream may still read
   sb_global_params gl{};
   bool gl_configured = false;
   float *gpart = nullptr, *gpoints = nullptr, *gvals = nullptr, *crop_off_dev = nullptr;

@@ -474,6 +474,48 @@ class BottomUpInferenceModel(InferenceModel):
     def call(self, example):
         return self.bottomup_layer.call(example)
 
+    def predict_batches(self, data, batch_size: int = 4):
+        """Generator over per-batch result dicts for a stack of uint8 frames (the Predictor batch loop,
+        inference.py:377-420), double-buffered: the upload of batch i+1 overlaps the compute of batch i."""
+        layer = self.bottomup_layer
+        imgs = _images_of(data)
+        n = len(imgs)
+        if n == 0:
+            return
+        first = layer._prep(np.asarray(imgs[0:min(n, batch_size)]))
+        if first.dtype != np.uint8 or layer.return_confmaps or layer.return_pafs or layer.return_paf_graph:
+            for i in range(0, n, batch_size):        # generic (synchronous) path
+                yield self.predict_on_batch(np.asarray(imgs[i:i + batch_size]))
+            return
+        _, H, W, C = first.shape
+        layer._configure(batch_size, H, W, C)
+        m = layer.keras_model
+        I, N = layer.max_instances, layer.paf_scorer.n_nodes
+        starts = list(range(0, n, batch_size))
+        keep = {}
+
+        def submit(k):
+            batch = layer._prep(np.asarray(imgs[starts[k]:starts[k] + batch_size]))
+            keep[k % 2] = batch                       # the async copy reads this host buffer until collect()
+            m.handle.call("sb_bottomup_submit", m.model_id, ptr(batch), batch.shape[0], k % 2)
+            return batch.shape[0]
+
+        sizes = {0: submit(0)}
+        for k in range(len(starts)):
+            if k + 1 < len(starts):
+                sizes[k + 1] = submit(k + 1)
+            B = sizes.pop(k)
+            ip = np.zeros((B, I, N, 2), np.float32); iv = np.zeros((B, I, N), np.float32)
+            isc = np.zeros((B, I), np.float32); nv = np.zeros((B,), np.int32); fl = np.zeros((B,), np.int32)
+            m.handle.call("sb_bottomup_collect", m.model_id, k % 2, B, ptr(ip), ptr(iv), ptr(isc), ptr(nv), ptr(fl))
+            w = int(nv.max()) if B else 0
+            yield {"instance_peaks": ip[:, :w], "instance_peak_vals": iv[:, :w], "instance_scores": isc[:, :w],
+                   "n_valid": nv.astype(np.int64), "flags": fl}
+
+    def predict(self, data, numpy: bool = True, batch_size: int = 4, **kwargs):
+        """sleap/nn/inference.py:989-1045 with the pipelined batch loop."""
+        return _merge_batches(list(self.predict_batches(data, batch_size)))
+
 
 # ------------------------------------------------------------------------------------------
 class PredictedInstance:
@@ -563,6 +605,15 @@ class Predictor:
 
     def _predict_generator(self, data):
         """:377-420: one predict_on_batch per batch (+ frame indices)."""
+        if hasattr(self.inference_model, "predict_batches"):      # pipelined device loop (upload i+1 || compute i)
+            i0 = 0
+            for ex in self.inference_model.predict_batches(_images_of(data), self.batch_size):
+                n = len(ex["n_valid"])
+                ex["frame_ind"] = np.arange(i0, i0 + n)
+                ex["video_ind"] = np.zeros(n, np.int64)
+                i0 += n
+                yield ex
+            return
         for i0, batch in self._batches(data):
             ex = self.inference_model.predict_on_batch(batch)
             ex["frame_ind"] = np.arange(i0, i0 + len(batch))

@@ -289,3 +289,25 @@ def test_tc_single_layers(cin, cout, k):
     w16 = torch.from_numpy(w1.astype(np.float16).astype(np.float32)).permute(3, 2, 0, 1)
     y = F.conv2d(x, w16, torch.from_numpy(b1), padding=k // 2).permute(0, 2, 3, 1).numpy()
     assert_allclose(outs, y, atol=2e-3 * max(1.0, np.abs(y).max()), rtol=2e-3)
+
+
+def test_pipelined_predict_matches_per_batch():
+    """submit/collect double buffering returns exactly what predict_on_batch returns, batch by batch."""
+    from sleap_b200.nn.inference import BottomUpPredictor
+    spec = _c4_small()
+    model, w, cm = _mk(spec, 1, 23, precision=0)
+    imgs = np.random.default_rng(8).integers(0, 256, size=(10, 256, 256, 1), dtype=np.uint8)
+    cms, _ = model.forward(imgs[:2])
+    thr = float(np.quantile(cms, 0.9995))
+    pred = BottomUpPredictor(model, synth.FLIES13_NODES, synth.FLIES13_EDGES, peak_threshold=thr, batch_size=4,
+                             max_peaks_per_sample=4096, max_node_peaks=64, max_instances_per_frame=128)
+    want = [pred.inference_model.predict_on_batch(imgs[i:i + 4]) for i in range(0, 10, 4)]
+    got = pred.predict(imgs, make_labels=False)
+    assert len(got) == 3
+    for g, x in zip(got, want):
+        assert_array_equal(g["n_valid"], x["n_valid"])
+        assert_array_equal(np.nan_to_num(g["instance_peaks"], nan=-1), np.nan_to_num(x["instance_peaks"], nan=-1))
+        assert_array_equal(np.nan_to_num(g["instance_scores"], nan=-1), np.nan_to_num(x["instance_scores"], nan=-1))
+    assert list(got[2]["frame_ind"]) == [8, 9]
+    merged = pred.inference_model.predict(imgs, batch_size=4)
+    assert merged["instance_peaks"].shape[0] == 10
