@@ -152,6 +152,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int row_bytes, int
   return d;
 }
 
+// 32-byte (256-bit) global store, sm_100: one full 32 B sector per thread and instruction
+__device__ __forceinline__ void st_global_256(void* p, const __half2 (&h)[8]) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(h);
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+               "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+
 // bias / BN scale / BN shift of output channels [n0, n0 + N) -> shared memory (zeros / ones beyond Cout)
 __device__ __forceinline__ void stage_params(const TcParams& P, float* s_par, int n0) {
   for (int i = threadIdx.x; i < P.N; i += blockDim.x) {
@@ -217,8 +224,11 @@ __device__ __forceinline__ void tc_epilogue_cols(const TcParams& P, const float*
       __align__(16) __half2 h[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(pv[2 * j], pv[2 * j + 1]);
-      reinterpret_cast<uint4*>(pp)[0] = *reinterpret_cast<uint4*>(&h[0]);
-      reinterpret_cast<uint4*>(pp)[1] = *reinterpret_cast<uint4*>(&h[4]);
+      if (((P.pool_Ctot | (P.pool_coff + n0)) & 15) == 0) st_global_256(pp, h);
+      else {
+        reinterpret_cast<uint4*>(pp)[0] = *reinterpret_cast<uint4*>(&h[0]);
+        reinterpret_cast<uint4*>(pp)[1] = *reinterpret_cast<uint4*>(&h[4]);
+      }
     }
   }
   if (!valid) return;
@@ -233,8 +243,11 @@ __device__ __forceinline__ void tc_epilogue_cols(const TcParams& P, const float*
       __align__(16) __half2 h[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-      reinterpret_cast<uint4*>(po)[0] = *reinterpret_cast<uint4*>(&h[0]);
-      reinterpret_cast<uint4*>(po)[1] = *reinterpret_cast<uint4*>(&h[4]);
+      if (((P.out_Ctot | (P.out_coff + n0)) & 15) == 0) st_global_256(po, h);
+      else {
+        reinterpret_cast<uint4*>(po)[0] = *reinterpret_cast<uint4*>(&h[0]);
+        reinterpret_cast<uint4*>(po)[1] = *reinterpret_cast<uint4*>(&h[4]);
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < 16; ++j)
@@ -692,6 +705,134 @@ __global__ void __launch_bounds__(192) k_conv_tc_halo(const __grid_constant__ CU
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// First layer on the tensor cores, fused with InferenceLayer.preprocess (inference.py:940-967):
+// raw uint8 / float frame -> * (1/255) -> zero pad -> 3x3 SAME conv + bias + ReLU -> fp16 NHWC.
+// K = 9 taps x CIN (9 or 27) is zero-padded to KPAD = 16 / 32; every thread gathers the 3x3
+// neighbourhood of "its" pixel and writes one K-major row of the A tile straight into the
+// 32B / 64B-swizzled UMMA layout (no TMA: the source is 1-3 bytes per pixel).  One MMA (two for
+// RGB) per 128-pixel tile; the epilogue is the shared tcgen05.ld path.
+template <typename TI, int CIN>
+__global__ void __launch_bounds__(128) k_conv_first_tc(const TI* __restrict__ img, int Hin, int Win, int Hnet, int Wnet,
+                                                       int tiles_x, int tiles_per_img, int n_tiles_total,
+                                                       const __half* __restrict__ wk /*[N][KPAD] fp16*/, int in_is_u8,
+                                                       const __grid_constant__ TcParams P) {
+  constexpr int KPAD = CIN == 1 ? 16 : 32;
+  constexpr int ROWB = KPAD * 2;                       // bytes per A / B row
+  constexpr int LAYOUT = CIN == 1 ? 6 : 4;             // SWIZZLE_32B / SWIZZLE_64B
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = base;                                   // 2 x (128 rows x ROWB): double buffered
+  uint8_t* sB = base + 2 * 128 * ROWB;                  // N rows x ROWB
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sB + 64 * ROWB);   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+  float* s_par = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~(uintptr_t)15);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  stage_params(P, s_par, 0);
+  // weights -> swizzled B tile: 16-byte chunk c of row r lands at chunk c ^ ((row address >> 7) & (ROWB/16 - 1))
+  for (int t = threadIdx.x; t < P.N * (ROWB / 16); t += 128) {
+    const int r = t / (ROWB / 16), c = t % (ROWB / 16);
+    const uint4 v = *reinterpret_cast<const uint4*>(wk + (size_t)r * KPAD + c * 8);
+    const int pc = c ^ (((r * ROWB) >> 7) & (ROWB / 16 - 1));
+    *reinterpret_cast<uint4*>(sB + r * ROWB + pc * 16) = v;
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(bar), 1);
+    mbar_init(smem_u32(bar + 1), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(P.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const float sc = in_is_u8 ? (1.0f / 255.0f) : 1.0f;
+  const int m = threadIdx.x;                            // A row = TMEM lane = tile pixel
+  const int ty = m / TW, tx = m % TW;
+
+  // gathers the 3x3 x CIN neighbourhood of this thread's pixel of tile (b, y0, x0) into A buffer `buf`
+  auto build = [&](int b, int y0, int x0, int buf) {
+    const int oy = y0 + ty, ox = x0 + tx;
+    __align__(16) __half row[KPAD];
+#pragma unroll
+    for (int k = 0; k < KPAD; ++k) row[k] = __float2half(0.f);
+    const TI* im = img + (size_t)b * Hin * Win * CIN;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy + ky - 1;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox + kx - 1;
+        const bool ok = iy >= 0 && iy < Hin && ix >= 0 && ix < Win;
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+          const float v = ok ? __fmul_rn((float)im[((size_t)iy * Win + ix) * CIN + ci], sc) : 0.f;
+          row[(ky * 3 + kx) * CIN + ci] = __float2half_rn(v);
+        }
+      }
+    }
+    uint8_t* dst = sA + buf * 128 * ROWB;
+#pragma unroll
+    for (int c = 0; c < ROWB / 16; ++c) {
+      const int pc = c ^ (((m * ROWB) >> 7) & (ROWB / 16 - 1));
+      *reinterpret_cast<uint4*>(dst + m * ROWB + pc * 16) = *reinterpret_cast<const uint4*>(&row[c * 8]);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+  };
+  auto issue = [&](int buf) {            // warp 0: one elected lane issues the MMA(s) of the tile staged in `buf`
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (elect_one()) {
+      const uint64_t da = make_desc(smem_u32(sA + buf * 128 * ROWB), ROWB, LAYOUT);
+      const uint64_t db = make_desc(smem_u32(sB), ROWB, LAYOUT);
+#pragma unroll
+      for (int k = 0; k < KPAD / 16; ++k) tc_mma_f16(tmem_base + (uint32_t)(buf * P.N), da + 2 * k, db + 2 * k, P.idesc, k ? 1u : 0u);
+      tc_commit(smem_u32(bar + buf));
+    }
+    __syncwarp();
+  };
+
+  TileIter it;
+  it.init(blockIdx.x, gridDim.x, tiles_x, tiles_per_img / tiles_x);
+  int t = blockIdx.x;
+  if (t < n_tiles_total) {
+    build(it.b, it.ty * TH, it.tx * TW, 0);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) issue(0);
+  }
+  // software pipeline: gather tile i+1 and issue its MMA while the MMA of tile i completes, then drain tile i
+  for (int i = 0; t < n_tiles_total; ++i, t += gridDim.x) {
+    const int b = it.b, y0 = it.ty * TH, x0 = it.tx * TW;
+    const int cur = i & 1, nxt = cur ^ 1;
+    const bool has_next = t + (int)gridDim.x < n_tiles_total;
+    it.next();
+    if (has_next) build(it.b, it.ty * TH, it.tx * TW, nxt);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();                      // A(i+1) staged; everyone is done reading TMEM stage `nxt` (tile i-1)
+    if (has_next && warp == 0) issue(nxt);
+    mbar_wait(smem_u32(bar + cur), (uint32_t)((i >> 1) & 1), 31);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int oy = y0 + ty, ox = x0 + tx;
+    const bool valid = (oy < Hnet) && (ox < Wnet);
+    const size_t pix = ((size_t)b * P.out_H + oy) * P.out_W + ox;
+    for (int c0 = 0; c0 < P.N; c0 += 16) {
+      uint32_t r16[16];
+      tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cur * P.N + c0), r16);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      tc_epilogue_cols(P, s_par, r16, 0, c0, valid, pix, b, x0, y0, warp, lane);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P.tmem_cols) : "memory");
+  }
+}
+
 // ------------------------------- host side ---------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -753,7 +894,10 @@ static bool tc_eligible(const SbModel* m, const SbOp& op) {
   return true;
 }
 
+void sb_conv_first_tc_release(const SbModel* m);
+
 void sb_conv_tc_release(SbModel* m) {
+  sb_conv_first_tc_release(m);
   for (SbConvTcPlan* p : m->tc_plans)
     if (p) { if (p->w16) cudaFree(p->w16); delete p; }
   m->tc_plans.clear();
@@ -1148,4 +1292,87 @@ int sb_conv_tc_launch(sb_handle_s* h, SbModel* m, int op_index, int B) {
   }
   for (size_t i = 1; i < n; ++i) SB_CUDA(h, cudaStreamWaitEvent(h->stream, h->join_ev[(i - 1) % 3], 0));
   return 0;
+}
+
+// ---- first layer on the tensor cores ----------------------------------------------------------
+struct SbFirstTc {
+  __half* wk = nullptr;   // [N][KPAD]
+  TcParams P;
+  int kpad = 16;
+};
+static std::vector<std::pair<const SbModel*, SbFirstTc*>> g_first_plans;
+
+bool sb_conv_first_tc_ok(const SbModel* m, const SbOp& cv) {
+  // same speed as the CUDA-core kernel (both are bound by the 16-channel output write); off by default
+  // because it rounds the input pixel to fp16 before the MAC.  SB_ENABLE_FIRST_TC=1 turns it on.
+  if (!getenv("SB_ENABLE_FIRST_TC")) return false;
+  const int co = cv.out_C();
+  return co == 16 || co == 32 || co == 64;
+}
+
+int sb_conv_first_tc_launch(sb_handle_s* h, SbModel* m, const SbOp& op, const void* frames_dev, int frames_are_u8, int B) {
+  SbFirstTc* fp = nullptr;
+  for (auto& pr : g_first_plans) if (pr.first == m) fp = pr.second;
+  const SbBuffer& ob = m->buffers[op.out_buf()];
+  const int Cin = op.in_C(), N = op.out_C();
+  if (!fp) {
+    fp = new SbFirstTc();
+    fp->kpad = Cin == 1 ? 16 : 32;
+    std::vector<__half> wk((size_t)N * fp->kpad, __float2half(0.f));
+    const float* w = m->weights_host.data() + op.w_off();     // [9][Cin][Cout]
+    for (int t = 0; t < 9; ++t)
+      for (int ci = 0; ci < Cin; ++ci)
+        for (int co = 0; co < N; ++co) wk[(size_t)co * fp->kpad + t * Cin + ci] = __float2half_rn(w[((size_t)t * Cin + ci) * N + co]);
+    SB_CUDA(h, cudaMalloc((void**)&fp->wk, wk.size() * sizeof(__half)));
+    SB_CUDA(h, cudaMemcpy(fp->wk, wk.data(), wk.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    TcParams& P = fp->P;
+    memset(&P, 0, sizeof(P));
+    P.H = ob.H; P.W = ob.W; P.N = N; P.Cout = N; P.tw = TW;
+    P.idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    int cols = 32;
+    while (cols < 2 * N) cols <<= 1;      // two accumulator stages
+    P.tmem_cols = cols;
+    P.out = ob.dev; P.out_f32 = 0; P.out_H = ob.H; P.out_W = ob.W; P.out_Ctot = ob.C; P.out_coff = op.out_coff();
+    P.oy_mul = 1; P.ox_mul = 1;
+    P.bias = op.b_off() >= 0 ? m->weights_dev + op.b_off() : nullptr;
+    P.relu = (op.flags() & SB_OPF_RELU) ? 1 : 0;
+    if (op.pool_buf() >= 0 && N % 16 == 0 && ob.H % 2 == 0 && ob.W % 2 == 0) {
+      const SbBuffer& pb = m->buffers[op.pool_buf()];
+      if (pb.C % 8 == 0 && op.pool_coff() % 8 == 0) { P.pool_out = pb.dev; P.pool_H = pb.H; P.pool_W = pb.W; P.pool_Ctot = pb.C; P.pool_coff = op.pool_coff(); }
+    }
+    g_first_plans.push_back({m, fp});
+  }
+  fp->P.out = ob.dev;
+  const int tiles_x = (ob.W + TW - 1) / TW, tiles_y = (ob.H + TH - 1) / TH;
+  const int n_tiles = tiles_x * tiles_y * B;
+  size_t smem = 1024 + 2 * 128 * 64 + 64 * 64 + 64 + 3 * 64 * sizeof(float) + 64;
+  const int occ = std::min(512 / fp->P.tmem_cols, 8);    // 64 regs x 128 threads -> at most 8 co-resident CTAs
+  if (occ < 8) {                                          // keep co-residency within what TMEM serves without waiting
+    smem = std::max(smem, (size_t)(227 * 1024) / occ - 2048);
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(k_conv_first_tc<unsigned char, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+      cudaFuncSetAttribute(k_conv_first_tc<unsigned char, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+      cudaFuncSetAttribute(k_conv_first_tc<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+      cudaFuncSetAttribute(k_conv_first_tc<float, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+      attr_done = true;
+    }
+  }
+  const int grid = std::max(1, std::min(n_tiles, h->sm_count * occ));
+#define LAUNCH_FIRST(TI, CIN_) k_conv_first_tc<TI, CIN_><<<grid, 128, smem, h->stream>>>((const TI*)frames_dev, m->Hin, m->Win, ob.H, ob.W, tiles_x, tiles_x * tiles_y, n_tiles, fp->wk, frames_are_u8, fp->P)
+  if (frames_are_u8) { if (Cin == 1) LAUNCH_FIRST(unsigned char, 1); else LAUNCH_FIRST(unsigned char, 3); }
+  else { if (Cin == 1) LAUNCH_FIRST(float, 1); else LAUNCH_FIRST(float, 3); }
+#undef LAUNCH_FIRST
+  SB_CHECK_LAUNCH(h);
+  return 0;
+}
+
+void sb_conv_first_tc_release(const SbModel* m) {
+  for (size_t i = 0; i < g_first_plans.size(); ++i)
+    if (g_first_plans[i].first == m) {
+      if (g_first_plans[i].second->wk) cudaFree(g_first_plans[i].second->wk);
+      delete g_first_plans[i].second;
+      g_first_plans.erase(g_first_plans.begin() + i);
+      return;
+    }
 }

@@ -193,6 +193,11 @@ static int run_ops_t(sb_handle_s* h, SbModel* m, const void* frames_dev, int fra
     SbBuffer& ob = m->buffers[op.out_buf()];
     if ((int)oi == m->guard_op && h->post_pending) SB_CUDA(h, cudaStreamWaitEvent(s, h->post_done_ev, 0));
     if (oi < m->skip_op.size() && m->skip_op[oi]) continue;     // 2x2 max-pool fused into the producing conv
+    if ((int)oi == fused_first && sb_conv_first_tc_ok(m, op)) {
+      int rc = sb_conv_first_tc_launch(h, m, op, frames_dev, frames_are_u8, B);
+      if (rc) return rc;
+      continue;
+    }
     if ((int)oi == fused_first) {
       const float* Wt = m->weights_dev + op.w_off();
       const float* bias = op.b_off() >= 0 ? m->weights_dev + op.b_off() : nullptr;

@@ -95,3 +95,7 @@ int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m);      // after buffers are al
 void sb_conv_tc_release(SbModel* m);
 bool sb_conv_tc_can(const SbModel* m, int op_index);
 int sb_conv_tc_launch(sb_handle_s* h, SbModel* m, int op_index, int B);
+
+// first layer fused with preprocessing on the tensor cores (sb_conv_tc.cu)
+bool sb_conv_first_tc_ok(const SbModel* m, const SbOp& conv);
+int sb_conv_first_tc_launch(sb_handle_s* h, SbModel* m, const SbOp& op, const void* frames_dev, int frames_are_u8, int B);
