@@ -379,9 +379,14 @@ def run_ours(args):
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
     achieved_tf = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
     step_ms = ms_max / args.steps
+    traffic, traffic_src = None, None
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_tc_traffic.json")
+    if os.path.exists(tpath) and B == FRAMES_PER_GPU and prec == 0:      # ncu dram__bytes_read+write of the same launches
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj.get("traffic_bytes_per_step"), "profiles/r01_tc_traffic.json (ncu dram__bytes_read.sum+dram__bytes_write.sum, summed over the step's k_conv_tc launches)"
     roofline = {"bound": "tensor", "kernel": "k_conv_tc (tcgen05 implicit-GEMM conv, all %d launches of a step)" % int(tc.sum()),
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                "peak_source": f"{peaks_src} bf16_tflops_sustained", "traffic": None,
+                "peak_source": f"{peaks_src} bf16_tflops_sustained", "traffic": traffic, "traffic_source": traffic_src,
                 "kernel_ms_per_step": tc_ms, "kernel_share_of_step": tc_ms / step_ms if step_ms else None,
                 "algorithmic_flops_per_step": tc_flops,
                 "hbm_model": {"unfused_activation_bytes_per_frame": 357e6,

@@ -32,6 +32,16 @@ constexpr int MAX_GROUPS = 3, MAX_TAPS = 3;
 struct TcTap { int row_off, w_tap; };
 struct TcGroup { int dx, n_taps; TcTap taps[MAX_TAPS]; };
 
+struct TcProgEntry {          // one step of the MMA program of k_conv_tc_prog (per input-channel chunk)
+  uint16_t a_off16;           // start-address offset of the activation operand inside the staged box, >> 4
+  uint8_t w_tap;              // weight tap (third coordinate of the filter tensor map)
+  uint8_t w_slot;             // resident slot of that tap (weights-resident mode)
+  uint8_t acc;                // accumulator (sub-tile / tconv phase) this step adds into
+  uint8_t first;              // first step of its accumulator (overwrites at chunk 0, k-step 0)
+  uint8_t w_adv, w_last;      // streamed mode: first / last step that uses the current ring slice
+};
+struct TcAccOut { int16_t dx, dy, oy_add, ox_add; };   // where accumulator s lands: tile offset + output phase
+
 struct TcParams {
   int H, W;                    // iteration grid (input grid for tconv phases, output grid for convs)
   int tiles_x;
@@ -69,6 +79,16 @@ struct TcParams {
   int dx0;
   int halo_base_offset;        // 1: put (addr >> 7) & 7 into the descriptor's base-offset field
   int n_stages;                // TMEM accumulator stages of the persistent kernels (2..8)
+  // halo super-tile: sub_x x sub_y sub-tiles of 8x16 pixels share ONE staged halo box and one
+  // barrier round trip (sub-tile s accumulates in TMEM columns [s*N, (s+1)*N) of the stage)
+  int sub_x, sub_y, pitch;     // pitch = 8*sub_x + 2 (pixels per staged row)
+  int epi_groups;              // 1 or 2 sets of 4 epilogue warps (2 only when sub_x*sub_y >= 2)
+  // filter bank too large for shared memory: stream one [N x KC] slice per (chunk, tap) through a ring
+  // of n_w_ring slots; every slice is used by all sub-tiles of the super-tile before it is released
+  int w_stream, n_w_ring;
+  int n_prog, n_acc;
+  TcProgEntry prog[36];
+  TcAccOut acc_out[4];
   int ablate;                  // profiling only (SB_ABLATE): 1 no TMA, 2 no MMA, 4 no stores, 8 no TMEM loads
 };
 
@@ -176,6 +196,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 
 // Shared epilogue: 16 accumulator columns of this thread's pixel -> bias / ReLU / BN -> stores
 // (+ fused 2x2 max-pool).  q = TMEM lane quadrant of the warp (rows 32q .. 32q+31 of the tile).
+template <int TWC = 0>   // TWC: tile width known at compile time (0 = P.tw)
 __device__ __forceinline__ void tc_epilogue_cols(const TcParams& P, const float* __restrict__ s_par, const uint32_t (&r)[16],
                                                  int n0, int c0, bool valid, size_t pix, int b, int x0, int y0, int q, int lane) {
   // s_par: [3][N] = bias | bn_scale | bn_shift of this N tile, staged in shared memory once per CTA
@@ -206,30 +227,50 @@ __device__ __forceinline__ void tc_epilogue_cols(const TcParams& P, const float*
     }
   }
   if (P.pool_out != nullptr) {
-    // fused MaxPool2D(2, strides=2): lanes of a warp hold tile pixels (ty = q*(32/tw) + lane/tw, tx = lane%tw);
-    // the 2x2 partners are lane^1 (x) and lane^tw (y); lanes with even tx and even ty store.
-    float pv[16];
+    // fused MaxPool2D(2, strides=2) (fp16 outputs only): lanes of a warp hold tile pixels
+    // (ty = q*(32/tw) + lane/tw, tx = lane%tw); the 2x2 partners are lane^1 (x) and lane^tw (y); lanes with
+    // even tx and even ty store.  The max runs on the already rounded, packed halves: rounding is
+    // monotonic, so max(round(a), round(b)) == round(max(a, b)) and this equals pooling the stored tensor.
+    const int tw = TWC ? TWC : P.tw;
+    __align__(16) __half2 h[8];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      float a = v[j];
-      a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 1));
-      a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, P.tw));
-      pv[j] = a;
+    for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+    if (valid) {
+      __half* po = reinterpret_cast<__half*>(P.out) + pix * P.out_Ctot + P.out_coff + n0 + c0;
+      if (n0 + c0 + 16 <= P.Cout) {
+        if (((P.out_Ctot | (P.out_coff + n0)) & 15) == 0) st_global_256(po, h);
+        else {
+          reinterpret_cast<uint4*>(po)[0] = *reinterpret_cast<uint4*>(&h[0]);
+          reinterpret_cast<uint4*>(po)[1] = *reinterpret_cast<uint4*>(&h[4]);
+        }
+      } else {
+        const __half* hs = reinterpret_cast<const __half*>(h);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (n0 + c0 + j < P.Cout) po[j] = hs[j];
+      }
     }
-    const int lr = lane / P.tw, lc = lane % P.tw;
-    if (valid && (lc & 1) == 0 && (lr & 1) == 0 && n0 + c0 + 16 <= P.Cout) {
-      const int py = (y0 >> 1) + ((q * (32 / P.tw) + lr) >> 1), px = (x0 >> 1) + (lc >> 1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint32_t a = *reinterpret_cast<uint32_t*>(&h[j]);
+      uint32_t o = __shfl_xor_sync(0xffffffffu, a, 1);
+      __half2 m2 = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&o));
+      a = *reinterpret_cast<uint32_t*>(&m2);
+      o = __shfl_xor_sync(0xffffffffu, a, tw);
+      h[j] = __hmax2(m2, *reinterpret_cast<__half2*>(&o));
+    }
+    const int lr = lane / tw, lc = lane % tw;
+    if (valid && ((lc | lr) & 1) == 0 && n0 + c0 + 16 <= P.Cout) {
+      const int py = (y0 >> 1) + ((q * (32 / tw) + lr) >> 1), px = (x0 >> 1) + (lc >> 1);
       __half* pp = reinterpret_cast<__half*>(P.pool_out) + (((size_t)b * P.pool_H + py) * P.pool_W + px) * P.pool_Ctot +
                    P.pool_coff + n0 + c0;
-      __align__(16) __half2 h[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(pv[2 * j], pv[2 * j + 1]);
       if (((P.pool_Ctot | (P.pool_coff + n0)) & 15) == 0) st_global_256(pp, h);
       else {
         reinterpret_cast<uint4*>(pp)[0] = *reinterpret_cast<uint4*>(&h[0]);
         reinterpret_cast<uint4*>(pp)[1] = *reinterpret_cast<uint4*>(&h[4]);
       }
     }
+    return;
   }
   if (!valid) return;
   if (P.out_f32) {
@@ -370,7 +411,7 @@ __global__ void __launch_bounds__(128) k_conv_tc(const __grid_constant__ CUtenso
     uint32_t r[16];
     tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    tc_epilogue_cols(P, s_par, r, n0, c0, valid, pix, b, x0, y0, warp, lane);
+    tc_epilogue_cols<16>(P, s_par, r, n0, c0, valid, pix, b, x0, y0, warp, lane);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -502,7 +543,7 @@ __global__ void __launch_bounds__(192) k_conv_tc_persist(const __grid_constant__
         uint32_t r16[16];
         tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(stage * P.N + c0), r16);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        tc_epilogue_cols(P, s_par, r16, 0, c0, valid, pix, b, x0, y0, q, lane);
+        tc_epilogue_cols<16>(P, s_par, r16, 0, c0, valid, pix, b, x0, y0, q, lane);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -677,7 +718,7 @@ __global__ void __launch_bounds__(192) k_conv_tc_halo(const __grid_constant__ CU
       mbar_wait(smem_u32(tfull + stage), fph, 25);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int m = q * 32 + lane;
-      const int iy = y0 + m / TWH, ix = x0 + m % TWH;
+      const int iy = y0 + (m >> 3), ix = x0 + (m & 7);
       const bool valid = (iy < P.H) && (ix < P.W);
       const size_t pix = ((size_t)b * P.out_H + (iy * P.oy_mul + P.oy_add)) * P.out_W + (ix * P.ox_mul + P.ox_add);
       for (int c0 = 0; c0 < P.N; c0 += 16) {
@@ -689,7 +730,188 @@ __global__ void __launch_bounds__(192) k_conv_tc_halo(const __grid_constant__ CU
           tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(stage * P.N + c0), r16);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         }
-        tc_epilogue_cols(P, s_par, r16, 0, c0, valid && !(P.ablate & 4), pix, b, x0, y0, q, lane);
+        tc_epilogue_cols<8>(P, s_par, r16, 0, c0, valid && !(P.ablate & 4), pix, b, x0, y0, q, lane);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(tempty + stage));
+      if (++stage == P.n_stages) { stage = 0; fph ^= 1; }
+    }
+  }
+  __syncwarp();
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P.tmem_cols) : "memory");
+  }
+}
+
+// Warp-uniform copy of a value (the compiler keeps the result in a uniform register, which is where
+// tcgen05.mma wants its descriptors: no per-instruction R2UR traffic in the single issuing thread).
+__device__ __forceinline__ uint32_t uni(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
+// "Programmed" halo kernel: one staged halo box [KC, pitch, box_h] per input-channel chunk feeds up
+// to four TMEM accumulators per stage.  The accumulators are either the 8x16-pixel sub-tiles of a
+// super-tile (one barrier round trip and one weight slice for 256/512 pixels) or the four sub-pixel
+// phases of a stride-2 transposed convolution (the whole Conv2DTranspose in ONE launch; every phase
+// reads the same staged activations).  The MMA sequence is a table in the kernel parameters
+// (TcProgEntry: activation start offset, weight slice, accumulator); the filter bank is either
+// resident in shared memory or streamed slice by slice through a ring (w_stream), in which case a
+// slice is consumed by all program entries that use it before the slot is released.
+template <int KSTEPS>
+__global__ void __launch_bounds__(320) k_conv_tc_prog(const __grid_constant__ CUtensorMap mapA,
+                                                      const __grid_constant__ CUtensorMap mapB,
+                                                      const __grid_constant__ TcParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const bool w_stream = P.w_stream != 0;
+  const int n_wslots = w_stream ? P.n_w_ring : P.n_chunks * P.n_used_taps;
+  uint8_t* w_res = base;
+  uint8_t* a_ring = w_res + (size_t)n_wslots * P.w_slot_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(a_ring + (size_t)P.n_a_slots * P.a_slot_bytes);
+  uint64_t* fullA = bars;
+  uint64_t* emptyA = fullA + P.n_a_slots;
+  uint64_t* tfull = emptyA + P.n_a_slots;
+  uint64_t* tempty = tfull + P.n_stages;
+  uint64_t* wbar = tempty + P.n_stages;
+  uint64_t* fullW = wbar + 1;          // [8] (streamed-weights mode only)
+  uint64_t* emptyW = fullW + 8;        // [8]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(emptyW + 8);
+  float* s_par = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~(uintptr_t)15);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int TWH = 8 * P.sub_x, THH = 16 * P.sub_y;
+  stage_params(P, s_par, 0);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < P.n_a_slots; ++i) { mbar_init(smem_u32(fullA + i), 1); mbar_init(smem_u32(emptyA + i), 1); }
+    for (int i = 0; i < P.n_stages; ++i) { mbar_init(smem_u32(tfull + i), 1); mbar_init(smem_u32(tempty + i), 4 * P.epi_groups); }
+    mbar_init(smem_u32(wbar), 1);
+    for (int i = 0; i < 8; ++i) { mbar_init(smem_u32(fullW + i), 1); mbar_init(smem_u32(emptyW + i), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(P.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    if (!w_stream) {
+      mbar_expect_tx(smem_u32(wbar), (uint32_t)(n_wslots * P.b_tx_bytes));
+      for (int ch = 0; ch < P.n_chunks; ++ch)
+        for (int u = 0; u < P.n_used_taps; ++u)
+          tma_load_3d(smem_u32(w_res + (size_t)(ch * P.n_used_taps + u) * P.w_slot_bytes), &mapB, smem_u32(wbar), ch * P.KC, 0,
+                      P.used_taps[u]);
+    }
+    int sa = 0, sw = 0;
+    uint32_t pha = 0, phw = 0;
+    TileIter it;
+    it.init(blockIdx.x, gridDim.x, P.tiles_x, P.tiles_per_img / P.tiles_x);
+    for (int t = blockIdx.x; t < P.n_tiles_total; t += gridDim.x, it.next()) {
+      const int b = it.b, y0 = it.ty * THH, x0 = it.tx * TWH;
+      for (int ch = 0; ch < P.n_chunks; ++ch) {
+        mbar_wait(smem_u32(emptyA + sa), pha ^ 1, 21);
+        if (P.ablate & 1) { mbar_arrive(smem_u32(fullA + sa)); }
+        else {
+          mbar_expect_tx(smem_u32(fullA + sa), (uint32_t)P.a_tx_bytes);
+          tma_load_4d(smem_u32(a_ring + (size_t)sa * P.a_slot_bytes), &mapA, smem_u32(fullA + sa), ch * P.KC, x0 + P.dx0,
+                      y0 + P.dy0, b);
+        }
+        if (++sa == P.n_a_slots) { sa = 0; pha ^= 1; }
+        if (w_stream) {
+          for (int i = 0; i < P.n_prog; ++i) {          // same order as the MMA warp consumes the slices
+            if (!P.prog[i].w_adv) continue;
+            mbar_wait(smem_u32(emptyW + sw), phw ^ 1, 26);
+            mbar_expect_tx(smem_u32(fullW + sw), (uint32_t)P.b_tx_bytes);
+            tma_load_3d(smem_u32(w_res + (size_t)sw * P.w_slot_bytes), &mapB, smem_u32(fullW + sw), ch * P.KC, 0, P.prog[i].w_tap);
+            if (++sw == P.n_w_ring) { sw = 0; phw ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (!w_stream) mbar_wait(smem_u32(wbar), 0, 22);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    int sa = 0, stage = 0, sw = 0;
+    uint32_t pha = 0, eph = 0, phw = 0;
+    // descriptor templates (everything but the 14-bit start address); all operands below are warp-uniform
+    const uint64_t desca_t = make_desc_unaligned(0, P.pitch * P.row_bytes, P.layout_type, 0);
+    const uint64_t descb_t = make_desc(0, P.row_bytes, P.layout_type);
+    const uint32_t a_base16 = uni(smem_u32(a_ring) >> 4), w_base16 = uni(smem_u32(w_res) >> 4);
+    const uint32_t a_slot16 = (uint32_t)P.a_slot_bytes >> 4, w_slot16 = (uint32_t)P.w_slot_bytes >> 4;
+    const uint32_t tm0 = uni(tmem_base);
+    const int n_acc_cols = P.n_acc * P.N;
+    for (int t = blockIdx.x; t < P.n_tiles_total; t += gridDim.x) {
+      mbar_wait(smem_u32(tempty + stage), eph ^ 1, 23);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d0 = tm0 + (uint32_t)(stage * n_acc_cols);
+      for (int ch = 0; ch < P.n_chunks; ++ch) {
+        mbar_wait(smem_u32(fullA + sa), pha, 24);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a16 = a_base16 + (uint32_t)sa * a_slot16;
+        const uint32_t wch16 = w_base16 + (uint32_t)(ch * P.n_used_taps) * w_slot16;
+        for (int i = 0; i < P.n_prog; ++i) {
+          const TcProgEntry e = P.prog[i];
+          if (w_stream && e.w_adv) {
+            mbar_wait(smem_u32(fullW + sw), phw, 27);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          }
+          const uint64_t da = desca_t + (uint64_t)(a16 + e.a_off16);
+          const uint64_t db = descb_t + (uint64_t)(w_stream ? w_base16 + (uint32_t)sw * w_slot16 : wch16 + (uint32_t)e.w_slot * w_slot16);
+          const uint32_t dt = d0 + (uint32_t)e.acc * (uint32_t)P.N;
+          const uint32_t acc0 = (uint32_t)ch | (uint32_t)(e.first ^ 1);
+          if (elect_one()) {
+            if (!(P.ablate & 2)) {
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k) tc_mma_f16(dt, da + 2 * k, db + 2 * k, P.idesc, (acc0 | (uint32_t)k) ? 1u : 0u);
+            }
+            if (w_stream && e.w_last) tc_commit(smem_u32(emptyW + sw));
+          }
+          __syncwarp();
+          if (w_stream && e.w_last) { if (++sw == P.n_w_ring) { sw = 0; phw ^= 1; } }
+        }
+        if (elect_one()) tc_commit(smem_u32(emptyA + sa));
+        __syncwarp();
+        if (++sa == P.n_a_slots) { sa = 0; pha ^= 1; }
+      }
+      if (elect_one()) tc_commit(smem_u32(tfull + stage));
+      __syncwarp();
+      if (++stage == P.n_stages) { stage = 0; eph ^= 1; }
+    }
+  } else if (warp >= 2) {
+    const int q = warp & 3, eg = (warp - 2) >> 2;
+    int stage = 0;
+    uint32_t fph = 0;
+    TileIter it;
+    it.init(blockIdx.x, gridDim.x, P.tiles_x, P.tiles_per_img / P.tiles_x);
+    for (int t = blockIdx.x; t < P.n_tiles_total; t += gridDim.x, it.next()) {
+      const int b = it.b, y0 = it.ty * THH, x0 = it.tx * TWH;
+      mbar_wait(smem_u32(tfull + stage), fph, 25);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int m = q * 32 + lane;
+      for (int s = eg; s < P.n_acc; s += P.epi_groups) {
+        const TcAccOut ao = P.acc_out[s];
+        const int xs = x0 + ao.dx, ys = y0 + ao.dy;
+        const int iy = ys + (m >> 3), ix = xs + (m & 7);
+        const bool valid = (iy < P.H) && (ix < P.W);
+        const size_t pix = ((size_t)b * P.out_H + (iy * P.oy_mul + ao.oy_add)) * P.out_W + (ix * P.ox_mul + ao.ox_add);
+        const uint32_t tcol = (uint32_t)((stage * P.n_acc + s) * P.N);
+        for (int c0 = 0; c0 < P.N; c0 += 16) {
+          uint32_t r16[16];
+          if (P.ablate & 8) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r16[j] = (uint32_t)(lane + j);
+          } else {
+            tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + tcol + (uint32_t)c0, r16);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          }
+          tc_epilogue_cols<8>(P, s_par, r16, 0, c0, valid && !(P.ablate & 4), pix, b, xs, ys, q, lane);
+        }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -860,17 +1082,18 @@ struct TcLaunch {
   size_t smem_p;
   int occ;
   int use_persist;     // variant chosen at configure time by timing them on the device: 0 stream, 1 persist, 2 halo
-  bool has_halo;
-  CUtensorMap mapAH;   // box [KC, 10, 18, 1]
-  TcParams PH;
-  size_t smem_h;
-  int occ_h;
+  // halo variants (variant id 2 + i): super-tiles of sub_x x sub_y 8x16 sub-tiles, box [KC, 8*sub_x+2, 16*sub_y+2, 1]
+  bool pp_valid;       // PP holds the tap/slot tables (the launch covers all output channels with one N)
+  int n_halo;
+  struct Halo { CUtensorMap map; TcParams P; size_t smem; int occ, threads; bool prog; } halo[4];
 };
 
 }  // namespace
 
 struct SbConvTcPlan {
   std::vector<TcLaunch> launches;   // 1 for conv, 4 phases for tconv
+  std::vector<TcLaunch> fused;      // tconv: all phases in one launch (two when 4 accumulators exceed TMEM)
+  bool use_fused = false;
   __half* w16 = nullptr;            // [taps][Cout_pad][Cin]
   int Cout_pad = 0;
 };
@@ -909,7 +1132,7 @@ bool sb_conv_tc_can(const SbModel* m, int op_index) {
 
 static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan* plan, int n_groups,
                        const TcGroup* groups, int dy0, int extra_rows, int n_wtaps, int oy_mul, int oy_add,
-                       int ox_mul, int ox_add) {
+                       int ox_mul, int ox_add, int fused_phases = 0, std::vector<TcLaunch>* dst = nullptr) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return sb_fail(h, SB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   const SbBuffer& ib = m->buffers[op.in_buf()];
@@ -978,7 +1201,7 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
   P.tw = TW;
   P.tiles_per_img = P.tiles_x * tiles_y;
   L.has_persist = false;
-  L.has_halo = false;
+  L.n_halo = 0;
   {
     int used[9], n_used = 0, slot_of[9];
     for (int i = 0; i < 9; ++i) slot_of[i] = -1;
@@ -989,14 +1212,18 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
       }
     const size_t w_bytes = (size_t)P.n_chunks * n_used * P.b_slot_bytes;
     const size_t budget = 196 * 1024;
-    if (!getenv("SB_DISABLE_PERSISTENT") && plan->Cout_pad == N && 2 * N <= 512 &&
-        w_bytes + 2 * (size_t)P.a_slot_bytes <= budget) {
+    L.pp_valid = plan->Cout_pad == N;
+    {
       TcParams& Q = L.PP;
       Q = P;
       Q.persistent = 1;
       Q.n_used_taps = n_used;
       for (int i = 0; i < 9; ++i) { Q.used_taps[i] = i < n_used ? used[i] : 0; Q.slot_of_tap[i] = slot_of[i]; }
       Q.w_slot_bytes = P.b_slot_bytes;
+    }
+    if (!getenv("SB_DISABLE_PERSISTENT") && plan->Cout_pad == N && 2 * N <= 512 &&
+        w_bytes + 2 * (size_t)P.a_slot_bytes <= budget) {
+      TcParams& Q = L.PP;
       // activation ring: two tiles of look-ahead (2 x n_groups halo tiles per chunk) when it fits
       int na = (int)((budget - w_bytes) / P.a_slot_bytes);
       Q.n_a_slots = std::max(2, std::min(na, std::max(6, 2 * n_groups)));
@@ -1028,59 +1255,145 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
       L.has_persist = true;
     }
   }
-  if (L.has_persist && ib.W >= 10 && ib.H >= 18 && !getenv("SB_DISABLE_HALO")) {
-    TcParams& Hp = L.PH;
-    Hp = L.PP;
-    Hp.tw = 8;
-    Hp.tiles_x = (ib.W + 7) / 8;
-    Hp.tiles_per_img = Hp.tiles_x * ((ib.H + 15) / 16);
-    int dxmin = 0;
-    for (int g = 0; g < n_groups; ++g) dxmin = std::min(dxmin, groups[g].dx);
-    Hp.dx0 = dxmin;
-    Hp.halo_base_offset = getenv("SB_HALO_BASEOFF") ? atoi(getenv("SB_HALO_BASEOFF")) : 0;
-    Hp.ablate = getenv("SB_ABLATE") ? atoi(getenv("SB_ABLATE")) : 0;
-    Hp.n_htaps = 0;
-    for (int g = 0; g < n_groups; ++g)
-      for (int t = 0; t < groups[g].n_taps; ++t) {
-        Hp.htap_off_rows[Hp.n_htaps] = groups[g].taps[t].row_off * 10 + (groups[g].dx - dxmin);
-        Hp.htap_w[Hp.n_htaps] = groups[g].taps[t].w_tap;
-        ++Hp.n_htaps;
-      }
-    Hp.a_tx_bytes = 18 * 10 * KC * 2;
-    Hp.a_slot_bytes = (Hp.a_tx_bytes + 1023) / 1024 * 1024;
-    const size_t w_bytes = (size_t)Hp.n_chunks * Hp.n_used_taps * Hp.w_slot_bytes;
-    const size_t budget = 196 * 1024;
-    if (w_bytes + 2 * (size_t)Hp.a_slot_bytes <= budget) {
-      int na = (int)((budget - w_bytes) / Hp.a_slot_bytes);
-      Hp.n_a_slots = std::max(2, std::min(na, 6));
-      L.smem_h = w_bytes + (size_t)Hp.n_a_slots * Hp.a_slot_bytes + 1024 + (size_t)(2 * Hp.n_a_slots + 2 * 8 + 1) * 8 + 64 + 3 * 256 * sizeof(float);
-      cudaFuncAttributes fa;
-      int occ = 1;
-      const void* fn = KC == 16 ? (const void*)k_conv_tc_halo<1> : (KC == 32 ? (const void*)k_conv_tc_halo<2> : (const void*)k_conv_tc_halo<4>);
-      if (cudaFuncGetAttributes(&fa, fn) == cudaSuccess) {
-        const int by_regs = 65536 / std::max(1, ((fa.numRegs + 7) / 8 * 8) * 192);
-        const int by_smem = (int)((227 * 1024) / (L.smem_h + fa.sharedSizeBytes + 1024));
-        occ = std::max(1, std::min(std::min(by_regs, by_smem), 16));
-        auto cols_for = [&](int nst) { int c = 32; while (c < nst * N) c <<= 1; return c; };
-        Hp.n_stages = getenv("SB_TMEM_STAGES") ? atoi(getenv("SB_TMEM_STAGES")) : 8;
-        while (Hp.n_stages > 2 && Hp.n_stages * N > 512) Hp.n_stages >>= 1;
-        Hp.tmem_cols = cols_for(Hp.n_stages);
-        while (occ * Hp.tmem_cols > 512 && Hp.n_stages > 2) { Hp.n_stages >>= 1; Hp.tmem_cols = cols_for(Hp.n_stages); }
-        if (occ * Hp.tmem_cols > 512) { Hp.n_stages = 1; Hp.tmem_cols = cols_for(1); }
-        if (occ * Hp.tmem_cols > 512) { L.smem_h = std::max(L.smem_h, (size_t)(227 * 1024) / (512 / Hp.tmem_cols) - 2048); occ = 512 / Hp.tmem_cols; }
-      }
-      L.occ_h = occ;
-      cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)ib.W, (cuuint64_t)ib.H, (cuuint64_t)m->B};
-      cuuint64_t strides[3] = {(cuuint64_t)ib.C * 2, (cuuint64_t)ib.W * ib.C * 2, (cuuint64_t)ib.H * ib.W * ib.C * 2};
-      cuuint32_t box[4] = {(cuuint32_t)KC, 10, 18, 1};
-      cuuint32_t es[4] = {1, 1, 1, 1};
-      void* gptr = (void*)((__half*)ib.dev + op.in_coff());
-      CUresult r = enc(&L.mapAH, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, gptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                       swz_for(KC), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (r != CUDA_SUCCESS) return sb_fail(h, SB_ERR_CUDA, "cuTensorMapEncodeTiled(A halo) failed: %d", (int)r);
-      L.has_halo = true;
+  L.n_halo = 0;
+  int kHaloShapes[5][3] = {{1, 1, 1}, {2, 1, 2}, {2, 2, 2}, {0, 0, 0}, {0, 0, 0}};   // sub_x, sub_y, epilogue groups
+  int n_shapes = 3;
+  if (const char* e = getenv("SB_HALO_SHAPES")) {      // experiments: "sx,sy,eg;sx,sy,eg;..."
+    n_shapes = 0;
+    while (*e && n_shapes < 4) {
+      int a = 1, b = 1, c = 1;
+      if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3) { kHaloShapes[n_shapes][0] = a; kHaloShapes[n_shapes][1] = b; kHaloShapes[n_shapes][2] = c; ++n_shapes; }
+      const char* semi = strchr(e, ';');
+      if (!semi) break;
+      e = semi + 1;
     }
   }
+  if (fused_phases) {          // fused transposed conv: ONE candidate, 8x16 input tile, one accumulator per phase
+    kHaloShapes[0][0] = 1; kHaloShapes[0][1] = 1; kHaloShapes[0][2] = 2;
+    n_shapes = 1;
+    L.has_persist = false;
+  }
+  for (int hs = 0; hs < n_shapes && L.pp_valid && !getenv("SB_DISABLE_HALO"); ++hs) {
+    const int sub_x = kHaloShapes[hs][0], sub_y = kHaloShapes[hs][1], egroups = kHaloShapes[hs][2];
+    const int n_sub = sub_x * sub_y;
+    const int pitch = fused_phases ? 9 : 8 * sub_x + 2, box_h = fused_phases ? 17 : 16 * sub_y + 2;
+    if (ib.W < pitch || ib.H < box_h) continue;
+    if ((n_sub > 1 || fused_phases) && getenv("SB_DISABLE_SUPERTILE")) continue;
+    TcLaunch::Halo& HC = L.halo[L.n_halo];
+    TcParams& Hp = HC.P;
+    Hp = L.PP;
+    Hp.tw = 8;
+    Hp.sub_x = sub_x; Hp.sub_y = sub_y; Hp.pitch = pitch; Hp.epi_groups = egroups;
+    Hp.tiles_x = (ib.W + 8 * sub_x - 1) / (8 * sub_x);
+    Hp.tiles_per_img = Hp.tiles_x * ((ib.H + 16 * sub_y - 1) / (16 * sub_y));
+    Hp.halo_base_offset = getenv("SB_HALO_BASEOFF") ? atoi(getenv("SB_HALO_BASEOFF")) : 0;
+    Hp.ablate = getenv("SB_ABLATE") ? atoi(getenv("SB_ABLATE")) : 0;
+    Hp.n_prog = 0; Hp.n_acc = 0;
+    if (fused_phases) {
+      // Conv2DTranspose k3 s2 (see sb_conv_tc_prepare): out[2i+a] gets (ky, row) = a==0 ? {(0,i),(2,i-1)} : {(1,i)};
+      // same along x.  Box origin (x0-1, y0-1); phase (a, bx) accumulates in its own TMEM columns.
+      Hp.dx0 = -1; Hp.dy0 = -1;
+      int n_used = 0;
+      for (int i = 0; i < 9; ++i) Hp.slot_of_tap[i] = -1;
+      for (int a = 0; a < 2; ++a)
+        for (int bx = 0; bx < 2; ++bx) {
+          if (!(fused_phases & (1 << (a * 2 + bx)))) continue;
+          const int acc = Hp.n_acc++;
+          Hp.acc_out[acc] = TcAccOut{0, 0, (int16_t)a, (int16_t)bx};
+          const int kys[2] = {a == 0 ? 0 : 1, 2}, dys[2] = {0, -1}, nky = a == 0 ? 2 : 1;
+          const int kxs[2] = {bx == 0 ? 0 : 1, 2}, dxs[2] = {0, -1}, nkx = bx == 0 ? 2 : 1;
+          bool first = true;
+          for (int qy = 0; qy < nky; ++qy)
+            for (int qx = 0; qx < nkx; ++qx) {
+              const int wt = kys[qy] * 3 + kxs[qx];
+              TcProgEntry& e = Hp.prog[Hp.n_prog++];
+              e.a_off16 = (uint16_t)((((dys[qy] + 1) * pitch + (dxs[qx] + 1)) * Hp.row_bytes) >> 4);
+              e.w_tap = (uint8_t)wt;
+              Hp.used_taps[n_used] = wt; Hp.slot_of_tap[wt] = n_used;
+              e.w_slot = (uint8_t)n_used++;
+              e.acc = (uint8_t)acc; e.first = first ? 1 : 0; e.w_adv = 1; e.w_last = 1;
+              first = false;
+            }
+        }
+      Hp.n_used_taps = n_used;
+    } else {
+      int dxmin = 0;
+      for (int g = 0; g < n_groups; ++g) dxmin = std::min(dxmin, groups[g].dx);
+      Hp.dx0 = dxmin;
+      Hp.n_htaps = 0;
+      for (int g = 0; g < n_groups; ++g)
+        for (int t = 0; t < groups[g].n_taps; ++t) {
+          Hp.htap_off_rows[Hp.n_htaps] = groups[g].taps[t].row_off * pitch + (groups[g].dx - dxmin);
+          Hp.htap_w[Hp.n_htaps] = groups[g].taps[t].w_tap;
+          ++Hp.n_htaps;
+        }
+      Hp.n_acc = n_sub;
+      for (int sIdx = 0; sIdx < n_sub; ++sIdx)
+        Hp.acc_out[sIdx] = TcAccOut{(int16_t)((sIdx % sub_x) * 8), (int16_t)((sIdx / sub_x) * 16), (int16_t)oy_add, (int16_t)ox_add};
+      for (int tp = 0; tp < Hp.n_htaps; ++tp)       // taps outermost: a weight slice serves every sub-tile
+        for (int sIdx = 0; sIdx < n_sub; ++sIdx) {
+          TcProgEntry& e = Hp.prog[Hp.n_prog++];
+          const int sub_rows = (sIdx / sub_x) * 16 * pitch + (sIdx % sub_x) * 8;
+          e.a_off16 = (uint16_t)(((sub_rows + Hp.htap_off_rows[tp]) * Hp.row_bytes) >> 4);
+          e.w_tap = (uint8_t)Hp.htap_w[tp];
+          e.w_slot = (uint8_t)Hp.slot_of_tap[Hp.htap_w[tp]];
+          e.acc = (uint8_t)sIdx; e.first = tp == 0 ? 1 : 0;
+          e.w_adv = sIdx == 0 ? 1 : 0; e.w_last = sIdx == n_sub - 1 ? 1 : 0;
+        }
+    }
+    if (Hp.n_acc * N > 512) continue;
+    Hp.a_tx_bytes = box_h * pitch * KC * 2;
+    Hp.a_slot_bytes = (Hp.a_tx_bytes + 1023) / 1024 * 1024;
+    size_t w_bytes = (size_t)Hp.n_chunks * Hp.n_used_taps * Hp.w_slot_bytes;
+    const size_t budget = 196 * 1024;
+    Hp.w_stream = 0; Hp.n_w_ring = 0;
+    const bool resident_fits = !getenv("SB_DISABLE_PERSISTENT") && w_bytes + 2 * (size_t)Hp.a_slot_bytes <= budget;
+    if (!resident_fits || getenv("SB_FORCE_WSTREAM")) {
+      if (getenv("SB_DISABLE_WSTREAM")) continue;
+      if (2 * (size_t)Hp.a_slot_bytes + 2 * (size_t)Hp.w_slot_bytes > budget) continue;
+      Hp.w_stream = 1;
+      Hp.n_a_slots = 2;
+      Hp.n_w_ring = (int)std::min<size_t>(6, (budget - 2 * (size_t)Hp.a_slot_bytes) / Hp.w_slot_bytes);
+      if (Hp.n_w_ring >= 5 && 3 * (size_t)Hp.a_slot_bytes + 4 * (size_t)Hp.w_slot_bytes <= budget) { Hp.n_a_slots = 3; Hp.n_w_ring = 4; }
+      w_bytes = (size_t)Hp.n_w_ring * Hp.w_slot_bytes;
+    } else {
+      const int na = (int)((budget - w_bytes) / Hp.a_slot_bytes);
+      Hp.n_a_slots = std::max(2, std::min(na, n_sub > 1 ? 3 : 6));
+    }
+    HC.prog = Hp.n_acc > 1 || Hp.w_stream;       // the plain 8x16 weights-resident case keeps the unrolled kernel
+    HC.threads = HC.prog ? 64 + 128 * egroups : 192;
+    if (!HC.prog) Hp.epi_groups = 1;
+    if (HC.prog && Hp.n_acc < 2) { Hp.epi_groups = 1; HC.threads = 192; }
+    HC.smem = w_bytes + (size_t)Hp.n_a_slots * Hp.a_slot_bytes + 1024 + (size_t)(2 * Hp.n_a_slots + 2 * 8 + 1 + 16) * 8 + 64 + 3 * 256 * sizeof(float);
+    cudaFuncAttributes fa;
+    int occ = 1;
+    const void* fn = HC.prog ? (KC == 16 ? (const void*)k_conv_tc_prog<1> : (KC == 32 ? (const void*)k_conv_tc_prog<2> : (const void*)k_conv_tc_prog<4>))
+                             : (KC == 16 ? (const void*)k_conv_tc_halo<1> : (KC == 32 ? (const void*)k_conv_tc_halo<2> : (const void*)k_conv_tc_halo<4>));
+    const int NS = Hp.n_acc * N;      // TMEM columns of one accumulator stage
+    auto cols_for = [&](int nst) { int c = 32; while (c < nst * NS) c <<= 1; return c; };
+    Hp.n_stages = getenv("SB_TMEM_STAGES") ? atoi(getenv("SB_TMEM_STAGES")) : (Hp.n_acc > 1 ? 4 : 8);
+    while (Hp.n_stages > 1 && Hp.n_stages * NS > 512) Hp.n_stages >>= 1;
+    Hp.tmem_cols = cols_for(Hp.n_stages);
+    if (cudaFuncGetAttributes(&fa, fn) == cudaSuccess) {
+      const int by_regs = 65536 / std::max(1, ((fa.numRegs + 7) / 8 * 8) * HC.threads);
+      const int by_smem = (int)((227 * 1024) / (HC.smem + fa.sharedSizeBytes + 1024));
+      occ = std::max(1, std::min(std::min(by_regs, by_smem), 16));
+      while (occ * Hp.tmem_cols > 512 && Hp.n_stages > 2) { Hp.n_stages >>= 1; Hp.tmem_cols = cols_for(Hp.n_stages); }
+      if (occ * Hp.tmem_cols > 512) { Hp.n_stages = 1; Hp.tmem_cols = cols_for(1); }
+      if (occ * Hp.tmem_cols > 512) { HC.smem = std::max(HC.smem, (size_t)(227 * 1024) / (512 / Hp.tmem_cols) - 2048); occ = 512 / Hp.tmem_cols; }
+    }
+    HC.occ = occ;
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)ib.W, (cuuint64_t)ib.H, (cuuint64_t)m->B};
+    cuuint64_t strides[3] = {(cuuint64_t)ib.C * 2, (cuuint64_t)ib.W * ib.C * 2, (cuuint64_t)ib.H * ib.W * ib.C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)pitch, (cuuint32_t)box_h, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    void* gptr = (void*)((__half*)ib.dev + op.in_coff());
+    CUresult r = enc(&HC.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, gptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swz_for(KC), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return sb_fail(h, SB_ERR_CUDA, "cuTensorMapEncodeTiled(A halo) failed: %d", (int)r);
+    ++L.n_halo;
+  }
+  if (fused_phases && L.n_halo == 0) return 1;     // caller falls back to the per-phase launches
   L.use_persist = 0;
   // A: NHWC view (slice channels, W, H, batch)
   {
@@ -1103,7 +1416,7 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return sb_fail(h, SB_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
   }
-  plan->launches.push_back(L);
+  (dst ? *dst : plan->launches).push_back(L);
   return 0;
 }
 
@@ -1122,8 +1435,11 @@ int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m) {
     SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_persist<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_persist<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_halo<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_prog<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_halo<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_prog<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_halo<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_prog<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     attr_set = true;
   }
   for (size_t oi = 0; oi < m->ops.size(); ++oi) {
@@ -1180,6 +1496,21 @@ int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m) {
           }
           rc = make_launch(h, m, op, plan, ng, g, a == 0 ? -1 : 0, extra, 9, 2, a, 2, bx);
         }
+      if (!rc && !getenv("SB_DISABLE_FUSED_TCONV")) {
+        // all four phases from one staged activation box; two launches (a = 0 / a = 1) when 4 x N columns exceed TMEM
+        TcGroup g[1];
+        g[0].dx = 0; g[0].n_taps = 1; g[0].taps[0] = TcTap{0, 4};
+        const int N = std::min(plan->Cout_pad, 256);
+        int r2 = 0;
+        if (4 * N <= 512) r2 = make_launch(h, m, op, plan, 1, g, 0, 0, 9, 2, 0, 2, 0, 0xF, &plan->fused);
+        else {
+          r2 = make_launch(h, m, op, plan, 1, g, 0, 0, 9, 2, 0, 2, 0, 0x3, &plan->fused);
+          if (!r2) r2 = make_launch(h, m, op, plan, 1, g, 0, 0, 9, 2, 0, 2, 0, 0xC, &plan->fused);
+        }
+        if (r2 < 0) rc = r2;
+        if (r2 != 0) plan->fused.clear();
+        for (TcLaunch& F : plan->fused) F.use_persist = 2;
+      }
     }
     if (rc) { cudaFree(plan->w16); delete plan; return rc; }
     m->tc_plans[oi] = plan;
@@ -1191,14 +1522,24 @@ int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m) {
 }
 
 static void launch_variant(sb_handle_s* h, TcLaunch& L, int B, int variant, cudaStream_t stream) {
-  if (variant == 2) {
-    TcParams P = L.PH;
+  if (variant >= 2) {
+    TcLaunch::Halo& HC = L.halo[variant - 2];
+    TcParams P = HC.P;
     P.n_tiles_total = P.tiles_per_img * B;
-    const int grid = std::max(1, std::min(P.n_tiles_total, h->sm_count * L.occ_h));
-    switch (P.KC) {
-      case 16: k_conv_tc_halo<1><<<grid, 192, L.smem_h, stream>>>(L.mapAH, L.mapB, P); break;
-      case 32: k_conv_tc_halo<2><<<grid, 192, L.smem_h, stream>>>(L.mapAH, L.mapB, P); break;
-      default: k_conv_tc_halo<4><<<grid, 192, L.smem_h, stream>>>(L.mapAH, L.mapB, P); break;
+    const int grid = std::max(1, std::min(P.n_tiles_total, h->sm_count * HC.occ));
+    if (getenv("SB_DEBUG_LAUNCH")) fprintf(stderr, "[halo %dx%d] KC=%d N=%d stages=%d cols=%d occ=%d grid=%d slots=%d smem=%zu tiles=%d thr=%d\n", P.sub_x, P.sub_y, P.KC, P.N, P.n_stages, P.tmem_cols, HC.occ, grid, P.n_a_slots, HC.smem, P.n_tiles_total, HC.threads);
+    if (HC.prog) {
+      switch (P.KC) {
+        case 16: k_conv_tc_prog<1><<<grid, HC.threads, HC.smem, stream>>>(HC.map, L.mapB, P); break;
+        case 32: k_conv_tc_prog<2><<<grid, HC.threads, HC.smem, stream>>>(HC.map, L.mapB, P); break;
+        default: k_conv_tc_prog<4><<<grid, HC.threads, HC.smem, stream>>>(HC.map, L.mapB, P); break;
+      }
+    } else {
+      switch (P.KC) {
+        case 16: k_conv_tc_halo<1><<<grid, HC.threads, HC.smem, stream>>>(HC.map, L.mapB, P); break;
+        case 32: k_conv_tc_halo<2><<<grid, HC.threads, HC.smem, stream>>>(HC.map, L.mapB, P); break;
+        default: k_conv_tc_halo<4><<<grid, HC.threads, HC.smem, stream>>>(HC.map, L.mapB, P); break;
+      }
     }
   } else if (variant == 1) {
     TcParams P = L.PP;
@@ -1221,16 +1562,22 @@ static void launch_variant(sb_handle_s* h, TcLaunch& L, int B, int variant, cuda
   }
 }
 
-// Pick, per launch, the faster of the two kernel variants by timing them on the device (buffers
-// are already allocated; their contents do not matter for timing).
+static int launch_plan(sb_handle_s* h, SbConvTcPlan* plan, int B, bool fused);
+
+// Pick, per launch, the fastest kernel variant by timing them on the device (buffers are already
+// allocated; their contents do not matter for timing); then, for transposed convs, the fused
+// single-launch form against the four forked per-phase launches.
 int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
   const char* force = getenv("SB_FORCE_VARIANT");
   const bool halo_ok = !getenv("SB_DISABLE_HALO");
-  auto avail = [&](const TcLaunch& L, int v) { return v == 0 || (v == 1 && L.has_persist) || (v == 2 && L.has_halo && halo_ok); };
+  auto avail = [&](const TcLaunch& L, int v) { return v == 0 || (v == 1 && L.has_persist) || (v >= 2 && v - 2 < L.n_halo && halo_ok); };
   if (force || getenv("SB_DISABLE_AUTOTUNE")) {
     const int want = force ? atoi(force) : 1;
     for (SbConvTcPlan* plan : m->tc_plans)
-      if (plan) for (TcLaunch& L : plan->launches) L.use_persist = avail(L, want) ? want : (avail(L, 1) && !force ? 1 : 0);
+      if (plan) {
+        for (TcLaunch& L : plan->launches) L.use_persist = avail(L, want) ? want : (avail(L, 1) && !force ? 1 : 0);
+        plan->use_fused = !plan->fused.empty() && (getenv("SB_FORCE_FUSED_TCONV") != nullptr);
+      }
     return 0;
   }
   cudaEvent_t e0, e1;
@@ -1241,9 +1588,9 @@ int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
     SbConvTcPlan* plan = m->tc_plans[oi];
     if (!plan) continue;
     for (TcLaunch& L : plan->launches) {
-      if (!L.has_persist) continue;
-      float best[3] = {1e30f, 1e30f, 1e30f};
-      for (int v = 0; v < 3; ++v) {
+      if (!L.has_persist && L.n_halo == 0) continue;
+      float best[6] = {1e30f, 1e30f, 1e30f, 1e30f, 1e30f, 1e30f};
+      for (int v = 0; v < 6; ++v) {
         if (!avail(L, v)) continue;
         for (int rep = 0; rep < 3; ++rep) {
           cudaEventRecord(e0, h->stream);
@@ -1257,12 +1604,41 @@ int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
         }
       }
       int pick = 0;
-      for (int v = 1; v < 3; ++v) if (best[v] < best[pick]) pick = v;
+      for (int v = 1; v < 6; ++v) if (best[v] < best[pick]) pick = v;
       L.use_persist = pick;
-      if (dbg)
-        fprintf(stderr, "[sb_conv_tc] op %zu Cin=%d N=%d %dx%d: stream %.1f, persist %.1f (occ %d, %d slots), halo %.1f (occ %d, %d slots) us -> %d\n",
-                oi, L.P.n_chunks * L.P.KC, L.P.N, L.P.H, L.P.W, best[0] * 1e3f, best[1] * 1e3f, L.occ, L.PP.n_a_slots,
-                best[2] * 1e3f, L.occ_h, L.has_halo ? L.PH.n_a_slots : 0, pick);
+      if (dbg) {
+        fprintf(stderr, "[sb_conv_tc] op %zu Cin=%d N=%d %dx%d: stream %.1f, persist %.1f (occ %d, %d slots)", oi, L.P.n_chunks * L.P.KC,
+                L.P.N, L.P.H, L.P.W, best[0] * 1e3f, best[1] * 1e3f, L.occ, L.PP.n_a_slots);
+        for (int i = 0; i < L.n_halo; ++i)
+          fprintf(stderr, ", halo%dx%d%s %.1f (occ %d, %d slots, %d stages)", L.halo[i].P.sub_x, L.halo[i].P.sub_y,
+                  L.halo[i].P.w_stream ? "w" : "", best[2 + i] * 1e3f, L.halo[i].occ, L.halo[i].P.n_a_slots, L.halo[i].P.n_stages);
+        fprintf(stderr, " us -> %d\n", pick);
+      }
+    }
+  }
+  for (size_t oi = 0; oi < m->tc_plans.size(); ++oi) {
+    SbConvTcPlan* plan = m->tc_plans[oi];
+    if (!plan || plan->fused.empty()) continue;
+    float best[2] = {1e30f, 1e30f};
+    for (int f = 0; f < 2; ++f)
+      for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0, h->stream);
+        int rc = launch_plan(h, plan, m->B, f == 1);
+        if (rc) return rc;
+        cudaEventRecord(e1, h->stream);
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) return sb_fail(h, SB_ERR_CUDA, "autotune launch (tconv, fused %d) failed: %s", f, cudaGetErrorString(e));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0) best[f] = std::min(best[f], ms);
+      }
+    plan->use_fused = best[1] < best[0];
+    if (getenv("SB_FORCE_FUSED_TCONV")) plan->use_fused = atoi(getenv("SB_FORCE_FUSED_TCONV")) != 0;
+    if (dbg) {
+      const TcParams& F = plan->fused[0].halo[0].P;
+      fprintf(stderr, "[sb_conv_tc] op %zu tconv Cin=%d N=%d: 4 phase launches %.1f us, fused x%zu (%s, %d stages, %d slots) %.1f us -> %s\n", oi,
+              F.n_chunks * F.KC, F.N, best[0] * 1e3f, plan->fused.size(), F.w_stream ? "streamed weights" : "resident weights", F.n_stages,
+              F.n_a_slots, best[1] * 1e3f, plan->use_fused ? "fused" : "phases");
     }
   }
   cudaEventDestroy(e0);
@@ -1272,6 +1648,17 @@ int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
 
 int sb_conv_tc_launch(sb_handle_s* h, SbModel* m, int op_index, int B) {
   SbConvTcPlan* plan = m->tc_plans[op_index];
+  return launch_plan(h, plan, B, plan->use_fused);
+}
+
+static int launch_plan(sb_handle_s* h, SbConvTcPlan* plan, int B, bool fused) {
+  if (fused) {
+    for (TcLaunch& L : plan->fused) {
+      launch_variant(h, L, B, 2, h->stream);
+      SB_CHECK_LAUNCH(h);
+    }
+    return 0;
+  }
   const size_t n = plan->launches.size();
   if (n == 1 || getenv("SB_DISABLE_FORK")) {
     for (TcLaunch& L : plan->launches) {

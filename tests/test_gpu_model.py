@@ -252,16 +252,98 @@ def test_tc_path_matches_direct_fp16(monkeypatch):
     assert launches_tc > 0
 
 
-@pytest.mark.parametrize("cin,cout,k", [(16, 16, 3), (32, 32, 3), (64, 64, 3), (128, 256, 3), (256, 512, 3), (64, 13, 1), (128, 24, 1)])
-def test_tc_single_layers(cin, cout, k):
-    """Each swizzle mode / chunk count / N-tile shape of the tensor-core conv on its own."""
+@pytest.mark.parametrize("fused", [None, "0", "1"])
+@pytest.mark.parametrize("cin,cout", [(16, 16), (64, 32), (128, 64), (256, 128), (512, 256)])
+def test_tc_tconv_layers(cin, cout, fused, monkeypatch):
+    """Conv2DTranspose(k3, s2) on the tensor cores: four forked per-phase launches ("0") or the fused
+    single-launch form with one TMEM accumulator per phase ("1"; weights resident or streamed, two launches
+    when 4 x Cout exceeds the 512 TMEM columns), or whatever the autotuner picks (None) -- against the
+    CUDA-core kernel on the same fp16 activations."""
+    from sleap_b200.nn import oplist as ol
+    from sleap_b200 import _lib
+    from ctypes import c_int, c_void_p, byref
+    rng = np.random.default_rng(cin * 3 + cout)
+    B, H, W = 2, 88, 72            # tconv input grid 44 x 36 -> output 88 x 72
+    recs = [ol.buffer_record(0, 1, 1, 0, 1), ol.buffer_record(1, 1, cin, 0, 0), ol.buffer_record(2, 2, cin, 0, 0),
+            ol.buffer_record(3, 1, cout, 0, 0), ol.preprocess_record(0, 1, 1.0, 2)]   # fp16 output (the CUDA-core tconv writes halves)
+    w0 = (rng.standard_normal((3, 3, 1, cin)) * 0.5).astype(np.float32)
+    b0 = rng.normal(0, 0.1, cin).astype(np.float32)
+    w1 = (rng.standard_normal((3, 3, cin, cout)) * np.sqrt(2.0 / (4 * cin))).astype(np.float32)
+    b1 = rng.normal(0, 0.1, cout).astype(np.float32)
+    blob = np.concatenate([w0.reshape(-1), b0, w1.reshape(-1), b1]).astype(np.float32)
+    o0, o1 = 0, w0.size + cin
+    recs.append(ol.conv_record(0, 0, 1, 1, 0, cin, 3, 1, True, o0, o0 + w0.size))
+    recs.append(ol.pool_record(1, 0, cin, 2, 0))
+    recs.append(ol.tconv_record(2, 0, cin, 3, 0, cout, o1, o1 + w1.size))
+    ops = np.ascontiguousarray(np.stack(recs).astype(np.int32))
+    imgs = rng.uniform(0, 1, size=(B, H, W, 1)).astype(np.float32)
+
+    def run():
+        h = _lib.default_handle()
+        mid = c_int(-1)
+        h.call("sb_load_model", _lib.ptr(ops), ops.shape[0], _lib.ptr(blob), int(blob.size), 0, byref(mid))
+        h.call("sb_model_configure", mid.value, B, H, W, 1)
+        out = np.zeros((B, H, W, cout), np.float32)
+        ids = np.asarray([3], np.int32)
+        ptrs = (c_void_p * 1)(out.ctypes.data)
+        h.call("sb_model_forward", mid.value, _lib.ptr(imgs), 0, B, 1, _lib.ptr(ids), ptrs)
+        return out
+
+    if fused is not None:
+        monkeypatch.setenv("SB_FORCE_VARIANT", "2")
+        if fused == "1":
+            monkeypatch.setenv("SB_FORCE_FUSED_TCONV", "1")
+    got = run()
+    monkeypatch.delenv("SB_FORCE_VARIANT", raising=False)
+    monkeypatch.delenv("SB_FORCE_FUSED_TCONV", raising=False)
+    monkeypatch.setenv("SB_DISABLE_TC", "1")
+    want = run()
+    assert np.abs(want).max() > 0.1
+    assert_allclose(got, want, atol=3e-3 * max(1.0, np.abs(want).max()), rtol=3e-3)
+
+
+@pytest.mark.parametrize("variant,fused", [("2", None), ("3", None), ("4", None), ("2", "1")])
+def test_tc_forced_variants_unet(variant, fused, monkeypatch):
+    """The whole fp16 UNet (transposed-conv phases, fused max-pool, concat-by-slice outputs) with every
+    halo variant forced, against the CUDA-core path."""
+    cfg = dict(filters=32, filters_rate=2, max_stride=8, output_stride=2, middle_block=True, up_interpolate=False)
+    heads = [dict(name="MultiInstanceConfmapsHead", channels=13, output_stride=2),
+             dict(name="PartAffinityFieldsHead", channels=24, output_stride=4)]
+    spec = _unet_spec(cfg, heads)
+    imgs = np.random.default_rng(12).integers(0, 256, size=(2, 288, 304, 1), dtype=np.uint8)
+    monkeypatch.setenv("SB_FORCE_VARIANT", variant)
+    if fused:
+        monkeypatch.setenv("SB_FORCE_FUSED_TCONV", fused)
+    tc_model, w, cm = _mk(spec, 1, 17, precision=0)
+    got_tc = tc_model.forward(imgs)
+    monkeypatch.delenv("SB_FORCE_VARIANT")
+    monkeypatch.delenv("SB_FORCE_FUSED_TCONV", raising=False)
+    monkeypatch.setenv("SB_DISABLE_TC", "1")
+    dm, _, _ = _mk(spec, 1, 17, precision=0)
+    got_direct = dm.forward(imgs)
+    for a, b in zip(got_tc, got_direct):
+        scale = np.abs(b).max()
+        assert np.abs(a - b).max() / scale < 3e-3, np.abs(a - b).max() / scale
+
+
+@pytest.mark.parametrize("variant", [None, "0", "1", "2", "3", "4"])
+@pytest.mark.parametrize("cin,cout,k,hw", [(16, 16, 3, (40, 48)), (32, 32, 3, (40, 48)), (64, 64, 3, (53, 70)),
+                                           (128, 128, 3, (40, 48)), (256, 128, 3, (53, 70)), (128, 256, 3, (40, 48)),
+                                           (256, 512, 3, (40, 48)), (64, 13, 1, (40, 48)), (128, 24, 1, (40, 48))])
+def test_tc_single_layers(cin, cout, k, hw, variant, monkeypatch):
+    """Each swizzle mode / chunk count / N-tile shape of the tensor-core conv on its own, with the
+    kernel variant chosen by the autotuner (None) or forced: 0 streaming, 1 weights-resident,
+    2 halo 8x16, 3 / 4 halo super-tiles 16x16 / 16x32 (weights resident or streamed); a forced variant
+    that does not apply to the layer falls back to the streaming kernel."""
+    if variant is not None:
+        monkeypatch.setenv("SB_FORCE_VARIANT", variant)
     import torch
     import torch.nn.functional as F
     from sleap_b200.nn import oplist as ol
     from sleap_b200 import _lib
     from ctypes import c_int, c_void_p, byref
     rng = np.random.default_rng(cin + cout)
-    B, H, W = 2, 40, 48
+    B, (H, W) = 2, hw
     # op-list: input(1ch) -> conv3x3 1->cin (direct, relu) -> [layer under test] (f32 out)
     recs = [ol.buffer_record(0, 1, 1, 0, 1), ol.buffer_record(1, 1, cin, 0, 0), ol.buffer_record(2, 1, cout, 1, 0),
             ol.preprocess_record(0, 1, 1.0, 1)]
