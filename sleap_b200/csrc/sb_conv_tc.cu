@@ -32,14 +32,10 @@ constexpr int MAX_GROUPS = 3, MAX_TAPS = 3;
 struct TcTap { int row_off, w_tap; };
 struct TcGroup { int dx, n_taps; TcTap taps[MAX_TAPS]; };
 
-struct TcProgEntry {          // one step of the MMA program of k_conv_tc_prog (per input-channel chunk)
-  uint16_t a_off16;           // start-address offset of the activation operand inside the staged box, >> 4
-  uint8_t w_tap;              // weight tap (third coordinate of the filter tensor map)
-  uint8_t w_slot;             // resident slot of that tap (weights-resident mode)
-  uint8_t acc;                // accumulator (sub-tile / tconv phase) this step adds into
-  uint8_t first;              // first step of its accumulator (overwrites at chunk 0, k-step 0)
-  uint8_t w_adv, w_last;      // streamed mode: first / last step that uses the current ring slice
-};
+struct TcProgEntry {          // one step of the MMA program of k_conv_tc_prog (per input-channel chunk), packed for the
+  uint32_t a_acc;             // single issuing thread: a_off16 (activation start offset in the staged box, >> 4) | acc_col << 16
+  uint32_t w_flags;           // w_off16 (resident slice offset >> 4) | first << 16 | n_same << 20 | w_tap << 26
+};                            // first: first step of its accumulator; n_same: entries from here on that share this weight slice
 struct TcAccOut { int16_t dx, dy, oy_add, ox_add; };   // where accumulator s lands: tile offset + output phase
 
 struct TcParams {
@@ -824,12 +820,13 @@ __global__ void __launch_bounds__(320) k_conv_tc_prog(const __grid_constant__ CU
         }
         if (++sa == P.n_a_slots) { sa = 0; pha ^= 1; }
         if (w_stream) {
-          for (int i = 0; i < P.n_prog; ++i) {          // same order as the MMA warp consumes the slices
-            if (!P.prog[i].w_adv) continue;
+          for (int i = 0; i < P.n_prog;) {              // same order as the MMA warp consumes the slices
+            const uint32_t ew = P.prog[i].w_flags;
             mbar_wait(smem_u32(emptyW + sw), phw ^ 1, 26);
             mbar_expect_tx(smem_u32(fullW + sw), (uint32_t)P.b_tx_bytes);
-            tma_load_3d(smem_u32(w_res + (size_t)sw * P.w_slot_bytes), &mapB, smem_u32(fullW + sw), ch * P.KC, 0, P.prog[i].w_tap);
+            tma_load_3d(smem_u32(w_res + (size_t)sw * P.w_slot_bytes), &mapB, smem_u32(fullW + sw), ch * P.KC, 0, (int)((ew >> 26) & 15));
             if (++sw == P.n_w_ring) { sw = 0; phw ^= 1; }
+            i += (int)((ew >> 20) & 63);
           }
         }
       }
@@ -842,6 +839,8 @@ __global__ void __launch_bounds__(320) k_conv_tc_prog(const __grid_constant__ CU
     // descriptor templates (everything but the 14-bit start address); all operands below are warp-uniform
     const uint64_t desca_t = make_desc_unaligned(0, P.pitch * P.row_bytes, P.layout_type, 0);
     const uint64_t descb_t = make_desc(0, P.row_bytes, P.layout_type);
+    const uint32_t desca_lo = (uint32_t)desca_t, desca_hi = (uint32_t)(desca_t >> 32);
+    const uint32_t descb_lo = (uint32_t)descb_t, descb_hi = (uint32_t)(descb_t >> 32);
     const uint32_t a_base16 = uni(smem_u32(a_ring) >> 4), w_base16 = uni(smem_u32(w_res) >> 4);
     const uint32_t a_slot16 = (uint32_t)P.a_slot_bytes >> 4, w_slot16 = (uint32_t)P.w_slot_bytes >> 4;
     const uint32_t tm0 = uni(tmem_base);
@@ -853,27 +852,37 @@ __global__ void __launch_bounds__(320) k_conv_tc_prog(const __grid_constant__ CU
       for (int ch = 0; ch < P.n_chunks; ++ch) {
         mbar_wait(smem_u32(fullA + sa), pha, 24);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a16 = a_base16 + (uint32_t)sa * a_slot16;
-        const uint32_t wch16 = w_base16 + (uint32_t)(ch * P.n_used_taps) * w_slot16;
-        for (int i = 0; i < P.n_prog; ++i) {
-          const TcProgEntry e = P.prog[i];
-          if (w_stream && e.w_adv) {
+        const uint32_t a_lo0 = desca_lo + uni(a_base16 + (uint32_t)sa * a_slot16);
+        const uint32_t b_lo0 = descb_lo + w_base16 + (uint32_t)(ch * P.n_used_taps) * w_slot16;
+        // entries [i, i + n_same) use one weight slice: a single elected region issues all their MMAs
+        for (int i = 0; i < P.n_prog;) {
+          const int n_same = w_stream ? (int)((P.prog[i].w_flags >> 20) & 63) : P.n_prog;
+          uint32_t b_ring = 0;
+          if (w_stream) {
             mbar_wait(smem_u32(fullW + sw), phw, 27);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            b_ring = descb_lo + w_base16 + uni((uint32_t)sw) * w_slot16;
           }
-          const uint64_t da = desca_t + (uint64_t)(a16 + e.a_off16);
-          const uint64_t db = descb_t + (uint64_t)(w_stream ? w_base16 + (uint32_t)sw * w_slot16 : wch16 + (uint32_t)e.w_slot * w_slot16);
-          const uint32_t dt = d0 + (uint32_t)e.acc * (uint32_t)P.N;
-          const uint32_t acc0 = (uint32_t)ch | (uint32_t)(e.first ^ 1);
           if (elect_one()) {
             if (!(P.ablate & 2)) {
+#pragma unroll 1
+              for (int e = i; e < i + n_same; ++e) {
+                const uint32_t ea = P.prog[e].a_acc, ew = P.prog[e].w_flags;
+                const uint32_t a_lo = a_lo0 + (ea & 0xffffu);
+                const uint32_t b_lo = w_stream ? b_ring : b_lo0 + (ew & 0xffffu);
+                const uint32_t dt = d0 + (ea >> 16);
+                const uint32_t accf = (uint32_t)ch | (((ew >> 16) & 1u) ^ 1u);
 #pragma unroll
-              for (int k = 0; k < KSTEPS; ++k) tc_mma_f16(dt, da + 2 * k, db + 2 * k, P.idesc, (acc0 | (uint32_t)k) ? 1u : 0u);
+                for (int k = 0; k < KSTEPS; ++k)
+                  tc_mma_f16(dt, ((uint64_t)desca_hi << 32) | (uint64_t)(a_lo + 2 * k), ((uint64_t)descb_hi << 32) | (uint64_t)(b_lo + 2 * k),
+                             P.idesc, (accf | (uint32_t)k) ? 1u : 0u);
+              }
             }
-            if (w_stream && e.w_last) tc_commit(smem_u32(emptyW + sw));
+            if (w_stream) tc_commit(smem_u32(emptyW + sw));
           }
           __syncwarp();
-          if (w_stream && e.w_last) { if (++sw == P.n_w_ring) { sw = 0; phw ^= 1; } }
+          if (w_stream) { if (++sw == P.n_w_ring) { sw = 0; phw ^= 1; } }
+          i += n_same;
         }
         if (elect_one()) tc_commit(smem_u32(emptyA + sa));
         __syncwarp();
@@ -1289,6 +1298,7 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
     Hp.halo_base_offset = getenv("SB_HALO_BASEOFF") ? atoi(getenv("SB_HALO_BASEOFF")) : 0;
     Hp.ablate = getenv("SB_ABLATE") ? atoi(getenv("SB_ABLATE")) : 0;
     Hp.n_prog = 0; Hp.n_acc = 0;
+    struct ProgTmp { int a_rows, w_tap, w_slot, acc, first, n_same; } prog_tmp[36];
     if (fused_phases) {
       // Conv2DTranspose k3 s2 (see sb_conv_tc_prepare): out[2i+a] gets (ky, row) = a==0 ? {(0,i),(2,i-1)} : {(1,i)};
       // same along x.  Box origin (x0-1, y0-1); phase (a, bx) accumulates in its own TMEM columns.
@@ -1306,12 +1316,8 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
           for (int qy = 0; qy < nky; ++qy)
             for (int qx = 0; qx < nkx; ++qx) {
               const int wt = kys[qy] * 3 + kxs[qx];
-              TcProgEntry& e = Hp.prog[Hp.n_prog++];
-              e.a_off16 = (uint16_t)((((dys[qy] + 1) * pitch + (dxs[qx] + 1)) * Hp.row_bytes) >> 4);
-              e.w_tap = (uint8_t)wt;
               Hp.used_taps[n_used] = wt; Hp.slot_of_tap[wt] = n_used;
-              e.w_slot = (uint8_t)n_used++;
-              e.acc = (uint8_t)acc; e.first = first ? 1 : 0; e.w_adv = 1; e.w_last = 1;
+              prog_tmp[Hp.n_prog++] = ProgTmp{((dys[qy] + 1) * pitch + (dxs[qx] + 1)), wt, n_used++, acc, first ? 1 : 0, 1};
               first = false;
             }
         }
@@ -1332,14 +1338,16 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
         Hp.acc_out[sIdx] = TcAccOut{(int16_t)((sIdx % sub_x) * 8), (int16_t)((sIdx / sub_x) * 16), (int16_t)oy_add, (int16_t)ox_add};
       for (int tp = 0; tp < Hp.n_htaps; ++tp)       // taps outermost: a weight slice serves every sub-tile
         for (int sIdx = 0; sIdx < n_sub; ++sIdx) {
-          TcProgEntry& e = Hp.prog[Hp.n_prog++];
           const int sub_rows = (sIdx / sub_x) * 16 * pitch + (sIdx % sub_x) * 8;
-          e.a_off16 = (uint16_t)(((sub_rows + Hp.htap_off_rows[tp]) * Hp.row_bytes) >> 4);
-          e.w_tap = (uint8_t)Hp.htap_w[tp];
-          e.w_slot = (uint8_t)Hp.slot_of_tap[Hp.htap_w[tp]];
-          e.acc = (uint8_t)sIdx; e.first = tp == 0 ? 1 : 0;
-          e.w_adv = sIdx == 0 ? 1 : 0; e.w_last = sIdx == n_sub - 1 ? 1 : 0;
+          prog_tmp[Hp.n_prog++] = ProgTmp{sub_rows + Hp.htap_off_rows[tp], Hp.htap_w[tp], Hp.slot_of_tap[Hp.htap_w[tp]], sIdx, tp == 0 ? 1 : 0,
+                                          sIdx == 0 ? n_sub : 0};
         }
+    }
+    for (int i = 0; i < Hp.n_prog; ++i) {
+      const ProgTmp& t = prog_tmp[i];
+      const uint32_t a_off16 = (uint32_t)(t.a_rows * Hp.row_bytes) >> 4, w_off16 = (uint32_t)(t.w_slot * Hp.w_slot_bytes) >> 4;
+      Hp.prog[i].a_acc = (a_off16 & 0xffffu) | ((uint32_t)(t.acc * N) << 16);
+      Hp.prog[i].w_flags = (w_off16 & 0xffffu) | ((uint32_t)t.first << 16) | ((uint32_t)t.n_same << 20) | ((uint32_t)t.w_tap << 26);
     }
     if (Hp.n_acc * N > 512) continue;
     Hp.a_tx_bytes = box_h * pitch * KC * 2;
