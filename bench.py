@@ -301,6 +301,14 @@ def run_ours(args):
     for i in range(args.warmup):
         step_device(i)
     barrier()
+    if args.ncu_step:
+        # `ncu --profile-from-start off ... bench.py --ncu-step`: exactly ONE warm step inside the
+        # cudaProfilerStart/Stop window (a profiling aid; prints no bench line)
+        torch.cuda.profiler.start()
+        step_device(args.warmup)
+        barrier()
+        torch.cuda.profiler.stop()
+        return
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -429,6 +437,7 @@ def main():
     ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32"])
     ap.add_argument("--cpu-frames", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu-step", action="store_true", help="profile window around one warm step, no bench line")
     args = ap.parse_args()
     # keep stdout clean for the ONE JSON line (NCCL / torchrun print banners on stdout)
     saved_stdout = os.dup(1)

@@ -1,0 +1,33 @@
+#!/bin/bash
+# One gpurun call that produces every artefact profiles/ is built from:
+#   bench line (+ autotune picks), ncu launch list with DRAM bytes, ncu --set full of one warm step, gpu tests.
+# usage (from the repo root on the GPU box): bash tools/gpu_evidence.sh [skip_tests]
+set -u
+O=gpurun_out
+mkdir -p $O
+export PYTHONUNBUFFERED=1
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/smi.txt 2>&1
+echo "== bench"; date +%s
+SB_DEBUG=1 BENCH_VERBOSE=1 SB_TUNE_SAVE=$O/tune.txt timeout 420 python bench.py > $O/bench_1gpu.json 2> $O/bench_1gpu.err
+echo "bench rc=$?"; tail -c 600 $O/bench_1gpu.json
+echo "== reference arm"; date +%s
+timeout 200 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_reference.json 2> $O/bench_reference.err
+echo "ref rc=$?"
+echo "== ncu launch list"; date +%s
+SB_TUNE_LOAD=$O/tune.txt timeout 400 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
+  --clock-control none --csv --log-file $O/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/ncu_list.log 2>&1
+echo "list rc=$?"
+echo "== ncu full (one warm step)"; date +%s
+SB_TUNE_LOAD=$O/tune.txt timeout 500 ncu --set full --clock-control none --import-source on --profile-from-start off \
+  -f -o $O/r01_step_full python bench.py --steps 1 --warmup 2 --no-cpu-baseline --ncu-step > $O/ncu_full.log 2>&1
+echo "full rc=$?"
+timeout 120 ncu -i $O/r01_step_full.ncu-rep --page raw --csv > $O/r01_step_full_raw.csv 2>/dev/null
+sz=$(stat -c %s $O/r01_step_full.ncu-rep 2>/dev/null || echo 0)
+if [ "$sz" -gt 45000000 ]; then echo "ncu-rep too big ($sz), keeping CSV only"; rm -f $O/r01_step_full.ncu-rep; fi
+ls -la $O
+if [ "${1:-}" != "skip_tests" ]; then
+  echo "== pytest gpu"; date +%s
+  timeout 600 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1
+  echo "pytest rc=$?"; tail -3 $O/pytest_gpu.log
+fi
+date +%s
