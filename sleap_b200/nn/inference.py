@@ -22,7 +22,7 @@ from sleap_b200 import _lib
 from sleap_b200._lib import BottomUpParams, CentroidParams, GlobalParams, f32, i32, ptr
 from sleap_b200.nn import architectures as arch
 from sleap_b200.nn import paf_grouping, peak_finding
-from sleap_b200.nn.model import DeviceModel, PRECISION_FP16, PRECISION_FP32, load_weights_npz
+from sleap_b200.nn.model import DeviceModel, PRECISION_FP16, PRECISION_FP32, load_weights, load_weights_npz
 
 REFINE = peak_finding.REFINE
 
@@ -563,17 +563,16 @@ class Predictor:
             raise ValueError("Must specify at least one model path.")   # :2479
         cfgs = {}
         for p in model_paths:
-            cfg_path = p if p.endswith(".json") else os.path.join(p, "training_config.json")
-            with open(cfg_path) as f:
-                cfg = json.load(f)
+            cfg, d = cls._read_config(p)
             heads = {k: v for k, v in cfg["model"]["heads"].items() if v is not None}
-            cfgs[next(iter(heads))] = (cfg, os.path.dirname(cfg_path))
+            cfgs[next(iter(heads))] = (cfg, d)
         kw = dict(peak_threshold=peak_threshold, integral_refinement=integral_refinement,
                   integral_patch_size=integral_patch_size, batch_size=batch_size, precision=precision, handle=handle)
         if "single_instance" in cfgs:
             return SingleInstancePredictor.from_trained_models(cfgs["single_instance"], **kw)
         if "centroid" in cfgs or "centered_instance" in cfgs:
-            return TopDownPredictor.from_trained_models(cfgs.get("centroid"), cfgs.get("centered_instance"),
+            return TopDownPredictor.from_trained_models(centroid_model_path=cfgs.get("centroid"),
+                                                        confmap_model_path=cfgs.get("centered_instance"),
                                                         max_instances=max_instances, **kw)
         if "multi_instance" in cfgs:
             return BottomUpPredictor.from_trained_models(cfgs["multi_instance"], max_instances=max_instances, **kw)
@@ -581,17 +580,25 @@ class Predictor:
 
     # -- shared helpers ---------------------------------------------------------------------
     @staticmethod
+    def _read_config(model_path):
+        """``TrainingJobConfig.load_json`` (config/training_job.py:93-124) on a model folder or a json inside it."""
+        cfg_path = model_path if model_path.endswith(".json") else os.path.join(model_path, "training_config.json")
+        with open(cfg_path) as f:
+            return json.load(f), os.path.dirname(cfg_path)
+
+    @staticmethod
     def _load(cfg_and_dir, precision, handle):
+        if isinstance(cfg_and_dir, (str, os.PathLike)):        # the reference passes model paths here
+            cfg_and_dir = Predictor._read_config(os.fspath(cfg_and_dir))
         cfg, d = cfg_and_dir
         spec = arch.spec_from_config(cfg["model"], *_skeleton_from_cfg(cfg))
-        wpath = os.path.join(d, "best_model.npz")
-        if not os.path.exists(wpath):
-            raise FileNotFoundError(
-                f"{wpath} not found.  Keras best_model.h5 files must be exported to .npz first "
-                "(see INTEGRATION.md: h5py is not available in this environment).")
         pre = cfg["data"]["preprocessing"]
-        in_ch = 1 if pre.get("ensure_grayscale") else (3 if pre.get("ensure_rgb") else int(cfg.get("_input_channels", 1)))
-        model = DeviceModel(spec, load_weights_npz(wpath), input_channels=in_ch,
+        weights = load_weights(d)
+        # The reference reads the channel count off the loaded Keras model's input (:905-911,
+        # ``is_grayscale``); here it is the C_in of the first convolution's kernel.
+        first = arch.compile_model(spec, 1).layers[0]["name"]
+        in_ch = int(np.asarray(weights[first]["kernel"]).shape[2])
+        model = DeviceModel(spec, weights, input_channels=in_ch,
                             input_scale=pre.get("input_scaling", 1.0) or 1.0, pad_to_stride=pre.get("pad_to_stride"),
                             precision=precision, handle=handle)
         return cfg, spec, model
@@ -701,9 +708,11 @@ class SingleInstancePredictor(Predictor):
             integral_patch_size=self.integral_patch_size))
 
     @classmethod
-    def from_trained_models(cls, cfg_and_dir, peak_threshold=0.2, integral_refinement=True, integral_patch_size=5,
-                            batch_size=4, precision=PRECISION_FP16, handle=None, **_):
-        _, _, model = cls._load(cfg_and_dir, precision, handle)
+    def from_trained_models(cls, model_path, inference_object=None, peak_threshold=0.2, integral_refinement=True,
+                            integral_patch_size=5, batch_size=4, resize_input_layer=True, precision=PRECISION_FP16,
+                            handle=None, **_):
+        """:1480-1545 (same argument names; ``model_path`` may also be a loaded (config, folder) pair)."""
+        _, _, model = cls._load(model_path, precision, handle)
         return cls(model, peak_threshold, integral_refinement, integral_patch_size, batch_size)
 
 
@@ -736,9 +745,11 @@ class TopDownPredictor(Predictor):
         self.inference_model = TopDownInferenceModel(cc, fp)
 
     @classmethod
-    def from_trained_models(cls, centroid_cfg, confmap_cfg, peak_threshold=0.2, integral_refinement=True,
-                            integral_patch_size=5, batch_size=4, max_instances=None, precision=PRECISION_FP16,
-                            handle=None, **_):
+    def from_trained_models(cls, centroid_model_path=None, confmap_model_path=None, batch_size=4, peak_threshold=0.2,
+                            integral_refinement=True, integral_patch_size=5, resize_input_layer=True,
+                            max_instances=None, precision=PRECISION_FP16, handle=None, **_):
+        """:2435-2560 (same argument names; paths may also be loaded (config, folder) pairs)."""
+        centroid_cfg, confmap_cfg = centroid_model_path, confmap_model_path
         if centroid_cfg is None and confmap_cfg is None:
             raise ValueError("Either the centroid or topdown confidence map model must be provided.")  # :2479
         if centroid_cfg is None or confmap_cfg is None:
@@ -784,10 +795,15 @@ class BottomUpPredictor(Predictor):
             max_node_peaks=self._caps[1], max_instances=self._caps[2]))
 
     @classmethod
-    def from_trained_models(cls, cfg_and_dir, peak_threshold=0.2, integral_refinement=True, integral_patch_size=5,
-                            batch_size=4, max_instances=None, precision=PRECISION_FP16, handle=None, **_):
-        _, spec, model = cls._load(cfg_and_dir, precision, handle)
+    def from_trained_models(cls, model_path, batch_size=4, peak_threshold=0.2, integral_refinement=True,
+                            integral_patch_size=5, max_edge_length_ratio=0.25, dist_penalty_weight=1.0,
+                            paf_line_points=10, min_line_scores=0.25, resize_input_layer=True, max_instances=None,
+                            precision=PRECISION_FP16, handle=None, **_):
+        """:3150-3228 (same argument names; ``model_path`` may also be an already loaded (config, folder) pair)."""
+        _, spec, model = cls._load(model_path, precision, handle)
         return cls(model, spec["part_names"], spec["edges"], peak_threshold=peak_threshold, batch_size=batch_size,
+                   max_edge_length_ratio=max_edge_length_ratio, dist_penalty_weight=dist_penalty_weight,
+                   paf_line_points=paf_line_points, min_line_scores=min_line_scores,
                    integral_refinement=integral_refinement, integral_patch_size=integral_patch_size,
                    max_instances=max_instances)
 

@@ -82,6 +82,36 @@ def load_weights_npz(path):
     return w
 
 
+_KERAS_PARAM = {"moving_mean": "mean", "moving_variance": "var"}
+
+
+def load_weights_h5(path):
+    """Keras ``best_model.h5`` -> ``{layer: {param: array}}`` (sleap/nn/inference.py:3203-3213 loads the same
+    file with ``tf.keras.models.load_model``).  Read with the in-tree HDF5 reader (no h5py needed).
+    Output layers are named ``{HeadClass}_{i}`` by the reference (sleap/nn/model.py:351-360); the
+    compiled graph uses the class name, so an index suffix ``_0`` is dropped."""
+    from sleap_b200.io import h5lite
+    raw = h5lite.read_keras_weights(path)
+    w = {}
+    for layer, params in raw.items():
+        name = layer
+        if "Head_" in layer and layer.rsplit("_", 1)[1].isdigit():
+            base, idx = layer.rsplit("_", 1)
+            name = base if idx == "0" else layer
+        w[name] = {_KERAS_PARAM.get(k, k): np.asarray(v) for k, v in params.items()}
+    return w
+
+
+def load_weights(model_dir):
+    """``best_model.npz`` (exported) if present, else the Keras ``best_model.h5``."""
+    npz, h5 = os.path.join(model_dir, "best_model.npz"), os.path.join(model_dir, "best_model.h5")
+    if os.path.exists(npz):
+        return load_weights_npz(npz)
+    if os.path.exists(h5):
+        return load_weights_h5(h5)
+    raise FileNotFoundError(f"neither best_model.npz nor best_model.h5 found in {model_dir}")
+
+
 def save_weights_npz(path, weights):
     flat = {f"{layer}/{param}": arr for layer, p in weights.items() for param, arr in p.items()}
     np.savez(path, **flat)

@@ -1,0 +1,31 @@
+"""Shared helpers for the trained-fixture-model parity tests (CPU oracle and CUDA path).
+
+Fixtures under tests/golden/ are made by tests/golden/make_reference_fixtures.py from the
+reference's own test data; the assertions restate tests/nn/test_inference.py:585-800."""
+import json
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def model_dir(name):
+    return os.path.join(GOLDEN, "models", name)
+
+
+def load_fixture_model(name):
+    """-> (cfg, spec, weights, in_ch)"""
+    from sleap_b200.nn import architectures as A
+    from sleap_b200.nn.model import load_weights
+    d = model_dir(name)
+    cfg = json.load(open(os.path.join(d, "training_config.json")))
+    spec = A.spec_from_config(cfg["model"])
+    w = load_weights(d)
+    first = next(v for k, v in w.items() if k.endswith("enc0_conv0"))
+    return cfg, spec, w, int(first["kernel"].shape[2])
+
+
+def frames(name):
+    z = np.load(os.path.join(GOLDEN, f"frames_{name}.npz"))
+    return z["images"], z["points_gt"]

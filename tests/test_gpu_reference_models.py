@@ -1,0 +1,84 @@
+"""CUDA path on the reference's trained fixture models (tests/golden/, made from the reference's own test data):
+the public ``Predictor.from_model_paths(...).predict(...)`` call must (1) satisfy the assertions of the
+reference's predictor tests against the ground-truth labels (tests/nn/test_inference.py:585-800) and
+(2) agree with the CPU oracle on the same frames (fp32 path: sub-pixel identical; fp16 tensor-core path: 0.15 px)."""
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose
+
+import reference_models as rm
+from oracle import inference as oinf
+
+pytestmark = pytest.mark.gpu
+
+TOL = {1: 5e-3, 0: 0.15}     # px, vs the fp32 oracle
+
+
+def _matched(a, b, atol):
+    i1, i2 = oinf.match_points(a, b)
+    assert len(i1) == len(a)
+    assert_allclose(a[i1], b[i2], atol=atol)
+
+
+@pytest.mark.parametrize("precision", [1, 0])
+def test_bottomup_trained_model(precision):
+    from sleap_b200.nn.inference import BottomUpPredictor, Predictor
+    imgs, gt = rm.frames("minimal_instance")
+    pred = Predictor.from_model_paths([rm.model_dir("minimal_instance.bottomup")], precision=precision)
+    assert isinstance(pred, BottomUpPredictor)
+    frames = pred.predict(imgs)
+    assert len(frames) == 1 and len(frames[0].instances) == 2
+    pts = np.concatenate([i.numpy() for i in frames[0].instances])
+    _matched(gt[0].reshape(-1, 2), pts, 1.75)
+    cfg, spec, w, in_ch = rm.load_fixture_model("minimal_instance.bottomup")
+    want = oinf.bottomup_layer(imgs, spec, w, in_ch, 1.0, 8)
+    out = pred.inference_model.predict_on_batch(imgs)
+    assert int(out["n_valid"][0]) == len(want["instance_peaks"][0]) == 2
+    assert_allclose(out["instance_peaks"][0, :2], want["instance_peaks"][0], atol=TOL[precision])
+    assert_allclose(out["instance_scores"][0, :2], want["instance_scores"][0], atol=2e-2 if precision == 0 else 1e-4)
+    hi = BottomUpPredictor.from_trained_models(model_path=rm.model_dir("minimal_instance.bottomup"), min_line_scores=1.1,
+                                               precision=precision)
+    assert len(hi.predict(imgs)[0].instances) == 0
+
+
+@pytest.mark.parametrize("precision", [1, 0])
+def test_topdown_trained_models(precision):
+    from sleap_b200.nn.inference import Predictor, TopDownPredictor
+    imgs, gt = rm.frames("minimal_instance")
+    paths = [rm.model_dir("minimal_instance.centroid"), rm.model_dir("minimal_instance.centered_instance")]
+    pred = Predictor.from_model_paths(paths, precision=precision)
+    assert isinstance(pred, TopDownPredictor) and pred.crop_size == 96
+    out = pred.inference_model.predict_on_batch(imgs)
+    assert int(out["n_valid"][0]) == 2
+    ccfg, cspec, cw, cin = rm.load_fixture_model("minimal_instance.centroid")
+    icfg, ispec, iw, iin = rm.load_fixture_model("minimal_instance.centered_instance")
+    want = oinf.topdown_model(imgs, cspec, cw, ispec, iw, 96, cin, iin, 1.0, 1.0, 8, 8)
+    assert_allclose(out["centroids"][0, :2], want["centroids"][0], atol=TOL[precision])
+    # a centroid that moves by d px moves the bilinear crop, so the instance stage is compared more loosely in fp16
+    assert_allclose(out["instance_peaks"][0, :2], want["instance_peaks"][0], atol=TOL[precision] * (1 if precision else 3))
+    _matched(gt[0].reshape(-1, 2), out["instance_peaks"][0, :2].reshape(-1, 2), 2.0)
+    for k in (1, 2, 3):                                      # test_topdown_predictor_centroid_max_instances
+        p = Predictor.from_model_paths(paths, precision=precision, max_instances=k)
+        assert int(p.inference_model.predict_on_batch(imgs)["n_valid"][0]) == min(k, 2)
+    p = Predictor.from_model_paths(paths, precision=precision, peak_threshold=1.5)
+    assert len(p.predict(imgs)[0].instances) == 0
+
+
+@pytest.mark.parametrize("precision", [1, 0])
+def test_single_instance_trained_model(precision):
+    from sleap_b200.nn.inference import Predictor, SingleInstancePredictor
+    imgs, gt = rm.frames("robot")
+    d = rm.model_dir("minimal_robot.single_instance")          # best_model.h5 read by the in-tree HDF5 reader
+    pred = Predictor.from_model_paths([d], precision=precision)
+    assert isinstance(pred, SingleInstancePredictor)
+    frames = pred.predict(imgs)
+    assert len(frames) == 2 and len(frames[0].instances) == 1
+    pts = np.stack([f.instances[0].numpy() for f in frames])
+    assert_allclose(pts, gt[:, 0], atol=10.0)
+    cfg, spec, w, in_ch = rm.load_fixture_model("minimal_robot.single_instance")
+    want = oinf.single_instance_layer(imgs, spec, w, in_ch, 0.5, 4)
+    assert_allclose(pts, want["instance_peaks"][:, 0], atol=TOL[precision] * 2)   # x2: coordinates are /input_scale
+    lo = Predictor.from_model_paths([d], precision=precision, peak_threshold=0.0).predict(imgs)
+    assert all(np.isfinite(f.instances[0].numpy()).all() for f in lo)
+    hi = Predictor.from_model_paths([d], precision=precision, peak_threshold=1.5).predict(imgs)
+    assert all(len(f.instances) == 0 for f in hi)

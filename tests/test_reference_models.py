@@ -1,0 +1,110 @@
+"""Pins the conv-network oracle (and the whole CPU restatement) to the reference's OWN predictor tests:
+trained fixture models + real frames + ground-truth labels, same assertions and tolerances as
+tests/nn/test_inference.py (test_single_instance_predictor :585-610, test_topdown_predictor_centroid :638-656,
+test_topdown_predictor_centered_instance-style matching :728-757, test_bottomup_predictor :770-800).
+Also exercises the in-tree HDF5 reader on the committed Keras .h5 / .slp files."""
+import os
+
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose
+
+from oracle import inference as oinf
+import reference_models as rm
+
+
+def _matched(points_gt, points_pr, atol):
+    i1, i2 = oinf.match_points(points_gt, points_pr)
+    assert len(i1) == len(points_gt)
+    assert_allclose(points_gt[i1], points_pr[i2], atol=atol)
+
+
+def test_h5_reader_keras_weights_match_npz_export():
+    from sleap_b200.io import h5lite
+    from sleap_b200.nn.model import load_weights_h5
+    d = rm.model_dir("minimal_robot.single_instance")
+    f = h5lite.File(os.path.join(d, "best_model.h5"))
+    assert set(f.keys()) >= {"model_weights"}
+    assert f.attrs["backend"] == "tensorflow"
+    w = load_weights_h5(os.path.join(d, "best_model.h5"))
+    assert w["stack0_enc0_conv0"]["kernel"].shape[:2] == (3, 3)
+    assert "SingleInstanceConfmapsHead" in w
+    n = sum(a.size for p in w.values() for a in p.values())
+    from sleap_b200.nn import architectures as A
+    _, spec, _, in_ch = rm.load_fixture_model("minimal_robot.single_instance")
+    assert n == A.count_params(A.compile_model(spec, in_ch))
+
+
+def test_h5_reader_slp_tables():
+    from sleap_b200.io import h5lite
+    f = h5lite.File(os.path.join(rm.GOLDEN, "labels", "minimal_instance.slp"))
+    assert sorted(f.keys()) == ["frames", "instances", "metadata", "points", "pred_points", "suggestions_json",
+                                "tracks_json", "videos_json"]
+    pts = f["points"].read()
+    assert pts.dtype.names == ("x", "y", "visible", "complete") and len(pts) == 4
+    assert_allclose([pts["x"][0], pts["y"][0]], [92.65220773, 202.72597774], rtol=1e-9)
+    inst = f["instances"].read()
+    assert list(inst["point_id_end"]) == [2, 4]
+    assert f["metadata"].attrs["format_id"] == 1.1 or str(f["metadata"].attrs["format_id"]).startswith("1.1")
+    _, gt = rm.frames("minimal_instance")
+    assert_allclose(gt[0, 0, 0], [pts["x"][0], pts["y"][0]], rtol=1e-6)
+
+
+def test_oracle_bottomup_on_trained_model():
+    """test_bottomup_predictor: 1 frame, 2 instances, matched points within 1.75 px of the labels."""
+    cfg, spec, w, in_ch = rm.load_fixture_model("minimal_instance.bottomup")
+    imgs, gt = rm.frames("minimal_instance")
+    pre = cfg["data"]["preprocessing"]
+    out = oinf.bottomup_layer(imgs, spec, w, in_ch, pre["input_scaling"], spec["backbone_cfg"]["max_stride"])
+    assert len(out["instance_peaks"][0]) == 2
+    _matched(gt[0].reshape(-1, 2), out["instance_peaks"][0].reshape(-1, 2), 1.75)
+    hi = oinf.bottomup_layer(imgs, spec, w, in_ch, pre["input_scaling"], spec["backbone_cfg"]["max_stride"],
+                             min_line_scores=1.1)
+    assert len(hi["instance_peaks"][0]) == 0
+
+
+def test_oracle_topdown_on_trained_models():
+    """test_topdown_predictor_centroid (:638-656, atol 1.5 on centroid-only instances) and the full
+    centroid -> centered-instance chain (atol 1.5 as :757)."""
+    ccfg, cspec, cw, cin = rm.load_fixture_model("minimal_instance.centroid")
+    icfg, ispec, iw, iin = rm.load_fixture_model("minimal_instance.centered_instance")
+    imgs, gt = rm.frames("minimal_instance")
+    crop = icfg["data"]["instance_cropping"]["crop_size"]
+    out = oinf.topdown_model(imgs, cspec, cw, ispec, iw, crop, cin, iin,
+                             ccfg["data"]["preprocessing"]["input_scaling"], icfg["data"]["preprocessing"]["input_scaling"],
+                             cspec["backbone_cfg"]["max_stride"], ispec["backbone_cfg"]["max_stride"])
+    assert len(out["instance_peaks"][0]) == 2
+    # full predicted chain: the reference has no test of this model pair against the labels (its centroid-only /
+    # instance-only tests stand in ground truth for the other stage); 2 px is our own sanity bound
+    _matched(gt[0].reshape(-1, 2), out["instance_peaks"][0].reshape(-1, 2), 2.0)
+    # centroid stage alone vs the labels' bounding-box midpoints (instance_centroids.py:12-33, anchor_part=None)
+    cent_gt = np.stack([(g.min(0) + g.max(0)) * 0.5 for g in gt[0]]).astype(np.float32)
+    _matched(cent_gt, out["centroids"][0], 1.5)
+    # test_topdown_predictor_centered_instance (:728-757): crops at the GROUND-TRUTH centroids
+    # (CentroidCropGroundTruth, inference.py:743-809), instance peaks within 1.5 px of the labels
+    from oracle import tf_ops
+    crops = tf_ops.crop_bboxes(imgs, tf_ops.make_centered_bboxes(cent_gt, crop, crop), np.zeros(2, np.int32))
+    pts, _ = oinf.find_instance_peaks_layer(crops, (cent_gt - np.float32(crop / 2)).astype(np.float32), ispec, iw, iin,
+                                            1.0, ispec["backbone_cfg"]["max_stride"])
+    _matched(gt[0].reshape(-1, 2), pts.reshape(-1, 2), 1.5)
+    for k in (1, 2, 3):                                     # test_topdown_predictor_centroid_max_instances :659-671
+        o = oinf.topdown_model(imgs, cspec, cw, ispec, iw, crop, cin, iin, 1.0, 1.0, 8, 8, max_instances=k)
+        assert len(o["instance_peaks"][0]) == min(k, 2)
+    hi = oinf.topdown_model(imgs, cspec, cw, ispec, iw, crop, cin, iin, 1.0, 1.0, 8, 8, peak_threshold=1.5)
+    assert len(hi["instance_peaks"][0]) == 0                # :674-683
+
+
+def test_oracle_single_instance_on_trained_model():
+    """test_single_instance_predictor (:585-610): 2 frames, 1 instance each, atol 10 px;
+    _high_peak_thresh (:613-635): threshold 0 -> 2 visible points, 1.5 -> none."""
+    cfg, spec, w, in_ch = rm.load_fixture_model("minimal_robot.single_instance")
+    imgs, gt = rm.frames("robot")
+    pre = cfg["data"]["preprocessing"]
+    out = oinf.single_instance_layer(imgs, spec, w, in_ch, pre["input_scaling"], spec["backbone_cfg"]["max_stride"],
+                                     peak_threshold=0.2)
+    assert out["instance_peaks"].shape == (2, 1, 2, 2)
+    assert_allclose(out["instance_peaks"][:, 0], gt[:, 0], atol=10.0)
+    lo = oinf.single_instance_layer(imgs, spec, w, in_ch, pre["input_scaling"], 4, peak_threshold=0.0)
+    assert not np.isnan(lo["instance_peaks"]).any()
+    hi = oinf.single_instance_layer(imgs, spec, w, in_ch, pre["input_scaling"], 4, peak_threshold=1.5)
+    assert np.isnan(hi["instance_peaks"]).all()
