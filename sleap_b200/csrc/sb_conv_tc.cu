@@ -1105,6 +1105,10 @@ struct SbConvTcPlan {
   bool use_fused = false;
   __half* w16 = nullptr;            // [taps][Cout_pad][Cin]
   int Cout_pad = 0;
+  // first layer as a Toeplitz GEMM (sb_first_view_prepare): staged [B][H][W/8][16] fp16 view of the frame
+  __half* view_in = nullptr;
+  float* view_bias = nullptr;       // bias replicated over the 8 pixels of a group: [8 * Cout]
+  int view_Wg = 0;
 };
 
 static CUtensorMapSwizzle swz_for(int KC) {
@@ -1131,7 +1135,12 @@ void sb_conv_first_tc_release(const SbModel* m);
 void sb_conv_tc_release(SbModel* m) {
   sb_conv_first_tc_release(m);
   for (SbConvTcPlan* p : m->tc_plans)
-    if (p) { if (p->w16) cudaFree(p->w16); delete p; }
+    if (p) {
+      if (p->w16) cudaFree(p->w16);
+      if (p->view_in) cudaFree(p->view_in);
+      if (p->view_bias) cudaFree(p->view_bias);
+      delete p;
+    }
   m->tc_plans.clear();
 }
 
@@ -1139,14 +1148,25 @@ bool sb_conv_tc_can(const SbModel* m, int op_index) {
   return op_index < (int)m->tc_plans.size() && m->tc_plans[op_index] != nullptr;
 }
 
+// A launch over tensors that are not op-list buffers (the Toeplitz view of the first layer): every
+// quantity make_launch would read from the op / its buffers.
+struct TcView {
+  SbBuffer ib, ob;
+  int Cin, Cout;
+  const float* bias;
+  int relu;
+};
+
 static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan* plan, int n_groups,
                        const TcGroup* groups, int dy0, int extra_rows, int n_wtaps, int oy_mul, int oy_add,
-                       int ox_mul, int ox_add, int fused_phases = 0, std::vector<TcLaunch>* dst = nullptr) {
+                       int ox_mul, int ox_add, int fused_phases = 0, std::vector<TcLaunch>* dst = nullptr,
+                       const TcView* view = nullptr) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return sb_fail(h, SB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  const SbBuffer& ib = m->buffers[op.in_buf()];
-  const SbBuffer& ob = m->buffers[op.out_buf()];
-  const int Cin = op.in_C(), Cout = op.out_C();
+  const SbBuffer& ib = view ? view->ib : m->buffers[op.in_buf()];
+  const SbBuffer& ob = view ? view->ob : m->buffers[op.out_buf()];
+  const int Cin = view ? view->Cin : op.in_C(), Cout = view ? view->Cout : op.out_C();
+  const int in_coff = view ? 0 : op.in_coff(), out_coff = view ? 0 : op.out_coff();
   const int KC = Cin >= 64 ? 64 : Cin;
   TcLaunch L;
   memset(&L, 0, sizeof(L));
@@ -1166,14 +1186,18 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
   int cols = 32;
   while (cols < N) cols <<= 1;
   P.tmem_cols = cols;
-  P.out = ob.dev; P.out_f32 = ob.f32; P.out_H = ob.H; P.out_W = ob.W; P.out_Ctot = ob.C; P.out_coff = op.out_coff();
+  P.out = ob.dev; P.out_f32 = ob.f32; P.out_H = ob.H; P.out_W = ob.W; P.out_Ctot = ob.C; P.out_coff = out_coff;
   P.oy_mul = oy_mul; P.oy_add = oy_add; P.ox_mul = ox_mul; P.ox_add = ox_add;
-  P.bias = op.b_off() >= 0 ? m->weights_dev + op.b_off() : nullptr;
-  P.bn_scale = (op.flags() & SB_OPF_BN) ? m->weights_dev + op.bn_scale_off() : nullptr;
-  P.bn_shift = (op.flags() & SB_OPF_BN) ? m->weights_dev + op.bn_shift_off() : nullptr;
-  P.relu = (op.flags() & SB_OPF_RELU) ? 1 : 0;
+  if (view) {
+    P.bias = view->bias; P.bn_scale = nullptr; P.bn_shift = nullptr; P.relu = view->relu;
+  } else {
+    P.bias = op.b_off() >= 0 ? m->weights_dev + op.b_off() : nullptr;
+    P.bn_scale = (op.flags() & SB_OPF_BN) ? m->weights_dev + op.bn_scale_off() : nullptr;
+    P.bn_shift = (op.flags() & SB_OPF_BN) ? m->weights_dev + op.bn_shift_off() : nullptr;
+    P.relu = (op.flags() & SB_OPF_RELU) ? 1 : 0;
+  }
   P.pool_out = nullptr;
-  if (op.kind() == SB_OPK_CONV && op.pool_buf() >= 0 && !ob.f32 && Cout % 16 == 0 &&
+  if (!view && op.kind() == SB_OPK_CONV && op.pool_buf() >= 0 && !ob.f32 && Cout % 16 == 0 &&
       m->buffers[op.pool_buf()].C % 8 == 0 && op.pool_coff() % 8 == 0 && ib.H % 2 == 0 && ib.W % 2 == 0) {
     const SbBuffer& pb = m->buffers[op.pool_buf()];
     P.pool_out = pb.dev; P.pool_H = pb.H; P.pool_W = pb.W; P.pool_Ctot = pb.C; P.pool_coff = op.pool_coff();
@@ -1395,7 +1419,7 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
     cuuint64_t strides[3] = {(cuuint64_t)ib.C * 2, (cuuint64_t)ib.W * ib.C * 2, (cuuint64_t)ib.H * ib.W * ib.C * 2};
     cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)pitch, (cuuint32_t)box_h, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
-    void* gptr = (void*)((__half*)ib.dev + op.in_coff());
+    void* gptr = (void*)((__half*)ib.dev + in_coff);
     CUresult r = enc(&HC.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, gptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      swz_for(KC), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return sb_fail(h, SB_ERR_CUDA, "cuTensorMapEncodeTiled(A halo) failed: %d", (int)r);
@@ -1409,7 +1433,7 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
     cuuint64_t strides[3] = {(cuuint64_t)ib.C * 2, (cuuint64_t)ib.W * ib.C * 2, (cuuint64_t)ib.H * ib.W * ib.C * 2};
     cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)TW, (cuuint32_t)P.box_rows, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
-    void* gptr = (void*)((__half*)ib.dev + op.in_coff());
+    void* gptr = (void*)((__half*)ib.dev + in_coff);
     CUresult r = enc(&L.mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, gptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      swz_for(KC), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return sb_fail(h, SB_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: %d", (int)r);
@@ -1426,6 +1450,126 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
   }
   (dst ? *dst : plan->launches).push_back(L);
   return 0;
+}
+
+// ---- first layer (1 input channel, 3x3) as a Toeplitz GEMM over groups of 8 output pixels ----------
+// out[y][8g+j][co] = sum_{ky,kx} in[y+ky-1][8g+j+kx-1] * w[ky][kx][co]   (SAME padding)
+// With G[y][g][c] = in[y][8g-1+c] (c = 0..9; c = 10..15 zero) the layer is an ordinary 3x1 convolution
+// over the [H][W/8] grid of groups with 16 "input channels" (the window) and 8*Cout "output channels"
+// (pixel j of the group x filter co): W'[ky][j*Cout+co][c] = w[ky][c-j][co] for 0 <= c-j <= 2.  The
+// output [H][W/8][8*Cout] is byte-identical to NHWC [H][W][Cout], so the stock tcgen05 conv kernels run
+// it unchanged: each epilogue thread writes 8 pixels (8*Cout*2 contiguous bytes) instead of gathering a
+// 3x3 neighbourhood per pixel, which is what bound the CUDA-core k_conv_first (28% of its FMA pipe, 19%
+// of DRAM write bandwidth in profiles/r01_step_full_summary.md).  Tensor work grows 3.5x (16x8*Cout
+// MACs per tap row instead of 9*Cout per pixel) on a pipe that is otherwise idle in this layer.
+template <typename TI>
+__global__ void __launch_bounds__(256) k_first_view(const TI* __restrict__ img, int Hin, int Win, int Hnet, int Wg,
+                                                    __half* __restrict__ G, int in_is_u8, size_t total) {
+  const float sc = in_is_u8 ? (1.0f / 255.0f) : 1.0f;       // ensure_float (normalization.py:34-49)
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+    const int g = (int)(i % Wg);
+    const size_t r = i / Wg;
+    const int y = (int)(r % Hnet), b = (int)(r / Hnet);
+    __align__(16) __half v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] = __float2half_rn(0.f);
+    if (y < Hin) {                                           // rows below the frame: bottom zero pad (resizing.py:34-68)
+      const TI* row = img + ((size_t)b * Hin + y) * Win;
+#pragma unroll
+      for (int c = 0; c < 10; ++c) {
+        const int x = 8 * g - 1 + c;
+        if (x >= 0 && x < Win) v[c] = __float2half_rn(__fmul_rn((float)row[x], sc));
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(G + i * 16);
+    dst[0] = *reinterpret_cast<const uint4*>(&v[0]);
+    dst[1] = *reinterpret_cast<const uint4*>(&v[8]);
+  }
+}
+
+int sb_first_fusion_op(const SbModel* m, size_t pre_index);   // sb_model.cu
+
+// Builds the plan of the first conv (op `oi`, fused with the PREPROCESS op before it) when the shape
+// allows the Toeplitz form; leaves m->tc_plans[oi] null otherwise (k_conv_first then runs the layer).
+static int first_view_prepare(sb_handle_s* h, SbModel* m, int oi) {
+  if (getenv("SB_DISABLE_FIRST_VIEW") || getenv("SB_DISABLE_TC")) return 0;
+  const SbOp& op = m->ops[oi];
+  const SbBuffer& ob = m->buffers[op.out_buf()];
+  const int Cout = op.out_C();
+  if (m->Cin != 1 || op.in_C() != 1 || op.k() != 3 || op.stride() != 1) return 0;
+  if (!(Cout == 8 || Cout == 16 || Cout == 24 || Cout == 32)) return 0;           // N = 8*Cout <= 256, multiple of 16
+  if (ob.f32 || ob.C != Cout || op.out_coff() != 0 || op.pool_buf() >= 0 || (op.flags() & SB_OPF_BN)) return 0;
+  if (ob.W % 8 || ob.W / 8 < TW || ob.H < TH + 2) return 0;                        // the streaming TMA box must fit inside the view
+  const int Wg = ob.W / 8, N = 8 * Cout;
+  SbConvTcPlan* plan = new SbConvTcPlan();
+  plan->Cout_pad = N;
+  plan->view_Wg = Wg;
+  std::vector<__half> w16((size_t)3 * N * 16, __float2half(0.f));
+  const float* w = m->weights_host.data() + op.w_off();                            // [9][1][Cout]
+  for (int ky = 0; ky < 3; ++ky)
+    for (int j = 0; j < 8; ++j)
+      for (int kx = 0; kx < 3; ++kx)
+        for (int co = 0; co < Cout; ++co)
+          w16[((size_t)ky * N + j * Cout + co) * 16 + j + kx] = __float2half_rn(w[(size_t)(ky * 3 + kx) * Cout + co]);
+  std::vector<float> brep(N, 0.f);
+  if (op.b_off() >= 0)
+    for (int n = 0; n < N; ++n) brep[n] = m->weights_host[op.b_off() + n % Cout];
+  auto fail = [&](const char* what, cudaError_t e) {
+    if (plan->w16) cudaFree(plan->w16);
+    if (plan->view_in) cudaFree(plan->view_in);
+    if (plan->view_bias) cudaFree(plan->view_bias);
+    delete plan;
+    return sb_fail(h, SB_ERR_CUDA, "first-layer view: %s: %s", what, cudaGetErrorString(e));
+  };
+  cudaError_t e = cudaMalloc((void**)&plan->w16, w16.size() * sizeof(__half));
+  if (e != cudaSuccess) return fail("cudaMalloc w16", e);
+  e = cudaMemcpy(plan->w16, w16.data(), w16.size() * sizeof(__half), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return fail("copy w16", e);
+  e = cudaMalloc((void**)&plan->view_bias, N * sizeof(float));
+  if (e != cudaSuccess) return fail("cudaMalloc bias", e);
+  e = cudaMemcpy(plan->view_bias, brep.data(), N * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return fail("copy bias", e);
+  const size_t vbytes = (size_t)m->B * ob.H * Wg * 16 * sizeof(__half);
+  e = cudaMalloc((void**)&plan->view_in, vbytes + 256);
+  if (e != cudaSuccess) return fail("cudaMalloc view", e);
+  e = cudaMemset(plan->view_in, 0, vbytes + 256);
+  if (e != cudaSuccess) return fail("memset view", e);
+  TcView V;
+  V.ib = SbBuffer(); V.ib.C = 16; V.ib.H = ob.H; V.ib.W = Wg; V.ib.dev = plan->view_in;
+  V.ob = SbBuffer(); V.ob.C = N; V.ob.H = ob.H; V.ob.W = Wg; V.ob.dev = ob.dev; V.ob.f32 = 0;
+  V.Cin = 16; V.Cout = N;
+  V.bias = plan->view_bias;
+  V.relu = (op.flags() & SB_OPF_RELU) ? 1 : 0;
+  TcGroup g[1];
+  g[0].dx = 0; g[0].n_taps = 3;
+  for (int ky = 0; ky < 3; ++ky) g[0].taps[ky] = TcTap{ky, ky};
+  const int rc = make_launch(h, m, op, plan, 1, g, -1, 2, 3, 1, 0, 1, 0, 0, nullptr, &V);
+  if (rc) {
+    cudaFree(plan->w16); cudaFree(plan->view_in); cudaFree(plan->view_bias);
+    delete plan;
+    return rc < 0 ? rc : 0;
+  }
+  m->tc_plans[oi] = plan;
+  return 0;
+}
+
+bool sb_first_view_can(const SbModel* m, int op_index) {
+  return op_index >= 0 && op_index < (int)m->tc_plans.size() && m->tc_plans[op_index] && m->tc_plans[op_index]->view_in;
+}
+
+// frame -> Toeplitz view -> tcgen05 conv (the launch sb_conv_tc_autotune picked)
+int sb_first_view_launch(sb_handle_s* h, SbModel* m, int op_index, const void* frames_dev, int frames_are_u8, int B) {
+  SbConvTcPlan* plan = m->tc_plans[op_index];
+  const SbBuffer& ob = m->buffers[m->ops[op_index].out_buf()];
+  const size_t total = (size_t)B * ob.H * plan->view_Wg;
+  const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)h->sm_count * 16);
+  if (frames_are_u8)
+    k_first_view<unsigned char><<<grid, 256, 0, h->stream>>>((const unsigned char*)frames_dev, m->Hin, m->Win, ob.H, plan->view_Wg,
+                                                             plan->view_in, 1, total);
+  else
+    k_first_view<float><<<grid, 256, 0, h->stream>>>((const float*)frames_dev, m->Hin, m->Win, ob.H, plan->view_Wg, plan->view_in, 0, total);
+  SB_CHECK_LAUNCH(h);
+  return sb_conv_tc_launch(h, m, op_index, B);
 }
 
 int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m);
@@ -1526,6 +1670,14 @@ int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m) {
         m->ops[oi + 1].kind() == SB_OPK_POOL && (m->ops[oi + 1].flags() & SB_OPF_FUSED_POOL))
       if (plan->launches[0].P.pool_out != nullptr) m->skip_op[oi + 1] = 1;
   }
+  for (size_t oi = 0; oi + 1 < m->ops.size(); ++oi)
+    if (m->ops[oi].kind() == SB_OPK_PREPROCESS) {
+      const int cv = sb_first_fusion_op(m, oi);
+      if (cv >= 0 && !m->tc_plans[cv]) {
+        const int rc = first_view_prepare(h, m, cv);
+        if (rc) return rc;
+      }
+    }
   return sb_conv_tc_autotune(h, m);
 }
 

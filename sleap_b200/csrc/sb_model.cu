@@ -149,7 +149,8 @@ int sb_model_configure(sb_handle_t h, int model_id, int max_batch, int H, int W,
 }  // extern "C"
 
 // First conv fused with preprocessing (fp16 path): returns the conv op index or -1.
-static int first_fusion_op(const SbModel* m, size_t pre_index) {
+static int first_fusion_op(const SbModel* m, size_t pre_index) { return sb_first_fusion_op(m, pre_index); }
+int sb_first_fusion_op(const SbModel* m, size_t pre_index) {
   if (m->precision != 0 || getenv("SB_DISABLE_FIRST_FUSION")) return -1;
   if (pre_index + 1 >= m->ops.size()) return -1;
   const SbOp& pre = m->ops[pre_index];
@@ -193,6 +194,11 @@ static int run_ops_t(sb_handle_s* h, SbModel* m, const void* frames_dev, int fra
     SbBuffer& ob = m->buffers[op.out_buf()];
     if ((int)oi == m->guard_op && h->post_pending) SB_CUDA(h, cudaStreamWaitEvent(s, h->post_done_ev, 0));
     if (oi < m->skip_op.size() && m->skip_op[oi]) continue;     // 2x2 max-pool fused into the producing conv
+    if ((int)oi == fused_first && sb_first_view_can(m, (int)oi)) {
+      int rc = sb_first_view_launch(h, m, (int)oi, frames_dev, frames_are_u8, B);
+      if (rc) return rc;
+      continue;
+    }
     if ((int)oi == fused_first && sb_conv_first_tc_ok(m, op)) {
       int rc = sb_conv_first_tc_launch(h, m, op, frames_dev, frames_are_u8, B);
       if (rc) return rc;

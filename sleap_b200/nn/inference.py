@@ -603,8 +603,23 @@ class Predictor:
                             precision=precision, handle=handle)
         return cfg, spec, model
 
+    def _as_frames(self, data):
+        """``predict`` accepts a video path, ``Video`` or ``VideoReader`` provider (:496-531, make_pipeline :329-371):
+        those are read through the threaded ``FrameFeeder`` (decode ahead into pinned batch buffers)."""
+        from sleap_b200.io.video import FrameFeeder, Video, VideoReader
+        if isinstance(data, (str, os.PathLike, Video, VideoReader)):
+            return FrameFeeder(data, batch_size=self.batch_size)
+        return data
+
     def _batches(self, data):
+        from sleap_b200.io.video import FrameFeeder
         imgs = _images_of(data)
+        if isinstance(imgs, FrameFeeder):
+            i = 0
+            for _, batch in imgs.batches():
+                yield i, batch
+                i += len(batch)
+            return
         n = len(imgs)
         for i in range(0, n, self.batch_size):
             batch = np.stack([np.asarray(imgs[j]) for j in range(i, min(n, i + self.batch_size))])
@@ -612,20 +627,28 @@ class Predictor:
 
     def _predict_generator(self, data):
         """:377-420: one predict_on_batch per batch (+ frame indices)."""
-        if hasattr(self.inference_model, "predict_batches"):      # pipelined device loop (upload i+1 || compute i)
-            i0 = 0
-            for ex in self.inference_model.predict_batches(_images_of(data), self.batch_size):
-                n = len(ex["n_valid"])
-                ex["frame_ind"] = np.arange(i0, i0 + n)
-                ex["video_ind"] = np.zeros(n, np.int64)
-                i0 += n
+        from sleap_b200.io.video import FrameFeeder
+        data = self._as_frames(data)
+        feeder = data if isinstance(data, FrameFeeder) else None
+        frame_inds = (lambda a, b: np.asarray(feeder.inds[a:b])) if feeder is not None else (lambda a, b: np.arange(a, b))
+        try:
+            if hasattr(self.inference_model, "predict_batches"):      # pipelined device loop (upload i+1 || compute i)
+                i0 = 0
+                for ex in self.inference_model.predict_batches(_images_of(data), self.batch_size):
+                    n = len(ex["n_valid"])
+                    ex["frame_ind"] = frame_inds(i0, i0 + n)
+                    ex["video_ind"] = np.zeros(n, np.int64)
+                    i0 += n
+                    yield ex
+                return
+            for i0, batch in self._batches(data):
+                ex = self.inference_model.predict_on_batch(batch)
+                ex["frame_ind"] = frame_inds(i0, i0 + len(batch))
+                ex["video_ind"] = np.zeros(len(batch), np.int64)
                 yield ex
-            return
-        for i0, batch in self._batches(data):
-            ex = self.inference_model.predict_on_batch(batch)
-            ex["frame_ind"] = np.arange(i0, i0 + len(batch))
-            ex["video_ind"] = np.zeros(len(batch), np.int64)
-            yield ex
+        finally:
+            if feeder is not None:
+                feeder.close()
 
     def predict(self, data, make_labels: bool = True):
         """:496-531."""

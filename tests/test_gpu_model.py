@@ -393,3 +393,59 @@ def test_pipelined_predict_matches_per_batch():
     assert list(got[2]["frame_ind"]) == [8, 9]
     merged = pred.inference_model.predict(imgs, batch_size=4)
     assert merged["instance_peaks"].shape[0] == 10
+
+
+@pytest.mark.parametrize("variant", [None, "0", "1", "2", "3"])
+@pytest.mark.parametrize("cout,hw,as_float", [(16, (64, 128), False), (16, (38, 136), False), (8, (48, 256), False),
+                                              (32, (64, 128), True), (24, (36, 160), False)])
+def test_first_layer_toeplitz_view(cout, hw, as_float, variant, monkeypatch):
+    """First conv (1 input channel) as a Toeplitz GEMM on the stock tcgen05 kernels (sb_conv_tc.cu,
+    first_view_prepare) vs the torch-CPU fp32 conv on the fp16-rounded operands it consumes, and vs the
+    CUDA-core k_conv_first (SB_DISABLE_FIRST_VIEW=1).  Covers every kernel variant, widths whose group
+    count is not a tile multiple, float frames, and the bottom zero pad (H not a multiple of the stride)."""
+    from ctypes import byref, c_int, c_void_p
+    import torch
+    from sleap_b200 import _lib
+    from sleap_b200.nn import oplist as ol
+    H, W = hw
+    B = 3
+    rng = np.random.default_rng(cout * 100 + H)
+    w0 = (rng.standard_normal((3, 3, 1, cout)) * 0.5).astype(np.float32)
+    b0 = (rng.standard_normal(cout) * 0.1).astype(np.float32)
+    blob = np.concatenate([w0.reshape(-1), b0]).astype(np.float32)
+    recs = [ol.buffer_record(0, 1, 1, 0, 1), ol.buffer_record(1, 1, cout, 0, 0), ol.preprocess_record(0, 1, 1.0, 4),
+            ol.conv_record(0, 0, 1, 1, 0, cout, 3, 1, True, 0, w0.size)]
+    ops = np.ascontiguousarray(np.stack(recs).astype(np.int32))
+    if as_float:
+        imgs = rng.random((B, H, W, 1)).astype(np.float32)
+        xin = imgs
+    else:
+        imgs = rng.integers(0, 256, size=(B, H, W, 1), dtype=np.uint8)
+        xin = imgs.astype(np.float32) * np.float32(1.0 / 255.0)
+    Hn = -(-H // 4) * 4
+
+    def run():
+        h = _lib.Handle(0)
+        mid = c_int(-1)
+        h.call("sb_load_model", _lib.ptr(ops), ops.shape[0], _lib.ptr(blob), int(blob.size), 0, byref(mid))
+        h.call("sb_model_configure", mid.value, B, H, W, 1)
+        out = np.zeros((B, Hn, W, cout), np.float32)
+        ids = np.asarray([1], np.int32)
+        ptrs = (c_void_p * 1)(out.ctypes.data)
+        h.call("sb_model_forward", mid.value, _lib.ptr(imgs), int(not as_float), B, 1, _lib.ptr(ids), ptrs)
+        n = h.gpu_launches()
+        h.close()
+        return out, n
+
+    if variant is not None:
+        monkeypatch.setenv("SB_FORCE_VARIANT", variant)
+    got, _ = run()
+    monkeypatch.setenv("SB_DISABLE_FIRST_VIEW", "1")
+    direct, _ = run()
+    monkeypatch.delenv("SB_DISABLE_FIRST_VIEW")
+    x16 = torch.from_numpy(np.pad(xin, ((0, 0), (0, Hn - H), (0, 0), (0, 0)))).half().float().permute(0, 3, 1, 2)
+    w16 = torch.from_numpy(w0).half().float().permute(3, 2, 0, 1)
+    want = torch.relu(torch.nn.functional.conv2d(x16, w16, torch.from_numpy(b0), padding=1)).permute(0, 2, 3, 1).numpy()
+    scale = max(1.0, float(np.abs(want).max()))
+    assert_allclose(got, want, atol=1.5e-3 * scale, rtol=0)          # fp16 output rounding (2^-11 relative)
+    assert_allclose(got, direct, atol=4e-3 * scale, rtol=0)          # direct kernel keeps fp32 pixels / weights

@@ -36,6 +36,14 @@ def test_bottomup_trained_model(precision):
     assert int(out["n_valid"][0]) == len(want["instance_peaks"][0]) == 2
     assert_allclose(out["instance_peaks"][0, :2], want["instance_peaks"][0], atol=TOL[precision])
     assert_allclose(out["instance_scores"][0, :2], want["instance_scores"][0], atol=2e-2 if precision == 0 else 1e-4)
+    # the same frames through the provider path: Video -> threaded FrameFeeder -> pipelined submit/collect
+    from sleap_b200.io.video import Video
+    rep = np.concatenate([imgs] * 9)
+    via_feeder = pred.predict(Video.from_numpy(rep))
+    assert len(via_feeder) == 9 and [f.frame_idx for f in via_feeder] == list(range(9))
+    for f in via_feeder:
+        assert len(f.instances) == 2
+        assert_allclose(np.concatenate([i.numpy() for i in f.instances]), pts, atol=1e-5)
     hi = BottomUpPredictor.from_trained_models(model_path=rm.model_dir("minimal_instance.bottomup"), min_line_scores=1.1,
                                                precision=precision)
     assert len(hi.predict(imgs)[0].instances) == 0
