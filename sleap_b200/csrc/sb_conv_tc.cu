@@ -28,6 +28,9 @@ namespace {
 
 constexpr int TW = 16, TH = 8;          // output tile (pixels); M = 128
 constexpr int MAX_GROUPS = 3, MAX_TAPS = 3;
+// dynamic shared memory every kernel here is opted in for (cudaFuncAttributeMaxDynamicSharedMemorySize); more than
+// half of the SM's 227 KB, so a launch padded to this size is guaranteed to run one CTA per SM
+constexpr size_t kMaxDynSmem = 210 * 1024;
 
 struct TcTap { int row_off, w_tap; };
 struct TcGroup { int dx, n_taps; TcTap taps[MAX_TAPS]; };
@@ -1109,6 +1112,7 @@ struct SbConvTcPlan {
   __half* view_in = nullptr;
   float* view_bias = nullptr;       // bias replicated over the 8 pixels of a group: [8 * Cout]
   int view_Wg = 0;
+  bool view_enabled = true;         // false: the autotuner measured k_conv_first faster for this shape
 };
 
 static CUtensorMapSwizzle swz_for(int KC) {
@@ -1145,7 +1149,8 @@ void sb_conv_tc_release(SbModel* m) {
 }
 
 bool sb_conv_tc_can(const SbModel* m, int op_index) {
-  return op_index < (int)m->tc_plans.size() && m->tc_plans[op_index] != nullptr;
+  return op_index < (int)m->tc_plans.size() && m->tc_plans[op_index] != nullptr &&
+         (!m->tc_plans[op_index]->view_in || m->tc_plans[op_index]->view_enabled);
 }
 
 // A launch over tensors that are not op-list buffers (the Toeplitz view of the first layer): every
@@ -1226,7 +1231,7 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
       const int by_smem = (int)((227 * 1024) / (L.smem + fa.sharedSizeBytes + 1024));
       const int hw_occ = std::max(1, std::min(std::min(by_regs, by_smem), 32));
       const int tmem_occ = 512 / P.tmem_cols;
-      if (hw_occ > tmem_occ) L.smem = std::max(L.smem, (size_t)(227 * 1024) / tmem_occ - 2048);
+      if (hw_occ > tmem_occ) L.smem = std::max(L.smem, std::min<size_t>(kMaxDynSmem, (size_t)(227 * 1024) / tmem_occ - 2048));
     }
   }
   // persistent variant when the whole filter bank of this launch fits in shared memory
@@ -1282,7 +1287,7 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
         auto cols_for = [&](int nst) { int c = 32; while (c < nst * N) c <<= 1; return c; };
         while (occ * Q.tmem_cols > 512 && Q.n_stages > 2) { Q.n_stages >>= 1; Q.tmem_cols = cols_for(Q.n_stages); }
         if (occ * Q.tmem_cols > 512) { Q.n_stages = 1; Q.tmem_cols = cols_for(1); }        // last resort: single stage
-        if (occ * Q.tmem_cols > 512) { L.smem_p = std::max(L.smem_p, (size_t)(227 * 1024) / (512 / Q.tmem_cols) - 2048); occ = 512 / Q.tmem_cols; }
+        if (occ * Q.tmem_cols > 512) { L.smem_p = std::max(L.smem_p, std::min<size_t>(kMaxDynSmem, (size_t)(227 * 1024) / (512 / Q.tmem_cols) - 2048)); occ = 512 / Q.tmem_cols; }
       }
       L.occ = occ;
       L.has_persist = true;
@@ -1412,7 +1417,7 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
       occ = std::max(1, std::min(std::min(by_regs, by_smem), 16));
       while (occ * Hp.tmem_cols > 512 && Hp.n_stages > 2) { Hp.n_stages >>= 1; Hp.tmem_cols = cols_for(Hp.n_stages); }
       if (occ * Hp.tmem_cols > 512) { Hp.n_stages = 1; Hp.tmem_cols = cols_for(1); }
-      if (occ * Hp.tmem_cols > 512) { HC.smem = std::max(HC.smem, (size_t)(227 * 1024) / (512 / Hp.tmem_cols) - 2048); occ = 512 / Hp.tmem_cols; }
+      if (occ * Hp.tmem_cols > 512) { HC.smem = std::max(HC.smem, std::min<size_t>(kMaxDynSmem, (size_t)(227 * 1024) / (512 / Hp.tmem_cols) - 2048)); occ = 512 / Hp.tmem_cols; }
     }
     HC.occ = occ;
     cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)ib.W, (cuuint64_t)ib.H, (cuuint64_t)m->B};
@@ -1554,7 +1559,8 @@ static int first_view_prepare(sb_handle_s* h, SbModel* m, int oi) {
 }
 
 bool sb_first_view_can(const SbModel* m, int op_index) {
-  return op_index >= 0 && op_index < (int)m->tc_plans.size() && m->tc_plans[op_index] && m->tc_plans[op_index]->view_in;
+  return op_index >= 0 && op_index < (int)m->tc_plans.size() && m->tc_plans[op_index] && m->tc_plans[op_index]->view_in &&
+         m->tc_plans[op_index]->view_enabled;
 }
 
 // frame -> Toeplitz view -> tcgen05 conv (the launch sb_conv_tc_autotune picked)
@@ -1749,6 +1755,7 @@ int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
       while (fscanf(f, "%d %d %d", &oi, &li, &pick) == 3) {
         if (oi < 0 || oi >= (int)m->tc_plans.size() || !m->tc_plans[oi]) continue;
         SbConvTcPlan* plan = m->tc_plans[oi];
+        if (li == -2) { plan->view_enabled = pick != 0; ++applied; continue; }
         if (li < 0) { plan->use_fused = pick != 0 && !plan->fused.empty(); ++applied; continue; }
         if (li >= (int)plan->launches.size()) continue;
         TcLaunch& L = plan->launches[li];
@@ -1774,9 +1781,16 @@ int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
         for (int rep = 0; rep < 3; ++rep) {
           cudaEventRecord(e0, h->stream);
           launch_variant(h, L, m->B, v, h->stream);
+          const cudaError_t le = cudaGetLastError();         // launch-configuration errors: the variant is unusable
           cudaEventRecord(e1, h->stream);
           cudaError_t e = cudaStreamSynchronize(h->stream);
           if (e != cudaSuccess) return sb_fail(h, SB_ERR_CUDA, "autotune launch (variant %d) failed: %s", v, cudaGetErrorString(e));
+          if (le != cudaSuccess) {
+            if (dbg) fprintf(stderr, "[sb_conv_tc] op %zu variant %d cannot launch: %s\n", oi, v, cudaGetErrorString(le));
+            if (v >= 2) { L.n_halo = std::min(L.n_halo, v - 2); } else if (v == 1) { L.has_persist = false; }
+            best[v] = 1e30f;
+            break;
+          }
           float ms = 0.f;
           cudaEventElapsedTime(&ms, e0, e1);
           if (rep > 0) best[v] = std::min(best[v], ms);
@@ -1794,6 +1808,29 @@ int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
         fprintf(stderr, " us -> %d\n", pick);
       }
     }
+  }
+  // first layer: Toeplitz tensor-core form (view kernel + the variant picked above) against k_conv_first
+  for (size_t oi = 0; oi < m->tc_plans.size(); ++oi) {
+    SbConvTcPlan* plan = m->tc_plans[oi];
+    if (!plan || !plan->view_in || !m->frames_dev) continue;
+    float best[2] = {1e30f, 1e30f};
+    for (int f = 0; f < 2; ++f)
+      for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0, h->stream);
+        const int rc = f == 0 ? sb_first_direct_launch(h, m, (int)oi, m->frames_dev, 1, m->B)
+                              : sb_first_view_launch(h, m, (int)oi, m->frames_dev, 1, m->B);
+        if (rc) return rc;
+        cudaEventRecord(e1, h->stream);
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) return sb_fail(h, SB_ERR_CUDA, "autotune launch (first layer, form %d) failed: %s", f, cudaGetErrorString(e));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0) best[f] = std::min(best[f], ms);
+      }
+    plan->view_enabled = best[1] < best[0];
+    if (const char* fv = getenv("SB_FORCE_FIRST_VIEW")) plan->view_enabled = atoi(fv) != 0;
+    if (dbg) fprintf(stderr, "[sb_conv_tc] op %zu first layer: k_conv_first %.1f us, Toeplitz view + tcgen05 %.1f us -> %s\n", oi,
+                     best[0] * 1e3f, best[1] * 1e3f, plan->view_enabled ? "view" : "direct");
   }
   for (size_t oi = 0; oi < m->tc_plans.size(); ++oi) {
     SbConvTcPlan* plan = m->tc_plans[oi];
@@ -1829,6 +1866,7 @@ int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
         if (!plan) continue;
         for (size_t li = 0; li < plan->launches.size(); ++li) fprintf(f, "%zu %zu %d\n", oi, li, plan->launches[li].use_persist);
         if (!plan->fused.empty()) fprintf(f, "%zu -1 %d\n", oi, plan->use_fused ? 1 : 0);
+        if (plan->view_in) fprintf(f, "%zu -2 %d\n", oi, plan->view_enabled ? 1 : 0);
       }
       fclose(f);
     }

@@ -183,6 +183,28 @@ static void launch_first(int co, int B, cudaStream_t s, const TI* img, int Hin, 
   }
 }
 
+// CUDA-core first layer fused with preprocessing (k_conv_first): the fallback of, and the timing rival
+// to, the Toeplitz tensor-core form (sb_first_view_launch).
+int sb_first_direct_launch(sb_handle_s* h, SbModel* m, int op_index, const void* frames_dev, int frames_are_u8, int B) {
+  const SbOp& op = m->ops[op_index];
+  SbBuffer& ob = m->buffers[op.out_buf()];
+  cudaStream_t s = h->stream;
+  const float* Wt = m->weights_dev + op.w_off();
+  const float* bias = op.b_off() >= 0 ? m->weights_dev + op.b_off() : nullptr;
+  const int g = B;
+  const int relu = (op.flags() & SB_OPF_RELU) ? 1 : 0;
+  // rows/cols beyond the resized frame (Hres, Wres) are the bottom/right zero padding
+  if (frames_are_u8) {
+    if (m->Cin == 1) launch_first<unsigned char, 1>(op.out_C(), g, s, (const unsigned char*)frames_dev, m->Hin, m->Win, ob.H, ob.W, (__half*)ob.dev, ob.C, op.out_coff(), Wt, bias, relu, 1);
+    else launch_first<unsigned char, 3>(op.out_C(), g, s, (const unsigned char*)frames_dev, m->Hin, m->Win, ob.H, ob.W, (__half*)ob.dev, ob.C, op.out_coff(), Wt, bias, relu, 1);
+  } else {
+    if (m->Cin == 1) launch_first<float, 1>(op.out_C(), g, s, (const float*)frames_dev, m->Hin, m->Win, ob.H, ob.W, (__half*)ob.dev, ob.C, op.out_coff(), Wt, bias, relu, 0);
+    else launch_first<float, 3>(op.out_C(), g, s, (const float*)frames_dev, m->Hin, m->Win, ob.H, ob.W, (__half*)ob.dev, ob.C, op.out_coff(), Wt, bias, relu, 0);
+  }
+  SB_CHECK_LAUNCH(h);
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 template <typename T>
 static int run_ops_t(sb_handle_s* h, SbModel* m, const void* frames_dev, int frames_are_u8, int B) {
@@ -205,19 +227,8 @@ static int run_ops_t(sb_handle_s* h, SbModel* m, const void* frames_dev, int fra
       continue;
     }
     if ((int)oi == fused_first) {
-      const float* Wt = m->weights_dev + op.w_off();
-      const float* bias = op.b_off() >= 0 ? m->weights_dev + op.b_off() : nullptr;
-      const int g = B;
-      const int relu = (op.flags() & SB_OPF_RELU) ? 1 : 0;
-      // rows/cols beyond the resized frame (Hres, Wres) are the bottom/right zero padding
-      if (frames_are_u8) {
-        if (m->Cin == 1) launch_first<unsigned char, 1>(op.out_C(), g, s, (const unsigned char*)frames_dev, m->Hin, m->Win, ob.H, ob.W, (__half*)ob.dev, ob.C, op.out_coff(), Wt, bias, relu, 1);
-        else launch_first<unsigned char, 3>(op.out_C(), g, s, (const unsigned char*)frames_dev, m->Hin, m->Win, ob.H, ob.W, (__half*)ob.dev, ob.C, op.out_coff(), Wt, bias, relu, 1);
-      } else {
-        if (m->Cin == 1) launch_first<float, 1>(op.out_C(), g, s, (const float*)frames_dev, m->Hin, m->Win, ob.H, ob.W, (__half*)ob.dev, ob.C, op.out_coff(), Wt, bias, relu, 0);
-        else launch_first<float, 3>(op.out_C(), g, s, (const float*)frames_dev, m->Hin, m->Win, ob.H, ob.W, (__half*)ob.dev, ob.C, op.out_coff(), Wt, bias, relu, 0);
-      }
-      SB_CHECK_LAUNCH(h);
+      int rc = sb_first_direct_launch(h, m, (int)oi, frames_dev, frames_are_u8, B);
+      if (rc) return rc;
       continue;
     }
     switch (op.kind()) {

@@ -101,6 +101,7 @@ int sb_first_fusion_op(const SbModel* m, size_t pre_index);
 // first layer as a Toeplitz GEMM on the stock tcgen05 conv kernels (sb_conv_tc.cu)
 bool sb_first_view_can(const SbModel* m, int op_index);
 int sb_first_view_launch(sb_handle_s* h, SbModel* m, int op_index, const void* frames_dev, int frames_are_u8, int B);
+int sb_first_direct_launch(sb_handle_s* h, SbModel* m, int op_index, const void* frames_dev, int frames_are_u8, int B);
 
 // first layer fused with preprocessing on the tensor cores (sb_conv_tc.cu)
 bool sb_conv_first_tc_ok(const SbModel* m, const SbOp& conv);

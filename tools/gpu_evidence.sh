@@ -7,6 +7,8 @@ O=gpurun_out
 mkdir -p $O
 export PYTHONUNBUFFERED=1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/smi.txt 2>&1
+./tools/probes/store_probe > $O/store_probe.txt 2>&1
+timeout 60 python tools/bw_probe.py > $O/bw_probe.txt 2>&1
 echo "== bench"; date +%s
 SB_DEBUG=1 BENCH_VERBOSE=1 SB_TUNE_SAVE=$O/tune.txt timeout 420 python bench.py > $O/bench_1gpu.json 2> $O/bench_1gpu.err
 echo "bench rc=$?"; tail -c 600 $O/bench_1gpu.json
@@ -25,6 +27,9 @@ timeout 120 ncu -i $O/r01_step_full.ncu-rep --page raw --csv > $O/r01_step_full_
 sz=$(stat -c %s $O/r01_step_full.ncu-rep 2>/dev/null || echo 0)
 if [ "$sz" -gt 45000000 ]; then echo "ncu-rep too big ($sz), keeping CSV only"; rm -f $O/r01_step_full.ncu-rep; fi
 ls -la $O
+echo "== other configs"; date +%s
+timeout 300 python tools/bench_configs.py > $O/configs.jsonl 2> $O/configs.err
+echo "configs rc=$?"; cat $O/configs.jsonl
 if [ "${1:-}" != "skip_tests" ]; then
   echo "== pytest gpu"; date +%s
   timeout 600 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1
