@@ -296,6 +296,40 @@ __device__ __forceinline__ void tc_epilogue_cols(const TcParams& P, const float*
   }
 }
 
+// Epilogue of one accumulator (P.N fp32 columns at TMEM address `taddr`), software pipelined: the
+// tcgen05.ld of chunk i+1 is in flight while chunk i is converted and stored, so the ~100-cycle
+// tcgen05.wait::ld is paid once per accumulator instead of once per 16 columns.
+// PIPE = false keeps the plain load-wait-store loop: the 16/32-input-channel kernels run 3-4 CTAs per SM and
+// the 16 extra registers of the pipelined form would cost them a resident CTA (80 -> 96 registers).
+template <int TWC, bool PIPE>
+__device__ __forceinline__ void tc_epilogue_acc(const TcParams& P, const float* __restrict__ s_par, uint32_t taddr, int n0,
+                                                bool valid, size_t pix, int b, int x0, int y0, int q, int lane) {
+  if constexpr (!PIPE) {
+    for (int c0 = 0; c0 < P.N; c0 += 16) {
+      uint32_t r16[16];
+      tc_ld16(taddr + (uint32_t)c0, r16);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      tc_epilogue_cols<TWC>(P, s_par, r16, n0, c0, valid, pix, b, x0, y0, q, lane);
+    }
+    return;
+  }
+  uint32_t ra[16], rb[16];
+  tc_ld16(taddr, ra);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  for (int c0 = 0; c0 < P.N; c0 += 32) {
+    const bool has_b = c0 + 16 < P.N;                  // warp-uniform
+    if (has_b) tc_ld16(taddr + (uint32_t)(c0 + 16), rb);
+    tc_epilogue_cols<TWC>(P, s_par, ra, n0, c0, valid, pix, b, x0, y0, q, lane);
+    if (has_b) {
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const bool has_a = c0 + 32 < P.N;
+      if (has_a) tc_ld16(taddr + (uint32_t)(c0 + 32), ra);
+      tc_epilogue_cols<TWC>(P, s_par, rb, n0, c0 + 16, valid, pix, b, x0, y0, q, lane);
+      if (has_a) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    }
+  }
+}
+
 template <int KSTEPS>
 __global__ void __launch_bounds__(128) k_conv_tc(const __grid_constant__ CUtensorMap mapA,
                                                  const __grid_constant__ CUtensorMap mapB,
@@ -406,12 +440,7 @@ __global__ void __launch_bounds__(128) k_conv_tc(const __grid_constant__ CUtenso
   const bool valid = (iy < P.H) && (ix < P.W);
   const int oy = iy * P.oy_mul + P.oy_add, ox = ix * P.ox_mul + P.ox_add;
   const size_t pix = ((size_t)b * P.out_H + oy) * P.out_W + ox;
-  for (int c0 = 0; c0 < P.N; c0 += 16) {
-    uint32_t r[16];
-    tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    tc_epilogue_cols<16>(P, s_par, r, n0, c0, valid, pix, b, x0, y0, warp, lane);
-  }
+  tc_epilogue_acc<16, KSTEPS == 4>(P, s_par, tmem_base + ((uint32_t)(warp * 32) << 16), n0, valid, pix, b, x0, y0, warp, lane);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) {
@@ -538,12 +567,7 @@ __global__ void __launch_bounds__(192) k_conv_tc_persist(const __grid_constant__
       const int iy = y0 + m / TW, ix = x0 + m % TW;
       const bool valid = (iy < P.H) && (ix < P.W);
       const size_t pix = ((size_t)b * P.out_H + (iy * P.oy_mul + P.oy_add)) * P.out_W + (ix * P.ox_mul + P.ox_add);
-      for (int c0 = 0; c0 < P.N; c0 += 16) {
-        uint32_t r16[16];
-        tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(stage * P.N + c0), r16);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        tc_epilogue_cols<16>(P, s_par, r16, 0, c0, valid, pix, b, x0, y0, q, lane);
-      }
+      tc_epilogue_acc<16, KSTEPS == 4>(P, s_par, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(stage * P.N), 0, valid, pix, b, x0, y0, q, lane);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(tempty + stage));
@@ -720,16 +744,16 @@ __global__ void __launch_bounds__(192) k_conv_tc_halo(const __grid_constant__ CU
       const int iy = y0 + (m >> 3), ix = x0 + (m & 7);
       const bool valid = (iy < P.H) && (ix < P.W);
       const size_t pix = ((size_t)b * P.out_H + (iy * P.oy_mul + P.oy_add)) * P.out_W + (ix * P.ox_mul + P.ox_add);
-      for (int c0 = 0; c0 < P.N; c0 += 16) {
-        uint32_t r16[16];
-        if (P.ablate & 8) {
+      if (P.ablate & 8) {                              // profiling only: epilogue without TMEM loads
+        for (int c0 = 0; c0 < P.N; c0 += 16) {
+          uint32_t r16[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) r16[j] = (uint32_t)(lane + j);
-        } else {
-          tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(stage * P.N + c0), r16);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          tc_epilogue_cols<8>(P, s_par, r16, 0, c0, valid && !(P.ablate & 4), pix, b, x0, y0, q, lane);
         }
-        tc_epilogue_cols<8>(P, s_par, r16, 0, c0, valid && !(P.ablate & 4), pix, b, x0, y0, q, lane);
+      } else {
+        tc_epilogue_acc<8, KSTEPS == 4>(P, s_par, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(stage * P.N), 0, valid && !(P.ablate & 4), pix,
+                           b, x0, y0, q, lane);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -913,16 +937,15 @@ __global__ void __launch_bounds__(320) k_conv_tc_prog(const __grid_constant__ CU
         const bool valid = (iy < P.H) && (ix < P.W);
         const size_t pix = ((size_t)b * P.out_H + (iy * P.oy_mul + ao.oy_add)) * P.out_W + (ix * P.ox_mul + ao.ox_add);
         const uint32_t tcol = (uint32_t)((stage * P.n_acc + s) * P.N);
-        for (int c0 = 0; c0 < P.N; c0 += 16) {
-          uint32_t r16[16];
-          if (P.ablate & 8) {
+        if (P.ablate & 8) {                            // profiling only: epilogue without TMEM loads
+          for (int c0 = 0; c0 < P.N; c0 += 16) {
+            uint32_t r16[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) r16[j] = (uint32_t)(lane + j);
-          } else {
-            tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + tcol + (uint32_t)c0, r16);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tc_epilogue_cols<8>(P, s_par, r16, 0, c0, valid && !(P.ablate & 4), pix, b, xs, ys, q, lane);
           }
-          tc_epilogue_cols<8>(P, s_par, r16, 0, c0, valid && !(P.ablate & 4), pix, b, xs, ys, q, lane);
+        } else {
+          tc_epilogue_acc<8, KSTEPS == 4>(P, s_par, tmem_base + ((uint32_t)(q * 32) << 16) + tcol, 0, valid && !(P.ablate & 4), pix, b, xs, ys, q, lane);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1294,8 +1317,9 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
     }
   }
   L.n_halo = 0;
-  int kHaloShapes[5][3] = {{1, 1, 1}, {2, 1, 2}, {2, 2, 2}, {0, 0, 0}, {0, 0, 0}};   // sub_x, sub_y, epilogue groups
-  int n_shapes = 3;
+  // sub_x, sub_y, epilogue groups; 8x32 (1x2) measured 2-5 % ahead of 16x16 (2x1) on the 64..256-channel layers
+  int kHaloShapes[5][3] = {{1, 1, 1}, {2, 1, 2}, {2, 2, 2}, {1, 2, 2}, {0, 0, 0}};
+  int n_shapes = 4;
   if (const char* e = getenv("SB_HALO_SHAPES")) {      // experiments: "sx,sy,eg;sx,sy,eg;..."
     n_shapes = 0;
     while (*e && n_shapes < 4) {

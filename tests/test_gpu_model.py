@@ -302,7 +302,7 @@ def test_tc_tconv_layers(cin, cout, fused, monkeypatch):
     assert_allclose(got, want, atol=3e-3 * max(1.0, np.abs(want).max()), rtol=3e-3)
 
 
-@pytest.mark.parametrize("variant,fused", [("2", None), ("3", None), ("4", None), ("2", "1")])
+@pytest.mark.parametrize("variant,fused", [("2", None), ("3", None), ("4", None), ("5", None), ("2", "1")])
 def test_tc_forced_variants_unet(variant, fused, monkeypatch):
     """The whole fp16 UNet (transposed-conv phases, fused max-pool, concat-by-slice outputs) with every
     halo variant forced, against the CUDA-core path."""
@@ -326,14 +326,14 @@ def test_tc_forced_variants_unet(variant, fused, monkeypatch):
         assert np.abs(a - b).max() / scale < 3e-3, np.abs(a - b).max() / scale
 
 
-@pytest.mark.parametrize("variant", [None, "0", "1", "2", "3", "4"])
+@pytest.mark.parametrize("variant", [None, "0", "1", "2", "3", "4", "5"])
 @pytest.mark.parametrize("cin,cout,k,hw", [(16, 16, 3, (40, 48)), (32, 32, 3, (40, 48)), (64, 64, 3, (53, 70)),
                                            (128, 128, 3, (40, 48)), (256, 128, 3, (53, 70)), (128, 256, 3, (40, 48)),
                                            (256, 512, 3, (40, 48)), (64, 13, 1, (40, 48)), (128, 24, 1, (40, 48))])
 def test_tc_single_layers(cin, cout, k, hw, variant, monkeypatch):
     """Each swizzle mode / chunk count / N-tile shape of the tensor-core conv on its own, with the
     kernel variant chosen by the autotuner (None) or forced: 0 streaming, 1 weights-resident,
-    2 halo 8x16, 3 / 4 halo super-tiles 16x16 / 16x32 (weights resident or streamed); a forced variant
+    2 halo 8x16, 3 / 4 / 5 halo super-tiles 16x16 / 16x32 / 8x32 (weights resident or streamed); a forced variant
     that does not apply to the layer falls back to the streaming kernel."""
     if variant is not None:
         monkeypatch.setenv("SB_FORCE_VARIANT", variant)
