@@ -1146,7 +1146,10 @@ static bool tc_eligible(const SbModel* m, const SbOp& op) {
   if (getenv("SB_DISABLE_TC")) return false;
   if (op.kind() != SB_OPK_CONV && op.kind() != SB_OPK_TCONV) return false;
   const int Cin = op.in_C();
-  if (!(Cin == 16 || Cin == 32 || Cin % 64 == 0)) return false;
+  // any channel count that keeps 16-byte aligned NHWC rows: K is cut into chunks of 16 / 32 / 64 channels and a
+  // chunk that reaches past C_in is zero-filled by TMA on both operands (activations and weights)
+  if (!(Cin >= 16 && Cin % 8 == 0)) return false;
+  if (getenv("SB_TC_STRICT_CIN") && !(Cin == 16 || Cin == 32 || Cin % 64 == 0)) return false;
   if (op.kind() == SB_OPK_CONV && !((op.k() == 1 || op.k() == 3) && op.stride() == 1)) return false;
   const SbBuffer& ib = m->buffers[op.in_buf()];
   const SbBuffer& ob = m->buffers[op.out_buf()];
@@ -1195,14 +1198,14 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
   const SbBuffer& ob = view ? view->ob : m->buffers[op.out_buf()];
   const int Cin = view ? view->Cin : op.in_C(), Cout = view ? view->Cout : op.out_C();
   const int in_coff = view ? 0 : op.in_coff(), out_coff = view ? 0 : op.out_coff();
-  const int KC = Cin >= 64 ? 64 : Cin;
+  const int KC = Cin > 32 ? 64 : (Cin > 16 ? 32 : 16);
   TcLaunch L;
   memset(&L, 0, sizeof(L));
   TcParams& P = L.P;
   P.H = ib.H; P.W = ib.W;
   P.tiles_x = (ib.W + TW - 1) / TW;
   const int tiles_y = (ib.H + TH - 1) / TH;
-  P.n_chunks = Cin / KC; P.KC = KC;
+  P.n_chunks = (Cin + KC - 1) / KC; P.KC = KC;
   P.n_groups = n_groups;
   for (int g = 0; g < n_groups; ++g) P.groups[g] = groups[g];
   P.dy0 = dy0; P.box_rows = TH + extra_rows;

@@ -329,7 +329,9 @@ def test_tc_forced_variants_unet(variant, fused, monkeypatch):
 @pytest.mark.parametrize("variant", [None, "0", "1", "2", "3", "4", "5"])
 @pytest.mark.parametrize("cin,cout,k,hw", [(16, 16, 3, (40, 48)), (32, 32, 3, (40, 48)), (64, 64, 3, (53, 70)),
                                            (128, 128, 3, (40, 48)), (256, 128, 3, (53, 70)), (128, 256, 3, (40, 48)),
-                                           (256, 512, 3, (40, 48)), (64, 13, 1, (40, 48)), (128, 24, 1, (40, 48))])
+                                           (256, 512, 3, (40, 48)), (64, 13, 1, (40, 48)), (128, 24, 1, (40, 48)),
+                                           (24, 24, 3, (40, 48)), (48, 36, 3, (40, 48)), (96, 48, 3, (53, 70)),
+                                           (192, 96, 3, (40, 48)), (24, 13, 1, (40, 48))])
 def test_tc_single_layers(cin, cout, k, hw, variant, monkeypatch):
     """Each swizzle mode / chunk count / N-tile shape of the tensor-core conv on its own, with the
     kernel variant chosen by the autotuner (None) or forced: 0 streaming, 1 weights-resident,
@@ -366,6 +368,13 @@ def test_tc_single_layers(cin, cout, k, hw, variant, monkeypatch):
     ids = np.asarray([1, 2], np.int32)
     ptrs = (c_void_p * 2)(mids.ctypes.data, outs.ctypes.data)
     h.call("sb_model_forward", mid.value, _lib.ptr(imgs), 0, B, 2, _lib.ptr(ids), ptrs)
+    # the layer must have run on the tensor-core path (kind 1 in the per-op profile), not on the CUDA-core fallback
+    dev = torch.zeros((B, H, W, 1), dtype=torch.uint8, device="cuda")
+    op_ms = np.zeros(16, np.float32); op_kind = np.zeros(16, np.int32); op_fl = np.zeros(16, np.float64)
+    n_ops = c_int(0)
+    h.call("sb_model_profile_ops", mid.value, c_void_p(dev.data_ptr()), B, 16, _lib.ptr(op_ms), _lib.ptr(op_kind), _lib.ptr(op_fl),
+           byref(n_ops))
+    assert op_kind[n_ops.value - 1] == 1, list(op_kind[:n_ops.value])
     # reference from the *device's* fp16 intermediate so only this layer is under test
     x = torch.from_numpy(mids).permute(0, 3, 1, 2)
     w16 = torch.from_numpy(w1.astype(np.float16).astype(np.float32)).permute(3, 2, 0, 1)
