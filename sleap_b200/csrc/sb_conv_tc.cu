@@ -89,6 +89,9 @@ struct TcParams {
   TcProgEntry prog[36];
   TcAccOut acc_out[4];
   int ablate;                  // profiling only (SB_ABLATE): 1 no TMA, 2 no MMA, 4 no stores, 8 no TMEM loads
+  // 1: the common epilogue shape (fp16 NHWC output, no BN affine, C_out a multiple of 16 covering the whole
+  //    N tile, 32-byte aligned channel slices for the output and the fused pool) runs tc_epilogue_cols_fast
+  int epi_mode;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -296,6 +299,87 @@ __device__ __forceinline__ void tc_epilogue_cols(const TcParams& P, const float*
   }
 }
 
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+
+// Specialised form of tc_epilogue_cols for P.epi_mode == 1.  The generic routine re-derives, for every 16
+// columns, facts that are fixed per launch (output dtype, BN, alignment, partial channel tiles): ncu's source
+// view of the 16->16 @1024^2 layer shows ~430 warp instructions per 128-pixel tile and 67 % issue-slot
+// utilisation, i.e. an instruction-issue bound epilogue.  Here the launch-invariant decisions are made on
+// the host, the bias comes from shared memory through ld.shared (the generic path emitted generic LDs), ReLU
+// is a branch-free max against 0 / -inf, and the output / pooled row pointers are computed once per tile.
+template <int TWC, bool POOL>
+__device__ __forceinline__ void tc_epilogue_cols_fast(uint32_t s_bias, const uint32_t (&r)[16], bool valid, __half* po, __half* pp,
+                                                      bool pool_store, float lo, int tw_rt) {
+  __align__(16) __half2 h[8];
+#pragma unroll
+  for (int j4 = 0; j4 < 4; ++j4) {
+    const float4 bb = lds_f4(s_bias + 16u * j4);
+    const float a0 = fmaxf(__uint_as_float(r[4 * j4 + 0]) + bb.x, lo), a1 = fmaxf(__uint_as_float(r[4 * j4 + 1]) + bb.y, lo);
+    const float a2 = fmaxf(__uint_as_float(r[4 * j4 + 2]) + bb.z, lo), a3 = fmaxf(__uint_as_float(r[4 * j4 + 3]) + bb.w, lo);
+    h[2 * j4] = __floats2half2_rn(a0, a1);
+    h[2 * j4 + 1] = __floats2half2_rn(a2, a3);
+  }
+  if (valid) st_global_256(po, h);
+  if (POOL) {
+    const int tw = TWC ? TWC : tw_rt;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint32_t a = *reinterpret_cast<uint32_t*>(&h[j]);
+      uint32_t o = __shfl_xor_sync(0xffffffffu, a, 1);
+      __half2 m2 = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&o));
+      a = *reinterpret_cast<uint32_t*>(&m2);
+      o = __shfl_xor_sync(0xffffffffu, a, tw);
+      h[j] = __hmax2(m2, *reinterpret_cast<__half2*>(&o));
+    }
+    if (pool_store) st_global_256(pp, h);
+  }
+}
+
+template <int TWC, bool PIPE, bool POOL>
+__device__ __forceinline__ void tc_epilogue_acc_fast(const TcParams& P, const float* __restrict__ s_par, uint32_t taddr, int n0, bool valid,
+                                                     size_t pix, int b, int x0, int y0, int q, int lane) {
+  const float lo = P.relu ? 0.f : -INFINITY;
+  const uint32_t sb = smem_u32(s_par);
+  __half* po = reinterpret_cast<__half*>(P.out) + pix * P.out_Ctot + P.out_coff + n0;
+  __half* pp = nullptr;
+  bool pool_store = false;
+  if (POOL) {
+    const int tw = TWC ? TWC : P.tw;
+    const int lr = lane / tw, lc = lane % tw;
+    pool_store = valid && ((lc | lr) & 1) == 0;
+    const int py = (y0 >> 1) + ((q * (32 / tw) + lr) >> 1), px = (x0 >> 1) + (lc >> 1);
+    pp = reinterpret_cast<__half*>(P.pool_out) + (((size_t)b * P.pool_H + py) * P.pool_W + px) * P.pool_Ctot + P.pool_coff + n0;
+  }
+  if constexpr (!PIPE) {
+    for (int c0 = 0; c0 < P.N; c0 += 16) {
+      uint32_t r16[16];
+      tc_ld16(taddr + (uint32_t)c0, r16);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      tc_epilogue_cols_fast<TWC, POOL>(sb + 4u * c0, r16, valid, po + c0, pp + c0, pool_store, lo, P.tw);
+    }
+    return;
+  }
+  uint32_t ra[16], rb[16];
+  tc_ld16(taddr, ra);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  for (int c0 = 0; c0 < P.N; c0 += 32) {
+    const bool has_b = c0 + 16 < P.N;
+    if (has_b) tc_ld16(taddr + (uint32_t)(c0 + 16), rb);
+    tc_epilogue_cols_fast<TWC, POOL>(sb + 4u * c0, ra, valid, po + c0, pp + c0, pool_store, lo, P.tw);
+    if (has_b) {
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const bool has_a = c0 + 32 < P.N;
+      if (has_a) tc_ld16(taddr + (uint32_t)(c0 + 32), ra);
+      tc_epilogue_cols_fast<TWC, POOL>(sb + 4u * (c0 + 16), rb, valid, po + c0 + 16, pp + c0 + 16, pool_store, lo, P.tw);
+      if (has_a) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    }
+  }
+}
+
 // Epilogue of one accumulator (P.N fp32 columns at TMEM address `taddr`), software pipelined: the
 // tcgen05.ld of chunk i+1 is in flight while chunk i is converted and stored, so the ~100-cycle
 // tcgen05.wait::ld is paid once per accumulator instead of once per 16 columns.
@@ -304,6 +388,11 @@ __device__ __forceinline__ void tc_epilogue_cols(const TcParams& P, const float*
 template <int TWC, bool PIPE>
 __device__ __forceinline__ void tc_epilogue_acc(const TcParams& P, const float* __restrict__ s_par, uint32_t taddr, int n0,
                                                 bool valid, size_t pix, int b, int x0, int y0, int q, int lane) {
+  if (P.epi_mode == 1) {                               // launch-uniform
+    if (P.pool_out != nullptr) tc_epilogue_acc_fast<TWC, PIPE, true>(P, s_par, taddr, n0, valid, pix, b, x0, y0, q, lane);
+    else tc_epilogue_acc_fast<TWC, PIPE, false>(P, s_par, taddr, n0, valid, pix, b, x0, y0, q, lane);
+    return;
+  }
   if constexpr (!PIPE) {
     for (int c0 = 0; c0 < P.N; c0 += 16) {
       uint32_t r16[16];
@@ -1233,6 +1322,10 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
     const SbBuffer& pb = m->buffers[op.pool_buf()];
     P.pool_out = pb.dev; P.pool_H = pb.H; P.pool_W = pb.W; P.pool_Ctot = pb.C; P.pool_coff = op.pool_coff();
   }
+  P.epi_mode = 0;
+  if (!getenv("SB_DISABLE_FAST_EPILOGUE") && !ob.f32 && P.bn_scale == nullptr && Cout % 16 == 0 && plan->Cout_pad == Cout &&
+      ob.C % 16 == 0 && out_coff % 16 == 0 && (P.pool_out == nullptr || (P.pool_Ctot % 16 == 0 && P.pool_coff % 16 == 0)))
+    P.epi_mode = 1;
   P.row_bytes = KC * 2;
   P.layout_type = KC == 64 ? 2 : (KC == 32 ? 4 : 6);
   P.a_tx_bytes = P.box_rows * TW * KC * 2;
