@@ -1,0 +1,263 @@
+"""Read-only ``Labels`` for the inference path's caller side: ground-truth / predicted instances from a
+SLEAP ``.slp`` file, and the ``LabelsReader`` provider the predictors accept.
+
+Restates the *data model* the path consumes, not the reference's editing API:
+  sleap/io/format/hdf5.py:70-330     LabelsV1Adaptor.read (tables frames / instances / points / pred_points,
+                                     videos_json, metadata attrs["json"] with skeletons + nodes)
+  sleap/instance.py:51-117           point record dtypes (x, y, visible, complete[, score])
+  sleap/skeleton.py:840-1000         Skeleton.from_dict (jsonpickle graph: nodes by index, links with EdgeType)
+  sleap/nn/data/providers.py:23-300  LabelsReader (keys image, raw_image_size, example_ind, video_ind, frame_ind,
+                                     scale, instances, skeleton_inds, track_inds, n_tracks)
+  sleap/nn/data/instance_centroids.py:12-33, 80-180   InstanceCentroidFinder (bounding-box midpoint or anchor part)
+The HDF5 container is read by the in-tree ``h5lite`` reader.
+"""
+import json
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from sleap_b200.io import h5lite
+from sleap_b200.io.video import Video
+
+
+class Skeleton:
+    def __init__(self, node_names: Sequence[str], edges: Sequence[Sequence[str]], symmetries=(), name="Skeleton-0"):
+        self.node_names = list(node_names)
+        self.edge_names = [tuple(e) for e in edges]
+        self.symmetry_names = [tuple(e) for e in symmetries]
+        self.name = name
+
+    @property
+    def nodes(self):
+        return self.node_names
+
+    @property
+    def edge_inds(self):
+        return [(self.node_names.index(a), self.node_names.index(b)) for a, b in self.edge_names]
+
+    def __len__(self):
+        return len(self.node_names)
+
+    @classmethod
+    def from_dict(cls, sk: dict, global_nodes: List[dict]):
+        """jsonpickle node-link graph: ``nodes[i]["id"]`` indexes the file-level node list; link ``type`` is
+        ``EdgeType(1)`` = BODY or ``EdgeType(2)`` = SYMMETRY, later occurrences are ``{"py/id": k}`` back-references
+        to the k-th distinct object met while decoding (skeleton.py:75-93, jsonpickle unpickler)."""
+        def node_name(ref):
+            if isinstance(ref, dict) and "py/object" in ref:          # inline Node object (older files)
+                return ref.get("py/state", {}).get("py/tuple", [ref.get("name")])[0]
+            if isinstance(ref, dict):
+                ref = ref.get("id", ref.get("py/id"))
+            return global_nodes[int(ref)]["name"] if global_nodes else str(ref)
+
+        names = [node_name(n["id"]) for n in sk["nodes"]]
+        seen_types = []
+        edges, syms = [], []
+        for link in sorted(sk.get("links", []), key=lambda l: l.get("edge_insert_idx", 0)):
+            t = link.get("type", {})
+            if "py/reduce" in t:
+                val = int(t["py/reduce"][1]["py/tuple"][0])
+                seen_types.append(val)
+            elif "py/id" in t:
+                val = seen_types[int(t["py/id"]) - 1] if int(t["py/id"]) - 1 < len(seen_types) else 1
+            else:
+                val = 1
+            src = global_nodes[int(link["source"])]["name"] if global_nodes else str(link["source"])
+            dst = global_nodes[int(link["target"])]["name"] if global_nodes else str(link["target"])
+            (edges if val == 1 else syms).append((src, dst))
+        return cls(names, edges, syms, sk.get("graph", {}).get("name", "Skeleton-0"))
+
+
+class Instance:
+    """Points of one animal: ``numpy()`` -> (n_nodes, 2) float32 with NaN for invisible nodes (instance.py:900-950)."""
+
+    def __init__(self, points: np.ndarray, skeleton: Skeleton, track: int = -1, score: float = float("nan"),
+                 point_scores: Optional[np.ndarray] = None, predicted: bool = False):
+        self.points = np.asarray(points, np.float32)
+        self.skeleton = skeleton
+        self.track = track
+        self.score = score
+        self.point_scores = point_scores
+        self.predicted = predicted
+
+    def numpy(self):
+        return self.points
+
+    @property
+    def n_visible_points(self):
+        return int(np.sum(~np.isnan(self.points[:, 0])))
+
+
+class LabeledFrame:
+    def __init__(self, video: int, frame_idx: int, instances: List[Instance]):
+        self.video, self.frame_idx, self.instances = video, frame_idx, instances
+
+    def __len__(self):
+        return len(self.instances)
+
+    def __getitem__(self, i):
+        return self.instances[i]
+
+    @property
+    def user_instances(self):
+        return [i for i in self.instances if not i.predicted]
+
+    @property
+    def predicted_instances(self):
+        return [i for i in self.instances if i.predicted]
+
+
+class Labels:
+    def __init__(self, labeled_frames: List[LabeledFrame], videos: List[dict], skeletons: List[Skeleton], tracks=()):
+        self.labeled_frames = labeled_frames
+        self.video_specs = videos
+        self.skeletons = skeletons
+        self.tracks = list(tracks)
+        self._videos = {}
+
+    def __len__(self):
+        return len(self.labeled_frames)
+
+    def __getitem__(self, i):
+        return self.labeled_frames[i]
+
+    @property
+    def skeleton(self):
+        return self.skeletons[0]
+
+    @property
+    def videos(self):
+        return [self.video(i) for i in range(len(self.video_specs))]
+
+    def video(self, ind: int, search: Sequence[str] = ()) -> Video:
+        """Opens the video of ``videos_json[ind]`` (path as stored, then relative to each ``search`` directory by
+        basename, like ``Labels.load_file(video_search=...)``, sleap/io/dataset.py:1990-2050)."""
+        if ind in self._videos:
+            return self._videos[ind]
+        be = self.video_specs[ind].get("backend", {})
+        fn = be.get("filename", "")
+        cands = [fn] + [os.path.join(d, os.path.basename(fn)) for d in search]
+        for c in cands:
+            if c and os.path.exists(c):
+                self._videos[ind] = Video.from_filename(c, grayscale=be.get("grayscale"), bgr=be.get("bgr", True))
+                return self._videos[ind]
+        raise FileNotFoundError(f"video {fn!r} not found (searched {list(search)})")
+
+    def set_video(self, ind: int, video: Video):
+        self._videos[ind] = video
+
+    @classmethod
+    def load_file(cls, filename: str, video_search: Sequence[str] = ()):
+        if not str(filename).endswith((".slp", ".h5", ".hdf5")):
+            raise ValueError("only the HDF5 .slp labels format is read here")
+        f = h5lite.File(filename)
+        meta = f["metadata"].attrs["json"]
+        meta = json.loads(meta.decode() if isinstance(meta, (bytes, np.bytes_)) else meta)
+        gnodes = meta.get("nodes", [])
+        skeletons = [Skeleton.from_dict(s, gnodes) for s in meta.get("skeletons", [])]
+        vj = f["videos_json"].read() if "videos_json" in f else []
+        videos = [json.loads(v.decode() if isinstance(v, (bytes, np.bytes_)) else v) for v in np.atleast_1d(vj)] if len(vj) else []
+        frames, inst = f["frames"].read(), f["instances"].read()
+        pts, ppts = f["points"].read(), f["pred_points"].read()
+        lfs = []
+        for fr in frames:
+            ins = []
+            for i in range(int(fr["instance_id_start"]), int(fr["instance_id_end"])):
+                row = inst[i]
+                sk = skeletons[int(row["skeleton"])] if skeletons else None
+                predicted = int(row["instance_type"]) == 1            # 0 = user Instance, 1 = PredictedInstance
+                table = ppts if predicted else pts
+                p = table[int(row["point_id_start"]):int(row["point_id_end"])]
+                xy = np.stack([p["x"], p["y"]], -1).astype(np.float32)
+                xy[p["visible"] == 0] = np.nan
+                ins.append(Instance(xy, sk, int(row["track"]), float(row["score"]),
+                                    p["score"].astype(np.float32) if predicted else None, predicted))
+            lfs.append(LabeledFrame(int(fr["video"]), int(fr["frame_idx"]), ins))
+        lab = cls(lfs, videos, skeletons, meta.get("tracks", []))
+        lab._search = list(video_search)
+        return lab
+
+
+def find_points_bbox_midpoint(points: np.ndarray) -> np.ndarray:
+    """instance_centroids.py:12-33: NaN-ignoring bounding-box midpoint over the node axis."""
+    lo = np.min(np.where(np.isnan(points), np.inf, points), axis=-2)
+    hi = np.max(np.where(np.isnan(points), -np.inf, points), axis=-2)
+    return ((hi + lo) * np.float32(0.5)).astype(np.float32)
+
+
+def find_instance_centroids(instances: np.ndarray, anchor_ind: Optional[int] = None) -> np.ndarray:
+    """instance_centroids.py:52-77 ``find_instance_centroids``: the anchor node where it is visible, else the
+    bounding-box midpoint of the visible nodes."""
+    instances = np.asarray(instances, np.float32)
+    mid = find_points_bbox_midpoint(instances)
+    if anchor_ind is None:
+        return mid
+    anchors = instances[:, anchor_ind, :]
+    ok = ~np.isnan(anchors).any(axis=-1, keepdims=True)
+    return np.where(ok, anchors, mid).astype(np.float32)
+
+
+class LabelsReader:
+    """Provider over ``Labels`` (providers.py:23-300): examples carry the frame and its instances; with
+    ``center_on_part`` set (or ``with_centroids=True``) also ``centroids`` (InstanceCentroidFinder,
+    instance_centroids.py:80-180), which the ground-truth stand-in layers of the top-down model consume."""
+
+    def __init__(self, labels: Labels, example_indices: Optional[Sequence[int]] = None, user_instances_only: bool = False,
+                 with_centroids: bool = False, center_on_part: Optional[str] = None, video_search: Sequence[str] = ()):
+        self.labels = labels
+        self.example_indices = example_indices
+        self.user_instances_only = user_instances_only
+        self.with_centroids = with_centroids or center_on_part is not None
+        self.center_on_part = center_on_part
+        self.video_search = list(video_search) or list(getattr(labels, "_search", []))
+
+    @classmethod
+    def from_user_instances(cls, labels: Labels, **kw):
+        return cls(labels, user_instances_only=True, **kw)
+
+    @classmethod
+    def from_filename(cls, filename: str, **kw):
+        return cls(Labels.load_file(filename), **kw)
+
+    @property
+    def output_keys(self):
+        keys = ["image", "raw_image_size", "example_ind", "video_ind", "frame_ind", "scale", "instances", "skeleton_inds",
+                "track_inds", "n_tracks"]
+        return keys + (["centroids"] if self.with_centroids else [])
+
+    def indices(self):
+        if self.example_indices is None:
+            return list(range(len(self.labels)))
+        return [int(i) for i in self.example_indices]
+
+    def __len__(self):
+        return len(self.indices())
+
+    @property
+    def videos(self):
+        return self.labels.videos
+
+    def example(self, ind: int) -> dict:
+        lf = self.labels[ind]
+        video = self.labels.video(lf.video, self.video_search)
+        img = video.get_frame(lf.frame_idx)
+        insts = lf.user_instances if self.user_instances_only else lf.instances
+        n_nodes = len(self.labels.skeleton) if self.labels.skeletons else (insts[0].points.shape[0] if insts else 0)
+        pts = np.stack([i.numpy() for i in insts]) if insts else np.zeros((0, n_nodes, 2), np.float32)
+        ex = {"image": img, "raw_image_size": np.asarray(img.shape, np.int32), "example_ind": np.int64(ind),
+              "video_ind": np.int32(lf.video), "frame_ind": np.int64(lf.frame_idx), "scale": np.ones(2, np.float32),
+              "instances": pts.astype(np.float32), "skeleton_inds": np.zeros(len(insts), np.int32),
+              "track_inds": np.asarray([i.track for i in insts], np.int32), "n_tracks": np.int32(len(self.labels.tracks))}
+        if self.with_centroids:
+            anchor = None
+            if self.center_on_part is not None:
+                anchor = self.labels.skeleton.node_names.index(self.center_on_part)
+            ex["centroids"] = find_instance_centroids(pts, anchor) if len(pts) else np.zeros((0, 2), np.float32)
+        return ex
+
+    def __iter__(self):
+        for i in self.indices():
+            yield self.example(i)
+
+    make_dataset = __iter__

@@ -298,6 +298,70 @@ class FindInstancePeaks(SingleInstanceInferenceLayer):
         return out
 
 
+class CentroidCropGroundTruth:
+    """sleap/nn/inference.py:694-809: stands in for a centroid model -- crops of ``crop_size`` around the
+    ground-truth centroids of a labels example (``example_gt["centroids"]``: one (n, 2) array per sample, made by
+    ``LabelsReader(with_centroids=True)`` = InstanceCentroidFinder).  The crop itself is the device kernel."""
+
+    def __init__(self, crop_size: int, input_scale: float = 1.0, handle=None):
+        self.crop_size = crop_size
+        self.input_scale = input_scale
+        self.handle = handle
+
+    def call(self, example_gt):
+        from sleap_b200 import _lib
+        full_imgs = np.ascontiguousarray(example_gt["image"])
+        if self.input_scale != 1.0:
+            raise NotImplementedError("CentroidCropGroundTruth with input_scale != 1 (resized full images) is not built yet")
+        cents = [f32(c).reshape(-1, 2) for c in example_gt["centroids"]]
+        B, H, W, C = full_imgs.shape
+        sinds = np.concatenate([np.full(len(c), s, np.int32) for s, c in enumerate(cents)]) if cents else np.zeros(0, np.int32)
+        pts = np.concatenate(cents) if cents else np.zeros((0, 2), np.float32)
+        k = len(pts)
+        crop_offsets = (pts - np.float32(self.crop_size / 2)).astype(np.float32)          # :777
+        crops = np.zeros((k, self.crop_size, self.crop_size, C), full_imgs.dtype)
+        if k > 0:
+            h = self.handle or _lib.default_handle()
+            h.call("sb_crop_centered", ptr(full_imgs), int(full_imgs.dtype == np.uint8), B, H, W, C, ptr(f32(pts)), ptr(i32(sinds)), k,
+                   self.crop_size, self.crop_size, ptr(crops))
+        return dict(crops=crops, crop_offsets=crop_offsets, crop_sample_inds=sinds, samples=B, centroids=cents,
+                    centroid_vals=[np.ones(len(c), np.float32) for c in cents])
+
+
+class FindInstancePeaksGroundTruth:
+    """sleap/nn/inference.py:812-893: stands in for a centered-instance model -- every centroid gets the
+    ground-truth instance whose nearest node is closest to it (``example_gt["instances"]``: one (n, nodes, 2)
+    array per sample); peak values are 1."""
+
+    def call(self, example_gt, crop_output):
+        peaks, vals = [], []
+        for inst, cent in zip(example_gt["instances"], crop_output["centroids"]):
+            inst, cent = f32(inst), f32(cent).reshape(-1, 2)
+            n_nodes = inst.shape[1] if inst.ndim == 3 else 0
+            rows = []
+            if len(inst) and len(cent):
+                import warnings
+                with np.errstate(invalid="ignore"), warnings.catch_warnings():
+                    warnings.simplefilter("ignore", RuntimeWarning)
+                    d = np.sqrt(((inst[None] - cent[:, None, None, :]) ** 2).sum(-1))      # (n_centroids, n_insts, n_nodes)
+                    # reduce_min over nodes (:860): Eigen's scalar min keeps the accumulator when the new value is NaN,
+                    # so invisible nodes are skipped and only an all-NaN instance yields NaN
+                    # (tests/nn/test_inference.py:168-209 "GT instances have NaNs")
+                    d = np.nanmin(d, axis=-1)
+                for c in range(len(cent)):
+                    if np.all(np.isnan(d[c])):
+                        continue                                                           # :866-868 all-NaN rows are dropped
+                    best = 0                                                               # tf.argmin: first index; NaN never wins a "<"
+                    for j in range(1, d.shape[1]):
+                        if d[c, j] < d[c, best]:
+                            best = j
+                    rows.append(inst[best])
+            peaks.append(np.stack(rows) if rows else np.zeros((0, n_nodes, 2), np.float32))
+            vals.append(np.ones(peaks[-1].shape[:2], np.float32))
+        return dict(centroids=crop_output["centroids"], centroid_vals=crop_output["centroid_vals"], instance_peaks=peaks,
+                    instance_peak_vals=vals)
+
+
 class TopDownInferenceModel(InferenceModel):
     """sleap/nn/inference.py:2246-2311."""
 
@@ -306,10 +370,17 @@ class TopDownInferenceModel(InferenceModel):
         self.instance_peaks = instance_peaks
 
     def call(self, example):
+        if isinstance(example, np.ndarray):
+            example = dict(image=example)
         crop_out = self.centroid_crop.call(example)
-        peaks_out = self.instance_peaks.call(crop_out)
-        n_nodes = peaks_out["instance_peaks"][0].shape[1] if peaks_out["instance_peaks"] and peaks_out["instance_peaks"][0].ndim == 3 else \
-            next(h["channels"] for h in self.instance_peaks.keras_model.spec["heads"] if h["name"] == self.instance_peaks.HEAD)
+        if isinstance(self.instance_peaks, FindInstancePeaksGroundTruth):                 # :2300-2304
+            peaks_out = self.instance_peaks.call(example, crop_out)
+        else:
+            peaks_out = self.instance_peaks.call(crop_out)
+        if isinstance(self.instance_peaks, FindInstancePeaksGroundTruth):
+            n_nodes = max([p.shape[1] for p in peaks_out["instance_peaks"] if p.ndim == 3] + [0])
+        else:
+            n_nodes = next(h["channels"] for h in self.instance_peaks.keras_model.spec["heads"] if h["name"] == self.instance_peaks.HEAD)
         ip, nv = _ragged_to_dense(peaks_out["instance_peaks"], (n_nodes, 2))
         iv, _ = _ragged_to_dense(peaks_out["instance_peak_vals"], (n_nodes,))
         ce, _ = _ragged_to_dense(peaks_out["centroids"], (2,))
@@ -611,6 +682,18 @@ class Predictor:
             return FrameFeeder(data, batch_size=self.batch_size)
         return data
 
+    def _label_examples(self, reader):
+        """Batches of labels examples (make_pipeline with a LabelsReader, :329-371): stacked frames plus the
+        per-sample ground-truth ``instances`` / ``centroids`` the stand-in layers read."""
+        idx = reader.indices()
+        for i in range(0, len(idx), self.batch_size):
+            exs = [reader.example(j) for j in idx[i:i + self.batch_size]]
+            batch = {"image": np.stack([e["image"] for e in exs]), "instances": [e["instances"] for e in exs],
+                     "frame_ind": np.asarray([e["frame_ind"] for e in exs]), "video_ind": np.asarray([e["video_ind"] for e in exs])}
+            if "centroids" in exs[0]:
+                batch["centroids"] = [e["centroids"] for e in exs]
+            yield batch
+
     def _batches(self, data):
         from sleap_b200.io.video import FrameFeeder
         imgs = _images_of(data)
@@ -627,7 +710,17 @@ class Predictor:
 
     def _predict_generator(self, data):
         """:377-420: one predict_on_batch per batch (+ frame indices)."""
+        from sleap_b200.io.labels import Labels, LabelsReader
         from sleap_b200.io.video import FrameFeeder
+        if isinstance(data, Labels):
+            data = LabelsReader(data, with_centroids=True, center_on_part=getattr(self, "anchor_part", None))
+        if isinstance(data, LabelsReader):
+            for batch in self._label_examples(data):
+                use_gt = getattr(self, "uses_ground_truth", False)
+                ex = self.inference_model.predict_on_batch(batch if use_gt else batch["image"])
+                ex["frame_ind"], ex["video_ind"] = batch["frame_ind"], batch["video_ind"]
+                yield ex
+            return
         data = self._as_frames(data)
         feeder = data if isinstance(data, FrameFeeder) else None
         frame_inds = (lambda a, b: np.asarray(feeder.inds[a:b])) if feeder is not None else (lambda a, b: np.arange(a, b))
@@ -745,10 +838,10 @@ class TopDownPredictor(Predictor):
     def __init__(self, centroid_model=None, confmap_model=None, crop_size=160, peak_threshold=0.2,
                  integral_refinement=True, integral_patch_size=5, batch_size=4, max_instances=None):
         super().__init__(batch_size)
-        if centroid_model is None or confmap_model is None:
-            raise ValueError("This build needs both a centroid and a centered-instance model "
-                             "(ground-truth stand-in layers are out of scope).")
+        if centroid_model is None and confmap_model is None:
+            raise ValueError("Either the centroid or topdown confidence map model must be provided.")   # :2479
         self.centroid_model, self.confmap_model = centroid_model, confmap_model
+        self.anchor_part = None          # instance_cropping.center_on_part of the model config (ground-truth centroids)
         self.crop_size = crop_size
         self.peak_threshold = peak_threshold
         self.integral_refinement = integral_refinement
@@ -760,12 +853,27 @@ class TopDownPredictor(Predictor):
         """:2373-2433."""
         ref = "integral" if self.integral_refinement else "local"
         cm, im = self.centroid_model, self.confmap_model
-        cc = CentroidCrop(keras_model=cm, crop_size=self.crop_size, input_scale=cm.input_scale,
-                          pad_to_stride=cm.cm.max_stride, peak_threshold=self.peak_threshold, refinement=ref,
-                          integral_patch_size=self.integral_patch_size, max_instances=self.max_instances)
-        fp = FindInstancePeaks(keras_model=im, input_scale=im.input_scale, peak_threshold=self.peak_threshold,
-                               refinement=ref, integral_patch_size=self.integral_patch_size)
+        if cm is None:                                   # ground-truth centroids stand in for the centroid model
+            cc = CentroidCropGroundTruth(crop_size=self.crop_size, handle=im.handle)
+        else:
+            cc = CentroidCrop(keras_model=cm, crop_size=self.crop_size if im is not None else 1, input_scale=cm.input_scale,
+                              pad_to_stride=cm.cm.max_stride, peak_threshold=self.peak_threshold, refinement=ref,
+                              integral_patch_size=self.integral_patch_size, max_instances=self.max_instances,
+                              return_crops=im is not None)
+        if im is None:                                   # ground-truth instances stand in for the instance model
+            fp = FindInstancePeaksGroundTruth()
+        else:
+            fp = FindInstancePeaks(keras_model=im, input_scale=im.input_scale, peak_threshold=self.peak_threshold,
+                                   refinement=ref, integral_patch_size=self.integral_patch_size)
+            if cm is None:
+                cc.input_scale = im.input_scale          # :2414-2415
+            else:
+                cc.precrop_resize = im.input_scale       # :2416-2419 (anything but 1 raises NotImplementedError in CentroidCrop)
         self.inference_model = TopDownInferenceModel(cc, fp)
+
+    @property
+    def uses_ground_truth(self):
+        return self.centroid_model is None or self.confmap_model is None
 
     @classmethod
     def from_trained_models(cls, centroid_model_path=None, confmap_model_path=None, batch_size=4, peak_threshold=0.2,
@@ -775,12 +883,18 @@ class TopDownPredictor(Predictor):
         centroid_cfg, confmap_cfg = centroid_model_path, confmap_model_path
         if centroid_cfg is None and confmap_cfg is None:
             raise ValueError("Either the centroid or topdown confidence map model must be provided.")  # :2479
-        if centroid_cfg is None or confmap_cfg is None:
-            raise ValueError("This build needs both a centroid and a centered-instance model.")
-        _, _, cmodel = cls._load(centroid_cfg, precision, handle)
-        icfg, _, imodel = cls._load(confmap_cfg, precision, handle)
-        crop = icfg["data"]["instance_cropping"]["crop_size"]
-        return cls(cmodel, imodel, crop, peak_threshold, integral_refinement, integral_patch_size, batch_size, max_instances)
+        cmodel = imodel = None
+        crop, anchor = 1, None
+        if centroid_cfg is not None:
+            ccfg, _, cmodel = cls._load(centroid_cfg, precision, handle)
+            anchor = ccfg["data"]["instance_cropping"].get("center_on_part")
+        if confmap_cfg is not None:
+            icfg, _, imodel = cls._load(confmap_cfg, precision, handle)
+            crop = icfg["data"]["instance_cropping"]["crop_size"]
+            anchor = icfg["data"]["instance_cropping"].get("center_on_part") if anchor is None else anchor
+        obj = cls(cmodel, imodel, crop, peak_threshold, integral_refinement, integral_patch_size, batch_size, max_instances)
+        obj.anchor_part = anchor
+        return obj
 
 
 class BottomUpPredictor(Predictor):

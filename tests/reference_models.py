@@ -29,3 +29,13 @@ def load_fixture_model(name):
 def frames(name):
     z = np.load(os.path.join(GOLDEN, f"frames_{name}.npz"))
     return z["images"], z["points_gt"]
+
+
+def labels_minimal_instance():
+    """The reference's ``min_labels`` fixture (tests/fixtures/datasets.py:52-54): 1 frame, 2 instances, with the video
+    replaced by the committed frame."""
+    from sleap_b200.io.labels import Labels
+    from sleap_b200.io.video import Video
+    lab = Labels.load_file(os.path.join(GOLDEN, "labels", "minimal_instance.slp"))
+    lab.set_video(0, Video.from_numpy(frames("minimal_instance")[0]))
+    return lab

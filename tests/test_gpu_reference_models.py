@@ -90,3 +90,35 @@ def test_single_instance_trained_model(precision):
     assert all(np.isfinite(f.instances[0].numpy()).all() for f in lo)
     hi = Predictor.from_model_paths([d], precision=precision, peak_threshold=1.5).predict(imgs)
     assert all(len(f.instances) == 0 for f in hi)
+
+
+@pytest.mark.parametrize("precision", [1, 0])
+def test_topdown_single_model_modes(precision):
+    """test_topdown_predictor_centroid (:638-656) and test_topdown_predictor_centered_instance (:728-757): a top-down
+    predictor built from ONE model, the other stage replaced by its ground-truth stand-in layer, fed the labels."""
+    from sleap_b200.nn.inference import TopDownPredictor
+    labels = rm.labels_minimal_instance()
+    gt = np.concatenate([i.numpy() for i in labels[0].instances])
+    # centroid model only: FindInstancePeaksGroundTruth hands back the labelled instance nearest to each centroid
+    pred = TopDownPredictor.from_trained_models(centroid_model_path=rm.model_dir("minimal_instance.centroid"), precision=precision)
+    frames = pred.predict(labels)
+    assert len(frames) == 1 and len(frames[0].instances) == 2
+    _matched(gt, np.concatenate([i.numpy() for i in frames[0].instances]), 1.5)
+    for k in (1, 2, 3):                                                    # :659-671
+        p = TopDownPredictor.from_trained_models(centroid_model_path=rm.model_dir("minimal_instance.centroid"), precision=precision,
+                                                 max_instances=k)
+        assert len(p.predict(labels)[0].instances) == min(k, 2)
+    hi = TopDownPredictor.from_trained_models(centroid_model_path=rm.model_dir("minimal_instance.centroid"), precision=precision,
+                                              peak_threshold=1.5)
+    assert len(hi.predict(labels)[0].instances) == 0                       # :674-683
+    # centered-instance model only: crops at the ground-truth centroids (CentroidCropGroundTruth)
+    pred = TopDownPredictor.from_trained_models(confmap_model_path=rm.model_dir("minimal_instance.centered_instance"), precision=precision)
+    assert pred.crop_size == 96
+    frames = pred.predict(labels)
+    assert len(frames) == 1 and len(frames[0].instances) == 2
+    _matched(gt, np.concatenate([i.numpy() for i in frames[0].instances]), 1.5)
+    hi = TopDownPredictor.from_trained_models(confmap_model_path=rm.model_dir("minimal_instance.centered_instance"), precision=precision,
+                                              peak_threshold=1.5)
+    assert len(hi.predict(labels)[0].instances) == 0                       # :760-769
+    with pytest.raises(ValueError):
+        TopDownPredictor.from_trained_models()
