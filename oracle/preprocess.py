@@ -45,6 +45,8 @@ def resize_image(image, scale):
     H, W = image.shape[-3], image.shape[-2]
     new_w = int(F32(W) * F32(scale))
     new_h = int(F32(H) * F32(scale))
+    if image.ndim == 3:                      # the reference accepts a single (H, W, C) image as well
+        return resize_image(image[None], scale)[0]
     out = resize_bilinear_half_pixel(image.astype(F32), new_h, new_w)
     if image.dtype == np.uint8:
         return np.trunc(out).astype(np.uint8)
