@@ -1,4 +1,4 @@
-"""Read-only ``Labels`` for the inference path's caller side: ground-truth / predicted instances from a
+"""``Labels`` for the inference path's caller side: ground-truth / predicted instances from a
 SLEAP ``.slp`` file, and the ``LabelsReader`` provider the predictors accept.
 
 Restates the *data model* the path consumes, not the reference's editing API:
@@ -147,6 +147,11 @@ class Labels:
     def set_video(self, ind: int, video: Video):
         self._videos[ind] = video
 
+    def save_file(self, filename: str):
+        save_file(self, filename)
+
+    save = save_file
+
     @classmethod
     def load_file(cls, filename: str, video_search: Sequence[str] = ()):
         if not str(filename).endswith((".slp", ".h5", ".hdf5")):
@@ -177,6 +182,104 @@ class Labels:
         lab = cls(lfs, videos, skeletons, meta.get("tracks", []))
         lab._search = list(video_search)
         return lab
+
+
+# Table dtypes of the .slp container (sleap/instance.py:51-58, 115-117; sleap/io/format/hdf5.py:390-420)
+FRAME_DTYPE = np.dtype([("frame_id", "u8"), ("video", "u4"), ("frame_idx", "u8"), ("instance_id_start", "u8"), ("instance_id_end", "u8")])
+INSTANCE_DTYPE = np.dtype([("instance_id", "i8"), ("instance_type", "u1"), ("frame_id", "u8"), ("skeleton", "u4"), ("track", "i4"),
+                           ("from_predicted", "i8"), ("score", "f4"), ("point_id_start", "u8"), ("point_id_end", "u8"),
+                           ("tracking_score", "f4")])
+POINT_DTYPE = np.dtype([("x", "f8"), ("y", "f8"), ("visible", "?"), ("complete", "?")])
+PRED_POINT_DTYPE = np.dtype([("x", "f8"), ("y", "f8"), ("visible", "?"), ("complete", "?"), ("score", "f8")])
+
+
+def skeleton_to_dict(sk: Skeleton, node_index: dict) -> dict:
+    """Inverse of ``Skeleton.from_dict``: the jsonpickle node-link form ``Skeleton.to_dict`` writes (skeleton.py:880-960):
+    the first EdgeType of each kind is spelled out (``py/reduce``), later ones are ``py/id`` back-references."""
+    seen = {}
+    links = []
+
+    def etype(val):
+        if val not in seen:
+            seen[val] = len(seen) + 1
+            return {"py/reduce": [{"py/type": "sleap.skeleton.EdgeType"}, {"py/tuple": [val]}]}
+        return {"py/id": seen[val]}
+
+    for i, (a, b) in enumerate(sk.edge_names):
+        links.append({"edge_insert_idx": i, "key": 0, "source": node_index[a], "target": node_index[b], "type": etype(1)})
+    for a, b in sk.symmetry_names:
+        links.append({"key": 0, "source": node_index[a], "target": node_index[b], "type": etype(2)})
+    return {"directed": True, "graph": {"name": sk.name, "num_edges_inserted": len(sk.edge_names)}, "links": links, "multigraph": True,
+            "nodes": [{"id": node_index[n]} for n in sk.node_names]}
+
+
+def save_file(labels: "Labels", filename: str):
+    """Writes the ``.slp`` (HDF5) container ``LabelsV1Adaptor.write`` produces (sleap/io/format/hdf5.py:332-575,
+    format 1.2): ``metadata`` group (attrs ``format_id``, ``json``), ``videos_json`` / ``tracks_json`` /
+    ``suggestions_json`` and the ``frames`` / ``instances`` / ``points`` / ``pred_points`` tables; predicted instances
+    carry per-point scores and an instance score.  Written with the in-tree ``h5write`` (no h5py)."""
+    from sleap_b200.io import h5write
+    sk_list = labels.skeletons
+    node_names = []
+    for sk in sk_list:
+        for n in sk.node_names:
+            if n not in node_names:
+                node_names.append(n)
+    node_index = {n: i for i, n in enumerate(node_names)}
+    meta = {"version": "2.0.0", "skeletons": [skeleton_to_dict(sk, node_index) for sk in sk_list],
+            "nodes": [{"name": n, "weight": 1.0} for n in node_names], "videos": [], "tracks": list(labels.tracks), "suggestions": [],
+            "negative_anchors": {}, "provenance": {"writer": "sleap_b200"}}
+    frames = np.zeros(len(labels.labeled_frames), FRAME_DTYPE)
+    n_inst = sum(len(lf.instances) for lf in labels.labeled_frames)
+    inst = np.zeros(n_inst, INSTANCE_DTYPE)
+    pts, ppts = [], []
+    ii = 0
+    for fi, lf in enumerate(labels.labeled_frames):
+        frames[fi] = (fi, lf.video, lf.frame_idx, ii, ii + len(lf.instances))
+        for ins in lf.instances:
+            xy = np.asarray(ins.numpy(), np.float64)
+            vis = ~np.isnan(xy[:, 0])
+            table = ppts if ins.predicted else pts
+            start = sum(len(t) for t in table)
+            if ins.predicted:
+                sc = np.asarray(ins.point_scores if ins.point_scores is not None else np.zeros(len(xy)), np.float64)
+                rec = np.zeros(len(xy), PRED_POINT_DTYPE)
+                rec["score"] = np.where(vis, sc, 0.0)
+            else:
+                rec = np.zeros(len(xy), POINT_DTYPE)
+            rec["x"], rec["y"], rec["visible"], rec["complete"] = xy[:, 0], xy[:, 1], vis, False if ins.predicted else vis
+            table.append(rec)
+            sk_ind = sk_list.index(ins.skeleton) if ins.skeleton in sk_list else 0
+            inst[ii] = (ii, 1 if ins.predicted else 0, fi, sk_ind, ins.track, -1, ins.score if ins.predicted else np.nan, start,
+                        start + len(xy), 0.0)
+            ii += 1
+    videos = [json.dumps(v, separators=(",", ":")).encode() for v in labels.video_specs]
+
+    def strings(rows):
+        return np.asarray(rows, dtype=f"S{max(len(r) for r in rows)}") if rows else np.zeros(0, np.float64)
+
+    with h5write.File(filename) as f:
+        g = f.create_group("metadata")
+        g.attrs["format_id"] = np.float64(1.2)
+        g.attrs["json"] = json.dumps(meta, separators=(",", ":"))
+        f.create_dataset("videos_json", strings(videos))
+        f.create_dataset("tracks_json", strings([json.dumps(t).encode() for t in labels.tracks]))
+        f.create_dataset("suggestions_json", np.zeros(0, np.float64))
+        f.create_dataset("frames", frames)
+        f.create_dataset("instances", inst)
+        f.create_dataset("points", np.concatenate(pts) if pts else np.zeros(0, POINT_DTYPE))
+        f.create_dataset("pred_points", np.concatenate(ppts) if ppts else np.zeros(0, PRED_POINT_DTYPE))
+
+
+def labels_from_predictions(frames, skeleton: Skeleton, video_spec: Optional[dict] = None, video_filename: str = "") -> "Labels":
+    """``Predictor.predict(..., make_labels=True)`` output (``LabeledFrame`` / ``PredictedInstance`` of
+    sleap_b200.nn.inference) -> ``Labels`` that ``save_file`` can write (sleap/nn/inference.py:3230-3343)."""
+    spec = video_spec or {"backend": {"filename": video_filename, "grayscale": True, "bgr": True, "dataset": "", "input_format": ""}}
+    lfs = []
+    for fr in frames:
+        ins = [Instance(i.numpy(), skeleton, -1, float(i.score), np.asarray(i.point_confidences, np.float32), True) for i in fr.instances]
+        lfs.append(LabeledFrame(int(fr.video) if isinstance(fr.video, (int, np.integer)) else 0, int(fr.frame_idx), ins))
+    return Labels(lfs, [spec], [skeleton])
 
 
 def find_points_bbox_midpoint(points: np.ndarray) -> np.ndarray:

@@ -750,6 +750,21 @@ class Predictor:
             return self._make_labeled_frames_from_generator(gen, data)
         return list(gen)
 
+    def skeleton(self):
+        """Skeleton of the loaded model(s): node names (+ edges for bottom-up models), as the reference takes them
+        from the training config (:1547-1560, :2562-2580, :3230-3240)."""
+        from sleap_b200.io.labels import Skeleton
+        for m in (getattr(self, "bottomup_model", None), getattr(self, "confmap_model", None), getattr(self, "centroid_model", None)):
+            if m is not None and m.spec.get("part_names"):
+                return Skeleton(m.spec["part_names"], m.spec.get("edges") or [])
+        raise ValueError("the loaded model carries no part names")
+
+    def to_labels(self, frames, video_filename: str = "", video_spec=None):
+        """``predict(..., make_labels=True)`` output -> ``sleap_b200.io.labels.Labels`` (``.save("out.slp")`` writes the
+        reference's HDF5 labels container, sleap/io/format/hdf5.py:332-575)."""
+        from sleap_b200.io.labels import labels_from_predictions
+        return labels_from_predictions(frames, self.skeleton(), video_spec, video_filename)
+
     def _make_labeled_frames_from_generator(self, generator, data):
         """:3230-3343 pattern: a consumer thread builds the objects while the batch loop runs."""
         q: "queue.Queue" = queue.Queue()
