@@ -343,18 +343,25 @@ def run_ours(args):
     big_np = big.numpy()
     for i in range(min(args.warmup, 3)):
         pred.predict(big_np[:2 * B], make_labels=False)
-    barrier()
-    t0 = time.perf_counter()
-    outs = pred.predict(big_np, make_labels=False)
-    if world > 1:
-        recs = torch.cat([parallel.pack_records(*[torch.from_numpy(np.ascontiguousarray(
-            np.pad(o[k], [(0, 0), (0, I - o[k].shape[1])] + [(0, 0)] * (o[k].ndim - 2), constant_values=np.nan)))
-            for k in ("instance_peaks", "instance_peak_vals", "instance_scores")] + [torch.from_numpy(o["n_valid"].astype(np.int32))])
-            for o in outs]).cuda()
-        with torch.cuda.stream(stream):
-            parallel.all_gather_records(recs)
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    def e2e_once():
+        barrier()
+        t0 = time.perf_counter()
+        outs = pred.predict(big_np, make_labels=False)
+        if world > 1:
+            recs = torch.cat([parallel.pack_records(*[torch.from_numpy(np.ascontiguousarray(
+                np.pad(o[k], [(0, 0), (0, I - o[k].shape[1])] + [(0, 0)] * (o[k].ndim - 2), constant_values=np.nan)))
+                for k in ("instance_peaks", "instance_peak_vals", "instance_scores")] + [torch.from_numpy(o["n_valid"].astype(np.int32))])
+                for o in outs]).cuda()
+            with torch.cuda.stream(stream):
+                parallel.all_gather_records(recs)
+        barrier()
+        return time.perf_counter() - t0, outs
+
+    # the K-step end-to-end pass is run three times and the median reported: a single pass of ~40 ms is at the
+    # mercy of one host scheduling hiccup (observed spread 5.0-6.0 k frames/s between otherwise identical runs)
+    runs = [e2e_once() for _ in range(3)]
+    e2e_s = sorted(r[0] for r in runs)[1]
+    outs = runs[-1][1]
     assert sum(len(o["n_valid"]) for o in outs) == args.steps * B
     d2h = B * (I * C * 2 + I * C + I + 2) * 4
     te = torch.tensor([e2e_s], device="cuda")
@@ -420,7 +427,8 @@ def run_ours(args):
                        "heads_calibrated_to_peaks_per_channel": TARGET_PEAKS_PER_CHANNEL},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * H * W, "d2h_bytes_per_step": d2h,
-                    "api": "BottomUpPredictor.predict(pinned uint8 frame stack, make_labels=False), double-buffered batches"},
+                    "api": "BottomUpPredictor.predict(pinned uint8 frame stack, make_labels=False), double-buffered batches",
+                    "timing": "median of 3 passes of K steps (wall clock, barrier on both sides)"},
             "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line))
     if world > 1:
