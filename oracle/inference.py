@@ -76,11 +76,14 @@ def centroid_crop_layer(imgs, spec, weights, crop_size, in_ch=1, input_scale=1.0
 
 
 def find_instance_peaks_layer(crops, crop_offsets, spec, weights, in_ch=1, input_scale=1.0, pad_stride=1,
-                              peak_threshold=0.2, refinement="integral", integral_patch_size=5):
+                              peak_threshold=0.2, refinement="integral", integral_patch_size=5, resize_input_image=True):
+    """``resize_input_image=False`` is how the top-down predictor builds the layer (:2405-2413): the crops were cut
+    from full frames already resized by ``input_scale`` (CentroidCrop.precrop_resize / CentroidCropGroundTruth.input_scale),
+    so only the coordinate fix-ups use ``input_scale``."""
     if len(crops) == 0:
         n = next(x["channels"] for x in spec["heads"] if x["name"] == "CenteredInstanceConfmapsHead")
         return np.zeros((0, n, 2), F), np.zeros((0, n), F)
-    h = _heads(spec, weights, crops, in_ch, input_scale, pad_stride)
+    h = _heads(spec, weights, crops, in_ch, input_scale, pad_stride, resize_img=resize_input_image)
     cms, offs = h["CenteredInstanceConfmapsHead"], h.get("OffsetRefinementHead")
     stride = spec["heads"][0]["output_stride"]
     if offs is None:
@@ -126,6 +129,20 @@ def bottomup_layer(imgs, spec, weights, in_ch=1, input_scale=1.0, pad_stride=1, 
         inst = [(x / F(input_scale) + F(0.5)).astype(F) for x in inst]                # :2980-2984
     return {"instance_peaks": inst, "instance_peak_vals": ivals, "instance_scores": iscores, "confmaps": cms,
             "part_affinity_fields": pafs}
+
+
+def centroid_crop_ground_truth_layer(imgs, centroids, crop_size, input_scale=1.0):
+    """sleap/nn/inference.py:743-809 CentroidCropGroundTruth.call: ``centroids`` = one (n, 2) array per sample."""
+    full = imgs
+    cents = [np.asarray(c, F).reshape(-1, 2) for c in centroids]
+    if input_scale != 1.0:
+        full = opre.resize_image(full, input_scale)                                   # :768-770
+        cents = [(c * F(input_scale)).astype(F) for c in cents]
+    sinds = np.concatenate([np.full(len(c), s, np.int32) for s, c in enumerate(cents)])
+    pts = np.concatenate(cents)
+    crop_offsets = (pts - F(crop_size / 2)).astype(F)
+    crops = tf_ops.crop_bboxes(full, tf_ops.make_centered_bboxes(pts, crop_size, crop_size), sinds)
+    return {"crops": crops, "crop_offsets": crop_offsets, "crop_sample_inds": sinds, "centroids": cents}
 
 
 def match_points(points_gt, points_pr):

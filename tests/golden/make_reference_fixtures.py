@@ -38,6 +38,7 @@ MODELS = {
     "minimal_instance.centroid": "minimal_instance.UNet.centroid",
     "minimal_instance.centered_instance": "minimal_instance.UNet.centered_instance",
     "minimal_robot.single_instance": "minimal_robot.UNet.single_instance",
+    "minimal_instance.centered_instance_with_scaling": "minimal_instance.UNet.centered_instance_with_scaling",
 }
 
 

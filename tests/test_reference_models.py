@@ -108,3 +108,20 @@ def test_oracle_single_instance_on_trained_model():
     assert not np.isnan(lo["instance_peaks"]).any()
     hi = oinf.single_instance_layer(imgs, spec, w, in_ch, pre["input_scaling"], 4, peak_threshold=1.5)
     assert np.isnan(hi["instance_peaks"]).all()
+
+
+def test_oracle_centered_instance_with_scaling():
+    """test_topdown_predictor_centered_instance_with_scaling (:708-729): instance model trained at input_scaling 0.5,
+    crops of 56 px cut at the ground-truth centroids from the half-size frame (CentroidCropGroundTruth.input_scale),
+    FindInstancePeaks with resize_input_image=False; matched points within 1.5 px of the labels."""
+    cfg, spec, w, in_ch = rm.load_fixture_model("minimal_instance.centered_instance_with_scaling")
+    imgs, gt = rm.frames("minimal_instance")
+    scale = cfg["data"]["preprocessing"]["input_scaling"]
+    crop = cfg["data"]["instance_cropping"]["crop_size"]
+    assert scale == 0.5 and crop == 56
+    cent_gt = np.stack([(g.min(0) + g.max(0)) * 0.5 for g in gt[0]]).astype(np.float32)
+    cc = oinf.centroid_crop_ground_truth_layer(imgs, [cent_gt], crop, input_scale=scale)
+    assert cc["crops"].shape == (2, 56, 56, 1) and cc["crops"].dtype == np.uint8
+    pts, vals = oinf.find_instance_peaks_layer(cc["crops"], cc["crop_offsets"], spec, w, in_ch, input_scale=scale, pad_stride=1,
+                                               resize_input_image=False)
+    _matched(gt[0].reshape(-1, 2), pts.reshape(-1, 2), 1.5)
