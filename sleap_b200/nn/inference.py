@@ -206,6 +206,7 @@ class CentroidCrop(InferenceLayer):
         self.precrop_resize = precrop_resize
         self.max_peaks_per_sample = max_peaks_per_sample
         self._cfg_key = None
+        self._resizer = None
 
     def call(self, inputs):
         full_imgs = self._prep(_images_of(inputs))
@@ -229,8 +230,13 @@ class CentroidCrop(InferenceLayer):
                       ptr(vals), ptr(sinds), byref(n), ptr(flags))
         k = n.value
         pts, vals, sinds = pts[:k].copy(), vals[:k].copy(), sinds[:k].copy()
-        if self.precrop_resize != 1.0:
-            raise NotImplementedError("precrop_resize != 1 (centered-instance input_scaling) is not built yet")
+        if self.precrop_resize != 1.0:                       # :1836-1841 (the returned centroids stay in the resized frame, as in the reference)
+            if self._resizer is None:
+                from sleap_b200.nn.model import FrameResizer
+                self._resizer = FrameResizer(m.handle)
+            full_imgs = self._resizer(full_imgs, self.precrop_resize)
+            H, W = full_imgs.shape[1:3]
+            pts = (pts * np.float32(self.precrop_resize)).astype(np.float32)
         if k > 0 and self.max_instances is not None:
             keep = []
             for s in range(B):   # tf.math.top_k: descending score, ties keep the lower index (:1879-1894)
@@ -307,13 +313,18 @@ class CentroidCropGroundTruth:
         self.crop_size = crop_size
         self.input_scale = input_scale
         self.handle = handle
+        self._resizer = None
 
     def call(self, example_gt):
         from sleap_b200 import _lib
         full_imgs = np.ascontiguousarray(example_gt["image"])
-        if self.input_scale != 1.0:
-            raise NotImplementedError("CentroidCropGroundTruth with input_scale != 1 (resized full images) is not built yet")
         cents = [f32(c).reshape(-1, 2) for c in example_gt["centroids"]]
+        if self.input_scale != 1.0:                          # :768-770: resized frames, centroids scaled with them
+            if self._resizer is None:
+                from sleap_b200.nn.model import FrameResizer
+                self._resizer = FrameResizer(self.handle or _lib.default_handle())
+            full_imgs = self._resizer(full_imgs, self.input_scale)
+            cents = [(c * np.float32(self.input_scale)).astype(np.float32) for c in cents]
         B, H, W, C = full_imgs.shape
         sinds = np.concatenate([np.full(len(c), s, np.int32) for s, c in enumerate(cents)]) if cents else np.zeros(0, np.int32)
         pts = np.concatenate(cents) if cents else np.zeros((0, 2), np.float32)
@@ -658,7 +669,10 @@ class Predictor:
             return json.load(f), os.path.dirname(cfg_path)
 
     @staticmethod
-    def _load(cfg_and_dir, precision, handle):
+    def _load(cfg_and_dir, precision, handle, resize_in_graph=True):
+        """``resize_in_graph=False``: the network graph gets no resize op (top-down instance models: their crops come
+        from frames that were already resized, FindInstancePeaks(resize_input_image=False), :2405-2413); the
+        configured ``input_scaling`` is still returned through ``model.input_scale``."""
         if isinstance(cfg_and_dir, (str, os.PathLike)):        # the reference passes model paths here
             cfg_and_dir = Predictor._read_config(os.fspath(cfg_and_dir))
         cfg, d = cfg_and_dir
@@ -669,9 +683,10 @@ class Predictor:
         # ``is_grayscale``); here it is the C_in of the first convolution's kernel.
         first = arch.compile_model(spec, 1).layers[0]["name"]
         in_ch = int(np.asarray(weights[first]["kernel"]).shape[2])
-        model = DeviceModel(spec, weights, input_channels=in_ch,
-                            input_scale=pre.get("input_scaling", 1.0) or 1.0, pad_to_stride=pre.get("pad_to_stride"),
-                            precision=precision, handle=handle)
+        scale = float(pre.get("input_scaling", 1.0) or 1.0)
+        model = DeviceModel(spec, weights, input_channels=in_ch, input_scale=scale if resize_in_graph else 1.0,
+                            pad_to_stride=pre.get("pad_to_stride"), precision=precision, handle=handle)
+        model.config_input_scale = scale
         return cfg, spec, model
 
     def _as_frames(self, data):
@@ -878,12 +893,15 @@ class TopDownPredictor(Predictor):
         if im is None:                                   # ground-truth instances stand in for the instance model
             fp = FindInstancePeaksGroundTruth()
         else:
-            fp = FindInstancePeaks(keras_model=im, input_scale=im.input_scale, peak_threshold=self.peak_threshold,
+            iscale = float(getattr(im, "config_input_scale", im.input_scale))
+            if im.input_scale != 1.0:
+                raise ValueError("top-down instance models must be built without a resize op (resize_input_image=False)")
+            fp = FindInstancePeaks(keras_model=im, input_scale=iscale, peak_threshold=self.peak_threshold,
                                    refinement=ref, integral_patch_size=self.integral_patch_size)
             if cm is None:
-                cc.input_scale = im.input_scale          # :2414-2415
+                cc.input_scale = iscale                  # :2414-2415
             else:
-                cc.precrop_resize = im.input_scale       # :2416-2419 (anything but 1 raises NotImplementedError in CentroidCrop)
+                cc.precrop_resize = iscale               # :2416-2419
         self.inference_model = TopDownInferenceModel(cc, fp)
 
     @property
@@ -904,7 +922,7 @@ class TopDownPredictor(Predictor):
             ccfg, _, cmodel = cls._load(centroid_cfg, precision, handle)
             anchor = ccfg["data"]["instance_cropping"].get("center_on_part")
         if confmap_cfg is not None:
-            icfg, _, imodel = cls._load(confmap_cfg, precision, handle)
+            icfg, _, imodel = cls._load(confmap_cfg, precision, handle, resize_in_graph=False)
             crop = icfg["data"]["instance_cropping"]["crop_size"]
             anchor = icfg["data"]["instance_cropping"].get("center_on_part") if anchor is None else anchor
         obj = cls(cmodel, imodel, crop, peak_threshold, integral_refinement, integral_patch_size, batch_size, max_instances)

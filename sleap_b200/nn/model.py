@@ -72,6 +72,41 @@ class DeviceModel:
         return outs
 
 
+class FrameResizer:
+    """``sleap.nn.data.resizing.resize_image`` (resizing.py:71-106) for uint8 / float frame stacks on the device:
+    a one-op model (PREPROCESS with ``input_scale``) runs the bilinear half-pixel resize kernel the networks use;
+    integer frames are fed as float 0..255 and cast back by truncation, like ``tf.cast(tf.image.resize(...), dtype)``."""
+
+    def __init__(self, handle=None):
+        self.handle = handle or _lib.default_handle()
+        self._models = {}
+
+    def __call__(self, imgs: np.ndarray, scale: float) -> np.ndarray:
+        from sleap_b200.nn import oplist as ol
+        imgs = np.ascontiguousarray(imgs)
+        B, H, W, C = imgs.shape
+        key = (H, W, C, float(scale))
+        if key not in self._models:
+            ops = np.ascontiguousarray(np.stack([ol.buffer_record(0, 1, C, 1, 1), ol.preprocess_record(0, C, float(scale), 1)]).astype(np.int32))
+            blob = np.zeros(1, np.float32)
+            mid = c_int(-1)
+            self.handle.call("sb_load_model", ptr(ops), ops.shape[0], ptr(blob), 1, int(PRECISION_FP32), ctypes.byref(mid))
+            self._models[key] = [mid.value, 0]
+        mid, cap = self._models[key]
+        if cap < B:
+            self.handle.call("sb_model_configure", mid, B, H, W, C)
+            self._models[key][1] = B
+        nh, nw = int(np.float32(H) * np.float32(scale)), int(np.float32(W) * np.float32(scale))
+        out = np.zeros((B, nh, nw, C), np.float32)
+        ids = np.asarray([0], np.int32)
+        ptrs = (c_void_p * 1)(out.ctypes.data)
+        src = np.ascontiguousarray(imgs, dtype=np.float32)                  # 0..255 stays 0..255 (no ensure_float scaling)
+        self.handle.call("sb_model_forward", mid, ptr(src), 0, B, 1, ptr(ids), ptrs)
+        if imgs.dtype == np.uint8:
+            return np.clip(np.trunc(out), 0, 255).astype(np.uint8)
+        return out.astype(imgs.dtype)
+
+
 def load_weights_npz(path):
     """``{layer}/{param}`` arrays exported from a Keras ``best_model.h5``."""
     z = np.load(path)
