@@ -14,14 +14,11 @@ Sources (all data files, no reference code is imported or copied):
 
 Outputs:
   models/<name>/training_config.json   reduced to the keys the inference path reads
-  models/<name>/best_model.npz         float32 weights {layer/param} (optimizer state dropped);
-  models/minimal_robot.single_instance/best_model.h5   verbatim Keras HDF5 (exercises the HDF5 reader)
-  labels/*.slp                         verbatim label files (exercise the HDF5 reader: compound types)
+  models/<name>/best_model.npz         float32 weights {layer/param} read out of best_model.h5 (optimizer state dropped)
   frames_minimal_instance.npz, frames_robot.npz   uint8 frames + ground-truth points (frame, instance, node, xy)
 """
 import json
 import os
-import shutil
 import sys
 
 import cv2
@@ -84,24 +81,20 @@ def main():
         os.makedirs(dst, exist_ok=True)
         cfg = json.load(open(os.path.join(src, "training_config.json")))
         json.dump(reduced_config(cfg), open(os.path.join(dst, "training_config.json"), "w"), indent=1, sort_keys=True)
-        if short.startswith("minimal_robot"):
-            shutil.copyfile(os.path.join(src, "best_model.h5"), os.path.join(dst, "best_model.h5"))
-        else:
-            w = load_weights_h5(os.path.join(src, "best_model.h5"))
-            save_weights_npz(os.path.join(dst, "best_model.npz"), w)
-    os.makedirs(os.path.join(HERE, "labels"), exist_ok=True)
-    for n in ("minimal_instance.slp", "small_robot_minimal.slp"):
-        shutil.copyfile(os.path.join(REF, "slp_hdf5", n), os.path.join(HERE, "labels", n))
+        w = load_weights_h5(os.path.join(src, "best_model.h5"))
+        save_weights_npz(os.path.join(dst, "best_model.npz"), w)
 
     pts, idxs, vid = gt_points(os.path.join(REF, "slp_hdf5", "minimal_instance.slp"))
     frames = read_frames(os.path.join(REF, "json_format_v1", "centered_pair_low_quality.mp4"), idxs, True)
-    np.savez_compressed(os.path.join(HERE, "frames_minimal_instance.npz"), images=frames, points_gt=pts, frame_idx=np.asarray(idxs))
+    np.savez_compressed(os.path.join(HERE, "frames_minimal_instance.npz"), images=frames, points_gt=pts, frame_idx=np.asarray(idxs),
+                        video_json=np.asarray(json.dumps(vid)))
     print("minimal_instance", frames.shape, pts.shape, idxs, vid)
 
     pts, idxs, vid = gt_points(os.path.join(REF, "slp_hdf5", "small_robot_minimal.slp"))
     gray = bool(vid["backend"].get("grayscale"))
     frames = read_frames(os.path.join(REF, "videos", "small_robot.mp4"), idxs, gray)
-    np.savez_compressed(os.path.join(HERE, "frames_robot.npz"), images=frames, points_gt=pts, frame_idx=np.asarray(idxs))
+    np.savez_compressed(os.path.join(HERE, "frames_robot.npz"), images=frames, points_gt=pts, frame_idx=np.asarray(idxs),
+                        video_json=np.asarray(json.dumps(vid)))
     print("robot", frames.shape, pts.shape, idxs, vid)
 
 

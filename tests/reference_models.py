@@ -31,11 +31,23 @@ def frames(name):
     return z["images"], z["points_gt"]
 
 
+REF_DATA = "/root/reference/tests/data"       # present in the build container only; never read by the -m gpu tests
+
+
+def ref_path(*parts):
+    """A data file of the reference checkout, or None where the checkout does not exist (GPU box)."""
+    p = os.path.join(REF_DATA, *parts)
+    return p if os.path.exists(p) else None
+
+
 def labels_minimal_instance():
-    """The reference's ``min_labels`` fixture (tests/fixtures/datasets.py:52-54): 1 frame, 2 instances, with the video
-    replaced by the committed frame."""
-    from sleap_b200.io.labels import Labels
+    """The reference's ``min_labels`` fixture (tests/fixtures/datasets.py:52-54: 1 frame, 2 instances, skeleton A-B),
+    rebuilt from the committed frame + ground-truth points."""
+    from sleap_b200.io.labels import Instance, LabeledFrame, Labels, Skeleton
     from sleap_b200.io.video import Video
-    lab = Labels.load_file(os.path.join(GOLDEN, "labels", "minimal_instance.slp"))
-    lab.set_video(0, Video.from_numpy(frames("minimal_instance")[0]))
+    z = np.load(os.path.join(GOLDEN, "frames_minimal_instance.npz"))
+    sk = Skeleton(["A", "B"], [("A", "B")])
+    lfs = [LabeledFrame(0, int(fi), [Instance(p, sk) for p in pts]) for fi, pts in zip(z["frame_idx"], z["points_gt"])]
+    lab = Labels(lfs, [json.loads(str(z["video_json"]))], [sk])
+    lab.set_video(0, Video.from_numpy(z["images"]))
     return lab

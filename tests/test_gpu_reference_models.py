@@ -76,7 +76,7 @@ def test_topdown_trained_models(precision):
 def test_single_instance_trained_model(precision):
     from sleap_b200.nn.inference import Predictor, SingleInstancePredictor
     imgs, gt = rm.frames("robot")
-    d = rm.model_dir("minimal_robot.single_instance")          # best_model.h5 read by the in-tree HDF5 reader
+    d = rm.model_dir("minimal_robot.single_instance")
     pred = Predictor.from_model_paths([d], precision=precision)
     assert isinstance(pred, SingleInstancePredictor)
     frames = pred.predict(imgs)

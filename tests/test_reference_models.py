@@ -19,25 +19,35 @@ def _matched(points_gt, points_pr, atol):
     assert_allclose(points_gt[i1], points_pr[i2], atol=atol)
 
 
+REF_H5 = rm.ref_path("models", "minimal_robot.UNet.single_instance", "best_model.h5")
+REF_SLP = rm.ref_path("slp_hdf5", "minimal_instance.slp")
+needs_reference = pytest.mark.skipif(REF_H5 is None or REF_SLP is None, reason="reads h5py-written files of the reference checkout")
+
+
+@needs_reference
 def test_h5_reader_keras_weights_match_npz_export():
+    """The in-tree HDF5 reader on a Keras ``best_model.h5`` written by h5py: every array equals the committed ``.npz``."""
     from sleap_b200.io import h5lite
-    from sleap_b200.nn.model import load_weights_h5
-    d = rm.model_dir("minimal_robot.single_instance")
-    f = h5lite.File(os.path.join(d, "best_model.h5"))
+    from sleap_b200.nn.model import load_weights_h5, load_weights_npz
+    f = h5lite.File(REF_H5)
     assert set(f.keys()) >= {"model_weights"}
     assert f.attrs["backend"] == "tensorflow"
-    w = load_weights_h5(os.path.join(d, "best_model.h5"))
+    w = load_weights_h5(REF_H5)
     assert w["stack0_enc0_conv0"]["kernel"].shape[:2] == (3, 3)
     assert "SingleInstanceConfmapsHead" in w
     n = sum(a.size for p in w.values() for a in p.values())
     from sleap_b200.nn import architectures as A
-    _, spec, _, in_ch = rm.load_fixture_model("minimal_robot.single_instance")
+    _, spec, wz, in_ch = rm.load_fixture_model("minimal_robot.single_instance")
     assert n == A.count_params(A.compile_model(spec, in_ch))
+    for layer, params in w.items():
+        for k, a in params.items():
+            np.testing.assert_array_equal(a, wz[layer][k])
 
 
+@needs_reference
 def test_h5_reader_slp_tables():
     from sleap_b200.io import h5lite
-    f = h5lite.File(os.path.join(rm.GOLDEN, "labels", "minimal_instance.slp"))
+    f = h5lite.File(REF_SLP)
     assert sorted(f.keys()) == ["frames", "instances", "metadata", "points", "pred_points", "suggestions_json",
                                 "tracks_json", "videos_json"]
     pts = f["points"].read()
@@ -48,6 +58,11 @@ def test_h5_reader_slp_tables():
     assert f["metadata"].attrs["format_id"] == 1.1 or str(f["metadata"].attrs["format_id"]).startswith("1.1")
     _, gt = rm.frames("minimal_instance")
     assert_allclose(gt[0, 0, 0], [pts["x"][0], pts["y"][0]], rtol=1e-6)
+    big = rm.ref_path("slp_hdf5", "dance.mp4.labels.slp")                       # chunked tables, 450 frames of predictions
+    if big:
+        g = h5lite.File(big)
+        assert g["frames"].read().shape == (450,) and g["pred_points"].read().shape == (7650,)
+        assert g["instances"].read().dtype.names[-1] == "tracking_score"
 
 
 def test_oracle_bottomup_on_trained_model():
