@@ -13,7 +13,7 @@ Sources (all data files, no reference code is imported or copied):
   tests/data/json_format_v1/centered_pair_low_quality.mp4 frame 0, tests/data/videos/small_robot.mp4 frames
 
 Outputs:
-  models/<name>/training_config.json   reduced to the keys the inference path reads
+  models/<name>/fixture_config.json    the training config reduced to the keys the inference path reads
   models/<name>/best_model.npz         float32 weights {layer/param} read out of best_model.h5 (optimizer state dropped)
   frames_minimal_instance.npz, frames_robot.npz   uint8 frames + ground-truth points (frame, instance, node, xy)
 """
@@ -80,7 +80,7 @@ def main():
         src, dst = os.path.join(REF, "models", name), os.path.join(HERE, "models", short)
         os.makedirs(dst, exist_ok=True)
         cfg = json.load(open(os.path.join(src, "training_config.json")))
-        json.dump(reduced_config(cfg), open(os.path.join(dst, "training_config.json"), "w"), indent=1, sort_keys=True)
+        json.dump(reduced_config(cfg), open(os.path.join(dst, "fixture_config.json"), "w"), indent=1, sort_keys=True)
         w = load_weights_h5(os.path.join(src, "best_model.h5"))
         save_weights_npz(os.path.join(dst, "best_model.npz"), w)
 

@@ -11,17 +11,19 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def model_dir(name):
-    return os.path.join(GOLDEN, "models", name)
+    """Path handed to the predictors: the config JSON inside the fixture model folder (the reference accepts "a model
+    folder or a training job JSON file inside a model folder", inference.py:3166-3168)."""
+    return os.path.join(GOLDEN, "models", name, "fixture_config.json")
 
 
 def load_fixture_model(name):
     """-> (cfg, spec, weights, in_ch)"""
     from sleap_b200.nn import architectures as A
     from sleap_b200.nn.model import load_weights
-    d = model_dir(name)
-    cfg = json.load(open(os.path.join(d, "training_config.json")))
+    cfg_path = model_dir(name)
+    cfg = json.load(open(cfg_path))
     spec = A.spec_from_config(cfg["model"])
-    w = load_weights(d)
+    w = load_weights(os.path.dirname(cfg_path))
     first = next(v for k, v in w.items() if k.endswith("enc0_conv0"))
     return cfg, spec, w, int(first["kernel"].shape[2])
 
