@@ -1,0 +1,79 @@
+"""C4 at BASELINE.json's full size (bottom-up UNet+PAF, 1024x1024x1, 8 frames per GPU): properties that do not need a
+CPU run of the whole batch -- order independence, duplicate-frame equality, the fused device pipeline against the
+oracle post-processing of the device's own maps, and one frame of the fp16 network against the fp32 oracle network.
+
+Written after the round's last GPU slot (the same flows run in bench.py / smoke() at this size); xfail(strict=False)
+until a device run has confirmed it, so that it cannot mask the rest of the suite."""
+import os
+import sys
+
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose, assert_array_equal
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first device run pending (see module docstring)")]
+
+
+def _c4():
+    import bench
+    from sleap_b200.nn import architectures as A
+    from sleap_b200.nn.inference import BottomUpPredictor
+    from sleap_b200.nn.model import DeviceModel
+    spec = bench.c4_spec()
+    weights = A.make_synthetic_weights(A.compile_model(spec, 1), bench.SEED)
+    calib = bench.make_frames(2, 500)
+    m0 = DeviceModel(spec, weights, input_channels=1, precision=0)
+    cms0, pafs0 = m0.forward(calib)
+    weights = bench.calibrate_heads(weights, cms0, pafs0, len(calib))
+    model = DeviceModel(spec, weights, input_channels=1, precision=0)
+    pred = BottomUpPredictor(model, bench.NODES, bench.EDGES, peak_threshold=0.2, batch_size=8, max_peaks_per_sample=1024,
+                             max_node_peaks=32, max_instances_per_frame=32)
+    return bench, spec, weights, model, pred
+
+
+def _per_frame(out):
+    rows = []
+    for b in range(len(out["n_valid"])):
+        n = int(out["n_valid"][b])
+        rows.append((n, np.nan_to_num(out["instance_peaks"][b, :n], nan=-1.0), np.nan_to_num(out["instance_scores"][b, :n], nan=-1.0)))
+    return rows
+
+
+def test_c4_full_size_properties():
+    from oracle import convnet, paf_grouping as opg, peak_finding as opf, preprocess as opre
+    bench, spec, weights, model, pred = _c4()
+    frames = bench.make_frames(8, 4242)
+    out = pred.inference_model.predict_on_batch(frames)
+    assert out["instance_peaks"].shape[0] == 8 and int(out["n_valid"].sum()) > 0 and not out["flags"].any()
+    # (1) order independence: every frame's result is the same wherever it sits in the batch
+    rev = pred.inference_model.predict_on_batch(frames[::-1].copy())
+    for a, b in zip(_per_frame(out), _per_frame(rev)[::-1]):
+        assert a[0] == b[0]
+        assert_array_equal(a[1], b[1])
+        assert_array_equal(a[2], b[2])
+    # (2) a batch of duplicates returns eight identical results
+    dup = _per_frame(pred.inference_model.predict_on_batch(np.repeat(frames[3:4], 8, axis=0)))
+    for d in dup[1:]:
+        assert d[0] == dup[0][0]
+        assert_array_equal(d[1], dup[0][1])
+    assert dup[0][0] == _per_frame(out)[3][0]
+    assert_array_equal(dup[0][1], _per_frame(out)[3][1])
+    # (3) fused pipeline == oracle post-processing of the device's own maps (indices / assignments exact)
+    cms, pafs = model.forward(frames[:2])
+    p, v, si, ci = opf.find_local_peaks(cms, 0.2, "integral", 5)
+    p = (p * np.float32(4)).astype(np.float32)
+    winst, _, wisc, *_ = opg.PAFScorer(bench.NODES, bench.EDGES, 8).predict(
+        pafs, [p[si == b] for b in range(2)], [v[si == b] for b in range(2)], [ci[si == b] for b in range(2)])
+    for b in range(2):
+        n = int(out["n_valid"][b])
+        assert n == len(winst[b])
+        assert_array_equal(np.isnan(out["instance_peaks"][b, :n]), np.isnan(winst[b]))
+        assert_allclose(out["instance_peaks"][b, :n], winst[b], atol=4e-4, rtol=0, equal_nan=True)
+        assert_allclose(out["instance_scores"][b, :n], wisc[b], atol=1e-4, rtol=0)
+    # (4) one frame of the fp16 tensor-core network against the fp32 oracle network (torch CPU)
+    x = opre.preprocess(frames[:1], ensure_gray=True, input_scale=1.0, pad_stride=32)
+    ocms, opafs = convnet.model_forward(x, spec, weights)
+    for got, want in ((cms[:1], ocms), (pafs[:1], opafs)):
+        assert np.abs(got - want).max() <= 3e-2 * np.abs(want).max()
