@@ -538,6 +538,153 @@ __global__ void __launch_bounds__(128) k_conv_tc(const __grid_constant__ CUtenso
 }
 
 
+// ---- EXPERIMENTAL (opt-in, SB_ENABLE_MULTICAST=2|4; not yet run on hardware) ---------------------------------
+// Streaming variant for thread-block clusters: the CS CTAs of a cluster work on CS neighbouring pixel tiles of
+// the same image and N tile, so they consume the same weight slices.  Each CTA fetches 1/CS of every [N x KC]
+// slice and TMA-multicasts it into the same ring slot of all CTAs of the cluster: the L2 -> SM weight traffic
+// (profiles/r01_l2_traffic.md: up to 28x the algorithmic bytes for the 512-channel layers) drops by CS.
+//   full barrier  (per CTA, per slot): expects the whole slice; every rank's multicast completes 1/CS of it.
+//   empty barrier (per CTA, per slot): CS arrivals -- every CTA's MMA warp multicasts its tcgen05.commit to the
+//                 cluster, so a slot is refilled only when all CTAs have finished reading it.
+// Activation tiles stay private.  Everything else (epilogue, parameters) is the streaming kernel's.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+
+template <int KSTEPS, int CS>
+__global__ void __launch_bounds__(128) k_conv_tc_mc(const __grid_constant__ CUtensorMap mapA,
+                                                    const __grid_constant__ CUtensorMap mapBpiece,   // box [KC, N / CS, 1]
+                                                    const __grid_constant__ TcParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_ring = base;
+  uint8_t* b_ring = a_ring + (size_t)P.n_a_slots * P.a_slot_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + (size_t)P.n_b_slots * P.b_slot_bytes);
+  uint64_t* fullA = bars;
+  uint64_t* emptyA = fullA + P.n_a_slots;
+  uint64_t* fullB = emptyA + P.n_a_slots;
+  uint64_t* emptyB = fullB + P.n_b_slots;
+  uint64_t* accum = emptyB + P.n_b_slots;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+  float* s_par = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~(uintptr_t)15);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;                       // the CS tiles of a cluster are consecutive in x
+  const int x0 = (tile % P.tiles_x) * TW, y0 = (tile / P.tiles_x) * TH;
+  const int n0 = blockIdx.y * P.N;
+  const int b = blockIdx.z;
+  const uint32_t rank = cluster_ctarank();
+  constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1u);
+  stage_params(P, s_par, n0);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < P.n_a_slots; ++i) { mbar_init(smem_u32(fullA + i), 1); mbar_init(smem_u32(emptyA + i), 1); }
+    for (int i = 0; i < P.n_b_slots; ++i) { mbar_init(smem_u32(fullB + i), 1); mbar_init(smem_u32(emptyB + i), CS); }
+    mbar_init(smem_u32(accum), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBpiece) : "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(P.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();                                 // every CTA's barriers exist before anyone signals them remotely
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const int piece_rows = P.N / CS;
+  const uint32_t piece_bytes = (uint32_t)(piece_rows * P.row_bytes);
+
+  if (warp == 0 && lane == 0) {
+    int sa = 0, sb = 0;
+    uint32_t pha = 0, phb = 0;
+    for (int ch = 0; ch < P.n_chunks; ++ch) {
+      for (int g = 0; g < P.n_groups; ++g) {
+        mbar_wait(smem_u32(emptyA + sa), pha ^ 1, 41);
+        mbar_expect_tx(smem_u32(fullA + sa), (uint32_t)P.a_tx_bytes);
+        tma_load_4d(smem_u32(a_ring + (size_t)sa * P.a_slot_bytes), &mapA, smem_u32(fullA + sa), ch * P.KC,
+                    x0 + P.groups[g].dx, y0 + P.dy0, b);
+        for (int t = 0; t < P.groups[g].n_taps; ++t) {
+          mbar_wait(smem_u32(emptyB + sb), phb ^ 1, 42);       // all CS CTAs are done with this slot
+          mbar_expect_tx(smem_u32(fullB + sb), (uint32_t)P.b_tx_bytes);
+          tma_load_3d_mc(smem_u32(b_ring + (size_t)sb * P.b_slot_bytes) + rank * piece_bytes, &mapBpiece, smem_u32(fullB + sb),
+                         ch * P.KC, n0 + (int)rank * piece_rows, P.groups[g].taps[t].w_tap, kMask);
+          if (++sb == P.n_b_slots) { sb = 0; phb ^= 1; }
+        }
+        if (++sa == P.n_a_slots) { sa = 0; pha ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    int sa = 0, sb = 0;
+    uint32_t pha = 0, phb = 0;
+    const uint64_t desc_hi = make_desc(0, P.row_bytes, P.layout_type);
+    for (int ch = 0; ch < P.n_chunks; ++ch) {
+#pragma unroll
+      for (int g = 0; g < MAX_GROUPS; ++g) {
+        if (g >= P.n_groups) break;
+        mbar_wait(smem_u32(fullA + sa), pha, 43);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_base = smem_u32(a_ring + (size_t)sa * P.a_slot_bytes);
+#pragma unroll
+        for (int t = 0; t < MAX_TAPS; ++t) {
+          if (t >= P.groups[g].n_taps) break;
+          mbar_wait(smem_u32(fullB + sb), phb, 44);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t b_base = smem_u32(b_ring + (size_t)sb * P.b_slot_bytes);
+          const uint64_t da = desc_hi + (uint64_t)((a_base + (uint32_t)(P.groups[g].taps[t].row_off * TW * P.row_bytes)) >> 4);
+          const uint64_t db = desc_hi + (uint64_t)(b_base >> 4);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < KSTEPS; ++k)
+              tc_mma_f16(tmem_base, da + 2 * k, db + 2 * k, P.idesc, (ch | g | t | k) ? 1u : 0u);
+            tc_commit_mc(smem_u32(emptyB + sb), kMask);        // one arrival on every CTA's empty barrier of this slot
+          }
+          __syncwarp();
+          if (++sb == P.n_b_slots) { sb = 0; phb ^= 1; }
+        }
+        if (elect_one()) tc_commit(smem_u32(emptyA + sa));
+        __syncwarp();
+        if (++sa == P.n_a_slots) { sa = 0; pha ^= 1; }
+      }
+    }
+    if (elect_one()) tc_commit(smem_u32(accum));
+  }
+  __syncwarp();
+
+  mbar_wait(smem_u32(accum), 0, 45);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const int m = warp * 32 + lane;
+  const int iy = y0 + m / TW, ix = x0 + m % TW;
+  const bool valid = (iy < P.H) && (ix < P.W);
+  const int oy = iy * P.oy_mul + P.oy_add, ox = ix * P.ox_mul + P.ox_add;
+  const size_t pix = ((size_t)b * P.out_H + oy) * P.out_W + ox;
+  tc_epilogue_acc<16, KSTEPS == 4>(P, s_par, tmem_base + ((uint32_t)(warp * 32) << 16), n0, valid, pix, b, x0, y0, warp, lane);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();                                 // nobody leaves while a peer may still signal its barriers
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P.tmem_cols) : "memory");
+  }
+}
+
+
 // Persistent, warp-specialised variant for layers whose whole filter bank fits in shared memory:
 // each CTA loads the weights once, then walks output tiles; warp 0 = TMA producer (activation
 // halo tiles), warp 1 = MMA issuer, warps 2..5 = epilogue.  Two TMEM accumulator stages let the
@@ -1206,6 +1353,8 @@ struct TcLaunch {
   size_t smem_p;
   int occ;
   int use_persist;     // variant chosen at configure time by timing them on the device: 0 stream, 1 persist, 2 halo
+  CUtensorMap mapBpiece;   // experimental multicast streaming: box [KC, N / mc_cluster, 1]
+  int mc_cluster;          // 0 = off; 2 / 4 = cluster size of k_conv_tc_mc (SB_ENABLE_MULTICAST)
   // halo variants (variant id 2 + i): super-tiles of sub_x x sub_y 8x16 sub-tiles, box [KC, 8*sub_x+2, 16*sub_y+2, 1]
   bool pp_valid;       // PP holds the tap/slot tables (the launch covers all output channels with one N)
   int n_halo;
@@ -1572,6 +1721,18 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz_for(KC), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return sb_fail(h, SB_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
+    // experimental: cluster multicast of the weight slices in the streaming variant
+    L.mc_cluster = 0;
+    if (const char* e = getenv("SB_ENABLE_MULTICAST")) {
+      const int cs = atoi(e);
+      const int tiles = P.tiles_x * ((ib.H + TH - 1) / TH);
+      if ((cs == 2 || cs == 4) && tiles % cs == 0 && N % (8 * cs) == 0 && P.n_chunks * total_steps >= 2) {
+        cuuint32_t pbox[3] = {(cuuint32_t)KC, (cuuint32_t)(N / cs), 1};
+        CUresult r2 = enc(&L.mapBpiece, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)plan->w16, dims, strides, pbox, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz_for(KC), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r2 == CUDA_SUCCESS) L.mc_cluster = cs;
+      }
+    }
   }
   (dst ? *dst : plan->launches).push_back(L);
   return 0;
@@ -1718,6 +1879,14 @@ int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m) {
     SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_prog<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_halo<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_prog<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    if (getenv("SB_ENABLE_MULTICAST")) {
+      SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_mc<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+      SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_mc<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+      SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_mc<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+      SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_mc<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+      SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_mc<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+      SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_mc<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    }
     attr_set = true;
   }
   for (size_t oi = 0; oi < m->ops.size(); ++oi) {
@@ -1840,6 +2009,19 @@ static void launch_variant(sb_handle_s* h, TcLaunch& L, int B, int variant, cuda
   } else {
     dim3 g = L.grid;
     g.z = B;
+    if (L.mc_cluster) {                 // experimental (SB_ENABLE_MULTICAST): clusters of mc_cluster CTAs along the tile axis
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = g; cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = L.smem; cfg.stream = stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = (unsigned)L.mc_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+#define SB_MC(KS, CS_) cudaLaunchKernelEx(&cfg, k_conv_tc_mc<KS, CS_>, L.mapA, L.mapBpiece, L.P)
+      if (L.mc_cluster == 2) { if (L.P.KC == 16) SB_MC(1, 2); else if (L.P.KC == 32) SB_MC(2, 2); else SB_MC(4, 2); }
+      else { if (L.P.KC == 16) SB_MC(1, 4); else if (L.P.KC == 32) SB_MC(2, 4); else SB_MC(4, 4); }
+#undef SB_MC
+      return;
+    }
     switch (L.P.KC) {
       case 16: k_conv_tc<1><<<g, 128, L.smem, stream>>>(L.mapA, L.mapB, L.P); break;
       case 32: k_conv_tc<2><<<g, 128, L.smem, stream>>>(L.mapA, L.mapB, L.P); break;
