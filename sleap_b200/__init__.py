@@ -11,3 +11,17 @@ def load_model(*args, **kwargs):
     from sleap_b200.nn.inference import load_model as _lm
 
     return _lm(*args, **kwargs)
+
+
+def load_video(filename, **kwargs):
+    """Mirror of ``sleap.load_video`` (sleap/io/video.py:1570-1620): a ``Video`` over a media file."""
+    from sleap_b200.io.video import Video
+
+    return Video.from_filename(filename, **kwargs)
+
+
+def load_file(filename, **kwargs):
+    """Mirror of ``sleap.load_file`` (sleap/io/dataset.py:2500-2530) for the ``.slp`` (HDF5) labels format."""
+    from sleap_b200.io.labels import Labels
+
+    return Labels.load_file(filename, **kwargs)
