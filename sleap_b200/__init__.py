@@ -14,14 +14,14 @@ def load_model(*args, **kwargs):
 
 
 def load_video(filename, **kwargs):
-    """Mirror of ``sleap.load_video`` (sleap/io/video.py:1570-1620): a ``Video`` over a media file."""
+    """Mirror of ``sleap.load_video`` (sleap/io/video.py:1638): a ``Video`` over a media file."""
     from sleap_b200.io.video import Video
 
     return Video.from_filename(filename, **kwargs)
 
 
 def load_file(filename, **kwargs):
-    """Mirror of ``sleap.load_file`` (sleap/io/dataset.py:2500-2530) for the ``.slp`` (HDF5) labels format."""
+    """Mirror of ``sleap.load_file`` (sleap/io/dataset.py:2747) for the ``.slp`` (HDF5) labels format."""
     from sleap_b200.io.labels import Labels
 
     return Labels.load_file(filename, **kwargs)

@@ -1,7 +1,7 @@
 """Minimal HDF5 *writer* for the ``.slp`` container (the counterpart of ``h5lite``'s reader).
 
 Emits the same classic layout h5py/libhdf5 1.10 writes by default and that the reference's
-``LabelsV1Adaptor.read`` opens (sleap/io/format/hdf5.py:70-330): superblock v0, version-1 object headers,
+``LabelsV1Adaptor.read`` opens (sleap/io/format/hdf5.py:132-263): superblock v0, version-1 object headers,
 symbol-table groups (one v1 B-tree node + one SNOD per group, names in a local heap), contiguous datasets,
 fixed-point / IEEE float / fixed-length string / compound (v1) datatypes, version-1 attributes.
 Restrictions (enough for labels files): <= 8 links per group (one symbol node, leaf K = 4), 1-D or scalar

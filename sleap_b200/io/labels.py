@@ -2,13 +2,13 @@
 SLEAP ``.slp`` file, and the ``LabelsReader`` provider the predictors accept.
 
 Restates the *data model* the path consumes, not the reference's editing API:
-  sleap/io/format/hdf5.py:70-330     LabelsV1Adaptor.read (tables frames / instances / points / pred_points,
+  sleap/io/format/hdf5.py:132-263    LabelsV1Adaptor.read (tables frames / instances / points / pred_points,
                                      videos_json, metadata attrs["json"] with skeletons + nodes)
   sleap/instance.py:51-117           point record dtypes (x, y, visible, complete[, score])
-  sleap/skeleton.py:840-1000         Skeleton.from_dict (jsonpickle graph: nodes by index, links with EdgeType)
-  sleap/nn/data/providers.py:23-300  LabelsReader (keys image, raw_image_size, example_ind, video_ind, frame_ind,
+  sleap/skeleton.py:1416-1480        Skeleton.to_dict / from_dict (jsonpickle graph: nodes by index, links with EdgeType)
+  sleap/nn/data/providers.py:11-305  LabelsReader (keys image, raw_image_size, example_ind, video_ind, frame_ind,
                                      scale, instances, skeleton_inds, track_inds, n_tracks)
-  sleap/nn/data/instance_centroids.py:12-33, 80-180   InstanceCentroidFinder (bounding-box midpoint or anchor part)
+  sleap/nn/data/instance_centroids.py:12-52, 55-200   InstanceCentroidFinder (bounding-box midpoint or anchor part)
 The HDF5 container is read by the in-tree ``h5lite`` reader.
 """
 import json
@@ -43,7 +43,7 @@ class Skeleton:
     def from_dict(cls, sk: dict, global_nodes: List[dict]):
         """jsonpickle node-link graph: ``nodes[i]["id"]`` indexes the file-level node list; link ``type`` is
         ``EdgeType(1)`` = BODY or ``EdgeType(2)`` = SYMMETRY, later occurrences are ``{"py/id": k}`` back-references
-        to the k-th distinct object met while decoding (skeleton.py:75-93, jsonpickle unpickler)."""
+        to the k-th distinct object met while decoding (skeleton.py:31-46 EdgeType, :88-376 SkeletonDecoder)."""
         def node_name(ref):
             if isinstance(ref, dict) and "py/object" in ref:          # inline Node object (older files)
                 return ref.get("py/state", {}).get("py/tuple", [ref.get("name")])[0]
@@ -184,7 +184,7 @@ class Labels:
         return lab
 
 
-# Table dtypes of the .slp container (sleap/instance.py:51-58, 115-117; sleap/io/format/hdf5.py:390-420)
+# Table dtypes of the .slp container (sleap/instance.py:51-58, 115-117; sleap/io/format/hdf5.py:330-420)
 FRAME_DTYPE = np.dtype([("frame_id", "u8"), ("video", "u4"), ("frame_idx", "u8"), ("instance_id_start", "u8"), ("instance_id_end", "u8")])
 INSTANCE_DTYPE = np.dtype([("instance_id", "i8"), ("instance_type", "u1"), ("frame_id", "u8"), ("skeleton", "u4"), ("track", "i4"),
                            ("from_predicted", "i8"), ("score", "f4"), ("point_id_start", "u8"), ("point_id_end", "u8"),
@@ -194,7 +194,7 @@ PRED_POINT_DTYPE = np.dtype([("x", "f8"), ("y", "f8"), ("visible", "?"), ("compl
 
 
 def skeleton_to_dict(sk: Skeleton, node_index: dict) -> dict:
-    """Inverse of ``Skeleton.from_dict``: the jsonpickle node-link form ``Skeleton.to_dict`` writes (skeleton.py:880-960):
+    """Inverse of ``Skeleton.from_dict``: the jsonpickle node-link form ``Skeleton.to_dict`` / ``SkeletonEncoder`` write (skeleton.py:378-582, 1416-1437):
     the first EdgeType of each kind is spelled out (``py/reduce``), later ones are ``py/id`` back-references."""
     seen = {}
     links = []
@@ -214,7 +214,7 @@ def skeleton_to_dict(sk: Skeleton, node_index: dict) -> dict:
 
 
 def save_file(labels: "Labels", filename: str):
-    """Writes the ``.slp`` (HDF5) container ``LabelsV1Adaptor.write`` produces (sleap/io/format/hdf5.py:332-575,
+    """Writes the ``.slp`` (HDF5) container ``LabelsV1Adaptor.write`` produces (sleap/io/format/hdf5.py:265-575,
     format 1.2): ``metadata`` group (attrs ``format_id``, ``json``), ``videos_json`` / ``tracks_json`` /
     ``suggestions_json`` and the ``frames`` / ``instances`` / ``points`` / ``pred_points`` tables; predicted instances
     carry per-point scores and an instance score.  Written with the in-tree ``h5write`` (no h5py)."""
@@ -290,7 +290,7 @@ def find_points_bbox_midpoint(points: np.ndarray) -> np.ndarray:
 
 
 def find_instance_centroids(instances: np.ndarray, anchor_ind: Optional[int] = None) -> np.ndarray:
-    """instance_centroids.py:52-77 ``find_instance_centroids``: the anchor node where it is visible, else the
+    """instance_centroids.py:137-200 ``InstanceCentroidFinder.transform_dataset``: the anchor node where it is visible, else the
     bounding-box midpoint of the visible nodes."""
     instances = np.asarray(instances, np.float32)
     mid = find_points_bbox_midpoint(instances)
@@ -304,7 +304,7 @@ def find_instance_centroids(instances: np.ndarray, anchor_ind: Optional[int] = N
 class LabelsReader:
     """Provider over ``Labels`` (providers.py:23-300): examples carry the frame and its instances; with
     ``center_on_part`` set (or ``with_centroids=True``) also ``centroids`` (InstanceCentroidFinder,
-    instance_centroids.py:80-180), which the ground-truth stand-in layers of the top-down model consume."""
+    instance_centroids.py:55-200), which the ground-truth stand-in layers of the top-down model consume."""
 
     def __init__(self, labels: Labels, example_indices: Optional[Sequence[int]] = None, user_instances_only: bool = False,
                  with_centroids: bool = False, center_on_part: Optional[str] = None, video_search: Sequence[str] = ()):

@@ -305,7 +305,7 @@ class FindInstancePeaks(SingleInstanceInferenceLayer):
 
 
 class CentroidCropGroundTruth:
-    """sleap/nn/inference.py:694-809: stands in for a centroid model -- crops of ``crop_size`` around the
+    """sleap/nn/inference.py:723-809: stands in for a centroid model -- crops of ``crop_size`` around the
     ground-truth centroids of a labels example (``example_gt["centroids"]``: one (n, 2) array per sample, made by
     ``LabelsReader(with_centroids=True)`` = InstanceCentroidFinder).  The crop itself is the device kernel."""
 
@@ -776,7 +776,7 @@ class Predictor:
 
     def to_labels(self, frames, video_filename: str = "", video_spec=None):
         """``predict(..., make_labels=True)`` output -> ``sleap_b200.io.labels.Labels`` (``.save("out.slp")`` writes the
-        reference's HDF5 labels container, sleap/io/format/hdf5.py:332-575)."""
+        reference's HDF5 labels container, sleap/io/format/hdf5.py:265-575)."""
         from sleap_b200.io.labels import labels_from_predictions
         return labels_from_predictions(frames, self.skeleton(), video_spec, video_filename)
 
