@@ -1,7 +1,7 @@
 """Minimal pure-Python reader for the subset of HDF5 that SLEAP's files use.
 
 The reference reads ``best_model.h5`` through Keras/h5py (``sleap/nn/inference.py:3203-3213``,
-``sleap/nn/model.py``) and ``.slp`` label files through h5py (``sleap/io/format/hdf5.py:70-330``).
+``sleap/nn/model.py``) and ``.slp`` label files through h5py (``sleap/io/format/hdf5.py:132-263``).
 h5py is not available on the deployment image, so this module restates the *file format*
 (HDF5 File Format Specification 1.x: superblock v0/v1, v1 object headers, symbol-table groups
 with v1 B-trees + local heaps, contiguous / compact / chunked layouts with deflate + shuffle

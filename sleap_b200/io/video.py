@@ -25,11 +25,11 @@ def _cv2():
 
 
 class Video:
-    """Minimal ``sleap.Video`` / ``MediaVideo`` (sleap/io/video.py:340-535, 1070-1320): random access to frames.
+    """Minimal ``sleap.Video`` / ``MediaVideo`` (sleap/io/video.py:340-509, 1001-1330): random access to frames.
 
     ``Video.from_filename(path, grayscale=None)``; ``.shape == (frames, height, width, channels)``;
     ``video[i]`` / ``video.get_frame(i)`` -> (H, W, C) uint8; ``video.get_frames(idxs)`` -> (n, H, W, C).
-    A (frames, H, W, C) array is accepted in place of a path (``NumpyVideo``, video.py:518-600).
+    A (frames, H, W, C) array is accepted in place of a path (``NumpyVideo``, video.py:511-620).
     """
 
     def __init__(self, filename: Union[str, np.ndarray], grayscale: Optional[bool] = None, bgr: bool = True):

@@ -1,5 +1,5 @@
 """Caller side of the path: ``.slp`` labels -> LabelsReader examples -> ground-truth stand-in layers
-of the top-down model (sleap/nn/inference.py:694-893).  Host logic only; no GPU."""
+of the top-down model (sleap/nn/inference.py:723-893).  Host logic only; no GPU."""
 import os
 
 import numpy as np
