@@ -408,6 +408,37 @@ def run_ours(args):
                               "achieved_gbs": 357e6 * B / (float(op_ms_m.sum()) * 1e-3) / 1e9,
                               "peak_gbs": float(peaks["hbm_gbs"])}}
 
+    # per-layer floors: a layer is bound by the larger of its tensor floor (FLOPs / sustained bf16 peak) and its HBM
+    # floor (activation bytes in + out at storage width / measured copy bandwidth); the whole network's attainable
+    # time is the sum of those floors.  Informational (tools/layer_rooflines.py writes the per-layer table).
+    try:
+        c4_layers = [(1, 1, 16, 1024, 1024, 9, 1.0, 2), (2, 16, 16, 1024, 1024, 9, 1.25, 2), (4, 16, 32, 512, 512, 9, 1.0, 2),
+                     (5, 32, 32, 512, 512, 9, 1.25, 2), (7, 32, 64, 256, 256, 9, 1.0, 2), (8, 64, 64, 256, 256, 9, 1.25, 2),
+                     (10, 64, 128, 128, 128, 9, 1.0, 2), (11, 128, 128, 128, 128, 9, 1.25, 2), (13, 128, 256, 64, 64, 9, 1.0, 2),
+                     (14, 256, 256, 64, 64, 9, 1.25, 2), (16, 256, 512, 32, 32, 9, 1.0, 2), (17, 512, 512, 32, 32, 9, 1.0, 2),
+                     (18, 512, 256, 32, 64, 2.25, 1.0, 2), (19, 512, 256, 64, 64, 9, 1.0, 2), (20, 256, 256, 64, 64, 9, 1.0, 2),
+                     (21, 256, 128, 64, 128, 2.25, 1.0, 2), (22, 256, 128, 128, 128, 9, 1.0, 2), (23, 128, 128, 128, 128, 9, 1.0, 2),
+                     (24, 128, 64, 128, 256, 2.25, 1.0, 2), (25, 128, 64, 256, 256, 9, 1.0, 2), (26, 64, 64, 256, 256, 9, 1.0, 2),
+                     (27, 64, 13, 256, 256, 1, 1.0, 4), (28, 128, 24, 128, 128, 1, 1.0, 4)]   # op, Cin, Cout, Hin, Hout, taps, pool factor, out B/elem
+        hbm = float(peaks["hbm_gbs"]) * 1e9
+        fsum = msum = 0.0
+        n_hbm = 0
+        if B == FRAMES_PER_GPU and prec == 0 and len(op_ms_m) > 28:
+            for op, cin, cout, hin, hout, taps, pf, ob in c4_layers:
+                fl_op = 2.0 * taps * cin * cout * hout * hout * B
+                if abs(fl_op - float(fl[op])) > 0.02 * fl_op:
+                    raise ValueError(f"op {op}: layer table does not match the compiled model")
+                t_t = fl_op / (peak_tf * 1e12) * 1e3
+                t_h = (B * hin * hin * cin * (1 if cin == 1 else 2) + B * hout * hout * cout * ob * pf) / hbm * 1e3
+                fsum += max(t_t, t_h)
+                n_hbm += int(t_h > t_t)
+                msum += float(op_ms_m[op])
+            roofline["per_layer_floors"] = {"sum_of_floors_ms": fsum, "measured_ms": msum, "frac": fsum / msum if msum else None,
+                                            "hbm_bound_layers": n_hbm, "tensor_bound_layers": len(c4_layers) - n_hbm,
+                                            "hbm_peak_gbs": float(peaks["hbm_gbs"]), "tensor_peak_tflops": peak_tf}
+    except Exception as e:                       # never let the informational block break the bench line
+        roofline["per_layer_floors"] = {"error": str(e)}
+
     # ---------------- CPU baseline (oracle port) on a bounded sample ----------------
     cpu = None
     if not args.no_cpu_baseline:
