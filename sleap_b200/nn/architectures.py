@@ -309,7 +309,26 @@ class CompiledModel:
         return blob
 
 
+def _compile_identity(spec: dict, input_channels: int, input_scale: float, pad_to_stride: Optional[int]) -> CompiledModel:
+    """``backbone="identity"``: the network is ``Lambda(lambda x: x)`` named after the head, as in the reference's
+    layer tests (tests/nn/test_inference.py:218-220, 270-274, 556-558): the preprocessed frame IS the head output.
+    One float32 buffer, one PREPROCESS op; only meaningful with the fp32 precision path."""
+    cm = CompiledModel()
+    head = spec["heads"][0]
+    if head["channels"] != input_channels:
+        raise ValueError("identity backbone: head channels must equal the input channels")
+    cm.records = [ol.buffer_record(0, 1, input_channels, 1, 1), ol.preprocess_record(0, input_channels, float(input_scale), int(pad_to_stride or 1))]
+    cm.n_buffers = 1
+    cm.head_buffers = {head["name"]: 0}
+    cm.head_strides = {head["name"]: 1}
+    cm.spec, cm.input_channels, cm.max_stride = spec, input_channels, int(pad_to_stride or 1)
+    cm.n_weights = 1                                  # the C-ABI wants a non-empty weight blob
+    return cm
+
+
 def compile_model(spec: dict, input_channels: int, input_scale: float = 1.0, pad_to_stride: Optional[int] = None) -> CompiledModel:
+    if spec["backbone"] == "identity":
+        return _compile_identity(spec, input_channels, input_scale, pad_to_stride)
     g = GraphBuilder()
     net_c = input_channels
     x0 = g.tensor(net_c, 1, False, "input")
