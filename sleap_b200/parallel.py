@@ -55,3 +55,48 @@ def all_gather_records(local: torch.Tensor, out: torch.Tensor = None) -> torch.T
         dist.all_gather(parts, local)
         out.copy_(torch.cat(parts, dim=0))
     return out
+
+
+def predict_sharded(predict_on_batch, frames, global_batch: int, max_instances: int, n_nodes: int, device=None):
+    """Frame-sharded prediction over all ranks of the default process group.
+
+    Every rank calls this with the same ``frames`` (array-like, ``len`` + slicing).  Each global batch of
+    ``global_batch`` frames is cut into contiguous per-rank shards (``frame_shard``); a rank runs
+    ``predict_on_batch(shard)`` -- the ``predict_on_batch`` of a bottom-up / top-down / single-instance inference
+    model: a dict with ``instance_peaks (b, i, C, 2)``, ``instance_peak_vals (b, i, C)``, optional
+    ``instance_scores (b, i)`` and ``n_valid (b,)`` -- packs fixed-size records and joins the ONE exchange step of the
+    path, an all-gather (NCCL on GPUs, gloo on CPU).  Yields, on every rank, one dict per global batch in frame order
+    with the arrays NaN-padded to ``max_instances``.  Ragged tails (fewer frames than ranks) are handled by padding
+    the local record block to the largest shard and dropping the padding rows after the gather."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    I, C = max_instances, n_nodes
+    width = record_width(I, C)
+    n = len(frames)
+    for g0 in range(0, n, global_batch):
+        g1 = min(n, g0 + global_batch)
+        nb = g1 - g0
+        sl = frame_shard(nb, rank, world)
+        cap = -(-nb // world)                                     # largest shard
+        rec = torch.full((cap, width), float("nan"), dtype=torch.float32)
+        rec[:, -1] = -1.0                                         # n_valid = -1 marks a padding row
+        if sl.stop > sl.start:
+            out = predict_on_batch(frames[g0 + sl.start:g0 + sl.stop])
+            b = sl.stop - sl.start
+            ip = np.full((b, I, C, 2), np.nan, np.float32); iv = np.full((b, I, C), np.nan, np.float32)
+            isc = np.full((b, I), np.nan, np.float32)
+            k = min(I, out["instance_peaks"].shape[1])
+            ip[:, :k] = out["instance_peaks"][:, :k]
+            iv[:, :k] = out["instance_peak_vals"][:, :k]
+            if "instance_scores" in out:
+                isc[:, :k] = out["instance_scores"][:, :k]
+            nv = np.minimum(np.asarray(out.get("n_valid", np.full(b, k)), np.int64), I)
+            rec[:b] = pack_records(torch.from_numpy(ip), torch.from_numpy(iv), torch.from_numpy(isc), torch.from_numpy(nv))
+        if device is not None:
+            rec = rec.to(device)
+        allrec = all_gather_records(rec).cpu()
+        keep = allrec[:, -1] >= 0                                 # rank-major order == frame order (contiguous shards)
+        peaks, vals, scores, n_valid = unpack_records(allrec[keep], I, C)
+        assert peaks.shape[0] == nb, (peaks.shape, nb)
+        yield {"instance_peaks": peaks.numpy(), "instance_peak_vals": vals.numpy(), "instance_scores": scores.numpy(),
+               "n_valid": n_valid.numpy(), "frame_ind": np.arange(g0, g1)}
