@@ -617,6 +617,10 @@ class PredictedInstance:
     def numpy(self):
         return self.points
 
+    @property
+    def n_visible_points(self):
+        return int(np.sum(~np.isnan(self.points).any(axis=1)))
+
 
 class LabeledFrame:
     def __init__(self, video, frame_idx, instances):
@@ -629,6 +633,7 @@ class Predictor:
     verbosity = "none"
     report_rate = 2.0
     model_paths: List[str] = []
+    tracker = None          # optional sleap_b200.nn.tracking.Tracker applied frame by frame (:3306-3313)
 
     def __init__(self, batch_size=4):
         self.batch_size = batch_size
@@ -790,7 +795,11 @@ class Predictor:
                 ex = q.get()
                 if ex is None:
                     return
-                frames.extend(self._frames_from_example(ex))
+                new = self._frames_from_example(ex)
+                if self.tracker is not None:                     # sequential by nature; runs on the consumer thread
+                    for lf in new:
+                        lf.instances = self.tracker.track(lf.instances, t=lf.frame_idx)
+                frames.extend(new)
 
         t = threading.Thread(target=worker)
         t.start()

@@ -1,0 +1,415 @@
+"""Identity tracking across frames: the step that follows the inference path.
+
+Restates the default tracker of the reference -- candidates from the last ``track_window`` frames, one similarity
+value per (instance, track), greedy or Hungarian assignment, new tracks for the unmatched, optional cap on the
+number of tracks -- without optical-flow shifting and without the Kalman variant:
+  sleap/nn/tracker/components.py:33-196   similarity functions (instance, normalized, object keypoint, centroid, IoU)
+  sleap/nn/tracker/components.py:198-226  hungarian_matching / greedy_matching, :637-647 first_choice_matching
+  sleap/nn/tracker/components.py:229-313  nms_instances / nms_fast, :316-422 cull_instances / cull_frame_instances
+  sleap/nn/tracker/components.py:457-634  Match, FrameMatches
+  sleap/nn/tracking.py:442-492            SimpleCandidateMaker, SimpleMaxTracksCandidateMaker
+  sleap/nn/tracking.py:542-844            Tracker.track / spawn / queues, :844-995 make_tracker_by_name
+Sequential host code by nature (frame t depends on t-1); instances are anything with ``numpy()`` (n_nodes, 2),
+``score`` and a settable ``track`` (``sleap_b200.nn.inference.PredictedInstance``).
+"""
+import copy
+from collections import deque
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+from scipy.optimize import linear_sum_assignment
+
+
+class Track:
+    """sleap/instance.py Track: identity token; compared by identity."""
+
+    def __init__(self, spawned_on: int = 0, name: str = ""):
+        self.spawned_on, self.name = spawned_on, name
+
+    def __repr__(self):
+        return f"Track(spawned_on={self.spawned_on}, name={self.name!r})"
+
+
+def _pts(inst) -> np.ndarray:
+    return np.asarray(inst.numpy(), np.float64)
+
+
+def n_visible_points(inst) -> int:
+    return int(np.sum(~np.isnan(_pts(inst)).any(axis=1)))
+
+
+def centroid(inst) -> np.ndarray:
+    """Median of the visible points (instance.py:867-875)."""
+    return np.nanmedian(_pts(inst), axis=0)
+
+
+def bounding_box(inst) -> np.ndarray:
+    """[y1, x1, y2, x2] over the visible points (instance.py:878-886)."""
+    p = _pts(inst)
+    if np.isnan(p).all():
+        return np.full(4, np.nan)
+    return np.concatenate([np.nanmin(p, axis=0)[::-1], np.nanmax(p, axis=0)[::-1]])
+
+
+# ---- similarities (larger = more alike) -----------------------------------------------------------
+def instance_similarity(ref, query) -> float:
+    r, q = _pts(ref), _pts(query)
+    n_ref = np.sum(~np.isnan(r).any(axis=1))
+    d2 = np.sum((q - r) ** 2, axis=1)
+    return float(np.nansum(np.exp(-d2)) / n_ref)
+
+
+def normalized_instance_similarity(ref, query, img_hw: Tuple[int, int]) -> float:
+    scale = np.asarray((img_hw[1], img_hw[0]), np.float64)
+    r, q = _pts(ref) / scale, _pts(query) / scale
+    n_ref = np.sum(~np.isnan(r).any(axis=1))
+    return float(np.nansum(np.exp(-np.sum((q - r) ** 2, axis=1))) / n_ref)
+
+
+def factory_object_keypoint_similarity(keypoint_errors=None, score_weighting: bool = False, normalization_keypoints: str = "all") -> Callable:
+    errors = np.asarray(1 if keypoint_errors is None or (hasattr(keypoint_errors, "__len__") and len(keypoint_errors) == 0) else keypoint_errors,
+                        np.float64)
+    with np.errstate(divide="ignore"):
+        precision = 1.0 / (2.0 * errors ** 2)
+
+    def object_keypoint_similarity(ref, query) -> float:
+        r, q = _pts(ref), _pts(query)
+        ws = 1.0
+        if score_weighting:
+            ws = np.asarray(getattr(ref, "point_confidences", np.ones(len(r))), np.float64) * \
+                np.asarray(getattr(query, "point_confidences", np.ones(len(q))), np.float64)
+        vis_r = ~np.isnan(r).any(axis=1)
+        if normalization_keypoints == "ref":
+            denom = int(vis_r.sum())
+        elif normalization_keypoints == "union":
+            denom = int(np.logical_and(vis_r, ~np.isnan(q).any(axis=1)).sum())
+        else:
+            denom = len(r)
+        if denom == 0:
+            return 0.0
+        prec = precision
+        if prec.size > 1 and prec.size != len(r):               # fit the per-keypoint errors to the skeleton
+            prec = prec[:len(r)] if prec.size > len(r) else np.pad(prec, (0, len(r) - prec.size), "edge")
+        d = np.sum((q - r) ** 2, axis=1) * prec
+        return float(np.nansum(ws * np.exp(-d)) / denom)
+
+    return object_keypoint_similarity
+
+
+def centroid_distance(ref, query) -> float:
+    return float(-np.linalg.norm(centroid(ref) - centroid(query)))
+
+
+def compute_iou(a: Sequence[float], b: Sequence[float]) -> float:
+    """sleap/nn/utils.py:45-76: inclusive-pixel IoU of [y1, x1, y2, x2] boxes."""
+    iy1, ix1, iy2, ix2 = max(a[0], b[0]), max(a[1], b[1]), min(a[2], b[2]), min(a[3], b[3])
+    inter = max(ix2 - ix1 + 1, 0) * max(iy2 - iy1 + 1, 0)
+    area = lambda t: (t[3] - t[1] + 1) * (t[2] - t[0] + 1)
+    return float(inter / (area(a) + area(b) - inter))
+
+
+def instance_iou(ref, query) -> float:
+    return compute_iou(bounding_box(ref), bounding_box(query))
+
+
+# ---- assignment -----------------------------------------------------------------------------------
+def hungarian_matching(cost: np.ndarray) -> List[Tuple[int, int]]:
+    rows, cols = linear_sum_assignment(cost)
+    return list(zip(rows.tolist(), cols.tolist()))
+
+
+def greedy_matching(cost: np.ndarray) -> List[Tuple[int, int]]:
+    """Cheapest remaining (row, column) pair first; ties in ``argsort`` order of the flattened matrix."""
+    order = np.argsort(cost, axis=None)
+    used_r, used_c, out = set(), set(), []
+    for flat in order.tolist():
+        r, c = divmod(flat, cost.shape[1])
+        if r in used_r or c in used_c:
+            continue
+        used_r.add(r); used_c.add(c)
+        out.append((r, c))
+    return out
+
+
+def first_choice_matching(cost: np.ndarray) -> List[Tuple[int, int]]:
+    return list(zip(range(len(cost)), cost.argmin(axis=1).tolist()))
+
+
+# ---- suppression of duplicate detections ----------------------------------------------------------
+def nms_fast(boxes: np.ndarray, scores: np.ndarray, iou_threshold: float, target_count: Optional[int] = None) -> List[int]:
+    """Score-ordered box suppression (overlap measured against the *other* box's area, +1 pixel convention), then, when
+    fewer than ``target_count`` survive, suppressed boxes are handed back best score first.  The hand-back count is
+    ``min(n_suppressed, n_kept - target_count)`` used as a slice end, exactly as the reference computes it
+    (components.py:306-309; negative ends drop from the tail, which its tests rely on)."""
+    boxes = np.asarray(boxes)
+    scores = np.asarray(scores, np.float64)
+    if len(boxes) == 0:
+        return []
+    if target_count and len(boxes) < target_count:
+        return list(range(len(boxes)))
+    boxes = boxes.astype(np.float64)
+    x1, y1, x2, y2 = boxes.T
+    area = (x2 - x1 + 1) * (y2 - y1 + 1)
+    alive = list(np.argsort(scores))
+    kept, dropped = [], []
+    while alive:
+        top = alive.pop()                                   # best remaining score
+        kept.append(int(top))
+        rest = np.asarray(alive, np.int64)
+        if len(rest) == 0:
+            break
+        w = np.maximum(0, np.minimum(x2[top], x2[rest]) - np.maximum(x1[top], x1[rest]) + 1)
+        h = np.maximum(0, np.minimum(y2[top], y2[rest]) - np.maximum(y1[top], y1[rest]) + 1)
+        over = (w * h) / area[rest] > iou_threshold
+        dropped.extend(int(i) for i in rest[over])
+        alive = [int(i) for i in rest[~over]]
+    if target_count and dropped and len(kept) < target_count:
+        dropped.sort(key=lambda i: -scores[i])
+        kept.extend(dropped[:min(len(dropped), len(kept) - target_count)])
+    return kept
+
+
+def nms_instances(instances: list, iou_threshold: float, target_count: Optional[int] = None):
+    boxes = np.asarray([bounding_box(i) for i in instances])
+    scores = np.asarray([i.score for i in instances])
+    picks = set(nms_fast(boxes, scores, iou_threshold, target_count))
+    return [x for i, x in enumerate(instances) if i in picks], [x for i, x in enumerate(instances) if i not in picks]
+
+
+def cull_frame_instances(instances: list, instance_count: int, iou_threshold: Optional[float] = None) -> list:
+    """At most ``instance_count`` instances in this frame: overlapping duplicates go first (when a threshold is given),
+    then the lowest scores.  Modifies and returns the list (components.py:365-422)."""
+    if not instances or len(instances) <= instance_count:
+        return instances
+    keep = list(instances)
+    if iou_threshold:
+        keep, extra = nms_instances(keep, iou_threshold, target_count=instance_count)
+        for x in extra:
+            instances.remove(x)
+    if len(keep) > instance_count:
+        for x in sorted(keep, key=lambda i: i.score)[:-instance_count]:
+            instances.remove(x)
+    return instances
+
+
+def cull_instances(frames: list, instance_count: int, iou_threshold: Optional[float] = None):
+    for lf in sorted(frames, key=lambda f: f.frame_idx):
+        cull_frame_instances(lf.instances, instance_count, iou_threshold)
+
+
+# ---- matches of one frame ---------------------------------------------------------------------------
+class Match:
+    def __init__(self, track, instance, score=None, is_first_choice=False):
+        self.track, self.instance, self.score, self.is_first_choice = track, instance, score, is_first_choice
+
+
+class FrameMatches:
+    """Matches of one frame + whether each instance got the track it would have picked alone (components.py:470-634)."""
+
+    def __init__(self, matches: List[Match], cost_matrix: np.ndarray, unmatched_instances: list):
+        self.matches, self.cost_matrix, self.unmatched_instances = matches, cost_matrix, unmatched_instances
+
+    @property
+    def has_only_first_choice_matches(self) -> bool:
+        return all(m.is_first_choice for m in self.matches)
+
+    @classmethod
+    def from_cost_matrix(cls, cost_matrix: np.ndarray, instances: list, tracks: list, matching_function: Callable):
+        matches, taken = [], set()
+        if instances and tracks:
+            first = cost_matrix.argmin(axis=1)
+            for i, j in matching_function(cost_matrix):
+                taken.add(i)
+                matches.append(Match(tracks[j], instances[i], -cost_matrix[i, j], bool(first[i] == j)))
+        return cls(matches, cost_matrix, [x for i, x in enumerate(instances) if i not in taken])
+
+    @classmethod
+    def from_candidate_instances(cls, untracked_instances: list, candidate_instances: list, similarity_function: Callable,
+                                 matching_function: Callable, robust_best_instance: float = 1.0):
+        cost, tracks = np.ndarray((0,)), []
+        if candidate_instances:
+            by_track: Dict[object, list] = {}
+            for c in candidate_instances:                       # insertion order = order of first appearance
+                by_track.setdefault(c.track, []).append(c)
+            tracks = list(by_track)
+            sim = np.full((len(untracked_instances), len(tracks)), np.nan)
+            for i, u in enumerate(untracked_instances):
+                for j, tr in enumerate(tracks):
+                    s = [similarity_function(u, c) for c in by_track[tr]]
+                    sim[i, j] = np.quantile(s, robust_best_instance) if 0 < robust_best_instance < 1 else np.max(s)
+            cost = -sim
+            cost[np.isnan(cost)] = np.inf
+        return cls.from_cost_matrix(cost, untracked_instances, tracks, matching_function)
+
+
+# ---- candidate pools --------------------------------------------------------------------------------
+class SimpleCandidateMaker:
+    """Every instance of the last ``track_window`` frames with enough visible points."""
+
+    uses_image = False
+
+    def __init__(self, min_points: int = 0):
+        self.min_points = min_points
+
+    def get_candidates(self, track_matching_queue, **kw) -> list:
+        return [x for _, insts in track_matching_queue for x in insts if n_visible_points(x) >= self.min_points]
+
+
+class SimpleMaxTracksCandidateMaker(SimpleCandidateMaker):
+    """Per-track history; with ``max_tracking`` only the first ``max_tracks`` tracks are matchable."""
+
+    def __init__(self, min_points: int = 0, max_tracks: Optional[int] = None):
+        super().__init__(min_points)
+        self.max_tracks = max_tracks
+
+    def get_candidates(self, track_matching_queue_dict, max_tracking: bool, **kw) -> list:
+        out, n = [], 0
+        for _, hist in track_matching_queue_dict.items():
+            if not max_tracking or n < self.max_tracks:
+                n += 1
+                out.extend(x for _, x in hist if n_visible_points(x) >= self.min_points)
+        return out
+
+
+SIMILARITIES = dict(instance=instance_similarity, centroid=centroid_distance, iou=instance_iou,
+                    normalized_instance=normalized_instance_similarity, object_keypoint=factory_object_keypoint_similarity)
+MATCHERS = dict(hungarian=hungarian_matching, greedy=greedy_matching)
+CANDIDATE_MAKERS = dict(simple=SimpleCandidateMaker, simplemaxtracks=SimpleMaxTracksCandidateMaker)
+
+
+class Tracker:
+    """One ``track(instances)`` call per frame, in order (tracking.py:542-844)."""
+
+    def __init__(self, track_window: int = 5, similarity_function: Optional[Callable] = instance_similarity,
+                 matching_function: Callable = greedy_matching, candidate_maker=None, max_tracks: Optional[int] = None,
+                 max_tracking: bool = False, min_new_track_points: int = 0, robust_best_instance: float = 1.0,
+                 pre_cull_function: Optional[Callable] = None, target_instance_count: int = 0):
+        self.track_window = track_window
+        self.similarity_function, self.matching_function = similarity_function, matching_function
+        self.candidate_maker = candidate_maker
+        self.max_tracks, self.max_tracking = max_tracks, max_tracking
+        self.min_new_track_points, self.robust_best_instance = min_new_track_points, robust_best_instance
+        self.pre_cull_function, self.target_instance_count = pre_cull_function, target_instance_count
+        self.track_matching_queue: deque = deque(maxlen=track_window)        # (t, [instances])
+        self.track_matching_queue_dict: Dict[Track, deque] = {}               # track -> deque of (t, instance)
+        self.spawned_tracks: List[Track] = []
+        self.last_matches: Optional[FrameMatches] = None
+
+    @property
+    def is_valid(self):
+        return self.similarity_function is not None
+
+    @property
+    def has_max_tracking(self) -> bool:
+        return isinstance(self.candidate_maker, SimpleMaxTracksCandidateMaker)
+
+    @property
+    def unique_tracks_in_queue(self) -> List[Track]:
+        if self.has_max_tracking:
+            return list(self.track_matching_queue_dict)
+        return list({x.track for _, insts in self.track_matching_queue for x in insts})
+
+    def reset_candidates(self):
+        self.track_matching_queue = deque(maxlen=self.track_window)
+        for tr in self.track_matching_queue_dict:
+            self.track_matching_queue_dict[tr] = deque(maxlen=self.track_window)
+
+    def _next_t(self) -> int:
+        if self.has_max_tracking:
+            if not self.track_matching_queue_dict:
+                return 0
+            longest = max(self.track_matching_queue_dict, key=lambda tr: len(self.track_matching_queue_dict[tr]))
+            return self.track_matching_queue_dict[longest][-1][0] + 1
+        return self.track_matching_queue[-1][0] + 1 if self.track_matching_queue else 0
+
+    def track(self, untracked_instances: list, img_hw: Tuple[int, int] = (1, 1), img=None, t: Optional[int] = None) -> list:
+        if self.candidate_maker is None:
+            return untracked_instances
+        sim = self.similarity_function
+        if sim is normalized_instance_similarity:
+            sim = lambda a, b: normalized_instance_similarity(a, b, img_hw=img_hw)
+        if t is None:
+            t = self._next_t()
+        tracked: list = []
+        if untracked_instances:
+            if self.pre_cull_function:
+                self.pre_cull_function(untracked_instances)
+            if self.has_max_tracking:
+                cands = self.candidate_maker.get_candidates(track_matching_queue_dict=self.track_matching_queue_dict,
+                                                            max_tracking=self.max_tracking, t=t, img=img)
+            else:
+                cands = self.candidate_maker.get_candidates(track_matching_queue=self.track_matching_queue, t=t, img=img)
+            fm = FrameMatches.from_candidate_instances(untracked_instances, cands, sim, self.matching_function, self.robust_best_instance)
+            self.last_matches = fm
+            for m in fm.matches:                                # matched: inherit the track
+                x = copy.copy(m.instance)
+                x.track, x.tracking_score = m.track, m.score
+                tracked.append(x)
+            for inst in fm.unmatched_instances:                 # unmatched: new tracks, unless the cap is reached
+                if n_visible_points(inst) < self.min_new_track_points:
+                    continue
+                if self.has_max_tracking and self.max_tracking and len(self.track_matching_queue_dict) >= self.max_tracks:
+                    break
+                tr = Track(spawned_on=t, name=f"track_{len(self.spawned_tracks)}")
+                self.spawned_tracks.append(tr)
+                x = copy.copy(inst)
+                x.track = tr
+                tracked.append(x)
+        if self.has_max_tracking:
+            for x in tracked:
+                if x.track in self.track_matching_queue_dict:
+                    self.track_matching_queue_dict[x.track].append((t, x))
+                elif not self.max_tracking or len(self.track_matching_queue_dict) < self.max_tracks:
+                    self.track_matching_queue_dict[x.track] = deque([(t, x)], maxlen=self.track_window)
+        else:
+            self.track_matching_queue.append((t, tracked))
+        return tracked
+
+    def final_pass(self, frames: list):
+        """Post-processing hook of the reference (track cleaning / single-break joining): nothing here."""
+
+    def get_name(self) -> str:
+        return f"{type(self.candidate_maker).__name__}.{getattr(self.similarity_function, '__name__', 'none')}." \
+               f"{getattr(self.matching_function, '__name__', 'none')}"
+
+    @classmethod
+    def make_tracker_by_name(cls, tracker: str = "simple", similarity: str = "instance", match: str = "greedy", track_window: int = 5,
+                             robust: float = 1.0, min_new_track_points: int = 0, min_match_points: int = 0,
+                             target_instance_count: int = 0, pre_cull_to_target: bool = False,
+                             pre_cull_iou_threshold: Optional[float] = None, max_tracks: Optional[int] = None,
+                             max_tracking: bool = False, oks_errors=None, oks_score_weighting: bool = False,
+                             oks_normalization: str = "all", **kwargs) -> "Tracker":
+        max_tracking = max_tracking if max_tracks else False
+        if max_tracking and tracker == "simple":
+            tracker = "simplemaxtracks"
+        if tracker.lower() == "none":
+            return cls(track_window=track_window, similarity_function=None, matching_function=None, candidate_maker=None)
+        if tracker in ("flow", "flowmaxtracks"):
+            raise ValueError("optical-flow candidate shifting is not part of this build; use tracker='simple' / 'simplemaxtracks'.")
+        if tracker not in CANDIDATE_MAKERS:
+            raise ValueError(f"{tracker} is not a valid tracker.")
+        if similarity not in SIMILARITIES:
+            raise ValueError(f"{similarity} is not a valid tracker similarity function.")
+        if match not in MATCHERS:
+            raise ValueError(f"{match} is not a valid tracker matching function.")
+        maker = CANDIDATE_MAKERS[tracker](min_points=min_match_points)
+        if tracker == "simplemaxtracks":
+            maker.max_tracks = max_tracks
+        sim = SIMILARITIES[similarity]
+        if similarity == "object_keypoint":
+            sim = factory_object_keypoint_similarity(oks_errors, oks_score_weighting, oks_normalization)
+        pre_cull = None
+        if target_instance_count and pre_cull_to_target:
+            pre_cull = lambda insts: cull_frame_instances(insts, target_instance_count, pre_cull_iou_threshold)
+        return cls(track_window=track_window, similarity_function=sim, matching_function=MATCHERS[match], candidate_maker=maker,
+                   max_tracks=max_tracks, max_tracking=max_tracking, min_new_track_points=min_new_track_points,
+                   robust_best_instance=robust, pre_cull_function=pre_cull, target_instance_count=target_instance_count)
+
+
+def run_tracker(frames: list, tracker: Tracker) -> list:
+    """Track the predicted instances of ``frames`` (sorted by frame index) in place (tracking.py:1542-1580)."""
+    frames = sorted(frames, key=lambda lf: lf.frame_idx)
+    for lf in frames:
+        lf.instances = tracker.track(list(lf.instances), t=lf.frame_idx)
+    tracker.final_pass(frames)
+    return frames

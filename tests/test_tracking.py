@@ -1,0 +1,100 @@
+"""Tracker against the reference's component / max-tracking known answers
+(tests/nn/test_tracker_components.py:104-170 nms, :173-232 FrameMatches + greedy matching, :235-430 max tracking)."""
+import numpy as np
+import pytest
+
+from sleap_b200.nn import tracking as T
+from sleap_b200.nn.inference import LabeledFrame, PredictedInstance
+
+
+def test_nms():
+    boxes = np.array([[10, 10, 20, 20], [10, 10, 15, 15], [30, 30, 40, 40], [32, 32, 42, 42]])
+    assert sorted(T.nms_fast(boxes, np.array([1, 0.3, 1, 0.5]), iou_threshold=0.5)) == [0, 2]
+    assert sorted(T.nms_fast(boxes, np.array([1, 0.3, 1, 0.5]), iou_threshold=0.5, target_count=3)) == [0, 2, 3]
+    assert sorted(T.nms_fast(boxes, np.array([1, 0.5, 1, 0.3]), iou_threshold=0.5, target_count=3)) == [0, 1, 2]
+    assert T.nms_fast(np.zeros((0, 4)), np.zeros(0), 0.5) == []
+
+
+def _inst(a, b, score):
+    return PredictedInstance.from_numpy(np.asarray([a, b], np.float32), np.ones(2, np.float32), score)
+
+
+def test_nms_instances_to_remove():
+    insts = [_inst((10, 10), (20, 20), 1), _inst((10, 10), (15, 15), 0.3), _inst((30, 30), (40, 40), 1), _inst((32, 32), (42, 42), 0.5)]
+    keep, remove = T.nms_instances(insts, iou_threshold=0.5, target_count=3)
+    assert len(remove) == 1 and remove[0] is insts[1] and len(keep) == 3
+    culled = T.cull_frame_instances(list(insts), 2, iou_threshold=0.5)
+    assert len(culled) == 2 and {id(x) for x in culled} == {id(insts[0]), id(insts[2])}
+
+
+def test_frame_match_object():
+    instances, tracks = ["instance a", "instance b"], ["track a", "track b"]
+    fm = T.FrameMatches.from_cost_matrix(np.array([[10, 200], [75, 150]]), instances, tracks, T.greedy_matching)
+    assert not fm.has_only_first_choice_matches and len(fm.matches) == 2
+    assert (fm.matches[0].track, fm.matches[0].instance, fm.matches[0].score) == ("track a", "instance a", -10)
+    assert (fm.matches[1].track, fm.matches[1].instance, fm.matches[1].score) == ("track b", "instance b", -150)
+    fm = T.FrameMatches.from_cost_matrix(np.array([[10, 200], [150, 75]]), instances, tracks, T.greedy_matching)
+    assert fm.has_only_first_choice_matches
+    assert T.hungarian_matching(np.array([[10, 200], [75, 150]])) == [(0, 0), (1, 1)]
+    assert T.first_choice_matching(np.array([[10, 200], [75, 150]])) == [(0, 0), (1, 0)]
+
+
+def _make_insts(trx):
+    out = []
+    for frame in trx:
+        out.append([PredictedInstance.from_numpy(np.array([[-0.1, -0.1], [0.0, 0.0], [0.1, 0.1]]) + np.array([[x, y]]), [1, 1, 1], 1)
+                    for x, y in frame])
+    return out
+
+
+def _n_tracks(preds, **kw):
+    tracker = T.Tracker.make_tracker_by_name(match="hungarian", track_window=2, **kw)
+    tracked = [tracker.track(insts, img_hw=(1, 1)) for insts in preds]
+    return len({id(inst.track) for frame in tracked for inst in frame}), tracked
+
+
+CASES = {
+    "large_gap_single_track": ([[(0, 0), (0, 1)], [(0.1, 0), (0.1, 1)], [(0.2, 0), (0.2, 1)], [(0.3, 0)], [(0.4, 0)], [(0.5, 0), (0.5, 1)],
+                                [(0.6, 0), (0.6, 1)]], 3),
+    "small_gap_on_both_tracks": ([[(0, 0), (0, 1)], [(0.1, 0), (0.1, 1)], [(0.2, 0), (0.2, 1)], [], [], [(0.5, 0), (0.5, 1)],
+                                  [(0.6, 0), (0.6, 1)]], 4),
+    "extra_detections": ([[(0, 0), (0, 1)], [(0.1, 0), (0.1, 1)], [(0.2, 0), (0.2, 1)], [(0.3, 0)], [(0.4, 0)], [(0.5, 0), (0.5, 1)],
+                          [(0.6, 0), (0.6, 1), (0.6, 0.5)]], 4),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_max_tracking(name):
+    """A gap longer than the window loses a track with the simple tracker; the max-tracks tracker keeps exactly 2."""
+    trx, n_simple = CASES[name]
+    assert _n_tracks(_make_insts(trx), tracker="simple")[0] == n_simple
+    n, tracked = _n_tracks(_make_insts(trx), tracker="simplemaxtracks", max_tracks=2, max_tracking=True)
+    assert n == 2
+    # identities follow the animals: y = 0 and y = 1 never share a track
+    by_track = {}
+    for frame in tracked:
+        for inst in frame:
+            by_track.setdefault(id(inst.track), set()).add(round(float(inst.numpy()[1, 1])))
+    assert all(len(v) == 1 or name == "extra_detections" for v in by_track.values())
+
+
+@pytest.mark.parametrize("similarity", ["instance", "normalized_instance", "iou", "centroid", "object_keypoint"])
+@pytest.mark.parametrize("match", ["greedy", "hungarian"])
+@pytest.mark.parametrize("tracker", ["simple", "simplemaxtracks"])
+def test_tracker_by_name(tracker, similarity, match):
+    """Every (tracker, similarity, match) combination runs and keeps two well-separated animals apart
+    (test_tracker_by_name, :46-68, on synthetic instead of recorded predictions)."""
+    shape = np.array([[-5.0, -5.0], [0.0, 0.0], [5.0, 5.0]])          # 10 px animals moving 1 px per frame (boxes overlap in time)
+    frames = [LabeledFrame(0, t, [PredictedInstance.from_numpy(shape + np.array([[10.0 + t, 10.0]]), [1, 1, 1], 1),
+                                  PredictedInstance.from_numpy(shape + np.array([[60.0 - t, 40.0]]), [1, 1, 1], 1)]) for t in range(6)]
+    tr = T.Tracker.make_tracker_by_name(tracker=tracker, similarity=similarity, match=match, max_tracks=2,
+                                        max_tracking=tracker == "simplemaxtracks")
+    out = T.run_tracker(frames, tr)
+    ids = [[id(i.track) for i in lf.instances] for lf in out]
+    assert all(len(set(x)) == 2 for x in ids) and all(x == ids[0] for x in ids)
+    assert "." in tr.get_name()
+    T.Tracker.make_tracker_by_name(tracker="none").track([])
+    with pytest.raises(ValueError):
+        T.Tracker.make_tracker_by_name(tracker="flow")
+    with pytest.raises(ValueError):
+        T.Tracker.make_tracker_by_name(similarity="bogus")
