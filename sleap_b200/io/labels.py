@@ -179,7 +179,12 @@ class Labels:
                 ins.append(Instance(xy, sk, int(row["track"]), float(row["score"]),
                                     p["score"].astype(np.float32) if predicted else None, predicted))
             lfs.append(LabeledFrame(int(fr["video"]), int(fr["frame_idx"]), ins))
-        lab = cls(lfs, videos, skeletons, meta.get("tracks", []))
+        tracks = meta.get("tracks", [])
+        if "tracks_json" in f:                                   # one '[spawned_on,"name"]' string per track (hdf5.py:150-160)
+            tj = f["tracks_json"].read()
+            if len(tj) and getattr(tj, "dtype", np.dtype("f8")).kind == "S":
+                tracks = [json.loads(t.decode()) for t in tj]
+        lab = cls(lfs, videos, skeletons, tracks)
         lab._search = list(video_search)
         return lab
 
@@ -227,7 +232,7 @@ def save_file(labels: "Labels", filename: str):
                 node_names.append(n)
     node_index = {n: i for i, n in enumerate(node_names)}
     meta = {"version": "2.0.0", "skeletons": [skeleton_to_dict(sk, node_index) for sk in sk_list],
-            "nodes": [{"name": n, "weight": 1.0} for n in node_names], "videos": [], "tracks": list(labels.tracks), "suggestions": [],
+            "nodes": [{"name": n, "weight": 1.0} for n in node_names], "videos": [], "tracks": [], "suggestions": [],
             "negative_anchors": {}, "provenance": {"writer": "sleap_b200"}}
     frames = np.zeros(len(labels.labeled_frames), FRAME_DTYPE)
     n_inst = sum(len(lf.instances) for lf in labels.labeled_frames)
@@ -263,7 +268,7 @@ def save_file(labels: "Labels", filename: str):
         g.attrs["format_id"] = np.float64(1.2)
         g.attrs["json"] = json.dumps(meta, separators=(",", ":"))
         f.create_dataset("videos_json", strings(videos))
-        f.create_dataset("tracks_json", strings([json.dumps(t).encode() for t in labels.tracks]))
+        f.create_dataset("tracks_json", strings([json.dumps(list(t), separators=(",", ":")).encode() for t in labels.tracks]))
         f.create_dataset("suggestions_json", np.zeros(0, np.float64))
         f.create_dataset("frames", frames)
         f.create_dataset("instances", inst)
@@ -275,11 +280,20 @@ def labels_from_predictions(frames, skeleton: Skeleton, video_spec: Optional[dic
     """``Predictor.predict(..., make_labels=True)`` output (``LabeledFrame`` / ``PredictedInstance`` of
     sleap_b200.nn.inference) -> ``Labels`` that ``save_file`` can write (sleap/nn/inference.py:3230-3343)."""
     spec = video_spec or {"backend": {"filename": video_filename, "grayscale": True, "bgr": True, "dataset": "", "input_format": ""}}
-    lfs = []
+    lfs, track_ids, tracks = [], {}, []
     for fr in frames:
-        ins = [Instance(i.numpy(), skeleton, -1, float(i.score), np.asarray(i.point_confidences, np.float32), True) for i in fr.instances]
+        ins = []
+        for i in fr.instances:
+            tr = getattr(i, "track", None)
+            ti = -1
+            if tr is not None:                                   # sleap_b200.nn.tracking.Track objects -> [spawned_on, name] rows
+                if id(tr) not in track_ids:
+                    track_ids[id(tr)] = len(tracks)
+                    tracks.append([int(getattr(tr, "spawned_on", 0)), str(getattr(tr, "name", f"track_{len(tracks)}"))])
+                ti = track_ids[id(tr)]
+            ins.append(Instance(i.numpy(), skeleton, ti, float(i.score), np.asarray(i.point_confidences, np.float32), True))
         lfs.append(LabeledFrame(int(fr.video) if isinstance(fr.video, (int, np.integer)) else 0, int(fr.frame_idx), ins))
-    return Labels(lfs, [spec], [skeleton])
+    return Labels(lfs, [spec], [skeleton], tracks)
 
 
 def find_points_bbox_midpoint(points: np.ndarray) -> np.ndarray:

@@ -112,3 +112,21 @@ def test_labels_from_predictions(tmp_path):
     back = L.Labels.load_file(p)
     assert [len(lf) for lf in back] == [1, 0] and back[0][0].predicted and back[0][0].n_visible_points == 2
     assert back.video_specs[0]["backend"]["filename"] == "movie.mp4" and back.skeleton.edge_inds == [(0, 1), (1, 2)]
+
+
+def test_tracked_predictions_round_trip(tmp_path):
+    """Tracker output -> Labels -> .slp -> Labels: track table ('[spawned_on,"name"]' rows) and per-instance track indices."""
+    from sleap_b200.nn import tracking as T
+    from sleap_b200.nn.inference import LabeledFrame, PredictedInstance
+    shape = np.array([[-5.0, -5.0], [0.0, 0.0], [5.0, 5.0]])
+    frames = [LabeledFrame(0, t, [PredictedInstance.from_numpy(shape + [[10.0 + t, 10.0]], [1, 1, 1], 1.0),
+                                  PredictedInstance.from_numpy(shape + [[60.0 - t, 40.0]], [1, 1, 1], 2.0)]) for t in range(4)]
+    T.run_tracker(frames, T.Tracker.make_tracker_by_name(tracker="simple"))
+    lab = L.labels_from_predictions(frames, L.Skeleton(["a", "b", "c"], [("a", "b"), ("b", "c")]), video_filename="m.mp4")
+    assert lab.tracks == [[0, "track_0"], [0, "track_1"]]
+    p = str(tmp_path / "tracked.slp")
+    lab.save(p)
+    back = L.Labels.load_file(p)
+    assert back.tracks == [[0, "track_0"], [0, "track_1"]]
+    assert [[i.track for i in lf.instances] for lf in back] == [[0, 1]] * 4
+    assert h5lite.File(p)["tracks_json"].read()[0] == b'[0,"track_0"]'
