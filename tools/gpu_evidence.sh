@@ -4,6 +4,7 @@
 # usage (from the repo root on the GPU box): bash tools/gpu_evidence.sh [skip_tests]
 set -u
 O=gpurun_out
+PFX=${PFX:-r02}          # round prefix of the ncu artefacts (profiles/${PFX}_*)
 mkdir -p $O
 export PYTHONUNBUFFERED=1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/smi.txt 2>&1
@@ -21,17 +22,17 @@ SB_TUNE_LOAD=$O/tune.txt timeout 400 ncu --metrics gpu__time_duration.sum,dram__
 echo "list rc=$?"
 echo "== ncu full (one warm step)"; date +%s
 SB_TUNE_LOAD=$O/tune.txt timeout 500 ncu --set full --clock-control none --profile-from-start off \
-  -f -o $O/r01_step_full python bench.py --steps 1 --warmup 2 --no-cpu-baseline --ncu-step > $O/ncu_full.log 2>&1
+  -f -o $O/${PFX}_step_full python bench.py --steps 1 --warmup 2 --no-cpu-baseline --ncu-step > $O/ncu_full.log 2>&1
 echo "full rc=$?"
-timeout 120 ncu -i $O/r01_step_full.ncu-rep --page raw --csv > $O/r01_step_full_raw.csv 2>/dev/null
+timeout 120 ncu -i $O/${PFX}_step_full.ncu-rep --page raw --csv > $O/${PFX}_step_full_raw.csv 2>/dev/null
 echo "== ncu source-level capture of the top kernel (one launch)"; date +%s
 SB_TUNE_LOAD=$O/tune.txt timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off \
-  -k regex:k_conv_tc_halo -c 2 -f -o $O/r01_top_kernel python bench.py --steps 1 --warmup 2 --no-cpu-baseline --ncu-step > $O/ncu_top.log 2>&1
+  -k regex:k_conv_tc_halo -c 2 -f -o $O/${PFX}_top_kernel python bench.py --steps 1 --warmup 2 --no-cpu-baseline --ncu-step > $O/ncu_top.log 2>&1
 echo "top rc=$?"
-timeout 120 ncu -i $O/r01_top_kernel.ncu-rep --page source --csv > $O/r01_top_kernel_source.csv 2>/dev/null
-timeout 120 ncu -i $O/r01_top_kernel.ncu-rep --page details > $O/r01_top_kernel_details.txt 2>/dev/null
-sz=$(stat -c %s $O/r01_step_full.ncu-rep 2>/dev/null || echo 0)
-if [ "$sz" -gt 35000000 ]; then echo "ncu-rep too big ($sz), keeping CSV only"; rm -f $O/r01_step_full.ncu-rep; fi
+timeout 120 ncu -i $O/${PFX}_top_kernel.ncu-rep --page source --csv > $O/${PFX}_top_kernel_source.csv 2>/dev/null
+timeout 120 ncu -i $O/${PFX}_top_kernel.ncu-rep --page details > $O/${PFX}_top_kernel_details.txt 2>/dev/null
+sz=$(stat -c %s $O/${PFX}_step_full.ncu-rep 2>/dev/null || echo 0)
+if [ "$sz" -gt 35000000 ]; then echo "ncu-rep too big ($sz), keeping CSV only"; rm -f $O/${PFX}_step_full.ncu-rep; fi
 ls -la $O
 echo "== other configs"; date +%s
 timeout 300 python tools/bench_configs.py > $O/configs.jsonl 2> $O/configs.err
