@@ -160,6 +160,94 @@ __global__ void __launch_bounds__(256) k_local_scan(const T* __restrict__ cms, i
   if (threadIdx.x == 0) chunk_cnt[b * n_chunks + chunk] = running;
 }
 
+// EXPERIMENTAL (opt-in, SB_ENABLE_SCAN4=1; not yet run on hardware): the same scan with four consecutive map
+// elements per thread (one 16-byte load, float maps only) and one block barrier per 1024 elements instead of one
+// per 256.  ncu (profiles/r01_step_full_summary.md): k_local_scan moves 27 MB in 60 us = 0.45 TB/s -- it is bound
+// by one scalar load in flight per thread and a __syncthreads_count per 256 elements, not by HBM.  Output (the
+// ordered (flat index, value) list per chunk) is identical: a thread's four elements are consecutive in flat order
+// and threads are ranked in order.
+__global__ void __launch_bounds__(256) k_local_scan4(const float* __restrict__ cms, int H, int W, int C,
+                                                     int rows_per_chunk, int chunk_cap, float threshold,
+                                                     int* __restrict__ chunk_cnt, uint2* __restrict__ chunk_items) {
+  const int chunk = blockIdx.x, b = blockIdx.y, n_chunks = gridDim.x;
+  const int y0 = chunk * rows_per_chunk;
+  const int y1 = min(H, y0 + rows_per_chunk);
+  const int rowlen = W * C;
+  const float* base = cms + (size_t)b * H * rowlen;
+  const int f0 = y0 * rowlen, f1 = y1 * rowlen;
+  uint2* items = chunk_items + ((size_t)b * n_chunks + chunk) * chunk_cap;
+  __shared__ int warp_tot[8];
+  __shared__ int running;
+  if (threadIdx.x == 0) running = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const bool vec_ok = ((((size_t)b * H * rowlen + f0) & 3) == 0) && ((reinterpret_cast<uintptr_t>(cms) & 15) == 0);
+  for (int fbase = f0; fbase < f1; fbase += 1024) {
+    const int f = fbase + 4 * threadIdx.x;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (vec_ok && f + 3 < f1) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(base + f));
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (f + k < f1) v[k] = __ldg(base + f + k);
+    }
+    unsigned mask = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int fk = f + k;
+      if (fk < f1 && v[k] > threshold) {
+        const int y = fk / rowlen;
+        const int r = fk - y * rowlen;
+        const int x = r / C;
+        float m = v[k] - 1.0f;
+        const bool up = y > 0, dn = y < H - 1, lf = x > 0, rt = x < W - 1;
+        const float* q = base + fk;
+        if (up) {
+          if (lf) m = fmaxf(m, __ldg(q - rowlen - C));
+          m = fmaxf(m, __ldg(q - rowlen));
+          if (rt) m = fmaxf(m, __ldg(q - rowlen + C));
+        }
+        if (lf) m = fmaxf(m, __ldg(q - C));
+        if (rt) m = fmaxf(m, __ldg(q + C));
+        if (dn) {
+          if (lf) m = fmaxf(m, __ldg(q + rowlen - C));
+          m = fmaxf(m, __ldg(q + rowlen));
+          if (rt) m = fmaxf(m, __ldg(q + rowlen + C));
+        }
+        if (v[k] > m) mask |= 1u << k;
+      }
+    }
+    const int mine = __popc(mask);
+    const int any = __syncthreads_count(mine != 0);
+    if (any == 0) continue;
+    // exclusive prefix of `mine` over the block, in thread order
+    int incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    int off = running + incl - mine;
+    for (int w = 0; w < wid; ++w) off += warp_tot[w];
+    int block_total = 0;
+    for (int w = 0; w < 8; ++w) block_total += warp_tot[w];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (mask & (1u << k)) {
+        if (off < chunk_cap) items[off] = make_uint2((unsigned)(f + k), __float_as_uint(v[k]));
+        ++off;
+      }
+    __syncthreads();
+    if (threadIdx.x == 0) running += block_total;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) chunk_cnt[b * n_chunks + chunk] = running;
+}
+
 // ------------------------------------------------------------------------------------------
 // Local peaks, pass B: one CTA per sample.  Concatenates the chunk lists in order (= tf.where
 // order), refines each peak, scales it, and builds the per-node (channel) ascending peak lists
@@ -898,9 +986,13 @@ int sbk_local_peaks(sb_handle_s* h, const void* cms, int cms_is_half, const floa
   if (B > ws.B || H != ws.H || W != ws.W || C != ws.C)
     return sb_fail(h, SB_ERR_INVALID, "local peaks: workspace shape mismatch");
   dim3 g(ws.n_chunks, B);
+  static const bool scan4 = getenv("SB_ENABLE_SCAN4") != nullptr;        // experimental vectorised scan (opt-in)
   if (cms_is_half)
     k_local_scan<__half><<<g, 256, 0, h->stream>>>((const __half*)cms, H, W, C, ws.rows_per_chunk,
                                                    ws.chunk_cap, p.threshold, ws.chunk_cnt, ws.chunk_items);
+  else if (scan4)
+    k_local_scan4<<<g, 256, 0, h->stream>>>((const float*)cms, H, W, C, ws.rows_per_chunk, ws.chunk_cap, p.threshold,
+                                            ws.chunk_cnt, ws.chunk_items);
   else
     k_local_scan<float><<<g, 256, 0, h->stream>>>((const float*)cms, H, W, C, ws.rows_per_chunk,
                                                   ws.chunk_cap, p.threshold, ws.chunk_cnt, ws.chunk_items);
