@@ -52,6 +52,16 @@ void sb_models_free(sb_handle_s* h) {
   h->models.clear();
 }
 
+// pinned staging + device frame slots of the submit/collect pipeline are sized from (B, H, W, C, max_instances,
+// n_nodes) at first use: any configure call that may change one of those drops them (re-created lazily)
+static void sb_pipeline_slots_free(SbModel* m) {
+  for (int i = 0; i < 2; ++i) {
+    if (m->frames_slot[i]) { cudaFree(m->frames_slot[i]); m->frames_slot[i] = nullptr; }
+    if (m->stage_host[i]) { cudaFreeHost(m->stage_host[i]); m->stage_host[i] = nullptr; }
+    m->slot_used[i] = false;
+  }
+}
+
 static SbModel* get_model(sb_handle_s* h, int id) {
   if (!h || id < 0 || id >= (int)h->models.size()) return nullptr;
   return h->models[id];
@@ -126,8 +136,16 @@ int sb_model_configure(sb_handle_t h, int model_id, int max_batch, int H, int W,
     if (Hnet % b.stride_den || Wnet % b.stride_den)
       return sb_fail(h, SB_ERR_INVALID, "net input %dx%d not divisible by stride %d (pad_to_stride too small)", Hnet, Wnet, b.stride_den);
   }
+  // a reconfigure invalidates everything sized from the old shape: drain the device first, then drop the
+  // activation buffers, the double-buffer pipeline slots and the predictor workspaces (their configure
+  // calls must be repeated; the C-ABI refuses to run a predictor on a stale workspace)
+  SB_CUDA(h, cudaDeviceSynchronize());
+  h->post_pending = false;
   for (auto& b : m->buffers) { if (b.dev) { cudaFree(b.dev); b.dev = nullptr; } }
   if (m->frames_dev) { cudaFree(m->frames_dev); m->frames_dev = nullptr; }
+  sb_pipeline_slots_free(m);
+  m->configured = false;
+  m->bu_configured = false; m->gl_configured = false; m->ce_configured = false; m->td_configured = false;
   sb_conv_tc_release(m);
   m->B = max_batch; m->Hin = H; m->Win = W; m->Cin = C_in; m->Hres = Hres; m->Wres = Wres; m->Hnet = Hnet; m->Wnet = Wnet;
   size_t total = 0;
@@ -441,6 +459,10 @@ int sb_bottomup_configure(sb_handle_t h, int model_id, const sb_bottomup_params*
     return sb_fail(h, SB_ERR_INVALID, "bad capacities");
   for (int e = 0; e < 2 * p->n_edges; ++e)
     if (p->edges[e] < 0 || p->edges[e] >= p->n_nodes) return sb_fail(h, SB_ERR_INVALID, "edge node index out of range");
+  SB_CUDA(h, cudaDeviceSynchronize());          // in-flight post-processing / result copies still use the old workspace
+  h->post_pending = false;
+  m->bu_configured = false;
+  sb_pipeline_slots_free(m);                      // staging records are sized from max_instances / n_nodes
   sb_post_ws_free(m->ws);
   int rc = sb_post_ws_alloc(h, m->ws, m->B, cb.H, cb.W, cb.C, p->max_peaks_per_sample, p->max_node_peaks, p->max_instances, p->n_edges);
   if (rc) return rc;

@@ -86,6 +86,7 @@ struct SbModel {
   int g_rpc = 1, g_chunks = 1;
   sb_centroid_params ce{};
   bool ce_configured = false;
+  bool td_configured = false;              // fused top-down pipeline (sb_topdown_configure)
 };
 
 int sb_run_ops(sb_handle_s* h, SbModel* m, const void* frames_dev, int frames_are_u8, int B);

@@ -73,13 +73,14 @@ class Instance:
     """Points of one animal: ``numpy()`` -> (n_nodes, 2) float32 with NaN for invisible nodes (instance.py:900-950)."""
 
     def __init__(self, points: np.ndarray, skeleton: Skeleton, track: int = -1, score: float = float("nan"),
-                 point_scores: Optional[np.ndarray] = None, predicted: bool = False):
+                 point_scores: Optional[np.ndarray] = None, predicted: bool = False, tracking_score: float = 0.0):
         self.points = np.asarray(points, np.float32)
         self.skeleton = skeleton
         self.track = track
         self.score = score
         self.point_scores = point_scores
         self.predicted = predicted
+        self.tracking_score = tracking_score
 
     def numpy(self):
         return self.points
@@ -165,6 +166,18 @@ class Labels:
         videos = [json.loads(v.decode() if isinstance(v, (bytes, np.bytes_)) else v) for v in np.atleast_1d(vj)] if len(vj) else []
         frames, inst = f["frames"].read(), f["instances"].read()
         pts, ppts = f["points"].read(), f["pred_points"].read()
+        # hdf5.py:143-155: user points of files older than format 1.1 were saved on a gridline coordinate system;
+        # tracking_score exists from format 1.2 on (:221-224)
+        fid = f["metadata"].attrs.get("format_id") if hasattr(f["metadata"].attrs, "get") else None
+        try:
+            format_id = None if fid is None else float(np.asarray(fid).reshape(-1)[0])
+        except (TypeError, ValueError):
+            format_id = None
+        if (format_id or 0) < 1.1 and len(pts):
+            pts = pts.copy()
+            pts["x"] = pts["x"] - 0.5
+            pts["y"] = pts["y"] - 0.5
+        has_ts = format_id is not None and format_id >= 1.2 and "tracking_score" in (inst.dtype.names or ())
         lfs = []
         for fr in frames:
             ins = []
@@ -177,7 +190,8 @@ class Labels:
                 xy = np.stack([p["x"], p["y"]], -1).astype(np.float32)
                 xy[p["visible"] == 0] = np.nan
                 ins.append(Instance(xy, sk, int(row["track"]), float(row["score"]),
-                                    p["score"].astype(np.float32) if predicted else None, predicted))
+                                    p["score"].astype(np.float32) if predicted else None, predicted,
+                                    float(row["tracking_score"]) if (predicted and has_ts) else 0.0))
             lfs.append(LabeledFrame(int(fr["video"]), int(fr["frame_idx"]), ins))
         tracks = meta.get("tracks", [])
         if "tracks_json" in f:                                   # one '[spawned_on,"name"]' string per track (hdf5.py:150-160)
@@ -256,7 +270,7 @@ def save_file(labels: "Labels", filename: str):
             table.append(rec)
             sk_ind = sk_list.index(ins.skeleton) if ins.skeleton in sk_list else 0
             inst[ii] = (ii, 1 if ins.predicted else 0, fi, sk_ind, ins.track, -1, ins.score if ins.predicted else np.nan, start,
-                        start + len(xy), 0.0)
+                        start + len(xy), float(getattr(ins, "tracking_score", 0.0) or 0.0) if ins.predicted else 0.0)
             ii += 1
     videos = [json.dumps(v, separators=(",", ":")).encode() for v in labels.video_specs]
 
@@ -291,7 +305,8 @@ def labels_from_predictions(frames, skeleton: Skeleton, video_spec: Optional[dic
                     track_ids[id(tr)] = len(tracks)
                     tracks.append([int(getattr(tr, "spawned_on", 0)), str(getattr(tr, "name", f"track_{len(tracks)}"))])
                 ti = track_ids[id(tr)]
-            ins.append(Instance(i.numpy(), skeleton, ti, float(i.score), np.asarray(i.point_confidences, np.float32), True))
+            ins.append(Instance(i.numpy(), skeleton, ti, float(i.score), np.asarray(i.point_confidences, np.float32), True,
+                                float(getattr(i, "tracking_score", 0.0) or 0.0)))
         lfs.append(LabeledFrame(int(fr.video) if isinstance(fr.video, (int, np.integer)) else 0, int(fr.frame_idx), ins))
     return Labels(lfs, [spec], [skeleton], tracks)
 

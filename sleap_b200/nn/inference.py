@@ -249,7 +249,8 @@ class CentroidCrop(InferenceLayer):
             pts, vals, sinds = pts[keep], vals[keep], sinds[keep]
             k = len(keep)
         crop_offsets = (pts - np.float32(self.crop_size / 2)).astype(np.float32)
-        out = dict(centroids=[pts[sinds == s] for s in range(B)], centroid_vals=[vals[sinds == s] for s in range(B)])
+        out = dict(centroids=[pts[sinds == s] for s in range(B)], centroid_vals=[vals[sinds == s] for s in range(B)],
+                   flags=flags)
         if self.return_crops:
             if k > 0:
                 crops = np.zeros((k, self.crop_size, self.crop_size, C), full_imgs.dtype)
@@ -396,7 +397,10 @@ class TopDownInferenceModel(InferenceModel):
         iv, _ = _ragged_to_dense(peaks_out["instance_peak_vals"], (n_nodes,))
         ce, _ = _ragged_to_dense(peaks_out["centroids"], (2,))
         cv, _ = _ragged_to_dense(peaks_out["centroid_vals"], ())
-        return {"centroids": ce, "centroid_vals": cv, "instance_peaks": ip, "instance_peak_vals": iv, "n_valid": nv}
+        out = {"centroids": ce, "centroid_vals": cv, "instance_peaks": ip, "instance_peak_vals": iv, "n_valid": nv}
+        if "flags" in crop_out:
+            out["flags"] = crop_out["flags"]
+        return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -642,7 +646,7 @@ class Predictor:
     @classmethod
     def from_model_paths(cls, model_paths, peak_threshold=0.2, integral_refinement=True, integral_patch_size=5,
                          batch_size=4, resize_input_layer=True, max_instances=None, precision=PRECISION_FP16,
-                         handle=None):
+                         handle=None, **caps):
         """:176-311: dispatch on the head type found in each model's training_config.json."""
         if isinstance(model_paths, str):
             model_paths = [model_paths]
@@ -655,6 +659,7 @@ class Predictor:
             cfgs[next(iter(heads))] = (cfg, d)
         kw = dict(peak_threshold=peak_threshold, integral_refinement=integral_refinement,
                   integral_patch_size=integral_patch_size, batch_size=batch_size, precision=precision, handle=handle)
+        kw.update(caps)
         if "single_instance" in cfgs:
             return SingleInstancePredictor.from_trained_models(cfgs["single_instance"], **kw)
         if "centroid" in cfgs or "centered_instance" in cfgs:
@@ -739,6 +744,8 @@ class Predictor:
                 use_gt = getattr(self, "uses_ground_truth", False)
                 ex = self.inference_model.predict_on_batch(batch if use_gt else batch["image"])
                 ex["frame_ind"], ex["video_ind"] = batch["frame_ind"], batch["video_ind"]
+                ex["image_hw"] = tuple(batch["image"].shape[1:3])
+                self._check_flags(ex)
                 yield ex
             return
         data = self._as_frames(data)
@@ -747,21 +754,50 @@ class Predictor:
         try:
             if hasattr(self.inference_model, "predict_batches"):      # pipelined device loop (upload i+1 || compute i)
                 i0 = 0
-                for ex in self.inference_model.predict_batches(_images_of(data), self.batch_size):
+                imgs_all = _images_of(data)
+                hw = tuple(np.asarray(imgs_all[0]).shape[:2]) if len(imgs_all) else (1, 1)
+                for ex in self.inference_model.predict_batches(imgs_all, self.batch_size):
                     n = len(ex["n_valid"])
                     ex["frame_ind"] = frame_inds(i0, i0 + n)
                     ex["video_ind"] = np.zeros(n, np.int64)
+                    ex["image_hw"] = hw
                     i0 += n
+                    self._check_flags(ex)
                     yield ex
                 return
             for i0, batch in self._batches(data):
                 ex = self.inference_model.predict_on_batch(batch)
                 ex["frame_ind"] = frame_inds(i0, i0 + len(batch))
                 ex["video_ind"] = np.zeros(len(batch), np.int64)
+                ex["image_hw"] = tuple(batch.shape[1:3])
+                self._check_flags(ex)
                 yield ex
         finally:
             if feeder is not None:
                 feeder.close()
+
+    # Device workspaces are capacity bounded (the reference's ragged tensors are not): a frame that hits a cap comes
+    # back truncated with SB_FLAG_* bits set.  ``on_overflow``: "warn" (default), "raise" or "ignore".
+    on_overflow = "warn"
+    _FLAG_NAMES = {1: "max_peaks_per_sample", 2: "max_node_peaks", 4: "max_instances_per_frame"}   # SB_FLAG_* (include/sleap_b200.h)
+
+    def _check_flags(self, ex):
+        fl = ex.get("flags")
+        if fl is None or self.on_overflow == "ignore":
+            return
+        fl = np.asarray(fl)
+        if not fl.any():
+            return
+        bits = int(np.bitwise_or.reduce(fl.astype(np.int64)))
+        names = [n for b, n in self._FLAG_NAMES.items() if bits & b] or [f"flags=0x{bits:x}"]
+        frames = np.asarray(ex.get("frame_ind", np.arange(len(fl))))[fl != 0].tolist()
+        msg = (f"device capacity reached ({', '.join(names)}) on frame(s) {frames[:8]}{'...' if len(frames) > 8 else ''}: "
+               "detections were truncated; raise the corresponding cap (max_peaks_per_sample / max_node_peaks / "
+               "max_instances_per_frame) when constructing the predictor")
+        if self.on_overflow == "raise":
+            raise OverflowError(msg)
+        import warnings
+        warnings.warn(msg, RuntimeWarning, stacklevel=3)
 
     def predict(self, data, make_labels: bool = True):
         """:496-531."""
@@ -797,8 +833,9 @@ class Predictor:
                     return
                 new = self._frames_from_example(ex)
                 if self.tracker is not None:                     # sequential by nature; runs on the consumer thread
+                    hw = tuple(ex.get("image_hw") or (1, 1))
                     for lf in new:
-                        lf.instances = self.tracker.track(lf.instances, t=lf.frame_idx)
+                        lf.instances = self.tracker.track(lf.instances, img_hw=hw, t=lf.frame_idx)
                 frames.extend(new)
 
         t = threading.Thread(target=worker)
@@ -814,6 +851,9 @@ class Predictor:
     def _frames_from_example(self, ex):
         out = []
         scores = ex.get("instance_scores")
+        topdown = scores is None and "centroid_vals" in ex
+        if topdown:                       # top-down: the instance score is the centroid confidence (:2640-2660)
+            scores = ex["centroid_vals"]
         for i in range(len(ex["instance_peaks"])):
             insts = []
             for j in range(ex["instance_peaks"].shape[1]):
@@ -822,7 +862,7 @@ class Predictor:
                     continue   # :3285
                 sc = float(scores[i, j]) if scores is not None else float(np.nansum(ex["instance_peak_vals"][i, j]))
                 insts.append(PredictedInstance.from_numpy(pts, ex["instance_peak_vals"][i, j], sc))
-            mi = getattr(self, "max_instances", None)
+            mi = None if topdown else getattr(self, "max_instances", None)   # top-down caps centroids (:1879-1894) only
             if mi is not None and len(insts) > mi:   # :3297
                 insts = sorted(insts, key=lambda x: x.score, reverse=True)[:mi]
             out.append(LabeledFrame(int(ex["video_ind"][i]), int(ex["frame_ind"][i]), insts))
@@ -875,8 +915,10 @@ class TopDownPredictor(Predictor):
     """sleap/nn/inference.py:2314-2735."""
 
     def __init__(self, centroid_model=None, confmap_model=None, crop_size=160, peak_threshold=0.2,
-                 integral_refinement=True, integral_patch_size=5, batch_size=4, max_instances=None):
+                 integral_refinement=True, integral_patch_size=5, batch_size=4, max_instances=None,
+                 max_peaks_per_sample=256):
         super().__init__(batch_size)
+        self.max_peaks_per_sample = max_peaks_per_sample
         if centroid_model is None and confmap_model is None:
             raise ValueError("Either the centroid or topdown confidence map model must be provided.")   # :2479
         self.centroid_model, self.confmap_model = centroid_model, confmap_model
@@ -898,7 +940,7 @@ class TopDownPredictor(Predictor):
             cc = CentroidCrop(keras_model=cm, crop_size=self.crop_size if im is not None else 1, input_scale=cm.input_scale,
                               pad_to_stride=cm.cm.max_stride, peak_threshold=self.peak_threshold, refinement=ref,
                               integral_patch_size=self.integral_patch_size, max_instances=self.max_instances,
-                              return_crops=im is not None)
+                              return_crops=im is not None, max_peaks_per_sample=self.max_peaks_per_sample)
         if im is None:                                   # ground-truth instances stand in for the instance model
             fp = FindInstancePeaksGroundTruth()
         else:
@@ -920,7 +962,7 @@ class TopDownPredictor(Predictor):
     @classmethod
     def from_trained_models(cls, centroid_model_path=None, confmap_model_path=None, batch_size=4, peak_threshold=0.2,
                             integral_refinement=True, integral_patch_size=5, resize_input_layer=True,
-                            max_instances=None, precision=PRECISION_FP16, handle=None, **_):
+                            max_instances=None, precision=PRECISION_FP16, handle=None, max_peaks_per_sample=256, **_):
         """:2435-2560 (same argument names; paths may also be loaded (config, folder) pairs)."""
         centroid_cfg, confmap_cfg = centroid_model_path, confmap_model_path
         if centroid_cfg is None and confmap_cfg is None:
@@ -934,7 +976,8 @@ class TopDownPredictor(Predictor):
             icfg, _, imodel = cls._load(confmap_cfg, precision, handle, resize_in_graph=False)
             crop = icfg["data"]["instance_cropping"]["crop_size"]
             anchor = icfg["data"]["instance_cropping"].get("center_on_part") if anchor is None else anchor
-        obj = cls(cmodel, imodel, crop, peak_threshold, integral_refinement, integral_patch_size, batch_size, max_instances)
+        obj = cls(cmodel, imodel, crop, peak_threshold, integral_refinement, integral_patch_size, batch_size, max_instances,
+                  max_peaks_per_sample)
         obj.anchor_part = anchor
         return obj
 
@@ -977,14 +1020,18 @@ class BottomUpPredictor(Predictor):
     def from_trained_models(cls, model_path, batch_size=4, peak_threshold=0.2, integral_refinement=True,
                             integral_patch_size=5, max_edge_length_ratio=0.25, dist_penalty_weight=1.0,
                             paf_line_points=10, min_line_scores=0.25, resize_input_layer=True, max_instances=None,
-                            precision=PRECISION_FP16, handle=None, **_):
-        """:3150-3228 (same argument names; ``model_path`` may also be an already loaded (config, folder) pair)."""
+                            precision=PRECISION_FP16, handle=None, max_peaks_per_sample=1024, max_node_peaks=32,
+                            max_instances_per_frame=64, **_):
+        """:3150-3228 (same argument names; ``model_path`` may also be an already loaded (config, folder) pair).
+        ``max_peaks_per_sample`` / ``max_node_peaks`` / ``max_instances_per_frame`` size the device workspaces (the
+        reference's ragged tensors are unbounded); a frame that reaches one is reported through ``on_overflow``."""
         _, spec, model = cls._load(model_path, precision, handle)
         return cls(model, spec["part_names"], spec["edges"], peak_threshold=peak_threshold, batch_size=batch_size,
                    max_edge_length_ratio=max_edge_length_ratio, dist_penalty_weight=dist_penalty_weight,
                    paf_line_points=paf_line_points, min_line_scores=min_line_scores,
                    integral_refinement=integral_refinement, integral_patch_size=integral_patch_size,
-                   max_instances=max_instances)
+                   max_instances=max_instances, max_peaks_per_sample=max_peaks_per_sample, max_node_peaks=max_node_peaks,
+                   max_instances_per_frame=max_instances_per_frame)
 
 
 def load_model(model_path, batch_size=4, peak_threshold=0.2, refinement="integral", **kwargs):

@@ -382,6 +382,41 @@ def test_tc_single_layers(cin, cout, k, hw, variant, monkeypatch):
     assert_allclose(outs, y, atol=2e-3 * max(1.0, np.abs(y).max()), rtol=2e-3)
 
 
+def test_predictor_reconfigures_between_frame_sizes():
+    """One predictor, two videos of different size / batch / capacity (the submit/collect slots and the pinned
+    staging were sized once): results equal a fresh predictor's, in both directions (grow and shrink)."""
+    from sleap_b200.nn.inference import BottomUpPredictor
+    spec = _c4_small()
+    model, w, cm = _mk(spec, 1, 29, precision=0)
+    rng = np.random.default_rng(5)
+    small = rng.integers(0, 256, size=(6, 128, 160, 1), dtype=np.uint8)
+    big = rng.integers(0, 256, size=(5, 256, 320, 1), dtype=np.uint8)
+    thr = float(np.quantile(model.forward(big[:2])[0], 0.9995))
+    kw = dict(peak_threshold=thr, max_peaks_per_sample=4096, max_node_peaks=64)
+
+    def fresh(imgs, bs, cap):
+        m2, _, _ = _mk(spec, 1, 29, precision=0)
+        return BottomUpPredictor(m2, synth.FLIES13_NODES, synth.FLIES13_EDGES, batch_size=bs, max_instances_per_frame=cap, **kw).predict(
+            imgs, make_labels=False)
+
+    pred = BottomUpPredictor(model, synth.FLIES13_NODES, synth.FLIES13_EDGES, batch_size=2, max_instances_per_frame=32, **kw)
+    for imgs, bs, cap in ((small, 2, 32), (big, 4, 32), (small, 2, 32)):
+        pred.batch_size = bs
+        got = pred.predict(imgs, make_labels=False)
+        want = fresh(imgs, bs, cap)
+        assert len(got) == len(want)
+        for g, x in zip(got, want):
+            assert_array_equal(g["n_valid"], x["n_valid"])
+            assert_array_equal(np.nan_to_num(g["instance_peaks"], nan=-1), np.nan_to_num(x["instance_peaks"], nan=-1))
+    # growing the instance capacity re-sizes the staging records as well
+    pred.inference_model.bottomup_layer.max_instances = 128
+    got = pred.predict(big, make_labels=False)
+    want = fresh(big, 4, 128)
+    for g, x in zip(got, want):
+        assert_array_equal(g["n_valid"], x["n_valid"])
+        assert_array_equal(np.nan_to_num(g["instance_peaks"], nan=-1), np.nan_to_num(x["instance_peaks"], nan=-1))
+
+
 def test_pipelined_predict_matches_per_batch():
     """submit/collect double buffering returns exactly what predict_on_batch returns, batch by batch."""
     from sleap_b200.nn.inference import BottomUpPredictor

@@ -124,8 +124,6 @@ def test_topdown_single_model_modes(precision):
         TopDownPredictor.from_trained_models()
 
 
-@pytest.mark.xfail(strict=False, reason="scaled top-down instance models (precrop_resize): device path written after the "
-                   "round's last GPU slot; first executed by the driver. The oracle variant is pinned on CPU.")
 @pytest.mark.parametrize("precision", [1, 0])
 def test_topdown_centered_instance_with_scaling(precision):
     """test_topdown_predictor_centered_instance_with_scaling (:708-729) and

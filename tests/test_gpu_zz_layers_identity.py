@@ -2,15 +2,14 @@
 head) feeds analytic confidence maps straight into CentroidCrop / FindInstancePeaks / SingleInstanceInferenceLayer
 (tests/nn/test_inference.py:213-254, 257-379, 542-589, 1091-1150).  The same tests pass on the oracle layers
 (tests/test_oracle_layers.py).
-
-The identity backbone was added after the round's last GPU slot: xfail(strict=False) until its first device run."""
+"""
 import numpy as np
 import pytest
 from numpy.testing import assert_allclose, assert_array_equal
 
 from oracle import synth
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="identity backbone: first device run pending")]
+pytestmark = pytest.mark.gpu
 
 
 def _model(head, channels, input_scale=1.0):

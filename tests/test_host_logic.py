@@ -72,3 +72,38 @@ def test_spec_from_config_order():
     spec = A.spec_from_config(cfg)
     assert [h["name"] for h in spec["heads"]] == ["MultiInstanceConfmapsHead", "PartAffinityFieldsHead", "OffsetRefinementHead"]
     assert [h["channels"] for h in spec["heads"]] == [2, 2, 4]
+
+
+def test_topdown_instance_score_is_centroid_confidence():
+    """sleap/nn/inference.py:2640-2660: a top-down PredictedInstance's score is the centroid confidence (not the sum of
+    its peak values), and no post-hoc max_instances cut is applied (the cap acts on centroids, :1879-1894)."""
+    import numpy as np
+    from sleap_b200.nn.inference import Predictor
+    p = Predictor()
+    p.max_instances = 1
+    ex = {"instance_peaks": np.asarray([[[[1, 2], [3, 4]], [[5, 6], [7, 8]]]], np.float32),
+          "instance_peak_vals": np.asarray([[[0.9, 0.8], [0.7, 0.6]]], np.float32),
+          "centroid_vals": np.asarray([[0.25, 0.5]], np.float32), "video_ind": np.zeros(1, int), "frame_ind": np.zeros(1, int)}
+    lf = p._frames_from_example(ex)[0]
+    assert [i.score for i in lf.instances] == [0.25, 0.5]
+    # bottom-up keeps its own scores and the max_instances cut (:3297)
+    ex2 = dict(ex, instance_scores=np.asarray([[1.0, 2.0]], np.float32))
+    lf2 = p._frames_from_example(ex2)[0]
+    assert [i.score for i in lf2.instances] == [2.0]
+
+
+def test_overflow_flags_are_reported():
+    import numpy as np
+    import pytest
+    from sleap_b200.nn.inference import Predictor
+    p = Predictor()
+    ex = {"flags": np.asarray([0, 2, 0], np.int32), "frame_ind": np.asarray([10, 11, 12])}
+    with pytest.warns(RuntimeWarning, match="max_node_peaks.*11"):
+        p._check_flags(ex)
+    p.on_overflow = "raise"
+    with pytest.raises(OverflowError):
+        p._check_flags(ex)
+    p.on_overflow = "ignore"
+    p._check_flags(ex)
+    p.on_overflow = "raise"
+    p._check_flags({"flags": np.zeros(3, np.int32)})

@@ -130,3 +130,31 @@ def test_tracked_predictions_round_trip(tmp_path):
     assert back.tracks == [[0, "track_0"], [0, "track_1"]]
     assert [[i.track for i in lf.instances] for lf in back] == [[0, 1]] * 4
     assert h5lite.File(p)["tracks_json"].read()[0] == b'[0,"track_0"]'
+
+
+def test_tracking_score_and_legacy_format(tmp_path):
+    """hdf5.py:143-155, 221-224: tracking_score is carried from format 1.2 on; user points of files older than format 1.1
+    are shifted by -0.5 px on load (predicted points are not)."""
+    sk = L.Skeleton(["a", "b"], [("a", "b")])
+    user = L.Instance(np.asarray([[4.0, 5.0], [6.0, 7.0]], np.float32), sk)
+    pred = L.Instance(np.asarray([[1.5, 2.5], [3.5, 4.5]], np.float32), sk, 0, 0.5, np.asarray([0.9, 0.8], np.float32), True,
+                      tracking_score=0.625)
+    lab = L.Labels([L.LabeledFrame(0, 0, [user, pred])], [{"backend": {"filename": "m.mp4"}}], [sk], [[0, "track_0"]])
+    p = str(tmp_path / "ts.slp")
+    lab.save(p)
+    back = L.Labels.load_file(p)
+    assert back[0][1].predicted and back[0][1].tracking_score == 0.625 and back[0][0].tracking_score == 0.0
+    assert_array_equal(back[0][0].numpy(), user.numpy())
+    # the same tables under a pre-1.1 format id: user points shift, predicted points and tracking_score do not survive
+    f = h5lite.File(p)
+    q = str(tmp_path / "old.slp")
+    with h5write.File(q) as w:
+        g = w.create_group("metadata")
+        g.attrs["format_id"] = np.float64(1.0)
+        g.attrs["json"] = f["metadata"].attrs["json"]
+        for name in ("videos_json", "tracks_json", "suggestions_json", "frames", "instances", "points", "pred_points"):
+            w.create_dataset(name, f[name].read())
+    old = L.Labels.load_file(q)
+    assert_array_equal(old[0][0].numpy(), user.numpy() - np.float32(0.5))
+    assert_array_equal(old[0][1].numpy(), pred.numpy())
+    assert old[0][1].tracking_score == 0.0
