@@ -40,11 +40,19 @@ struct SbPostWs {
   float* inst_scores = nullptr;             // [B][max_instances]
   int* n_inst = nullptr;                    // [B]
   int* flags = nullptr;                     // [B]  overflow bit flags
+  // contiguous per-frame result records written by the grouping kernel's epilogue:
+  // [B][I*C*2 peaks | I*C vals | I scores | n_valid | flags]  (sb_record_width floats per frame)
+  float* records = nullptr;
+  uint2* sorted_items = nullptr;            // [B][max_peaks]  scanned items in tf.where order (k_local_emit scratch)
   int* edges_dev = nullptr;                 // [E][2]
   int* sorted_edges_dev = nullptr;          // [n_sorted]
   int n_sorted = 0;
   size_t bytes = 0;
 };
+
+static inline size_t sb_record_width(int max_instances, int n_nodes) {
+  return (size_t)max_instances * n_nodes * 3 + max_instances + 2;
+}
 
 struct sb_handle_s {
   int device = 0;

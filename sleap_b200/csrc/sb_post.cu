@@ -160,119 +160,183 @@ __global__ void __launch_bounds__(256) k_local_scan(const T* __restrict__ cms, i
   if (threadIdx.x == 0) chunk_cnt[b * n_chunks + chunk] = running;
 }
 
-// EXPERIMENTAL (opt-in, SB_ENABLE_SCAN4=1; not yet run on hardware): the same scan with four consecutive map
-// elements per thread (one 16-byte load, float maps only) and one block barrier per 1024 elements instead of one
-// per 256.  ncu (profiles/r01_step_full_summary.md): k_local_scan moves 27 MB in 60 us = 0.45 TB/s -- it is bound
-// by one scalar load in flight per thread and a __syncthreads_count per 256 elements, not by HBM.  Output (the
-// ordered (flat index, value) list per chunk) is identical: a thread's four elements are consecutive in flat order
-// and threads are ranked in order.
-__global__ void __launch_bounds__(256) k_local_scan4(const float* __restrict__ cms, int H, int W, int C,
-                                                     int rows_per_chunk, int chunk_cap, float threshold,
-                                                     int* __restrict__ chunk_cnt, uint2* __restrict__ chunk_items) {
+// Vectorised scan (float maps whose rows are a multiple of 4 elements): a pure streaming pass, no block barrier.
+// Round 1's k_local_scan moved 27 MB in 60 us (0.45 TB/s): one scalar load in flight per thread and a
+// __syncthreads_count per 256 elements.  Here every thread keeps UN 16-byte loads in flight, elements above the
+// threshold (a fraction of a percent of the map) take the 8-neighbour slow path, and a peak is appended to its
+// chunk's list with one atomicAdd -- the list is therefore UNORDERED inside a chunk; k_local_emit restores the
+// tf.where order by ranking the (unique) flat indices of a chunk.  chunk_cap can never overflow: strict
+// 8-neighbour maxima are at most one per 2x2 block.  chunk_cnt must be zero on entry.
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+template <int UN>
+__global__ void __launch_bounds__(256) k_local_scan_v(const float* __restrict__ cms, int H, int W, int C,
+                                                      int rows_per_chunk, int chunk_cap, float threshold,
+                                                      int* __restrict__ chunk_cnt, uint2* __restrict__ chunk_items) {
   const int chunk = blockIdx.x, b = blockIdx.y, n_chunks = gridDim.x;
   const int y0 = chunk * rows_per_chunk;
   const int y1 = min(H, y0 + rows_per_chunk);
   const int rowlen = W * C;
   const float* base = cms + (size_t)b * H * rowlen;
-  const int f0 = y0 * rowlen, f1 = y1 * rowlen;
+  const int f0 = y0 * rowlen, f1 = y1 * rowlen;          // multiples of 4 (host-checked)
   uint2* items = chunk_items + ((size_t)b * n_chunks + chunk) * chunk_cap;
-  __shared__ int warp_tot[8];
-  __shared__ int running;
-  if (threadIdx.x == 0) running = 0;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const bool vec_ok = ((((size_t)b * H * rowlen + f0) & 3) == 0) && ((reinterpret_cast<uintptr_t>(cms) & 15) == 0);
-  for (int fbase = f0; fbase < f1; fbase += 1024) {
-    const int f = fbase + 4 * threadIdx.x;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (vec_ok && f + 3 < f1) {
-      const float4 q = __ldg(reinterpret_cast<const float4*>(base + f));
-      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-    } else {
+  int* cnt = chunk_cnt + b * n_chunks + chunk;
+  for (int fb = f0 + 4 * (int)threadIdx.x; fb < f1; fb += 4 * 256 * UN) {
+    float4 q[UN];
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (f + k < f1) v[k] = __ldg(base + f + k);
+    for (int u = 0; u < UN; ++u) {
+      const int f = fb + u * 1024;
+      q[u] = (f < f1) ? ldg_stream4(base + f) : make_float4(threshold, threshold, threshold, threshold);
     }
-    unsigned mask = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int fk = f + k;
-      if (fk < f1 && v[k] > threshold) {
+    for (int u = 0; u < UN; ++u) {
+      if (!(fmaxf(fmaxf(q[u].x, q[u].y), fmaxf(q[u].z, q[u].w)) > threshold)) continue;
+      const float vv[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float v = vv[k];
+        if (!(v > threshold)) continue;
+        const int fk = fb + u * 1024 + k;
         const int y = fk / rowlen;
         const int r = fk - y * rowlen;
         const int x = r / C;
-        float m = v[k] - 1.0f;
+        float m = v - 1.0f;                             // centre tap: v + (-1)
         const bool up = y > 0, dn = y < H - 1, lf = x > 0, rt = x < W - 1;
-        const float* q = base + fk;
+        const float* p = base + fk;
         if (up) {
-          if (lf) m = fmaxf(m, __ldg(q - rowlen - C));
-          m = fmaxf(m, __ldg(q - rowlen));
-          if (rt) m = fmaxf(m, __ldg(q - rowlen + C));
+          if (lf) m = fmaxf(m, __ldg(p - rowlen - C));
+          m = fmaxf(m, __ldg(p - rowlen));
+          if (rt) m = fmaxf(m, __ldg(p - rowlen + C));
         }
-        if (lf) m = fmaxf(m, __ldg(q - C));
-        if (rt) m = fmaxf(m, __ldg(q + C));
+        if (lf) m = fmaxf(m, __ldg(p - C));
+        if (rt) m = fmaxf(m, __ldg(p + C));
         if (dn) {
-          if (lf) m = fmaxf(m, __ldg(q + rowlen - C));
-          m = fmaxf(m, __ldg(q + rowlen));
-          if (rt) m = fmaxf(m, __ldg(q + rowlen + C));
+          if (lf) m = fmaxf(m, __ldg(p + rowlen - C));
+          m = fmaxf(m, __ldg(p + rowlen));
+          if (rt) m = fmaxf(m, __ldg(p + rowlen + C));
         }
-        if (v[k] > m) mask |= 1u << k;
+        if (v > m) {
+          const int pos = atomicAdd(cnt, 1);
+          if (pos < chunk_cap) items[pos] = make_uint2((unsigned)fk, __float_as_uint(v));
+        }
       }
     }
-    const int mine = __popc(mask);
-    const int any = __syncthreads_count(mine != 0);
-    if (any == 0) continue;
-    // exclusive prefix of `mine` over the block, in thread order
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Warp-cooperative form of refine_offset: lane s computes patch sample s (the four bilinear taps are its only
+// memory traffic, so the 4 x p*p dependent-looking loads of the scalar routine become one round of independent
+// loads), then every lane replays the SAME sequential accumulation over the samples (shuffle broadcast), i.e. the
+// float operations and their order are those of refine_offset -- results are bit-identical to it.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__device__ void refine_offset_warp(const T* __restrict__ plane, int H, int W, int C, float px, float py, int mode, int p,
+                                   int lane, float* dx, float* dy) {
+  const float Hm1 = (float)(H - 1), Wm1 = (float)(W - 1);
+  const float half = (float)(p - 1) * 0.5f;
+  const float y1 = (py + (float)(-p + 1) * 0.5f) / Hm1;
+  const float x1 = (px + (float)(-p + 1) * 0.5f) / Wm1;
+  const float y2 = (py + (float)(p - 1) * 0.5f) / Hm1;
+  const float x2 = (px + (float)(p - 1) * 0.5f) / Wm1;
+  const float hs = (p > 1) ? ((y2 - y1) * Hm1) / (float)(p - 1) : 0.f;
+  const float wsx = (p > 1) ? ((x2 - x1) * Wm1) / (float)(p - 1) : 0.f;
+  const int n = p * p;
+  float vals[4] = {0.f, 0.f, 0.f, 0.f};                 // samples lane, lane+32, lane+64, lane+96 (p <= 11)
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int sidx = r * 32 + lane;
+    if (sidx >= n) continue;
+    const int i = sidx / p, j = sidx - i * p;
+    const float in_y = (p > 1) ? (y1 * Hm1 + (float)i * hs) : (0.5f * (y1 + y2) * Hm1);
+    const float in_x = (p > 1) ? (x1 * Wm1 + (float)j * wsx) : (0.5f * (x1 + x2) * Wm1);
+    float v = 0.f;
+    if (!(in_y < 0.f || in_y > Hm1) && !(in_x < 0.f || in_x > Wm1)) {
+      const int ty = (int)floorf(in_y), by = (int)ceilf(in_y);
+      const float ly = in_y - (float)ty;
+      const int lx = (int)floorf(in_x), rx = (int)ceilf(in_x);
+      const float xl = in_x - (float)lx;
+      const float tl = ldf(plane + ((size_t)ty * W + lx) * C);
+      const float tr = ldf(plane + ((size_t)ty * W + rx) * C);
+      const float bl = ldf(plane + ((size_t)by * W + lx) * C);
+      const float br = ldf(plane + ((size_t)by * W + rx) * C);
+      const float t = tl + (tr - tl) * xl;
+      const float bt = bl + (br - bl) * xl;
+      v = t + (bt - t) * ly;
+    }
+    vals[r] = v;
+  }
+  if (mode == SB_REFINE_INTEGRAL) {
+    float z = 0.f, sx = 0.f, sy = 0.f;
+    for (int i = 0; i < p; ++i)
+      for (int j = 0; j < p; ++j) {
+        const int sidx = i * p + j;
+        const int r = sidx >> 5;
+        const float mine = r == 0 ? vals[0] : (r == 1 ? vals[1] : (r == 2 ? vals[2] : vals[3]));
+        const float v = __shfl_sync(0xffffffffu, mine, sidx & 31);
+        z += v;
+        sx += ((float)j - half) * v;
+        sy += ((float)i - half) * v;
+      }
+    *dx = sx / z;
+    *dy = sy / z;
+  } else {                                              // 3x3: left (1,0), right (1,2), top (0,1), bottom (2,1)
+    const float left = __shfl_sync(0xffffffffu, vals[0], 3), right = __shfl_sync(0xffffffffu, vals[0], 5);
+    const float top = __shfl_sync(0xffffffffu, vals[0], 1), bottom = __shfl_sync(0xffffffffu, vals[0], 7);
+    const float gx = right - left, gy = bottom - top;
+    *dx = (gx > 0.f ? 0.25f : (gx < 0.f ? -0.25f : gx * 0.f));
+    *dy = (gy > 0.f ? 0.25f : (gy < 0.f ? -0.25f : gy * 0.f));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Local peaks, pass B: one CTA per sample.  (1) block scan of the chunk counts; (2) every scanned item finds its
+// place in tf.where order -- chunks are row ranges (ordered), inside a chunk the rank of its (unique) flat index --
+// and the first max_peaks of them are kept; (3) one warp per kept peak refines it (refine_offset_warp), scales it and
+// stores it; (4) the per-node (channel) ascending peak lists that PAF candidate enumeration needs (stable argsort by
+// channel, paf_grouping.py:106-109): the slot of peak i in its node's list is the number of earlier peaks of that
+// channel.
+// ------------------------------------------------------------------------------------------
+constexpr int EMIT_THREADS = 512;
+
+template <typename T>
+__global__ void __launch_bounds__(EMIT_THREADS) k_local_emit(
+    const T* __restrict__ cms, const float* __restrict__ offsets, int H, int W, int C, int n_chunks,
+    int chunk_cap, int refinement, int patch, float scale, float input_scale, int max_peaks,
+    int max_node_peaks, const int* __restrict__ chunk_cnt, const uint2* __restrict__ chunk_items,
+    uint2* __restrict__ sorted_items /*[B][max_peaks]*/, float* __restrict__ peaks, float* __restrict__ peak_vals,
+    int* __restrict__ peak_ch, int* __restrict__ n_peaks, int* __restrict__ total_peaks, int* __restrict__ node_cnt,
+    int* __restrict__ node_peaks, int* __restrict__ flags) {
+  extern __shared__ int s_prefix[];  // n_chunks + 1
+  const int b = blockIdx.x;
+  __shared__ int s_warp[EMIT_THREADS / 32];
+  __shared__ int s_carry;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int k0 = 0; k0 < n_chunks; k0 += EMIT_THREADS) {         // exclusive block scan of min(cnt, cap)
+    const int k = k0 + threadIdx.x;
+    const int mine = k < n_chunks ? min(chunk_cnt[b * n_chunks + k], chunk_cap) : 0;
     int incl = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const int t = __shfl_up_sync(0xffffffffu, incl, d);
       if (lane >= d) incl += t;
     }
-    if (lane == 31) warp_tot[wid] = incl;
+    if (lane == 31) s_warp[wid] = incl;
     __syncthreads();
-    int off = running + incl - mine;
-    for (int w = 0; w < wid; ++w) off += warp_tot[w];
-    int block_total = 0;
-    for (int w = 0; w < 8; ++w) block_total += warp_tot[w];
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (mask & (1u << k)) {
-        if (off < chunk_cap) items[off] = make_uint2((unsigned)(f + k), __float_as_uint(v[k]));
-        ++off;
-      }
+    int off = s_carry;
+    for (int w = 0; w < wid; ++w) off += s_warp[w];
+    if (k < n_chunks) s_prefix[k] = off + incl - mine;
     __syncthreads();
-    if (threadIdx.x == 0) running += block_total;
+    if (threadIdx.x == EMIT_THREADS - 1) s_carry = off + incl;
+    __syncthreads();
   }
-  __syncthreads();
-  if (threadIdx.x == 0) chunk_cnt[b * n_chunks + chunk] = running;
-}
-
-// ------------------------------------------------------------------------------------------
-// Local peaks, pass B: one CTA per sample.  Concatenates the chunk lists in order (= tf.where
-// order), refines each peak, scales it, and builds the per-node (channel) ascending peak lists
-// that PAF candidate enumeration needs (stable argsort by channel, paf_grouping.py:106-109).
-// ------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256) k_local_emit(
-    const T* __restrict__ cms, const float* __restrict__ offsets, int H, int W, int C, int n_chunks,
-    int chunk_cap, int refinement, int patch, float scale, float input_scale, int max_peaks,
-    int max_node_peaks, const int* __restrict__ chunk_cnt, const uint2* __restrict__ chunk_items,
-    float* __restrict__ peaks, float* __restrict__ peak_vals, int* __restrict__ peak_ch,
-    int* __restrict__ n_peaks, int* __restrict__ total_peaks, int* __restrict__ node_cnt,
-    int* __restrict__ node_peaks, int* __restrict__ flags) {
-  extern __shared__ int s_prefix[];  // n_chunks + 1
-  const int b = blockIdx.x;
-  __shared__ int warp_tot[8];
-  __shared__ int running;
-  if (threadIdx.x == 0) {
-    int acc = 0;
-    for (int k = 0; k < n_chunks; ++k) {
-      s_prefix[k] = acc;
-      acc += min(chunk_cnt[b * n_chunks + k], chunk_cap);
-    }
-    s_prefix[n_chunks] = acc;
-  }
+  if (threadIdx.x == 0) s_prefix[n_chunks] = s_carry;
   __syncthreads();
   const int total = s_prefix[n_chunks];
   const int n = min(total, max_peaks);
@@ -282,13 +346,30 @@ __global__ void __launch_bounds__(256) k_local_emit(
   float* pk = peaks + (size_t)b * max_peaks * 2;
   float* pv = peak_vals + (size_t)b * max_peaks;
   int* pc = peak_ch + (size_t)b * max_peaks;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    int lo = 0, hi = n_chunks - 1;  // largest k with prefix[k] <= i
+  uint2* srt = sorted_items + (size_t)b * max_peaks;
+  // (2) place every item
+  for (int t = threadIdx.x; t < total; t += EMIT_THREADS) {
+    int lo = 0, hi = n_chunks - 1;  // largest k with prefix[k] <= t
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
-      if (s_prefix[mid] <= i) lo = mid; else hi = mid - 1;
+      if (s_prefix[mid] <= t) lo = mid; else hi = mid - 1;
     }
-    const uint2 it = chunk_items[((size_t)b * n_chunks + lo) * chunk_cap + (i - s_prefix[lo])];
+    const uint2* lst = chunk_items + ((size_t)b * n_chunks + lo) * chunk_cap;
+    const int cnt = s_prefix[lo + 1] - s_prefix[lo];
+    const uint2 it = lst[t - s_prefix[lo]];
+    int rank = 0;
+    for (int q = 0; q < cnt; ++q) rank += (lst[q].x < it.x) ? 1 : 0;
+    const int pos = s_prefix[lo] + rank;
+    if (pos < n) {
+      srt[pos] = it;
+      const int r = (int)it.x % rowlen;
+      pc[pos] = r % C;
+    }
+  }
+  __syncthreads();                  // srt / pc written by this CTA are visible to it
+  // (3) one warp per kept peak
+  for (int i = wid; i < n; i += EMIT_THREADS / 32) {
+    const uint2 it = srt[i];
     const int f = (int)it.x;
     const int y = f / rowlen;
     const int r = f - y * rowlen;
@@ -302,8 +383,9 @@ __global__ void __launch_bounds__(256) k_local_emit(
       fy = fy + o[1];
     } else if (refinement != SB_REFINE_NONE) {
       float dx, dy;
-      refine_offset<T>(base + c, H, W, C, fx, fy, refinement,
-                       refinement == SB_REFINE_INTEGRAL ? patch : 3, &dx, &dy);
+      const int pp = refinement == SB_REFINE_INTEGRAL ? patch : 3;
+      if (pp * pp <= 128) refine_offset_warp<T>(base + c, H, W, C, fx, fy, refinement, pp, lane, &dx, &dy);
+      else refine_offset<T>(base + c, H, W, C, fx, fy, refinement, pp, &dx, &dy);
       fx = fx + dx;
       fy = fy + dy;
     }
@@ -313,44 +395,31 @@ __global__ void __launch_bounds__(256) k_local_emit(
       fx = fx / input_scale + 0.5f;
       fy = fy / input_scale + 0.5f;
     }
-    pk[2 * i] = fx;
-    pk[2 * i + 1] = fy;
-    pv[i] = __uint_as_float(it.y);
-    pc[i] = c;
+    if (lane == 0) {
+      pk[2 * i] = fx;
+      pk[2 * i + 1] = fy;
+      pv[i] = __uint_as_float(it.y);
+    }
   }
-  __syncthreads();  // peak_ch written by this CTA is visible to it
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // (4) per-node ascending lists
   if (node_cnt != nullptr) {
-    for (int c = 0; c < C; ++c) {
-      if (threadIdx.x == 0) running = 0;
-      __syncthreads();
-      int* lst = node_peaks + ((size_t)b * C + c) * max_node_peaks;
-      for (int i0 = 0; i0 < n; i0 += blockDim.x) {
-        const int i = i0 + threadIdx.x;
-        const bool hit = (i < n) && (pc[i] == c);
-        const int any = __syncthreads_count(hit);
-        if (any == 0) continue;
-        const unsigned bal = __ballot_sync(0xffffffffu, hit);
-        const int rank = __popc(bal & ((1u << lane) - 1u));
-        if (lane == 0) warp_tot[wid] = __popc(bal);
-        __syncthreads();
-        int off = running;
-        for (int w = 0; w < wid; ++w) off += warp_tot[w];
-        if (hit && off + rank < max_node_peaks) lst[off + rank] = i;
-        __syncthreads();
-        if (threadIdx.x == 0) running += any;
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        node_cnt[b * C + c] = running;
-        if (running > max_node_peaks) flag |= SB_FLAG_NODE_PEAKS_TRUNCATED;
-      }
+    for (int i = threadIdx.x; i < n; i += EMIT_THREADS) {
+      const int c = pc[i];
+      int slot = 0;
+      for (int j = 0; j < i; ++j) slot += (pc[j] == c) ? 1 : 0;
+      if (slot < max_node_peaks) node_peaks[((size_t)b * C + c) * max_node_peaks + slot] = i;
+    }
+    for (int c = threadIdx.x; c < C; c += EMIT_THREADS) {
+      int cnt = 0;
+      for (int j = 0; j < n; ++j) cnt += (pc[j] == c) ? 1 : 0;
+      node_cnt[b * C + c] = cnt;
+      if (cnt > max_node_peaks) atomicOr(&flags[b], SB_FLAG_NODE_PEAKS_TRUNCATED);
     }
   }
   if (threadIdx.x == 0) {
     n_peaks[b] = n;
     total_peaks[b] = total;
-    flags[b] = flag;
+    if (flag) atomicOr(&flags[b], flag);
   }
 }
 
@@ -654,19 +723,38 @@ __global__ void k_lsap_batch(const float* __restrict__ scores, const int* __rest
 __global__ void __launch_bounds__(128) k_group(
     int C, int E, int K, int max_peaks, int max_inst, const int* __restrict__ edges,
     const int* __restrict__ sorted_edges, int n_sorted, const float* __restrict__ peaks,
-    const float* __restrict__ peak_vals, const int* __restrict__ node_cnt,
-    const int* __restrict__ node_peaks, const int* __restrict__ match_cnt,
-    const int* __restrict__ match_src, const int* __restrict__ match_dst,
-    const float* __restrict__ match_score, int min_instance_peaks, float min_line_scores,
+    const float* __restrict__ peak_vals, const int* __restrict__ g_node_cnt,
+    const int* __restrict__ node_peaks, const int* __restrict__ g_match_cnt,
+    const int* __restrict__ g_match_src, const int* __restrict__ g_match_dst,
+    const float* __restrict__ g_match_score, int min_instance_peaks, float min_line_scores,
     float input_scale, float* __restrict__ inst_peaks, float* __restrict__ inst_vals,
-    float* __restrict__ inst_scores, int* __restrict__ n_inst, int* __restrict__ flags) {
+    float* __restrict__ inst_scores, int* __restrict__ n_inst, int* __restrict__ flags,
+    float* __restrict__ records /* [B][max_inst*C*3 + max_inst + 2] or null */) {
   extern __shared__ int s_assign[];  // [C*K] instance id or -1; then [C*K] rank map scratch
   const int b = blockIdx.x;
   int* assign = s_assign;
   int* idrank = s_assign + C * K;    // instance id -> rank (ids < C*K)
   int* order = s_assign + 2 * C * K; // dict insertion sequence of each (node, peak) key
+  // the sequential replay below runs on ONE thread: everything it reads is staged in shared memory first
+  // (round 1 read the match tables from global memory, ~50 us per launch of dependent-load latency)
+  int* node_cnt = s_assign + 3 * C * K;            // [C]
+  int* match_cnt = node_cnt + C;                   // [E]
+  int* match_src = match_cnt + E;                  // [E*K]
+  int* match_dst = match_src + E * K;              // [E*K]
+  float* match_score = reinterpret_cast<float*>(match_dst + E * K);   // [E*K]
+  int* s_edges = reinterpret_cast<int*>(match_score + E * K);         // [2*E]
+  int* s_sorted = s_edges + 2 * E;                                    // [n_sorted <= E]
   __shared__ int s_ninst;
   for (int t = threadIdx.x; t < C * K; t += blockDim.x) { assign[t] = -1; idrank[t] = -1; order[t] = -1; }
+  for (int t = threadIdx.x; t < C; t += blockDim.x) node_cnt[t] = g_node_cnt[b * C + t];
+  for (int t = threadIdx.x; t < E; t += blockDim.x) match_cnt[t] = g_match_cnt[b * E + t];
+  for (int t = threadIdx.x; t < E * K; t += blockDim.x) {
+    match_src[t] = g_match_src[(size_t)b * E * K + t];
+    match_dst[t] = g_match_dst[(size_t)b * E * K + t];
+    match_score[t] = g_match_score[(size_t)b * E * K + t];
+  }
+  for (int t = threadIdx.x; t < 2 * E; t += blockDim.x) s_edges[t] = edges[t];
+  for (int t = threadIdx.x; t < n_sorted; t += blockDim.x) s_sorted[t] = sorted_edges[t];
   float* op = inst_peaks + (size_t)b * max_inst * C * 2;
   float* ov = inst_vals + (size_t)b * max_inst * C;
   float* os = inst_scores + (size_t)b * max_inst;
@@ -678,10 +766,10 @@ __global__ void __launch_bounds__(128) k_group(
     const int n_slots = C * K;
     int seq = 0, cur_max = -1;
     for (int se = 0; se < n_sorted; ++se) {
-      const int e = sorted_edges[se];
-      const int sn = edges[2 * e], dn = edges[2 * e + 1];
-      const int cnt = match_cnt[b * E + e];
-      const size_t mo = ((size_t)b * E + e) * K;
+      const int e = s_sorted[se];
+      const int sn = s_edges[2 * e], dn = s_edges[2 * e + 1];
+      const int cnt = match_cnt[e];
+      const int mo = e * K;
       for (int m = 0; m < cnt; ++m) {
         if (!(match_score[mo + m] >= min_line_scores)) continue;
         const int sid = sn * K + match_src[mo + m], did = dn * K + match_dst[mo + m];
@@ -701,7 +789,7 @@ __global__ void __launch_bounds__(128) k_group(
           bool share = false;
           for (int node = 0; node < C && !share; ++node) {
             bool in_s = false, in_d = false;
-            const int kn = min(node_cnt[b * C + node], K);
+            const int kn = min(node_cnt[node], K);
             for (int k = 0; k < kn; ++k) {
               const int a = assign[node * K + k];
               in_s |= (a == si);
@@ -711,14 +799,14 @@ __global__ void __launch_bounds__(128) k_group(
           }
           if (!share)
             for (int node = 0; node < C; ++node) {
-              const int kn = min(node_cnt[b * C + node], K);
+              const int kn = min(node_cnt[node], K);
               for (int k = 0; k < kn; ++k)
                 if (assign[node * K + k] == di) assign[node * K + k] = si;
             }
           // instance ids can disappear through merges / steals: recompute the running maximum
           cur_max = -1;
           for (int node = 0; node < C; ++node) {
-            const int kn = min(node_cnt[b * C + node], K);
+            const int kn = min(node_cnt[node], K);
             for (int k = 0; k < kn; ++k) cur_max = max(cur_max, assign[node * K + k]);
           }
         }
@@ -743,10 +831,10 @@ __global__ void __launch_bounds__(128) k_group(
     const int keep = min(r, max_inst);
     for (int t = 0; t < keep; ++t) os[t] = 0.f;
     for (int se = 0; se < n_sorted; ++se) {
-      const int e = sorted_edges[se];
-      const int sn = edges[2 * e];
-      const int cnt = match_cnt[b * E + e];
-      const size_t mo = ((size_t)b * E + e) * K;
+      const int e = s_sorted[se];
+      const int sn = s_edges[2 * e];
+      const int cnt = match_cnt[e];
+      const int mo = e * K;
       for (int m = 0; m < cnt; ++m) {
         const float sc = match_score[mo + m];
         if (!(sc >= min_line_scores)) continue;
@@ -770,7 +858,7 @@ __global__ void __launch_bounds__(128) k_group(
     const int rk = idrank[a];
     if (rk >= keep) continue;
     const int node = t / K, k = t - node * K;
-    if (k >= min(node_cnt[b * C + node], K)) continue;
+    if (k >= min(node_cnt[node], K)) continue;
     // two peaks of one node type can land in the same instance (skeletons where a node is the
     // destination of several edges); the reference fills the output in dict insertion order, so the
     // key inserted last wins (paf_grouping.py:973-979)
@@ -787,6 +875,20 @@ __global__ void __launch_bounds__(128) k_group(
     op[((size_t)rk * C + node) * 2] = x;
     op[((size_t)rk * C + node) * 2 + 1] = y;
     ov[(size_t)rk * C + node] = pv[pi];
+  }
+  if (records == nullptr) return;
+  // Epilogue: this frame's fixed-size result record, contiguous -- the ONE thing that leaves the GPU per frame
+  // (single D2H copy) and the unit of the multi-GPU exchange (sb_gather_*): peaks | peak values | instance scores |
+  // n_valid | flags, all float32 (the two counters are small integers, exact in float).
+  __syncthreads();                       // this CTA's op / ov / os writes are visible to all its threads
+  const int n2 = max_inst * C * 2, n1 = max_inst * C;
+  float* rec = records + (size_t)b * (n2 + n1 + max_inst + 2);
+  for (int t = threadIdx.x; t < n2; t += blockDim.x) rec[t] = op[t];
+  for (int t = threadIdx.x; t < n1; t += blockDim.x) rec[n2 + t] = ov[t];
+  for (int t = threadIdx.x; t < max_inst; t += blockDim.x) rec[n2 + n1 + t] = os[t];
+  if (threadIdx.x == 0) {
+    rec[n2 + n1 + max_inst] = (float)keep;
+    rec[n2 + n1 + max_inst + 1] = (float)flags[b];
   }
 }
 
@@ -937,9 +1039,11 @@ int sb_post_ws_alloc(sb_handle_s* h, SbPostWs& ws, int B, int H, int W, int C, i
   ws.B = B; ws.H = H; ws.W = W; ws.C = C;
   ws.max_peaks = max_peaks; ws.max_node_peaks = max_node_peaks; ws.max_instances = max_instances;
   ws.n_edges = n_edges;
-  int target_chunks = (2 * h->sm_count + B - 1) / B;          // >= 2 CTAs per SM over the batch
+  // streaming scan: ~8 CTAs of 256 threads per SM over the batch, each with >= ~16 KB of map to walk
+  int target_chunks = (8 * h->sm_count + B - 1) / B;
   int rpc = (H + target_chunks - 1) / target_chunks;
   if (rpc < 1) rpc = 1;
+  while ((long long)rpc * W * C < 4096 && rpc < H) ++rpc;
   while ((long long)rpc * W * C > 65536 && rpc > 1) rpc = (rpc + 1) / 2;
   ws.rows_per_chunk = rpc;
   ws.n_chunks = (H + rpc - 1) / rpc;
@@ -949,6 +1053,7 @@ int sb_post_ws_alloc(sb_handle_s* h, SbPostWs& ws, int B, int H, int W, int C, i
 #define A(ptr, n) do { if ((rc = sb_dev_alloc(h, &ptr, (size_t)(n))) != 0) return rc; ws.bytes += sizeof(*ptr) * (size_t)(n); } while (0)
   A(ws.chunk_cnt, (size_t)B * ws.n_chunks);
   A(ws.chunk_items, (size_t)B * ws.n_chunks * ws.chunk_cap);
+  A(ws.sorted_items, (size_t)B * max_peaks);
   A(ws.peaks, (size_t)B * max_peaks * 2);
   A(ws.peak_vals, (size_t)B * max_peaks);
   A(ws.peak_ch, (size_t)B * max_peaks);
@@ -965,6 +1070,7 @@ int sb_post_ws_alloc(sb_handle_s* h, SbPostWs& ws, int B, int H, int W, int C, i
     A(ws.inst_vals, (size_t)B * max_instances * C);
     A(ws.inst_scores, (size_t)B * max_instances);
     A(ws.n_inst, B);
+    A(ws.records, (size_t)B * sb_record_width(max_instances, C));
     A(ws.edges_dev, (size_t)E * 2);
     A(ws.sorted_edges_dev, (size_t)E);
   }
@@ -976,7 +1082,7 @@ void sb_post_ws_free(SbPostWs& ws) {
   void* ptrs[] = {ws.chunk_cnt, ws.chunk_items, ws.peaks, ws.peak_vals, ws.peak_ch, ws.n_peaks,
                   ws.total_peaks, ws.flags, ws.node_cnt, ws.node_peaks, ws.score_mat, ws.match_cnt,
                   ws.match_src, ws.match_dst, ws.match_score, ws.inst_peaks, ws.inst_vals,
-                  ws.inst_scores, ws.n_inst, ws.edges_dev, ws.sorted_edges_dev};
+                  ws.inst_scores, ws.n_inst, ws.edges_dev, ws.sorted_edges_dev, ws.sorted_items, ws.records};
   for (void* p : ptrs) if (p) cudaFree(p);
   ws = SbPostWs();
 }
@@ -986,13 +1092,17 @@ int sbk_local_peaks(sb_handle_s* h, const void* cms, int cms_is_half, const floa
   if (B > ws.B || H != ws.H || W != ws.W || C != ws.C)
     return sb_fail(h, SB_ERR_INVALID, "local peaks: workspace shape mismatch");
   dim3 g(ws.n_chunks, B);
-  static const bool scan4 = getenv("SB_ENABLE_SCAN4") != nullptr;        // experimental vectorised scan (opt-in)
+  // zero the per-chunk append counters and the per-frame overflow flags (one memset node each, same stream)
+  SB_CUDA(h, cudaMemsetAsync(ws.chunk_cnt, 0, (size_t)ws.B * ws.n_chunks * sizeof(int), h->stream));
+  SB_CUDA(h, cudaMemsetAsync(ws.flags, 0, (size_t)ws.B * sizeof(int), h->stream));
+  const bool vec_ok = !cms_is_half && ((W * C) % 4 == 0) && ((reinterpret_cast<uintptr_t>(cms) & 15) == 0) &&
+                      !getenv("SB_DISABLE_SCAN_V");
   if (cms_is_half)
     k_local_scan<__half><<<g, 256, 0, h->stream>>>((const __half*)cms, H, W, C, ws.rows_per_chunk,
                                                    ws.chunk_cap, p.threshold, ws.chunk_cnt, ws.chunk_items);
-  else if (scan4)
-    k_local_scan4<<<g, 256, 0, h->stream>>>((const float*)cms, H, W, C, ws.rows_per_chunk, ws.chunk_cap, p.threshold,
-                                            ws.chunk_cnt, ws.chunk_items);
+  else if (vec_ok)
+    k_local_scan_v<4><<<g, 256, 0, h->stream>>>((const float*)cms, H, W, C, ws.rows_per_chunk, ws.chunk_cap, p.threshold,
+                                                ws.chunk_cnt, ws.chunk_items);
   else
     k_local_scan<float><<<g, 256, 0, h->stream>>>((const float*)cms, H, W, C, ws.rows_per_chunk,
                                                   ws.chunk_cap, p.threshold, ws.chunk_cnt, ws.chunk_items);
@@ -1000,14 +1110,14 @@ int sbk_local_peaks(sb_handle_s* h, const void* cms, int cms_is_half, const floa
   const size_t sm = (size_t)(ws.n_chunks + 1) * sizeof(int);
   int* ncnt = ws.n_edges > 0 ? ws.node_cnt : nullptr;
   if (cms_is_half)
-    k_local_emit<__half><<<B, 256, sm, h->stream>>>(
+    k_local_emit<__half><<<B, EMIT_THREADS, sm, h->stream>>>(
         (const __half*)cms, offsets, H, W, C, ws.n_chunks, ws.chunk_cap, p.refinement, p.patch,
-        p.scale, p.input_scale, ws.max_peaks, ws.max_node_peaks, ws.chunk_cnt, ws.chunk_items, ws.peaks,
+        p.scale, p.input_scale, ws.max_peaks, ws.max_node_peaks, ws.chunk_cnt, ws.chunk_items, ws.sorted_items, ws.peaks,
         ws.peak_vals, ws.peak_ch, ws.n_peaks, ws.total_peaks, ncnt, ws.node_peaks, ws.flags);
   else
-    k_local_emit<float><<<B, 256, sm, h->stream>>>(
+    k_local_emit<float><<<B, EMIT_THREADS, sm, h->stream>>>(
         (const float*)cms, offsets, H, W, C, ws.n_chunks, ws.chunk_cap, p.refinement, p.patch,
-        p.scale, p.input_scale, ws.max_peaks, ws.max_node_peaks, ws.chunk_cnt, ws.chunk_items, ws.peaks,
+        p.scale, p.input_scale, ws.max_peaks, ws.max_node_peaks, ws.chunk_cnt, ws.chunk_items, ws.sorted_items, ws.peaks,
         ws.peak_vals, ws.peak_ch, ws.n_peaks, ws.total_peaks, ncnt, ws.node_peaks, ws.flags);
   SB_CHECK_LAUNCH(h);
   return 0;
@@ -1060,7 +1170,8 @@ int sbk_score_match(sb_handle_s* h, const float* pafs, int B, int Hp, int Wp, in
 int sbk_group(sb_handle_s* h, int B, int n_nodes, int min_instance_peaks, float min_line_scores,
               float input_scale, SbPostWs& ws) {
   const int K = ws.max_node_peaks;
-  const size_t sm = (size_t)3 * n_nodes * K * sizeof(int);
+  const int E = ws.n_edges;
+  const size_t sm = ((size_t)3 * n_nodes * K + n_nodes + E + 3 * (size_t)E * K + 3 * E) * sizeof(int);
   if (sm > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return sb_fail(h, SB_ERR_CUDA, "group smem %zu: %s", sm, cudaGetErrorString(e));
@@ -1069,7 +1180,7 @@ int sbk_group(sb_handle_s* h, int B, int n_nodes, int min_instance_peaks, float 
                                      ws.sorted_edges_dev, ws.n_sorted, ws.peaks, ws.peak_vals, ws.node_cnt,
                                      ws.node_peaks, ws.match_cnt, ws.match_src, ws.match_dst, ws.match_score,
                                      min_instance_peaks, min_line_scores, input_scale, ws.inst_peaks,
-                                     ws.inst_vals, ws.inst_scores, ws.n_inst, ws.flags);
+                                     ws.inst_vals, ws.inst_scores, ws.n_inst, ws.flags, ws.records);
   SB_CHECK_LAUNCH(h);
   return 0;
 }
