@@ -92,6 +92,12 @@ struct TcParams {
   // 1: the common epilogue shape (fp16 NHWC output, no BN affine, C_out a multiple of 16 covering the whole
   //    N tile, 32-byte aligned channel slices for the output and the fused pool) runs tc_epilogue_cols_fast
   int epi_mode;
+  // 1: the full-resolution output of this conv has no reader (only its fused 2x2 max-pool is consumed): skip the stores
+  int skip_out;
+  // 1: fp32 head output whose pixels are contiguous (Cout == C of the buffer, plain conv): the epilogue stages each
+  //    warp's 32 pixels in shared memory and writes them back as whole 128-byte lines (round 1: one 4-byte store per
+  //    channel and lane at a 4*Cout-byte stride -> 0.31-0.45 of the layers' HBM floor)
+  int f32_stage;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -237,7 +243,7 @@ __device__ __forceinline__ void tc_epilogue_cols(const TcParams& P, const float*
     __align__(16) __half2 h[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-    if (valid) {
+    if (valid && !P.skip_out) {
       __half* po = reinterpret_cast<__half*>(P.out) + pix * P.out_Ctot + P.out_coff + n0 + c0;
       if (n0 + c0 + 16 <= P.Cout) {
         if (((P.out_Ctot | (P.out_coff + n0)) & 15) == 0) st_global_256(po, h);
@@ -354,6 +360,7 @@ __device__ __forceinline__ void tc_epilogue_acc_fast(const TcParams& P, const fl
     const int py = (y0 >> 1) + ((q * (32 / tw) + lr) >> 1), px = (x0 >> 1) + (lc >> 1);
     pp = reinterpret_cast<__half*>(P.pool_out) + (((size_t)b * P.pool_H + py) * P.pool_W + px) * P.pool_Ctot + P.pool_coff + n0;
   }
+  if (POOL && P.skip_out) valid = false;               // launch-uniform: only the pooled tensor is consumed
   if constexpr (!PIPE) {
     for (int c0 = 0; c0 < P.N; c0 += 16) {
       uint32_t r16[16];
@@ -385,9 +392,52 @@ __device__ __forceinline__ void tc_epilogue_acc_fast(const TcParams& P, const fl
 // tcgen05.wait::ld is paid once per accumulator instead of once per 16 columns.
 // PIPE = false keeps the plain load-wait-store loop: the 16/32-input-channel kernels run 3-4 CTAs per SM and
 // the 16 extra registers of the pipelined form would cost them a resident CTA (80 -> 96 registers).
+// fp32 head epilogue with coalesced stores (P.f32_stage): accumulator -> bias / ReLU / BN -> this warp's private staging
+// tile [32 px][Cout] in shared memory (bank-conflict free for odd Cout, 2-way for Cout = 24) -> per tile row one
+// contiguous run of tw * Cout floats, written 32 lanes x 4 B at a time.
+template <int TWC>
+__device__ __forceinline__ void tc_epilogue_acc_f32_staged(const TcParams& P, const float* __restrict__ s_par, uint32_t taddr,
+                                                           int b, int x0, int y0, int q, int lane) {
+  const int tw = TWC ? TWC : P.tw;
+  const int Cout = P.Cout;
+  float* stage = const_cast<float*>(s_par) + 768 + (size_t)(threadIdx.x >> 5) * 32 * Cout;
+  for (int c0 = 0; c0 < P.N; c0 += 16) {
+    uint32_t r16[16];
+    tc_ld16(taddr + (uint32_t)c0, r16);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int co = c0 + j;
+      if (co < Cout) {
+        float v = __uint_as_float(r16[j]) + s_par[co];
+        if (P.relu) v = fmaxf(v, 0.f);
+        if (P.bn_scale != nullptr) v = v * s_par[P.N + co] + s_par[2 * P.N + co];
+        stage[lane * Cout + co] = v;
+      }
+    }
+  }
+  __syncwarp();
+  const int rows = 32 / tw;
+  const int nv = min(tw, P.W - x0);
+  float* out = reinterpret_cast<float*>(P.out);
+  for (int r = 0; r < rows; ++r) {
+    const int iy = y0 + q * rows + r;
+    if (iy >= P.H || nv <= 0) break;
+    float* dst = out + (((size_t)b * P.out_H + iy) * P.out_W + x0) * (size_t)Cout;
+    const float* src = stage + r * tw * Cout;
+    const int n = nv * Cout;
+    for (int i = lane; i < n; i += 32) dst[i] = src[i];
+  }
+  __syncwarp();                                        // the staging tile is rewritten by this warp's next accumulator
+}
+
 template <int TWC, bool PIPE>
 __device__ __forceinline__ void tc_epilogue_acc(const TcParams& P, const float* __restrict__ s_par, uint32_t taddr, int n0,
                                                 bool valid, size_t pix, int b, int x0, int y0, int q, int lane) {
+  if (P.f32_stage) {                                   // launch-uniform
+    tc_epilogue_acc_f32_staged<TWC>(P, s_par, taddr, b, x0, y0, q, lane);
+    return;
+  }
   if (P.epi_mode == 1) {                               // launch-uniform
     if (P.pool_out != nullptr) tc_epilogue_acc_fast<TWC, PIPE, true>(P, s_par, taddr, n0, valid, pix, b, x0, y0, q, lane);
     else tc_epilogue_acc_fast<TWC, PIPE, false>(P, s_par, taddr, n0, valid, pix, b, x0, y0, q, lane);
@@ -1374,6 +1424,8 @@ struct SbConvTcPlan {
   float* view_bias = nullptr;       // bias replicated over the 8 pixels of a group: [8 * Cout]
   int view_Wg = 0;
   bool view_enabled = true;         // false: the autotuner measured k_conv_first faster for this shape
+  bool out_dead = false;            // nobody reads the full-resolution output (only the fused pool): stores are skipped
+  bool skip_now = false;            // out_dead, unless the caller asked for that buffer (sb_model_forward)
 };
 
 static CUtensorMapSwizzle swz_for(int KC) {
@@ -1410,6 +1462,12 @@ void sb_conv_tc_release(SbModel* m) {
       delete p;
     }
   m->tc_plans.clear();
+}
+
+bool sb_conv_tc_out_dead(const SbModel* m, int buffer_id) {
+  for (size_t oi = 0; oi < m->tc_plans.size(); ++oi)
+    if (m->tc_plans[oi] && m->tc_plans[oi]->out_dead && m->ops[oi].out_buf() == buffer_id) return true;
+  return false;
 }
 
 bool sb_conv_tc_can(const SbModel* m, int op_index) {
@@ -1475,6 +1533,11 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
   if (!getenv("SB_DISABLE_FAST_EPILOGUE") && !ob.f32 && P.bn_scale == nullptr && Cout % 16 == 0 && plan->Cout_pad == Cout &&
       ob.C % 16 == 0 && out_coff % 16 == 0 && (P.pool_out == nullptr || (P.pool_Ctot % 16 == 0 && P.pool_coff % 16 == 0)))
     P.epi_mode = 1;
+  P.f32_stage = 0;
+  if (!getenv("SB_DISABLE_F32_STAGE") && ob.f32 && !view && op.kind() == SB_OPK_CONV && Cout == ob.C && out_coff == 0 &&
+      oy_mul == 1 && ox_mul == 1 && plan->Cout_pad == N && P.pool_out == nullptr)
+    P.f32_stage = 1;
+  const size_t stage_bytes = P.f32_stage ? (size_t)10 * 32 * Cout * sizeof(float) : 0;   // up to 10 warps per CTA
   P.row_bytes = KC * 2;
   P.layout_type = KC == 64 ? 2 : (KC == 32 ? 4 : 6);
   P.a_tx_bytes = P.box_rows * TW * KC * 2;
@@ -1485,10 +1548,10 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
   for (int g = 0; g < n_groups; ++g) total_steps += groups[g].n_taps;
   P.n_a_slots = std::min(3, P.n_chunks * n_groups);
   P.n_b_slots = std::min(4, P.n_chunks * total_steps);
-  while ((size_t)P.n_a_slots * P.a_slot_bytes + (size_t)P.n_b_slots * P.b_slot_bytes > 200 * 1024 && P.n_b_slots > 2) P.n_b_slots--;
-  while ((size_t)P.n_a_slots * P.a_slot_bytes + (size_t)P.n_b_slots * P.b_slot_bytes > 200 * 1024 && P.n_a_slots > 2) P.n_a_slots--;
+  while ((size_t)P.n_a_slots * P.a_slot_bytes + (size_t)P.n_b_slots * P.b_slot_bytes > 200 * 1024 - stage_bytes && P.n_b_slots > 2) P.n_b_slots--;
+  while ((size_t)P.n_a_slots * P.a_slot_bytes + (size_t)P.n_b_slots * P.b_slot_bytes > 200 * 1024 - stage_bytes && P.n_a_slots > 2) P.n_a_slots--;
   L.smem = (size_t)P.n_a_slots * P.a_slot_bytes + (size_t)P.n_b_slots * P.b_slot_bytes + 1024 /*align slack*/ +
-           (size_t)(2 * P.n_a_slots + 2 * P.n_b_slots + 1) * 8 + 64 + 3 * 256 * sizeof(float);
+           (size_t)(2 * P.n_a_slots + 2 * P.n_b_slots + 1) * 8 + 64 + 3 * 256 * sizeof(float) + stage_bytes;
   L.grid = dim3(P.tiles_x * tiles_y, plan->Cout_pad / N, 1 /* z = batch, set at launch */);
   {
     // never let more CTAs become co-resident than TMEM can serve without waiting inside tcgen05.alloc
@@ -1517,7 +1580,7 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
         if (slot_of[wt] < 0) { slot_of[wt] = n_used; used[n_used++] = wt; }
       }
     const size_t w_bytes = (size_t)P.n_chunks * n_used * P.b_slot_bytes;
-    const size_t budget = 196 * 1024;
+    const size_t budget = 196 * 1024 - stage_bytes;
     L.pp_valid = plan->Cout_pad == N;
     {
       TcParams& Q = L.PP;
@@ -1541,7 +1604,7 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
       int c2 = 32;
       while (c2 < ns * N) c2 <<= 1;
       Q.tmem_cols = c2;
-      L.smem_p = w_bytes + (size_t)Q.n_a_slots * P.a_slot_bytes + 1024 + (size_t)(2 * Q.n_a_slots + 2 * 8 + 1) * 8 + 64 + 3 * 256 * sizeof(float);
+      L.smem_p = w_bytes + (size_t)Q.n_a_slots * P.a_slot_bytes + 1024 + (size_t)(2 * Q.n_a_slots + 2 * 8 + 1) * 8 + 64 + 3 * 256 * sizeof(float) + stage_bytes;
       // co-residency the hardware may reach (registers / shared memory); the TMEM demand of that many
       // CTAs must fit the 512 columns of the SM outright, because a CTA that has to wait inside
       // tcgen05.alloc for a neighbour to exit was observed to fault on sm_100a
@@ -1651,7 +1714,7 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
     Hp.a_tx_bytes = box_h * pitch * KC * 2;
     Hp.a_slot_bytes = (Hp.a_tx_bytes + 1023) / 1024 * 1024;
     size_t w_bytes = (size_t)Hp.n_chunks * Hp.n_used_taps * Hp.w_slot_bytes;
-    const size_t budget = 196 * 1024;
+    const size_t budget = 196 * 1024 - stage_bytes;
     Hp.w_stream = 0; Hp.n_w_ring = 0;
     const bool resident_fits = !getenv("SB_DISABLE_PERSISTENT") && w_bytes + 2 * (size_t)Hp.a_slot_bytes <= budget;
     if (!resident_fits || getenv("SB_FORCE_WSTREAM")) {
@@ -1670,7 +1733,7 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
     HC.threads = HC.prog ? 64 + 128 * egroups : 192;
     if (!HC.prog) Hp.epi_groups = 1;
     if (HC.prog && Hp.n_acc < 2) { Hp.epi_groups = 1; HC.threads = 192; }
-    HC.smem = w_bytes + (size_t)Hp.n_a_slots * Hp.a_slot_bytes + 1024 + (size_t)(2 * Hp.n_a_slots + 2 * 8 + 1 + 16) * 8 + 64 + 3 * 256 * sizeof(float);
+    HC.smem = w_bytes + (size_t)Hp.n_a_slots * Hp.a_slot_bytes + 1024 + (size_t)(2 * Hp.n_a_slots + 2 * 8 + 1 + 16) * 8 + 64 + 3 * 256 * sizeof(float) + stage_bytes;
     cudaFuncAttributes fa;
     int occ = 1;
     const void* fn = HC.prog ? (KC == 16 ? (const void*)k_conv_tc_prog<1> : (KC == 32 ? (const void*)k_conv_tc_prog<2> : (const void*)k_conv_tc_prog<4>))
@@ -1963,7 +2026,23 @@ int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m) {
     m->tc_plans[oi] = plan;
     if (op.kind() == SB_OPK_CONV && op.pool_buf() >= 0 && oi + 1 < m->ops.size() &&
         m->ops[oi + 1].kind() == SB_OPK_POOL && (m->ops[oi + 1].flags() & SB_OPF_FUSED_POOL))
-      if (plan->launches[0].P.pool_out != nullptr) m->skip_op[oi + 1] = 1;
+      if (plan->launches[0].P.pool_out != nullptr) {
+        m->skip_op[oi + 1] = 1;
+        // dead-store elimination: with the pool fused, the conv's own output is written only for other readers
+        // (skip connections into the decoder, heads).  The two finest encoder blocks of a UNet with output_stride 4
+        // have none: 268 + 134 MB of stores per 8-frame C4 step.
+        bool read = false;
+        for (size_t oj = 0; oj < m->ops.size() && !read; ++oj) {
+          if (oj == oi || oj == oi + 1) continue;
+          const SbOp& o2 = m->ops[oj];
+          if (o2.kind() == SB_OPK_PREPROCESS) continue;
+          const bool overl_in = o2.in_buf() == op.out_buf() && o2.in_coff() < op.out_coff() + Cout && op.out_coff() < o2.in_coff() + o2.in_C();
+          const bool overl_in2 = o2.kind() == SB_OPK_ADD && o2.in2_buf() == op.out_buf() && o2.in2_coff() < op.out_coff() + Cout &&
+                                 op.out_coff() < o2.in2_coff() + o2.in_C();
+          read = overl_in || overl_in2;
+        }
+        plan->out_dead = !read && !getenv("SB_DISABLE_DEAD_STORE_ELIM");
+      }
   }
   for (size_t oi = 0; oi + 1 < m->ops.size(); ++oi)
     if (m->ops[oi].kind() == SB_OPK_PREPROCESS) {
@@ -1976,10 +2055,11 @@ int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m) {
   return sb_conv_tc_autotune(h, m);
 }
 
-static void launch_variant(sb_handle_s* h, TcLaunch& L, int B, int variant, cudaStream_t stream) {
+static void launch_variant(sb_handle_s* h, TcLaunch& L, int B, int variant, cudaStream_t stream, int skip_out = 0) {
   if (variant >= 2) {
     TcLaunch::Halo& HC = L.halo[variant - 2];
     TcParams P = HC.P;
+    P.skip_out = skip_out;
     P.n_tiles_total = P.tiles_per_img * B;
     const int grid = std::max(1, std::min(P.n_tiles_total, h->sm_count * HC.occ));
     if (getenv("SB_DEBUG_LAUNCH")) fprintf(stderr, "[halo %dx%d] KC=%d N=%d stages=%d cols=%d occ=%d grid=%d slots=%d smem=%zu tiles=%d thr=%d\n", P.sub_x, P.sub_y, P.KC, P.N, P.n_stages, P.tmem_cols, HC.occ, grid, P.n_a_slots, HC.smem, P.n_tiles_total, HC.threads);
@@ -1998,6 +2078,7 @@ static void launch_variant(sb_handle_s* h, TcLaunch& L, int B, int variant, cuda
     }
   } else if (variant == 1) {
     TcParams P = L.PP;
+    P.skip_out = skip_out;
     P.n_tiles_total = P.tiles_per_img * B;
     const int grid = std::max(1, std::min(P.n_tiles_total, h->sm_count * L.occ));
     if (getenv("SB_DEBUG_LAUNCH")) fprintf(stderr, "[persist] KC=%d N=%d stages=%d cols=%d occ=%d grid=%d slots=%d smem=%zu tiles=%d\n", P.KC, P.N, P.n_stages, P.tmem_cols, L.occ, grid, P.n_a_slots, L.smem_p, P.n_tiles_total);
@@ -2009,6 +2090,7 @@ static void launch_variant(sb_handle_s* h, TcLaunch& L, int B, int variant, cuda
   } else {
     dim3 g = L.grid;
     g.z = B;
+    L.P.skip_out = skip_out;
     if (L.mc_cluster) {                 // experimental (SB_ENABLE_MULTICAST): clusters of mc_cluster CTAs along the tile axis
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = g; cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = L.smem; cfg.stream = stream;
@@ -2082,7 +2164,7 @@ int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
         if (!avail(L, v)) continue;
         for (int rep = 0; rep < 3; ++rep) {
           cudaEventRecord(e0, h->stream);
-          launch_variant(h, L, m->B, v, h->stream);
+          launch_variant(h, L, m->B, v, h->stream, plan->out_dead ? 1 : 0);
           const cudaError_t le = cudaGetLastError();         // launch-configuration errors: the variant is unusable
           cudaEventRecord(e1, h->stream);
           cudaError_t e = cudaStreamSynchronize(h->stream);
@@ -2178,6 +2260,7 @@ int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
 
 int sb_conv_tc_launch(sb_handle_s* h, SbModel* m, int op_index, int B) {
   SbConvTcPlan* plan = m->tc_plans[op_index];
+  plan->skip_now = plan->out_dead && !m->keep_dead_stores;
   return launch_plan(h, plan, B, plan->use_fused);
 }
 
@@ -2192,7 +2275,7 @@ static int launch_plan(sb_handle_s* h, SbConvTcPlan* plan, int B, bool fused) {
   const size_t n = plan->launches.size();
   if (n == 1 || getenv("SB_DISABLE_FORK")) {
     for (TcLaunch& L : plan->launches) {
-      launch_variant(h, L, B, L.use_persist, h->stream);
+      launch_variant(h, L, B, L.use_persist, h->stream, plan->skip_now ? 1 : 0);
       SB_CHECK_LAUNCH(h);
     }
     return 0;

@@ -37,6 +37,7 @@ void sb_models_free(sb_handle_s* h) {
     if (m->gpart) cudaFree(m->gpart);
     if (m->gpoints) cudaFree(m->gpoints);
     if (m->gvals) cudaFree(m->gvals);
+    if (m->rec_host) cudaFreeHost(m->rec_host);
     for (int i = 0; i < 2; ++i) {
       if (m->frames_slot[i]) cudaFree(m->frames_slot[i]);
       if (m->stage_host[i]) cudaFreeHost(m->stage_host[i]);
@@ -60,6 +61,7 @@ static void sb_pipeline_slots_free(SbModel* m) {
     if (m->stage_host[i]) { cudaFreeHost(m->stage_host[i]); m->stage_host[i] = nullptr; }
     m->slot_used[i] = false;
   }
+  if (m->rec_host) { cudaFreeHost(m->rec_host); m->rec_host = nullptr; }
 }
 
 static SbModel* get_model(sb_handle_s* h, int id) {
@@ -385,7 +387,11 @@ int sb_model_forward(sb_handle_t h, int model_id, const void* images_host, int i
   if (B <= 0 || B > m->B) return sb_fail(h, SB_ERR_INVALID, "bad batch");
   int rc = upload_frames(h, m, images_host, images_are_u8, B);
   if (rc) return rc;
-  if ((rc = sb_run_ops(h, m, m->frames_dev, images_are_u8, B))) return rc;
+  for (int i = 0; i < n_outputs; ++i)                    // a tensor nobody reads inside the graph is only written on request
+    if (output_buffer_ids[i] >= 0 && sb_conv_tc_out_dead(m, output_buffer_ids[i])) m->keep_dead_stores = true;
+  rc = sb_run_ops(h, m, m->frames_dev, images_are_u8, B);
+  m->keep_dead_stores = false;
+  if (rc) return rc;
   for (int i = 0; i < n_outputs; ++i) {
     const int id = output_buffer_ids[i];
     if (id < 0 || id >= (int)m->buffers.size()) return sb_fail(h, SB_ERR_INVALID, "bad output buffer id %d", id);
@@ -483,6 +489,23 @@ int sb_bottomup_configure(sb_handle_t h, int model_id, const sb_bottomup_params*
   return SB_OK;
 }
 
+static size_t stage_floats(const SbModel* m) {
+  return (size_t)m->B * sb_record_width(m->bu.max_instances, m->bu.n_nodes);
+}
+
+static void unpack_records(const SbModel* m, const float* rec, int B, float* out_instance_peaks, float* out_instance_peak_vals,
+                           float* out_instance_scores, int32_t* out_n_valid, int32_t* out_flags) {
+  const size_t I = m->bu.max_instances, C = m->bu.n_nodes, w = sb_record_width((int)I, (int)C);
+  for (int b = 0; b < B; ++b) {
+    const float* r = rec + (size_t)b * w;
+    memcpy(out_instance_peaks + (size_t)b * I * C * 2, r, I * C * 2 * sizeof(float));
+    memcpy(out_instance_peak_vals + (size_t)b * I * C, r + I * C * 2, I * C * sizeof(float));
+    memcpy(out_instance_scores + (size_t)b * I, r + I * C * 3, I * sizeof(float));
+    out_n_valid[b] = (int32_t)r[I * C * 3 + I];
+    if (out_flags) out_flags[b] = (int32_t)r[I * C * 3 + I + 1];
+  }
+}
+
 static int bottomup_post_kernels(sb_handle_s* h, SbModel* m, int B) {
   const sb_bottomup_params& p = m->bu;
   SbBuffer& cb = m->buffers[p.cms_buffer];
@@ -535,16 +558,13 @@ int sb_infer_bottomup(sb_handle_t h, int model_id, const uint8_t* frames_host, i
   if (rc) return rc;
   if ((rc = sb_run_ops(h, m, m->frames_dev, 1, B))) return rc;
   if ((rc = bottomup_post(h, m, B))) return rc;
-  const sb_bottomup_params& p = m->bu;
-  const size_t I = p.max_instances, C = p.n_nodes;
   cudaStream_t rs = h->post_pending ? h->post_stream : h->stream;
-  SB_CUDA(h, cudaMemcpyAsync(out_instance_peaks, m->ws.inst_peaks, (size_t)B * I * C * 2 * 4, cudaMemcpyDeviceToHost, rs));
-  SB_CUDA(h, cudaMemcpyAsync(out_instance_peak_vals, m->ws.inst_vals, (size_t)B * I * C * 4, cudaMemcpyDeviceToHost, rs));
-  SB_CUDA(h, cudaMemcpyAsync(out_instance_scores, m->ws.inst_scores, (size_t)B * I * 4, cudaMemcpyDeviceToHost, rs));
-  SB_CUDA(h, cudaMemcpyAsync(out_n_valid, m->ws.n_inst, (size_t)B * 4, cudaMemcpyDeviceToHost, rs));
-  if (out_flags) SB_CUDA(h, cudaMemcpyAsync(out_flags, m->ws.flags, (size_t)B * 4, cudaMemcpyDeviceToHost, rs));
+  if (!m->rec_host) SB_CUDA(h, cudaHostAlloc((void**)&m->rec_host, stage_floats(m) * sizeof(float), cudaHostAllocDefault));
+  const size_t w = sb_record_width(m->bu.max_instances, m->bu.n_nodes);
+  SB_CUDA(h, cudaMemcpyAsync(m->rec_host, m->ws.records, (size_t)B * w * sizeof(float), cudaMemcpyDeviceToHost, rs));
   SB_CUDA(h, cudaStreamSynchronize(rs));
   h->post_pending = false;
+  unpack_records(m, m->rec_host, B, out_instance_peaks, out_instance_peak_vals, out_instance_scores, out_n_valid, out_flags);
   return SB_OK;
 }
 
@@ -564,13 +584,10 @@ int sb_get_post_stream(sb_handle_t h, void** out_stream) {
   return SB_OK;
 }
 
+// Splits the per-frame result records (written by k_group's epilogue, ONE D2H copy per batch) into the caller's arrays.
 // Asynchronous, double-buffered variant of sb_infer_bottomup for streaming many batches: submit
 // batch i+1 (its H2D copy runs on a copy stream) while batch i computes, then collect batch i.
 // Layout of the pinned staging record per slot: peaks | vals | scores | n_valid | flags.
-static size_t stage_floats(const SbModel* m) {
-  const size_t I = m->bu.max_instances, C = m->bu.n_nodes;
-  return (size_t)m->B * (I * C * 3 + I + 2);
-}
 
 int sb_bottomup_submit(sb_handle_t h, int model_id, const uint8_t* frames_host, int B, int slot) {
   SbModel* m = get_model(h, model_id);
@@ -600,17 +617,8 @@ int sb_bottomup_submit(sb_handle_t h, int model_id, const uint8_t* frames_host, 
   SB_CUDA(h, cudaEventRecord(m->frames_free_ev[slot], h->stream));
   if ((rc = bottomup_post(h, m, B))) return rc;
   cudaStream_t rs = h->post_pending ? h->post_stream : h->stream;
-  const size_t I = m->bu.max_instances, C = m->bu.n_nodes;
-  float* st = m->stage_host[slot];
-  SB_CUDA(h, cudaMemcpyAsync(st, m->ws.inst_peaks, (size_t)B * I * C * 2 * 4, cudaMemcpyDeviceToHost, rs));
-  st += (size_t)m->B * I * C * 2;
-  SB_CUDA(h, cudaMemcpyAsync(st, m->ws.inst_vals, (size_t)B * I * C * 4, cudaMemcpyDeviceToHost, rs));
-  st += (size_t)m->B * I * C;
-  SB_CUDA(h, cudaMemcpyAsync(st, m->ws.inst_scores, (size_t)B * I * 4, cudaMemcpyDeviceToHost, rs));
-  st += (size_t)m->B * I;
-  SB_CUDA(h, cudaMemcpyAsync(st, m->ws.n_inst, (size_t)B * 4, cudaMemcpyDeviceToHost, rs));
-  st += m->B;
-  SB_CUDA(h, cudaMemcpyAsync(st, m->ws.flags, (size_t)B * 4, cudaMemcpyDeviceToHost, rs));
+  SB_CUDA(h, cudaMemcpyAsync(m->stage_host[slot], m->ws.records,
+                             (size_t)B * sb_record_width(m->bu.max_instances, m->bu.n_nodes) * sizeof(float), cudaMemcpyDeviceToHost, rs));
   SB_CUDA(h, cudaEventRecord(m->result_ev[slot], rs));
   m->slot_used[slot] = true;
   return SB_OK;
@@ -623,13 +631,7 @@ int sb_bottomup_collect(sb_handle_t h, int model_id, int slot, int B, float* out
   if (!m || !m->bu_configured) return sb_fail(h, SB_ERR_INVALID, "bottom-up predictor not configured");
   if (slot < 0 || slot > 1 || !m->slot_used[slot] || B <= 0 || B > m->B) return sb_fail(h, SB_ERR_INVALID, "bad slot / batch");
   SB_CUDA(h, cudaEventSynchronize(m->result_ev[slot]));
-  const size_t I = m->bu.max_instances, C = m->bu.n_nodes;
-  const float* st = m->stage_host[slot];
-  memcpy(out_instance_peaks, st, (size_t)B * I * C * 2 * 4); st += (size_t)m->B * I * C * 2;
-  memcpy(out_instance_peak_vals, st, (size_t)B * I * C * 4); st += (size_t)m->B * I * C;
-  memcpy(out_instance_scores, st, (size_t)B * I * 4); st += (size_t)m->B * I;
-  memcpy(out_n_valid, st, (size_t)B * 4); st += m->B;
-  if (out_flags) memcpy(out_flags, st, (size_t)B * 4);
+  unpack_records(m, m->stage_host[slot], B, out_instance_peaks, out_instance_peak_vals, out_instance_scores, out_n_valid, out_flags);
   return SB_OK;
 }
 

@@ -76,7 +76,8 @@ struct SbModel {
   int guard_op = -1;
   // double-buffered asynchronous pipeline (sb_bottomup_submit / sb_bottomup_collect)
   void* frames_slot[2] = {nullptr, nullptr};
-  float* stage_host[2] = {nullptr, nullptr};     // pinned result staging
+  float* stage_host[2] = {nullptr, nullptr};     // pinned result staging (per-frame records)
+  float* rec_host = nullptr;                     // pinned staging of the synchronous sb_infer_bottomup
   cudaEvent_t h2d_done_ev[2] = {nullptr, nullptr}, frames_free_ev[2] = {nullptr, nullptr}, result_ev[2] = {nullptr, nullptr};
   bool slot_used[2] = {false, false};
   cudaStream_t copy_stream = nullptr;      // first op that overwrites a head buffer the post-processing stream may still read
@@ -86,7 +87,8 @@ struct SbModel {
   int g_rpc = 1, g_chunks = 1;
   sb_centroid_params ce{};
   bool ce_configured = false;
-  bool td_configured = false;              // fused top-down pipeline (sb_topdown_configure)
+  bool td_configured = false;
+  bool keep_dead_stores = false;           // sb_model_forward asked for a tensor whose stores are normally elided              // fused top-down pipeline (sb_topdown_configure)
 };
 
 int sb_run_ops(sb_handle_s* h, SbModel* m, const void* frames_dev, int frames_are_u8, int B);
@@ -95,6 +97,7 @@ int sb_run_ops(sb_handle_s* h, SbModel* m, const void* frames_dev, int frames_ar
 int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m);      // after buffers are allocated
 void sb_conv_tc_release(SbModel* m);
 bool sb_conv_tc_can(const SbModel* m, int op_index);
+bool sb_conv_tc_out_dead(const SbModel* m, int buffer_id);   // its stores are elided unless keep_dead_stores is set
 int sb_conv_tc_launch(sb_handle_s* h, SbModel* m, int op_index, int B);
 
 // first conv fused with the PREPROCESS op before it (sb_model.cu): conv op index or -1
