@@ -94,98 +94,10 @@ struct TcParams {
   int epi_mode;
   // 1: the full-resolution output of this conv has no reader (only its fused 2x2 max-pool is consumed): skip the stores
   int skip_out;
-  // 1: fp32 head output whose pixels are contiguous (Cout == C of the buffer, plain conv): the epilogue stages each
-  //    warp's 32 pixels in shared memory and writes them back as whole 128-byte lines (round 1: one 4-byte store per
-  //    channel and lane at a 4*Cout-byte stride -> 0.31-0.45 of the layers' HBM floor)
-  int f32_stage;
+  int prefetch;                // tiles of look-ahead for the L2 prefetch of the activation boxes (0 = off)
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// one elected lane of a converged warp (elect.sync): lets ptxas predicate the tcgen05 instructions
-// directly instead of building a per-lane uniformisation loop around them
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred = 0;
-  asm volatile(
-      "{\n\t.reg .pred P;\n\t"
-      "elect.sync _|P, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
-  for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it) {
-    if (it > (1u << 24)) {   // never hang the GPU: a lost arrival becomes a launch error
-      printf("[sb_conv_tc] mbarrier timeout tag=%d block=(%d,%d,%d) thread=%d\n", tag, blockIdx.x, blockIdx.y,
-             blockIdx.z, threadIdx.x);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
-                                            int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-
-// K-major swizzled UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout):
-//   [0,14) start address >> 4, [16,30) leading byte offset >> 4, [32,46) stride byte offset >> 4,
-//   [46,48) version = 1 (Blackwell), [61,64) layout type.  SBO = 8 rows x row_bytes.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int row_bytes, int layout_type) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(((8 * row_bytes) >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)layout_type << 61;
-  return d;
-}
-
-// 32-byte (256-bit) global store, sm_100: one full 32 B sector per thread and instruction
-__device__ __forceinline__ void st_global_256(void* p, const __half2 (&h)[8]) {
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(h);
-  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]),
-               "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
-}
+#include "sb_tc_prims.cuh"
 
 // bias / BN scale / BN shift of output channels [n0, n0 + N) -> shared memory (zeros / ones beyond Cout)
 __device__ __forceinline__ void stage_params(const TcParams& P, float* s_par, int n0) {
@@ -196,10 +108,6 @@ __device__ __forceinline__ void stage_params(const TcParams& P, float* s_par, in
     s_par[P.N + i] = (ok && P.bn_scale) ? P.bn_scale[co] : 1.f;
     s_par[2 * P.N + i] = (ok && P.bn_shift) ? P.bn_shift[co] : 0.f;
   }
-}
-
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
 // Shared epilogue: 16 accumulator columns of this thread's pixel -> bias / ReLU / BN -> stores
@@ -392,52 +300,9 @@ __device__ __forceinline__ void tc_epilogue_acc_fast(const TcParams& P, const fl
 // tcgen05.wait::ld is paid once per accumulator instead of once per 16 columns.
 // PIPE = false keeps the plain load-wait-store loop: the 16/32-input-channel kernels run 3-4 CTAs per SM and
 // the 16 extra registers of the pipelined form would cost them a resident CTA (80 -> 96 registers).
-// fp32 head epilogue with coalesced stores (P.f32_stage): accumulator -> bias / ReLU / BN -> this warp's private staging
-// tile [32 px][Cout] in shared memory (bank-conflict free for odd Cout, 2-way for Cout = 24) -> per tile row one
-// contiguous run of tw * Cout floats, written 32 lanes x 4 B at a time.
-template <int TWC>
-__device__ __forceinline__ void tc_epilogue_acc_f32_staged(const TcParams& P, const float* __restrict__ s_par, uint32_t taddr,
-                                                           int b, int x0, int y0, int q, int lane) {
-  const int tw = TWC ? TWC : P.tw;
-  const int Cout = P.Cout;
-  float* stage = const_cast<float*>(s_par) + 768 + (size_t)(threadIdx.x >> 5) * 32 * Cout;
-  for (int c0 = 0; c0 < P.N; c0 += 16) {
-    uint32_t r16[16];
-    tc_ld16(taddr + (uint32_t)c0, r16);
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int co = c0 + j;
-      if (co < Cout) {
-        float v = __uint_as_float(r16[j]) + s_par[co];
-        if (P.relu) v = fmaxf(v, 0.f);
-        if (P.bn_scale != nullptr) v = v * s_par[P.N + co] + s_par[2 * P.N + co];
-        stage[lane * Cout + co] = v;
-      }
-    }
-  }
-  __syncwarp();
-  const int rows = 32 / tw;
-  const int nv = min(tw, P.W - x0);
-  float* out = reinterpret_cast<float*>(P.out);
-  for (int r = 0; r < rows; ++r) {
-    const int iy = y0 + q * rows + r;
-    if (iy >= P.H || nv <= 0) break;
-    float* dst = out + (((size_t)b * P.out_H + iy) * P.out_W + x0) * (size_t)Cout;
-    const float* src = stage + r * tw * Cout;
-    const int n = nv * Cout;
-    for (int i = lane; i < n; i += 32) dst[i] = src[i];
-  }
-  __syncwarp();                                        // the staging tile is rewritten by this warp's next accumulator
-}
-
 template <int TWC, bool PIPE>
 __device__ __forceinline__ void tc_epilogue_acc(const TcParams& P, const float* __restrict__ s_par, uint32_t taddr, int n0,
                                                 bool valid, size_t pix, int b, int x0, int y0, int q, int lane) {
-  if (P.f32_stage) {                                   // launch-uniform
-    tc_epilogue_acc_f32_staged<TWC>(P, s_par, taddr, b, x0, y0, q, lane);
-    return;
-  }
   if (P.epi_mode == 1) {                               // launch-uniform
     if (P.pool_out != nullptr) tc_epilogue_acc_fast<TWC, PIPE, true>(P, s_par, taddr, n0, valid, pix, b, x0, y0, q, lane);
     else tc_epilogue_acc_fast<TWC, PIPE, false>(P, s_par, taddr, n0, valid, pix, b, x0, y0, q, lane);
@@ -785,7 +650,16 @@ __global__ void __launch_bounds__(192) k_conv_tc_persist(const __grid_constant__
                     P.used_taps[u]);
     int sa = 0;
     uint32_t pha = 0;
+    auto prefetch_tile = [&](int t) {
+      if (t >= P.n_tiles_total) return;
+      const int b = t / P.tiles_per_img, r = t - b * P.tiles_per_img;
+      const int y0 = (r / P.tiles_x) * TH, x0 = (r % P.tiles_x) * TW;
+      for (int ch = 0; ch < P.n_chunks; ++ch)
+        for (int g = 0; g < P.n_groups; ++g) tma_prefetch_4d(&mapA, ch * P.KC, x0 + P.groups[g].dx, y0 + P.dy0, b);
+    };
+    for (int k = 0; k < P.prefetch; ++k) prefetch_tile(blockIdx.x + k * gridDim.x);
     for (int t = blockIdx.x; t < P.n_tiles_total; t += gridDim.x) {
+      if (P.prefetch) prefetch_tile(t + P.prefetch * gridDim.x);
       const int b = t / P.tiles_per_img, r = t - b * P.tiles_per_img;
       const int y0 = (r / P.tiles_x) * TH, x0 = (r % P.tiles_x) * TW;
       for (int ch = 0; ch < P.n_chunks; ++ch)
@@ -954,9 +828,17 @@ __global__ void __launch_bounds__(192) k_conv_tc_halo(const __grid_constant__ CU
                     P.used_taps[u]);
     int sa = 0;
     uint32_t pha = 0;
-    TileIter it;
+    TileIter it, pf;
     it.init(blockIdx.x, gridDim.x, P.tiles_x, P.tiles_per_img / P.tiles_x);
+    pf = it;
+    int tp = blockIdx.x;                               // prefetch cursor: P.prefetch tiles ahead of the load cursor
+    for (int k = 0; k < P.prefetch && tp < P.n_tiles_total; ++k, tp += gridDim.x, pf.next())
+      for (int ch = 0; ch < P.n_chunks; ++ch) tma_prefetch_4d(&mapA, ch * P.KC, pf.tx * TWH + P.dx0, pf.ty * THH + P.dy0, pf.b);
     for (int t = blockIdx.x; t < P.n_tiles_total; t += gridDim.x, it.next()) {
+      if (P.prefetch && tp < P.n_tiles_total) {
+        for (int ch = 0; ch < P.n_chunks; ++ch) tma_prefetch_4d(&mapA, ch * P.KC, pf.tx * TWH + P.dx0, pf.ty * THH + P.dy0, pf.b);
+        tp += gridDim.x; pf.next();
+      }
       const int b = it.b, y0 = it.ty * THH, x0 = it.tx * TWH;
       for (int ch = 0; ch < P.n_chunks; ++ch) {
         mbar_wait(smem_u32(emptyA + sa), pha ^ 1, 21);
@@ -1119,9 +1001,17 @@ __global__ void __launch_bounds__(320) k_conv_tc_prog(const __grid_constant__ CU
     }
     int sa = 0, sw = 0;
     uint32_t pha = 0, phw = 0;
-    TileIter it;
+    TileIter it, pf;
     it.init(blockIdx.x, gridDim.x, P.tiles_x, P.tiles_per_img / P.tiles_x);
+    pf = it;
+    int tp = blockIdx.x;                               // prefetch cursor: P.prefetch tiles ahead of the load cursor
+    for (int k = 0; k < P.prefetch && tp < P.n_tiles_total; ++k, tp += gridDim.x, pf.next())
+      for (int ch = 0; ch < P.n_chunks; ++ch) tma_prefetch_4d(&mapA, ch * P.KC, pf.tx * TWH + P.dx0, pf.ty * THH + P.dy0, pf.b);
     for (int t = blockIdx.x; t < P.n_tiles_total; t += gridDim.x, it.next()) {
+      if (P.prefetch && tp < P.n_tiles_total) {
+        for (int ch = 0; ch < P.n_chunks; ++ch) tma_prefetch_4d(&mapA, ch * P.KC, pf.tx * TWH + P.dx0, pf.ty * THH + P.dy0, pf.b);
+        tp += gridDim.x; pf.next();
+      }
       const int b = it.b, y0 = it.ty * THH, x0 = it.tx * TWH;
       for (int ch = 0; ch < P.n_chunks; ++ch) {
         mbar_wait(smem_u32(emptyA + sa), pha ^ 1, 21);
@@ -1533,11 +1423,6 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
   if (!getenv("SB_DISABLE_FAST_EPILOGUE") && !ob.f32 && P.bn_scale == nullptr && Cout % 16 == 0 && plan->Cout_pad == Cout &&
       ob.C % 16 == 0 && out_coff % 16 == 0 && (P.pool_out == nullptr || (P.pool_Ctot % 16 == 0 && P.pool_coff % 16 == 0)))
     P.epi_mode = 1;
-  P.f32_stage = 0;
-  if (!getenv("SB_DISABLE_F32_STAGE") && ob.f32 && !view && op.kind() == SB_OPK_CONV && Cout == ob.C && out_coff == 0 &&
-      oy_mul == 1 && ox_mul == 1 && plan->Cout_pad == N && P.pool_out == nullptr)
-    P.f32_stage = 1;
-  const size_t stage_bytes = P.f32_stage ? (size_t)10 * 32 * Cout * sizeof(float) : 0;   // up to 10 warps per CTA
   P.row_bytes = KC * 2;
   P.layout_type = KC == 64 ? 2 : (KC == 32 ? 4 : 6);
   P.a_tx_bytes = P.box_rows * TW * KC * 2;
@@ -1548,10 +1433,10 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
   for (int g = 0; g < n_groups; ++g) total_steps += groups[g].n_taps;
   P.n_a_slots = std::min(3, P.n_chunks * n_groups);
   P.n_b_slots = std::min(4, P.n_chunks * total_steps);
-  while ((size_t)P.n_a_slots * P.a_slot_bytes + (size_t)P.n_b_slots * P.b_slot_bytes > 200 * 1024 - stage_bytes && P.n_b_slots > 2) P.n_b_slots--;
-  while ((size_t)P.n_a_slots * P.a_slot_bytes + (size_t)P.n_b_slots * P.b_slot_bytes > 200 * 1024 - stage_bytes && P.n_a_slots > 2) P.n_a_slots--;
+  while ((size_t)P.n_a_slots * P.a_slot_bytes + (size_t)P.n_b_slots * P.b_slot_bytes > 200 * 1024 && P.n_b_slots > 2) P.n_b_slots--;
+  while ((size_t)P.n_a_slots * P.a_slot_bytes + (size_t)P.n_b_slots * P.b_slot_bytes > 200 * 1024 && P.n_a_slots > 2) P.n_a_slots--;
   L.smem = (size_t)P.n_a_slots * P.a_slot_bytes + (size_t)P.n_b_slots * P.b_slot_bytes + 1024 /*align slack*/ +
-           (size_t)(2 * P.n_a_slots + 2 * P.n_b_slots + 1) * 8 + 64 + 3 * 256 * sizeof(float) + stage_bytes;
+           (size_t)(2 * P.n_a_slots + 2 * P.n_b_slots + 1) * 8 + 64 + 3 * 256 * sizeof(float);
   L.grid = dim3(P.tiles_x * tiles_y, plan->Cout_pad / N, 1 /* z = batch, set at launch */);
   {
     // never let more CTAs become co-resident than TMEM can serve without waiting inside tcgen05.alloc
@@ -1580,7 +1465,7 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
         if (slot_of[wt] < 0) { slot_of[wt] = n_used; used[n_used++] = wt; }
       }
     const size_t w_bytes = (size_t)P.n_chunks * n_used * P.b_slot_bytes;
-    const size_t budget = 196 * 1024 - stage_bytes;
+    const size_t budget = 196 * 1024;
     L.pp_valid = plan->Cout_pad == N;
     {
       TcParams& Q = L.PP;
@@ -1604,7 +1489,7 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
       int c2 = 32;
       while (c2 < ns * N) c2 <<= 1;
       Q.tmem_cols = c2;
-      L.smem_p = w_bytes + (size_t)Q.n_a_slots * P.a_slot_bytes + 1024 + (size_t)(2 * Q.n_a_slots + 2 * 8 + 1) * 8 + 64 + 3 * 256 * sizeof(float) + stage_bytes;
+      L.smem_p = w_bytes + (size_t)Q.n_a_slots * P.a_slot_bytes + 1024 + (size_t)(2 * Q.n_a_slots + 2 * 8 + 1) * 8 + 64 + 3 * 256 * sizeof(float);
       // co-residency the hardware may reach (registers / shared memory); the TMEM demand of that many
       // CTAs must fit the 512 columns of the SM outright, because a CTA that has to wait inside
       // tcgen05.alloc for a neighbour to exit was observed to fault on sm_100a
@@ -1714,7 +1599,7 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
     Hp.a_tx_bytes = box_h * pitch * KC * 2;
     Hp.a_slot_bytes = (Hp.a_tx_bytes + 1023) / 1024 * 1024;
     size_t w_bytes = (size_t)Hp.n_chunks * Hp.n_used_taps * Hp.w_slot_bytes;
-    const size_t budget = 196 * 1024 - stage_bytes;
+    const size_t budget = 196 * 1024;
     Hp.w_stream = 0; Hp.n_w_ring = 0;
     const bool resident_fits = !getenv("SB_DISABLE_PERSISTENT") && w_bytes + 2 * (size_t)Hp.a_slot_bytes <= budget;
     if (!resident_fits || getenv("SB_FORCE_WSTREAM")) {
@@ -1733,7 +1618,7 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
     HC.threads = HC.prog ? 64 + 128 * egroups : 192;
     if (!HC.prog) Hp.epi_groups = 1;
     if (HC.prog && Hp.n_acc < 2) { Hp.epi_groups = 1; HC.threads = 192; }
-    HC.smem = w_bytes + (size_t)Hp.n_a_slots * Hp.a_slot_bytes + 1024 + (size_t)(2 * Hp.n_a_slots + 2 * 8 + 1 + 16) * 8 + 64 + 3 * 256 * sizeof(float) + stage_bytes;
+    HC.smem = w_bytes + (size_t)Hp.n_a_slots * Hp.a_slot_bytes + 1024 + (size_t)(2 * Hp.n_a_slots + 2 * 8 + 1 + 16) * 8 + 64 + 3 * 256 * sizeof(float);
     cudaFuncAttributes fa;
     int occ = 1;
     const void* fn = HC.prog ? (KC == 16 ? (const void*)k_conv_tc_prog<1> : (KC == 32 ? (const void*)k_conv_tc_prog<2> : (const void*)k_conv_tc_prog<4>))
@@ -2055,11 +1940,18 @@ int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m) {
   return sb_conv_tc_autotune(h, m);
 }
 
+// look-ahead (in tiles of a CTA's own sequence) of the activation-box L2 prefetch in the persistent kernels
+static int tc_prefetch_dist() {
+  static const int d = getenv("SB_PREFETCH_DIST") ? atoi(getenv("SB_PREFETCH_DIST")) : 4;
+  return d < 0 ? 0 : (d > 32 ? 32 : d);
+}
+
 static void launch_variant(sb_handle_s* h, TcLaunch& L, int B, int variant, cudaStream_t stream, int skip_out = 0) {
   if (variant >= 2) {
     TcLaunch::Halo& HC = L.halo[variant - 2];
     TcParams P = HC.P;
     P.skip_out = skip_out;
+    P.prefetch = tc_prefetch_dist();
     P.n_tiles_total = P.tiles_per_img * B;
     const int grid = std::max(1, std::min(P.n_tiles_total, h->sm_count * HC.occ));
     if (getenv("SB_DEBUG_LAUNCH")) fprintf(stderr, "[halo %dx%d] KC=%d N=%d stages=%d cols=%d occ=%d grid=%d slots=%d smem=%zu tiles=%d thr=%d\n", P.sub_x, P.sub_y, P.KC, P.N, P.n_stages, P.tmem_cols, HC.occ, grid, P.n_a_slots, HC.smem, P.n_tiles_total, HC.threads);
@@ -2079,6 +1971,7 @@ static void launch_variant(sb_handle_s* h, TcLaunch& L, int B, int variant, cuda
   } else if (variant == 1) {
     TcParams P = L.PP;
     P.skip_out = skip_out;
+    P.prefetch = tc_prefetch_dist();
     P.n_tiles_total = P.tiles_per_img * B;
     const int grid = std::max(1, std::min(P.n_tiles_total, h->sm_count * L.occ));
     if (getenv("SB_DEBUG_LAUNCH")) fprintf(stderr, "[persist] KC=%d N=%d stages=%d cols=%d occ=%d grid=%d slots=%d smem=%zu tiles=%d\n", P.KC, P.N, P.n_stages, P.tmem_cols, L.occ, grid, P.n_a_slots, L.smem_p, P.n_tiles_total);
