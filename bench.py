@@ -384,11 +384,24 @@ def run_ours(args):
     out0 = pred.inference_model.predict_on_batch(host[0].numpy())          # configures everything
     n_inst_mean = float(np.mean(out0["n_valid"]))
     I, C = layer.max_instances, 13
-    ptrs = [c_void_p() for _ in range(5)]
-    handle.call("sb_bottomup_device_outputs", model.model_id, *[byref(p) for p in ptrs])
     from sleap_b200 import parallel
-    gather_out = (torch.empty((world * B, parallel.record_width(I, C)), dtype=torch.float32, device="cuda")
-                  if world > 1 else None)
+    # The path's one exchange step (N > 1).  Default: the grouping kernel's epilogue stores every frame's record into every
+    # rank's gather window over NVLink peer memory (sb_gather_*; no collective call in the step).  SB_EXCHANGE=nccl, or a box
+    # where CUDA IPC peer mappings are not available, falls back to one ncclAllGather of the same records per step.
+    pg, exchange = None, "none (1 GPU)"
+    gather_out = None
+    if world > 1:
+        if os.environ.get("SB_EXCHANGE", "p2p") == "p2p":
+            try:
+                pg = parallel.PeerGather(model, generations=8)
+                exchange = "peer-memory stores from the grouping kernel's epilogue (CUDA IPC over NVLink), 8 generations, device consumer lag 2"
+            except Exception as e:
+                sys.stderr.write(f"[bench] peer-memory exchange unavailable, using NCCL: {e}\n")
+                exchange = f"ncclAllGather of the device records (peer-memory exchange unavailable: {str(e)[:80]})"
+        else:
+            exchange = "ncclAllGather of the device records (SB_EXCHANGE=nccl)"
+        if pg is None:
+            gather_out = torch.empty((world * B, parallel.record_width(I, C)), dtype=torch.float32, device="cuda")
 
     def as_tensor(p, shape, typestr):
         """torch view of a library-owned device buffer (plain pointer -> __cuda_array_interface__)."""
@@ -398,15 +411,14 @@ def run_ours(args):
         v.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (p.value, False), "version": 2}
         return torch.as_tensor(v, device="cuda")
 
-    t_peaks = as_tensor(ptrs[0], (B, I, C, 2), "<f4")
-    t_vals = as_tensor(ptrs[1], (B, I, C), "<f4")
-    t_scores = as_tensor(ptrs[2], (B, I), "<f4")
-    t_nvalid = as_tensor(ptrs[3], (B,), "<i4")
+    rec_ptr = c_void_p()
+    handle.call("sb_bottomup_device_records", model.model_id, byref(rec_ptr))
+    t_rec = as_tensor(rec_ptr, (B, parallel.record_width(I, C)), "<f4")      # written by the grouping kernel's epilogue
 
     def gather_step():
-        # the path's one exchange step: fixed-size instance records of every frame to every rank
-        rec = parallel.pack_records(t_peaks, t_vals, t_scores, t_nvalid)
-        parallel.all_gather_records(rec, gather_out)
+        parallel.all_gather_records(t_rec, gather_out)                        # NCCL fallback: zero torch ops besides the collective
+
+    EX_LAG = 2
 
     post_ptr = c_void_p()
     handle.call("sb_get_post_stream", byref(post_ptr))
@@ -415,9 +427,17 @@ def run_ours(args):
     def step_device(i):
         with torch.cuda.stream(stream):
             handle.call("sb_infer_bottomup_dev", model.model_id, c_void_p(dev[i % n_sets].data_ptr()), B)
-        if world > 1:
+        if pg is not None:
+            if pg.pushed() - pg.consumed > EX_LAG:                # device consumer: all ranks' records of step (now - 2)
+                pg.consume_next_dev()
+        elif world > 1:
             with torch.cuda.stream(post_stream):                  # queued behind this step's grouping kernel
                 gather_step()
+
+    def drain_exchange():
+        if pg is not None:
+            while pg.consumed < pg.pushed():
+                pg.consume_next_dev()
 
     def barrier():
         torch.cuda.synchronize()
@@ -428,6 +448,7 @@ def run_ours(args):
     # ---------------- device-resident throughput ("value") ----------------
     for i in range(args.warmup):
         step_device(i)
+    drain_exchange()
     barrier()
     if args.ncu_step:
         # `ncu --profile-from-start off ... bench.py --ncu-step --steps K`: exactly K warm steps inside the
@@ -435,6 +456,7 @@ def run_ours(args):
         torch.cuda.profiler.start()
         for i in range(args.steps):
             step_device(args.warmup + i)
+        drain_exchange()
         barrier()
         torch.cuda.profiler.stop()
         return
@@ -449,6 +471,7 @@ def run_ours(args):
         ev0.record(stream)
     for i in range(args.steps):
         step_device(i)
+    drain_exchange()                                              # every step's records are consumed inside the timed region
     stream.wait_stream(post_stream)                               # last step's post-processing (+ gather) is inside the timing
     with torch.cuda.stream(stream):
         ev1.record(stream)
@@ -475,6 +498,7 @@ def run_ours(args):
             ev0.record(stream)
         for i in range(n_sus):
             step_device(i)
+        drain_exchange()
         stream.wait_stream(post_stream)
         with torch.cuda.stream(stream):
             ev1.record(stream)
@@ -500,13 +524,15 @@ def run_ours(args):
         barrier()
         t0 = time.perf_counter()
         outs = pred.predict(big_np, make_labels=False)
-        if world > 1:
+        if world > 1 and pg is None:                             # NCCL fallback: one all-gather of the K steps' records
             recs = torch.cat([parallel.pack_records(*[torch.from_numpy(np.ascontiguousarray(
                 np.pad(o[k], [(0, 0), (0, I - o[k].shape[1])] + [(0, 0)] * (o[k].ndim - 2), constant_values=np.nan)))
                 for k in ("instance_peaks", "instance_peak_vals", "instance_scores")] + [torch.from_numpy(o["n_valid"].astype(np.int32))])
                 for o in outs]).cuda()
             with torch.cuda.stream(stream):
                 parallel.all_gather_records(recs)
+        elif pg is not None:                                     # peer-memory exchange: predict() collected every step's records
+            assert all(o["gathered_records"].shape[0] == world * B for o in outs)
         barrier()
         return time.perf_counter() - t0, outs
 
@@ -629,7 +655,7 @@ def run_ours(args):
                        "frames_per_gpu_per_step": B, "global_batch": world * B, "parallelism": f"frame-shard x{world}",
                        "gflop_per_frame": GFLOP_PER_FRAME,
                        "l2": "3 rotating input batches; per-step activation working set ~2.9 GB >> 126 MB L2",
-                       "accumulate": "fp32", "head_outputs": "fp32", "mean_instances_per_frame": n_inst_mean,
+                       "accumulate": "fp32", "head_outputs": "fp32", "mean_instances_per_frame": n_inst_mean, "exchange": exchange,
                        "heads_calibrated_to_peaks_per_channel": TARGET_PEAKS_PER_CHANNEL},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * H * W, "d2h_bytes_per_step": d2h,

@@ -210,6 +210,9 @@ int sb_get_post_stream(sb_handle_t h, void** out_stream);
 int sb_bottomup_device_outputs(sb_handle_t h, int model_id, float** instance_peaks_dev,
                                float** instance_peak_vals_dev, float** instance_scores_dev,
                                int32_t** n_valid_dev, int32_t** flags_dev);
+/* Device pointer of the contiguous per-frame result records the grouping kernel writes ([max_batch][width] float32,
+ * width = ceil4(max_instances*n_nodes*3 + max_instances + 2): peaks | peak values | instance scores | n_valid | flags). */
+int sb_bottomup_device_records(sb_handle_t h, int model_id, float** records_dev);
 /* PAF graph of the last bottom-up call (return_paf_graph, inference.py:2995-3001); same layout
  * as sb_find_local_peaks / sb_score_paf_lines_batch outputs. */
 int sb_bottomup_fetch_graph(sb_handle_t h, int model_id, int B, int cap_peaks, float* peaks,
@@ -229,6 +232,33 @@ int sb_bottomup_from_maps(sb_handle_t h, const sb_bottomup_params* params, const
                           float* peak_vals, int32_t* peak_channel_inds, int32_t* peak_offsets,
                           int cap_cands, int32_t* edge_inds, int32_t* edge_peak_inds,
                           float* line_scores, int32_t* cand_offsets);
+
+/* ---- multi-GPU: exchange of the per-frame result records over NVLink peer memory -----------------
+ * The reference runs on one GPU (sleap/nn/system.py:29-46 rejects more than one visible device); its consumer of the
+ * per-frame results is Predictor._make_labeled_frames_from_generator (sleap/nn/inference.py:3230-3343).  Here frames
+ * are sharded over one process per GPU and the grouping kernel's epilogue writes every frame's fixed-size record
+ * [max_instances*n_nodes*2 peaks | max_instances*n_nodes values | max_instances scores | n_valid | flags] (float32)
+ * directly into a gather window in EVERY rank's HBM (CUDA-IPC peer mappings over NVLink / NVSwitch) -- no collective
+ * call, no rank waits for another inside a step.  Windows are `generations` deep; a consumer acknowledges a step to
+ * all producers, and a producer only ever waits when it is `generations` steps ahead of the slowest consumer.
+ *   sb_gather_init     allocate this rank's window, return its 64-byte CUDA IPC handle (exchange the handles of all
+ *                      ranks out of band, e.g. torch.distributed.all_gather_object)
+ *   sb_gather_connect  map every peer's window (all_ipc_handles: world x 64 bytes, rank order); from now on every
+ *                      sb_infer_bottomup* / sb_bottomup_submit call pushes its records (one "step" per call)
+ *   sb_gather_collect  host consumer: records of `step` from all ranks -> out_records_host [world][B][width]
+ *                      (rank-major = frame order for contiguous shards), out_counts[r] = frames rank r pushed
+ *   sb_gather_consume_dev  device consumer: wait + acknowledge on the post-processing stream (results stay in the
+ *                      window returned by sb_gather_window until `generations` later steps have been pushed)
+ * All waits are bounded (5 s): a dead peer produces an error from sb_gather_collect / sb_gather_status, not a hang. */
+#define SB_IPC_HANDLE_BYTES 64
+int sb_gather_init(sb_handle_t h, int model_id, int rank, int world, int generations, void* out_ipc_handle);
+int sb_gather_connect(sb_handle_t h, int model_id, const void* all_ipc_handles);
+int sb_gather_enabled(sb_handle_t h, int model_id);
+int sb_gather_consume_dev(sb_handle_t h, int model_id, int64_t step);
+int sb_gather_window(sb_handle_t h, int model_id, int64_t step, float** out_dev_ptr, int64_t* out_floats);
+int sb_gather_collect(sb_handle_t h, int model_id, int64_t step, int B, float* out_records_host, int32_t* out_counts);
+int sb_gather_status(sb_handle_t h, int model_id, int32_t* out_status, int64_t* out_steps_pushed);
+int sb_gather_close(sb_handle_t h, int model_id);
 
 /* sleap/nn/inference.py:1229-1380 SingleInstanceInferenceLayer.call and :1969-2200
  * FindInstancePeaks.call: net -> global peaks -> * output_stride -> (/input_scale + 0.5)

@@ -96,11 +96,20 @@ _SIGS = {
     "sb_get_post_stream": [c_void_p, POINTER(c_void_p)],
     "sb_bottomup_device_outputs": [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
                                    POINTER(c_void_p), POINTER(c_void_p)],
+    "sb_bottomup_device_records": [c_void_p, c_int, POINTER(c_void_p)],
     "sb_bottomup_fetch_graph": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                 c_void_p, c_void_p, c_void_p, c_void_p],
     "sb_bottomup_from_maps": [c_void_p, POINTER(BottomUpParams), c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int,
                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "sb_gather_init": [c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "sb_gather_connect": [c_void_p, c_int, c_void_p],
+    "sb_gather_enabled": [c_void_p, c_int],
+    "sb_gather_consume_dev": [c_void_p, c_int, c_int64],
+    "sb_gather_window": [c_void_p, c_int, c_int64, POINTER(c_void_p), POINTER(c_int64)],
+    "sb_gather_collect": [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p],
+    "sb_gather_status": [c_void_p, c_int, c_void_p, c_void_p],
+    "sb_gather_close": [c_void_p, c_int],
     "sb_global_configure": [c_void_p, c_int, POINTER(GlobalParams)],
     "sb_infer_global": [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "sb_centroid_configure": [c_void_p, c_int, POINTER(CentroidParams)],

@@ -50,8 +50,34 @@ struct SbPostWs {
   size_t bytes = 0;
 };
 
-static inline size_t sb_record_width(int max_instances, int n_nodes) {
-  return (size_t)max_instances * n_nodes * 3 + max_instances + 2;
+// ---- peer-memory record exchange (sb_gather.cu; pushed from k_group's epilogue) ----
+#define SB_GATHER_MAX_WORLD 8
+#define SB_GATHER_TIMEOUT_ARRIVE 1
+#define SB_GATHER_TIMEOUT_ACK 2
+struct SbGatherDev {                        // by-value kernel argument: one step's view of the exchange
+  int on, rank, world, G, Bmax;
+  size_t width;
+  unsigned long long step, timeout_ns;
+  float* data[SB_GATHER_MAX_WORLD];               // every rank's window (own rank: local memory, others: NVLink peer mappings)
+  unsigned long long* arrive[SB_GATHER_MAX_WORLD];
+  unsigned long long* ack[SB_GATHER_MAX_WORLD];
+  unsigned int* done;
+  int* status;
+};
+struct SbGather {
+  int rank = 0, world = 0, G = 0, Bmax = 0;
+  size_t width = 0;
+  void* local = nullptr;
+  void* peer[SB_GATHER_MAX_WORLD] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool connected = false;
+  long long step = 0;                              // steps pushed so far
+  unsigned long long timeout_ns = 0;
+  int *status_host = nullptr, *status_dev = nullptr, *counts_host = nullptr, *counts_dev = nullptr;
+};
+
+static __host__ __device__ inline size_t sb_record_width(int max_instances, int n_nodes) {
+  // peaks | values | scores | n_valid | flags, padded to a multiple of 4 floats (16-byte rows for vector copies)
+  return (((size_t)max_instances * n_nodes * 3 + max_instances + 2) + 3) & ~(size_t)3;
 }
 
 struct sb_handle_s {
@@ -114,7 +140,7 @@ int sbk_score_match(sb_handle_s* h, const float* pafs, int B, int Hp, int Wp, in
                     int n_points, int pafs_stride, float max_edge_length, float dist_penalty_weight,
                     SbPostWs& ws);
 int sbk_group(sb_handle_s* h, int B, int n_nodes, int min_instance_peaks, float min_line_scores,
-              float input_scale, SbPostWs& ws);
+              float input_scale, SbPostWs& ws, const SbGatherDev* gather = nullptr);
 int sbk_lsap_batch(sb_handle_s* h, const float* scores, const int* n_src, const int* n_dst,
                    const int* offsets, int n_problems, int max_k, int* out_rows, int* out_cols,
                    float* out_scores, int* out_counts);

@@ -94,7 +94,6 @@ struct TcParams {
   int epi_mode;
   // 1: the full-resolution output of this conv has no reader (only its fused 2x2 max-pool is consumed): skip the stores
   int skip_out;
-  int prefetch;                // tiles of look-ahead for the L2 prefetch of the activation boxes (0 = off)
 };
 
 #include "sb_tc_prims.cuh"
@@ -650,16 +649,7 @@ __global__ void __launch_bounds__(192) k_conv_tc_persist(const __grid_constant__
                     P.used_taps[u]);
     int sa = 0;
     uint32_t pha = 0;
-    auto prefetch_tile = [&](int t) {
-      if (t >= P.n_tiles_total) return;
-      const int b = t / P.tiles_per_img, r = t - b * P.tiles_per_img;
-      const int y0 = (r / P.tiles_x) * TH, x0 = (r % P.tiles_x) * TW;
-      for (int ch = 0; ch < P.n_chunks; ++ch)
-        for (int g = 0; g < P.n_groups; ++g) tma_prefetch_4d(&mapA, ch * P.KC, x0 + P.groups[g].dx, y0 + P.dy0, b);
-    };
-    for (int k = 0; k < P.prefetch; ++k) prefetch_tile(blockIdx.x + k * gridDim.x);
     for (int t = blockIdx.x; t < P.n_tiles_total; t += gridDim.x) {
-      if (P.prefetch) prefetch_tile(t + P.prefetch * gridDim.x);
       const int b = t / P.tiles_per_img, r = t - b * P.tiles_per_img;
       const int y0 = (r / P.tiles_x) * TH, x0 = (r % P.tiles_x) * TW;
       for (int ch = 0; ch < P.n_chunks; ++ch)
@@ -828,17 +818,9 @@ __global__ void __launch_bounds__(192) k_conv_tc_halo(const __grid_constant__ CU
                     P.used_taps[u]);
     int sa = 0;
     uint32_t pha = 0;
-    TileIter it, pf;
+    TileIter it;
     it.init(blockIdx.x, gridDim.x, P.tiles_x, P.tiles_per_img / P.tiles_x);
-    pf = it;
-    int tp = blockIdx.x;                               // prefetch cursor: P.prefetch tiles ahead of the load cursor
-    for (int k = 0; k < P.prefetch && tp < P.n_tiles_total; ++k, tp += gridDim.x, pf.next())
-      for (int ch = 0; ch < P.n_chunks; ++ch) tma_prefetch_4d(&mapA, ch * P.KC, pf.tx * TWH + P.dx0, pf.ty * THH + P.dy0, pf.b);
     for (int t = blockIdx.x; t < P.n_tiles_total; t += gridDim.x, it.next()) {
-      if (P.prefetch && tp < P.n_tiles_total) {
-        for (int ch = 0; ch < P.n_chunks; ++ch) tma_prefetch_4d(&mapA, ch * P.KC, pf.tx * TWH + P.dx0, pf.ty * THH + P.dy0, pf.b);
-        tp += gridDim.x; pf.next();
-      }
       const int b = it.b, y0 = it.ty * THH, x0 = it.tx * TWH;
       for (int ch = 0; ch < P.n_chunks; ++ch) {
         mbar_wait(smem_u32(emptyA + sa), pha ^ 1, 21);
@@ -1001,17 +983,9 @@ __global__ void __launch_bounds__(320) k_conv_tc_prog(const __grid_constant__ CU
     }
     int sa = 0, sw = 0;
     uint32_t pha = 0, phw = 0;
-    TileIter it, pf;
+    TileIter it;
     it.init(blockIdx.x, gridDim.x, P.tiles_x, P.tiles_per_img / P.tiles_x);
-    pf = it;
-    int tp = blockIdx.x;                               // prefetch cursor: P.prefetch tiles ahead of the load cursor
-    for (int k = 0; k < P.prefetch && tp < P.n_tiles_total; ++k, tp += gridDim.x, pf.next())
-      for (int ch = 0; ch < P.n_chunks; ++ch) tma_prefetch_4d(&mapA, ch * P.KC, pf.tx * TWH + P.dx0, pf.ty * THH + P.dy0, pf.b);
     for (int t = blockIdx.x; t < P.n_tiles_total; t += gridDim.x, it.next()) {
-      if (P.prefetch && tp < P.n_tiles_total) {
-        for (int ch = 0; ch < P.n_chunks; ++ch) tma_prefetch_4d(&mapA, ch * P.KC, pf.tx * TWH + P.dx0, pf.ty * THH + P.dy0, pf.b);
-        tp += gridDim.x; pf.next();
-      }
       const int b = it.b, y0 = it.ty * THH, x0 = it.tx * TWH;
       for (int ch = 0; ch < P.n_chunks; ++ch) {
         mbar_wait(smem_u32(emptyA + sa), pha ^ 1, 21);
@@ -1940,18 +1914,11 @@ int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m) {
   return sb_conv_tc_autotune(h, m);
 }
 
-// look-ahead (in tiles of a CTA's own sequence) of the activation-box L2 prefetch in the persistent kernels
-static int tc_prefetch_dist() {
-  static const int d = getenv("SB_PREFETCH_DIST") ? atoi(getenv("SB_PREFETCH_DIST")) : 4;
-  return d < 0 ? 0 : (d > 32 ? 32 : d);
-}
-
 static void launch_variant(sb_handle_s* h, TcLaunch& L, int B, int variant, cudaStream_t stream, int skip_out = 0) {
   if (variant >= 2) {
     TcLaunch::Halo& HC = L.halo[variant - 2];
     TcParams P = HC.P;
     P.skip_out = skip_out;
-    P.prefetch = tc_prefetch_dist();
     P.n_tiles_total = P.tiles_per_img * B;
     const int grid = std::max(1, std::min(P.n_tiles_total, h->sm_count * HC.occ));
     if (getenv("SB_DEBUG_LAUNCH")) fprintf(stderr, "[halo %dx%d] KC=%d N=%d stages=%d cols=%d occ=%d grid=%d slots=%d smem=%zu tiles=%d thr=%d\n", P.sub_x, P.sub_y, P.KC, P.N, P.n_stages, P.tmem_cols, HC.occ, grid, P.n_a_slots, HC.smem, P.n_tiles_total, HC.threads);
@@ -1971,7 +1938,6 @@ static void launch_variant(sb_handle_s* h, TcLaunch& L, int B, int variant, cuda
   } else if (variant == 1) {
     TcParams P = L.PP;
     P.skip_out = skip_out;
-    P.prefetch = tc_prefetch_dist();
     P.n_tiles_total = P.tiles_per_img * B;
     const int grid = std::max(1, std::min(P.n_tiles_total, h->sm_count * L.occ));
     if (getenv("SB_DEBUG_LAUNCH")) fprintf(stderr, "[persist] KC=%d N=%d stages=%d cols=%d occ=%d grid=%d slots=%d smem=%zu tiles=%d\n", P.KC, P.N, P.n_stages, P.tmem_cols, L.occ, grid, P.n_a_slots, L.smem_p, P.n_tiles_total);

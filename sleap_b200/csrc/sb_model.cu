@@ -47,6 +47,7 @@ void sb_models_free(sb_handle_s* h) {
     }
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     sb_post_ws_free(m->ws);
+    sb_gather_free(m);
     sb_conv_tc_release(m);
     delete m;
   }
@@ -146,6 +147,7 @@ int sb_model_configure(sb_handle_t h, int model_id, int max_batch, int H, int W,
   for (auto& b : m->buffers) { if (b.dev) { cudaFree(b.dev); b.dev = nullptr; } }
   if (m->frames_dev) { cudaFree(m->frames_dev); m->frames_dev = nullptr; }
   sb_pipeline_slots_free(m);
+  sb_gather_free(m);                             // window sizes depend on (B, max_instances, n_nodes): re-init after a reconfigure
   m->configured = false;
   m->bu_configured = false; m->gl_configured = false; m->ce_configured = false; m->td_configured = false;
   sb_conv_tc_release(m);
@@ -469,6 +471,7 @@ int sb_bottomup_configure(sb_handle_t h, int model_id, const sb_bottomup_params*
   h->post_pending = false;
   m->bu_configured = false;
   sb_pipeline_slots_free(m);                      // staging records are sized from max_instances / n_nodes
+  sb_gather_free(m);
   sb_post_ws_free(m->ws);
   int rc = sb_post_ws_alloc(h, m->ws, m->B, cb.H, cb.W, cb.C, p->max_peaks_per_sample, p->max_node_peaks, p->max_instances, p->n_edges);
   if (rc) return rc;
@@ -517,6 +520,12 @@ static int bottomup_post_kernels(sb_handle_s* h, SbModel* m, int B) {
   const float max_len = p.max_edge_length_ratio * (float)std::max(std::max(pb.H, pb.W), pb.C) * (float)p.paf_output_stride;
   if ((rc = sbk_score_match(h, (const float*)pb.dev, B, pb.H, pb.W, pb.C, p.n_line_points, p.paf_output_stride, max_len,
                             p.dist_penalty_weight, m->ws))) return rc;
+  if (m->gather.connected) {               // fused exchange: k_group's epilogue pushes the records to every peer
+    const SbGatherDev gx = sb_gather_dev(m, (unsigned long long)m->gather.step);
+    rc = sbk_group(h, B, p.n_nodes, p.min_instance_peaks, p.min_line_scores, p.input_scale, m->ws, &gx);
+    if (!rc) m->gather.step++;
+    return rc;
+  }
   return sbk_group(h, B, p.n_nodes, p.min_instance_peaks, p.min_line_scores, p.input_scale, m->ws);
 }
 
@@ -644,6 +653,13 @@ int sb_bottomup_device_outputs(sb_handle_t h, int model_id, float** instance_pea
   if (instance_scores_dev) *instance_scores_dev = m->ws.inst_scores;
   if (n_valid_dev) *n_valid_dev = m->ws.n_inst;
   if (flags_dev) *flags_dev = m->ws.flags;
+  return SB_OK;
+}
+
+int sb_bottomup_device_records(sb_handle_t h, int model_id, float** records_dev) {
+  SbModel* m = get_model(h, model_id);
+  if (!m || !m->bu_configured || !records_dev) return sb_fail(h, SB_ERR_INVALID, "bottom-up predictor not configured");
+  *records_dev = m->ws.records;
   return SB_OK;
 }
 

@@ -88,10 +88,15 @@ struct SbModel {
   sb_centroid_params ce{};
   bool ce_configured = false;
   bool td_configured = false;
+  SbGather gather;                         // peer-memory exchange of the result records (sb_gather.cu)
   bool keep_dead_stores = false;           // sb_model_forward asked for a tensor whose stores are normally elided              // fused top-down pipeline (sb_topdown_configure)
 };
 
 int sb_run_ops(sb_handle_s* h, SbModel* m, const void* frames_dev, int frames_are_u8, int B);
+
+// record exchange (sb_gather.cu)
+SbGatherDev sb_gather_dev(const SbModel* m, unsigned long long step);
+void sb_gather_free(SbModel* m);
 
 // tensor-core conv path (sb_conv_tc.cu)
 int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m);      // after buffers are allocated

@@ -729,7 +729,7 @@ __global__ void __launch_bounds__(128) k_group(
     const float* __restrict__ g_match_score, int min_instance_peaks, float min_line_scores,
     float input_scale, float* __restrict__ inst_peaks, float* __restrict__ inst_vals,
     float* __restrict__ inst_scores, int* __restrict__ n_inst, int* __restrict__ flags,
-    float* __restrict__ records /* [B][max_inst*C*3 + max_inst + 2] or null */) {
+    float* __restrict__ records /* [B][max_inst*C*3 + max_inst + 2] or null */, const SbGatherDev gx) {
   extern __shared__ int s_assign[];  // [C*K] instance id or -1; then [C*K] rank map scratch
   const int b = blockIdx.x;
   int* assign = s_assign;
@@ -882,13 +882,60 @@ __global__ void __launch_bounds__(128) k_group(
   // n_valid | flags, all float32 (the two counters are small integers, exact in float).
   __syncthreads();                       // this CTA's op / ov / os writes are visible to all its threads
   const int n2 = max_inst * C * 2, n1 = max_inst * C;
-  float* rec = records + (size_t)b * (n2 + n1 + max_inst + 2);
+  const int w = (int)sb_record_width(max_inst, C);
+  float* rec = records + (size_t)b * w;
   for (int t = threadIdx.x; t < n2; t += blockDim.x) rec[t] = op[t];
   for (int t = threadIdx.x; t < n1; t += blockDim.x) rec[n2 + t] = ov[t];
   for (int t = threadIdx.x; t < max_inst; t += blockDim.x) rec[n2 + n1 + t] = os[t];
   if (threadIdx.x == 0) {
     rec[n2 + n1 + max_inst] = (float)keep;
     rec[n2 + n1 + max_inst + 1] = (float)flags[b];
+    for (int t = n2 + n1 + max_inst + 2; t < w; ++t) rec[t] = 0.f;   // padding
+  }
+  if (!gx.on) return;
+  // ---- fused exchange: this frame's record goes straight into every rank's gather window over NVLink peer memory.
+  // Generation gen of a window may be overwritten only when every consumer has acknowledged step - G (flow control:
+  // only a producer G steps ahead of the slowest consumer ever waits here).
+  __shared__ int s_go;
+  const int gen = (int)(gx.step % (unsigned long long)gx.G);
+  if (threadIdx.x == 0) {
+    int go = 1;
+    if (gx.step >= (unsigned long long)gx.G) {
+      const unsigned long long need = gx.step - gx.G + 1;
+      unsigned long long t0;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      for (int r = 0; r < gx.world && go; ++r) {
+        const volatile unsigned long long* a = gx.ack[gx.rank] + r;
+        while (*a < need) {
+          unsigned long long t1;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+          if (t1 - t0 > gx.timeout_ns) { go = 0; atomicExch(gx.status, SB_GATHER_TIMEOUT_ACK); break; }
+          __nanosleep(200);
+        }
+      }
+      __threadfence_system();
+    }
+    s_go = go;
+  }
+  __syncthreads();                       // also: rec[] of this CTA is complete
+  if (s_go) {
+    const float4* src4 = reinterpret_cast<const float4*>(rec);
+    for (int r = 0; r < gx.world; ++r) {  // record width is a multiple of 4 floats: 16-byte peer stores
+      float4* dst4 = reinterpret_cast<float4*>(gx.data[r] + (((size_t)gen * gx.world + gx.rank) * gx.Bmax + b) * (size_t)w);
+      for (int t = threadIdx.x; t < w / 4; t += blockDim.x) dst4[t] = src4[t];
+    }
+  }
+  __threadfence_system();                // this thread's peer stores are ordered before the arrival word below
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(gx.done, 1u);
+    if (prev == gridDim.x - 1) {         // last CTA of the launch: every frame's record is on its way / visible
+      *gx.done = 0;
+      __threadfence_system();
+      const unsigned long long word = ((gx.step + 1) << 8) | (unsigned long long)gridDim.x;
+      for (int r = 0; r < gx.world; ++r)
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(gx.arrive[r] + (size_t)gen * gx.world + gx.rank), "l"(word) : "memory");
+    }
   }
 }
 
@@ -1168,7 +1215,9 @@ int sbk_score_match(sb_handle_s* h, const float* pafs, int B, int Hp, int Wp, in
 }
 
 int sbk_group(sb_handle_s* h, int B, int n_nodes, int min_instance_peaks, float min_line_scores,
-              float input_scale, SbPostWs& ws) {
+              float input_scale, SbPostWs& ws, const SbGatherDev* gather) {
+  SbGatherDev gx;
+  if (gather) gx = *gather; else memset(&gx, 0, sizeof(gx));
   const int K = ws.max_node_peaks;
   const int E = ws.n_edges;
   const size_t sm = ((size_t)3 * n_nodes * K + n_nodes + E + 3 * (size_t)E * K + 3 * E) * sizeof(int);
@@ -1180,7 +1229,7 @@ int sbk_group(sb_handle_s* h, int B, int n_nodes, int min_instance_peaks, float 
                                      ws.sorted_edges_dev, ws.n_sorted, ws.peaks, ws.peak_vals, ws.node_cnt,
                                      ws.node_peaks, ws.match_cnt, ws.match_src, ws.match_dst, ws.match_score,
                                      min_instance_peaks, min_line_scores, input_scale, ws.inst_peaks,
-                                     ws.inst_vals, ws.inst_scores, ws.n_inst, ws.flags, ws.records);
+                                     ws.inst_vals, ws.inst_scores, ws.n_inst, ws.flags, ws.records, gx);
   SB_CHECK_LAUNCH(h);
   return 0;
 }

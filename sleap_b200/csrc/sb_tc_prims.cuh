@@ -94,11 +94,3 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 
 
-// TMA prefetch of a tensor box into L2 (no shared-memory slot, no barrier): fire-and-forget.  The activation boxes of the
-// HBM-bound layers are first touched from DRAM; with only the ring's few loads in flight per CTA the measured ingest was
-// ~9 B/clk/SM whatever the box shape (16->16 @1024^2, 32->32 @512^2, 64->13 heads alike), i.e. DRAM latency x bytes in
-// flight.  Prefetching the boxes a few tiles ahead turns the ring's loads into L2 hits.
-__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}

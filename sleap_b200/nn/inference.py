@@ -73,6 +73,9 @@ def _merge_batches(chunks):
     if not chunks:
         return out
     for k in chunks[0]:
+        if k.startswith("gathered_"):             # per-step arrays of the multi-GPU exchange: kept as a list
+            out[k] = [c[k] for c in chunks]
+            continue
         arrs = [np.asarray(c[k]) for c in chunks]
         if arrs[0].ndim >= 2 and np.issubdtype(arrs[0].dtype, np.floating):
             n = max(a.shape[1] for a in arrs)
@@ -483,6 +486,9 @@ class BottomUpInferenceLayer(InferenceLayer):
         n = int(nv.max()) if B else 0
         out = {"instance_peaks": ip[:, :n].copy(), "instance_peak_vals": iv[:, :n].copy(),
                "instance_scores": isc[:, :n].copy(), "n_valid": nv.astype(np.int64), "flags": fl}
+        pg = getattr(m, "peer_gather", None)
+        if pg is not None:          # multi-GPU: this call was one exchange step; consume it (sb_gather_collect)
+            out["gathered_records"], out["gathered_counts"] = pg.collect_next(B, I, N)
         if self.return_confmaps or self.return_pafs:
             cms, pafs = m.forward(imgs, ["MultiInstanceConfmapsHead", "PartAffinityFieldsHead"])
             if self.return_confmaps:
@@ -595,8 +601,12 @@ class BottomUpInferenceModel(InferenceModel):
             isc = np.zeros((B, I), np.float32); nv = np.zeros((B,), np.int32); fl = np.zeros((B,), np.int32)
             m.handle.call("sb_bottomup_collect", m.model_id, k % 2, B, ptr(ip), ptr(iv), ptr(isc), ptr(nv), ptr(fl))
             w = int(nv.max()) if B else 0
-            yield {"instance_peaks": ip[:, :w], "instance_peak_vals": iv[:, :w], "instance_scores": isc[:, :w],
+            out = {"instance_peaks": ip[:, :w], "instance_peak_vals": iv[:, :w], "instance_scores": isc[:, :w],
                    "n_valid": nv.astype(np.int64), "flags": fl}
+            pg = getattr(m, "peer_gather", None)
+            if pg is not None:      # multi-GPU: every rank's records of this step, already in this rank's HBM (sb_gather_*)
+                out["gathered_records"], out["gathered_counts"] = pg.collect_next(B, I, N)
+            yield out
 
     def predict(self, data, numpy: bool = True, batch_size: int = 4, **kwargs):
         """sleap/nn/inference.py:989-1045 with the pipelined batch loop."""

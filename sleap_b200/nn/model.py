@@ -30,6 +30,7 @@ class DeviceModel:
                          ctypes.byref(mid))
         self.model_id = mid.value
         self.configured_for = None
+        self.peer_gather = None      # sleap_b200.parallel.PeerGather once the multi-GPU record exchange is connected
 
     def head_buffer(self, name):
         return self.cm.head_buffers[name]

@@ -20,14 +20,22 @@ def frame_shard(n_frames: int, rank: int, world: int) -> slice:
 
 
 def record_width(max_instances: int, n_nodes: int) -> int:
-    return max_instances * n_nodes * 3 + max_instances + 1
+    """Floats per frame record: peaks | peak values | instance scores | n_valid | flags, padded to a multiple of 4
+    (= ``sb_record_width`` of the library: the grouping kernel writes exactly this record)."""
+    return (max_instances * n_nodes * 3 + max_instances + 2 + 3) // 4 * 4
 
 
-def pack_records(instance_peaks, instance_peak_vals, instance_scores, n_valid) -> torch.Tensor:
-    """(B,I,C,2), (B,I,C), (B,I), (B,) -> (B, I*C*3 + I + 1) float32 records (tensors, any device)."""
-    B = instance_peaks.shape[0]
-    return torch.cat([instance_peaks.reshape(B, -1), instance_peak_vals.reshape(B, -1),
-                      instance_scores.reshape(B, -1), n_valid.reshape(B, 1).to(torch.float32)], dim=1).contiguous()
+def pack_records(instance_peaks, instance_peak_vals, instance_scores, n_valid, flags=None) -> torch.Tensor:
+    """(B,I,C,2), (B,I,C), (B,I), (B,) [, (B,)] -> (B, record_width) float32 records (tensors, any device) -- the host-side
+    twin of the record the grouping kernel writes on the device."""
+    B, I, C = instance_peaks.shape[0], instance_peaks.shape[1], instance_peaks.shape[2]
+    rec = torch.zeros((B, record_width(I, C)), dtype=torch.float32, device=instance_peaks.device)
+    o = I * C * 3 + I
+    rec[:, :o] = torch.cat([instance_peaks.reshape(B, -1), instance_peak_vals.reshape(B, -1), instance_scores.reshape(B, -1)], dim=1)
+    rec[:, o] = n_valid.reshape(B).to(torch.float32)
+    if flags is not None:
+        rec[:, o + 1] = flags.reshape(B).to(torch.float32)
+    return rec
 
 
 def unpack_records(rec: torch.Tensor, max_instances: int, n_nodes: int):
@@ -79,7 +87,8 @@ def predict_sharded(predict_on_batch, frames, global_batch: int, max_instances: 
         sl = frame_shard(nb, rank, world)
         cap = -(-nb // world)                                     # largest shard
         rec = torch.full((cap, width), float("nan"), dtype=torch.float32)
-        rec[:, -1] = -1.0                                         # n_valid = -1 marks a padding row
+        nv_col = I * C * 3 + I
+        rec[:, nv_col] = -1.0                                     # n_valid = -1 marks a padding row
         if sl.stop > sl.start:
             out = predict_on_batch(frames[g0 + sl.start:g0 + sl.stop])
             b = sl.stop - sl.start
@@ -95,8 +104,88 @@ def predict_sharded(predict_on_batch, frames, global_batch: int, max_instances: 
         if device is not None:
             rec = rec.to(device)
         allrec = all_gather_records(rec).cpu()
-        keep = allrec[:, -1] >= 0                                 # rank-major order == frame order (contiguous shards)
+        keep = allrec[:, nv_col] >= 0                             # rank-major order == frame order (contiguous shards)
         peaks, vals, scores, n_valid = unpack_records(allrec[keep], I, C)
         assert peaks.shape[0] == nb, (peaks.shape, nb)
         yield {"instance_peaks": peaks.numpy(), "instance_peak_vals": vals.numpy(), "instance_scores": scores.numpy(),
                "n_valid": n_valid.numpy(), "frame_ind": np.arange(g0, g1)}
+
+
+class PeerGather:
+    """The path's ONE exchange step without a collective call: every rank's grouping kernel stores its frames' records
+    straight into a gather window in each peer's HBM (CUDA IPC mappings over NVLink / NVSwitch; ``sb_gather_*`` in
+    include/sleap_b200.h).  This class only does the out-of-band part: it exchanges the 64-byte IPC handles of the
+    windows through ``torch.distributed`` (any backend) and maps the peers.
+
+    ``model``: a configured bottom-up ``DeviceModel`` (``sb_bottomup_configure`` done).  After construction every
+    ``sb_infer_bottomup*`` / ``sb_bottomup_submit`` call of that model is one exchange *step*; steps are consumed in
+    order, either on the device (``consume_next_dev``) or into host memory (``collect_next``).  A producer blocks only
+    when it is ``generations`` steps ahead of the slowest consumer."""
+
+    def __init__(self, model, generations: int = 8, group=None):
+        import ctypes
+        self.model, self.handle = model, model.handle
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.generations = int(generations)
+        self.consumed = 0
+        buf = ctypes.create_string_buffer(64)
+        self.handle.call("sb_gather_init", model.model_id, self.rank, self.world, self.generations, buf)
+        handles = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(handles, bytes(buf.raw), group=group)
+        else:
+            handles[0] = bytes(buf.raw)
+        blob = ctypes.create_string_buffer(b"".join(handles), 64 * self.world)
+        err = None
+        try:
+            self.handle.call("sb_gather_connect", model.model_id, blob)
+        except Exception as e:                       # e.g. peer access not permitted between two of the GPUs
+            err = e
+        if self.world > 1:                           # all ranks agree before anybody pushes (or everybody falls back)
+            dev = torch.device("cuda", self.handle.device_id) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+            ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
+                try:
+                    self.handle.call("sb_gather_close", model.model_id)
+                finally:
+                    raise RuntimeError(f"peer-memory exchange unavailable on at least one rank ({err})")
+        elif err:
+            raise err
+        model.peer_gather = self
+
+    def pushed(self) -> int:
+        import ctypes
+        st, n = ctypes.c_int32(0), ctypes.c_int64(0)
+        self.handle.call("sb_gather_status", self.model.model_id, ctypes.byref(st), ctypes.byref(n))
+        if st.value:
+            raise RuntimeError(f"record exchange reported status {st.value} (1: arrivals timed out, 2: acknowledgements timed out)")
+        return int(n.value)
+
+    def consume_next_dev(self):
+        """Device consumer of the oldest unconsumed step (queued on the post-processing stream)."""
+        self.handle.call("sb_gather_consume_dev", self.model.model_id, self.consumed)
+        self.consumed += 1
+
+    def window(self, step: int):
+        """(device pointer, float count) of the [world][Bmax][width] window that holds ``step``."""
+        from ctypes import byref, c_int64, c_void_p
+        p, n = c_void_p(), c_int64()
+        self.handle.call("sb_gather_window", self.model.model_id, int(step), byref(p), byref(n))
+        return p.value, n.value
+
+    def collect_next(self, B: int, max_instances: int, n_nodes: int):
+        """Host consumer of the oldest unconsumed step: (world*B, width) records in rank-major (= frame) order and the
+        number of frames every rank pushed."""
+        from sleap_b200._lib import ptr
+        w = record_width(max_instances, n_nodes)
+        out = np.zeros((self.world, B, w), np.float32)
+        counts = np.zeros((self.world,), np.int32)
+        self.handle.call("sb_gather_collect", self.model.model_id, self.consumed, int(B), ptr(out), ptr(counts))
+        self.consumed += 1
+        return out.reshape(self.world * B, w), counts
+
+    def close(self):
+        self.model.peer_gather = None
+        self.handle.call("sb_gather_close", self.model.model_id)
