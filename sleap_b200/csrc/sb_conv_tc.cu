@@ -1911,6 +1911,15 @@ int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m) {
         if (rc) return rc;
       }
     }
+  // fused first encoder block: frame -> conv0 -> conv1 -> pool in one kernel (sb_conv01.cu) when conv1's own output is dead
+  for (size_t oi = 0; oi + 2 < m->ops.size(); ++oi)
+    if (m->ops[oi].kind() == SB_OPK_PREPROCESS) {
+      const int cv = sb_first_fusion_op(m, oi);
+      if (cv >= 0 && cv + 1 < (int)m->ops.size() && m->ops[cv + 1].kind() == SB_OPK_CONV && m->tc_plans[cv + 1]) {
+        const int rc = sb_conv01_prepare(h, m, cv, cv + 1, m->tc_plans[cv + 1]->out_dead);
+        if (rc) return rc;
+      }
+    }
   return sb_conv_tc_autotune(h, m);
 }
 
@@ -1982,6 +1991,7 @@ int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
   auto avail = [&](const TcLaunch& L, int v) { return v == 0 || (v == 1 && L.has_persist) || (v >= 2 && v - 2 < L.n_halo && halo_ok); };
   if (force || getenv("SB_DISABLE_AUTOTUNE")) {
     const int want = force ? atoi(force) : 1;
+    m->conv01_enabled = m->conv01 && (getenv("SB_FORCE_CONV01") ? atoi(getenv("SB_FORCE_CONV01")) != 0 : true);
     for (SbConvTcPlan* plan : m->tc_plans)
       if (plan) {
         for (TcLaunch& L : plan->launches) L.use_persist = avail(L, want) ? want : (avail(L, 1) && !force ? 1 : 0);
@@ -1998,6 +2008,7 @@ int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
       while (fscanf(f, "%d %d %d", &oi, &li, &pick) == 3) {
         if (oi < 0 || oi >= (int)m->tc_plans.size() || !m->tc_plans[oi]) continue;
         SbConvTcPlan* plan = m->tc_plans[oi];
+        if (li == -3) { m->conv01_enabled = m->conv01 && pick != 0; ++applied; continue; }
         if (li == -2) { plan->view_enabled = pick != 0; ++applied; continue; }
         if (li < 0) { plan->use_fused = pick != 0 && !plan->fused.empty(); ++applied; continue; }
         if (li >= (int)plan->launches.size()) continue;
@@ -2075,6 +2086,32 @@ int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
     if (dbg) fprintf(stderr, "[sb_conv_tc] op %zu first layer: k_conv_first %.1f us, Toeplitz view + tcgen05 %.1f us -> %s\n", oi,
                      best[0] * 1e3f, best[1] * 1e3f, plan->view_enabled ? "view" : "direct");
   }
+  // fused first block (k_conv01) against its two separate launches (whatever forms were just picked for them)
+  if (m->conv01 && m->frames_dev) {
+    const int c1op = sb_conv01_conv1_op(m), c0op = c1op - 1;
+    float best[2] = {1e30f, 1e30f};
+    for (int f = 0; f < 2; ++f)
+      for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0, h->stream);
+        int rc = 0;
+        if (f == 1) rc = sb_conv01_launch(h, m, m->frames_dev, 1, m->B);
+        else {
+          rc = sb_first_view_can(m, c0op) ? sb_first_view_launch(h, m, c0op, m->frames_dev, 1, m->B) : sb_first_direct_launch(h, m, c0op, m->frames_dev, 1, m->B);
+          if (!rc) rc = sb_conv_tc_launch(h, m, c1op, m->B);
+        }
+        if (rc) return rc;
+        cudaEventRecord(e1, h->stream);
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) return sb_fail(h, SB_ERR_CUDA, "autotune launch (first block, fused %d) failed: %s", f, cudaGetErrorString(e));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0) best[f] = std::min(best[f], ms);
+      }
+    m->conv01_enabled = best[1] < best[0];
+    if (const char* fv = getenv("SB_FORCE_CONV01")) m->conv01_enabled = atoi(fv) != 0;
+    if (dbg) fprintf(stderr, "[sb_conv_tc] first block: conv0 + conv1 launches %.1f us, fused k_conv01 %.1f us -> %s\n", best[0] * 1e3f,
+                     best[1] * 1e3f, m->conv01_enabled ? "fused" : "separate");
+  }
   for (size_t oi = 0; oi < m->tc_plans.size(); ++oi) {
     SbConvTcPlan* plan = m->tc_plans[oi];
     if (!plan || plan->fused.empty()) continue;
@@ -2110,6 +2147,7 @@ int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
         for (size_t li = 0; li < plan->launches.size(); ++li) fprintf(f, "%zu %zu %d\n", oi, li, plan->launches[li].use_persist);
         if (!plan->fused.empty()) fprintf(f, "%zu -1 %d\n", oi, plan->use_fused ? 1 : 0);
         if (plan->view_in) fprintf(f, "%zu -2 %d\n", oi, plan->view_enabled ? 1 : 0);
+        if (m->conv01 && (int)oi == sb_conv01_conv1_op(m)) fprintf(f, "%zu -3 %d\n", oi, m->conv01_enabled ? 1 : 0);
       }
       fclose(f);
     }

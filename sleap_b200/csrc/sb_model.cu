@@ -48,6 +48,7 @@ void sb_models_free(sb_handle_s* h) {
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     sb_post_ws_free(m->ws);
     sb_gather_free(m);
+    sb_conv01_release(m);
     sb_conv_tc_release(m);
     delete m;
   }
@@ -150,6 +151,8 @@ int sb_model_configure(sb_handle_t h, int model_id, int max_batch, int H, int W,
   sb_gather_free(m);                             // window sizes depend on (B, max_instances, n_nodes): re-init after a reconfigure
   m->configured = false;
   m->bu_configured = false; m->gl_configured = false; m->ce_configured = false; m->td_configured = false;
+  sb_conv01_release(m);
+  m->conv01_enabled = false;
   sb_conv_tc_release(m);
   m->B = max_batch; m->Hin = H; m->Win = W; m->Cin = C_in; m->Hres = Hres; m->Wres = Wres; m->Hnet = Hnet; m->Wnet = Wnet;
   size_t total = 0;
@@ -231,13 +234,20 @@ int sb_first_direct_launch(sb_handle_s* h, SbModel* m, int op_index, const void*
 template <typename T>
 static int run_ops_t(sb_handle_s* h, SbModel* m, const void* frames_dev, int frames_are_u8, int B) {
   cudaStream_t s = h->stream;
-  int fused_first = -1;
+  int fused_first = -1, fused_conv1 = -1;
   for (size_t oi = 0; oi < m->ops.size(); ++oi) {
     const SbOp& op = m->ops[oi];
     if (!m->prof_events.empty()) cudaEventRecord(m->prof_events[oi], s);
     SbBuffer& ob = m->buffers[op.out_buf()];
     if ((int)oi == m->guard_op && h->post_pending) SB_CUDA(h, cudaStreamWaitEvent(s, h->post_done_ev, 0));
     if (oi < m->skip_op.size() && m->skip_op[oi]) continue;     // 2x2 max-pool fused into the producing conv
+    if ((int)oi == fused_conv1) continue;                       // ran inside the fused first block
+    if ((int)oi == fused_first && sb_conv01_can(m, (int)oi) && !m->keep_dead_stores) {
+      int rc = sb_conv01_launch(h, m, frames_dev, frames_are_u8, B);
+      if (rc) return rc;
+      fused_conv1 = sb_conv01_conv1_op(m);
+      continue;
+    }
     if ((int)oi == fused_first && sb_first_view_can(m, (int)oi)) {
       int rc = sb_first_view_launch(h, m, (int)oi, frames_dev, frames_are_u8, B);
       if (rc) return rc;
@@ -389,8 +399,12 @@ int sb_model_forward(sb_handle_t h, int model_id, const void* images_host, int i
   if (B <= 0 || B > m->B) return sb_fail(h, SB_ERR_INVALID, "bad batch");
   int rc = upload_frames(h, m, images_host, images_are_u8, B);
   if (rc) return rc;
-  for (int i = 0; i < n_outputs; ++i)                    // a tensor nobody reads inside the graph is only written on request
+  for (int i = 0; i < n_outputs; ++i) {                  // a tensor nobody reads inside the graph is only written on request
     if (output_buffer_ids[i] >= 0 && sb_conv_tc_out_dead(m, output_buffer_ids[i])) m->keep_dead_stores = true;
+    if (m->conv01 && output_buffer_ids[i] >= 0 && output_buffer_ids[i] < (int)m->buffers.size() &&
+        (output_buffer_ids[i] == m->ops[sb_conv01_conv1_op(m)].in_buf() || output_buffer_ids[i] == m->ops[sb_conv01_conv1_op(m)].out_buf()))
+      m->keep_dead_stores = true;                          // tensors internal to the fused first block
+  }
   rc = sb_run_ops(h, m, m->frames_dev, images_are_u8, B);
   m->keep_dead_stores = false;
   if (rc) return rc;

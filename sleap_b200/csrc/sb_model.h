@@ -52,6 +52,7 @@ struct SbBuffer {
 };
 
 struct SbConvTcPlan;  // sb_conv_tc.cu
+struct SbConv01Plan;  // sb_conv01.cu
 
 struct SbModel {
   int precision = 0;  // 0: fp16 activations + tensor-core convs; 1: fp32 CUDA-core path
@@ -88,6 +89,8 @@ struct SbModel {
   sb_centroid_params ce{};
   bool ce_configured = false;
   bool td_configured = false;
+  SbConv01Plan* conv01 = nullptr;          // fused first encoder block (frame -> conv0 -> conv1 -> pool), sb_conv01.cu
+  bool conv01_enabled = false;             // the autotuner measured it faster than the two separate launches
   SbGather gather;                         // peer-memory exchange of the result records (sb_gather.cu)
   bool keep_dead_stores = false;           // sb_model_forward asked for a tensor whose stores are normally elided              // fused top-down pipeline (sb_topdown_configure)
 };
@@ -111,6 +114,13 @@ int sb_first_fusion_op(const SbModel* m, size_t pre_index);
 bool sb_first_view_can(const SbModel* m, int op_index);
 int sb_first_view_launch(sb_handle_s* h, SbModel* m, int op_index, const void* frames_dev, int frames_are_u8, int B);
 int sb_first_direct_launch(sb_handle_s* h, SbModel* m, int op_index, const void* frames_dev, int frames_are_u8, int B);
+
+// fused first encoder block (sb_conv01.cu)
+int sb_conv01_prepare(sb_handle_s* h, SbModel* m, int conv0_op, int conv1_op, bool conv1_out_dead);
+void sb_conv01_release(SbModel* m);
+bool sb_conv01_can(const SbModel* m, int conv0_op);
+int sb_conv01_conv1_op(const SbModel* m);
+int sb_conv01_launch(sb_handle_s* h, SbModel* m, const void* frames_dev, int frames_are_u8, int B);
 
 // first layer fused with preprocessing on the tensor cores (sb_conv_tc.cu)
 bool sb_conv_first_tc_ok(const SbModel* m, const SbOp& conv);

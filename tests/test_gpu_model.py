@@ -506,3 +506,68 @@ def test_tc_multicast_streaming(cs, cin, cout, hw, monkeypatch):
     streaming kernel.  Run with SB_TEST_EXPERIMENTAL=1."""
     monkeypatch.setenv("SB_ENABLE_MULTICAST", cs)
     test_tc_single_layers(cin, cout, 3, hw, "0", monkeypatch)
+
+
+@pytest.mark.parametrize("hw,as_float,relu", [((64, 64), False, True), ((34, 1056), False, True), ((96, 520), True, True),
+                                              ((40, 516), False, False)])
+def test_conv01_fused_first_block(hw, as_float, relu, monkeypatch):
+    """k_conv01 (sb_conv01.cu): frame -> conv0 (1 -> 16) -> conv1 (16 -> 16) -> 2x2 max-pool in ONE kernel, against
+    (a) torch fp32 convs on the operands the tensor cores consume (fp16 pixels / weights, fp16-rounded intermediate) and
+    (b) the two separate tcgen05 launches (SB_FORCE_CONV01=0).  Several strips (W > 512, partial last strip), odd row
+    counts per CTA range, float frames, bottom zero padding, no-ReLU."""
+    from ctypes import byref, c_int, c_void_p
+    import torch
+    import torch.nn.functional as F
+    from sleap_b200 import _lib
+    from sleap_b200.nn import oplist as ol
+    H, W = hw
+    B = 3
+    rng = np.random.default_rng(H * 7 + W)
+    w0 = (rng.standard_normal((3, 3, 1, 16)) * 0.5).astype(np.float32); b0 = (rng.standard_normal(16) * 0.1).astype(np.float32)
+    w1 = (rng.standard_normal((3, 3, 16, 16)) * np.sqrt(2.0 / 144)).astype(np.float32); b1 = (rng.standard_normal(16) * 0.1).astype(np.float32)
+    blob = np.concatenate([w0.reshape(-1), b0, w1.reshape(-1), b1]).astype(np.float32)
+    o1 = w0.size + 16
+    # buffers: 0 input, 1 conv0 out (stride 1), 2 conv1 out (stride 1), 3 pooled (stride 2), 4 copy of pooled as f32 via 1x1 identity conv
+    eye = np.eye(16, dtype=np.float32).reshape(1, 1, 16, 16)
+    blob = np.concatenate([blob, eye.reshape(-1), np.zeros(16, np.float32)])
+    o2 = o1 + w1.size + 16
+    recs = [ol.buffer_record(0, 1, 1, 0, 1), ol.buffer_record(1, 1, 16, 0, 0), ol.buffer_record(2, 1, 16, 0, 0), ol.buffer_record(3, 2, 16, 0, 0),
+            ol.buffer_record(4, 2, 16, 1, 0), ol.preprocess_record(0, 1, 1.0, 4),
+            ol.conv_record(0, 0, 1, 1, 0, 16, 3, 1, relu, 0, w0.size),
+            ol.conv_record(1, 0, 16, 2, 0, 16, 3, 1, relu, o1, o1 + w1.size, pool_buf=3, pool_coff=0),
+            ol.pool_record(2, 0, 16, 3, 0, fused=True),
+            ol.conv_record(3, 0, 16, 4, 0, 16, 1, 1, False, o2, o2 + 256)]
+    ops = np.ascontiguousarray(np.stack(recs).astype(np.int32))
+    if as_float:
+        imgs = rng.random((B, H, W, 1)).astype(np.float32); xin = imgs
+    else:
+        imgs = rng.integers(0, 256, size=(B, H, W, 1), dtype=np.uint8); xin = imgs.astype(np.float32) * np.float32(1.0 / 255.0)
+    Hn, Wn = -(-H // 4) * 4, -(-W // 4) * 4
+
+    def run(fused):
+        monkeypatch.setenv("SB_FORCE_CONV01", "1" if fused else "0")
+        h = _lib.Handle(0)
+        mid = c_int(-1)
+        h.call("sb_load_model", _lib.ptr(ops), ops.shape[0], _lib.ptr(blob), int(blob.size), 0, byref(mid))
+        h.call("sb_model_configure", mid.value, B, H, W, 1)
+        out = np.zeros((B, Hn // 2, Wn // 2, 16), np.float32)
+        ids = np.asarray([4], np.int32)
+        ptrs = (c_void_p * 1)(out.ctypes.data)
+        for _ in range(2):                                   # twice: ring / barrier state must be reusable across launches
+            h.call("sb_model_forward", mid.value, _lib.ptr(imgs), int(not as_float), B, 1, _lib.ptr(ids), ptrs)
+        n = h.gpu_launches()
+        h.close()
+        return out, n
+
+    got, n_fused = run(True)
+    sep, n_sep = run(False)
+    assert n_fused < n_sep                                   # the fused block really ran (one launch instead of view + conv0 + conv1)
+    act = (lambda t: torch.relu(t)) if relu else (lambda t: t)
+    x = torch.from_numpy(np.pad(xin, ((0, 0), (0, Hn - H), (0, Wn - W), (0, 0)))).half().float().permute(0, 3, 1, 2)
+    y0 = act(F.conv2d(x, torch.from_numpy(w0).half().float().permute(3, 2, 0, 1), torch.from_numpy(b0), padding=1)).half().float()
+    y1 = act(F.conv2d(y0, torch.from_numpy(w1).half().float().permute(3, 2, 0, 1), torch.from_numpy(b1), padding=1)).half().float()
+    want = F.max_pool2d(y1, 2).permute(0, 2, 3, 1).numpy()
+    scale = max(1.0, float(np.abs(want).max()))
+    assert_allclose(got, want, atol=2.5e-3 * scale, rtol=0)      # one fp16 ulp of the intermediate propagated through 144 taps
+    assert_allclose(got, sep, atol=2.5e-3 * scale, rtol=0)
+    assert np.mean(np.abs(got - want) > 1e-3 * scale) < 1e-3     # ... and only on a handful of values
