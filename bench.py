@@ -428,7 +428,8 @@ def run_ours(args):
         with torch.cuda.stream(stream):
             handle.call("sb_infer_bottomup_dev", model.model_id, c_void_p(dev[i % n_sets].data_ptr()), B)
         if pg is not None:
-            if pg.pushed() - pg.consumed > EX_LAG:                # device consumer: all ranks' records of step (now - 2)
+            n_pushed, n_consumed = pg._status()
+            if n_pushed - n_consumed > EX_LAG:                    # device consumer: all ranks' records of step (now - 2)
                 pg.consume_next_dev()
         elif world > 1:
             with torch.cuda.stream(post_stream):                  # queued behind this step's grouping kernel
@@ -436,7 +437,8 @@ def run_ours(args):
 
     def drain_exchange():
         if pg is not None:
-            while pg.consumed < pg.pushed():
+            n_pushed, n_consumed = pg._status()
+            for _ in range(n_pushed - n_consumed):
                 pg.consume_next_dev()
 
     def barrier():

@@ -247,8 +247,9 @@ int sb_bottomup_from_maps(sb_handle_t h, const sb_bottomup_params* params, const
  *                      sb_infer_bottomup* / sb_bottomup_submit call pushes its records (one "step" per call)
  *   sb_gather_collect  host consumer: records of `step` from all ranks -> out_records_host [world][B][width]
  *                      (rank-major = frame order for contiguous shards), out_counts[r] = frames rank r pushed
- *   sb_gather_consume_dev  device consumer: wait + acknowledge on the post-processing stream (results stay in the
- *                      window returned by sb_gather_window until `generations` later steps have been pushed)
+ *   sb_gather_consume_dev  device consumer: wait + acknowledge on the post-processing stream (step < 0: the next
+ *                      unconsumed step; results stay in the window returned by sb_gather_window until `generations`
+ *                      later steps have been pushed)
  * All waits are bounded (5 s): a dead peer produces an error from sb_gather_collect / sb_gather_status, not a hang. */
 #define SB_IPC_HANDLE_BYTES 64
 int sb_gather_init(sb_handle_t h, int model_id, int rank, int world, int generations, void* out_ipc_handle);
@@ -257,7 +258,12 @@ int sb_gather_enabled(sb_handle_t h, int model_id);
 int sb_gather_consume_dev(sb_handle_t h, int model_id, int64_t step);
 int sb_gather_window(sb_handle_t h, int model_id, int64_t step, float** out_dev_ptr, int64_t* out_floats);
 int sb_gather_collect(sb_handle_t h, int model_id, int64_t step, int B, float* out_records_host, int32_t* out_counts);
-int sb_gather_status(sb_handle_t h, int model_id, int32_t* out_status, int64_t* out_steps_pushed);
+int sb_gather_status(sb_handle_t h, int model_id, int32_t* out_status, int64_t* out_steps_pushed, int64_t* out_steps_consumed);
+/* With the exchange connected, sb_infer_bottomup / sb_bottomup_submit wait (on the device, behind the post-processing) for
+ * every rank's records of their step and bring the WHOLE gather window to the host in the one result copy they do anyway
+ * (their own outputs are the rank's slice of it).  sb_bottomup_gathered returns that copy: slot 0 / 1 after
+ * sb_bottomup_collect(slot), slot -1 after sb_infer_bottomup.  out_records [world][B][width], out_counts [world]. */
+int sb_bottomup_gathered(sb_handle_t h, int model_id, int slot, int B, float* out_records, int32_t* out_counts);
 int sb_gather_close(sb_handle_t h, int model_id);
 
 /* sleap/nn/inference.py:1229-1380 SingleInstanceInferenceLayer.call and :1969-2200

@@ -108,7 +108,8 @@ _SIGS = {
     "sb_gather_consume_dev": [c_void_p, c_int, c_int64],
     "sb_gather_window": [c_void_p, c_int, c_int64, POINTER(c_void_p), POINTER(c_int64)],
     "sb_gather_collect": [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p],
-    "sb_gather_status": [c_void_p, c_int, c_void_p, c_void_p],
+    "sb_gather_status": [c_void_p, c_int, c_void_p, c_void_p, c_void_p],
+    "sb_bottomup_gathered": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "sb_gather_close": [c_void_p, c_int],
     "sb_global_configure": [c_void_p, c_int, POINTER(GlobalParams)],
     "sb_infer_global": [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p],

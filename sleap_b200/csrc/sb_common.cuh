@@ -71,6 +71,7 @@ struct SbGather {
   void* peer[SB_GATHER_MAX_WORLD] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool connected = false;
   long long step = 0;                              // steps pushed so far
+  long long consumed = 0;                          // steps acknowledged so far (acks are cumulative)
   unsigned long long timeout_ns = 0;
   int *status_host = nullptr, *status_dev = nullptr, *counts_host = nullptr, *counts_dev = nullptr;
 };

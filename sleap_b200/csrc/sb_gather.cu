@@ -14,6 +14,8 @@
 //   u64    arrive[G][world]                   ((step + 1) << 8) | B   written by rank r after its records
 //   u64    ack   [world]                      steps consumed by rank r (written by r into every peer's window)
 //   u32    done                               local: CTAs of the current k_group launch that finished their stores
+#include <algorithm>
+
 #include "sb_common.cuh"
 #include "sb_model.h"
 
@@ -103,6 +105,20 @@ SbGatherDev sb_gather_dev(const SbModel* m, unsigned long long step) {
   return d;
 }
 
+int sb_gather_queue_collect(sb_handle_s* h, SbModel* m, long long step, int B, float* host_dst, int* counts_dev, cudaStream_t s) {
+  SbGather& g = m->gather;
+  const SbGatherDev d = sb_gather_dev(m, (unsigned long long)step);
+  k_gather_wait<<<1, 32, 0, s>>>(d, (unsigned long long)step, 0, g.timeout_ns, counts_dev);
+  SB_CHECK_LAUNCH(h);
+  const float* src = (const float*)g.local + (size_t)(step % g.G) * g.world * g.Bmax * g.width;
+  SB_CUDA(h, cudaMemcpy2DAsync(host_dst, (size_t)B * g.width * sizeof(float), src, (size_t)g.Bmax * g.width * sizeof(float),
+                               (size_t)B * g.width * sizeof(float), g.world, cudaMemcpyDeviceToHost, s));
+  k_gather_ack<<<1, 32, 0, s>>>(d, (unsigned long long)step);
+  SB_CHECK_LAUNCH(h);
+  g.consumed = std::max(g.consumed, step + 1);
+  return 0;
+}
+
 extern "C" {
 
 int sb_gather_init(sb_handle_t h, int model_id, int rank, int world, int generations, void* out_ipc_handle) {
@@ -121,7 +137,7 @@ int sb_gather_init(sb_handle_t h, int model_id, int rank, int world, int generat
   SB_CUDA(h, cudaMalloc(&g.local, win_bytes(g)));
   SB_CUDA(h, cudaMemset(g.local, 0, win_bytes(g)));
   SB_CUDA(h, cudaHostAlloc((void**)&g.status_host, sizeof(int), cudaHostAllocMapped));
-  SB_CUDA(h, cudaHostAlloc((void**)&g.counts_host, sizeof(int) * SB_GATHER_MAX_WORLD, cudaHostAllocMapped));
+  SB_CUDA(h, cudaHostAlloc((void**)&g.counts_host, sizeof(int) * SB_GATHER_MAX_WORLD * 4, cudaHostAllocMapped));   // [collect | slot 0 | slot 1 | sync]
   *g.status_host = 0;
   SB_CUDA(h, cudaHostGetDevicePointer((void**)&g.status_dev, g.status_host, 0));
   SB_CUDA(h, cudaHostGetDevicePointer((void**)&g.counts_dev, g.counts_host, 0));
@@ -151,6 +167,8 @@ int sb_gather_connect(sb_handle_t h, int model_id, const void* all_ipc_handles) 
   }
   g.connected = true;
   g.step = 0;
+  g.consumed = 0;
+  sb_pipeline_slots_free(m);                       // host staging now holds [world][B][width] windows
   return SB_OK;
 }
 
@@ -165,10 +183,12 @@ int sb_gather_enabled(sb_handle_t h, int model_id) {
 int sb_gather_consume_dev(sb_handle_t h, int model_id, int64_t step) {
   SbModel* m = gmodel(h, model_id);
   if (!m || !m->gather.connected) return sb_fail(h, SB_ERR_INVALID, "sb_gather_consume_dev: exchange not connected");
-  if (step < 0 || step >= m->gather.step) return sb_fail(h, SB_ERR_INVALID, "sb_gather_consume_dev: step %lld was not pushed", (long long)step);
+  if (step < 0) step = m->gather.consumed;        // next unconsumed step
+  if (step >= m->gather.step) return sb_fail(h, SB_ERR_INVALID, "sb_gather_consume_dev: step %lld was not pushed", (long long)step);
   SB_CUDA(h, cudaSetDevice(h->device));
   k_gather_wait<<<1, 32, 0, h->post_stream>>>(sb_gather_dev(m, (unsigned long long)step), (unsigned long long)step, 1, m->gather.timeout_ns, nullptr);
   SB_CHECK_LAUNCH(h);
+  m->gather.consumed = std::max(m->gather.consumed, (long long)step + 1);
   return SB_OK;
 }
 
@@ -191,14 +211,8 @@ int sb_gather_collect(sb_handle_t h, int model_id, int64_t step, int B, float* o
   if (B <= 0 || B > g.Bmax) return sb_fail(h, SB_ERR_INVALID, "sb_gather_collect: bad batch");
   SB_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t s = h->post_stream;
-  const SbGatherDev d = sb_gather_dev(m, (unsigned long long)step);
-  k_gather_wait<<<1, 32, 0, s>>>(d, (unsigned long long)step, 0, g.timeout_ns, g.counts_dev);
-  SB_CHECK_LAUNCH(h);
-  const float* src = (const float*)g.local + (size_t)(step % g.G) * g.world * g.Bmax * g.width;
-  SB_CUDA(h, cudaMemcpy2DAsync(out_records_host, (size_t)B * g.width * sizeof(float), src, (size_t)g.Bmax * g.width * sizeof(float),
-                               (size_t)B * g.width * sizeof(float), g.world, cudaMemcpyDeviceToHost, s));
-  k_gather_ack<<<1, 32, 0, s>>>(d, (unsigned long long)step);
-  SB_CHECK_LAUNCH(h);
+  int rc = sb_gather_queue_collect(h, m, step, B, out_records_host, g.counts_dev, s);
+  if (rc) return rc;
   SB_CUDA(h, cudaStreamSynchronize(s));
   if (out_counts) for (int r = 0; r < g.world; ++r) out_counts[r] = g.counts_host[r];
   if (*g.status_host != 0) {
@@ -210,11 +224,12 @@ int sb_gather_collect(sb_handle_t h, int model_id, int64_t step, int B, float* o
   return SB_OK;
 }
 
-int sb_gather_status(sb_handle_t h, int model_id, int32_t* out_status, int64_t* out_steps_pushed) {
+int sb_gather_status(sb_handle_t h, int model_id, int32_t* out_status, int64_t* out_steps_pushed, int64_t* out_steps_consumed) {
   SbModel* m = gmodel(h, model_id);
   if (!m || !m->gather.local) return sb_fail(h, SB_ERR_INVALID, "sb_gather_status: exchange not initialised");
   if (out_status) *out_status = *m->gather.status_host;
   if (out_steps_pushed) *out_steps_pushed = m->gather.step;
+  if (out_steps_consumed) *out_steps_consumed = m->gather.consumed;
   return SB_OK;
 }
 

@@ -57,7 +57,7 @@ void sb_models_free(sb_handle_s* h) {
 
 // pinned staging + device frame slots of the submit/collect pipeline are sized from (B, H, W, C, max_instances,
 // n_nodes) at first use: any configure call that may change one of those drops them (re-created lazily)
-static void sb_pipeline_slots_free(SbModel* m) {
+void sb_pipeline_slots_free(SbModel* m) {
   for (int i = 0; i < 2; ++i) {
     if (m->frames_slot[i]) { cudaFree(m->frames_slot[i]); m->frames_slot[i] = nullptr; }
     if (m->stage_host[i]) { cudaFreeHost(m->stage_host[i]); m->stage_host[i] = nullptr; }
@@ -506,8 +506,30 @@ int sb_bottomup_configure(sb_handle_t h, int model_id, const sb_bottomup_params*
   return SB_OK;
 }
 
-static size_t stage_floats(const SbModel* m) {
-  return (size_t)m->B * sb_record_width(m->bu.max_instances, m->bu.n_nodes);
+static size_t stage_floats(const SbModel* m) {          // [world][B][width] when the exchange is connected
+  return (size_t)(m->gather.connected ? m->gather.world : 1) * m->B * sb_record_width(m->bu.max_instances, m->bu.n_nodes);
+}
+
+// One D2H copy of a batch's results into pinned `dst`: the rank's own records, or -- exchange connected -- the whole gather
+// window of the step just pushed (device-side wait for the peers, copy, acknowledge; all on stream rs).
+static int queue_result_copy(sb_handle_s* h, SbModel* m, int B, cudaStream_t rs, float* dst, int counts_slot) {
+  const size_t w = sb_record_width(m->bu.max_instances, m->bu.n_nodes);
+  if (m->gather.connected)
+    return sb_gather_queue_collect(h, m, m->gather.step - 1, B, dst, m->gather.counts_dev + counts_slot * SB_GATHER_MAX_WORLD, rs);
+  SB_CUDA(h, cudaMemcpyAsync(dst, m->ws.records, (size_t)B * w * sizeof(float), cudaMemcpyDeviceToHost, rs));
+  return 0;
+}
+static const float* own_slice(const SbModel* m, const float* staged, int B) {
+  return staged + (m->gather.connected ? (size_t)m->gather.rank * B * sb_record_width(m->bu.max_instances, m->bu.n_nodes) : 0);
+}
+static int check_exchange(sb_handle_s* h, SbModel* m) {
+  if (m->gather.connected && *m->gather.status_host != 0) {
+    const int st = *m->gather.status_host;
+    *m->gather.status_host = 0;
+    return sb_fail(h, SB_ERR_CUDA, "record exchange timed out (%s): a peer rank stopped pushing or consuming",
+                   st == SB_GATHER_TIMEOUT_ARRIVE ? "waiting for arrivals" : "waiting for acknowledgements");
+  }
+  return 0;
 }
 
 static void unpack_records(const SbModel* m, const float* rec, int B, float* out_instance_peaks, float* out_instance_peak_vals,
@@ -583,11 +605,12 @@ int sb_infer_bottomup(sb_handle_t h, int model_id, const uint8_t* frames_host, i
   if ((rc = bottomup_post(h, m, B))) return rc;
   cudaStream_t rs = h->post_pending ? h->post_stream : h->stream;
   if (!m->rec_host) SB_CUDA(h, cudaHostAlloc((void**)&m->rec_host, stage_floats(m) * sizeof(float), cudaHostAllocDefault));
-  const size_t w = sb_record_width(m->bu.max_instances, m->bu.n_nodes);
-  SB_CUDA(h, cudaMemcpyAsync(m->rec_host, m->ws.records, (size_t)B * w * sizeof(float), cudaMemcpyDeviceToHost, rs));
+  if ((rc = queue_result_copy(h, m, B, rs, m->rec_host, 3))) return rc;
   SB_CUDA(h, cudaStreamSynchronize(rs));
   h->post_pending = false;
-  unpack_records(m, m->rec_host, B, out_instance_peaks, out_instance_peak_vals, out_instance_scores, out_n_valid, out_flags);
+  m->rec_B = B;
+  if ((rc = check_exchange(h, m))) return rc;
+  unpack_records(m, own_slice(m, m->rec_host, B), B, out_instance_peaks, out_instance_peak_vals, out_instance_scores, out_n_valid, out_flags);
   return SB_OK;
 }
 
@@ -640,8 +663,8 @@ int sb_bottomup_submit(sb_handle_t h, int model_id, const uint8_t* frames_host, 
   SB_CUDA(h, cudaEventRecord(m->frames_free_ev[slot], h->stream));
   if ((rc = bottomup_post(h, m, B))) return rc;
   cudaStream_t rs = h->post_pending ? h->post_stream : h->stream;
-  SB_CUDA(h, cudaMemcpyAsync(m->stage_host[slot], m->ws.records,
-                             (size_t)B * sb_record_width(m->bu.max_instances, m->bu.n_nodes) * sizeof(float), cudaMemcpyDeviceToHost, rs));
+  if ((rc = queue_result_copy(h, m, B, rs, m->stage_host[slot], 1 + slot))) return rc;
+  m->slot_B[slot] = B;
   SB_CUDA(h, cudaEventRecord(m->result_ev[slot], rs));
   m->slot_used[slot] = true;
   return SB_OK;
@@ -654,7 +677,22 @@ int sb_bottomup_collect(sb_handle_t h, int model_id, int slot, int B, float* out
   if (!m || !m->bu_configured) return sb_fail(h, SB_ERR_INVALID, "bottom-up predictor not configured");
   if (slot < 0 || slot > 1 || !m->slot_used[slot] || B <= 0 || B > m->B) return sb_fail(h, SB_ERR_INVALID, "bad slot / batch");
   SB_CUDA(h, cudaEventSynchronize(m->result_ev[slot]));
-  unpack_records(m, m->stage_host[slot], B, out_instance_peaks, out_instance_peak_vals, out_instance_scores, out_n_valid, out_flags);
+  int rc = check_exchange(h, m);
+  if (rc) return rc;
+  unpack_records(m, own_slice(m, m->stage_host[slot], B), B, out_instance_peaks, out_instance_peak_vals, out_instance_scores, out_n_valid, out_flags);
+  return SB_OK;
+}
+
+int sb_bottomup_gathered(sb_handle_t h, int model_id, int slot, int B, float* out_records, int32_t* out_counts) {
+  SbModel* m = get_model(h, model_id);
+  if (!m || !m->bu_configured || !m->gather.connected) return sb_fail(h, SB_ERR_INVALID, "sb_bottomup_gathered: exchange not connected");
+  if (slot < -1 || slot > 1 || !out_records) return sb_fail(h, SB_ERR_INVALID, "sb_bottomup_gathered: bad slot");
+  const float* src = slot < 0 ? m->rec_host : m->stage_host[slot];
+  const int have = slot < 0 ? m->rec_B : m->slot_B[slot];
+  if (!src || have != B) return sb_fail(h, SB_ERR_INVALID, "sb_bottomup_gathered: no collected batch of %d frames in that slot", B);
+  memcpy(out_records, src, (size_t)m->gather.world * B * sb_record_width(m->bu.max_instances, m->bu.n_nodes) * sizeof(float));
+  if (out_counts)
+    for (int r = 0; r < m->gather.world; ++r) out_counts[r] = m->gather.counts_host[(slot < 0 ? 3 : 1 + slot) * SB_GATHER_MAX_WORLD + r];
   return SB_OK;
 }
 

@@ -78,6 +78,7 @@ struct SbModel {
   // double-buffered asynchronous pipeline (sb_bottomup_submit / sb_bottomup_collect)
   void* frames_slot[2] = {nullptr, nullptr};
   float* stage_host[2] = {nullptr, nullptr};     // pinned result staging (per-frame records)
+  int slot_B[2] = {0, 0}, rec_B = 0;            // frames of the batch last staged in each slot / in rec_host
   float* rec_host = nullptr;                     // pinned staging of the synchronous sb_infer_bottomup
   cudaEvent_t h2d_done_ev[2] = {nullptr, nullptr}, frames_free_ev[2] = {nullptr, nullptr}, result_ev[2] = {nullptr, nullptr};
   bool slot_used[2] = {false, false};
@@ -100,6 +101,9 @@ int sb_run_ops(sb_handle_s* h, SbModel* m, const void* frames_dev, int frames_ar
 // record exchange (sb_gather.cu)
 SbGatherDev sb_gather_dev(const SbModel* m, unsigned long long step);
 void sb_gather_free(SbModel* m);
+// queues on `s`: wait for every rank's records of `step`, copy the [world][B][width] window to host_dst, acknowledge
+int sb_gather_queue_collect(sb_handle_s* h, SbModel* m, long long step, int B, float* host_dst, int* counts_dev, cudaStream_t s);
+void sb_pipeline_slots_free(SbModel* m);
 
 // tensor-core conv path (sb_conv_tc.cu)
 int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m);      // after buffers are allocated

@@ -487,8 +487,8 @@ class BottomUpInferenceLayer(InferenceLayer):
         out = {"instance_peaks": ip[:, :n].copy(), "instance_peak_vals": iv[:, :n].copy(),
                "instance_scores": isc[:, :n].copy(), "n_valid": nv.astype(np.int64), "flags": fl}
         pg = getattr(m, "peer_gather", None)
-        if pg is not None:          # multi-GPU: this call was one exchange step; consume it (sb_gather_collect)
-            out["gathered_records"], out["gathered_counts"] = pg.collect_next(B, I, N)
+        if pg is not None:          # multi-GPU: this call was one exchange step; the window came over with the result copy
+            out["gathered_records"], out["gathered_counts"] = pg.gathered(-1, B, I, N)
         if self.return_confmaps or self.return_pafs:
             cms, pafs = m.forward(imgs, ["MultiInstanceConfmapsHead", "PartAffinityFieldsHead"])
             if self.return_confmaps:
@@ -604,8 +604,8 @@ class BottomUpInferenceModel(InferenceModel):
             out = {"instance_peaks": ip[:, :w], "instance_peak_vals": iv[:, :w], "instance_scores": isc[:, :w],
                    "n_valid": nv.astype(np.int64), "flags": fl}
             pg = getattr(m, "peer_gather", None)
-            if pg is not None:      # multi-GPU: every rank's records of this step, already in this rank's HBM (sb_gather_*)
-                out["gathered_records"], out["gathered_counts"] = pg.collect_next(B, I, N)
+            if pg is not None:      # multi-GPU: every rank's records of this step came over with the result copy (sb_gather_*)
+                out["gathered_records"], out["gathered_counts"] = pg.gathered(k % 2, B, I, N)
             yield out
 
     def predict(self, data, numpy: bool = True, batch_size: int = 4, **kwargs):

@@ -118,9 +118,10 @@ class PeerGather:
     windows through ``torch.distributed`` (any backend) and maps the peers.
 
     ``model``: a configured bottom-up ``DeviceModel`` (``sb_bottomup_configure`` done).  After construction every
-    ``sb_infer_bottomup*`` / ``sb_bottomup_submit`` call of that model is one exchange *step*; steps are consumed in
-    order, either on the device (``consume_next_dev``) or into host memory (``collect_next``).  A producer blocks only
-    when it is ``generations`` steps ahead of the slowest consumer."""
+    ``sb_infer_bottomup*`` / ``sb_bottomup_submit`` call of that model is one exchange *step*.  The host-facing calls
+    (``sb_infer_bottomup``, ``sb_bottomup_submit`` / ``collect``) consume their own step: the whole gather window rides on
+    the result copy they do anyway (``gathered``); the device-resident call (``sb_infer_bottomup_dev``) leaves consumption
+    to ``consume_next_dev``.  A producer blocks only when it is ``generations`` steps ahead of the slowest consumer."""
 
     def __init__(self, model, generations: int = 8, group=None):
         import ctypes
@@ -128,7 +129,6 @@ class PeerGather:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.generations = int(generations)
-        self.consumed = 0
         buf = ctypes.create_string_buffer(64)
         self.handle.call("sb_gather_init", model.model_id, self.rank, self.world, self.generations, buf)
         handles = [None] * self.world
@@ -155,18 +155,24 @@ class PeerGather:
             raise err
         model.peer_gather = self
 
-    def pushed(self) -> int:
+    def _status(self):
         import ctypes
-        st, n = ctypes.c_int32(0), ctypes.c_int64(0)
-        self.handle.call("sb_gather_status", self.model.model_id, ctypes.byref(st), ctypes.byref(n))
+        st, n, c = ctypes.c_int32(0), ctypes.c_int64(0), ctypes.c_int64(0)
+        self.handle.call("sb_gather_status", self.model.model_id, ctypes.byref(st), ctypes.byref(n), ctypes.byref(c))
         if st.value:
             raise RuntimeError(f"record exchange reported status {st.value} (1: arrivals timed out, 2: acknowledgements timed out)")
-        return int(n.value)
+        return int(n.value), int(c.value)
+
+    def pushed(self) -> int:
+        return self._status()[0]
+
+    @property
+    def consumed(self) -> int:
+        return self._status()[1]
 
     def consume_next_dev(self):
-        """Device consumer of the oldest unconsumed step (queued on the post-processing stream)."""
-        self.handle.call("sb_gather_consume_dev", self.model.model_id, self.consumed)
-        self.consumed += 1
+        """Device consumer of the oldest unconsumed step (wait + acknowledge, queued on the post-processing stream)."""
+        self.handle.call("sb_gather_consume_dev", self.model.model_id, -1)
 
     def window(self, step: int):
         """(device pointer, float count) of the [world][Bmax][width] window that holds ``step``."""
@@ -175,15 +181,15 @@ class PeerGather:
         self.handle.call("sb_gather_window", self.model.model_id, int(step), byref(p), byref(n))
         return p.value, n.value
 
-    def collect_next(self, B: int, max_instances: int, n_nodes: int):
-        """Host consumer of the oldest unconsumed step: (world*B, width) records in rank-major (= frame) order and the
-        number of frames every rank pushed."""
+    def gathered(self, slot: int, B: int, max_instances: int, n_nodes: int):
+        """Every rank's records of the batch last collected from ``slot`` (0 / 1: sb_bottomup_collect, -1: the synchronous
+        sb_infer_bottomup): (world*B, width) in rank-major (= frame) order + frames pushed per rank.  Host memory only: the
+        window came over with the batch's own result copy."""
         from sleap_b200._lib import ptr
         w = record_width(max_instances, n_nodes)
         out = np.zeros((self.world, B, w), np.float32)
         counts = np.zeros((self.world,), np.int32)
-        self.handle.call("sb_gather_collect", self.model.model_id, self.consumed, int(B), ptr(out), ptr(counts))
-        self.consumed += 1
+        self.handle.call("sb_bottomup_gathered", self.model.model_id, int(slot), int(B), ptr(out), ptr(counts))
         return out.reshape(self.world * B, w), counts
 
     def close(self):

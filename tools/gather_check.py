@@ -23,6 +23,7 @@ def main():
     B, I, C = 3, 16, 13
     w = parallel.record_width(I, C)
     frames = np.random.default_rng(100 + rank).integers(0, 256, size=(B * 13, 128, 128, 1), dtype=np.uint8)
+    pred.inference_model.predict_on_batch(frames[:B])                      # configures the device pipeline
     pg = parallel.PeerGather(model, generations=4)
     # (1) host consumer through the public predictor: 13 steps > 4 generations
     outs = pred.predict(frames, make_labels=False)
