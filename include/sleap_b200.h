@@ -297,6 +297,28 @@ int sb_infer_centroids(sb_handle_t h, int model_id, const void* images_host, int
                        int B, float* out_centroids, float* out_vals, int32_t* out_sample_inds,
                        int32_t* out_n, int32_t* out_flags);
 
+/* sleap/nn/inference.py:2273-2311 TopDownInferenceModel.call = CentroidCrop.call (:1747-1966) -> FindInstancePeaks.call
+ * (:2059-2200), as ONE device pipeline: frames are uploaded once, the centroid peaks, the per-frame top-k
+ * (tf.math.top_k(max_instances), :1879-1894), the crops (crop_bboxes on the resident frames, :1918-1927) and the
+ * centered-instance network + global peaks (+ crop offsets) never leave the GPU; results come back in one copy.
+ * Outputs are dense and NaN padded: centroids (B,K,2), centroid_vals (B,K), instance_peaks (B,K,n_nodes,2),
+ * instance_peak_vals (B,K,n_nodes) with K = max_centroids_per_frame; n_valid (B); flags (B).  The instance network is
+ * configured for max_crops_per_call crops of crop_size x crop_size and runs as often as the batch's crop count needs.
+ * Not covered (use the stage-level calls): instance models trained at an input scale != 1 (pre-crop resize). */
+typedef struct sb_topdown_params {
+  int32_t centroid_model, instance_model;
+  sb_centroid_params centroid;      /* as sb_centroid_configure */
+  sb_global_params instance;        /* as sb_global_configure */
+  int32_t crop_size;
+  int32_t max_instances;            /* top-k per frame by centroid confidence; <= 0: keep every centroid */
+  int32_t max_centroids_per_frame;  /* K */
+  int32_t max_crops_per_call;       /* batch the instance network is planned for */
+} sb_topdown_params;
+int sb_topdown_configure(sb_handle_t h, const sb_topdown_params* params, int max_batch, int H, int W, int C_in);
+int sb_infer_topdown(sb_handle_t h, int centroid_model_id, const void* frames_host, int frames_are_u8, int B,
+                     float* out_centroids, float* out_centroid_vals, float* out_instance_peaks,
+                     float* out_instance_peak_vals, int32_t* out_n_valid, int32_t* out_flags);
+
 #ifdef __cplusplus
 }
 #endif

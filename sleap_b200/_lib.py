@@ -56,6 +56,12 @@ class CentroidParams(ctypes.Structure):
     ]
 
 
+class TopdownParams(ctypes.Structure):
+    _fields_ = [("centroid_model", c_int32), ("instance_model", c_int32), ("centroid", CentroidParams), ("instance", GlobalParams),
+                ("crop_size", c_int32), ("max_instances", c_int32), ("max_centroids_per_frame", c_int32),
+                ("max_crops_per_call", c_int32)]
+
+
 # name -> argtypes (restype is always int unless noted)
 _SIGS = {
     "sb_version": [],
@@ -113,6 +119,8 @@ _SIGS = {
     "sb_gather_close": [c_void_p, c_int],
     "sb_global_configure": [c_void_p, c_int, POINTER(GlobalParams)],
     "sb_infer_global": [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "sb_topdown_configure": [c_void_p, POINTER(TopdownParams), c_int, c_int, c_int, c_int],
+    "sb_infer_topdown": [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "sb_centroid_configure": [c_void_p, c_int, POINTER(CentroidParams)],
     "sb_infer_centroids": [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                            c_void_p],

@@ -48,6 +48,7 @@ void sb_models_free(sb_handle_s* h) {
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     sb_post_ws_free(m->ws);
     sb_gather_free(m);
+    sb_topdown_free(m);
     sb_conv01_release(m);
     sb_conv_tc_release(m);
     delete m;

@@ -53,6 +53,7 @@ struct SbBuffer {
 
 struct SbConvTcPlan;  // sb_conv_tc.cu
 struct SbConv01Plan;  // sb_conv01.cu
+struct SbTopdown;     // sb_topdown.cu
 
 struct SbModel {
   int precision = 0;  // 0: fp16 activations + tensor-core convs; 1: fp32 CUDA-core path
@@ -89,14 +90,17 @@ struct SbModel {
   int g_rpc = 1, g_chunks = 1;
   sb_centroid_params ce{};
   bool ce_configured = false;
-  bool td_configured = false;
+  bool td_configured = false;              // fused top-down pipeline (sb_topdown_configure); state lives on the centroid model
+  SbTopdown* td = nullptr;
   SbConv01Plan* conv01 = nullptr;          // fused first encoder block (frame -> conv0 -> conv1 -> pool), sb_conv01.cu
   bool conv01_enabled = false;             // the autotuner measured it faster than the two separate launches
   SbGather gather;                         // peer-memory exchange of the result records (sb_gather.cu)
-  bool keep_dead_stores = false;           // sb_model_forward asked for a tensor whose stores are normally elided              // fused top-down pipeline (sb_topdown_configure)
+  bool keep_dead_stores = false;           // sb_model_forward asked for a tensor whose stores are normally elided
 };
 
 int sb_run_ops(sb_handle_s* h, SbModel* m, const void* frames_dev, int frames_are_u8, int B);
+
+void sb_topdown_free(SbModel* m);        // sb_topdown.cu
 
 // record exchange (sb_gather.cu)
 SbGatherDev sb_gather_dev(const SbModel* m, unsigned long long step);

@@ -19,7 +19,7 @@ from typing import Dict, List, Optional
 import numpy as np
 
 from sleap_b200 import _lib
-from sleap_b200._lib import BottomUpParams, CentroidParams, GlobalParams, f32, i32, ptr
+from sleap_b200._lib import BottomUpParams, CentroidParams, GlobalParams, TopdownParams, f32, i32, ptr
 from sleap_b200.nn import architectures as arch
 from sleap_b200.nn import paf_grouping, peak_finding
 from sleap_b200.nn.model import DeviceModel, PRECISION_FP16, PRECISION_FP32, load_weights, load_weights_npz
@@ -383,10 +383,56 @@ class TopDownInferenceModel(InferenceModel):
     def __init__(self, centroid_crop, instance_peaks):
         self.centroid_crop = centroid_crop
         self.instance_peaks = instance_peaks
+        self.fused = True            # one device pipeline (sb_infer_topdown) when both stages are device models
+        self._td_key = None
+
+    def _can_fuse(self):
+        cc, fp = self.centroid_crop, self.instance_peaks
+        return (self.fused and type(cc) is CentroidCrop and type(fp) is FindInstancePeaks and cc.precrop_resize == 1.0 and
+                cc.return_crops and not cc.return_confmaps and not fp.return_confmaps and cc.keras_model.handle is fp.keras_model.handle
+                and fp.keras_model.input_scale == 1.0)
+
+    def _call_fused(self, imgs):
+        """sb_infer_topdown: frames up once, centroid peaks / top-k / crops / instance network / peaks on the device, one
+        dense record back (include/sleap_b200.h)."""
+        cc, fp = self.centroid_crop, self.instance_peaks
+        imgs = cc._prep(imgs)
+        B, H, W, C = imgs.shape
+        mc, mi = cc.keras_model, fp.keras_model
+        K = int(cc.max_instances) if cc.max_instances else int(cc.max_peaks_per_sample)
+        cap = max(B, self._td_key[0]) if self._td_key else B
+        key = (cap, H, W, C, K, cc.peak_threshold, cc.refinement, cc.integral_patch_size, cc.input_scale, cc.max_peaks_per_sample,
+               cc.max_instances, cc.crop_size, fp.peak_threshold, fp.refinement, fp.integral_patch_size, fp.input_scale,
+               fp.max_crops_per_call)
+        if self._td_key != key or mc.configured_for != (cap, H, W, C) or mi.configured_for != (fp.max_crops_per_call, cc.crop_size, cc.crop_size, C):
+            p = TopdownParams(
+                mc.model_id, mi.model_id,
+                CentroidParams(cc.confmaps_buffer, -1 if cc.offsets_buffer is None else cc.offsets_buffer, int(cc.output_stride),
+                               float(cc.peak_threshold), REFINE.get(cc.refinement, 0), int(cc.integral_patch_size), float(cc.input_scale),
+                               int(cc.max_peaks_per_sample)),
+                GlobalParams(fp.confmaps_buffer, -1 if fp.offsets_buffer is None else fp.offsets_buffer, int(fp.output_stride),
+                             float(fp.peak_threshold), REFINE.get(fp.refinement, 0), int(fp.integral_patch_size), float(fp.input_scale)),
+                int(cc.crop_size), int(cc.max_instances or 0), K, int(fp.max_crops_per_call))
+            mc.handle.call("sb_topdown_configure", byref(p), cap, H, W, C)
+            mc.configured_for = (cap, H, W, C)
+            mi.configured_for = (fp.max_crops_per_call, cc.crop_size, cc.crop_size, C)
+            cc._cfg_key = fp._cfg_key = None
+            self._td_key = key
+        n_nodes = next(h["channels"] for h in mi.spec["heads"] if h["name"] == fp.HEAD)
+        ce = np.zeros((B, K, 2), np.float32); cv = np.zeros((B, K), np.float32)
+        ip = np.zeros((B, K, n_nodes, 2), np.float32); iv = np.zeros((B, K, n_nodes), np.float32)
+        nv = np.zeros((B,), np.int32); fl = np.zeros((B,), np.int32)
+        mc.handle.call("sb_infer_topdown", mc.model_id, ptr(imgs), int(imgs.dtype == np.uint8), B, ptr(ce), ptr(cv), ptr(ip), ptr(iv),
+                       ptr(nv), ptr(fl))
+        n = int(nv.max()) if B else 0
+        return {"centroids": ce[:, :n].copy(), "centroid_vals": cv[:, :n].copy(), "instance_peaks": ip[:, :n].copy(),
+                "instance_peak_vals": iv[:, :n].copy(), "n_valid": nv.astype(np.int64), "flags": fl}
 
     def call(self, example):
         if isinstance(example, np.ndarray):
             example = dict(image=example)
+        if self._can_fuse():
+            return self._call_fused(_images_of(example))
         crop_out = self.centroid_crop.call(example)
         if isinstance(self.instance_peaks, FindInstancePeaksGroundTruth):                 # :2300-2304
             peaks_out = self.instance_peaks.call(example, crop_out)

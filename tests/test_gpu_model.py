@@ -227,6 +227,19 @@ def test_topdown_predictor():
         assert n == int((csi == s).sum())
         assert_allclose(out["centroids"][s, :n], cp[csi == s], atol=1e-4)
         assert_allclose(out["instance_peaks"][s, :n], wp[csi == s], atol=5e-4, equal_nan=True)
+    # the fused device pipeline (sb_infer_topdown, default) and the stage-by-stage path (CentroidCrop -> FindInstancePeaks
+    # through host memory) run the same kernels on the same data: identical results, with and without the top-k cut
+    assert pred.inference_model._can_fuse()
+    for mi in (3, None, 1):
+        pred.inference_model.centroid_crop.max_instances = mi
+        pred.inference_model.fused = True
+        a = pred.inference_model.predict_on_batch(imgs)
+        pred.inference_model.fused = False
+        b = pred.inference_model.predict_on_batch(imgs)
+        assert_array_equal(a["n_valid"], b["n_valid"])
+        for k in ("centroids", "centroid_vals", "instance_peaks", "instance_peak_vals"):
+            assert_array_equal(np.nan_to_num(a[k], nan=-7.0), np.nan_to_num(b[k], nan=-7.0))
+    assert int(a["n_valid"].max()) == 1
 
 
 def test_tc_path_matches_direct_fp16(monkeypatch):
