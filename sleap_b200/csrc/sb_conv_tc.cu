@@ -27,7 +27,7 @@
 namespace {
 
 constexpr int TW = 16, TH = 8;          // output tile (pixels); M = 128
-constexpr int MAX_GROUPS = 3, MAX_TAPS = 3;
+constexpr int MAX_GROUPS = 7, MAX_TAPS = 7;   // filter columns / rows of the widest kernel taken (7x7); the 3x3 kernels unroll 3
 // dynamic shared memory every kernel here is opted in for (cudaFuncAttributeMaxDynamicSharedMemorySize); more than
 // half of the SM's 227 KB, so a launch padded to this size is guaranteed to run one CTA per SM
 constexpr size_t kMaxDynSmem = 210 * 1024;
@@ -333,7 +333,7 @@ __device__ __forceinline__ void tc_epilogue_acc(const TcParams& P, const float* 
   }
 }
 
-template <int KSTEPS>
+template <int KSTEPS, int MAXG = 3>   // MAXG: unroll bound of the filter-column / filter-row loops (3: 1x1 and 3x3, 7: 5x5 and 7x7)
 __global__ void __launch_bounds__(128) k_conv_tc(const __grid_constant__ CUtensorMap mapA,
                                                  const __grid_constant__ CUtensorMap mapB,
                                                  const __grid_constant__ TcParams P) {
@@ -404,13 +404,13 @@ __global__ void __launch_bounds__(128) k_conv_tc(const __grid_constant__ CUtenso
     const uint64_t desc_hi = make_desc(0, P.row_bytes, P.layout_type);
     for (int ch = 0; ch < P.n_chunks; ++ch) {
 #pragma unroll
-      for (int g = 0; g < MAX_GROUPS; ++g) {
+      for (int g = 0; g < MAXG; ++g) {
         if (g >= P.n_groups) break;
         mbar_wait(smem_u32(fullA + sa), pha, 3);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a_base = smem_u32(a_ring + (size_t)sa * P.a_slot_bytes);
 #pragma unroll
-        for (int t = 0; t < MAX_TAPS; ++t) {
+        for (int t = 0; t < MAXG; ++t) {
           if (t >= P.groups[g].n_taps) break;
           mbar_wait(smem_u32(fullB + sb), phb, 4);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -551,13 +551,13 @@ __global__ void __launch_bounds__(128) k_conv_tc_mc(const __grid_constant__ CUte
     const uint64_t desc_hi = make_desc(0, P.row_bytes, P.layout_type);
     for (int ch = 0; ch < P.n_chunks; ++ch) {
 #pragma unroll
-      for (int g = 0; g < MAX_GROUPS; ++g) {
+      for (int g = 0; g < 3; ++g) {
         if (g >= P.n_groups) break;
         mbar_wait(smem_u32(fullA + sa), pha, 43);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a_base = smem_u32(a_ring + (size_t)sa * P.a_slot_bytes);
 #pragma unroll
-        for (int t = 0; t < MAX_TAPS; ++t) {
+        for (int t = 0; t < 3; ++t) {
           if (t >= P.groups[g].n_taps) break;
           mbar_wait(smem_u32(fullB + sb), phb, 44);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -676,13 +676,13 @@ __global__ void __launch_bounds__(192) k_conv_tc_persist(const __grid_constant__
       const uint32_t d_tmem = tmem_base + (uint32_t)(stage * P.N);
       for (int ch = 0; ch < P.n_chunks; ++ch) {
 #pragma unroll
-        for (int g = 0; g < MAX_GROUPS; ++g) {
+        for (int g = 0; g < 3; ++g) {
           if (g >= P.n_groups) break;
           mbar_wait(smem_u32(fullA + sa), pha, 14);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_base = smem_u32(a_ring + (size_t)sa * P.a_slot_bytes);
 #pragma unroll
-          for (int tp = 0; tp < MAX_TAPS; ++tp) {
+          for (int tp = 0; tp < 3; ++tp) {
             if (tp >= P.groups[g].n_taps) break;
             const int slot = ch * P.n_used_taps + P.slot_of_tap[P.groups[g].taps[tp].w_tap];
             const uint64_t da = desc_hi + (uint64_t)((a_base + (uint32_t)(P.groups[g].taps[tp].row_off * TW * P.row_bytes)) >> 4);
@@ -1288,6 +1288,8 @@ struct SbConvTcPlan {
   float* view_bias = nullptr;       // bias replicated over the 8 pixels of a group: [8 * Cout]
   int view_Wg = 0;
   bool view_enabled = true;         // false: the autotuner measured k_conv_first faster for this shape
+  bool s2d = false;                 // view_in is the space-to-depth view of the frame (7x7 stride-2 stem as a 4x4 conv)
+  int s2d_Hs = 0, s2d_Ws = 0;
   bool out_dead = false;            // nobody reads the full-resolution output (only the fused pool): stores are skipped
   bool skip_now = false;            // out_dead, unless the caller asked for that buffer (sb_model_forward)
 };
@@ -1304,11 +1306,11 @@ static bool tc_eligible(const SbModel* m, const SbOp& op) {
   // chunk that reaches past C_in is zero-filled by TMA on both operands (activations and weights)
   if (!(Cin >= 16 && Cin % 8 == 0)) return false;
   if (getenv("SB_TC_STRICT_CIN") && !(Cin == 16 || Cin == 32 || Cin % 64 == 0)) return false;
-  if (op.kind() == SB_OPK_CONV && !((op.k() == 1 || op.k() == 3) && op.stride() == 1)) return false;
+  if (op.kind() == SB_OPK_CONV && !((op.k() == 1 || op.k() == 3 || op.k() == 5 || op.k() == 7) && op.stride() == 1)) return false;
   const SbBuffer& ib = m->buffers[op.in_buf()];
   const SbBuffer& ob = m->buffers[op.out_buf()];
   if (ib.f32) return false;
-  if (ib.W < TW || ib.H < TH + 2) return false;   // TMA box must fit inside the tensor
+  if (ib.W < TW || ib.H < TH + std::max(2, op.k() - 1)) return false;   // TMA box must fit inside the tensor
   if (ib.C % 8 || op.in_coff() % 8) return false;
   if (!ob.f32 && (ob.C % 8 || op.out_coff() % 8)) return false;
   return true;
@@ -1346,6 +1348,9 @@ struct TcView {
   int Cin, Cout;
   const float* bias;
   int relu;
+  const float* bn_scale = nullptr;
+  const float* bn_shift = nullptr;
+  int out_coff = 0;
 };
 
 static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan* plan, int n_groups,
@@ -1357,7 +1362,7 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
   const SbBuffer& ib = view ? view->ib : m->buffers[op.in_buf()];
   const SbBuffer& ob = view ? view->ob : m->buffers[op.out_buf()];
   const int Cin = view ? view->Cin : op.in_C(), Cout = view ? view->Cout : op.out_C();
-  const int in_coff = view ? 0 : op.in_coff(), out_coff = view ? 0 : op.out_coff();
+  const int in_coff = view ? 0 : op.in_coff(), out_coff = view ? view->out_coff : op.out_coff();
   const int KC = Cin > 32 ? 64 : (Cin > 16 ? 32 : 16);
   TcLaunch L;
   memset(&L, 0, sizeof(L));
@@ -1380,7 +1385,7 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
   P.out = ob.dev; P.out_f32 = ob.f32; P.out_H = ob.H; P.out_W = ob.W; P.out_Ctot = ob.C; P.out_coff = out_coff;
   P.oy_mul = oy_mul; P.oy_add = oy_add; P.ox_mul = ox_mul; P.ox_add = ox_add;
   if (view) {
-    P.bias = view->bias; P.bn_scale = nullptr; P.bn_shift = nullptr; P.relu = view->relu;
+    P.bias = view->bias; P.bn_scale = view->bn_scale; P.bn_shift = view->bn_shift; P.relu = view->relu;
   } else {
     P.bias = op.b_off() >= 0 ? m->weights_dev + op.b_off() : nullptr;
     P.bn_scale = (op.flags() & SB_OPF_BN) ? m->weights_dev + op.bn_scale_off() : nullptr;
@@ -1430,7 +1435,8 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
   P.tiles_per_img = P.tiles_x * tiles_y;
   L.has_persist = false;
   L.n_halo = 0;
-  {
+  const bool small_filter = n_wtaps <= 9 && n_groups <= 3;     // persistent / halo variants: 1x1, 3x3 and the transposed-conv phases
+  if (small_filter) {
     int used[9], n_used = 0, slot_of[9];
     for (int i = 0; i < 9; ++i) slot_of[i] = -1;
     for (int g = 0; g < n_groups; ++g)
@@ -1502,7 +1508,7 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
     n_shapes = 1;
     L.has_persist = false;
   }
-  for (int hs = 0; hs < n_shapes && L.pp_valid && !getenv("SB_DISABLE_HALO"); ++hs) {
+  for (int hs = 0; hs < n_shapes && L.pp_valid && small_filter && !getenv("SB_DISABLE_HALO"); ++hs) {
     const int sub_x = kHaloShapes[hs][0], sub_y = kHaloShapes[hs][1], egroups = kHaloShapes[hs][2];
     const int n_sub = sub_x * sub_y;
     const int pitch = fused_phases ? 9 : 8 * sub_x + 2, box_h = fused_phases ? 17 : 16 * sub_y + 2;
@@ -1648,7 +1654,7 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
     if (const char* e = getenv("SB_ENABLE_MULTICAST")) {
       const int cs = atoi(e);
       const int tiles = P.tiles_x * ((ib.H + TH - 1) / TH);
-      if ((cs == 2 || cs == 4) && tiles % cs == 0 && N % (8 * cs) == 0 && P.n_chunks * total_steps >= 2) {
+      if ((cs == 2 || cs == 4) && small_filter && tiles % cs == 0 && N % (8 * cs) == 0 && P.n_chunks * total_steps >= 2) {
         cuuint32_t pbox[3] = {(cuuint32_t)KC, (cuuint32_t)(N / cs), 1};
         CUresult r2 = enc(&L.mapBpiece, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)plan->w16, dims, strides, pbox, es,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz_for(KC), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1761,9 +1767,127 @@ static int first_view_prepare(sb_handle_s* h, SbModel* m, int oi) {
   return 0;
 }
 
+
+// ---- 7x7 stride-2 stem (hourglass.py:49-100; 1 or 3 input channels) on the tensor cores -----------------------
+// SAME padding of an even-sized input puts 2 rows / columns before and 3 after: output pixel o reads input rows
+// 2o-2 .. 2o+4.  With the frame regrouped into 2x2 blocks ("space to depth": block (Y, X) holds pixels (2Y+py, 2X+px),
+// 4*Cin values, padded to 16 channels) those are blocks o-1 .. o+2, i.e. a 4x4 stride-1 convolution over the block grid
+// with W'[dy][dx][(py, px, c)][co] = w[2(dy+1)+py][2(dx+1)+px][c][co] (zero where the index reaches 7).  The view kernel
+// does InferenceLayer.preprocess (uint8 -> float * 1/255, zero pad) on the way; the stock streaming tcgen05 kernel runs
+// the convolution (K = 16 taps x 16 channels = 256 instead of 147: the stem was on the CUDA cores before).
+template <typename TI>
+__global__ void __launch_bounds__(256) k_s2d_view(const TI* __restrict__ img, int Hin, int Win, int Cin, int Hs, int Ws,
+                                                  __half* __restrict__ G, int in_is_u8, size_t total) {
+  const float sc = in_is_u8 ? (1.0f / 255.0f) : 1.0f;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+    const int X = (int)(i % Ws);
+    const size_t r = i / Ws;
+    const int Y = (int)(r % Hs), b = (int)(r / Hs);
+    __align__(16) __half v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] = __float2half_rn(0.f);
+#pragma unroll
+    for (int py = 0; py < 2; ++py)
+#pragma unroll
+      for (int px = 0; px < 2; ++px) {
+        const int y = 2 * Y + py, x = 2 * X + px;
+        if (y < Hin && x < Win)
+          for (int c = 0; c < Cin; ++c)
+            v[(py * 2 + px) * Cin + c] = __float2half_rn(__fmul_rn((float)img[(((size_t)b * Hin + y) * Win + x) * Cin + c], sc));
+      }
+    uint4* dst = reinterpret_cast<uint4*>(G + i * 16);
+    dst[0] = *reinterpret_cast<const uint4*>(&v[0]);
+    dst[1] = *reinterpret_cast<const uint4*>(&v[8]);
+  }
+}
+
+int sb_stem_fusion_op(const SbModel* m, size_t pre_index);   // sb_model.cu
+
+static int stem_view_prepare(sb_handle_s* h, SbModel* m, int oi) {
+  if (getenv("SB_DISABLE_STEM_VIEW") || getenv("SB_DISABLE_TC")) return 0;
+  const SbOp& op = m->ops[oi];
+  const SbBuffer& ib = m->buffers[op.in_buf()];
+  const SbBuffer& ob = m->buffers[op.out_buf()];
+  const int Cin = op.in_C(), Cout = op.out_C();
+  if (ib.H % 2 || ib.W % 2 || ob.H != ib.H / 2 || ob.W != ib.W / 2) return 0;
+  if (ob.f32 || ob.C % 8 || op.out_coff() % 8 || ob.W < TW || ob.H < TH + 3) return 0;
+  SbConvTcPlan* plan = new SbConvTcPlan();
+  int cp = (Cout + 15) / 16 * 16;
+  if (cp > 256) cp = (cp + 255) / 256 * 256;
+  plan->Cout_pad = cp;
+  plan->s2d = true; plan->s2d_Hs = ob.H; plan->s2d_Ws = ob.W;
+  std::vector<__half> w16((size_t)16 * cp * 16, __float2half(0.f));
+  const float* w = m->weights_host.data() + op.w_off();      // [7*7][Cin][Cout]
+  for (int dy = 0; dy < 4; ++dy)
+    for (int dx = 0; dx < 4; ++dx)
+      for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+          const int ky = 2 * dy + py, kx = 2 * dx + px;
+          if (ky > 6 || kx > 6) continue;
+          for (int c = 0; c < Cin; ++c)
+            for (int co = 0; co < Cout; ++co)
+              w16[((size_t)(dy * 4 + dx) * cp + co) * 16 + (py * 2 + px) * Cin + c] = __float2half_rn(w[((size_t)(ky * 7 + kx) * Cin + c) * Cout + co]);
+        }
+  auto fail = [&](const char* what, cudaError_t e) {
+    if (plan->w16) cudaFree(plan->w16);
+    if (plan->view_in) cudaFree(plan->view_in);
+    delete plan;
+    return sb_fail(h, SB_ERR_CUDA, "stem view: %s: %s", what, cudaGetErrorString(e));
+  };
+  cudaError_t e = cudaMalloc((void**)&plan->w16, w16.size() * sizeof(__half));
+  if (e != cudaSuccess) return fail("cudaMalloc w16", e);
+  e = cudaMemcpy(plan->w16, w16.data(), w16.size() * sizeof(__half), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return fail("copy w16", e);
+  const size_t vbytes = (size_t)m->B * ob.H * ob.W * 16 * sizeof(__half);
+  e = cudaMalloc((void**)&plan->view_in, vbytes + 256);
+  if (e != cudaSuccess) return fail("cudaMalloc view", e);
+  e = cudaMemset(plan->view_in, 0, vbytes + 256);
+  if (e != cudaSuccess) return fail("memset view", e);
+  TcView V;
+  V.ib = SbBuffer(); V.ib.C = 16; V.ib.H = ob.H; V.ib.W = ob.W; V.ib.dev = plan->view_in;
+  V.ob = ob;
+  V.Cin = 16; V.Cout = Cout;
+  V.bias = op.b_off() >= 0 ? m->weights_dev + op.b_off() : nullptr;
+  V.relu = (op.flags() & SB_OPF_RELU) ? 1 : 0;
+  V.bn_scale = (op.flags() & SB_OPF_BN) ? m->weights_dev + op.bn_scale_off() : nullptr;
+  V.bn_shift = (op.flags() & SB_OPF_BN) ? m->weights_dev + op.bn_shift_off() : nullptr;
+  V.out_coff = op.out_coff();
+  TcGroup g[4];
+  for (int dx = 0; dx < 4; ++dx) {
+    g[dx].dx = dx - 1; g[dx].n_taps = 4;
+    for (int dy = 0; dy < 4; ++dy) g[dx].taps[dy] = TcTap{dy, dy * 4 + dx};
+  }
+  const int rc = make_launch(h, m, op, plan, 4, g, -1, 3, 16, 1, 0, 1, 0, 0, nullptr, &V);
+  if (rc) {
+    cudaFree(plan->w16); cudaFree(plan->view_in);
+    delete plan;
+    return rc < 0 ? rc : 0;
+  }
+  m->tc_plans[oi] = plan;
+  return 0;
+}
+
+bool sb_stem_view_can(const SbModel* m, int op_index) {
+  return op_index >= 0 && op_index < (int)m->tc_plans.size() && m->tc_plans[op_index] && m->tc_plans[op_index]->s2d;
+}
+
+// frame -> space-to-depth view -> tcgen05 4x4 conv
+int sb_stem_view_launch(sb_handle_s* h, SbModel* m, int op_index, const void* frames_dev, int frames_are_u8, int B) {
+  SbConvTcPlan* plan = m->tc_plans[op_index];
+  const size_t total = (size_t)B * plan->s2d_Hs * plan->s2d_Ws;
+  const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)h->sm_count * 16);
+  if (frames_are_u8)
+    k_s2d_view<unsigned char><<<grid, 256, 0, h->stream>>>((const unsigned char*)frames_dev, m->Hin, m->Win, m->Cin, plan->s2d_Hs, plan->s2d_Ws,
+                                                           plan->view_in, 1, total);
+  else
+    k_s2d_view<float><<<grid, 256, 0, h->stream>>>((const float*)frames_dev, m->Hin, m->Win, m->Cin, plan->s2d_Hs, plan->s2d_Ws, plan->view_in, 0, total);
+  SB_CHECK_LAUNCH(h);
+  return sb_conv_tc_launch(h, m, op_index, B);
+}
+
 bool sb_first_view_can(const SbModel* m, int op_index) {
   return op_index >= 0 && op_index < (int)m->tc_plans.size() && m->tc_plans[op_index] && m->tc_plans[op_index]->view_in &&
-         m->tc_plans[op_index]->view_enabled;
+         !m->tc_plans[op_index]->s2d && m->tc_plans[op_index]->view_enabled;
 }
 
 // frame -> Toeplitz view -> tcgen05 conv (the launch sb_conv_tc_autotune picked)
@@ -1792,6 +1916,9 @@ int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m) {
     SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    SB_CUDA(h, cudaFuncSetAttribute((k_conv_tc<1, 7>), cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    SB_CUDA(h, cudaFuncSetAttribute((k_conv_tc<2, 7>), cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    SB_CUDA(h, cudaFuncSetAttribute((k_conv_tc<4, 7>), cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_persist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_persist<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_persist<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
@@ -1831,13 +1958,13 @@ int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m) {
     e = cudaMemcpy(plan->w16, w16.data(), w16.size() * sizeof(__half), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(plan->w16); delete plan; return sb_fail(h, SB_ERR_CUDA, "copy w16: %s", cudaGetErrorString(e)); }
     int rc = 0;
-    if (op.kind() == SB_OPK_CONV && k == 3) {
-      TcGroup g[3];
-      for (int kx = 0; kx < 3; ++kx) {
-        g[kx].dx = kx - 1; g[kx].n_taps = 3;
-        for (int ky = 0; ky < 3; ++ky) g[kx].taps[ky] = TcTap{ky, ky * 3 + kx};
+    if (op.kind() == SB_OPK_CONV && k >= 3) {   // 3x3 / 5x5 / 7x7, stride 1, SAME: one staged tile per filter column, rows are start offsets
+      TcGroup g[MAX_GROUPS];
+      for (int kx = 0; kx < k; ++kx) {
+        g[kx].dx = kx - k / 2; g[kx].n_taps = k;
+        for (int ky = 0; ky < k; ++ky) g[kx].taps[ky] = TcTap{ky, ky * k + kx};
       }
-      rc = make_launch(h, m, op, plan, 3, g, -1, 2, 9, 1, 0, 1, 0);
+      rc = make_launch(h, m, op, plan, k, g, -(k / 2), k - 1, taps, 1, 0, 1, 0);
     } else if (op.kind() == SB_OPK_CONV) {   // 1x1
       TcGroup g[1];
       g[0].dx = 0; g[0].n_taps = 1; g[0].taps[0] = TcTap{0, 0};
@@ -1910,6 +2037,11 @@ int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m) {
         const int rc = first_view_prepare(h, m, cv);
         if (rc) return rc;
       }
+      const int sv = sb_stem_fusion_op(m, oi);
+      if (sv >= 0 && !m->tc_plans[sv]) {
+        const int rc = stem_view_prepare(h, m, sv);
+        if (rc) return rc;
+      }
     }
   // fused first encoder block: frame -> conv0 -> conv1 -> pool in one kernel (sb_conv01.cu) when conv1's own output is dead
   for (size_t oi = 0; oi + 2 < m->ops.size(); ++oi)
@@ -1970,6 +2102,16 @@ static void launch_variant(sb_handle_s* h, TcLaunch& L, int B, int variant, cuda
       if (L.mc_cluster == 2) { if (L.P.KC == 16) SB_MC(1, 2); else if (L.P.KC == 32) SB_MC(2, 2); else SB_MC(4, 2); }
       else { if (L.P.KC == 16) SB_MC(1, 4); else if (L.P.KC == 32) SB_MC(2, 4); else SB_MC(4, 4); }
 #undef SB_MC
+      return;
+    }
+    bool wide = L.P.n_groups > 3;                      // 5x5 / 7x7 (and the 4x4 space-to-depth stem): loops unrolled to 7
+    for (int gi = 0; gi < L.P.n_groups; ++gi) wide |= L.P.groups[gi].n_taps > 3;
+    if (wide) {
+      switch (L.P.KC) {
+        case 16: k_conv_tc<1, 7><<<g, 128, L.smem, stream>>>(L.mapA, L.mapB, L.P); break;
+        case 32: k_conv_tc<2, 7><<<g, 128, L.smem, stream>>>(L.mapA, L.mapB, L.P); break;
+        default: k_conv_tc<4, 7><<<g, 128, L.smem, stream>>>(L.mapA, L.mapB, L.P); break;
+      }
       return;
     }
     switch (L.P.KC) {
@@ -2066,7 +2208,7 @@ int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
   // first layer: Toeplitz tensor-core form (view kernel + the variant picked above) against k_conv_first
   for (size_t oi = 0; oi < m->tc_plans.size(); ++oi) {
     SbConvTcPlan* plan = m->tc_plans[oi];
-    if (!plan || !plan->view_in || !m->frames_dev) continue;
+    if (!plan || !plan->view_in || plan->s2d || !m->frames_dev) continue;
     float best[2] = {1e30f, 1e30f};
     for (int f = 0; f < 2; ++f)
       for (int rep = 0; rep < 4; ++rep) {

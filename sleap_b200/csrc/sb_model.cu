@@ -195,6 +195,22 @@ int sb_first_fusion_op(const SbModel* m, size_t pre_index) {
   return (int)pre_index + 1;
 }
 
+// 7x7 stride-2 stem right after PREPROCESS (hourglass.py:49-100) with 1 / 3 input channels and no resize: the conv op
+// index when the tensor-core space-to-depth form can take it (the PREPROCESS op is then fused into the view kernel).
+int sb_stem_fusion_op(const SbModel* m, size_t pre_index) {
+  if (m->precision != 0 || pre_index + 1 >= m->ops.size()) return -1;
+  const SbOp& pre = m->ops[pre_index];
+  const SbOp& cv = m->ops[pre_index + 1];
+  if (cv.kind() != SB_OPK_CONV || cv.in_buf() != pre.out_buf() || cv.k() != 7 || cv.stride() != 2) return -1;
+  if (pre.input_scale() != 1.0f) return -1;
+  const SbBuffer& ib = m->buffers[pre.out_buf()];
+  if (m->Cin != ib.C || (ib.C != 1 && ib.C != 3) || cv.in_C() != ib.C) return -1;
+  for (size_t i = pre_index + 2; i < m->ops.size(); ++i)      // nobody else may read the preprocessed frame
+    if (m->ops[i].kind() != SB_OPK_PREPROCESS && (m->ops[i].in_buf() == pre.out_buf() ||
+        (m->ops[i].kind() == SB_OPK_ADD && m->ops[i].in2_buf() == pre.out_buf()))) return -1;
+  return (int)pre_index + 1;
+}
+
 template <typename TI, int CIN>
 static void launch_first(int co, int B, cudaStream_t s, const TI* img, int Hin, int Win, int Hnet, int Wnet, __half* out,
                          int Ctot, int coff, const float* w, const float* b, int relu, int is_u8) {
@@ -235,7 +251,7 @@ int sb_first_direct_launch(sb_handle_s* h, SbModel* m, int op_index, const void*
 template <typename T>
 static int run_ops_t(sb_handle_s* h, SbModel* m, const void* frames_dev, int frames_are_u8, int B) {
   cudaStream_t s = h->stream;
-  int fused_first = -1, fused_conv1 = -1;
+  int fused_first = -1, fused_conv1 = -1, fused_stem = -1;
   for (size_t oi = 0; oi < m->ops.size(); ++oi) {
     const SbOp& op = m->ops[oi];
     if (!m->prof_events.empty()) cudaEventRecord(m->prof_events[oi], s);
@@ -243,6 +259,11 @@ static int run_ops_t(sb_handle_s* h, SbModel* m, const void* frames_dev, int fra
     if ((int)oi == m->guard_op && h->post_pending) SB_CUDA(h, cudaStreamWaitEvent(s, h->post_done_ev, 0));
     if (oi < m->skip_op.size() && m->skip_op[oi]) continue;     // 2x2 max-pool fused into the producing conv
     if ((int)oi == fused_conv1) continue;                       // ran inside the fused first block
+    if ((int)oi == fused_stem) {                                // 7x7 s2 stem: frame -> space-to-depth view -> tcgen05
+      int rc = sb_stem_view_launch(h, m, (int)oi, frames_dev, frames_are_u8, B);
+      if (rc) return rc;
+      continue;
+    }
     if ((int)oi == fused_first && sb_conv01_can(m, (int)oi) && !m->keep_dead_stores) {
       int rc = sb_conv01_launch(h, m, frames_dev, frames_are_u8, B);
       if (rc) return rc;
@@ -267,6 +288,7 @@ static int run_ops_t(sb_handle_s* h, SbModel* m, const void* frames_dev, int fra
     switch (op.kind()) {
       case SB_OPK_PREPROCESS: {
         if (sizeof(T) == 2 && (fused_first = first_fusion_op(m, oi)) >= 0) break;
+        if (sizeof(T) == 2 && sb_stem_view_can(m, sb_stem_fusion_op(m, oi))) { fused_stem = sb_stem_fusion_op(m, oi); break; }
         const size_t total = (size_t)B * ob.H * ob.W * ob.C;
         const int resize = op.input_scale() != 1.0f;
         int mode_ch = 0;

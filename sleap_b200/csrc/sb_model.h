@@ -123,6 +123,11 @@ bool sb_first_view_can(const SbModel* m, int op_index);
 int sb_first_view_launch(sb_handle_s* h, SbModel* m, int op_index, const void* frames_dev, int frames_are_u8, int B);
 int sb_first_direct_launch(sb_handle_s* h, SbModel* m, int op_index, const void* frames_dev, int frames_are_u8, int B);
 
+// 7x7 stride-2 stem through a space-to-depth view of the frame (sb_conv_tc.cu); conv op index or -1 (sb_model.cu)
+int sb_stem_fusion_op(const SbModel* m, size_t pre_index);
+bool sb_stem_view_can(const SbModel* m, int op_index);
+int sb_stem_view_launch(sb_handle_s* h, SbModel* m, int op_index, const void* frames_dev, int frames_are_u8, int B);
+
 // fused first encoder block (sb_conv01.cu)
 int sb_conv01_prepare(sb_handle_s* h, SbModel* m, int conv0_op, int conv1_op, bool conv1_out_dead);
 void sb_conv01_release(SbModel* m);

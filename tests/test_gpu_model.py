@@ -344,7 +344,8 @@ def test_tc_forced_variants_unet(variant, fused, monkeypatch):
                                            (128, 128, 3, (40, 48)), (256, 128, 3, (53, 70)), (128, 256, 3, (40, 48)),
                                            (256, 512, 3, (40, 48)), (64, 13, 1, (40, 48)), (128, 24, 1, (40, 48)),
                                            (24, 24, 3, (40, 48)), (48, 36, 3, (40, 48)), (96, 48, 3, (53, 70)),
-                                           (192, 96, 3, (40, 48)), (24, 13, 1, (40, 48))])
+                                           (192, 96, 3, (40, 48)), (24, 13, 1, (40, 48)),
+                                           (32, 32, 5, (40, 48)), (64, 48, 7, (53, 70)), (128, 64, 5, (40, 48)), (16, 16, 7, (40, 48))])
 def test_tc_single_layers(cin, cout, k, hw, variant, monkeypatch):
     """Each swizzle mode / chunk count / N-tile shape of the tensor-core conv on its own, with the
     kernel variant chosen by the autotuner (None) or forced: 0 streaming, 1 weights-resident,
@@ -584,3 +585,54 @@ def test_conv01_fused_first_block(hw, as_float, relu, monkeypatch):
     assert_allclose(got, want, atol=2.5e-3 * scale, rtol=0)      # one fp16 ulp of the intermediate propagated through 144 taps
     assert_allclose(got, sep, atol=2.5e-3 * scale, rtol=0)
     assert np.mean(np.abs(got - want) > 1e-3 * scale) < 1e-3     # ... and only on a handful of values
+
+
+@pytest.mark.parametrize("cin,cout,hw,as_float,bn", [(3, 32, (64, 96), False, True), (1, 16, (70, 130), False, False), (3, 128, (96, 64), True, True)])
+def test_tc_stem_7x7_stride2(cin, cout, hw, as_float, bn):
+    """Hourglass stem (hourglass.py:49-100): 7x7 stride-2 SAME convolution on 1 / 3 input channels as a 4x4 convolution over
+    the space-to-depth view of the frame on the tcgen05 path (sb_conv_tc.cu, stem_view_prepare), conv -> ReLU -> BN affine.
+    Reference: torch conv2d with TF SAME padding (2 before, 3 after for even sizes) on the fp16-rounded operands."""
+    from ctypes import byref, c_int, c_void_p
+    import torch
+    import torch.nn.functional as F
+    from sleap_b200 import _lib
+    from sleap_b200.nn import oplist as ol
+    H, W = hw
+    B = 2
+    rng = np.random.default_rng(cin * 100 + cout)
+    w0 = (rng.standard_normal((7, 7, cin, cout)) * np.sqrt(2.0 / (49 * cin))).astype(np.float32)
+    b0 = (rng.standard_normal(cout) * 0.1).astype(np.float32)
+    sc = rng.uniform(0.5, 1.5, cout).astype(np.float32); sh = (rng.standard_normal(cout) * 0.1).astype(np.float32)
+    eye = np.eye(cout, dtype=np.float32).reshape(-1)
+    blob = np.concatenate([w0.reshape(-1), b0, sc, sh, eye, np.zeros(cout, np.float32)]).astype(np.float32)
+    ob, osc, osh, oe = w0.size, w0.size + cout, w0.size + 2 * cout, w0.size + 3 * cout
+    recs = [ol.buffer_record(0, 1, cin, 0, 1), ol.buffer_record(1, 2, cout, 0, 0), ol.buffer_record(2, 2, cout, 1, 0),
+            ol.preprocess_record(0, cin, 1.0, 2),
+            ol.conv_record(0, 0, cin, 1, 0, cout, 7, 2, True, 0, ob, bn_scale_off=osc if bn else -1, bn_shift_off=osh if bn else -1),
+            ol.conv_record(1, 0, cout, 2, 0, cout, 1, 1, False, oe, oe + cout * cout)]
+    ops = np.ascontiguousarray(np.stack(recs).astype(np.int32))
+    if as_float:
+        imgs = rng.random((B, H, W, cin)).astype(np.float32); xin = imgs
+    else:
+        imgs = rng.integers(0, 256, size=(B, H, W, cin), dtype=np.uint8); xin = imgs.astype(np.float32) * np.float32(1.0 / 255.0)
+    Hn, Wn = -(-H // 2) * 2, -(-W // 2) * 2
+    h = _lib.default_handle()
+    mid = c_int(-1)
+    h.call("sb_load_model", _lib.ptr(ops), ops.shape[0], _lib.ptr(blob), int(blob.size), 0, byref(mid))
+    h.call("sb_model_configure", mid.value, B, H, W, cin)
+    out = np.zeros((B, Hn // 2, Wn // 2, cout), np.float32)
+    ids = np.asarray([2], np.int32)
+    ptrs = (c_void_p * 1)(out.ctypes.data)
+    h.call("sb_model_forward", mid.value, _lib.ptr(imgs), int(not as_float), B, 1, _lib.ptr(ids), ptrs)
+    dev = torch.zeros((B, H, W, cin), dtype=torch.uint8, device="cuda")
+    op_ms = np.zeros(8, np.float32); op_kind = np.zeros(8, np.int32); op_fl = np.zeros(8, np.float64)
+    n_ops = c_int(0)
+    h.call("sb_model_profile_ops", mid.value, c_void_p(dev.data_ptr()), B, 8, _lib.ptr(op_ms), _lib.ptr(op_kind), _lib.ptr(op_fl), byref(n_ops))
+    assert op_kind[1] == 1, list(op_kind[:n_ops.value])                   # the stem ran on the tensor-core path
+    x = torch.from_numpy(np.pad(xin, ((0, 0), (0, Hn - H), (0, Wn - W), (0, 0)))).half().float().permute(0, 3, 1, 2)
+    x = F.pad(x, (2, 3, 2, 3))                                               # TF SAME for k = 7, s = 2 on even sizes
+    y = torch.relu(F.conv2d(x, torch.from_numpy(w0).half().float().permute(3, 2, 0, 1), torch.from_numpy(b0), stride=2))
+    if bn:
+        y = y * torch.from_numpy(sc).view(1, -1, 1, 1) + torch.from_numpy(sh).view(1, -1, 1, 1)
+    want = y.half().float().permute(0, 2, 3, 1).numpy()
+    assert_allclose(out, want, atol=2e-3 * max(1.0, float(np.abs(want).max())), rtol=2e-3)
