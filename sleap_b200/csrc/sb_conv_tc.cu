@@ -1288,6 +1288,7 @@ struct SbConvTcPlan {
   float* view_bias = nullptr;       // bias replicated over the 8 pixels of a group: [8 * Cout]
   int view_Wg = 0;
   bool view_enabled = true;         // false: the autotuner measured k_conv_first faster for this shape
+  bool from_buffer = false;         // Toeplitz view built from the (resized / converted) PREPROCESS output instead of the raw frame
   bool s2d = false;                 // view_in is the space-to-depth view of the frame (7x7 stride-2 stem as a 4x4 conv)
   int s2d_Hs = 0, s2d_Ws = 0;
   bool out_dead = false;            // nobody reads the full-resolution output (only the fused pool): stores are skipped
@@ -1310,7 +1311,10 @@ static bool tc_eligible(const SbModel* m, const SbOp& op) {
   const SbBuffer& ib = m->buffers[op.in_buf()];
   const SbBuffer& ob = m->buffers[op.out_buf()];
   if (ib.f32) return false;
-  if (ib.W < TW || ib.H < TH + std::max(2, op.k() - 1)) return false;   // TMA box must fit inside the tensor
+  // feature maps smaller than the TMA box (16 px x 8 + k - 1 rows): the box simply hangs over the tensor, the overhang is
+  // zero-filled like every other out-of-image tap (SB_TC_MIN_BOX=1 restores round 1's rule that kept e.g. the 10x10 middle
+  // block of a 160x160 crop network -- 2/3 of its step time -- on the CUDA-core kernel)
+  if (getenv("SB_TC_MIN_BOX") && (ib.W < TW || ib.H < TH + std::max(2, op.k() - 1))) return false;
   if (ib.C % 8 || op.in_coff() % 8) return false;
   if (!ob.f32 && (ob.C % 8 || op.out_coff() % 8)) return false;
   return true;
@@ -1705,12 +1709,13 @@ int sb_first_fusion_op(const SbModel* m, size_t pre_index);   // sb_model.cu
 
 // Builds the plan of the first conv (op `oi`, fused with the PREPROCESS op before it) when the shape
 // allows the Toeplitz form; leaves m->tc_plans[oi] null otherwise (k_conv_first then runs the layer).
-static int first_view_prepare(sb_handle_s* h, SbModel* m, int oi) {
+static int first_view_prepare(sb_handle_s* h, SbModel* m, int oi, bool from_buffer = false) {
   if (getenv("SB_DISABLE_FIRST_VIEW") || getenv("SB_DISABLE_TC")) return 0;
   const SbOp& op = m->ops[oi];
   const SbBuffer& ob = m->buffers[op.out_buf()];
   const int Cout = op.out_C();
-  if (m->Cin != 1 || op.in_C() != 1 || op.k() != 3 || op.stride() != 1) return 0;
+  if ((!from_buffer && m->Cin != 1) || op.in_C() != 1 || op.k() != 3 || op.stride() != 1) return 0;
+  if (from_buffer && (m->buffers[op.in_buf()].C != 1 || m->buffers[op.in_buf()].f32 || op.in_coff() != 0)) return 0;
   if (!(Cout == 8 || Cout == 16 || Cout == 24 || Cout == 32)) return 0;           // N = 8*Cout <= 256, multiple of 16
   if (ob.f32 || ob.C != Cout || op.out_coff() != 0 || op.pool_buf() >= 0 || (op.flags() & SB_OPF_BN)) return 0;
   if (ob.W % 8 || ob.W / 8 < TW || ob.H < TH + 2) return 0;                        // the streaming TMA box must fit inside the view
@@ -1718,6 +1723,7 @@ static int first_view_prepare(sb_handle_s* h, SbModel* m, int oi) {
   SbConvTcPlan* plan = new SbConvTcPlan();
   plan->Cout_pad = N;
   plan->view_Wg = Wg;
+  plan->from_buffer = from_buffer;
   std::vector<__half> w16((size_t)3 * N * 16, __float2half(0.f));
   const float* w = m->weights_host.data() + op.w_off();                            // [9][1][Cout]
   for (int ky = 0; ky < 3; ++ky)
@@ -1887,7 +1893,25 @@ int sb_stem_view_launch(sb_handle_s* h, SbModel* m, int op_index, const void* fr
 
 bool sb_first_view_can(const SbModel* m, int op_index) {
   return op_index >= 0 && op_index < (int)m->tc_plans.size() && m->tc_plans[op_index] && m->tc_plans[op_index]->view_in &&
-         !m->tc_plans[op_index]->s2d && m->tc_plans[op_index]->view_enabled;
+         !m->tc_plans[op_index]->s2d && !m->tc_plans[op_index]->from_buffer && m->tc_plans[op_index]->view_enabled;
+}
+
+// First conv of a model whose frames are resized / converted first (input_scale != 1, rgb -> gray): the PREPROCESS kernel
+// runs as usual and the Toeplitz view is built from ITS one-channel fp16 output, so the layer still runs on tcgen05.
+bool sb_first_buffer_view_can(const SbModel* m, int op_index) {
+  return op_index >= 0 && op_index < (int)m->tc_plans.size() && m->tc_plans[op_index] && m->tc_plans[op_index]->view_in &&
+         m->tc_plans[op_index]->from_buffer;
+}
+
+int sb_first_buffer_view_launch(sb_handle_s* h, SbModel* m, int op_index, int B) {
+  SbConvTcPlan* plan = m->tc_plans[op_index];
+  const SbBuffer& ib = m->buffers[m->ops[op_index].in_buf()];
+  const SbBuffer& ob = m->buffers[m->ops[op_index].out_buf()];
+  const size_t total = (size_t)B * ob.H * plan->view_Wg;
+  const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)h->sm_count * 16);
+  k_first_view<__half><<<grid, 256, 0, h->stream>>>((const __half*)ib.dev, ib.H, ib.W, ob.H, plan->view_Wg, plan->view_in, 0, total);
+  SB_CHECK_LAUNCH(h);
+  return sb_conv_tc_launch(h, m, op_index, B);
 }
 
 // frame -> Toeplitz view -> tcgen05 conv (the launch sb_conv_tc_autotune picked)
@@ -2035,6 +2059,12 @@ int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m) {
       const int cv = sb_first_fusion_op(m, oi);
       if (cv >= 0 && !m->tc_plans[cv]) {
         const int rc = first_view_prepare(h, m, cv);
+        if (rc) return rc;
+      }
+      // not fusable with PREPROCESS (resize / channel conversion first): Toeplitz view of the preprocessed one-channel buffer
+      if (cv < 0 && oi + 1 < m->ops.size() && m->ops[oi + 1].kind() == SB_OPK_CONV && m->ops[oi + 1].in_buf() == m->ops[oi].out_buf() &&
+          m->ops[oi + 1].in_C() == 1 && !m->tc_plans[oi + 1]) {
+        const int rc = first_view_prepare(h, m, (int)oi + 1, true);
         if (rc) return rc;
       }
       const int sv = sb_stem_fusion_op(m, oi);
@@ -2208,7 +2238,7 @@ int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
   // first layer: Toeplitz tensor-core form (view kernel + the variant picked above) against k_conv_first
   for (size_t oi = 0; oi < m->tc_plans.size(); ++oi) {
     SbConvTcPlan* plan = m->tc_plans[oi];
-    if (!plan || !plan->view_in || plan->s2d || !m->frames_dev) continue;
+    if (!plan || !plan->view_in || plan->s2d || plan->from_buffer || !m->frames_dev) continue;
     float best[2] = {1e30f, 1e30f};
     for (int f = 0; f < 2; ++f)
       for (int rep = 0; rep < 4; ++rep) {

@@ -305,6 +305,11 @@ static int run_ops_t(sb_handle_s* h, SbModel* m, const void* frames_dev, int fra
       }
       case SB_OPK_CONV: {
         SbBuffer& ib = m->buffers[op.in_buf()];
+        if (m->precision == 0 && sb_first_buffer_view_can(m, (int)oi)) {
+          int rc = sb_first_buffer_view_launch(h, m, (int)oi, B);
+          if (rc) return rc;
+          break;
+        }
         if (m->precision == 0 && sb_conv_tc_can(m, (int)oi)) {
           int rc = sb_conv_tc_launch(h, m, (int)oi, B);
           if (rc) return rc;

@@ -121,6 +121,8 @@ int sb_first_fusion_op(const SbModel* m, size_t pre_index);
 // first layer as a Toeplitz GEMM on the stock tcgen05 conv kernels (sb_conv_tc.cu)
 bool sb_first_view_can(const SbModel* m, int op_index);
 int sb_first_view_launch(sb_handle_s* h, SbModel* m, int op_index, const void* frames_dev, int frames_are_u8, int B);
+bool sb_first_buffer_view_can(const SbModel* m, int op_index);
+int sb_first_buffer_view_launch(sb_handle_s* h, SbModel* m, int op_index, int B);
 int sb_first_direct_launch(sb_handle_s* h, SbModel* m, int op_index, const void* frames_dev, int frames_are_u8, int B);
 
 // 7x7 stride-2 stem through a space-to-depth view of the frame (sb_conv_tc.cu); conv op index or -1 (sb_model.cu)

@@ -9,6 +9,7 @@
 // crops H2D -> instance network (sleap_b200/nn/inference.py CentroidCrop / FindInstancePeaks, kept for the stage-level
 // surface and for models that need a pre-crop resize).
 #include <algorithm>
+#include <time.h>
 
 #include <math_constants.h>
 
@@ -184,7 +185,11 @@ int sb_infer_topdown(sb_handle_t h, int centroid_model_id, const void* frames_ho
   SB_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
   const size_t esz = frames_are_u8 ? 1 : 4;
+  static const bool dbg = getenv("SB_DEBUG_TD") != nullptr;      // stage timing (host clock around stream syncs), profiling only
+  auto now = []() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; };
+  double t0 = now(), t1 = 0, t2 = 0, t3 = 0;
   SB_CUDA(h, cudaMemcpyAsync(mc->frames_dev, frames_host, (size_t)B * mc->Hin * mc->Win * mc->Cin * esz, cudaMemcpyHostToDevice, s));
+  if (dbg) { cudaStreamSynchronize(s); t1 = now(); }
   int rc = sb_run_ops(h, mc, mc->frames_dev, frames_are_u8, B);
   if (rc) return rc;
   const sb_centroid_params& cp = mc->ce;
@@ -201,6 +206,7 @@ int sb_infer_topdown(sb_handle_t h, int centroid_model_id, const void* frames_ho
   SB_CUDA(h, cudaMemcpyAsync(t->total_host, t->total, 4, cudaMemcpyDeviceToHost, s));
   SB_CUDA(h, cudaStreamSynchronize(s));                     // the one mid-pipeline sync: how many crops the instance net runs on
   const int total = *t->total_host;
+  if (dbg) t2 = now();
   const sb_global_params& gp = mi->gl;
   SbBuffer& ib = mi->buffers[gp.cms_buffer];
   const float* ioff = gp.offsets_buffer >= 0 ? (const float*)mi->buffers[gp.offsets_buffer].dev : nullptr;
@@ -220,6 +226,11 @@ int sb_infer_topdown(sb_handle_t h, int centroid_model_id, const void* frames_ho
   SB_CHECK_LAUNCH(h);
   SB_CUDA(h, cudaMemcpyAsync(t->record_host, t->record, (size_t)B * t->width * 4, cudaMemcpyDeviceToHost, s));
   SB_CUDA(h, cudaStreamSynchronize(s));
+  if (dbg) {
+    t3 = now();
+    fprintf(stderr, "[sb_infer_topdown] B=%d crops=%d: H2D %.3f ms, centroid stage %.3f ms, instance stage + D2H %.3f ms\n", B, total, t1 - t0,
+            t2 - t1, t3 - t2);
+  }
   const size_t K = t->K, nd = t->nodes;
   for (int b = 0; b < B; ++b) {
     const float* r = t->record_host + (size_t)b * t->width;

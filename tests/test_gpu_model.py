@@ -77,6 +77,28 @@ def test_unet_forward_resize_and_rgb():
         assert_allclose(g, x, atol=1e-4 * max(1.0, np.abs(x).max()), rtol=1e-4)
 
 
+def test_unet_forward_resize_fp16_first_layer_on_tensor_cores():
+    """input_scale != 1 (and rgb -> gray): PREPROCESS runs as its own kernel and the first 3x3 conv takes the Toeplitz
+    tcgen05 form from the preprocessed one-channel buffer (sb_first_buffer_view_launch) instead of k_conv_direct."""
+    from ctypes import byref, c_int, c_void_p
+    import torch
+    from sleap_b200 import _lib
+    cfg = dict(filters=16, filters_rate=2, max_stride=16, output_stride=2, middle_block=True, up_interpolate=False)
+    spec = _unet_spec(cfg, HEADS2)
+    model, w, cm = _mk(spec, 1, 6, input_scale=0.5, precision=0)
+    imgs = np.random.default_rng(3).integers(0, 256, size=(2, 256, 320, 3), dtype=np.uint8)   # rgb -> gray -> resize 0.5
+    got = model.forward(imgs)
+    want = _oracle_forward(imgs, spec, w, 1, 0.5, cfg["max_stride"])
+    for g, x in zip(got, want):
+        assert np.abs(g - x).max() <= 2e-2 * np.abs(x).max()
+    h = model.handle
+    dev = torch.zeros((2, 256, 320, 3), dtype=torch.uint8, device="cuda")
+    op_ms = np.zeros(64, np.float32); op_kind = np.zeros(64, np.int32); op_fl = np.zeros(64, np.float64)
+    n_ops = c_int(0)
+    h.call("sb_model_profile_ops", model.model_id, c_void_p(dev.data_ptr()), 2, 64, _lib.ptr(op_ms), _lib.ptr(op_kind), _lib.ptr(op_fl), byref(n_ops))
+    assert 2 not in list(op_kind[:n_ops.value]), list(op_kind[:n_ops.value])       # no conv left on the CUDA-core kernel
+
+
 def test_hourglass_forward_fp32():
     spec = dict(backbone="hourglass", head_type="multi_instance", part_names=None, edges=None,
                 backbone_cfg=dict(stem_stride=4, max_stride=32, output_stride=4, stem_filters=8, filters=16, filter_increase=8, stacks=2),
@@ -345,7 +367,8 @@ def test_tc_forced_variants_unet(variant, fused, monkeypatch):
                                            (256, 512, 3, (40, 48)), (64, 13, 1, (40, 48)), (128, 24, 1, (40, 48)),
                                            (24, 24, 3, (40, 48)), (48, 36, 3, (40, 48)), (96, 48, 3, (53, 70)),
                                            (192, 96, 3, (40, 48)), (24, 13, 1, (40, 48)),
-                                           (32, 32, 5, (40, 48)), (64, 48, 7, (53, 70)), (128, 64, 5, (40, 48)), (16, 16, 7, (40, 48))])
+                                           (32, 32, 5, (40, 48)), (64, 48, 7, (53, 70)), (128, 64, 5, (40, 48)), (16, 16, 7, (40, 48)),
+                                           (192, 384, 3, (10, 10)), (384, 384, 3, (5, 7)), (64, 64, 3, (12, 20)), (96, 24, 1, (3, 3))])
 def test_tc_single_layers(cin, cout, k, hw, variant, monkeypatch):
     """Each swizzle mode / chunk count / N-tile shape of the tensor-core conv on its own, with the
     kernel variant chosen by the autotuner (None) or forced: 0 streaming, 1 weights-resident,
