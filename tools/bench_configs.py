@@ -21,7 +21,10 @@ FLIES13 = ["head", "thorax", "abdomen", "wingL", "wingR", "forelegL", "forelegR"
 
 
 def frames(n, h, w, c, seed):
-    return np.random.default_rng(seed).integers(0, 256, size=(n, h, w, c), dtype=np.uint8)
+    """Page-locked frame stack (what FrameFeeder hands the predictors): the upload is a true asynchronous DMA."""
+    import torch
+    a = np.random.default_rng(seed).integers(0, 256, size=(n, h, w, c), dtype=np.uint8)
+    return torch.from_numpy(a).pin_memory().numpy()
 
 
 def model_for(spec, in_ch, seed, input_scale=1.0):
