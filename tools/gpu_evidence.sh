@@ -41,8 +41,8 @@ timeout 400 python tools/bench_configs.py > $O/${PFX}_other_configs.jsonl 2> $O/
 echo "configs rc=$?"; cat $O/${PFX}_other_configs.jsonl
 echo "== compute-sanitizer"; date +%s
 timeout 600 compute-sanitizer --tool memcheck --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > $O/${PFX}_sanitizer_memcheck_smoke.log 2>&1; echo "memcheck smoke rc=$?"; tail -3 $O/${PFX}_sanitizer_memcheck_smoke.log
-timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize_step.py > $O/${PFX}_sanitizer_memcheck_c4_variants.log 2>&1; echo "memcheck variants rc=$?"; tail -4 $O/${PFX}_sanitizer_memcheck_c4_variants.log
-timeout 900 compute-sanitizer --tool racecheck --print-limit 20 python tools/sanitize_step.py quick > $O/${PFX}_sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -4 $O/${PFX}_sanitizer_racecheck.log
+timeout 900 compute-sanitizer --target-processes all --tool memcheck --print-limit 20 python tools/sanitize_step.py > $O/${PFX}_sanitizer_memcheck_c4_variants.log 2>&1; echo "memcheck variants rc=$?"; tail -4 $O/${PFX}_sanitizer_memcheck_c4_variants.log
+timeout 900 compute-sanitizer --target-processes all --tool racecheck --print-limit 20 python tools/sanitize_step.py quick > $O/${PFX}_sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -4 $O/${PFX}_sanitizer_racecheck.log
 if [ "${1:-}" != "skip_tests" ]; then
   echo "== pytest gpu"; date +%s
   timeout 900 python -m pytest tests -m gpu -q > $O/${PFX}_pytest_gpu.log 2>&1
