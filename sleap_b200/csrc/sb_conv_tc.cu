@@ -452,15 +452,7 @@ __global__ void __launch_bounds__(128) k_conv_tc(const __grid_constant__ CUtenso
 }
 
 
-// ---- EXPERIMENTAL (opt-in, SB_ENABLE_MULTICAST=2|4; not yet run on hardware) ---------------------------------
-// Streaming variant for thread-block clusters: the CS CTAs of a cluster work on CS neighbouring pixel tiles of
-// the same image and N tile, so they consume the same weight slices.  Each CTA fetches 1/CS of every [N x KC]
-// slice and TMA-multicasts it into the same ring slot of all CTAs of the cluster: the L2 -> SM weight traffic
-// (profiles/r01_l2_traffic.md: up to 28x the algorithmic bytes for the 512-channel layers) drops by CS.
-//   full barrier  (per CTA, per slot): expects the whole slice; every rank's multicast completes 1/CS of it.
-//   empty barrier (per CTA, per slot): CS arrivals -- every CTA's MMA warp multicasts its tcgen05.commit to the
-//                 cluster, so a slot is refilled only when all CTAs have finished reading it.
-// Activation tiles stay private.  Everything else (epilogue, parameters) is the streaming kernel's.
+// ---- thread-block cluster helpers (weight slices multicast to the CTAs of a cluster: k_conv_tc_prog<KSTEPS, 2>) ----
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -478,124 +470,6 @@ __device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* 
 __device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
                : "memory");
-}
-
-template <int KSTEPS, int CS>
-__global__ void __launch_bounds__(128) k_conv_tc_mc(const __grid_constant__ CUtensorMap mapA,
-                                                    const __grid_constant__ CUtensorMap mapBpiece,   // box [KC, N / CS, 1]
-                                                    const __grid_constant__ TcParams P) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* a_ring = base;
-  uint8_t* b_ring = a_ring + (size_t)P.n_a_slots * P.a_slot_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + (size_t)P.n_b_slots * P.b_slot_bytes);
-  uint64_t* fullA = bars;
-  uint64_t* emptyA = fullA + P.n_a_slots;
-  uint64_t* fullB = emptyA + P.n_a_slots;
-  uint64_t* emptyB = fullB + P.n_b_slots;
-  uint64_t* accum = emptyB + P.n_b_slots;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
-  float* s_par = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~(uintptr_t)15);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x;                       // the CS tiles of a cluster are consecutive in x
-  const int x0 = (tile % P.tiles_x) * TW, y0 = (tile / P.tiles_x) * TH;
-  const int n0 = blockIdx.y * P.N;
-  const int b = blockIdx.z;
-  const uint32_t rank = cluster_ctarank();
-  constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1u);
-  stage_params(P, s_par, n0);
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < P.n_a_slots; ++i) { mbar_init(smem_u32(fullA + i), 1); mbar_init(smem_u32(emptyA + i), 1); }
-    for (int i = 0; i < P.n_b_slots; ++i) { mbar_init(smem_u32(fullB + i), 1); mbar_init(smem_u32(emptyB + i), CS); }
-    mbar_init(smem_u32(accum), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBpiece) : "memory");
-  }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(P.tmem_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  cluster_sync_all();                                 // every CTA's barriers exist before anyone signals them remotely
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
-  const int piece_rows = P.N / CS;
-  const uint32_t piece_bytes = (uint32_t)(piece_rows * P.row_bytes);
-
-  if (warp == 0 && lane == 0) {
-    int sa = 0, sb = 0;
-    uint32_t pha = 0, phb = 0;
-    for (int ch = 0; ch < P.n_chunks; ++ch) {
-      for (int g = 0; g < P.n_groups; ++g) {
-        mbar_wait(smem_u32(emptyA + sa), pha ^ 1, 41);
-        mbar_expect_tx(smem_u32(fullA + sa), (uint32_t)P.a_tx_bytes);
-        tma_load_4d(smem_u32(a_ring + (size_t)sa * P.a_slot_bytes), &mapA, smem_u32(fullA + sa), ch * P.KC,
-                    x0 + P.groups[g].dx, y0 + P.dy0, b);
-        for (int t = 0; t < P.groups[g].n_taps; ++t) {
-          mbar_wait(smem_u32(emptyB + sb), phb ^ 1, 42);       // all CS CTAs are done with this slot
-          mbar_expect_tx(smem_u32(fullB + sb), (uint32_t)P.b_tx_bytes);
-          tma_load_3d_mc(smem_u32(b_ring + (size_t)sb * P.b_slot_bytes) + rank * piece_bytes, &mapBpiece, smem_u32(fullB + sb),
-                         ch * P.KC, n0 + (int)rank * piece_rows, P.groups[g].taps[t].w_tap, kMask);
-          if (++sb == P.n_b_slots) { sb = 0; phb ^= 1; }
-        }
-        if (++sa == P.n_a_slots) { sa = 0; pha ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    int sa = 0, sb = 0;
-    uint32_t pha = 0, phb = 0;
-    const uint64_t desc_hi = make_desc(0, P.row_bytes, P.layout_type);
-    for (int ch = 0; ch < P.n_chunks; ++ch) {
-#pragma unroll
-      for (int g = 0; g < 3; ++g) {
-        if (g >= P.n_groups) break;
-        mbar_wait(smem_u32(fullA + sa), pha, 43);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_base = smem_u32(a_ring + (size_t)sa * P.a_slot_bytes);
-#pragma unroll
-        for (int t = 0; t < 3; ++t) {
-          if (t >= P.groups[g].n_taps) break;
-          mbar_wait(smem_u32(fullB + sb), phb, 44);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t b_base = smem_u32(b_ring + (size_t)sb * P.b_slot_bytes);
-          const uint64_t da = desc_hi + (uint64_t)((a_base + (uint32_t)(P.groups[g].taps[t].row_off * TW * P.row_bytes)) >> 4);
-          const uint64_t db = desc_hi + (uint64_t)(b_base >> 4);
-          if (elect_one()) {
-#pragma unroll
-            for (int k = 0; k < KSTEPS; ++k)
-              tc_mma_f16(tmem_base, da + 2 * k, db + 2 * k, P.idesc, (ch | g | t | k) ? 1u : 0u);
-            tc_commit_mc(smem_u32(emptyB + sb), kMask);        // one arrival on every CTA's empty barrier of this slot
-          }
-          __syncwarp();
-          if (++sb == P.n_b_slots) { sb = 0; phb ^= 1; }
-        }
-        if (elect_one()) tc_commit(smem_u32(emptyA + sa));
-        __syncwarp();
-        if (++sa == P.n_a_slots) { sa = 0; pha ^= 1; }
-      }
-    }
-    if (elect_one()) tc_commit(smem_u32(accum));
-  }
-  __syncwarp();
-
-  mbar_wait(smem_u32(accum), 0, 45);
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const int m = warp * 32 + lane;
-  const int iy = y0 + m / TW, ix = x0 + m % TW;
-  const bool valid = (iy < P.H) && (ix < P.W);
-  const int oy = iy * P.oy_mul + P.oy_add, ox = ix * P.ox_mul + P.ox_add;
-  const size_t pix = ((size_t)b * P.out_H + oy) * P.out_W + ox;
-  tc_epilogue_acc<16, KSTEPS == 4>(P, s_par, tmem_base + ((uint32_t)(warp * 32) << 16), n0, valid, pix, b, x0, y0, warp, lane);
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  cluster_sync_all();                                 // nobody leaves while a peer may still signal its barriers
-  if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P.tmem_cols) : "memory");
-  }
 }
 
 
@@ -931,7 +805,13 @@ __device__ __forceinline__ uint32_t uni(uint32_t v) { return __shfl_sync(0xfffff
 // (TcProgEntry: activation start offset, weight slice, accumulator); the filter bank is either
 // resident in shared memory or streamed slice by slice through a ring (w_stream), in which case a
 // slice is consumed by all program entries that use it before the slot is released.
-template <int KSTEPS>
+// CS = 2: the launch is made of clusters of two CTAs (neighbouring tiles of one sweep) that consume the SAME sequence of
+// weight slices: each CTA fetches half of every [N x KC] slice and TMA-multicasts it into the same ring slot of both, so the
+// L2 -> SM weight traffic per output pixel halves (round 1: the >= 128-channel layers and the transposed convs sat on the
+// L2 read bandwidth, 10-28x read amplification, 37-57 % tensor-active).  A ring slot is refilled only when BOTH CTAs'
+// MMAs have consumed it (tcgen05.commit multicast to both empty barriers); every CTA walks the same number of tiles
+// (the host only launches this form when tiles % grid == 0).
+template <int KSTEPS, int CS = 1>
 __global__ void __launch_bounds__(320) k_conv_tc_prog(const __grid_constant__ CUtensorMap mapA,
                                                       const __grid_constant__ CUtensorMap mapB,
                                                       const __grid_constant__ TcParams P) {
@@ -959,7 +839,7 @@ __global__ void __launch_bounds__(320) k_conv_tc_prog(const __grid_constant__ CU
     for (int i = 0; i < P.n_a_slots; ++i) { mbar_init(smem_u32(fullA + i), 1); mbar_init(smem_u32(emptyA + i), 1); }
     for (int i = 0; i < P.n_stages; ++i) { mbar_init(smem_u32(tfull + i), 1); mbar_init(smem_u32(tempty + i), 4 * P.epi_groups); }
     mbar_init(smem_u32(wbar), 1);
-    for (int i = 0; i < 8; ++i) { mbar_init(smem_u32(fullW + i), 1); mbar_init(smem_u32(emptyW + i), 1); }
+    for (int i = 0; i < 8; ++i) { mbar_init(smem_u32(fullW + i), 1); mbar_init(smem_u32(emptyW + i), CS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
@@ -970,8 +850,12 @@ __global__ void __launch_bounds__(320) k_conv_tc_prog(const __grid_constant__ CU
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if constexpr (CS > 1) cluster_sync_all();          // every CTA's barriers exist before a peer signals them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t crank = CS > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1u);
+  const uint32_t piece_bytes = (uint32_t)(P.b_tx_bytes / CS);
 
   if (warp == 0 && lane == 0) {
     if (!w_stream) {
@@ -999,9 +883,13 @@ __global__ void __launch_bounds__(320) k_conv_tc_prog(const __grid_constant__ CU
         if (w_stream) {
           for (int i = 0; i < P.n_prog;) {              // same order as the MMA warp consumes the slices
             const uint32_t ew = P.prog[i].w_flags;
-            mbar_wait(smem_u32(emptyW + sw), phw ^ 1, 26);
+            mbar_wait(smem_u32(emptyW + sw), phw ^ 1, 26);                 // CS > 1: all CTAs of the cluster are done with this slot
             mbar_expect_tx(smem_u32(fullW + sw), (uint32_t)P.b_tx_bytes);
-            tma_load_3d(smem_u32(w_res + (size_t)sw * P.w_slot_bytes), &mapB, smem_u32(fullW + sw), ch * P.KC, 0, (int)((ew >> 26) & 15));
+            if constexpr (CS > 1)                                          // this CTA's 1/CS of the slice, into every CTA of the cluster
+              tma_load_3d_mc(smem_u32(w_res + (size_t)sw * P.w_slot_bytes) + crank * piece_bytes, &mapB, smem_u32(fullW + sw), ch * P.KC,
+                             (int)crank * (P.N / CS), (int)((ew >> 26) & 15), kMask);
+            else
+              tma_load_3d(smem_u32(w_res + (size_t)sw * P.w_slot_bytes), &mapB, smem_u32(fullW + sw), ch * P.KC, 0, (int)((ew >> 26) & 15));
             if (++sw == P.n_w_ring) { sw = 0; phw ^= 1; }
             i += (int)((ew >> 20) & 63);
           }
@@ -1055,7 +943,10 @@ __global__ void __launch_bounds__(320) k_conv_tc_prog(const __grid_constant__ CU
                              P.idesc, (accf | (uint32_t)k) ? 1u : 0u);
               }
             }
-            if (w_stream) tc_commit(smem_u32(emptyW + sw));
+            if (w_stream) {
+              if constexpr (CS > 1) tc_commit_mc(smem_u32(emptyW + sw), kMask);   // one arrival on every CTA's empty barrier of this slot
+              else tc_commit(smem_u32(emptyW + sw));
+            }
           }
           __syncwarp();
           if (w_stream) { if (++sw == P.n_w_ring) { sw = 0; phw ^= 1; } }
@@ -1107,6 +998,7 @@ __global__ void __launch_bounds__(320) k_conv_tc_prog(const __grid_constant__ CU
   __syncwarp();
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if constexpr (CS > 1) cluster_sync_all();          // nobody leaves while a peer may still multicast into it / signal its barriers
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P.tmem_cols) : "memory");
   }
@@ -1267,12 +1159,10 @@ struct TcLaunch {
   size_t smem_p;
   int occ;
   int use_persist;     // variant chosen at configure time by timing them on the device: 0 stream, 1 persist, 2 halo
-  CUtensorMap mapBpiece;   // experimental multicast streaming: box [KC, N / mc_cluster, 1]
-  int mc_cluster;          // 0 = off; 2 / 4 = cluster size of k_conv_tc_mc (SB_ENABLE_MULTICAST)
   // halo variants (variant id 2 + i): super-tiles of sub_x x sub_y 8x16 sub-tiles, box [KC, 8*sub_x+2, 16*sub_y+2, 1]
   bool pp_valid;       // PP holds the tap/slot tables (the launch covers all output channels with one N)
   int n_halo;
-  struct Halo { CUtensorMap map; TcParams P; size_t smem; int occ, threads; bool prog; } halo[4];
+  struct Halo { CUtensorMap map; TcParams P; size_t smem; int occ, threads; bool prog; int mc; CUtensorMap mapBpiece; } halo[6];
 };
 
 }  // namespace
@@ -1512,7 +1402,7 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
     n_shapes = 1;
     L.has_persist = false;
   }
-  for (int hs = 0; hs < n_shapes && L.pp_valid && small_filter && !getenv("SB_DISABLE_HALO"); ++hs) {
+  for (int hs = 0; hs < n_shapes && L.n_halo < 6 && L.pp_valid && small_filter && !getenv("SB_DISABLE_HALO"); ++hs) {
     const int sub_x = kHaloShapes[hs][0], sub_y = kHaloShapes[hs][1], egroups = kHaloShapes[hs][2];
     const int n_sub = sub_x * sub_y;
     const int pitch = fused_phases ? 9 : 8 * sub_x + 2, box_h = fused_phases ? 17 : 16 * sub_y + 2;
@@ -1629,7 +1519,22 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
     CUresult r = enc(&HC.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, gptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      swz_for(KC), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return sb_fail(h, SB_ERR_CUDA, "cuTensorMapEncodeTiled(A halo) failed: %d", (int)r);
+    HC.mc = 0;
     ++L.n_halo;
+    // cluster-multicast twin of a weight-streamed candidate: same plan, clusters of 2 CTAs, each fetching half of every slice
+    if (Hp.w_stream && HC.prog && N % 16 == 0 && L.n_halo < 6 && !getenv("SB_DISABLE_MULTICAST")) {
+      TcLaunch::Halo& H2 = L.halo[L.n_halo];
+      H2 = HC;
+      H2.mc = 2;
+      H2.occ = 1;
+      cuuint64_t wdims[3] = {(cuuint64_t)Cin, (cuuint64_t)plan->Cout_pad, (cuuint64_t)n_wtaps};
+      cuuint64_t wstrides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)plan->Cout_pad * Cin * 2};
+      cuuint32_t pbox[3] = {(cuuint32_t)KC, (cuuint32_t)(N / 2), 1};
+      cuuint32_t wes[3] = {1, 1, 1};
+      if (enc(&H2.mapBpiece, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)plan->w16, wdims, wstrides, pbox, wes, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              swz_for(KC), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+        ++L.n_halo;
+    }
   }
   if (fused_phases && L.n_halo == 0) return 1;     // caller falls back to the per-phase launches
   L.use_persist = 0;
@@ -1653,18 +1558,6 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz_for(KC), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return sb_fail(h, SB_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed: %d", (int)r);
-    // experimental: cluster multicast of the weight slices in the streaming variant
-    L.mc_cluster = 0;
-    if (const char* e = getenv("SB_ENABLE_MULTICAST")) {
-      const int cs = atoi(e);
-      const int tiles = P.tiles_x * ((ib.H + TH - 1) / TH);
-      if ((cs == 2 || cs == 4) && small_filter && tiles % cs == 0 && N % (8 * cs) == 0 && P.n_chunks * total_steps >= 2) {
-        cuuint32_t pbox[3] = {(cuuint32_t)KC, (cuuint32_t)(N / cs), 1};
-        CUresult r2 = enc(&L.mapBpiece, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)plan->w16, dims, strides, pbox, es,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz_for(KC), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r2 == CUDA_SUCCESS) L.mc_cluster = cs;
-      }
-    }
   }
   (dst ? *dst : plan->launches).push_back(L);
   return 0;
@@ -1952,14 +1845,9 @@ int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m) {
     SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_prog<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_halo<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_prog<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    if (getenv("SB_ENABLE_MULTICAST")) {
-      SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_mc<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-      SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_mc<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-      SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_mc<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-      SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_mc<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-      SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_mc<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-      SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_mc<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    }
+    SB_CUDA(h, cudaFuncSetAttribute((k_conv_tc_prog<1, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    SB_CUDA(h, cudaFuncSetAttribute((k_conv_tc_prog<2, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    SB_CUDA(h, cudaFuncSetAttribute((k_conv_tc_prog<4, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     attr_set = true;
   }
   for (size_t oi = 0; oi < m->ops.size(); ++oi) {
@@ -2093,6 +1981,27 @@ static void launch_variant(sb_handle_s* h, TcLaunch& L, int B, int variant, cuda
     P.n_tiles_total = P.tiles_per_img * B;
     const int grid = std::max(1, std::min(P.n_tiles_total, h->sm_count * HC.occ));
     if (getenv("SB_DEBUG_LAUNCH")) fprintf(stderr, "[halo %dx%d] KC=%d N=%d stages=%d cols=%d occ=%d grid=%d slots=%d smem=%zu tiles=%d thr=%d\n", P.sub_x, P.sub_y, P.KC, P.N, P.n_stages, P.tmem_cols, HC.occ, grid, P.n_a_slots, HC.smem, P.n_tiles_total, HC.threads);
+    if (HC.mc) {
+      // clusters of 2: every CTA must walk the same number of tiles -> the largest even grid that divides the tile count
+      int g2 = std::min(P.n_tiles_total, h->sm_count) & ~1;
+      while (g2 >= 2 && P.n_tiles_total % g2) g2 -= 2;
+      if (g2 < 2 || 4 * g2 < 3 * std::min(P.n_tiles_total, h->sm_count)) {      // no such grid (or it idles > 1/4 of the SMs): the unicast twin
+        launch_variant(h, L, B, variant - 1, stream, skip_out);
+        return;
+      }
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(g2); cfg.blockDim = dim3(HC.threads); cfg.dynamicSmemBytes = HC.smem; cfg.stream = stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      switch (P.KC) {
+        case 16: cudaLaunchKernelEx(&cfg, k_conv_tc_prog<1, 2>, HC.map, HC.mapBpiece, P); break;
+        case 32: cudaLaunchKernelEx(&cfg, k_conv_tc_prog<2, 2>, HC.map, HC.mapBpiece, P); break;
+        default: cudaLaunchKernelEx(&cfg, k_conv_tc_prog<4, 2>, HC.map, HC.mapBpiece, P); break;
+      }
+      return;
+    }
     if (HC.prog) {
       switch (P.KC) {
         case 16: k_conv_tc_prog<1><<<grid, HC.threads, HC.smem, stream>>>(HC.map, L.mapB, P); break;
@@ -2121,19 +2030,6 @@ static void launch_variant(sb_handle_s* h, TcLaunch& L, int B, int variant, cuda
     dim3 g = L.grid;
     g.z = B;
     L.P.skip_out = skip_out;
-    if (L.mc_cluster) {                 // experimental (SB_ENABLE_MULTICAST): clusters of mc_cluster CTAs along the tile axis
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = g; cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = L.smem; cfg.stream = stream;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = (unsigned)L.mc_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-      cfg.attrs = at; cfg.numAttrs = 1;
-#define SB_MC(KS, CS_) cudaLaunchKernelEx(&cfg, k_conv_tc_mc<KS, CS_>, L.mapA, L.mapBpiece, L.P)
-      if (L.mc_cluster == 2) { if (L.P.KC == 16) SB_MC(1, 2); else if (L.P.KC == 32) SB_MC(2, 2); else SB_MC(4, 2); }
-      else { if (L.P.KC == 16) SB_MC(1, 4); else if (L.P.KC == 32) SB_MC(2, 4); else SB_MC(4, 4); }
-#undef SB_MC
-      return;
-    }
     bool wide = L.P.n_groups > 3;                      // 5x5 / 7x7 (and the 4x4 space-to-depth stem): loops unrolled to 7
     for (int gi = 0; gi < L.P.n_groups; ++gi) wide |= L.P.groups[gi].n_taps > 3;
     if (wide) {
@@ -2182,7 +2078,12 @@ int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
         SbConvTcPlan* plan = m->tc_plans[oi];
         if (li == -3) { m->conv01_enabled = m->conv01 && pick != 0; ++applied; continue; }
         if (li == -2) { plan->view_enabled = pick != 0; ++applied; continue; }
-        if (li < 0) { plan->use_fused = pick != 0 && !plan->fused.empty(); ++applied; continue; }
+        if (li < 0) {
+          plan->use_fused = pick != 0 && !plan->fused.empty();
+          for (TcLaunch& F : plan->fused) F.use_persist = (pick == 2 && F.n_halo >= 2) ? 3 : 2;
+          ++applied;
+          continue;
+        }
         if (li >= (int)plan->launches.size()) continue;
         TcLaunch& L = plan->launches[li];
         L.use_persist = avail(L, pick) ? pick : 0;
@@ -2201,8 +2102,8 @@ int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
     if (!plan) continue;
     for (TcLaunch& L : plan->launches) {
       if (!L.has_persist && L.n_halo == 0) continue;
-      float best[6] = {1e30f, 1e30f, 1e30f, 1e30f, 1e30f, 1e30f};
-      for (int v = 0; v < 6; ++v) {
+      float best[8] = {1e30f, 1e30f, 1e30f, 1e30f, 1e30f, 1e30f, 1e30f, 1e30f};
+      for (int v = 0; v < 8; ++v) {
         if (!avail(L, v)) continue;
         for (int rep = 0; rep < 3; ++rep) {
           cudaEventRecord(e0, h->stream);
@@ -2223,14 +2124,15 @@ int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
         }
       }
       int pick = 0;
-      for (int v = 1; v < 6; ++v) if (best[v] < best[pick]) pick = v;
+      for (int v = 1; v < 8; ++v) if (best[v] < best[pick]) pick = v;
       L.use_persist = pick;
       if (dbg) {
         fprintf(stderr, "[sb_conv_tc] op %zu Cin=%d N=%d %dx%d: stream %.1f, persist %.1f (occ %d, %d slots)", oi, L.P.n_chunks * L.P.KC,
                 L.P.N, L.P.H, L.P.W, best[0] * 1e3f, best[1] * 1e3f, L.occ, L.PP.n_a_slots);
         for (int i = 0; i < L.n_halo; ++i)
-          fprintf(stderr, ", halo%dx%d%s %.1f (occ %d, %d slots, %d stages)", L.halo[i].P.sub_x, L.halo[i].P.sub_y,
-                  L.halo[i].P.w_stream ? "w" : "", best[2 + i] * 1e3f, L.halo[i].occ, L.halo[i].P.n_a_slots, L.halo[i].P.n_stages);
+          fprintf(stderr, ", halo%dx%d%s%s %.1f (occ %d, %d slots, %d stages)", L.halo[i].P.sub_x, L.halo[i].P.sub_y,
+                  L.halo[i].P.w_stream ? "w" : "", L.halo[i].mc ? "-mc2" : "", best[2 + i] * 1e3f, L.halo[i].occ, L.halo[i].P.n_a_slots,
+                  L.halo[i].P.n_stages);
         fprintf(stderr, " us -> %d\n", pick);
       }
     }
@@ -2287,11 +2189,14 @@ int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
   for (size_t oi = 0; oi < m->tc_plans.size(); ++oi) {
     SbConvTcPlan* plan = m->tc_plans[oi];
     if (!plan || plan->fused.empty()) continue;
-    float best[2] = {1e30f, 1e30f};
-    for (int f = 0; f < 2; ++f)
+    float best[3] = {1e30f, 1e30f, 1e30f};             // 4 phase launches | fused | fused with cluster-multicast weight slices
+    bool has_mc = true;
+    for (TcLaunch& F : plan->fused) has_mc &= F.n_halo >= 2 && F.halo[1].mc != 0;
+    for (int f = 0; f < (has_mc ? 3 : 2); ++f)
       for (int rep = 0; rep < 4; ++rep) {
+        for (TcLaunch& F : plan->fused) F.use_persist = f == 2 ? 3 : 2;
         cudaEventRecord(e0, h->stream);
-        int rc = launch_plan(h, plan, m->B, f == 1);
+        int rc = launch_plan(h, plan, m->B, f >= 1);
         if (rc) return rc;
         cudaEventRecord(e1, h->stream);
         cudaError_t e = cudaStreamSynchronize(h->stream);
@@ -2300,13 +2205,16 @@ int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
         cudaEventElapsedTime(&ms, e0, e1);
         if (rep > 0) best[f] = std::min(best[f], ms);
       }
-    plan->use_fused = best[1] < best[0];
+    const bool mc_wins = best[2] < best[1];
+    for (TcLaunch& F : plan->fused) F.use_persist = mc_wins ? 3 : 2;
+    plan->use_fused = std::min(best[1], best[2]) < best[0];
     if (getenv("SB_FORCE_FUSED_TCONV")) plan->use_fused = atoi(getenv("SB_FORCE_FUSED_TCONV")) != 0;
     if (dbg) {
       const TcParams& F = plan->fused[0].halo[0].P;
       fprintf(stderr, "[sb_conv_tc] op %zu tconv Cin=%d N=%d: 4 phase launches %.1f us, fused x%zu (%s, %d stages, %d slots) %.1f us -> %s\n", oi,
               F.n_chunks * F.KC, F.N, best[0] * 1e3f, plan->fused.size(), F.w_stream ? "streamed weights" : "resident weights", F.n_stages,
-              F.n_a_slots, best[1] * 1e3f, plan->use_fused ? "fused" : "phases");
+              F.n_a_slots, best[1] * 1e3f, plan->use_fused ? (mc_wins ? "fused-mc2" : "fused") : "phases");
+      if (has_mc) fprintf(stderr, "[sb_conv_tc] op %zu tconv fused with cluster-multicast weights: %.1f us\n", oi, best[2] * 1e3f);
     }
   }
   cudaEventDestroy(e0);
@@ -2317,7 +2225,7 @@ int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
         SbConvTcPlan* plan = m->tc_plans[oi];
         if (!plan) continue;
         for (size_t li = 0; li < plan->launches.size(); ++li) fprintf(f, "%zu %zu %d\n", oi, li, plan->launches[li].use_persist);
-        if (!plan->fused.empty()) fprintf(f, "%zu -1 %d\n", oi, plan->use_fused ? 1 : 0);
+        if (!plan->fused.empty()) fprintf(f, "%zu -1 %d\n", oi, plan->use_fused ? (plan->fused[0].use_persist == 3 ? 2 : 1) : 0);
         if (plan->view_in) fprintf(f, "%zu -2 %d\n", oi, plan->view_enabled ? 1 : 0);
         if (m->conv01 && (int)oi == sb_conv01_conv1_op(m)) fprintf(f, "%zu -3 %d\n", oi, m->conv01_enabled ? 1 : 0);
       }
@@ -2336,7 +2244,7 @@ int sb_conv_tc_launch(sb_handle_s* h, SbModel* m, int op_index, int B) {
 static int launch_plan(sb_handle_s* h, SbConvTcPlan* plan, int B, bool fused) {
   if (fused) {
     for (TcLaunch& L : plan->fused) {
-      launch_variant(h, L, B, 2, h->stream);
+      launch_variant(h, L, B, L.use_persist >= 2 ? L.use_persist : 2, h->stream);
       SB_CHECK_LAUNCH(h);
     }
     return 0;

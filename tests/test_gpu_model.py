@@ -534,17 +534,6 @@ def test_first_layer_toeplitz_view(cout, hw, as_float, variant, monkeypatch):
     assert_allclose(got, direct, atol=4e-3 * scale, rtol=0)          # direct kernel keeps fp32 pixels / weights
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("SB_TEST_EXPERIMENTAL"),
-                    reason="experimental cluster-multicast streaming kernel (SB_ENABLE_MULTICAST): opt-in, not yet run on hardware")
-@pytest.mark.parametrize("cs", ["2", "4"])
-@pytest.mark.parametrize("cin,cout,hw", [(64, 64, (64, 64)), (128, 128, (32, 32)), (256, 256, (32, 64)), (512, 256, (32, 32))])
-def test_tc_multicast_streaming(cs, cin, cout, hw, monkeypatch):
-    """k_conv_tc_mc: clusters of 2 / 4 CTAs share every weight slice through TMA multicast; same answers as the
-    streaming kernel.  Run with SB_TEST_EXPERIMENTAL=1."""
-    monkeypatch.setenv("SB_ENABLE_MULTICAST", cs)
-    test_tc_single_layers(cin, cout, 3, hw, "0", monkeypatch)
-
-
 @pytest.mark.parametrize("hw,as_float,relu", [((64, 64), False, True), ((34, 1056), False, True), ((96, 520), True, True),
                                               ((40, 516), False, False)])
 def test_conv01_fused_first_block(hw, as_float, relu, monkeypatch):
