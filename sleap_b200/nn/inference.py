@@ -801,6 +801,8 @@ class Predictor:
                 ex = self.inference_model.predict_on_batch(batch if use_gt else batch["image"])
                 ex["frame_ind"], ex["video_ind"] = batch["frame_ind"], batch["video_ind"]
                 ex["image_hw"] = tuple(batch["image"].shape[1:3])
+                if self.tracker is not None and getattr(self.tracker, "uses_image", False):
+                    ex["image"] = batch["image"]
                 self._check_flags(ex)
                 yield ex
             return
@@ -810,6 +812,7 @@ class Predictor:
         try:
             if hasattr(self.inference_model, "predict_batches"):      # pipelined device loop (upload i+1 || compute i)
                 i0 = 0
+                want_img = self.tracker is not None and getattr(self.tracker, "uses_image", False)   # flow trackers (:2664-2671)
                 imgs_all = _images_of(data)
                 hw = tuple(np.asarray(imgs_all[0]).shape[:2]) if len(imgs_all) else (1, 1)
                 for ex in self.inference_model.predict_batches(imgs_all, self.batch_size):
@@ -817,6 +820,8 @@ class Predictor:
                     ex["frame_ind"] = frame_inds(i0, i0 + n)
                     ex["video_ind"] = np.zeros(n, np.int64)
                     ex["image_hw"] = hw
+                    if want_img:
+                        ex["image"] = np.stack([np.asarray(imgs_all[j]) for j in range(i0, i0 + n)])
                     i0 += n
                     self._check_flags(ex)
                     yield ex
@@ -826,6 +831,8 @@ class Predictor:
                 ex["frame_ind"] = frame_inds(i0, i0 + len(batch))
                 ex["video_ind"] = np.zeros(len(batch), np.int64)
                 ex["image_hw"] = tuple(batch.shape[1:3])
+                if self.tracker is not None and getattr(self.tracker, "uses_image", False):
+                    ex["image"] = batch
                 self._check_flags(ex)
                 yield ex
         finally:
@@ -890,8 +897,9 @@ class Predictor:
                 new = self._frames_from_example(ex)
                 if self.tracker is not None:                     # sequential by nature; runs on the consumer thread
                     hw = tuple(ex.get("image_hw") or (1, 1))
-                    for lf in new:
-                        lf.instances = self.tracker.track(lf.instances, img_hw=hw, t=lf.frame_idx)
+                    for k, lf in enumerate(new):
+                        img = ex["image"][k] if "image" in ex else None
+                        lf.instances = self.tracker.track(lf.instances, img_hw=hw, img=img, t=lf.frame_idx)
                 frames.extend(new)
 
         t = threading.Thread(target=worker)

@@ -2,12 +2,15 @@
 
 Restates the default tracker of the reference -- candidates from the last ``track_window`` frames, one similarity
 value per (instance, track), greedy or Hungarian assignment, new tracks for the unmatched, optional cap on the
-number of tracks -- without optical-flow shifting and without the Kalman variant:
+number of tracks -- and the optical-flow variant that first shifts the candidates of earlier frames into the current frame
+(Lucas-Kanade through OpenCV, exactly the library call the reference makes); the Kalman variant is not built:
   sleap/nn/tracker/components.py:33-196   similarity functions (instance, normalized, object keypoint, centroid, IoU)
   sleap/nn/tracker/components.py:198-226  hungarian_matching / greedy_matching, :637-647 first_choice_matching
   sleap/nn/tracker/components.py:229-313  nms_instances / nms_fast, :316-422 cull_instances / cull_frame_instances
   sleap/nn/tracker/components.py:457-634  Match, FrameMatches
   sleap/nn/tracking.py:442-492            SimpleCandidateMaker, SimpleMaxTracksCandidateMaker
+  sleap/nn/tracking.py:33-86, 108-360     ShiftedInstance, FlowCandidateMaker (flow_shift_instances, saved shifts, pruning)
+  sleap/nn/tracking.py:363-440            FlowMaxTracksCandidateMaker
   sleap/nn/tracking.py:542-844            Tracker.track / spawn / queues, :844-995 make_tracker_by_name
 Sequential host code by nature (frame t depends on t-1); instances are anything with ``numpy()`` (n_nodes, 2),
 ``score`` and a settable ``track`` (``sleap_b200.nn.inference.PredictedInstance``).
@@ -252,7 +255,7 @@ class SimpleCandidateMaker:
         self.min_points = min_points
 
     def get_candidates(self, track_matching_queue, **kw) -> list:
-        return [x for _, insts in track_matching_queue for x in insts if n_visible_points(x) >= self.min_points]
+        return [x for item in track_matching_queue for x in item[1] if n_visible_points(x) >= self.min_points]
 
 
 class SimpleMaxTracksCandidateMaker(SimpleCandidateMaker):
@@ -267,14 +270,156 @@ class SimpleMaxTracksCandidateMaker(SimpleCandidateMaker):
         for _, hist in track_matching_queue_dict.items():
             if not max_tracking or n < self.max_tracks:
                 n += 1
-                out.extend(x for _, x in hist if n_visible_points(x) >= self.min_points)
+                out.extend(item[1] for item in hist if n_visible_points(item[1]) >= self.min_points)
+        return out
+
+
+class ShiftedInstance:
+    """A reference instance moved into the current frame by optical flow (tracking.py:33-86): same track, new points
+    (NaN where the flow lost the point), ``shift_score`` = -mean tracking error."""
+
+    def __init__(self, points_array: np.ndarray, track, shift_score: float = 0.0, source=None):
+        self.points_array = np.asarray(points_array, np.float64)
+        self.track, self.shift_score, self.source = track, shift_score, source
+        self.score = getattr(source, "score", float("nan"))
+
+    def numpy(self):
+        return self.points_array
+
+    @classmethod
+    def from_instance(cls, ref_instance, new_points_array=None, shift_score: float = 0.0):
+        pts = _pts(ref_instance) if new_points_array is None else new_points_array
+        return cls(pts, getattr(ref_instance, "track", None), shift_score, ref_instance)
+
+
+def _ensure_u8(img: np.ndarray) -> np.ndarray:
+    """normalization.ensure_int (sleap/nn/data/normalization.py:52-66): float images in [0, 1] -> uint8."""
+    img = np.asarray(img)
+    if img.dtype == np.uint8:
+        return img
+    if np.issubdtype(img.dtype, np.floating) and img.size and float(np.nanmax(img)) <= 1.0:
+        img = img * 255.0
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+class FlowCandidateMaker:
+    """Candidates = the instances of the last ``track_window`` frames, each flow-shifted into the current frame
+    (tracking.py:108-360).  ``save_shifted_instances`` chains the shifts frame to frame instead of always starting from
+    the original frame (:139-160)."""
+
+    uses_image = True
+
+    def __init__(self, min_points: int = 0, img_scale: float = 1.0, of_window_size: int = 21, of_max_levels: int = 3,
+                 save_shifted_instances: bool = False, track_window: int = 5):
+        self.min_points, self.img_scale = min_points, img_scale
+        self.of_window_size, self.of_max_levels = of_window_size, of_max_levels
+        self.save_shifted_instances, self.track_window = save_shifted_instances, track_window
+        self.shifted_instances: Dict[Tuple[int, int], tuple] = {}        # (ref_t, t) -> (instances, img)
+
+    def get_shifted_instances_from_earlier_time(self, ref_t: int, ref_img, ref_instances: list, t: int):
+        for ti in reversed(range(ref_t, t)):
+            if (ref_t, ti) in self.shifted_instances:
+                insts, img = self.shifted_instances[(ref_t, ti)]
+                if len(insts) > 0:
+                    return img, insts
+        return ref_img, ref_instances
+
+    def get_shifted_instances(self, ref_instances: list, ref_img, ref_t: int, img, t: int) -> list:
+        shifted = self.flow_shift_instances(ref_instances, ref_img, img, min_shifted_points=self.min_points, scale=self.img_scale,
+                                            window_size=self.of_window_size, max_levels=self.of_max_levels)
+        if self.save_shifted_instances:
+            self.shifted_instances[(ref_t, t)] = (shifted, img)
+        return shifted
+
+    def prune_shifted_instances(self, t: int):
+        if not self.save_shifted_instances:
+            return
+        for k in list(self.shifted_instances):
+            if t - k[0] > self.track_window:
+                del self.shifted_instances[k]
+
+    def get_candidates(self, track_matching_queue, t: int, img, **kw) -> list:
+        if img is None:
+            raise ValueError("the flow tracker needs the frame image: Tracker.track(instances, img=frame, ...)")
+        out = []
+        self.prune_shifted_instances(t)
+        for item in track_matching_queue:
+            ref_t, ref_instances, ref_img = item[0], item[1], item[2]
+            if self.save_shifted_instances:
+                ref_img, ref_instances = self.get_shifted_instances_from_earlier_time(ref_t, ref_img, ref_instances, t)
+            if len(ref_instances) > 0:
+                out.extend(self.get_shifted_instances(ref_instances, ref_img, ref_t, img, t))
+        return out
+
+    @staticmethod
+    def flow_shift_instances(ref_instances: list, ref_img, new_img, min_shifted_points: int = 0, scale: float = 1.0,
+                             window_size: int = 21, max_levels: int = 3) -> list:
+        """tracking.py:262-360: pyramidal Lucas-Kanade (cv2.calcOpticalFlowPyrLK, 30 iterations / eps 0.01) of every
+        reference point; instances keep the points the flow found (> min_shifted_points of them)."""
+        import cv2
+        ref_img, new_img = _ensure_u8(ref_img), _ensure_u8(new_img)
+        if ref_img.ndim > 2 and ref_img.shape[-1] == 1:
+            ref_img, new_img = ref_img[..., 0], new_img[..., 0]
+        if ref_img.ndim > 2 and ref_img.shape[-1] == 3:
+            ref_img, new_img = cv2.cvtColor(ref_img, cv2.COLOR_BGR2GRAY), cv2.cvtColor(new_img, cv2.COLOR_BGR2GRAY)
+        if scale != 1:
+            ref_img = cv2.resize(ref_img, None, None, scale, scale)
+            new_img = cv2.resize(new_img, None, None, scale, scale)
+        ref_pts = [_pts(x) for x in ref_instances]
+        shifted, status, errs = cv2.calcOpticalFlowPyrLK(
+            np.ascontiguousarray(ref_img), np.ascontiguousarray(new_img), (np.concatenate(ref_pts, axis=0)).astype("float32") * scale, None,
+            winSize=(window_size, window_size), maxLevel=max_levels,
+            criteria=(cv2.TERM_CRITERIA_EPS | cv2.TERM_CRITERIA_COUNT, 30, 0.01))
+        shifted = shifted / scale
+        sections = np.cumsum([len(x) for x in ref_pts])[:-1]
+        out = []
+        for ref, pts, found, err in zip(ref_instances, np.split(shifted, sections, axis=0), np.split(status, sections, axis=0),
+                                        np.split(errs, sections, axis=0)):
+            if found.sum() > min_shifted_points:
+                found = found.reshape(-1).astype(bool)
+                pts = pts.astype(np.float64)
+                pts[~found] = np.nan
+                out.append(ShiftedInstance.from_instance(ref, new_points_array=pts, shift_score=-float(np.mean(err.reshape(-1)[found]))))
+        return out
+
+
+class FlowMaxTracksCandidateMaker(FlowCandidateMaker):
+    """Flow candidates from the per-track history, at most ``max_tracks`` tracks (tracking.py:363-440)."""
+
+    def __init__(self, max_tracks: Optional[int] = None, **kw):
+        super().__init__(**kw)
+        self.max_tracks = max_tracks
+
+    @staticmethod
+    def get_ref_instances(ref_t: int, ref_img, track_matching_queue_dict) -> list:
+        out = []
+        for _, hist in track_matching_queue_dict.items():
+            out += [item[1] for item in hist if item[0] == ref_t and np.all(item[2] == ref_img)]
+        return out
+
+    def get_candidates(self, track_matching_queue_dict, max_tracking: bool, t: int, img, **kw) -> list:
+        if img is None:
+            raise ValueError("the flow tracker needs the frame image: Tracker.track(instances, img=frame, ...)")
+        out, tracks = [], []
+        self.prune_shifted_instances(t)
+        for track, hist in track_matching_queue_dict.items():
+            if not max_tracking or len(tracks) < self.max_tracks:
+                tracks.append(track)
+                for item in hist:
+                    ref_t, ref_img = item[0], item[2]
+                    ref_instances = self.get_ref_instances(ref_t, ref_img, track_matching_queue_dict)
+                    if self.save_shifted_instances:
+                        ref_img, ref_instances = self.get_shifted_instances_from_earlier_time(ref_t, ref_img, ref_instances, t)
+                    if len(ref_instances) > 0:
+                        out.extend(self.get_shifted_instances(ref_instances, ref_img, ref_t, img, t))
         return out
 
 
 SIMILARITIES = dict(instance=instance_similarity, centroid=centroid_distance, iou=instance_iou,
                     normalized_instance=normalized_instance_similarity, object_keypoint=factory_object_keypoint_similarity)
 MATCHERS = dict(hungarian=hungarian_matching, greedy=greedy_matching)
-CANDIDATE_MAKERS = dict(simple=SimpleCandidateMaker, simplemaxtracks=SimpleMaxTracksCandidateMaker)
+CANDIDATE_MAKERS = dict(simple=SimpleCandidateMaker, simplemaxtracks=SimpleMaxTracksCandidateMaker, flow=FlowCandidateMaker,
+                        flowmaxtracks=FlowMaxTracksCandidateMaker)
 
 
 class Tracker:
@@ -301,13 +446,17 @@ class Tracker:
 
     @property
     def has_max_tracking(self) -> bool:
-        return isinstance(self.candidate_maker, SimpleMaxTracksCandidateMaker)
+        return isinstance(self.candidate_maker, (SimpleMaxTracksCandidateMaker, FlowMaxTracksCandidateMaker))
+
+    @property
+    def uses_image(self) -> bool:
+        return bool(getattr(self.candidate_maker, "uses_image", False))
 
     @property
     def unique_tracks_in_queue(self) -> List[Track]:
         if self.has_max_tracking:
             return list(self.track_matching_queue_dict)
-        return list({x.track for _, insts in self.track_matching_queue for x in insts})
+        return list({x.track for item in self.track_matching_queue for x in item[1]})
 
     def reset_candidates(self):
         self.track_matching_queue = deque(maxlen=self.track_window)
@@ -355,14 +504,15 @@ class Tracker:
                 x = copy.copy(inst)
                 x.track = tr
                 tracked.append(x)
+        keep_img = img if self.uses_image else None              # only the flow makers look at earlier frames (:780-800)
         if self.has_max_tracking:
             for x in tracked:
                 if x.track in self.track_matching_queue_dict:
-                    self.track_matching_queue_dict[x.track].append((t, x))
+                    self.track_matching_queue_dict[x.track].append((t, x, keep_img))
                 elif not self.max_tracking or len(self.track_matching_queue_dict) < self.max_tracks:
-                    self.track_matching_queue_dict[x.track] = deque([(t, x)], maxlen=self.track_window)
+                    self.track_matching_queue_dict[x.track] = deque([(t, x, keep_img)], maxlen=self.track_window)
         else:
-            self.track_matching_queue.append((t, tracked))
+            self.track_matching_queue.append((t, tracked, keep_img))
         return tracked
 
     def final_pass(self, frames: list):
@@ -378,14 +528,16 @@ class Tracker:
                              target_instance_count: int = 0, pre_cull_to_target: bool = False,
                              pre_cull_iou_threshold: Optional[float] = None, max_tracks: Optional[int] = None,
                              max_tracking: bool = False, oks_errors=None, oks_score_weighting: bool = False,
-                             oks_normalization: str = "all", **kwargs) -> "Tracker":
+                             oks_normalization: str = "all", img_scale: float = 1.0, of_window_size: int = 21,
+                             of_max_levels: int = 3, save_shifted_instances: bool = False, kf_init_frame_count: int = 0,
+                             **kwargs) -> "Tracker":
         max_tracking = max_tracking if max_tracks else False
-        if max_tracking and tracker == "simple":
-            tracker = "simplemaxtracks"
+        if max_tracking and tracker in ("simple", "flow"):          # :882-884
+            tracker += "maxtracks"
+        if kf_init_frame_count:
+            raise ValueError("the Kalman-filter tracker (kf_init_frame_count > 0) is not part of this build.")
         if tracker.lower() == "none":
             return cls(track_window=track_window, similarity_function=None, matching_function=None, candidate_maker=None)
-        if tracker in ("flow", "flowmaxtracks"):
-            raise ValueError("optical-flow candidate shifting is not part of this build; use tracker='simple' / 'simplemaxtracks'.")
         if tracker not in CANDIDATE_MAKERS:
             raise ValueError(f"{tracker} is not a valid tracker.")
         if similarity not in SIMILARITIES:
@@ -393,7 +545,10 @@ class Tracker:
         if match not in MATCHERS:
             raise ValueError(f"{match} is not a valid tracker matching function.")
         maker = CANDIDATE_MAKERS[tracker](min_points=min_match_points)
-        if tracker == "simplemaxtracks":
+        if tracker in ("flow", "flowmaxtracks"):                   # :913-918
+            maker.img_scale, maker.of_window_size, maker.of_max_levels = img_scale, of_window_size, of_max_levels
+            maker.save_shifted_instances, maker.track_window = save_shifted_instances, track_window
+        if tracker in ("simplemaxtracks", "flowmaxtracks"):
             maker.max_tracks = max_tracks
         sim = SIMILARITIES[similarity]
         if similarity == "object_keypoint":
@@ -406,10 +561,15 @@ class Tracker:
                    robust_best_instance=robust, pre_cull_function=pre_cull, target_instance_count=target_instance_count)
 
 
-def run_tracker(frames: list, tracker: Tracker) -> list:
-    """Track the predicted instances of ``frames`` (sorted by frame index) in place (tracking.py:1542-1580)."""
+def run_tracker(frames: list, tracker: Tracker, images=None) -> list:
+    """Track the predicted instances of ``frames`` (sorted by frame index) in place (tracking.py:1542-1580).
+    ``images``: ``frame_idx -> image`` (mapping or callable), needed by the flow trackers."""
     frames = sorted(frames, key=lambda lf: lf.frame_idx)
     for lf in frames:
-        lf.instances = tracker.track(list(lf.instances), t=lf.frame_idx)
+        img = None
+        if images is not None:
+            img = images(lf.frame_idx) if callable(images) else images[lf.frame_idx]
+        hw = tuple(np.asarray(img).shape[:2]) if img is not None else (1, 1)
+        lf.instances = tracker.track(list(lf.instances), img_hw=hw, img=img, t=lf.frame_idx)
     tracker.final_pass(frames)
     return frames

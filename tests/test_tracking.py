@@ -95,6 +95,53 @@ def test_tracker_by_name(tracker, similarity, match):
     assert "." in tr.get_name()
     T.Tracker.make_tracker_by_name(tracker="none").track([])
     with pytest.raises(ValueError):
-        T.Tracker.make_tracker_by_name(tracker="flow")
+        T.Tracker.make_tracker_by_name(tracker="simple", max_tracks=2, kf_init_frame_count=10)     # Kalman variant: not built
     with pytest.raises(ValueError):
         T.Tracker.make_tracker_by_name(similarity="bogus")
+
+
+def _blob_frame(centers, hw=(96, 128), sigma=4.0):
+    """Textured uint8 frame: one Gaussian blob per animal node (what Lucas-Kanade can lock on to)."""
+    yy, xx = np.mgrid[0:hw[0], 0:hw[1]].astype(np.float64)
+    img = np.zeros(hw)
+    for cx, cy in centers:
+        img += np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2 * sigma ** 2))
+    return np.clip(img * 255, 0, 255).astype(np.uint8)[..., None]
+
+
+def test_flow_shift_instances_follows_motion():
+    """FlowCandidateMaker.flow_shift_instances (tracking.py:262-360): the reference points move with the image content;
+    a point the flow loses becomes NaN and does not count towards min_shifted_points."""
+    shape = np.array([[-8.0, 0.0], [0.0, 0.0], [8.0, 0.0]])
+    a, b = shape + [40.0, 40.0], shape + [43.0, 42.0]                      # whole animal moves by (+3, +2)
+    ref = PredictedInstance.from_numpy(a, [1, 1, 1], 1.0)
+    ref.track = T.Track(0, "t0")
+    out = T.FlowCandidateMaker.flow_shift_instances([ref], _blob_frame(a), _blob_frame(b), window_size=21, max_levels=3)
+    assert len(out) == 1 and out[0].track is ref.track
+    assert np.allclose(out[0].numpy(), b, atol=0.35)
+    assert out[0].shift_score <= 0
+    half = T.FlowCandidateMaker.flow_shift_instances([ref], _blob_frame(a), _blob_frame(b), scale=0.5)
+    assert np.allclose(half[0].numpy(), b, atol=1.0)
+    assert T.FlowCandidateMaker.flow_shift_instances([ref], _blob_frame(a), _blob_frame(b), min_shifted_points=3) == []
+
+
+@pytest.mark.parametrize("tracker,save", [("flow", False), ("flow", True), ("flowmaxtracks", False)])
+def test_flow_tracker_keeps_identities_across_a_jump(tracker, save):
+    """Two animals move 6 px per frame towards each other's positions: with the instance similarity (exp(-d^2)) the simple
+    tracker cannot bridge a 6 px step, the flow tracker can because candidates are first shifted into the current frame."""
+    shape = np.array([[-8.0, 0.0], [0.0, 0.0], [8.0, 0.0]])
+    pos = lambda t: (shape + [30.0 + 6 * t, 30.0], shape + [100.0 - 6 * t, 70.0])
+    frames = [LabeledFrame(0, t, [PredictedInstance.from_numpy(pos(t)[0], [1, 1, 1], 1.0), PredictedInstance.from_numpy(pos(t)[1], [1, 1, 1], 1.0)])
+              for t in range(6)]
+    imgs = {t: _blob_frame(np.concatenate(pos(t))) for t in range(6)}
+    tr = T.Tracker.make_tracker_by_name(tracker=tracker, similarity="instance", match="hungarian", track_window=3, max_tracks=2,
+                                        max_tracking=tracker == "flowmaxtracks", save_shifted_instances=save)
+    assert tr.uses_image
+    out = T.run_tracker(frames, tr, images=imgs)
+    names = [[i.track.name for i in lf.instances] for lf in out]
+    assert all(n == names[0] for n in names) and len(set(names[0])) == 2, names
+    with pytest.raises(ValueError):
+        tr.track(list(frames[0].instances), t=99)                          # flow needs the image
+    simple = T.run_tracker([LabeledFrame(0, f.frame_idx, [PredictedInstance.from_numpy(i.numpy(), [1, 1, 1], 1.0) for i in f.instances])
+                            for f in frames], T.Tracker.make_tracker_by_name(tracker="simple", similarity="instance", match="hungarian"))
+    assert len({i.track.name for lf in simple for i in lf.instances}) >= 2
