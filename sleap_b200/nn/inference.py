@@ -377,6 +377,25 @@ class FindInstancePeaksGroundTruth:
                     instance_peak_vals=vals)
 
 
+class CentroidInferenceModel(InferenceModel):
+    """sleap/nn/inference.py:2203-2244: the first stage of the top-down path on its own (centroids only)."""
+
+    def __init__(self, centroid_crop):
+        self.centroid_crop = centroid_crop
+
+    def call(self, example):
+        if isinstance(example, np.ndarray):
+            example = dict(image=example)
+        out = self.centroid_crop.call(example)
+        ce, nv = _ragged_to_dense(out["centroids"], (2,))
+        cv, _ = _ragged_to_dense(out["centroid_vals"], ())
+        res = {"centroids": ce, "centroid_vals": cv, "n_valid": nv}
+        for k in ("crops", "crop_offsets", "crop_sample_inds", "flags"):
+            if k in out:
+                res[k] = out[k]
+        return res
+
+
 class TopDownInferenceModel(InferenceModel):
     """sleap/nn/inference.py:2246-2311."""
 
@@ -862,9 +881,57 @@ class Predictor:
         import warnings
         warnings.warn(msg, RuntimeWarning, stacklevel=3)
 
+    def _with_progress(self, gen, n_total):
+        """:422-491: ``verbosity`` = "none" | "json" (one JSON line per ``report_period`` seconds: n_processed, n_total, elapsed,
+        rate over the last 30 batches, eta) | "rich" (a rich progress bar with the same rate estimate)."""
+        import time
+        from collections import deque
+        if self.verbosity not in ("json", "rich"):
+            yield from gen
+            return
+        n_processed, n_recent, el_recent = 0, deque(maxlen=30), deque(maxlen=30)
+        t0_all = t0_batch = last_report = time.time()
+        period = 1.0 / self.report_rate
+        progress = task = None
+        if self.verbosity == "rich":
+            import rich.progress
+            progress = rich.progress.Progress("{task.description}", rich.progress.BarColumn(), "[progress.percentage]{task.percentage:>3.0f}%",
+                                              "ETA:", rich.progress.TimeRemainingColumn(), auto_refresh=False, speed_estimate_period=5)
+            progress.start()
+            task = progress.add_task("Predicting...", total=n_total)
+        try:
+            for ex in gen:
+                now = time.time()
+                n_batch = len(ex["frame_ind"])
+                n_processed += n_batch
+                n_recent.append(n_batch); el_recent.append(now - t0_batch)
+                t0_batch = now
+                rate = sum(n_recent) / max(sum(el_recent), 1e-9)
+                if progress is not None:
+                    progress.update(task, advance=n_batch)
+                if now - last_report > period:
+                    if progress is not None:
+                        progress.refresh()
+                    else:
+                        print(json.dumps({"n_processed": n_processed, "n_total": n_total, "elapsed": now - t0_all, "rate": rate,
+                                          "eta": (n_total - n_processed) / rate if n_total else None}), flush=True)
+                    last_report = now
+                yield ex
+        finally:
+            if progress is not None:
+                progress.refresh()
+                progress.stop()
+
+    @staticmethod
+    def _n_total(data):
+        try:
+            return len(_images_of(data))
+        except TypeError:
+            return len(getattr(data, "inds", [])) or None
+
     def predict(self, data, make_labels: bool = True):
         """:496-531."""
-        gen = self._predict_generator(data)
+        gen = self._with_progress(self._predict_generator(data), self._n_total(data))
         if make_labels:
             return self._make_labeled_frames_from_generator(gen, data)
         return list(gen)

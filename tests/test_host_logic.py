@@ -107,3 +107,20 @@ def test_overflow_flags_are_reported():
     p._check_flags(ex)
     p.on_overflow = "raise"
     p._check_flags({"flags": np.zeros(3, np.int32)})
+
+
+def test_progress_reporting_json_and_rich(capsys):
+    """Predictor.verbosity (sleap/nn/inference.py:422-491): json lines carry n_processed / n_total / rate / eta."""
+    import json
+    import numpy as np
+    from sleap_b200.nn.inference import Predictor
+    p = Predictor()
+    p.verbosity, p.report_rate = "json", 1e9
+    out = list(p._with_progress(({"frame_ind": np.arange(i, i + 4)} for i in range(0, 12, 4)), 12))
+    lines = [json.loads(l) for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
+    assert len(out) == 3 and lines[-1]["n_processed"] == 12 and lines[-1]["n_total"] == 12 and lines[-1]["eta"] == 0
+    assert [l["n_processed"] for l in lines] == [4, 8, 12]
+    p.verbosity = "rich"
+    assert len(list(p._with_progress(({"frame_ind": np.arange(4)} for _ in range(3)), 12))) == 3
+    p.verbosity = "none"
+    assert len(list(p._with_progress(iter([{"frame_ind": np.arange(2)}]), 2))) == 1
