@@ -469,6 +469,9 @@ def run_ours(args):
     l0 = handle.gpu_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    # live timing of the dominant kernel family: the library brackets the conv launches of every timed step with a
+    # CUDA event pair on the launching stream (sb_model_forward_times); read back after the region
+    handle.call("sb_model_forward_times", model.model_id, 1, 0, None, None)
     with torch.cuda.stream(stream):
         ev0.record(stream)
     for i in range(args.steps):
@@ -479,6 +482,10 @@ def run_ours(args):
         ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
+    fwd_ms = np.zeros(max(args.steps, 1), np.float32)
+    n_fwd = c_int32(0)
+    handle.call("sb_model_forward_times", model.model_id, 0, len(fwd_ms), _lib.ptr(fwd_ms), byref(n_fwd))
+    fwd_ms = fwd_ms[:n_fwd.value]
     launches = handle.gpu_launches() - l0
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([ms], device="cuda")
@@ -570,7 +577,10 @@ def run_ours(args):
     if os.environ.get("BENCH_VERBOSE"):
         for i in range(len(kind)):
             sys.stderr.write(f"[op {i:2d}] kind={int(kind[i])} {op_ms_m[i]*1e3:8.1f} us  {fl[i]/1e9:7.2f} GF  {(fl[i]/max(op_ms_m[i],1e-6)/1e9):8.1f} TF/s\n")
-    tc_ms, tc_flops = float(op_ms_m[tc].sum()), float(fl[tc].sum())
+    per_op_ms, tc_flops = float(op_ms_m[tc].sum()), float(fl[tc].sum())
+    # the conv launches of one step, timed inside the timed region (mean over its K steps); the per-op pass above
+    # serialises the forked transposed-conv phases and adds an event per op, so its sum is only the fallback
+    tc_ms = float(fwd_ms.mean()) if len(fwd_ms) else per_op_ms
     peaks, peaks_src = peaks_file()
     # a timed region shorter than ~1 s runs at boost clocks (1965 MHz, ~300 W): the honest denominator is the BURST
     # cuBLAS figure; the power-capped "sustained" figure belongs to the seconds-long loop reported under `sustained`
@@ -594,6 +604,10 @@ def run_ours(args):
                 "frac_of_sustained_peak": achieved_tf / float(peaks.get("bf16_tflops_sustained", peak_tf)),
                 "traffic": traffic, "traffic_source": traffic_src,
                 "kernel_ms_per_step": tc_ms, "kernel_share_of_step": tc_ms / step_ms if step_ms else None,
+                "kernel_timing": (f"CUDA event pair around the conv launches of each of the {len(fwd_ms)} timed steps, on the launching "
+                                  "stream (sb_model_forward_times); the previous step's peak / grouping kernels overlap on a second stream"
+                                  if len(fwd_ms) else "per-op CUDA events of a separate pass (sb_model_profile_ops)"),
+                "per_op_sum_ms": per_op_ms,
                 "algorithmic_flops_per_step": tc_flops,
                 "hbm_model": {"unfused_activation_bytes_per_frame": 357e6,
                               "achieved_gbs": 357e6 * B / (float(op_ms_m.sum()) * 1e-3) / 1e9,

@@ -161,6 +161,14 @@ int sb_model_forward(sb_handle_t h, int model_id, const void* images_host, int i
 int sb_model_profile_ops(sb_handle_t h, int model_id, const uint8_t* frames_dev, int B, int cap,
                          float* out_ms, int32_t* out_kind, double* out_flops, int32_t* out_n_ops);
 
+/* Live timing of the network part of every step: while enabled, each forward pass (whatever entry point runs it:
+ * sb_model_forward, sb_infer_*, sb_bottomup_submit, sb_infer_topdown) is bracketed by a pair of CUDA events on the
+ * launching stream.  A call synchronises that stream, returns the milliseconds of the passes recorded since the last
+ * call (at most cap, at most 1024 are kept), clears them, and switches the recording on / off.  bench.py derives
+ * `roofline.achieved` from the passes of its timed region.  Replaces nothing in the reference (it has no device
+ * timers; tf.profiler is its tool). */
+int sb_model_forward_times(sb_handle_t h, int model_id, int enable, int cap, float* out_ms, int32_t* out_n);
+
 /* ---- fused predictors ------------------------------------------------------------------------
  * sleap/nn/inference.py:2737-3003 BottomUpInferenceLayer.call: preprocess -> net -> local peaks
  * -> * cm_output_stride -> PAFScorer.predict -> (/input_scale + 0.5). */

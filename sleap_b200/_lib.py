@@ -93,6 +93,7 @@ _SIGS = {
     "sb_model_configure": [c_void_p, c_int, c_int, c_int, c_int, c_int],
     "sb_model_forward": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "sb_model_profile_ops": [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "sb_model_forward_times": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "sb_bottomup_configure": [c_void_p, c_int, POINTER(BottomUpParams)],
     "sb_infer_bottomup": [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "sb_infer_bottomup_dev": [c_void_p, c_int, c_void_p, c_int],

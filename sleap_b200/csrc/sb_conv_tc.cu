@@ -467,6 +467,38 @@ __device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* 
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
 }
+// ---- CTA-pair helpers (cta_group::2: one M = 256 MMA over the two CTAs of a cluster; k_conv_tc_prog<KSTEPS, 2, 2>) ----
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {    // shared::cta address -> the same offset in CTA `rank`
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+// TMA loads of a CTA pair: the data lands in the executing CTA, the bytes are counted on the LEADER's barrier
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {      // one arrival on the barrier at this offset in BOTH CTAs
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
 __device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
                : "memory");
@@ -811,7 +843,16 @@ __device__ __forceinline__ uint32_t uni(uint32_t v) { return __shfl_sync(0xfffff
 // L2 read bandwidth, 10-28x read amplification, 37-57 % tensor-active).  A ring slot is refilled only when BOTH CTAs'
 // MMAs have consumed it (tcgen05.commit multicast to both empty barriers); every CTA walks the same number of tiles
 // (the host only launches this form when tiles % grid == 0).
-template <int KSTEPS, int CS = 1>
+// CG = 2 (with CS = 2): the two CTAs form a cta_group::2 PAIR.  Every MMA is M = 256: the leader (cluster rank 0) issues
+// tcgen05.mma.cta_group::2 over both CTAs' staged activation boxes (128 pixels each, at the same shared-memory offsets) and
+// a weight slice of which each CTA holds N/2 rows; each CTA's TMEM receives the accumulators of its own pixels and its own
+// epilogue warps drain them.  What it buys (tools/probes/mma_probe.cu): an SM's shared memory serves the TMA
+// fills AND the operand reads of the tensor core; with streamed weights a CTA writes N x KC x 2 bytes per slice that it
+// reads back once per sub-tile -- the pair writes only half a slice per CTA, and reads half of B per MMA.
+//   barriers: all TMA loads of both CTAs count on the LEADER's full barriers (.cta_group::2 loads); the leader's commits
+//   are multicast to both CTAs' empty / accumulator-full barriers; both CTAs' epilogue warps arrive on the leader's
+//   accumulator-empty barrier (the peer remotely).
+template <int KSTEPS, int CS = 1, int CG = 1>
 __global__ void __launch_bounds__(320) k_conv_tc_prog(const __grid_constant__ CUtensorMap mapA,
                                                       const __grid_constant__ CUtensorMap mapB,
                                                       const __grid_constant__ TcParams P) {
@@ -833,20 +874,29 @@ __global__ void __launch_bounds__(320) k_conv_tc_prog(const __grid_constant__ CU
   float* s_par = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~(uintptr_t)15);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int TWH = 8 * P.sub_x, THH = 16 * P.sub_y;
+  constexpr bool PAIR = CG == 2;
+  static_assert(!PAIR || CS == 2, "a cta_group::2 pair is a cluster of two");
   stage_params(P, s_par, 0);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < P.n_a_slots; ++i) { mbar_init(smem_u32(fullA + i), 1); mbar_init(smem_u32(emptyA + i), 1); }
-    for (int i = 0; i < P.n_stages; ++i) { mbar_init(smem_u32(tfull + i), 1); mbar_init(smem_u32(tempty + i), 4 * P.epi_groups); }
+    // pair: the leader's accumulator-empty barrier collects the epilogue warps of both CTAs; a slot's empty barrier gets
+    // ONE multicast commit (the leader's) instead of one per CTA
+    for (int i = 0; i < P.n_stages; ++i) { mbar_init(smem_u32(tfull + i), 1); mbar_init(smem_u32(tempty + i), 4 * P.epi_groups * CG); }
     mbar_init(smem_u32(wbar), 1);
-    for (int i = 0; i < 8; ++i) { mbar_init(smem_u32(fullW + i), 1); mbar_init(smem_u32(emptyW + i), CS); }
+    for (int i = 0; i < 8; ++i) { mbar_init(smem_u32(fullW + i), 1); mbar_init(smem_u32(emptyW + i), PAIR ? 1 : CS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(P.tmem_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(P.tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(P.tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -875,17 +925,26 @@ __global__ void __launch_bounds__(320) k_conv_tc_prog(const __grid_constant__ CU
         mbar_wait(smem_u32(emptyA + sa), pha ^ 1, 21);
         if (P.ablate & 1) { mbar_arrive(smem_u32(fullA + sa)); }
         else {
-          mbar_expect_tx(smem_u32(fullA + sa), (uint32_t)P.a_tx_bytes);
-          tma_load_4d(smem_u32(a_ring + (size_t)sa * P.a_slot_bytes), &mapA, smem_u32(fullA + sa), ch * P.KC, x0 + P.dx0,
-                      y0 + P.dy0, b);
+          if constexpr (PAIR) {      // both CTAs' boxes are counted on the leader's barrier
+            if (crank == 0) mbar_expect_tx(smem_u32(fullA + sa), 2u * (uint32_t)P.a_tx_bytes);
+            tma_load_4d_pair(smem_u32(a_ring + (size_t)sa * P.a_slot_bytes), &mapA, mapa_rank(smem_u32(fullA + sa), 0), ch * P.KC,
+                             x0 + P.dx0, y0 + P.dy0, b);
+          } else {
+            mbar_expect_tx(smem_u32(fullA + sa), (uint32_t)P.a_tx_bytes);
+            tma_load_4d(smem_u32(a_ring + (size_t)sa * P.a_slot_bytes), &mapA, smem_u32(fullA + sa), ch * P.KC, x0 + P.dx0,
+                        y0 + P.dy0, b);
+          }
         }
         if (++sa == P.n_a_slots) { sa = 0; pha ^= 1; }
         if (w_stream) {
           for (int i = 0; i < P.n_prog;) {              // same order as the MMA warp consumes the slices
             const uint32_t ew = P.prog[i].w_flags;
             mbar_wait(smem_u32(emptyW + sw), phw ^ 1, 26);                 // CS > 1: all CTAs of the cluster are done with this slot
-            mbar_expect_tx(smem_u32(fullW + sw), (uint32_t)P.b_tx_bytes);
-            if constexpr (CS > 1)                                          // this CTA's 1/CS of the slice, into every CTA of the cluster
+            if (!PAIR || crank == 0) mbar_expect_tx(smem_u32(fullW + sw), (uint32_t)P.b_tx_bytes);
+            if constexpr (PAIR)                                            // this CTA's N/2 rows of the slice, into its own (half-size) slot
+              tma_load_3d_pair(smem_u32(w_res + (size_t)sw * P.w_slot_bytes), &mapB, mapa_rank(smem_u32(fullW + sw), 0), ch * P.KC,
+                               (int)crank * (P.N / 2), (int)((ew >> 26) & 15));
+            else if constexpr (CS > 1)                                     // this CTA's 1/CS of the slice, into every CTA of the cluster
               tma_load_3d_mc(smem_u32(w_res + (size_t)sw * P.w_slot_bytes) + crank * piece_bytes, &mapB, smem_u32(fullW + sw), ch * P.KC,
                              (int)crank * (P.N / CS), (int)((ew >> 26) & 15), kMask);
             else
@@ -896,7 +955,7 @@ __global__ void __launch_bounds__(320) k_conv_tc_prog(const __grid_constant__ CU
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && (!PAIR || crank == 0)) {
     if (!w_stream) mbar_wait(smem_u32(wbar), 0, 22);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     int sa = 0, stage = 0, sw = 0;
@@ -938,13 +997,16 @@ __global__ void __launch_bounds__(320) k_conv_tc_prog(const __grid_constant__ CU
                 const uint32_t dt = d0 + (ea >> 16);
                 const uint32_t accf = (uint32_t)ch | (((ew >> 16) & 1u) ^ 1u);
 #pragma unroll
-                for (int k = 0; k < KSTEPS; ++k)
-                  tc_mma_f16(dt, ((uint64_t)desca_hi << 32) | (uint64_t)(a_lo + 2 * k), ((uint64_t)descb_hi << 32) | (uint64_t)(b_lo + 2 * k),
-                             P.idesc, (accf | (uint32_t)k) ? 1u : 0u);
+                for (int k = 0; k < KSTEPS; ++k) {
+                  const uint64_t da = ((uint64_t)desca_hi << 32) | (uint64_t)(a_lo + 2 * k), db = ((uint64_t)descb_hi << 32) | (uint64_t)(b_lo + 2 * k);
+                  if constexpr (PAIR) tc_mma_f16_pair(dt, da, db, P.idesc, (accf | (uint32_t)k) ? 1u : 0u);
+                  else tc_mma_f16(dt, da, db, P.idesc, (accf | (uint32_t)k) ? 1u : 0u);
+                }
               }
             }
             if (w_stream) {
-              if constexpr (CS > 1) tc_commit_mc(smem_u32(emptyW + sw), kMask);   // one arrival on every CTA's empty barrier of this slot
+              if constexpr (PAIR) tc_commit_pair(smem_u32(emptyW + sw));
+              else if constexpr (CS > 1) tc_commit_mc(smem_u32(emptyW + sw), kMask);   // one arrival on every CTA's empty barrier of this slot
               else tc_commit(smem_u32(emptyW + sw));
             }
           }
@@ -952,11 +1014,11 @@ __global__ void __launch_bounds__(320) k_conv_tc_prog(const __grid_constant__ CU
           if (w_stream) { if (++sw == P.n_w_ring) { sw = 0; phw ^= 1; } }
           i += n_same;
         }
-        if (elect_one()) tc_commit(smem_u32(emptyA + sa));
+        if (elect_one()) { if constexpr (PAIR) tc_commit_pair(smem_u32(emptyA + sa)); else tc_commit(smem_u32(emptyA + sa)); }
         __syncwarp();
         if (++sa == P.n_a_slots) { sa = 0; pha ^= 1; }
       }
-      if (elect_one()) tc_commit(smem_u32(tfull + stage));
+      if (elect_one()) { if constexpr (PAIR) tc_commit_pair(smem_u32(tfull + stage)); else tc_commit(smem_u32(tfull + stage)); }
       __syncwarp();
       if (++stage == P.n_stages) { stage = 0; eph ^= 1; }
     }
@@ -991,7 +1053,10 @@ __global__ void __launch_bounds__(320) k_conv_tc_prog(const __grid_constant__ CU
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(tempty + stage));
+      if (lane == 0) {
+        if (PAIR && crank != 0) mbar_arrive_cluster(mapa_rank(smem_u32(tempty + stage), 0));   // the leader's MMA warp owns the accumulators
+        else mbar_arrive(smem_u32(tempty + stage));
+      }
       if (++stage == P.n_stages) { stage = 0; fph ^= 1; }
     }
   }
@@ -1000,7 +1065,8 @@ __global__ void __launch_bounds__(320) k_conv_tc_prog(const __grid_constant__ CU
   __syncthreads();
   if constexpr (CS > 1) cluster_sync_all();          // nobody leaves while a peer may still multicast into it / signal its barriers
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P.tmem_cols) : "memory");
+    if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P.tmem_cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P.tmem_cols) : "memory");
   }
 }
 
@@ -1383,6 +1449,8 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
       L.has_persist = true;
     }
   }
+  // a pair twin is only valid when its half-size weight slot keeps the 1024-byte alignment of the swizzle atoms
+  auto Q_ok = [](const TcLaunch::Halo& Hh) { return Hh.mc != 4 || (Hh.P.w_slot_bytes % 1024 == 0 && Hh.P.n_w_ring >= 2); };
   L.n_halo = 0;
   // sub_x, sub_y, epilogue groups; 8x32 (1x2) measured 2-5 % ahead of 16x16 (2x1) on the 64..256-channel layers
   int kHaloShapes[5][3] = {{1, 1, 1}, {2, 1, 2}, {2, 2, 2}, {1, 2, 2}, {0, 0, 0}};
@@ -1521,17 +1589,31 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
     if (r != CUDA_SUCCESS) return sb_fail(h, SB_ERR_CUDA, "cuTensorMapEncodeTiled(A halo) failed: %d", (int)r);
     HC.mc = 0;
     ++L.n_halo;
-    // cluster-multicast twin of a weight-streamed candidate: same plan, clusters of 2 CTAs, each fetching half of every slice
-    if (Hp.w_stream && HC.prog && N % 16 == 0 && L.n_halo < 6 && !getenv("SB_DISABLE_MULTICAST")) {
+    // twin of a weight-streamed candidate on clusters of two CTAs.  Default: the cta_group::2 PAIR (mc = 4: M = 256 MMAs,
+    // each CTA stages N/2 rows of every slice in a half-size slot, so the ring is deeper).  SB_ENABLE_MULTICAST=1 selects the
+    // round-2 multicast form instead (mc = 2: full slices in both CTAs, each fetching half) -- measured no faster than
+    // unicast, kept as an experiment.
+    if (Hp.w_stream && HC.prog && N % 16 == 0 && L.n_halo < 6 && !getenv("SB_DISABLE_MULTICAST") && !getenv("SB_DISABLE_PAIR")) {
       TcLaunch::Halo& H2 = L.halo[L.n_halo];
-      H2 = HC;
-      H2.mc = 2;
+      const TcLaunch::Halo& H1 = L.halo[L.n_halo - 1];
+      H2 = H1;
+      H2.mc = getenv("SB_ENABLE_MULTICAST") ? 2 : 4;
       H2.occ = 1;
+      if (H2.mc == 4) {
+        TcParams& Q = H2.P;
+        Q.w_slot_bytes = H1.P.w_slot_bytes / 2;                      // N/2 rows x KC: stays a multiple of 8 rows (N % 16 == 0)
+        Q.idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+        const size_t a_bytes = (size_t)Q.n_a_slots * Q.a_slot_bytes;
+        Q.n_w_ring = (int)std::min<size_t>(8, (196 * 1024 - a_bytes) / Q.w_slot_bytes);
+        if (Q.n_a_slots == 2 && Q.n_w_ring >= 7 && 3 * (size_t)Q.a_slot_bytes + 6 * (size_t)Q.w_slot_bytes <= 196 * 1024) { Q.n_a_slots = 3; Q.n_w_ring = 6; }
+        H2.smem = (size_t)Q.n_w_ring * Q.w_slot_bytes + (size_t)Q.n_a_slots * Q.a_slot_bytes + 1024 +
+                  (size_t)(2 * Q.n_a_slots + 2 * 8 + 1 + 16) * 8 + 64 + 3 * 256 * sizeof(float);
+      }
       cuuint64_t wdims[3] = {(cuuint64_t)Cin, (cuuint64_t)plan->Cout_pad, (cuuint64_t)n_wtaps};
       cuuint64_t wstrides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)plan->Cout_pad * Cin * 2};
       cuuint32_t pbox[3] = {(cuuint32_t)KC, (cuuint32_t)(N / 2), 1};
       cuuint32_t wes[3] = {1, 1, 1};
-      if (enc(&H2.mapBpiece, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)plan->w16, wdims, wstrides, pbox, wes, CU_TENSOR_MAP_INTERLEAVE_NONE,
+      if (Q_ok(H2) && enc(&H2.mapBpiece, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)plan->w16, wdims, wstrides, pbox, wes, CU_TENSOR_MAP_INTERLEAVE_NONE,
               swz_for(KC), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
         ++L.n_halo;
     }
@@ -1848,6 +1930,9 @@ int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m) {
     SB_CUDA(h, cudaFuncSetAttribute((k_conv_tc_prog<1, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     SB_CUDA(h, cudaFuncSetAttribute((k_conv_tc_prog<2, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     SB_CUDA(h, cudaFuncSetAttribute((k_conv_tc_prog<4, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    SB_CUDA(h, cudaFuncSetAttribute((k_conv_tc_prog<1, 2, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    SB_CUDA(h, cudaFuncSetAttribute((k_conv_tc_prog<2, 2, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    SB_CUDA(h, cudaFuncSetAttribute((k_conv_tc_prog<4, 2, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
     attr_set = true;
   }
   for (size_t oi = 0; oi < m->ops.size(); ++oi) {
@@ -1995,6 +2080,14 @@ static void launch_variant(sb_handle_s* h, TcLaunch& L, int B, int variant, cuda
       at[0].id = cudaLaunchAttributeClusterDimension;
       at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
+      if (HC.mc == 4) {
+        switch (P.KC) {
+          case 16: cudaLaunchKernelEx(&cfg, k_conv_tc_prog<1, 2, 2>, HC.map, HC.mapBpiece, P); break;
+          case 32: cudaLaunchKernelEx(&cfg, k_conv_tc_prog<2, 2, 2>, HC.map, HC.mapBpiece, P); break;
+          default: cudaLaunchKernelEx(&cfg, k_conv_tc_prog<4, 2, 2>, HC.map, HC.mapBpiece, P); break;
+        }
+        return;
+      }
       switch (P.KC) {
         case 16: cudaLaunchKernelEx(&cfg, k_conv_tc_prog<1, 2>, HC.map, HC.mapBpiece, P); break;
         case 32: cudaLaunchKernelEx(&cfg, k_conv_tc_prog<2, 2>, HC.map, HC.mapBpiece, P); break;
@@ -2064,6 +2157,9 @@ int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
       if (plan) {
         for (TcLaunch& L : plan->launches) L.use_persist = avail(L, want) ? want : (avail(L, 1) && !force ? 1 : 0);
         plan->use_fused = !plan->fused.empty() && (getenv("SB_FORCE_FUSED_TCONV") != nullptr);
+        // SB_FORCE_FUSED_TCONV=2: the cluster twin of the fused transposed conv where it has one
+        const bool twin = getenv("SB_FORCE_FUSED_TCONV") && atoi(getenv("SB_FORCE_FUSED_TCONV")) == 2;
+        for (TcLaunch& F : plan->fused) F.use_persist = (twin && F.n_halo >= 2 && F.halo[1].mc) ? 3 : 2;
       }
     return 0;
   }
@@ -2131,7 +2227,7 @@ int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
                 L.P.N, L.P.H, L.P.W, best[0] * 1e3f, best[1] * 1e3f, L.occ, L.PP.n_a_slots);
         for (int i = 0; i < L.n_halo; ++i)
           fprintf(stderr, ", halo%dx%d%s%s %.1f (occ %d, %d slots, %d stages)", L.halo[i].P.sub_x, L.halo[i].P.sub_y,
-                  L.halo[i].P.w_stream ? "w" : "", L.halo[i].mc ? "-mc2" : "", best[2 + i] * 1e3f, L.halo[i].occ, L.halo[i].P.n_a_slots,
+                  L.halo[i].P.w_stream ? "w" : "", L.halo[i].mc == 4 ? "-2cta" : (L.halo[i].mc ? "-mc2" : ""), best[2 + i] * 1e3f, L.halo[i].occ, L.halo[i].P.n_a_slots,
                   L.halo[i].P.n_stages);
         fprintf(stderr, " us -> %d\n", pick);
       }
@@ -2213,8 +2309,8 @@ int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
       const TcParams& F = plan->fused[0].halo[0].P;
       fprintf(stderr, "[sb_conv_tc] op %zu tconv Cin=%d N=%d: 4 phase launches %.1f us, fused x%zu (%s, %d stages, %d slots) %.1f us -> %s\n", oi,
               F.n_chunks * F.KC, F.N, best[0] * 1e3f, plan->fused.size(), F.w_stream ? "streamed weights" : "resident weights", F.n_stages,
-              F.n_a_slots, best[1] * 1e3f, plan->use_fused ? (mc_wins ? "fused-mc2" : "fused") : "phases");
-      if (has_mc) fprintf(stderr, "[sb_conv_tc] op %zu tconv fused with cluster-multicast weights: %.1f us\n", oi, best[2] * 1e3f);
+              F.n_a_slots, best[1] * 1e3f, plan->use_fused ? (mc_wins ? "fused-twin" : "fused") : "phases");
+      if (has_mc) fprintf(stderr, "[sb_conv_tc] op %zu tconv fused, cluster twin (2-CTA pair / multicast): %.1f us\n", oi, best[2] * 1e3f);
     }
   }
   cudaEventDestroy(e0);

@@ -46,6 +46,7 @@ void sb_models_free(sb_handle_s* h) {
       if (m->result_ev[i]) cudaEventDestroy(m->result_ev[i]);
     }
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+    for (auto& e : m->fwd_events) cudaEventDestroy(e);
     sb_post_ws_free(m->ws);
     sb_gather_free(m);
     sb_topdown_free(m);
@@ -401,8 +402,12 @@ static int run_ops_t(sb_handle_s* h, SbModel* m, const void* frames_dev, int fra
 int sb_run_ops(sb_handle_s* h, SbModel* m, const void* frames_dev, int frames_are_u8, int B) {
   if (!m->configured) return sb_fail(h, SB_ERR_INVALID, "model not configured");
   if (B <= 0 || B > m->B) return sb_fail(h, SB_ERR_INVALID, "batch %d exceeds configured max %d", B, m->B);
-  if (m->precision == 1) return run_ops_t<float>(h, m, frames_dev, frames_are_u8, B);
-  return run_ops_t<__half>(h, m, frames_dev, frames_are_u8, B);
+  const bool timed = m->fwd_timing && 2 * (m->fwd_n + 1) <= (int)m->fwd_events.size();
+  if (timed) cudaEventRecord(m->fwd_events[2 * m->fwd_n], h->stream);
+  const int rc = m->precision == 1 ? run_ops_t<float>(h, m, frames_dev, frames_are_u8, B)
+                                   : run_ops_t<__half>(h, m, frames_dev, frames_are_u8, B);
+  if (timed) { cudaEventRecord(m->fwd_events[2 * m->fwd_n + 1], h->stream); ++m->fwd_n; }
+  return rc;
 }
 
 __global__ void k_half_to_float(const __half* __restrict__ in, float* __restrict__ out, size_t n) {
@@ -488,6 +493,24 @@ int sb_model_profile_ops(sb_handle_t h, int model_id, const uint8_t* frames_dev,
   m->prof_events.clear();
   *out_n_ops = n;
   return rc;
+}
+
+int sb_model_forward_times(sb_handle_t h, int model_id, int enable, int cap, float* out_ms, int32_t* out_n) {
+  SbModel* m = get_model(h, model_id);
+  if (!m) return sb_fail(h, SB_ERR_INVALID, "bad model id");
+  SB_CUDA(h, cudaSetDevice(h->device));
+  SB_CUDA(h, cudaStreamSynchronize(h->stream));
+  int n = 0;
+  for (; n < m->fwd_n && n < cap && out_ms; ++n)
+    SB_CUDA(h, cudaEventElapsedTime(&out_ms[n], m->fwd_events[2 * n], m->fwd_events[2 * n + 1]));
+  if (out_n) *out_n = n;
+  m->fwd_n = 0;
+  if (enable && m->fwd_events.empty()) {
+    m->fwd_events.resize(2 * 1024);
+    for (auto& e : m->fwd_events) SB_CUDA(h, cudaEventCreate(&e));
+  }
+  m->fwd_timing = enable != 0;
+  return SB_OK;
 }
 
 // ---------------------------------- bottom-up ------------------------------------------------

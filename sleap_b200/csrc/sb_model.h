@@ -70,6 +70,9 @@ struct SbModel {
   std::vector<SbConvTcPlan*> tc_plans;  // per op (nullptr = direct path)
   std::vector<char> skip_op;            // POOL ops fused into the producing tensor-core conv
   std::vector<cudaEvent_t> prof_events; // non-empty only inside sb_model_profile_ops
+  std::vector<cudaEvent_t> fwd_events;  // sb_model_forward_times: (start, end) pairs around every forward pass
+  int fwd_n = 0;                        // pairs recorded since the last read
+  bool fwd_timing = false;
   // predictors
   SbPostWs ws;
   sb_bottomup_params bu{};

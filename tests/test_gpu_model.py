@@ -287,7 +287,7 @@ def test_tc_path_matches_direct_fp16(monkeypatch):
     assert launches_tc > 0
 
 
-@pytest.mark.parametrize("fused", [None, "0", "1"])
+@pytest.mark.parametrize("fused", [None, "0", "1", "2"])
 @pytest.mark.parametrize("cin,cout", [(16, 16), (64, 32), (128, 64), (256, 128), (512, 256)])
 def test_tc_tconv_layers(cin, cout, fused, monkeypatch):
     """Conv2DTranspose(k3, s2) on the tensor cores: four forked per-phase launches ("0") or the fused
@@ -326,8 +326,8 @@ def test_tc_tconv_layers(cin, cout, fused, monkeypatch):
 
     if fused is not None:
         monkeypatch.setenv("SB_FORCE_VARIANT", "2")
-        if fused == "1":
-            monkeypatch.setenv("SB_FORCE_FUSED_TCONV", "1")
+        if fused in ("1", "2"):            # "2": the cluster twin (cta_group::2 pair) of the fused form where weights are streamed
+            monkeypatch.setenv("SB_FORCE_FUSED_TCONV", fused)
     got = run()
     monkeypatch.delenv("SB_FORCE_VARIANT", raising=False)
     monkeypatch.delenv("SB_FORCE_FUSED_TCONV", raising=False)
@@ -361,7 +361,7 @@ def test_tc_forced_variants_unet(variant, fused, monkeypatch):
         assert np.abs(a - b).max() / scale < 3e-3, np.abs(a - b).max() / scale
 
 
-@pytest.mark.parametrize("variant", [None, "0", "1", "2", "3", "4", "5"])
+@pytest.mark.parametrize("variant", [None, "0", "1", "2", "3", "4", "5", "6", "7"])
 @pytest.mark.parametrize("cin,cout,k,hw", [(16, 16, 3, (40, 48)), (32, 32, 3, (40, 48)), (64, 64, 3, (53, 70)),
                                            (128, 128, 3, (40, 48)), (256, 128, 3, (53, 70)), (128, 256, 3, (40, 48)),
                                            (256, 512, 3, (40, 48)), (64, 13, 1, (40, 48)), (128, 24, 1, (40, 48)),
@@ -370,10 +370,25 @@ def test_tc_forced_variants_unet(variant, fused, monkeypatch):
                                            (32, 32, 5, (40, 48)), (64, 48, 7, (53, 70)), (128, 64, 5, (40, 48)), (16, 16, 7, (40, 48)),
                                            (192, 384, 3, (10, 10)), (384, 384, 3, (5, 7)), (64, 64, 3, (12, 20)), (96, 24, 1, (3, 3))])
 def test_tc_single_layers(cin, cout, k, hw, variant, monkeypatch):
+    _tc_single_layer(cin, cout, k, hw, variant, monkeypatch)
+
+
+@pytest.mark.parametrize("variant", ["3", "5", "7"])
+@pytest.mark.parametrize("cin,cout,hw", [(256, 128, (53, 70)), (128, 256, (40, 48))])
+def test_tc_multicast_twins(cin, cout, hw, variant, monkeypatch):
+    """The multicast form of the cluster twins (each CTA fetches half of every weight slice and multicasts it to both;
+    SB_ENABLE_MULTICAST=1 -- by default the twin is the cta_group::2 pair, covered by test_tc_single_layers)."""
+    monkeypatch.setenv("SB_ENABLE_MULTICAST", "1")
+    _tc_single_layer(cin, cout, 3, hw, variant, monkeypatch)
+
+
+def _tc_single_layer(cin, cout, k, hw, variant, monkeypatch):
     """Each swizzle mode / chunk count / N-tile shape of the tensor-core conv on its own, with the
     kernel variant chosen by the autotuner (None) or forced: 0 streaming, 1 weights-resident,
-    2 halo 8x16, 3 / 4 / 5 halo super-tiles 16x16 / 16x32 / 8x32 (weights resident or streamed); a forced variant
-    that does not apply to the layer falls back to the streaming kernel."""
+    2.. the halo candidates in plan order: 8x16, super-tiles 16x16 / 16x32 / 8x32 (weights resident or streamed), each
+    weight-streamed one followed by its cluster twin (the cta_group::2 pair: M = 256 MMAs over two CTAs; with
+    SB_ENABLE_MULTICAST=1 the multicast form) -- up to six candidates, so 2..7; a forced variant that does not apply to
+    the layer falls back to the streaming kernel."""
     if variant is not None:
         monkeypatch.setenv("SB_FORCE_VARIANT", variant)
     import torch
