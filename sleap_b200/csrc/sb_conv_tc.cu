@@ -94,6 +94,9 @@ struct TcParams {
   int epi_mode;
   // 1: the full-resolution output of this conv has no reader (only its fused 2x2 max-pool is consumed): skip the stores
   int skip_out;
+  // precision 2 (split-fp16 activations): the C_out logical channels are stored as three fp16 planes [lo | hi | hi],
+  // Cout channels apart, from out_coff / pool_coff (sb_kernels_direct.cuh: st_split); 0 for fp32 head outputs
+  int split;
 };
 
 #include "sb_tc_prims.cuh"
@@ -140,6 +143,53 @@ __device__ __forceinline__ void tc_epilogue_cols(const TcParams& P, const float*
       v[4 * j4 + 2] = v[4 * j4 + 2] * sc.z + sh.z;
       v[4 * j4 + 3] = v[4 * j4 + 3] * sc.w + sh.w;
     }
+  }
+  if (P.split) {
+    // v = hi + lo: both planes (and the second copy of hi that pairs with the consumer's Wl rows) are written; the fused
+    // 2x2 max-pool takes the maximum of the fp32 values BEFORE they are split (max is not separable over hi / lo)
+    const bool full = n0 + c0 + 16 <= P.Cout;
+    auto store3 = [&](__half* base, int Ctot, int coff, const float (&x)[16]) {
+      __align__(16) __half hh[16], ll[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        hh[j] = __float2half_rn(x[j]);
+        ll[j] = __float2half_rn(x[j] - __half2float(hh[j]));
+      }
+      __half* p0 = base + coff + n0 + c0;
+      if (full) {
+        const bool wide = ((Ctot | (coff + n0) | P.Cout) & 15) == 0;
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) {
+          __half* pd = p0 + pl * P.Cout;
+          const __half* src = pl == 0 ? ll : hh;
+          if (wide) st_global_256(pd, *reinterpret_cast<const __half2 (*)[8]>(src));
+          else {
+            reinterpret_cast<uint4*>(pd)[0] = *reinterpret_cast<const uint4*>(src);
+            reinterpret_cast<uint4*>(pd)[1] = *reinterpret_cast<const uint4*>(src + 8);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (n0 + c0 + j < P.Cout) { p0[j] = ll[j]; p0[P.Cout + j] = hh[j]; p0[2 * P.Cout + j] = hh[j]; }
+      }
+    };
+    if (valid && !(P.pool_out != nullptr && P.skip_out))
+      store3(reinterpret_cast<__half*>(P.out) + pix * P.out_Ctot, P.out_Ctot, P.out_coff, v);
+    if (P.pool_out != nullptr) {
+      const int tw = TWC ? TWC : P.tw;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+        v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], tw));
+      }
+      const int lr = lane / tw, lc = lane % tw;
+      if (valid && ((lc | lr) & 1) == 0) {
+        const int py = (y0 >> 1) + ((q * (32 / tw) + lr) >> 1), px = (x0 >> 1) + (lc >> 1);
+        store3(reinterpret_cast<__half*>(P.pool_out) + (((size_t)b * P.pool_H + py) * P.pool_W + px) * P.pool_Ctot, P.pool_Ctot, P.pool_coff, v);
+      }
+    }
+    return;
   }
   if (P.pool_out != nullptr) {
     // fused MaxPool2D(2, strides=2) (fp16 outputs only): lanes of a warp hold tile pixels
@@ -1358,8 +1408,9 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
     const SbBuffer& pb = m->buffers[op.pool_buf()];
     P.pool_out = pb.dev; P.pool_H = pb.H; P.pool_W = pb.W; P.pool_Ctot = pb.C; P.pool_coff = op.pool_coff();
   }
+  P.split = (m->precision == 2 && !ob.f32) ? 1 : 0;
   P.epi_mode = 0;
-  if (!getenv("SB_DISABLE_FAST_EPILOGUE") && !ob.f32 && P.bn_scale == nullptr && Cout % 16 == 0 && plan->Cout_pad == Cout &&
+  if (!P.split && !getenv("SB_DISABLE_FAST_EPILOGUE") && !ob.f32 && P.bn_scale == nullptr && Cout % 16 == 0 && plan->Cout_pad == Cout &&
       ob.C % 16 == 0 && out_coff % 16 == 0 && (P.pool_out == nullptr || (P.pool_Ctot % 16 == 0 && P.pool_coff % 16 == 0)))
     P.epi_mode = 1;
   P.row_bytes = KC * 2;
@@ -1909,7 +1960,8 @@ int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m);
 int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m) {
   m->tc_plans.assign(m->ops.size(), nullptr);
   m->skip_op.assign(m->ops.size(), 0);
-  if (m->precision != 0) return 0;
+  if (m->precision == 1) return 0;
+  const bool split = m->precision == 2;          // physical extent of a conv's output slice: 3 x C_out fp16 planes
   static bool attr_set = false;
   if (!attr_set) {
     SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
@@ -2019,15 +2071,16 @@ int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m) {
           if (oj == oi || oj == oi + 1) continue;
           const SbOp& o2 = m->ops[oj];
           if (o2.kind() == SB_OPK_PREPROCESS) continue;
-          const bool overl_in = o2.in_buf() == op.out_buf() && o2.in_coff() < op.out_coff() + Cout && op.out_coff() < o2.in_coff() + o2.in_C();
-          const bool overl_in2 = o2.kind() == SB_OPK_ADD && o2.in2_buf() == op.out_buf() && o2.in2_coff() < op.out_coff() + Cout &&
+          const int ext = split ? 3 * Cout : Cout;
+          const bool overl_in = o2.in_buf() == op.out_buf() && o2.in_coff() < op.out_coff() + ext && op.out_coff() < o2.in_coff() + o2.in_C();
+          const bool overl_in2 = o2.kind() == SB_OPK_ADD && o2.in2_buf() == op.out_buf() && o2.in2_coff() < op.out_coff() + ext &&
                                  op.out_coff() < o2.in2_coff() + o2.in_C();
           read = overl_in || overl_in2;
         }
         plan->out_dead = !read && !getenv("SB_DISABLE_DEAD_STORE_ELIM");
       }
   }
-  for (size_t oi = 0; oi + 1 < m->ops.size(); ++oi)
+  for (size_t oi = 0; oi + 1 < m->ops.size() && !split; ++oi)   // precision 2: the first conv runs on k_conv_first / k_conv_direct in fp32
     if (m->ops[oi].kind() == SB_OPK_PREPROCESS) {
       const int cv = sb_first_fusion_op(m, oi);
       if (cv >= 0 && !m->tc_plans[cv]) {
@@ -2047,7 +2100,7 @@ int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m) {
       }
     }
   // fused first encoder block: frame -> conv0 -> conv1 -> pool in one kernel (sb_conv01.cu) when conv1's own output is dead
-  for (size_t oi = 0; oi + 2 < m->ops.size(); ++oi)
+  for (size_t oi = 0; oi + 2 < m->ops.size() && !split; ++oi)
     if (m->ops[oi].kind() == SB_OPK_PREPROCESS) {
       const int cv = sb_first_fusion_op(m, oi);
       if (cv >= 0 && cv + 1 < (int)m->ops.size() && m->ops[cv + 1].kind() == SB_OPK_CONV && m->tc_plans[cv + 1]) {
@@ -2378,7 +2431,7 @@ static std::vector<std::pair<const SbModel*, SbFirstTc*>> g_first_plans;
 bool sb_conv_first_tc_ok(const SbModel* m, const SbOp& cv) {
   // same speed as the CUDA-core kernel (both are bound by the 16-channel output write); off by default
   // because it rounds the input pixel to fp16 before the MAC.  SB_ENABLE_FIRST_TC=1 turns it on.
-  if (!getenv("SB_ENABLE_FIRST_TC")) return false;
+  if (!getenv("SB_ENABLE_FIRST_TC") || m->precision != 0) return false;
   const int co = cv.out_C();
   return co == 16 || co == 32 || co == 64;
 }

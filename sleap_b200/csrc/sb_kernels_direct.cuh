@@ -22,6 +22,19 @@ template <> __device__ __forceinline__ float ld<float>(const float* p) { return 
 template <> __device__ __forceinline__ float ld<__half>(const __half* p) { return __half2float(*p); }
 __device__ __forceinline__ void st(float* p, float v) { *p = v; }
 __device__ __forceinline__ void st(__half* p, float v) { *p = __float2half_rn(v); }
+// Split-fp16 activations (precision 2): a tensor of C logical channels occupies 3C fp16 channels [lo | hi | hi] with
+// hi = fp16(v), lo = fp16(v - hi); a consumer conv whose weight rows are [Wh | Wl | Wh] (Wh = fp16(W), Wl = fp16(W - Wh))
+// then accumulates lo*Wh + hi*Wl + hi*Wh = v*W up to the dropped lo*Wl term (2^-22 relative) on the fp16 tensor cores.
+// The two correction planes come FIRST in channel (= K) order: the tensor core's fp32 accumulator truncates, each MMA
+// step losing ~ulp(accumulator), so the 2^-11-sized terms are added while the accumulator is still small.
+// `split` = C (the distance between the three planes), 0 = plain store.
+__device__ __forceinline__ void st_split(float* p, float v, int) { *p = v; }
+__device__ __forceinline__ void st_split(__half* p, float v, int split) {
+  const __half hi = __float2half_rn(v);
+  if (split) { p[0] = __float2half_rn(v - __half2float(hi)); p[split] = hi; p[2 * split] = hi; }
+  else *p = hi;
+}
+__device__ __forceinline__ float ld_split(const __half* p, int split) { return __half2float(p[0]) + __half2float(p[split]); }
 
 struct View {       // channel-slice view of an NHWC buffer
   void* ptr;
@@ -39,7 +52,7 @@ __global__ void __launch_bounds__(256) k_conv_direct(
     const TI* __restrict__ in, int Hin, int Win, int in_Ctot, int in_coff, int Cin,
     TO* __restrict__ out, int Hout, int Wout, int out_Ctot, int out_coff, int Cout,
     const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ bn_scale,
-    const float* __restrict__ bn_shift, int k, int stride, int pad_top, int pad_left, int relu) {
+    const float* __restrict__ bn_shift, int k, int stride, int pad_top, int pad_left, int relu, int split = 0) {
   extern __shared__ float smem[];
   const int in_tile = (DC_TILE - 1) * stride + k;
   float* s_in = smem;                                   // [in_tile][in_tile][DC_CK]
@@ -102,7 +115,7 @@ __global__ void __launch_bounds__(256) k_conv_direct(
         float v = acc[c] + (bias ? bias[co0 + c] : 0.f);
         if (relu) v = fmaxf(v, 0.f);
         if (bn_scale) v = v * bn_scale[co0 + c] + bn_shift[co0 + c];
-        st(po + c, v);
+        st_split(po + c, v, split);
       }
     }
   }
@@ -117,7 +130,7 @@ template <typename TI, int CIN, int COUT, int PX>
 __global__ void __launch_bounds__(256) k_conv_first(const TI* __restrict__ img, int Hin, int Win, int Hnet, int Wnet,
                                                     __half* __restrict__ out, int out_Ctot, int out_coff,
                                                     const float* __restrict__ w /*[9][CIN][COUT]*/,
-                                                    const float* __restrict__ bias, int relu, int in_is_u8) {
+                                                    const float* __restrict__ bias, int relu, int in_is_u8, int split = 0) {
   // each thread: PX horizontally adjacent output pixels x COUT channels (weights read once from
   // shared memory per PX pixels; the thread's PX*COUT fp16 outputs are contiguous in NHWC)
   __shared__ __align__(16) float s_w[9 * CIN * COUT];
@@ -170,6 +183,23 @@ __global__ void __launch_bounds__(256) k_conv_first(const TI* __restrict__ img, 
   for (int p = 0; p < PX; ++p) {
     if (ox0 + p >= Wnet) break;
     __half* po = out + (((size_t)b * Hnet + oy) * Wnet + ox0 + p) * out_Ctot + out_coff;
+    if (split) {                                             // precision 2: [lo | hi | hi] planes, COUT channels apart
+#pragma unroll
+      for (int q = 0; q < COUT / 8; ++q) {
+        __align__(16) __half hh[8], ll[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float a = acc[p][8 * q + j];
+          if (relu) a = fmaxf(a, 0.f);
+          hh[j] = __float2half_rn(a);
+          ll[j] = __float2half_rn(a - __half2float(hh[j]));
+        }
+        reinterpret_cast<uint4*>(po)[q] = *reinterpret_cast<uint4*>(ll);
+        reinterpret_cast<uint4*>(po + COUT)[q] = *reinterpret_cast<uint4*>(hh);
+        reinterpret_cast<uint4*>(po + 2 * COUT)[q] = *reinterpret_cast<uint4*>(hh);
+      }
+      continue;
+    }
     const bool wide = (COUT % 16 == 0) && (((out_Ctot | out_coff) & 15) == 0);     // 32-byte aligned rows
 #pragma unroll
     for (int q = 0; q < COUT / 8; ++q) {
@@ -205,7 +235,7 @@ template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) k_tconv_direct(
     const TI* __restrict__ in, int Hin, int Win, int in_Ctot, int in_coff, int Cin,
     TO* __restrict__ out, int out_Ctot, int out_coff, int Cout, const float* __restrict__ w,
-    const float* __restrict__ bias, int relu) {
+    const float* __restrict__ bias, int relu, int split = 0) {
   const int Hout = 2 * Hin, Wout = 2 * Win;
   const int b = blockIdx.z;
   const int co0 = blockIdx.y * DC_CO;
@@ -238,7 +268,7 @@ __global__ void __launch_bounds__(256) k_tconv_direct(
     if (co0 + c < Cout) {
       float v = acc[c] + (bias ? bias[co0 + c] : 0.f);
       if (relu) v = fmaxf(v, 0.f);
-      st(po + c, v);
+      st_split(po + c, v, split);
     }
 }
 
@@ -361,6 +391,63 @@ __global__ void k_preprocess(const TI* __restrict__ in, int Hin, int Win, int Ci
       }
     }
     st(out + t, v);
+  }
+}
+
+// ---- precision 2 (split-fp16 activations, see st_split): the elementwise ops act on v = hi + lo ----
+// C is the LOGICAL channel count; the tensors hold 3C channels [lo | hi | hi] from their channel offset.
+__global__ void k_maxpool2_split(const __half* __restrict__ in, int Hin, int Win, int in_Ctot, int in_coff, int C,
+                                 __half* __restrict__ out, int Hout, int Wout, int out_Ctot, int out_coff, size_t total) {
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(t % C);
+    const int ox = (int)((t / C) % Wout);
+    const int oy = (int)((t / ((size_t)C * Wout)) % Hout);
+    const int b = (int)(t / ((size_t)C * Wout * Hout));
+    const __half* pin = in + (size_t)b * Hin * Win * in_Ctot + in_coff + c;
+    float m = -INFINITY;
+    for (int dy = 0; dy < 2; ++dy)
+      for (int dx = 0; dx < 2; ++dx) {
+        const int iy = 2 * oy + dy, ix = 2 * ox + dx;
+        if (iy < Hin && ix < Win) m = fmaxf(m, ld_split(pin + ((size_t)iy * Win + ix) * in_Ctot, C));
+      }
+    st_split(out + (((size_t)b * Hout + oy) * Wout + ox) * out_Ctot + out_coff + c, m, C);
+  }
+}
+
+__global__ void k_upsample2_split(const __half* __restrict__ in, int Hin, int Win, int in_Ctot, int in_coff, int C,
+                                  __half* __restrict__ out, int out_Ctot, int out_coff, int bilinear, size_t total) {
+  const int Hout = 2 * Hin, Wout = 2 * Win;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(t % C);
+    const int ox = (int)((t / C) % Wout);
+    const int oy = (int)((t / ((size_t)C * Wout)) % Hout);
+    const int b = (int)(t / ((size_t)C * Wout * Hout));
+    const __half* pin = in + (size_t)b * Hin * Win * in_Ctot + in_coff + c;
+    float v;
+    if (!bilinear) {
+      v = ld_split(pin + ((size_t)(oy >> 1) * Win + (ox >> 1)) * in_Ctot, C);
+    } else {
+      const float sy = ((float)oy + 0.5f) * 0.5f - 0.5f, sx = ((float)ox + 0.5f) * 0.5f - 0.5f;
+      const float fy = floorf(sy), fx = floorf(sx);
+      const int y0 = max((int)fy, 0), y1 = min((int)ceilf(sy), Hin - 1);
+      const int x0 = max((int)fx, 0), x1 = min((int)ceilf(sx), Win - 1);
+      const float ly = sy - fy, lx = sx - fx;
+      const float tl = ld_split(pin + ((size_t)y0 * Win + x0) * in_Ctot, C), tr = ld_split(pin + ((size_t)y0 * Win + x1) * in_Ctot, C);
+      const float bl = ld_split(pin + ((size_t)y1 * Win + x0) * in_Ctot, C), br = ld_split(pin + ((size_t)y1 * Win + x1) * in_Ctot, C);
+      const float tp = tl + (tr - tl) * lx, bt = bl + (br - bl) * lx;
+      v = tp + (bt - tp) * ly;
+    }
+    st_split(out + (((size_t)b * Hout + oy) * Wout + ox) * out_Ctot + out_coff + c, v, C);
+  }
+}
+
+__global__ void k_add_split(const __half* __restrict__ a, int a_Ctot, int a_coff, const __half* __restrict__ bsrc, int b_Ctot,
+                            int b_coff, __half* __restrict__ out, int out_Ctot, int out_coff, int C, size_t npix) {
+  const size_t total = npix * C;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(t % C);
+    const size_t p = t / C;
+    st_split(out + p * out_Ctot + out_coff + c, ld_split(a + p * a_Ctot + a_coff + c, C) + ld_split(bsrc + p * b_Ctot + b_coff + c, C), C);
   }
 }
 

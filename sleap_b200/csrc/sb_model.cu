@@ -80,7 +80,7 @@ int sb_load_model(sb_handle_t h, const int32_t* ops, int n_ops, const float* wei
   if (!h) return sb_fail(nullptr, SB_ERR_INVALID, "null handle");
   if (!ops || n_ops <= 0 || !weights || n_weights <= 0 || !out_model_id)
     return sb_fail(h, SB_ERR_INVALID, "sb_load_model: bad arguments");
-  if (precision != 0 && precision != 1) return sb_fail(h, SB_ERR_INVALID, "precision must be 0 (fp16) or 1 (fp32)");
+  if (precision < 0 || precision > 2) return sb_fail(h, SB_ERR_INVALID, "precision must be 0 (fp16), 1 (fp32 CUDA cores) or 2 (split fp16 on the tensor cores)");
   SB_CUDA(h, cudaSetDevice(h->device));
   SbModel* m = new SbModel();
   m->precision = precision;
@@ -178,7 +178,7 @@ int sb_model_configure(sb_handle_t h, int model_id, int max_batch, int H, int W,
 // First conv fused with preprocessing (fp16 path): returns the conv op index or -1.
 static int first_fusion_op(const SbModel* m, size_t pre_index) { return sb_first_fusion_op(m, pre_index); }
 int sb_first_fusion_op(const SbModel* m, size_t pre_index) {
-  if (m->precision != 0 || getenv("SB_DISABLE_FIRST_FUSION")) return -1;
+  if (m->precision == 1 || getenv("SB_DISABLE_FIRST_FUSION")) return -1;
   if (pre_index + 1 >= m->ops.size()) return -1;
   const SbOp& pre = m->ops[pre_index];
   const SbOp& cv = m->ops[pre_index + 1];
@@ -214,15 +214,15 @@ int sb_stem_fusion_op(const SbModel* m, size_t pre_index) {
 
 template <typename TI, int CIN>
 static void launch_first(int co, int B, cudaStream_t s, const TI* img, int Hin, int Win, int Hnet, int Wnet, __half* out,
-                         int Ctot, int coff, const float* w, const float* b, int relu, int is_u8) {
+                         int Ctot, int coff, const float* w, const float* b, int relu, int is_u8, int split) {
   dim3 blk(32, 8);
   auto grid = [&](int px) { return dim3((Wnet + 32 * px - 1) / (32 * px), (Hnet + 7) / 8, B); };
   switch (co) {
-    case 8: k_conv_first<TI, CIN, 8, 4><<<grid(4), blk, 0, s>>>(img, Hin, Win, Hnet, Wnet, out, Ctot, coff, w, b, relu, is_u8); break;
-    case 16: k_conv_first<TI, CIN, 16, 4><<<grid(4), blk, 0, s>>>(img, Hin, Win, Hnet, Wnet, out, Ctot, coff, w, b, relu, is_u8); break;
-    case 24: k_conv_first<TI, CIN, 24, 2><<<grid(2), blk, 0, s>>>(img, Hin, Win, Hnet, Wnet, out, Ctot, coff, w, b, relu, is_u8); break;
-    case 32: k_conv_first<TI, CIN, 32, 2><<<grid(2), blk, 0, s>>>(img, Hin, Win, Hnet, Wnet, out, Ctot, coff, w, b, relu, is_u8); break;
-    default: k_conv_first<TI, CIN, 64, 1><<<grid(1), blk, 0, s>>>(img, Hin, Win, Hnet, Wnet, out, Ctot, coff, w, b, relu, is_u8); break;
+    case 8: k_conv_first<TI, CIN, 8, 4><<<grid(4), blk, 0, s>>>(img, Hin, Win, Hnet, Wnet, out, Ctot, coff, w, b, relu, is_u8, split); break;
+    case 16: k_conv_first<TI, CIN, 16, 4><<<grid(4), blk, 0, s>>>(img, Hin, Win, Hnet, Wnet, out, Ctot, coff, w, b, relu, is_u8, split); break;
+    case 24: k_conv_first<TI, CIN, 24, 2><<<grid(2), blk, 0, s>>>(img, Hin, Win, Hnet, Wnet, out, Ctot, coff, w, b, relu, is_u8, split); break;
+    case 32: k_conv_first<TI, CIN, 32, 2><<<grid(2), blk, 0, s>>>(img, Hin, Win, Hnet, Wnet, out, Ctot, coff, w, b, relu, is_u8, split); break;
+    default: k_conv_first<TI, CIN, 64, 1><<<grid(1), blk, 0, s>>>(img, Hin, Win, Hnet, Wnet, out, Ctot, coff, w, b, relu, is_u8, split); break;
   }
 }
 
@@ -236,13 +236,14 @@ int sb_first_direct_launch(sb_handle_s* h, SbModel* m, int op_index, const void*
   const float* bias = op.b_off() >= 0 ? m->weights_dev + op.b_off() : nullptr;
   const int g = B;
   const int relu = (op.flags() & SB_OPF_RELU) ? 1 : 0;
+  const int split = m->precision == 2 ? op.out_C() : 0;
   // rows/cols beyond the resized frame (Hres, Wres) are the bottom/right zero padding
   if (frames_are_u8) {
-    if (m->Cin == 1) launch_first<unsigned char, 1>(op.out_C(), g, s, (const unsigned char*)frames_dev, m->Hin, m->Win, ob.H, ob.W, (__half*)ob.dev, ob.C, op.out_coff(), Wt, bias, relu, 1);
-    else launch_first<unsigned char, 3>(op.out_C(), g, s, (const unsigned char*)frames_dev, m->Hin, m->Win, ob.H, ob.W, (__half*)ob.dev, ob.C, op.out_coff(), Wt, bias, relu, 1);
+    if (m->Cin == 1) launch_first<unsigned char, 1>(op.out_C(), g, s, (const unsigned char*)frames_dev, m->Hin, m->Win, ob.H, ob.W, (__half*)ob.dev, ob.C, op.out_coff(), Wt, bias, relu, 1, split);
+    else launch_first<unsigned char, 3>(op.out_C(), g, s, (const unsigned char*)frames_dev, m->Hin, m->Win, ob.H, ob.W, (__half*)ob.dev, ob.C, op.out_coff(), Wt, bias, relu, 1, split);
   } else {
-    if (m->Cin == 1) launch_first<float, 1>(op.out_C(), g, s, (const float*)frames_dev, m->Hin, m->Win, ob.H, ob.W, (__half*)ob.dev, ob.C, op.out_coff(), Wt, bias, relu, 0);
-    else launch_first<float, 3>(op.out_C(), g, s, (const float*)frames_dev, m->Hin, m->Win, ob.H, ob.W, (__half*)ob.dev, ob.C, op.out_coff(), Wt, bias, relu, 0);
+    if (m->Cin == 1) launch_first<float, 1>(op.out_C(), g, s, (const float*)frames_dev, m->Hin, m->Win, ob.H, ob.W, (__half*)ob.dev, ob.C, op.out_coff(), Wt, bias, relu, 0, split);
+    else launch_first<float, 3>(op.out_C(), g, s, (const float*)frames_dev, m->Hin, m->Win, ob.H, ob.W, (__half*)ob.dev, ob.C, op.out_coff(), Wt, bias, relu, 0, split);
   }
   SB_CHECK_LAUNCH(h);
   return 0;
@@ -252,6 +253,7 @@ int sb_first_direct_launch(sb_handle_s* h, SbModel* m, int op_index, const void*
 template <typename T>
 static int run_ops_t(sb_handle_s* h, SbModel* m, const void* frames_dev, int frames_are_u8, int B) {
   cudaStream_t s = h->stream;
+  const bool split = m->precision == 2;         // split-fp16 activations: [lo | hi | hi] channel planes (sb_kernels_direct.cuh)
   int fused_first = -1, fused_conv1 = -1, fused_stem = -1;
   for (size_t oi = 0; oi < m->ops.size(); ++oi) {
     const SbOp& op = m->ops[oi];
@@ -295,7 +297,14 @@ static int run_ops_t(sb_handle_s* h, SbModel* m, const void* frames_dev, int fra
         int mode_ch = 0;
         if (m->Cin == 3 && ob.C == 1) mode_ch = 1;
         if (m->Cin == 1 && ob.C == 3) mode_ch = 2;
-        if (frames_are_u8)
+        if (ob.f32 && sizeof(T) == 2) {          // precision 2 keeps the preprocessed frame in fp32
+          if (frames_are_u8)
+            k_preprocess<unsigned char, float><<<grid_for(total, h->sm_count), 256, 0, s>>>(
+                (const unsigned char*)frames_dev, m->Hin, m->Win, m->Cin, (float*)ob.dev, ob.H, ob.W, ob.C, m->Hres, m->Wres, resize, mode_ch, 1, total);
+          else
+            k_preprocess<float, float><<<grid_for(total, h->sm_count), 256, 0, s>>>(
+                (const float*)frames_dev, m->Hin, m->Win, m->Cin, (float*)ob.dev, ob.H, ob.W, ob.C, m->Hres, m->Wres, resize, mode_ch, 0, total);
+        } else if (frames_are_u8)
           k_preprocess<unsigned char, T><<<grid_for(total, h->sm_count), 256, 0, s>>>(
               (const unsigned char*)frames_dev, m->Hin, m->Win, m->Cin, (T*)ob.dev, ob.H, ob.W, ob.C, m->Hres, m->Wres, resize, mode_ch, 1, total);
         else
@@ -311,12 +320,13 @@ static int run_ops_t(sb_handle_s* h, SbModel* m, const void* frames_dev, int fra
           if (rc) return rc;
           break;
         }
-        if (m->precision == 0 && sb_conv_tc_can(m, (int)oi)) {
+        if (m->precision != 1 && sb_conv_tc_can(m, (int)oi)) {
           int rc = sb_conv_tc_launch(h, m, (int)oi, B);
           if (rc) return rc;
           break;
         }
         const int k = op.k(), st = op.stride();
+        const int osplit = (split && !ob.f32) ? op.out_C() : 0;
         const int Hout = ob.H, Wout = ob.W;
         const int tot_h = std::max((Hout - 1) * st + k - ib.H, 0), tot_w = std::max((Wout - 1) * st + k - ib.W, 0);
         const int pad_top = tot_h / 2, pad_left = tot_w / 2;
@@ -328,23 +338,29 @@ static int run_ops_t(sb_handle_s* h, SbModel* m, const void* frames_dev, int fra
         const size_t sm = ((size_t)in_tile * in_tile * DC_CK + (size_t)k * k * DC_CK * DC_CO) * sizeof(float);
         dim3 g(((Wout + DC_TILE - 1) / DC_TILE) * ((Hout + DC_TILE - 1) / DC_TILE), (op.out_C() + DC_CO - 1) / DC_CO, B);
         const int relu = (op.flags() & SB_OPF_RELU) ? 1 : 0;
-        if (ob.f32 && sizeof(T) == 2) {
+        if (ib.f32 && sizeof(T) == 2) {              // precision 2: first conv straight from the fp32 preprocessed frame
+          if (ob.f32) return sb_fail(h, SB_ERR_INVALID, "conv from the fp32 input buffer to an fp32 head is not supported in precision 2");
+          auto kern = k_conv_direct<float, __half>;
+          if (sm > 48 * 1024) SB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+          kern<<<g, 256, sm, s>>>((const float*)ib.dev, ib.H, ib.W, ib.C, op.in_coff(), op.in_C(), (__half*)ob.dev, Hout, Wout,
+                                  ob.C, op.out_coff(), op.out_C(), W, bias, bs, bh, k, st, pad_top, pad_left, relu, osplit);
+        } else if (ob.f32 && sizeof(T) == 2) {
           auto kern = k_conv_direct<T, float>;
           if (sm > 48 * 1024) SB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
           kern<<<g, 256, sm, s>>>((const T*)ib.dev, ib.H, ib.W, ib.C, op.in_coff(), op.in_C(), (float*)ob.dev, Hout, Wout,
-                                  ob.C, op.out_coff(), op.out_C(), W, bias, bs, bh, k, st, pad_top, pad_left, relu);
+                                  ob.C, op.out_coff(), op.out_C(), W, bias, bs, bh, k, st, pad_top, pad_left, relu, 0);
         } else {
           auto kern = k_conv_direct<T, T>;
           if (sm > 48 * 1024) SB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
           kern<<<g, 256, sm, s>>>((const T*)ib.dev, ib.H, ib.W, ib.C, op.in_coff(), op.in_C(), (T*)ob.dev, Hout, Wout,
-                                  ob.C, op.out_coff(), op.out_C(), W, bias, bs, bh, k, st, pad_top, pad_left, relu);
+                                  ob.C, op.out_coff(), op.out_C(), W, bias, bs, bh, k, st, pad_top, pad_left, relu, osplit);
         }
         SB_CHECK_LAUNCH(h);
         break;
       }
       case SB_OPK_TCONV: {
         SbBuffer& ib = m->buffers[op.in_buf()];
-        if (m->precision == 0 && sb_conv_tc_can(m, (int)oi)) {
+        if (m->precision != 1 && sb_conv_tc_can(m, (int)oi)) {
           int rc = sb_conv_tc_launch(h, m, (int)oi, B);
           if (rc) return rc;
           break;
@@ -353,13 +369,18 @@ static int run_ops_t(sb_handle_s* h, SbModel* m, const void* frames_dev, int fra
         const float* bias = op.b_off() >= 0 ? m->weights_dev + op.b_off() : nullptr;
         dim3 g((ob.H * ob.W + 255) / 256, (op.out_C() + DC_CO - 1) / DC_CO, B);
         k_tconv_direct<T, T><<<g, 256, 0, s>>>((const T*)ib.dev, ib.H, ib.W, ib.C, op.in_coff(), op.in_C(), (T*)ob.dev, ob.C,
-                                               op.out_coff(), op.out_C(), W, bias, (op.flags() & SB_OPF_RELU) ? 1 : 0);
+                                               op.out_coff(), op.out_C(), W, bias, (op.flags() & SB_OPF_RELU) ? 1 : 0, split ? op.out_C() : 0);
         SB_CHECK_LAUNCH(h);
         break;
       }
       case SB_OPK_POOL: {
         SbBuffer& ib = m->buffers[op.in_buf()];
-        const size_t total = (size_t)B * ob.H * ob.W * op.in_C();
+        // precision 2: the record carries the physical channel count (3C); the split kernels work on logical channels
+        const size_t total = (size_t)B * ob.H * ob.W * (split ? op.in_C() / 3 : op.in_C());
+        if (split)
+          k_maxpool2_split<<<grid_for(total, h->sm_count), 256, 0, s>>>((const __half*)ib.dev, ib.H, ib.W, ib.C, op.in_coff(), op.in_C() / 3,
+                                                                        (__half*)ob.dev, ob.H, ob.W, ob.C, op.out_coff(), total);
+        else
         k_maxpool2<T><<<grid_for(total, h->sm_count), 256, 0, s>>>((const T*)ib.dev, ib.H, ib.W, ib.C, op.in_coff(), op.in_C(),
                                                                    (T*)ob.dev, ob.H, ob.W, ob.C, op.out_coff(), total);
         SB_CHECK_LAUNCH(h);
@@ -367,7 +388,12 @@ static int run_ops_t(sb_handle_s* h, SbModel* m, const void* frames_dev, int fra
       }
       case SB_OPK_UPSAMPLE: {
         SbBuffer& ib = m->buffers[op.in_buf()];
-        const size_t total = (size_t)B * ob.H * ob.W * op.in_C();
+        const size_t total = (size_t)B * ob.H * ob.W * (split ? op.in_C() / 3 : op.in_C());
+        if (split)
+          k_upsample2_split<<<grid_for(total, h->sm_count), 256, 0, s>>>((const __half*)ib.dev, ib.H, ib.W, ib.C, op.in_coff(), op.in_C() / 3,
+                                                                         (__half*)ob.dev, ob.C, op.out_coff(),
+                                                                         (op.flags() & SB_OPF_BILINEAR) ? 1 : 0, total);
+        else
         k_upsample2<T><<<grid_for(total, h->sm_count), 256, 0, s>>>((const T*)ib.dev, ib.H, ib.W, ib.C, op.in_coff(), op.in_C(),
                                                                     (T*)ob.dev, ob.C, op.out_coff(),
                                                                     (op.flags() & SB_OPF_BILINEAR) ? 1 : 0, total);
@@ -378,6 +404,11 @@ static int run_ops_t(sb_handle_s* h, SbModel* m, const void* frames_dev, int fra
         SbBuffer& ib = m->buffers[op.in_buf()];
         SbBuffer& ib2 = m->buffers[op.in2_buf()];
         const size_t npix = (size_t)B * ob.H * ob.W;
+        if (split)
+          k_add_split<<<grid_for(npix * (op.in_C() / 3), h->sm_count), 256, 0, s>>>((const __half*)ib.dev, ib.C, op.in_coff(), (const __half*)ib2.dev,
+                                                                                     ib2.C, op.in2_coff(), (__half*)ob.dev, ob.C, op.out_coff(),
+                                                                                     op.in_C() / 3, npix);
+        else
         k_add<T><<<grid_for(npix * op.in_C(), h->sm_count), 256, 0, s>>>((const T*)ib.dev, ib.C, op.in_coff(), (const T*)ib2.dev, ib2.C,
                                                                          op.in2_coff(), (T*)ob.dev, ob.C, op.out_coff(), op.in_C(), npix);
         SB_CHECK_LAUNCH(h);

@@ -296,6 +296,11 @@ class CompiledModel:
                 if L["kind"] == "tconv":
                     kern = np.transpose(kern, (0, 1, 3, 2))     # (kh,kw,Cout,Cin) -> (kh,kw,Cin,Cout)
                 assert kern.shape == (L["k"], L["k"], L["cin"], L["cout"]), (L["name"], kern.shape)
+                if "expand" in L:        # precision 2: input rows in the physical order of the split input, [Wh | Wl | Wh]
+                    src, part = L["expand"]
+                    wh = kern.astype(np.float16).astype(np.float32)
+                    wl = (kern - wh).astype(np.float16).astype(np.float32)
+                    kern = np.where((part == 1)[None, None, :, None], wl[:, :, src, :], wh[:, :, src, :])
                 blob[slot["w"]:slot["w"] + kern.size] = kern.reshape(-1)
                 bias = p.get("bias")
                 if bias is None:
@@ -326,7 +331,13 @@ def _compile_identity(spec: dict, input_channels: int, input_scale: float, pad_t
     return cm
 
 
-def compile_model(spec: dict, input_channels: int, input_scale: float = 1.0, pad_to_stride: Optional[int] = None) -> CompiledModel:
+def compile_model(spec: dict, input_channels: int, input_scale: float = 1.0, pad_to_stride: Optional[int] = None,
+                  split: bool = False) -> CompiledModel:
+    """``split=True`` lays the graph out for precision 2 (split-fp16 activations on the tensor cores): every fp16 tensor of
+    C channels occupies 3C physical channels [lo | hi | hi] (csrc/sb_kernels_direct.cuh: st_split), the preprocessed
+    frame stays fp32, and ``pack_weights`` expands every consumer conv's input rows to [Wh | Wl | Wh] in the physical
+    channel order of its input (concat buffers interleave the triples of their parts).  Records carry physical
+    channel counts / offsets, except ``out_C`` of CONV / TCONV which stays the GEMM N (logical C_out)."""
     if spec["backbone"] == "identity":
         return _compile_identity(spec, input_channels, input_scale, pad_to_stride)
     g = GraphBuilder()
@@ -357,22 +368,46 @@ def compile_model(spec: dict, input_channels: int, input_scale: float = 1.0, pad
         bufs.append((C, stride, f32))
         return len(bufs) - 1
 
-    x0.buf, x0.coff = new_buf(x0.C, 1, False), 0
+    if split:
+        x0.f32 = True            # the preprocessed frame stays fp32 (first conv on the CUDA cores, exact)
+
+    def pc(t):                   # physical channels of a tensor
+        return t.C if (not split or t.f32) else 3 * t.C
+
+    concat_parts = {}            # tensor id -> parts (for the physical channel map of split tensors)
+
+    def phys_map(t):
+        """(src, part) per physical channel: logical source channel and plane 0 = lo (pairs with Wh), 1 = hi (pairs with
+        Wl), 2 = hi (pairs with Wh): the correction terms first in K order (see st_split in csrc/sb_kernels_direct.cuh)."""
+        if not split or t.f32:
+            return np.arange(t.C), np.zeros(t.C, np.int64)
+        if t.id in concat_parts:
+            srcs, parts, off = [], [], 0
+            for p in concat_parts[t.id]:
+                s_, p_ = phys_map(p)
+                srcs.append(s_ + off)
+                parts.append(p_)
+                off += p.C
+            return np.concatenate(srcs), np.concatenate(parts)
+        return np.tile(np.arange(t.C), 3), np.repeat(np.arange(3), t.C)
+
+    x0.buf, x0.coff = new_buf(x0.C, 1, x0.f32), 0
     copies_before = {}   # sym op index -> list of (src tensor, dst buf, dst coff)
     for idx, (kind, o) in enumerate(g.sym_ops):
         if kind == "concat":
             y = o["y"]
-            y.buf, y.coff = new_buf(y.C, y.stride, False), 0
+            concat_parts[y.id] = list(o["parts"])
+            y.buf, y.coff = new_buf(pc(y), y.stride, False), 0
             off = 0
             for p in o["parts"]:
                 if p.buf is None:
                     p.buf, p.coff = y.buf, off
                 else:
                     copies_before.setdefault(idx, []).append((p, y.buf, off))
-                off += p.C
+                off += pc(p)
     for t in g.tensors:
         if t.buf is None:
-            t.buf, t.coff = new_buf(t.C, t.stride, t.f32), 0
+            t.buf, t.coff = new_buf(pc(t), t.stride, t.f32), 0
 
     cm = CompiledModel()
     cm.spec = spec
@@ -384,10 +419,16 @@ def compile_model(spec: dict, input_channels: int, input_scale: float = 1.0, pad
     cm.records.append(ol.preprocess_record(0, net_c, input_scale, pad_to_stride or max_stride))
 
     # ---- weights layout ----
+    if split:
+        by_name = {L["name"]: L for L in g.layers}
+        for kind, o in g.sym_ops:
+            if kind in ("conv", "tconv") and not o["x"].f32:
+                src, part = phys_map(o["x"])
+                by_name[o["name"]]["expand"] = (src, part)
     off = 0
     for L in g.layers:
         if L["kind"] in ("conv", "tconv"):
-            n = L["k"] * L["k"] * L["cin"] * L["cout"]
+            n = L["k"] * L["k"] * (len(L["expand"][0]) if "expand" in L else L["cin"]) * L["cout"]
             cm._w_slots[L["name"]] = dict(w=off, b=off + n)
             off += n + L["cout"]
         else:
@@ -401,7 +442,7 @@ def compile_model(spec: dict, input_channels: int, input_scale: float = 1.0, pad
     fused_pools = set()
     for idx, (kind, o) in enumerate(g.sym_ops):
         for (src, dbuf, dcoff) in copies_before.get(idx, []):
-            cm.records.append(ol.copy_record(src.buf, src.coff, src.C, dbuf, dcoff))
+            cm.records.append(ol.copy_record(src.buf, src.coff, pc(src), dbuf, dcoff))
         if kind == "conv":
             x, y = o["x"], o["y"]
             slot = cm._w_slots[o["name"]]
@@ -414,7 +455,7 @@ def compile_model(spec: dict, input_channels: int, input_scale: float = 1.0, pad
                 py = g.sym_ops[idx + 1][1]["y"]
                 pool_buf, pool_coff = py.buf, py.coff
                 fused_pools.add(idx + 1)
-            cm.records.append(ol.conv_record(x.buf, x.coff, x.C, y.buf, y.coff, y.C, o["k"], o["stride"],
+            cm.records.append(ol.conv_record(x.buf, x.coff, pc(x), y.buf, y.coff, y.C, o["k"], o["stride"],
                                              relu=o["relu"], w_off=slot["w"], b_off=slot["b"],
                                              bn_scale_off=bn["scale"] if bn else -1, bn_shift_off=bn["shift"] if bn else -1,
                                              pool_buf=pool_buf, pool_coff=pool_coff))
@@ -422,15 +463,15 @@ def compile_model(spec: dict, input_channels: int, input_scale: float = 1.0, pad
         elif kind == "tconv":
             x, y = o["x"], o["y"]
             slot = cm._w_slots[o["name"]]
-            cm.records.append(ol.tconv_record(x.buf, x.coff, x.C, y.buf, y.coff, y.C, w_off=slot["w"], b_off=slot["b"]))
+            cm.records.append(ol.tconv_record(x.buf, x.coff, pc(x), y.buf, y.coff, y.C, w_off=slot["w"], b_off=slot["b"]))
             flops += 2.0 * 9 * x.C * y.C / (x.stride ** 2)     # 2*9*Cin*Cout MACs per *input* pixel (Keras count)
         elif kind == "pool":
-            cm.records.append(ol.pool_record(o["x"].buf, o["x"].coff, o["x"].C, o["y"].buf, o["y"].coff,
+            cm.records.append(ol.pool_record(o["x"].buf, o["x"].coff, pc(o["x"]), o["y"].buf, o["y"].coff,
                                              fused=idx in fused_pools))
         elif kind == "up":
-            cm.records.append(ol.upsample_record(o["x"].buf, o["x"].coff, o["x"].C, o["y"].buf, o["y"].coff, o["bilinear"]))
+            cm.records.append(ol.upsample_record(o["x"].buf, o["x"].coff, pc(o["x"]), o["y"].buf, o["y"].coff, o["bilinear"]))
         elif kind == "add":
-            cm.records.append(ol.add_record(o["a"].buf, o["a"].coff, o["b"].buf, o["b"].coff, o["a"].C, o["y"].buf, o["y"].coff))
+            cm.records.append(ol.add_record(o["a"].buf, o["a"].coff, o["b"].buf, o["b"].coff, pc(o["a"]), o["y"].buf, o["y"].coff))
         elif kind == "concat":
             pass
     cm.flops_per_pixel = flops

@@ -13,6 +13,8 @@ from sleap_b200.nn import architectures as arch
 
 PRECISION_FP16 = 0   # fp16 activations, tensor-core convs, fp32 accumulate, fp32 head outputs
 PRECISION_FP32 = 1   # fp32 CUDA-core path (strict parity with the fp32 reference)
+PRECISION_SPLIT = 2  # fp32-grade results on the fp16 tensor cores: activations and weights as hi + lo fp16 pairs, three
+                     # MMAs per product term (hi*Wh + lo*Wh + hi*Wl), fp32 accumulate; ~1e-6 of the fp32 path
 
 
 class DeviceModel:
@@ -22,7 +24,7 @@ class DeviceModel:
         self.spec = spec
         self.precision = precision
         self.input_scale = float(input_scale)
-        self.cm = arch.compile_model(spec, input_channels, input_scale, pad_to_stride)
+        self.cm = arch.compile_model(spec, input_channels, input_scale, pad_to_stride, split=(precision == PRECISION_SPLIT))
         blob = self.cm.pack_weights(weights)
         ops = self.cm.ops_array()
         mid = c_int(-1)
