@@ -30,7 +30,17 @@ constexpr int TW = 16, TH = 8;          // output tile (pixels); M = 128
 constexpr int MAX_GROUPS = 7, MAX_TAPS = 7;   // filter columns / rows of the widest kernel taken (7x7); the 3x3 kernels unroll 3
 // dynamic shared memory every kernel here is opted in for (cudaFuncAttributeMaxDynamicSharedMemorySize); more than
 // half of the SM's 227 KB, so a launch padded to this size is guaranteed to run one CTA per SM
-constexpr size_t kMaxDynSmem = 210 * 1024;
+constexpr size_t kMaxDynSmem = 225 * 1024;
+// shared memory the persistent / halo / programmed variants plan with (filter bank or weight ring + activation ring);
+// barriers, the TMEM slot and the bias / BN vectors come on top (~2.5 KB).  SB_SMEM_BUDGET_KB overrides (<= 220).
+static size_t tc_budget() {
+  static size_t b = 0;
+  if (!b) {
+    const char* e = getenv("SB_SMEM_BUDGET_KB");
+    b = (size_t)std::min(220, std::max(96, e ? atoi(e) : 196)) * 1024;
+  }
+  return b;
+}
 
 struct TcTap { int row_off, w_tap; };
 struct TcGroup { int dx, n_taps; TcTap taps[MAX_TAPS]; };
@@ -959,11 +969,21 @@ __global__ void __launch_bounds__(320) k_conv_tc_prog(const __grid_constant__ CU
 
   if (warp == 0 && lane == 0) {
     if (!w_stream) {
-      mbar_expect_tx(smem_u32(wbar), (uint32_t)(n_wslots * P.b_tx_bytes));
-      for (int ch = 0; ch < P.n_chunks; ++ch)
-        for (int u = 0; u < P.n_used_taps; ++u)
-          tma_load_3d(smem_u32(w_res + (size_t)(ch * P.n_used_taps + u) * P.w_slot_bytes), &mapB, smem_u32(wbar), ch * P.KC, 0,
-                      P.used_taps[u]);
+      if constexpr (PAIR) {
+        // resident filter bank split over the pair: each CTA keeps N/2 rows of every (chunk, tap) slice (half the shared
+        // memory -> a deeper activation ring); all loads are counted on the leader's barrier, whose MMA warp waits for it
+        if (crank == 0) mbar_expect_tx(smem_u32(wbar), (uint32_t)(n_wslots * P.b_tx_bytes));
+        for (int ch = 0; ch < P.n_chunks; ++ch)
+          for (int u = 0; u < P.n_used_taps; ++u)
+            tma_load_3d_pair(smem_u32(w_res + (size_t)(ch * P.n_used_taps + u) * P.w_slot_bytes), &mapB, mapa_rank(smem_u32(wbar), 0), ch * P.KC,
+                             (int)crank * (P.N / 2), P.used_taps[u]);
+      } else {
+        mbar_expect_tx(smem_u32(wbar), (uint32_t)(n_wslots * P.b_tx_bytes));
+        for (int ch = 0; ch < P.n_chunks; ++ch)
+          for (int u = 0; u < P.n_used_taps; ++u)
+            tma_load_3d(smem_u32(w_res + (size_t)(ch * P.n_used_taps + u) * P.w_slot_bytes), &mapB, smem_u32(wbar), ch * P.KC, 0,
+                        P.used_taps[u]);
+      }
     }
     int sa = 0, sw = 0;
     uint32_t pha = 0, phw = 0;
@@ -1265,6 +1285,98 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// 1x1 linear head (heads.py:55-63: Conv2D(channels, 1, activation="linear"), fp32 output): C_in x C_out per pixel is a few
+// hundred MACs against C_in * 2 + C_out * 4 bytes of traffic, i.e. an HBM-bound layer.  On the tcgen05 path each of the
+// 4 epilogue warps of an SM wrote 13 (24) strided 4-byte stores per pixel and the launch ran at 0.3-0.45 of its HBM
+// floor (profiles/r01_step_full_summary.md).  Here: warp-level mma.sync m16n8k16 (fp16 x fp16 -> fp32; the layer is not
+// tensor bound, what matters is that the MACs cost no issue slots), 16 pixels x C_in channels per warp staged with 16-byte-per-lane loads (whole 128-byte
+// lines per warp instruction; fragment loads straight from global memory cost 8 L1 wavefronts per 128 useful bytes and
+// ran at 1.7 TB/s) and read back with ldmatrix, weights [N_pad][C_in] fp16 in shared memory, and the 16 x C_out fp32 results of a warp staged through shared memory so that the global stores
+// are contiguous 4-byte-per-lane runs.  64 warps per SM keep ~128 KB of loads in flight.
+template <int NT>   // n-tiles of 8 output channels (C_out <= 8 * NT)
+__global__ void __launch_bounds__(256) k_head_1x1(const __half* __restrict__ in, int in_Ctot, int in_coff, int Cin,
+                                                  const __half* __restrict__ w /*[Cout_pad][Cin]*/, const float* __restrict__ bias,
+                                                  float* __restrict__ out, int out_Ctot, int out_coff, int Cout, int relu,
+                                                  size_t npix) {
+  extern __shared__ __align__(16) uint8_t hsm[];
+  const int KCH = Cin < 128 ? Cin : 128;                   // input channels staged per pass (Cin is a multiple of 16; of 128 beyond 128)
+  const int wpitch = Cin + 8;                              // halves per weight row (+16 B: conflict-free fragment loads)
+  const int apitch = KCH + 8;                              // halves per staged pixel row
+  __half* s_w = reinterpret_cast<__half*>(hsm);            // [8 * NT][wpitch]
+  __half* s_a = s_w + (size_t)8 * NT * wpitch;             // [8 warps][16][apitch]
+  float* s_out = reinterpret_cast<float*>(s_a + (size_t)8 * 16 * apitch);     // [8 warps][16][8 * NT + 1]
+  float* s_bias = s_out + 8 * 16 * (8 * NT + 1);
+  for (int t = threadIdx.x; t < 8 * NT * (Cin / 8); t += 256) {
+    const int r = t / (Cin / 8), c8 = t % (Cin / 8);
+    *reinterpret_cast<uint4*>(s_w + (size_t)r * wpitch + 8 * c8) = *reinterpret_cast<const uint4*>(w + (size_t)r * Cin + 8 * c8);
+  }
+  for (int t = threadIdx.x; t < 8 * NT; t += 256) s_bias[t] = (t < Cout && bias) ? bias[t] : 0.f;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+  float* so = s_out + warp * 16 * (8 * NT + 1);
+  __half* sa = s_a + (size_t)warp * 16 * apitch;
+  const uint32_t sa_ld = smem_u32(sa + (size_t)(lane & 15) * apitch + (lane >> 4) * 8);     // ldmatrix.x4 row address of this lane
+  const int c8n = KCH / 8;                                 // 16-byte pieces per staged row (a power of two: the host checks)
+  const int c8sh = __ffs(c8n) - 1;
+  const size_t n_tiles = (npix + 15) / 16;
+  for (size_t tile = (size_t)blockIdx.x * 8 + warp; tile < n_tiles; tile += (size_t)gridDim.x * 8) {
+    float acc[NT][4];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) { acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f; }
+    const __half* src = in + tile * 16 * in_Ctot + in_coff;
+    const int rows = (int)min((size_t)16, npix - tile * 16);
+    for (int k0 = 0; k0 < Cin; k0 += KCH) {
+      // 16 pixels x KCH channels, 16 bytes per lane and load: a warp-wide load covers whole 128-byte lines
+      for (int t = lane; t < 16 * c8n; t += 32) {        // no integer division anywhere in the tile loop: the first cut of this
+        const int r = t >> c8sh, c8 = t & (c8n - 1);     // kernel spent 57 % of its issue slots, mostly on them (ncu, profiles/)
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (r < rows) v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)r * in_Ctot + k0 + 8 * c8));
+        *reinterpret_cast<uint4*>(sa + (size_t)r * apitch + 8 * c8) = v;
+      }
+      __syncwarp();
+      for (int k = 0; k < KCH; k += 16) {
+        uint32_t ra0, ra1, ra2, ra3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(ra0), "=r"(ra1), "=r"(ra2), "=r"(ra3) : "r"(sa_ld + 2u * (uint32_t)k));
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+          const __half* wb = s_w + (size_t)(8 * n + g) * wpitch + k0 + k + 2 * tq;
+          const uint32_t rb0 = *reinterpret_cast<const uint32_t*>(wb), rb1 = *reinterpret_cast<const uint32_t*>(wb + 8);
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                       : "+f"(acc[n][0]), "+f"(acc[n][1]), "+f"(acc[n][2]), "+f"(acc[n][3])
+                       : "r"(ra0), "r"(ra1), "r"(ra2), "r"(ra3), "r"(rb0), "r"(rb1));
+        }
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      const int c = 8 * n + 2 * tq;
+      float v0 = acc[n][0] + s_bias[c], v1 = acc[n][1] + s_bias[c + 1], v2 = acc[n][2] + s_bias[c], v3 = acc[n][3] + s_bias[c + 1];
+      if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+      so[g * (8 * NT + 1) + c] = v0; so[g * (8 * NT + 1) + c + 1] = v1;
+      so[(g + 8) * (8 * NT + 1) + c] = v2; so[(g + 8) * (8 * NT + 1) + c + 1] = v3;
+    }
+    __syncwarp();
+    float* ob = out + tile * 16 * out_Ctot + out_coff;
+    if (NT <= 2) {                                        // two pixel rows per warp store: lanes 0-15 / 16-31 hold the channels of a row
+      const int rr = lane >> 4, cc = lane & 15;
+      if (cc < Cout) {
+#pragma unroll
+        for (int r = 0; r < 16; r += 2)
+          if (r + rr < rows) ob[(size_t)(r + rr) * out_Ctot + cc] = so[(r + rr) * (8 * NT + 1) + cc];
+      }
+    } else if (lane < Cout) {
+#pragma unroll
+      for (int r = 0; r < 16; ++r)
+        if (r < rows) ob[(size_t)r * out_Ctot + lane] = so[r * (8 * NT + 1) + lane];
+    }
+    __syncwarp();
+  }
+}
+
 struct TcLaunch {
   CUtensorMap mapA, mapB;
   TcParams P;          // streaming variant (one CTA per tile, weights streamed through a TMA ring)
@@ -1278,7 +1390,7 @@ struct TcLaunch {
   // halo variants (variant id 2 + i): super-tiles of sub_x x sub_y 8x16 sub-tiles, box [KC, 8*sub_x+2, 16*sub_y+2, 1]
   bool pp_valid;       // PP holds the tap/slot tables (the launch covers all output channels with one N)
   int n_halo;
-  struct Halo { CUtensorMap map; TcParams P; size_t smem; int occ, threads; bool prog; int mc; CUtensorMap mapBpiece; } halo[6];
+  struct Halo { CUtensorMap map; TcParams P; size_t smem; int occ, threads; bool prog; int mc; CUtensorMap mapBpiece; } halo[8];
 };
 
 }  // namespace
@@ -1456,7 +1568,7 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
         if (slot_of[wt] < 0) { slot_of[wt] = n_used; used[n_used++] = wt; }
       }
     const size_t w_bytes = (size_t)P.n_chunks * n_used * P.b_slot_bytes;
-    const size_t budget = 196 * 1024;
+    const size_t budget = tc_budget();
     L.pp_valid = plan->Cout_pad == N;
     {
       TcParams& Q = L.PP;
@@ -1521,7 +1633,7 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
     n_shapes = 1;
     L.has_persist = false;
   }
-  for (int hs = 0; hs < n_shapes && L.n_halo < 6 && L.pp_valid && small_filter && !getenv("SB_DISABLE_HALO"); ++hs) {
+  for (int hs = 0; hs < n_shapes && L.n_halo < 8 && L.pp_valid && small_filter && !getenv("SB_DISABLE_HALO"); ++hs) {
     const int sub_x = kHaloShapes[hs][0], sub_y = kHaloShapes[hs][1], egroups = kHaloShapes[hs][2];
     const int n_sub = sub_x * sub_y;
     const int pitch = fused_phases ? 9 : 8 * sub_x + 2, box_h = fused_phases ? 17 : 16 * sub_y + 2;
@@ -1592,7 +1704,7 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
     Hp.a_tx_bytes = box_h * pitch * KC * 2;
     Hp.a_slot_bytes = (Hp.a_tx_bytes + 1023) / 1024 * 1024;
     size_t w_bytes = (size_t)Hp.n_chunks * Hp.n_used_taps * Hp.w_slot_bytes;
-    const size_t budget = 196 * 1024;
+    const size_t budget = tc_budget();
     Hp.w_stream = 0; Hp.n_w_ring = 0;
     const bool resident_fits = !getenv("SB_DISABLE_PERSISTENT") && w_bytes + 2 * (size_t)Hp.a_slot_bytes <= budget;
     if (!resident_fits || getenv("SB_FORCE_WSTREAM")) {
@@ -1644,7 +1756,7 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
     // each CTA stages N/2 rows of every slice in a half-size slot, so the ring is deeper).  SB_ENABLE_MULTICAST=1 selects the
     // round-2 multicast form instead (mc = 2: full slices in both CTAs, each fetching half) -- measured no faster than
     // unicast, kept as an experiment.
-    if (Hp.w_stream && HC.prog && N % 16 == 0 && L.n_halo < 6 && !getenv("SB_DISABLE_MULTICAST") && !getenv("SB_DISABLE_PAIR")) {
+    if (Hp.w_stream && HC.prog && N % 16 == 0 && L.n_halo < 8 && !getenv("SB_DISABLE_MULTICAST") && !getenv("SB_DISABLE_PAIR")) {
       TcLaunch::Halo& H2 = L.halo[L.n_halo];
       const TcLaunch::Halo& H1 = L.halo[L.n_halo - 1];
       H2 = H1;
@@ -1655,8 +1767,8 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
         Q.w_slot_bytes = H1.P.w_slot_bytes / 2;                      // N/2 rows x KC: stays a multiple of 8 rows (N % 16 == 0)
         Q.idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
         const size_t a_bytes = (size_t)Q.n_a_slots * Q.a_slot_bytes;
-        Q.n_w_ring = (int)std::min<size_t>(8, (196 * 1024 - a_bytes) / Q.w_slot_bytes);
-        if (Q.n_a_slots == 2 && Q.n_w_ring >= 7 && 3 * (size_t)Q.a_slot_bytes + 6 * (size_t)Q.w_slot_bytes <= 196 * 1024) { Q.n_a_slots = 3; Q.n_w_ring = 6; }
+        Q.n_w_ring = (int)std::min<size_t>(8, (tc_budget() - a_bytes) / Q.w_slot_bytes);
+        if (Q.n_a_slots == 2 && Q.n_w_ring >= 7 && 3 * (size_t)Q.a_slot_bytes + 6 * (size_t)Q.w_slot_bytes <= tc_budget()) { Q.n_a_slots = 3; Q.n_w_ring = 6; }
         H2.smem = (size_t)Q.n_w_ring * Q.w_slot_bytes + (size_t)Q.n_a_slots * Q.a_slot_bytes + 1024 +
                   (size_t)(2 * Q.n_a_slots + 2 * 8 + 1 + 16) * 8 + 64 + 3 * 256 * sizeof(float);
       }
@@ -1665,6 +1777,38 @@ static int make_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
       cuuint32_t pbox[3] = {(cuuint32_t)KC, (cuuint32_t)(N / 2), 1};
       cuuint32_t wes[3] = {1, 1, 1};
       if (Q_ok(H2) && enc(&H2.mapBpiece, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)plan->w16, wdims, wstrides, pbox, wes, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              swz_for(KC), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+        ++L.n_halo;
+    } else if (!Hp.w_stream && N % 16 == 0 && L.n_halo < 8 && !getenv("SB_DISABLE_PAIR") && !getenv("SB_DISABLE_RESIDENT_PAIR") &&
+               (size_t)Hp.n_chunks * Hp.n_used_taps * Hp.w_slot_bytes >= 64 * 1024 && (Hp.w_slot_bytes / 2) % 1024 == 0) {
+      // cta_group::2 twin of a weights-RESIDENT candidate whose filter bank takes a large part of shared memory (128 -> 64:
+      // 147 KB, leaving two activation slots = one tile of look-ahead against ~1.5 us of TMA latency per box; ablations in
+      // DESIGN.md 7): the pair splits the bank, each CTA keeps N/2 rows of every slice, the activation ring gets the rest,
+      // and the M = 256 MMAs read half of B per SM (tools/probes/mma_probe.cu: N = 64, 43 instead of 48 clocks).
+      TcLaunch::Halo& H2 = L.halo[L.n_halo];
+      const TcLaunch::Halo& H1 = L.halo[L.n_halo - 1];
+      H2 = H1;
+      H2.mc = 4; H2.occ = 1; H2.prog = true;
+      TcParams& Q = H2.P;
+      Q.w_slot_bytes = H1.P.w_slot_bytes / 2;
+      Q.idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      for (int i = 0; i < Q.n_prog; ++i) {           // resident slices are addressed by offset: half-size slots
+        const uint32_t off16 = Q.prog[i].w_flags & 0xffffu;
+        Q.prog[i].w_flags = (Q.prog[i].w_flags & ~0xffffu) | ((off16 / 2) & 0xffffu);
+      }
+      const size_t wb2 = (size_t)Q.n_chunks * Q.n_used_taps * Q.w_slot_bytes;
+      Q.n_a_slots = std::max(2, std::min((int)((budget - wb2) / Q.a_slot_bytes), n_sub > 1 ? 4 : 8));
+      if (Q.n_acc < 2) { Q.epi_groups = 1; H2.threads = 192; } else H2.threads = 64 + 128 * Q.epi_groups;
+      const int NS2 = Q.n_acc * N;
+      Q.n_stages = Q.n_acc > 1 ? 4 : 8;
+      while (Q.n_stages > 1 && Q.n_stages * NS2 > 512) Q.n_stages >>= 1;
+      { int c = 32; while (c < Q.n_stages * NS2) c <<= 1; Q.tmem_cols = c; }
+      H2.smem = wb2 + (size_t)Q.n_a_slots * Q.a_slot_bytes + 1024 + (size_t)(2 * Q.n_a_slots + 2 * 8 + 1 + 16) * 8 + 64 + 3 * 256 * sizeof(float);
+      cuuint64_t wdims[3] = {(cuuint64_t)Cin, (cuuint64_t)plan->Cout_pad, (cuuint64_t)n_wtaps};
+      cuuint64_t wstrides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)plan->Cout_pad * Cin * 2};
+      cuuint32_t pbox[3] = {(cuuint32_t)KC, (cuuint32_t)(N / 2), 1};
+      cuuint32_t wes[3] = {1, 1, 1};
+      if (enc(&H2.mapBpiece, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)plan->w16, wdims, wstrides, pbox, wes, CU_TENSOR_MAP_INTERLEAVE_NONE,
               swz_for(KC), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
         ++L.n_halo;
     }
@@ -1964,27 +2108,27 @@ int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m) {
   const bool split = m->precision == 2;          // physical extent of a conv's output slice: 3 x C_out fp16 planes
   static bool attr_set = false;
   if (!attr_set) {
-    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    SB_CUDA(h, cudaFuncSetAttribute((k_conv_tc<1, 7>), cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    SB_CUDA(h, cudaFuncSetAttribute((k_conv_tc<2, 7>), cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    SB_CUDA(h, cudaFuncSetAttribute((k_conv_tc<4, 7>), cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_persist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_persist<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_persist<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_halo<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_prog<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_halo<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_prog<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_halo<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_prog<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    SB_CUDA(h, cudaFuncSetAttribute((k_conv_tc_prog<1, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    SB_CUDA(h, cudaFuncSetAttribute((k_conv_tc_prog<2, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    SB_CUDA(h, cudaFuncSetAttribute((k_conv_tc_prog<4, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    SB_CUDA(h, cudaFuncSetAttribute((k_conv_tc_prog<1, 2, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    SB_CUDA(h, cudaFuncSetAttribute((k_conv_tc_prog<2, 2, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
-    SB_CUDA(h, cudaFuncSetAttribute((k_conv_tc_prog<4, 2, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+    SB_CUDA(h, cudaFuncSetAttribute((k_conv_tc<1, 7>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+    SB_CUDA(h, cudaFuncSetAttribute((k_conv_tc<2, 7>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+    SB_CUDA(h, cudaFuncSetAttribute((k_conv_tc<4, 7>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_persist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_persist<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_persist<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_halo<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_prog<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_halo<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_prog<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_halo<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+    SB_CUDA(h, cudaFuncSetAttribute(k_conv_tc_prog<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+    SB_CUDA(h, cudaFuncSetAttribute((k_conv_tc_prog<1, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+    SB_CUDA(h, cudaFuncSetAttribute((k_conv_tc_prog<2, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+    SB_CUDA(h, cudaFuncSetAttribute((k_conv_tc_prog<4, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+    SB_CUDA(h, cudaFuncSetAttribute((k_conv_tc_prog<1, 2, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+    SB_CUDA(h, cudaFuncSetAttribute((k_conv_tc_prog<2, 2, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+    SB_CUDA(h, cudaFuncSetAttribute((k_conv_tc_prog<4, 2, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
     attr_set = true;
   }
   for (size_t oi = 0; oi < m->ops.size(); ++oi) {
@@ -2120,10 +2264,10 @@ static void launch_variant(sb_handle_s* h, TcLaunch& L, int B, int variant, cuda
     const int grid = std::max(1, std::min(P.n_tiles_total, h->sm_count * HC.occ));
     if (getenv("SB_DEBUG_LAUNCH")) fprintf(stderr, "[halo %dx%d] KC=%d N=%d stages=%d cols=%d occ=%d grid=%d slots=%d smem=%zu tiles=%d thr=%d\n", P.sub_x, P.sub_y, P.KC, P.N, P.n_stages, P.tmem_cols, HC.occ, grid, P.n_a_slots, HC.smem, P.n_tiles_total, HC.threads);
     if (HC.mc) {
-      // clusters of 2: every CTA must walk the same number of tiles -> the largest even grid that divides the tile count
-      int g2 = std::min(P.n_tiles_total, h->sm_count) & ~1;
-      while (g2 >= 2 && P.n_tiles_total % g2) g2 -= 2;
-      if (g2 < 2 || 4 * g2 < 3 * std::min(P.n_tiles_total, h->sm_count)) {      // no such grid (or it idles > 1/4 of the SMs): the unicast twin
+      // clusters of 2: the two CTAs of a cluster walk tiles (t, t + 1), (t + g, t + 1 + g), ... and must make the same number
+      // of steps -> an even grid over an even tile count (cluster ranks are consecutive block indices)
+      const int g2 = std::min(P.n_tiles_total, h->sm_count) & ~1;
+      if (g2 < 2 || (P.n_tiles_total & 1)) {      // odd tile count: the unicast twin
         launch_variant(h, L, B, variant - 1, stream, skip_out);
         return;
       }
@@ -2251,8 +2395,8 @@ int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
     if (!plan) continue;
     for (TcLaunch& L : plan->launches) {
       if (!L.has_persist && L.n_halo == 0) continue;
-      float best[8] = {1e30f, 1e30f, 1e30f, 1e30f, 1e30f, 1e30f, 1e30f, 1e30f};
-      for (int v = 0; v < 8; ++v) {
+      float best[10] = {1e30f, 1e30f, 1e30f, 1e30f, 1e30f, 1e30f, 1e30f, 1e30f, 1e30f, 1e30f};
+      for (int v = 0; v < 10; ++v) {
         if (!avail(L, v)) continue;
         for (int rep = 0; rep < 3; ++rep) {
           cudaEventRecord(e0, h->stream);
@@ -2273,7 +2417,7 @@ int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
         }
       }
       int pick = 0;
-      for (int v = 1; v < 8; ++v) if (best[v] < best[pick]) pick = v;
+      for (int v = 1; v < 10; ++v) if (best[v] < best[pick]) pick = v;
       L.use_persist = pick;
       if (dbg) {
         fprintf(stderr, "[sb_conv_tc] op %zu Cin=%d N=%d %dx%d: stream %.1f, persist %.1f (occ %d, %d slots)", oi, L.P.n_chunks * L.P.KC,
@@ -2384,8 +2528,46 @@ int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
   return 0;
 }
 
+// 1x1 fp32 heads on k_head_1x1 (HBM-bound; see the kernel) instead of the tcgen05 kernels.  SB_DISABLE_HEAD_KERNEL=1 reverts.
+static bool head_kernel_ok(const SbModel* m, const SbOp& op, const SbConvTcPlan* plan) {
+  if (getenv("SB_DISABLE_HEAD_KERNEL")) return false;
+  const SbBuffer& ib = m->buffers[op.in_buf()];
+  const SbBuffer& ob = m->buffers[op.out_buf()];
+  return op.kind() == SB_OPK_CONV && op.k() == 1 && op.stride() == 1 && ob.f32 && !ib.f32 && !(op.flags() & SB_OPF_BN) && op.in_C() % 16 == 0 &&
+         (op.in_C() == 16 || op.in_C() == 32 || op.in_C() == 64 || op.in_C() % 128 == 0) && op.out_C() <= 32 && ib.C % 8 == 0 && op.in_coff() % 8 == 0 && plan->w16 != nullptr && plan->Cout_pad >= (op.out_C() + 7) / 8 * 8 &&
+         (size_t)plan->Cout_pad * (op.in_C() + 8) * 2 <= 160 * 1024;
+}
+
+static int head_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan* plan, int B) {
+  const SbBuffer& ib = m->buffers[op.in_buf()];
+  const SbBuffer& ob = m->buffers[op.out_buf()];
+  const int nt = (op.out_C() + 7) / 8;
+  const size_t npix = (size_t)B * ob.H * ob.W;
+  const int kch = std::min(op.in_C(), 128);
+  const size_t smem = (size_t)8 * nt * (op.in_C() + 8) * 2 + (size_t)8 * 16 * (kch + 8) * 2 + (size_t)8 * 16 * (8 * nt + 1) * 4 + (size_t)8 * nt * 4;
+  const float* bias = op.b_off() >= 0 ? m->weights_dev + op.b_off() : nullptr;
+  const int relu = (op.flags() & SB_OPF_RELU) ? 1 : 0;
+  const int grid = (int)std::min<size_t>((npix + 127) / 128, (size_t)h->sm_count * 8);
+#define SB_HEAD_CASE(NT)                                                                                                        \
+  case NT: {                                                                                                                    \
+    static bool attr = false;                                                                                                   \
+    if (!attr) { SB_CUDA(h, cudaFuncSetAttribute(k_head_1x1<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; } \
+    k_head_1x1<NT><<<grid, 256, smem, h->stream>>>((const __half*)ib.dev, ib.C, op.in_coff(), op.in_C(), plan->w16, bias, (float*)ob.dev, ob.C, \
+                                                   op.out_coff(), op.out_C(), relu, npix);                                      \
+    break;                                                                                                                      \
+  }
+  switch (nt) {
+    SB_HEAD_CASE(1) SB_HEAD_CASE(2) SB_HEAD_CASE(3) SB_HEAD_CASE(4)
+    default: return sb_fail(h, SB_ERR_INVALID, "head kernel: %d output channels", op.out_C());
+  }
+#undef SB_HEAD_CASE
+  SB_CHECK_LAUNCH(h);
+  return 0;
+}
+
 int sb_conv_tc_launch(sb_handle_s* h, SbModel* m, int op_index, int B) {
   SbConvTcPlan* plan = m->tc_plans[op_index];
+  if (head_kernel_ok(m, m->ops[op_index], plan)) return head_launch(h, m, m->ops[op_index], plan, B);
   plan->skip_now = plan->out_dead && !m->keep_dead_stores;
   return launch_plan(h, plan, B, plan->use_fused);
 }

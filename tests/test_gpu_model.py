@@ -361,9 +361,9 @@ def test_tc_forced_variants_unet(variant, fused, monkeypatch):
         assert np.abs(a - b).max() / scale < 3e-3, np.abs(a - b).max() / scale
 
 
-@pytest.mark.parametrize("variant", [None, "0", "1", "2", "3", "4", "5", "6", "7"])
+@pytest.mark.parametrize("variant", [None, "0", "1", "2", "3", "4", "5", "6", "7", "8", "9"])
 @pytest.mark.parametrize("cin,cout,k,hw", [(16, 16, 3, (40, 48)), (32, 32, 3, (40, 48)), (64, 64, 3, (53, 70)),
-                                           (128, 128, 3, (40, 48)), (256, 128, 3, (53, 70)), (128, 256, 3, (40, 48)),
+                                           (128, 128, 3, (40, 48)), (256, 128, 3, (53, 70)), (128, 256, 3, (40, 48)), (128, 64, 3, (53, 70)),
                                            (256, 512, 3, (40, 48)), (64, 13, 1, (40, 48)), (128, 24, 1, (40, 48)),
                                            (24, 24, 3, (40, 48)), (48, 36, 3, (40, 48)), (96, 48, 3, (53, 70)),
                                            (192, 96, 3, (40, 48)), (24, 13, 1, (40, 48)),

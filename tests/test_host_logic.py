@@ -124,3 +124,53 @@ def test_progress_reporting_json_and_rich(capsys):
     assert len(list(p._with_progress(({"frame_ind": np.arange(4)} for _ in range(3)), 12))) == 3
     p.verbosity = "none"
     assert len(list(p._with_progress(iter([{"frame_ind": np.arange(2)}]), 2))) == 1
+
+
+def test_split_precision_layout_and_weight_expansion():
+    """Precision 2 (compile_model(split=True)): every fp16 tensor takes 3C physical channels [lo | hi | hi], concat
+    buffers interleave the triples of their parts, conv records carry physical in_C but logical out_C, and the expanded
+    weight rows [Wh | Wl | Wh] reproduce x @ W to ~1e-6 from the split activations (numpy emulation of the three products)."""
+    from oracle import synth
+    from sleap_b200.nn import architectures as A, oplist as ol
+    spec = dict(backbone="unet", head_type="multi_instance", part_names=synth.FLIES13_NODES, edges=synth.FLIES13_EDGES,
+                backbone_cfg=dict(filters=16, filters_rate=2, max_stride=32, output_stride=4, middle_block=True, up_interpolate=False),
+                heads=[dict(name="MultiInstanceConfmapsHead", channels=13, output_stride=4),
+                       dict(name="PartAffinityFieldsHead", channels=24, output_stride=8)])
+    cm1, cm2 = A.compile_model(spec, 1), A.compile_model(spec, 1, split=True)
+    assert cm1.n_buffers == cm2.n_buffers and len(cm1.records) == len(cm2.records)
+    r1, r2 = np.stack(cm1.records), np.stack(cm2.records)
+    for a, b in zip(r1, r2):
+        assert a[0] == b[0]
+        if a[0] == ol.BUFFER:
+            if a[1] == 0:
+                assert b[3] == a[3] and b[4] == 1               # the preprocessed frame: same channels, fp32
+            else:
+                assert b[3] == (a[3] if a[4] else 3 * a[3])     # fp32 head buffers keep their size
+        elif a[0] in (ol.CONV, ol.TCONV):
+            first = a[1] == 0
+            assert b[3] == (a[3] if first else 3 * a[3]) and b[8] == a[8]       # physical in_C, logical out_C
+            assert b[2] == 3 * a[2] and b[7] == (a[7] if r2[int(b[6])][4] else 3 * a[7])
+    w = A.make_synthetic_weights(cm1, 3)
+    blob1, blob2 = cm1.pack_weights(w), cm2.pack_weights(w)
+    rng = np.random.default_rng(0)
+    # a decoder conv that reads a concat buffer (skip | upsampled): physical order [Xl Xh Xh | Ul Uh Uh]
+    name = "stack0_dec1_s16_to_s8_refine_conv0"
+    L1 = next(L for L in cm1.layers if L["name"] == name)
+    L2 = next(L for L in cm2.layers if L["name"] == name)
+    cin, cout, k = L1["cin"], L1["cout"], L1["k"]
+    src, part = L2["expand"]
+    assert len(src) == 3 * cin and sorted(src.tolist()) == sorted(list(range(cin)) * 3)
+    half = cin // 2
+    assert part[:half].tolist() == [0] * half and part[half:2 * half].tolist() == [1] * half and part[2 * half:3 * half].tolist() == [2] * half
+    assert src[3 * half:4 * half].tolist() == list(range(half, cin))           # the second part's triple follows the first's
+    W = blob1[cm1._w_slots[name]["w"]:][:k * k * cin * cout].reshape(k * k, cin, cout)
+    We = blob2[cm2._w_slots[name]["w"]:][:k * k * 3 * cin * cout].reshape(k * k, 3 * cin, cout)
+    assert np.array_equal(We.astype(np.float16).astype(np.float32), We)       # every expanded weight is exactly fp16
+    x = np.maximum(rng.standard_normal((64, cin)), 0).astype(np.float32)
+    hi = x.astype(np.float16).astype(np.float32)
+    lo = (x - hi).astype(np.float16).astype(np.float32)
+    planes = np.stack([lo, hi, hi])                                             # plane p of logical channel c
+    xe = planes[part, :, src].T                                                 # (64, 3*cin) in physical channel order
+    got = xe.astype(np.float64) @ We[4].astype(np.float64)
+    want = x.astype(np.float64) @ W[4].astype(np.float64)
+    assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()
