@@ -142,7 +142,10 @@ int sb_group_instances_batch(sb_handle_t h, int B, int n_nodes, const float* pea
  * encoder_decoder.py, hourglass.py, heads.py:42-63.  ops: n_ops records of SB_OP_WORDS int32
  * (layout in sleap_b200/nn/oplist.py); weights: float32 blob the ops index into.
  * Replaces tf.keras.models.load_model + keras_model(imgs) (sleap/nn/inference.py:3203-3213,
- * :2875).  precision: 0 = fp16 tensor-core path (fp32 accumulate), 1 = fp32 CUDA-core path. */
+ * :2875).  precision: 0 = fp16 tensor-core path (fp32 accumulate), 1 = fp32 CUDA-core path,
+ * 2 = fp32-grade results on the tensor-core path: activations / weights as hi + lo fp16 pairs; the op-list must
+ * have been compiled for it (compile_model(split=True): 3C physical channels [lo | hi | hi] per fp16 tensor, weight
+ * rows [Wh | Wl | Wh], fp32 frame buffer; conv out_C stays the logical C_out) -- DESIGN.md 5.7. */
 #define SB_OP_WORDS 24
 int sb_load_model(sb_handle_t h, const int32_t* ops, int n_ops, const float* weights,
                   int64_t n_weights, int precision, int* out_model_id);

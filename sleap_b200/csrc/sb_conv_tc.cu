@@ -1295,13 +1295,12 @@ EncodeTiledFn get_encode() {
 // lines per warp instruction; fragment loads straight from global memory cost 8 L1 wavefronts per 128 useful bytes and
 // ran at 1.7 TB/s) and read back with ldmatrix, weights [N_pad][C_in] fp16 in shared memory, and the 16 x C_out fp32 results of a warp staged through shared memory so that the global stores
 // are contiguous 4-byte-per-lane runs.  64 warps per SM keep ~128 KB of loads in flight.
-template <int NT>   // n-tiles of 8 output channels (C_out <= 8 * NT)
+template <int NT, int KCH>   // n-tiles of 8 output channels (C_out <= 8 * NT); input channels staged per pass (16 / 32 / 64 / 128)
 __global__ void __launch_bounds__(256) k_head_1x1(const __half* __restrict__ in, int in_Ctot, int in_coff, int Cin,
                                                   const __half* __restrict__ w /*[Cout_pad][Cin]*/, const float* __restrict__ bias,
                                                   float* __restrict__ out, int out_Ctot, int out_coff, int Cout, int relu,
                                                   size_t npix) {
   extern __shared__ __align__(16) uint8_t hsm[];
-  const int KCH = Cin < 128 ? Cin : 128;                   // input channels staged per pass (Cin is a multiple of 16; of 128 beyond 128)
   const int wpitch = Cin + 8;                              // halves per weight row (+16 B: conflict-free fragment loads)
   const int apitch = KCH + 8;                              // halves per staged pixel row
   __half* s_w = reinterpret_cast<__half*>(hsm);            // [8 * NT][wpitch]
@@ -1318,8 +1317,9 @@ __global__ void __launch_bounds__(256) k_head_1x1(const __half* __restrict__ in,
   float* so = s_out + warp * 16 * (8 * NT + 1);
   __half* sa = s_a + (size_t)warp * 16 * apitch;
   const uint32_t sa_ld = smem_u32(sa + (size_t)(lane & 15) * apitch + (lane >> 4) * 8);     // ldmatrix.x4 row address of this lane
-  const int c8n = KCH / 8;                                 // 16-byte pieces per staged row (a power of two: the host checks)
-  const int c8sh = __ffs(c8n) - 1;
+  constexpr int c8n = KCH / 8;                             // 16-byte pieces per staged row
+  constexpr int c8sh = KCH == 128 ? 4 : (KCH == 64 ? 3 : (KCH == 32 ? 2 : 1));
+  constexpr int LI = c8n / 2;                              // 16-byte loads per lane and pass
   const size_t n_tiles = (npix + 15) / 16;
   for (size_t tile = (size_t)blockIdx.x * 8 + warp; tile < n_tiles; tile += (size_t)gridDim.x * 8) {
     float acc[NT][4];
@@ -1328,12 +1328,21 @@ __global__ void __launch_bounds__(256) k_head_1x1(const __half* __restrict__ in,
     const __half* src = in + tile * 16 * in_Ctot + in_coff;
     const int rows = (int)min((size_t)16, npix - tile * 16);
     for (int k0 = 0; k0 < Cin; k0 += KCH) {
-      // 16 pixels x KCH channels, 16 bytes per lane and load: a warp-wide load covers whole 128-byte lines
-      for (int t = lane; t < 16 * c8n; t += 32) {        // no integer division anywhere in the tile loop: the first cut of this
-        const int r = t >> c8sh, c8 = t & (c8n - 1);     // kernel spent 57 % of its issue slots, mostly on them (ncu, profiles/)
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (r < rows) v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)r * in_Ctot + k0 + 8 * c8));
-        *reinterpret_cast<uint4*>(sa + (size_t)r * apitch + 8 * c8) = v;
+      // 16 pixels x KCH channels, 16 bytes per lane and load: a warp-wide load covers whole 128-byte lines.  ALL loads of
+      // the pass are issued before the first shared-memory store (the second cut looped load -> store and had one 512-byte
+      // load in flight per warp: 43 % of its stall samples sat on that store, 1.8 TB/s); no integer division in the tile
+      // loop (that cut also spent 57 % of its issue slots, mostly on t / Cout and t / c8n; ncu, profiles/r02_head_kernel.md)
+      uint4 v[LI];
+#pragma unroll
+      for (int i = 0; i < LI; ++i) {
+        const int t = lane + 32 * i, r = t >> c8sh, c8 = t & (c8n - 1);
+        v[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (r < rows) v[i] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)r * in_Ctot + k0 + 8 * c8));
+      }
+#pragma unroll
+      for (int i = 0; i < LI; ++i) {
+        const int t = lane + 32 * i, r = t >> c8sh, c8 = t & (c8n - 1);
+        *reinterpret_cast<uint4*>(sa + (size_t)r * apitch + 8 * c8) = v[i];
       }
       __syncwarp();
       for (int k = 0; k < KCH; k += 16) {
@@ -2548,19 +2557,24 @@ static int head_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
   const float* bias = op.b_off() >= 0 ? m->weights_dev + op.b_off() : nullptr;
   const int relu = (op.flags() & SB_OPF_RELU) ? 1 : 0;
   const int grid = (int)std::min<size_t>((npix + 127) / 128, (size_t)h->sm_count * 8);
-#define SB_HEAD_CASE(NT)                                                                                                        \
-  case NT: {                                                                                                                    \
+#define SB_HEAD_LAUNCH(NT, KC)                                                                                                  \
+  {                                                                                                                             \
     static bool attr = false;                                                                                                   \
-    if (!attr) { SB_CUDA(h, cudaFuncSetAttribute(k_head_1x1<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; } \
-    k_head_1x1<NT><<<grid, 256, smem, h->stream>>>((const __half*)ib.dev, ib.C, op.in_coff(), op.in_C(), plan->w16, bias, (float*)ob.dev, ob.C, \
-                                                   op.out_coff(), op.out_C(), relu, npix);                                      \
-    break;                                                                                                                      \
+    if (!attr) { SB_CUDA(h, cudaFuncSetAttribute((k_head_1x1<NT, KC>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; } \
+    k_head_1x1<NT, KC><<<grid, 256, smem, h->stream>>>((const __half*)ib.dev, ib.C, op.in_coff(), op.in_C(), plan->w16, bias, (float*)ob.dev, ob.C, \
+                                                       op.out_coff(), op.out_C(), relu, npix);                                  \
   }
+#define SB_HEAD_CASE(NT)                                                                                                        \
+  case NT:                                                                                                                      \
+    if (kch == 16) SB_HEAD_LAUNCH(NT, 16) else if (kch == 32) SB_HEAD_LAUNCH(NT, 32) else if (kch == 64) SB_HEAD_LAUNCH(NT, 64)   \
+    else SB_HEAD_LAUNCH(NT, 128)                                                                                                \
+    break;
   switch (nt) {
     SB_HEAD_CASE(1) SB_HEAD_CASE(2) SB_HEAD_CASE(3) SB_HEAD_CASE(4)
     default: return sb_fail(h, SB_ERR_INVALID, "head kernel: %d output channels", op.out_C());
   }
 #undef SB_HEAD_CASE
+#undef SB_HEAD_LAUNCH
   SB_CHECK_LAUNCH(h);
   return 0;
 }

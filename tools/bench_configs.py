@@ -2,7 +2,7 @@
 JSON line each (frames/s end to end with host frames, CUDA-event timed device loop where available).
 Not the driver's bench (that is bench.py = C4); results are copied into profiles/.
 
-  python tools/bench_configs.py [c1] [c2] [c3] [c5] [--steps K]
+  python tools/bench_configs.py [c1] [c2] [c3] [c5] [--steps K] [--c5-batch B]   (C5 default: 16 frames per GPU and step)
 """
 import json
 import os
@@ -34,12 +34,32 @@ def model_for(spec, in_ch, seed, input_scale=1.0):
 
 
 def timed(fn, steps, warmup=3):
+    """Seconds per call (wall clock, the call returns host results) + nvidia-smi clock samples taken meanwhile."""
+    global LAST_CLOCKS
+    import bench
     for _ in range(warmup):
         fn()
+    sampler = bench.ClockSampler(0)
+    sampler.start()
+    time.sleep(0.25)
     t0 = time.perf_counter()
     for _ in range(steps):
         fn()
-    return (time.perf_counter() - t0) / steps
+    dt = (time.perf_counter() - t0) / steps
+    LAST_CLOCKS = sampler.stop()
+    return dt
+
+
+LAST_CLOCKS = None
+
+
+def roofline(gflop_per_frame, fps):
+    """Tensor roofline of a whole config: algorithmic conv FLOPs per second / measured cuBLAS bf16 burst peak."""
+    import bench
+    peaks, src = bench.peaks_file()
+    tf = gflop_per_frame * fps / 1e3
+    return {"bound": "tensor", "achieved": tf, "peak": float(peaks["bf16_tflops"]), "unit": "TFLOP/s",
+            "frac": tf / float(peaks["bf16_tflops"]), "peak_source": f"{src} bf16_tflops", "note": "end-to-end time incl. H2D / post-processing / D2H"}
 
 
 def unet(filters, max_stride, output_stride):
@@ -55,7 +75,8 @@ def single(name, size, nodes, B, steps):
     fr = frames(B, size, size, 1, 1)
     dt = timed(lambda: pred.inference_model.predict_on_batch(fr), steps)
     return {"config": name, "metric": "frames/s (predict_on_batch, host frames)", "value": B / dt, "ms_per_step": dt * 1e3,
-            "batch": B, "gflop_per_frame": cm.flops_per_pixel * size * size / 1e9, "dtype": "f16"}
+            "batch": B, "gflop_per_frame": cm.flops_per_pixel * size * size / 1e9, "dtype": "f16", "clocks": LAST_CLOCKS,
+            "roofline": roofline(cm.flops_per_pixel * size * size / 1e9, B / dt)}
 
 
 def topdown(steps):
@@ -77,10 +98,12 @@ def topdown(steps):
     dt = timed(lambda: pred.inference_model.predict_on_batch(fr), steps)
     return {"config": "C3 top-down centroid(512^2 after 0.5 scale)+centered-instance(160^2 crops), 1024x1024, max 5 animals, B=16",
             "metric": "frames/s (predict_on_batch, host frames)", "value": B / dt, "ms_per_step": dt * 1e3, "batch": B,
-            "mean_instances_per_frame": float(np.mean(out.get("n_valid", [0]))), "dtype": "f16"}
+            "mean_instances_per_frame": float(np.mean(out.get("n_valid", [0]))), "dtype": "f16", "clocks": LAST_CLOCKS,
+            "gflop_per_frame": ccm.flops_per_pixel * 512 * 512 / 1e9 + 5 * icm.flops_per_pixel * 160 * 160 / 1e9,
+            "roofline": roofline(ccm.flops_per_pixel * 512 * 512 / 1e9 + 5 * icm.flops_per_pixel * 160 * 160 / 1e9, B / dt)}
 
 
-def hourglass(steps):
+def hourglass(steps, B=16):
     nodes = [f"n{i}" for i in range(24)]
     edges = [(f"n{i}", f"n{i + 1}") for i in range(23)]
     spec = dict(backbone="hourglass", backbone_cfg=dict(stem_stride=4, max_stride=64, output_stride=4, stem_filters=128,
@@ -88,7 +111,6 @@ def hourglass(steps):
                 head_type="multi_instance", part_names=nodes, edges=edges,
                 heads=[dict(name="MultiInstanceConfmapsHead", channels=24, output_stride=4),
                        dict(name="PartAffinityFieldsHead", channels=46, output_stride=4)])
-    B = 4
     m, cm, w = model_for(spec, 3, 1005)
     fr = frames(B, 1536, 1536, 3, 5)
     cms, pafs = m.forward(fr[:1])
@@ -98,9 +120,10 @@ def hourglass(steps):
     out = pred.inference_model.predict_on_batch(fr)
     dt = timed(lambda: pred.inference_model.predict_on_batch(fr), steps, warmup=2)
     gf = cm.flops_per_pixel * 1536 * 1536 / 1e9
-    return {"config": "C5 stacked hourglass x3 bottom-up 1536x1536x3, 24 nodes / 23 edges, B=4 per step",
+    return {"config": f"C5 stacked hourglass x3 bottom-up 1536x1536x3, 24 nodes / 23 edges, B={B} per GPU and step",
             "metric": "frames/s (predict_on_batch, host frames)", "value": B / dt, "ms_per_step": dt * 1e3, "batch": B,
-            "gflop_per_frame": gf, "tflops": gf * B / dt / 1e3, "flags": [int(f) for f in out.get("flags", [])], "dtype": "f16"}
+            "gflop_per_frame": gf, "tflops": gf * B / dt / 1e3, "flags": [int(f) for f in out.get("flags", [])], "dtype": "f16",
+            "clocks": LAST_CLOCKS, "roofline": roofline(gf, B / dt)}
 
 
 if __name__ == "__main__":
@@ -114,5 +137,6 @@ if __name__ == "__main__":
         elif c == "c3":
             r = topdown(steps)
         else:
-            r = hourglass(max(3, steps // 3))
+            b5 = int(sys.argv[sys.argv.index("--c5-batch") + 1]) if "--c5-batch" in sys.argv else 16
+            r = hourglass(max(3, steps // 3), b5)
         print(json.dumps(r), flush=True)

@@ -50,6 +50,8 @@ struct Args {
   int row_bytes;  // 128 / 64 / 32: swizzle span = bytes of K per staged row
   int layout;     // UMMA layout type: 2 = SW128, 4 = SW64, 6 = SW32
   int stages;     // distinct operand tiles cycled through
+  int a_off_rows; // start address of the A tile shifted by this many staged rows (the halo kernels' tap offsets)
+  int a_pitch;    // rows between consecutive 8-row groups of A (8 = dense tile; 10 = the 8+2-pixel halo box of the conv kernels)
   unsigned long long* cycles;  // per CTA
 };
 
@@ -64,7 +66,7 @@ __global__ void __launch_bounds__(128) k_probe(Args a) {
   if (CG == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
 
   const int b_rows = a.n / CG;
-  const int a_bytes = 128 * a.row_bytes, b_bytes = b_rows * a.row_bytes;
+  const int a_bytes = ((16 * a.a_pitch + a.a_off_rows + 8) * a.row_bytes + 1023) / 1024 * 1024, b_bytes = b_rows * a.row_bytes;
   // operands: small non-trivial fp16 values (0x2c00 = 0.0625)
   for (int i = threadIdx.x; i < a.stages * (a_bytes + b_bytes) / 2; i += blockDim.x)
     ((uint16_t*)smem)[i] = (uint16_t)(0x2c00 + (i & 7));
@@ -102,7 +104,9 @@ __global__ void __launch_bounds__(128) k_probe(Args a) {
         // descriptors differ only in the start-address field (low word): one add per stage, an immediate per k step,
         // so the loop costs a few instructions per MMA (earlier versions measured their own address arithmetic:
         // 240 and 127 clocks per iteration whatever N)
-        const uint64_t ad0 = make_desc(a0, a.row_bytes, a.layout), bd0 = make_desc(b0, a.row_bytes, a.layout);
+        uint64_t ad0 = make_desc(a0 + (uint32_t)(a.a_off_rows * a.row_bytes), a.row_bytes, a.layout);
+        ad0 = (ad0 & ~((uint64_t)0x3FFF << 32)) | ((uint64_t)(((a.a_pitch * a.row_bytes) >> 4) & 0x3FFF) << 32);   // SBO = pitch rows
+        const uint64_t bd0 = make_desc(b0, a.row_bytes, a.layout);
         const uint32_t a_hi = (uint32_t)(ad0 >> 32), b_hi = (uint32_t)(bd0 >> 32);
         const uint32_t a_lo0 = (uint32_t)ad0, b_lo0 = (uint32_t)bd0;
         const uint32_t a_st = (uint32_t)a_bytes >> 4, b_st = (uint32_t)b_bytes >> 4;
@@ -163,6 +167,7 @@ __global__ void __launch_bounds__(128) k_probe(Args a) {
   }
 }
 
+static int g_a_off_rows = 0, g_a_pitch = 8;
 template <int CG, int KS>
 static double run_ks(int grid, int n, int nmma, float* ms_out) {
   const int row_bytes = 32 * KS;
@@ -170,7 +175,9 @@ static double run_ks(int grid, int n, int nmma, float* ms_out) {
   a.n = n; a.nmma = nmma; a.row_bytes = row_bytes;
   a.layout = row_bytes == 128 ? 2 : row_bytes == 64 ? 4 : 6;
   a.stages = 4;
-  const int smem = a.stages * (128 + n / CG) * row_bytes + 1024;
+  a.a_off_rows = g_a_off_rows; a.a_pitch = g_a_pitch;
+  const int a_tile = ((16 * a.a_pitch + a.a_off_rows + 8) * row_bytes + 1023) / 1024 * 1024;
+  const int smem = a.stages * (a_tile + (n / CG) * row_bytes) + 1024;
   CK(cudaMalloc(&a.cycles, grid * sizeof(unsigned long long)));
   CK(cudaMemset(a.cycles, 0, grid * sizeof(unsigned long long)));
   CK(cudaFuncSetAttribute(k_probe<CG, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -213,6 +220,25 @@ int main() {
   printf("%-10s %5s %5s %9s %6s %12s %10s %10s\n", "cta_group", "M", "N", "row_bytes", "grid", "clk_per_mma", "floor_clk", "TFLOP/s");
   const int nmma = 8192;
   const int grids[2] = {2, p.multiProcessorCount & ~1};
+  // A-operand addressing of the halo conv kernels: start offsets that are not a multiple of the 8-row swizzle atom, and
+  // 8-row groups 10 rows apart (the [8+2]-pixel staged box).  Full chip, 128-byte rows.
+  printf("# A start offset / group pitch (rows of 128 B), grid = %d: clocks per MMA\n", grids[1]);
+  printf("%-10s %5s %8s %8s %12s\n", "cta_group", "N", "off_rows", "pitch", "clk_per_mma");
+  const int offs[5][2] = {{0, 8}, {1, 8}, {0, 10}, {1, 10}, {11, 10}};
+  for (int oi = 0; oi < 5; ++oi) {
+    g_a_off_rows = offs[oi][0]; g_a_pitch = offs[oi][1];
+    for (int n = 32; n <= 256; n <<= 1) {
+      float ms;
+      const double c1 = run<1>(grids[1], n, 128, nmma, &ms);
+      printf("%-10d %5d %8d %8d %12.1f\n", 1, n, g_a_off_rows, g_a_pitch, c1);
+      if (n == 64 || n == 128) {
+        const double c2 = run<2>(grids[1], n, 128, nmma, &ms);
+        printf("%-10d %5d %8d %8d %12.1f\n", 2, n, g_a_off_rows, g_a_pitch, c2);
+      }
+    }
+  }
+  g_a_off_rows = 0; g_a_pitch = 8;
+  if (getenv("MMA_PROBE_OFFSETS_ONLY")) return 0;
   for (int gi = 0; gi < 2; ++gi) {
     for (int rb = 128; rb >= 32; rb >>= 1) {
       for (int n = 32; n <= 256; n <<= 1) {
