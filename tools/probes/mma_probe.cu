@@ -51,6 +51,7 @@ struct Args {
   int layout;     // UMMA layout type: 2 = SW128, 4 = SW64, 6 = SW32
   int stages;     // distinct operand tiles cycled through
   int a_off_rows; // start address of the A tile shifted by this many staged rows (the halo kernels' tap offsets)
+  int random;     // 1: pseudo-random fp16 operands in [-2, 2) (switching activity of real data) instead of near-constant ones
   int a_pitch;    // rows between consecutive 8-row groups of A (8 = dense tile; 10 = the 8+2-pixel halo box of the conv kernels)
   unsigned long long* cycles;  // per CTA
 };
@@ -68,8 +69,12 @@ __global__ void __launch_bounds__(128) k_probe(Args a) {
   const int b_rows = a.n / CG;
   const int a_bytes = ((16 * a.a_pitch + a.a_off_rows + 8) * a.row_bytes + 1023) / 1024 * 1024, b_bytes = b_rows * a.row_bytes;
   // operands: small non-trivial fp16 values (0x2c00 = 0.0625)
-  for (int i = threadIdx.x; i < a.stages * (a_bytes + b_bytes) / 2; i += blockDim.x)
-    ((uint16_t*)smem)[i] = (uint16_t)(0x2c00 + (i & 7));
+  for (int i = threadIdx.x; i < a.stages * (a_bytes + b_bytes) / 2; i += blockDim.x) {
+    uint32_t hsh = (uint32_t)i * 2654435761u + blockIdx.x * 40503u;
+    hsh ^= hsh >> 15; hsh *= 2246822519u; hsh ^= hsh >> 13;
+    // random: sign + exponent 0x38..0x3f (0.5 .. 2) + random mantissa; else small near-constant values (0x2c00 = 0.0625)
+    ((uint16_t*)smem)[i] = a.random ? (uint16_t)((hsh & 0x8000u) | 0x3800u | (hsh & 0x07ffu)) : (uint16_t)(0x2c00 + (i & 7));
+  }
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -167,7 +172,7 @@ __global__ void __launch_bounds__(128) k_probe(Args a) {
   }
 }
 
-static int g_a_off_rows = 0, g_a_pitch = 8;
+static int g_a_off_rows = 0, g_a_pitch = 8, g_random = 0;
 template <int CG, int KS>
 static double run_ks(int grid, int n, int nmma, float* ms_out) {
   const int row_bytes = 32 * KS;
@@ -175,7 +180,7 @@ static double run_ks(int grid, int n, int nmma, float* ms_out) {
   a.n = n; a.nmma = nmma; a.row_bytes = row_bytes;
   a.layout = row_bytes == 128 ? 2 : row_bytes == 64 ? 4 : 6;
   a.stages = 4;
-  a.a_off_rows = g_a_off_rows; a.a_pitch = g_a_pitch;
+  a.a_off_rows = g_a_off_rows; a.a_pitch = g_a_pitch; a.random = g_random;
   const int a_tile = ((16 * a.a_pitch + a.a_off_rows + 8) * row_bytes + 1023) / 1024 * 1024;
   const int smem = a.stages * (a_tile + (n / CG) * row_bytes) + 1024;
   CK(cudaMalloc(&a.cycles, grid * sizeof(unsigned long long)));
@@ -238,6 +243,22 @@ int main() {
     }
   }
   g_a_off_rows = 0; g_a_pitch = 8;
+  // operand data: the tensor pipe's power draw, hence the clock the chip grants it, depends on the switching activity of
+  // the operands.  Same MMA stream (262144 MMAs per CTA, all SMs), near-constant vs pseudo-random fp16 data: clocks per MMA
+  // from clock64 (SM cycles) and TFLOP/s from the CUDA-event time -> effective SM clock = cycles / time.
+  printf("# operand data vs effective clock (grid = %d, 262144 MMAs per CTA)\n", grids[1]);
+  printf("%-10s %5s %8s %12s %10s %12s\n", "cta_group", "N", "data", "clk_per_mma", "TFLOP/s", "eff_clk_GHz");
+  for (int rnd = 0; rnd < 2; ++rnd) {
+    g_random = rnd;
+    for (int n = 64; n <= 256; n <<= 1) {
+      float ms;
+      const int nm = 262144;
+      const double c1 = run<1>(grids[1], n, 128, nm, &ms);
+      const double tf = 2.0 * 128 * n * 16 * (double)nm * grids[1] / (ms * 1e-3) / 1e12;
+      printf("%-10d %5d %8s %12.1f %10.1f %12.3f\n", 1, n, rnd ? "random" : "const", c1, tf, c1 * nm / (ms * 1e-3) / 1e9);
+    }
+  }
+  g_random = 0;
   if (getenv("MMA_PROBE_OFFSETS_ONLY")) return 0;
   for (int gi = 0; gi < 2; ++gi) {
     for (int rb = 128; rb >= 32; rb >>= 1) {
