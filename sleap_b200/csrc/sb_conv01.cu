@@ -53,6 +53,7 @@ constexpr int OFF_PAR = OFF_STG + STG * STG_ROW;        // bias0[16] bias1[16] w
 constexpr int OFF_BAR = OFF_PAR + (176 + 256) * 4;
 constexpr int N_BARS = 1 + 2 * RI + 2 * S0 + 2 * RC + 2 * S1 + 2 * STG;
 constexpr int SMEM_BYTES = OFF_BAR + N_BARS * 8 + 16 + 1024;
+constexpr int SMEM_LAUNCH = SMEM_BYTES > 225 * 1024 ? SMEM_BYTES : 225 * 1024;
 
 struct C01Params {
   const void* frames;
@@ -147,6 +148,11 @@ __global__ void __launch_bounds__(448, 1) k_conv01(const __grid_constant__ CUten
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: this CTA owns the SM (448 threads, ~all of its shared memory), so the next kernel's CTAs
+  // may be scheduled as SMs drain; the pooled output buffer this kernel writes is read by the previous step's second
+  // kernel, so nothing is stored before the previous kernel chain has completed
+  griddep_launch();
+  griddep_wait();
 
   long long wcyc[3] = {0, 0, 0};
   const long long t_start = P.dbg ? clock64() : 0;
@@ -568,8 +574,8 @@ int sb_conv01_prepare(sb_handle_s* h, SbModel* m, int conv0_op, int conv1_op, bo
   P.idesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(k_conv01<unsigned char>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(k_conv01<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(k_conv01<unsigned char>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LAUNCH) != cudaSuccess ||
+        cudaFuncSetAttribute(k_conv01<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LAUNCH) != cudaSuccess)
       return fail("cudaFuncSetAttribute");
     attr = true;
   }
@@ -590,8 +596,16 @@ int sb_conv01_launch(sb_handle_s* h, SbModel* m, const void* frames_dev, int fra
   if (getenv("SB_C01_TIMING") && !dbg_dev) cudaMalloc((void**)&dbg_dev, 14 * 4 * sizeof(long long));
   P.dbg = getenv("SB_C01_TIMING") ? dbg_dev : nullptr;
   const int grid = (int)std::max<long long>(1, std::min<long long>(h->sm_count, P.total_pairs));
-  if (frames_are_u8) k_conv01<unsigned char><<<grid, 448, SMEM_BYTES, h->stream>>>(pl->mapW0, pl->mapW1, P);
-  else k_conv01<float><<<grid, 448, SMEM_BYTES, h->stream>>>(pl->mapW0, pl->mapW1, P);
+  // programmatic dependent launch (sb_tc_prims.cuh): padded to the SM's whole shared memory so that no CTA of the next
+  // kernel can become co-resident (and queue on TMEM) once this kernel has triggered its dependents
+  cudaLaunchConfig_t cfg = {};
+  const bool pdl = !getenv("SB_DISABLE_PDL");
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(448); cfg.dynamicSmemBytes = pdl ? (size_t)SMEM_LAUNCH : (size_t)SMEM_BYTES; cfg.stream = h->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  if (frames_are_u8) cudaLaunchKernelEx(&cfg, k_conv01<unsigned char>, pl->mapW0, pl->mapW1, P);
+  else cudaLaunchKernelEx(&cfg, k_conv01<float>, pl->mapW0, pl->mapW1, P);
   SB_CHECK_LAUNCH(h);
   if (P.dbg) {                                          // profiling aid: where each warp role of CTA 0 waited
     long long hbuf[14 * 4];

@@ -107,6 +107,9 @@ struct TcParams {
   // precision 2 (split-fp16 activations): the C_out logical channels are stored as three fp16 planes [lo | hi | hi],
   // Cout channels apart, from out_coff / pool_coff (sb_kernels_direct.cuh: st_split); 0 for fp32 head outputs
   int split;
+  // programmatic dependent launch: 1 = call griddepcontrol.launch_dependents after the prologue (host: only for launches
+  // padded to the whole SM's shared memory, so that no CTA of the successor can become co-resident and queue on TMEM)
+  int pdl_trigger;
 };
 
 #include "sb_tc_prims.cuh"
@@ -435,8 +438,10 @@ __global__ void __launch_bounds__(128) k_conv_tc(const __grid_constant__ CUtenso
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
+  if (P.pdl_trigger) griddep_launch();
   if (warp == 0 && lane == 0) {
     // ------------------------------ TMA producer ------------------------------
+    griddep_wait();                    // activations come from the previous kernel of the stream
     int sa = 0, sb = 0;
     uint32_t pha = 0, phb = 0;
     for (int ch = 0; ch < P.n_chunks; ++ch) {
@@ -606,6 +611,7 @@ __global__ void __launch_bounds__(192) k_conv_tc_persist(const __grid_constant__
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
+  if (P.pdl_trigger) griddep_launch();
   if (warp == 0 && lane == 0) {
     // ------------------------------ TMA producer ------------------------------
     mbar_expect_tx(smem_u32(wbar), (uint32_t)(n_wslots * P.b_tx_bytes));
@@ -613,6 +619,7 @@ __global__ void __launch_bounds__(192) k_conv_tc_persist(const __grid_constant__
       for (int u = 0; u < P.n_used_taps; ++u)
         tma_load_3d(smem_u32(w_res + (size_t)(ch * P.n_used_taps + u) * P.w_slot_bytes), &mapB, smem_u32(wbar), ch * P.KC, 0,
                     P.used_taps[u]);
+    griddep_wait();                    // the filter bank above does not depend on the previous kernel; the activations do
     int sa = 0;
     uint32_t pha = 0;
     for (int t = blockIdx.x; t < P.n_tiles_total; t += gridDim.x) {
@@ -776,12 +783,14 @@ __global__ void __launch_bounds__(192) k_conv_tc_halo(const __grid_constant__ CU
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
+  if (P.pdl_trigger) griddep_launch();
   if (warp == 0 && lane == 0) {
     mbar_expect_tx(smem_u32(wbar), (uint32_t)(n_wslots * P.b_tx_bytes));
     for (int ch = 0; ch < P.n_chunks; ++ch)
       for (int u = 0; u < P.n_used_taps; ++u)
         tma_load_3d(smem_u32(w_res + (size_t)(ch * P.n_used_taps + u) * P.w_slot_bytes), &mapB, smem_u32(wbar), ch * P.KC, 0,
                     P.used_taps[u]);
+    griddep_wait();
     int sa = 0;
     uint32_t pha = 0;
     TileIter it;
@@ -967,6 +976,7 @@ __global__ void __launch_bounds__(320) k_conv_tc_prog(const __grid_constant__ CU
   constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1u);
   const uint32_t piece_bytes = (uint32_t)(P.b_tx_bytes / CS);
 
+  if (P.pdl_trigger) griddep_launch();
   if (warp == 0 && lane == 0) {
     if (!w_stream) {
       if constexpr (PAIR) {
@@ -985,6 +995,7 @@ __global__ void __launch_bounds__(320) k_conv_tc_prog(const __grid_constant__ CU
                         P.used_taps[u]);
       }
     }
+    griddep_wait();                    // resident filter bank (if any) is already in flight; activations need the previous kernel
     int sa = 0, sw = 0;
     uint32_t pha = 0, phw = 0;
     TileIter it;
@@ -1313,6 +1324,7 @@ __global__ void __launch_bounds__(256) k_head_1x1(const __half* __restrict__ in,
   }
   for (int t = threadIdx.x; t < 8 * NT; t += 256) s_bias[t] = (t < Cout && bias) ? bias[t] : 0.f;
   __syncthreads();
+  griddep_wait();                      // weights / bias above are static; the feature map comes from the previous kernel
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
   float* so = s_out + warp * 16 * (8 * NT + 1);
   __half* sa = s_a + (size_t)warp * 16 * apitch;
@@ -2264,6 +2276,39 @@ int sb_conv_tc_prepare(sb_handle_s* h, SbModel* m) {
   return sb_conv_tc_autotune(h, m);
 }
 
+// Programmatic dependent launch (sb_tc_prims.cuh): every tcgen05 conv launch carries the attribute (its producer thread
+// waits on the grid dependency before the first activation load); a launch that owns its SMs (one CTA per SM) is padded to
+// the SM's whole shared memory and triggers its dependents right after its prologue, so that the next layer's CTAs set up
+// (barriers, TMEM, descriptors, resident filter bank) while this layer's last tiles drain.  SB_DISABLE_PDL=1 switches it off.
+static bool pdl_on() {
+  static int v = -1;
+  if (v < 0) v = getenv("SB_DISABLE_PDL") ? 0 : 1;
+  return v != 0;
+}
+
+template <typename K>
+static void launch_tc(K kern, int grid_x, int grid_y, int grid_z, int threads, size_t smem, cudaStream_t stream, int cluster, bool exclusive,
+                      const CUtensorMap& a, const CUtensorMap& b, TcParams& P) {
+  cudaLaunchConfig_t cfg = {};
+  P.pdl_trigger = (pdl_on() && exclusive) ? 1 : 0;
+  if (P.pdl_trigger) smem = std::max(smem, kMaxDynSmem);       // nothing else fits on the SM: no successor CTA can queue on its TMEM
+  cfg.gridDim = dim3(grid_x, grid_y, grid_z); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (cluster > 1) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = cluster; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_on()) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = at; cfg.numAttrs = na;
+  cudaLaunchKernelEx(&cfg, kern, a, b, P);
+}
+
 static void launch_variant(sb_handle_s* h, TcLaunch& L, int B, int variant, cudaStream_t stream, int skip_out = 0) {
   if (variant >= 2) {
     TcLaunch::Halo& HC = L.halo[variant - 2];
@@ -2272,6 +2317,7 @@ static void launch_variant(sb_handle_s* h, TcLaunch& L, int B, int variant, cuda
     P.n_tiles_total = P.tiles_per_img * B;
     const int grid = std::max(1, std::min(P.n_tiles_total, h->sm_count * HC.occ));
     if (getenv("SB_DEBUG_LAUNCH")) fprintf(stderr, "[halo %dx%d] KC=%d N=%d stages=%d cols=%d occ=%d grid=%d slots=%d smem=%zu tiles=%d thr=%d\n", P.sub_x, P.sub_y, P.KC, P.N, P.n_stages, P.tmem_cols, HC.occ, grid, P.n_a_slots, HC.smem, P.n_tiles_total, HC.threads);
+    const bool excl = HC.occ == 1;
     if (HC.mc) {
       // clusters of 2: the two CTAs of a cluster walk tiles (t, t + 1), (t + g, t + 1 + g), ... and must make the same number
       // of steps -> an even grid over an even tile count (cluster ranks are consecutive block indices)
@@ -2280,38 +2326,32 @@ static void launch_variant(sb_handle_s* h, TcLaunch& L, int B, int variant, cuda
         launch_variant(h, L, B, variant - 1, stream, skip_out);
         return;
       }
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(g2); cfg.blockDim = dim3(HC.threads); cfg.dynamicSmemBytes = HC.smem; cfg.stream = stream;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-      cfg.attrs = at; cfg.numAttrs = 1;
       if (HC.mc == 4) {
         switch (P.KC) {
-          case 16: cudaLaunchKernelEx(&cfg, k_conv_tc_prog<1, 2, 2>, HC.map, HC.mapBpiece, P); break;
-          case 32: cudaLaunchKernelEx(&cfg, k_conv_tc_prog<2, 2, 2>, HC.map, HC.mapBpiece, P); break;
-          default: cudaLaunchKernelEx(&cfg, k_conv_tc_prog<4, 2, 2>, HC.map, HC.mapBpiece, P); break;
+          case 16: launch_tc(k_conv_tc_prog<1, 2, 2>, g2, 1, 1, HC.threads, HC.smem, stream, 2, true, HC.map, HC.mapBpiece, P); break;
+          case 32: launch_tc(k_conv_tc_prog<2, 2, 2>, g2, 1, 1, HC.threads, HC.smem, stream, 2, true, HC.map, HC.mapBpiece, P); break;
+          default: launch_tc(k_conv_tc_prog<4, 2, 2>, g2, 1, 1, HC.threads, HC.smem, stream, 2, true, HC.map, HC.mapBpiece, P); break;
         }
         return;
       }
       switch (P.KC) {
-        case 16: cudaLaunchKernelEx(&cfg, k_conv_tc_prog<1, 2>, HC.map, HC.mapBpiece, P); break;
-        case 32: cudaLaunchKernelEx(&cfg, k_conv_tc_prog<2, 2>, HC.map, HC.mapBpiece, P); break;
-        default: cudaLaunchKernelEx(&cfg, k_conv_tc_prog<4, 2>, HC.map, HC.mapBpiece, P); break;
+        case 16: launch_tc(k_conv_tc_prog<1, 2>, g2, 1, 1, HC.threads, HC.smem, stream, 2, true, HC.map, HC.mapBpiece, P); break;
+        case 32: launch_tc(k_conv_tc_prog<2, 2>, g2, 1, 1, HC.threads, HC.smem, stream, 2, true, HC.map, HC.mapBpiece, P); break;
+        default: launch_tc(k_conv_tc_prog<4, 2>, g2, 1, 1, HC.threads, HC.smem, stream, 2, true, HC.map, HC.mapBpiece, P); break;
       }
       return;
     }
     if (HC.prog) {
       switch (P.KC) {
-        case 16: k_conv_tc_prog<1><<<grid, HC.threads, HC.smem, stream>>>(HC.map, L.mapB, P); break;
-        case 32: k_conv_tc_prog<2><<<grid, HC.threads, HC.smem, stream>>>(HC.map, L.mapB, P); break;
-        default: k_conv_tc_prog<4><<<grid, HC.threads, HC.smem, stream>>>(HC.map, L.mapB, P); break;
+        case 16: launch_tc(k_conv_tc_prog<1>, grid, 1, 1, HC.threads, HC.smem, stream, 1, excl, HC.map, L.mapB, P); break;
+        case 32: launch_tc(k_conv_tc_prog<2>, grid, 1, 1, HC.threads, HC.smem, stream, 1, excl, HC.map, L.mapB, P); break;
+        default: launch_tc(k_conv_tc_prog<4>, grid, 1, 1, HC.threads, HC.smem, stream, 1, excl, HC.map, L.mapB, P); break;
       }
     } else {
       switch (P.KC) {
-        case 16: k_conv_tc_halo<1><<<grid, HC.threads, HC.smem, stream>>>(HC.map, L.mapB, P); break;
-        case 32: k_conv_tc_halo<2><<<grid, HC.threads, HC.smem, stream>>>(HC.map, L.mapB, P); break;
-        default: k_conv_tc_halo<4><<<grid, HC.threads, HC.smem, stream>>>(HC.map, L.mapB, P); break;
+        case 16: launch_tc(k_conv_tc_halo<1>, grid, 1, 1, HC.threads, HC.smem, stream, 1, excl, HC.map, L.mapB, P); break;
+        case 32: launch_tc(k_conv_tc_halo<2>, grid, 1, 1, HC.threads, HC.smem, stream, 1, excl, HC.map, L.mapB, P); break;
+        default: launch_tc(k_conv_tc_halo<4>, grid, 1, 1, HC.threads, HC.smem, stream, 1, excl, HC.map, L.mapB, P); break;
       }
     }
   } else if (variant == 1) {
@@ -2320,10 +2360,11 @@ static void launch_variant(sb_handle_s* h, TcLaunch& L, int B, int variant, cuda
     P.n_tiles_total = P.tiles_per_img * B;
     const int grid = std::max(1, std::min(P.n_tiles_total, h->sm_count * L.occ));
     if (getenv("SB_DEBUG_LAUNCH")) fprintf(stderr, "[persist] KC=%d N=%d stages=%d cols=%d occ=%d grid=%d slots=%d smem=%zu tiles=%d\n", P.KC, P.N, P.n_stages, P.tmem_cols, L.occ, grid, P.n_a_slots, L.smem_p, P.n_tiles_total);
+    const bool excl = L.occ == 1;
     switch (P.KC) {
-      case 16: k_conv_tc_persist<1><<<grid, 192, L.smem_p, stream>>>(L.mapA, L.mapB, P); break;
-      case 32: k_conv_tc_persist<2><<<grid, 192, L.smem_p, stream>>>(L.mapA, L.mapB, P); break;
-      default: k_conv_tc_persist<4><<<grid, 192, L.smem_p, stream>>>(L.mapA, L.mapB, P); break;
+      case 16: launch_tc(k_conv_tc_persist<1>, grid, 1, 1, 192, L.smem_p, stream, 1, excl, L.mapA, L.mapB, P); break;
+      case 32: launch_tc(k_conv_tc_persist<2>, grid, 1, 1, 192, L.smem_p, stream, 1, excl, L.mapA, L.mapB, P); break;
+      default: launch_tc(k_conv_tc_persist<4>, grid, 1, 1, 192, L.smem_p, stream, 1, excl, L.mapA, L.mapB, P); break;
     }
   } else {
     dim3 g = L.grid;
@@ -2331,18 +2372,19 @@ static void launch_variant(sb_handle_s* h, TcLaunch& L, int B, int variant, cuda
     L.P.skip_out = skip_out;
     bool wide = L.P.n_groups > 3;                      // 5x5 / 7x7 (and the 4x4 space-to-depth stem): loops unrolled to 7
     for (int gi = 0; gi < L.P.n_groups; ++gi) wide |= L.P.groups[gi].n_taps > 3;
+    const bool excl = L.smem >= 114 * 1024;            // already one CTA per SM
     if (wide) {
       switch (L.P.KC) {
-        case 16: k_conv_tc<1, 7><<<g, 128, L.smem, stream>>>(L.mapA, L.mapB, L.P); break;
-        case 32: k_conv_tc<2, 7><<<g, 128, L.smem, stream>>>(L.mapA, L.mapB, L.P); break;
-        default: k_conv_tc<4, 7><<<g, 128, L.smem, stream>>>(L.mapA, L.mapB, L.P); break;
+        case 16: launch_tc((k_conv_tc<1, 7>), g.x, g.y, g.z, 128, L.smem, stream, 1, excl, L.mapA, L.mapB, L.P); break;
+        case 32: launch_tc((k_conv_tc<2, 7>), g.x, g.y, g.z, 128, L.smem, stream, 1, excl, L.mapA, L.mapB, L.P); break;
+        default: launch_tc((k_conv_tc<4, 7>), g.x, g.y, g.z, 128, L.smem, stream, 1, excl, L.mapA, L.mapB, L.P); break;
       }
       return;
     }
     switch (L.P.KC) {
-      case 16: k_conv_tc<1><<<g, 128, L.smem, stream>>>(L.mapA, L.mapB, L.P); break;
-      case 32: k_conv_tc<2><<<g, 128, L.smem, stream>>>(L.mapA, L.mapB, L.P); break;
-      default: k_conv_tc<4><<<g, 128, L.smem, stream>>>(L.mapA, L.mapB, L.P); break;
+      case 16: launch_tc(k_conv_tc<1>, g.x, g.y, g.z, 128, L.smem, stream, 1, excl, L.mapA, L.mapB, L.P); break;
+      case 32: launch_tc(k_conv_tc<2>, g.x, g.y, g.z, 128, L.smem, stream, 1, excl, L.mapA, L.mapB, L.P); break;
+      default: launch_tc(k_conv_tc<4>, g.x, g.y, g.z, 128, L.smem, stream, 1, excl, L.mapA, L.mapB, L.P); break;
     }
   }
 }
@@ -2561,8 +2603,13 @@ static int head_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
   {                                                                                                                             \
     static bool attr = false;                                                                                                   \
     if (!attr) { SB_CUDA(h, cudaFuncSetAttribute((k_head_1x1<NT, KC>), cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; } \
-    k_head_1x1<NT, KC><<<grid, 256, smem, h->stream>>>((const __half*)ib.dev, ib.C, op.in_coff(), op.in_C(), plan->w16, bias, (float*)ob.dev, ob.C, \
-                                                       op.out_coff(), op.out_C(), relu, npix);                                  \
+    cudaLaunchConfig_t cfg = {};                                                                                                \
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;                    \
+    cudaLaunchAttribute at[1];                                                                                                  \
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;        \
+    cfg.attrs = at; cfg.numAttrs = pdl_on() ? 1 : 0;                                                                            \
+    cudaLaunchKernelEx(&cfg, k_head_1x1<NT, KC>, (const __half*)ib.dev, ib.C, op.in_coff(), op.in_C(), (const __half*)plan->w16, bias,        \
+                       (float*)ob.dev, ob.C, op.out_coff(), op.out_C(), relu, npix);                                            \
   }
 #define SB_HEAD_CASE(NT)                                                                                                        \
   case NT:                                                                                                                      \

@@ -94,3 +94,11 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 
 
+
+// Programmatic dependent launch (PDL).  A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// become resident while its predecessor in the stream is still running: everything that does not read the predecessor's
+// output (barrier init, TMEM allocation, descriptor prefetch, the resident filter bank) runs ahead, griddep_wait() then
+// blocks until the predecessor has completed and its memory is visible (a no-op for a normally launched kernel).
+// griddep_launch() lets the successor's CTAs be scheduled as soon as every CTA of this grid has called it or exited.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
