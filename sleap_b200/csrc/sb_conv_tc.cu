@@ -2642,7 +2642,10 @@ static int launch_plan(sb_handle_s* h, SbConvTcPlan* plan, int B, bool fused) {
     return 0;
   }
   const size_t n = plan->launches.size();
-  if (n == 1 || getenv("SB_DISABLE_FORK")) {
+  // with programmatic dependent launch the phases run back to back on the launching stream: each phase's CTAs start as
+  // the previous phase's SMs drain, which fills the GPU like the fork did, without 3 event records + 6 stream waits per
+  // transposed conv on the host's launch path (same device time, +3 % end to end; SB_FORCE_FORK=1 restores the fork)
+  if (n == 1 || getenv("SB_DISABLE_FORK") || (pdl_on() && !getenv("SB_FORCE_FORK"))) {
     for (TcLaunch& L : plan->launches) {
       launch_variant(h, L, B, L.use_persist, h->stream, plan->skip_now ? 1 : 0);
       SB_CHECK_LAUNCH(h);
