@@ -702,7 +702,8 @@ def run_ours(args):
                        "gflop_per_frame": GFLOP_PER_FRAME,
                        "l2": "3 rotating input batches; per-step activation working set ~2.9 GB >> 126 MB L2",
                        "accumulate": "fp32", "head_outputs": "fp32", "mean_instances_per_frame": n_inst_mean, "exchange": exchange,
-                       "heads_calibrated_to_peaks_per_channel": TARGET_PEAKS_PER_CHANNEL},
+                       "heads_calibrated_to_peaks_per_channel": TARGET_PEAKS_PER_CHANNEL,
+                       "programmatic_dependent_launch": not bool(os.environ.get("SB_DISABLE_PDL"))},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * H * W, "d2h_bytes_per_step": d2h,
                     "api": "BottomUpPredictor.predict(pinned uint8 frame stack, make_labels=False), double-buffered batches",

@@ -97,6 +97,27 @@ def test_c4_fp16_parity_on_bench_frames():
     assert r["max_offset_err_px"] <= 0.25
 
 
+def test_c4_split_precision_parity_on_bench_frames():
+    """Precision 2 (split fp16 pairs on the tcgen05 kernels) on the bench's own 8 frames at full size: north_star's
+    tolerance -- confidence maps / PAFs within 1e-4 of the map maximum against the fp32 CUDA path and the fp32 CPU oracle
+    (measured 2.4e-5 / 2.6e-5), sub-pixel offsets within 1e-3 px (6e-5), every instance with identical node assignments."""
+    from sleap_b200 import _lib
+    from sleap_b200.nn.inference import BottomUpPredictor
+    from sleap_b200.nn.model import DeviceModel
+    bench, spec, weights, _, _ = _c4()
+    m2 = DeviceModel(spec, weights, input_channels=1, precision=2)
+    p2 = BottomUpPredictor(m2, bench.NODES, bench.EDGES, peak_threshold=0.2, batch_size=8, max_peaks_per_sample=1024,
+                           max_node_peaks=32, max_instances_per_frame=32)
+    frames = bench.make_frames(8, 0)
+    r = bench.c4_parity(spec, weights, _lib.default_handle(), frames, p2, m2, n_oracle=1, tag="split")
+    print(r)
+    assert r["max_rel_cm"] <= 1e-4 and r["max_rel_paf"] <= 1e-4
+    assert r["oracle"]["split_path_max_rel_cm"] <= 1e-4 and r["oracle"]["split_path_max_rel_paf"] <= 1e-4
+    assert r["peak_index_match"] >= 0.99
+    assert r["instance_assignment_match"] == 1.0 and r["frames_identical_grouping"] == 1.0
+    assert r["max_offset_err_px"] <= 1e-3 and r["max_instance_score_err"] <= 1e-3
+
+
 def test_c4_analytic_maps_bit_exact():
     """Network-bypassing entry at C4 map size, B=8, 5 instances per frame: indices / candidate lists / assignments bit-exact,
     coordinates and scores <= 1e-4 (north_star's bar)."""

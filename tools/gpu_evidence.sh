@@ -1,7 +1,8 @@
 #!/bin/bash
 # One gpurun call that produces every artefact profiles/ is built from:
 #   bench line (+ autotune picks, parity, sustained), reference arm, ncu launch list with DRAM bytes of exactly K warm steps,
-#   ncu --set full of one warm step, source-level capture of the top kernels, secondary configs, compute-sanitizer, gpu tests.
+#   ncu --set full of one warm step, source-level capture of the top kernels, secondary configs, gpu tests.
+#   (compute-sanitizer: tools/gpu_sanitize.sh, a separate gpurun call)
 # usage (from the repo root on the GPU box): bash tools/gpu_evidence.sh [skip_tests]
 set -u
 O=gpurun_out
@@ -9,6 +10,8 @@ PFX=${PFX:-r02}          # round prefix of the ncu artefacts (profiles/${PFX}_*)
 mkdir -p $O
 export PYTHONUNBUFFERED=1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/smi.txt 2>&1
+echo "== smoke"; date +%s
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/${PFX}_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 $O/${PFX}_smoke.log
 echo "== bench"; date +%s
 SB_DEBUG=1 BENCH_VERBOSE=1 SB_TUNE_SAVE=$O/tune.txt timeout 600 python bench.py --steps 20 --warmup 5 > $O/${PFX}_bench_1gpu.json 2> $O/${PFX}_bench_1gpu.err
 echo "bench rc=$?"; tail -c 400 $O/${PFX}_bench_1gpu.json; echo
@@ -39,10 +42,6 @@ if [ "$sz" -gt 30000000 ]; then echo "ncu-rep too big ($sz), keeping CSV only"; 
 echo "== other configs"; date +%s
 timeout 400 python tools/bench_configs.py > $O/${PFX}_other_configs.jsonl 2> $O/configs.err
 echo "configs rc=$?"; cat $O/${PFX}_other_configs.jsonl
-echo "== compute-sanitizer"; date +%s
-timeout 600 compute-sanitizer --tool memcheck --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > $O/${PFX}_sanitizer_memcheck_smoke.log 2>&1; echo "memcheck smoke rc=$?"; tail -3 $O/${PFX}_sanitizer_memcheck_smoke.log
-timeout 900 compute-sanitizer --target-processes all --tool memcheck --print-limit 20 python tools/sanitize_step.py > $O/${PFX}_sanitizer_memcheck_c4_variants.log 2>&1; echo "memcheck variants rc=$?"; tail -4 $O/${PFX}_sanitizer_memcheck_c4_variants.log
-timeout 900 compute-sanitizer --target-processes all --tool racecheck --print-limit 20 python tools/sanitize_step.py quick > $O/${PFX}_sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -4 $O/${PFX}_sanitizer_racecheck.log
 if [ "${1:-}" != "skip_tests" ]; then
   echo "== pytest gpu"; date +%s
   timeout 900 python -m pytest tests -m gpu -q > $O/${PFX}_pytest_gpu.log 2>&1
