@@ -2563,7 +2563,9 @@ int sb_conv_tc_autotune(sb_handle_s* h, SbModel* m) {
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  if (const char* sf = getenv("SB_TUNE_SAVE")) {
+  // (a process may configure several models -- bench.py builds the fp16 model, then the precision-2 model for its strict
+  //  block: only the fp16 tensor-core model's picks are recorded, they are what SB_TUNE_LOAD replays under ncu)
+  if (const char* sf = m->precision == 0 ? getenv("SB_TUNE_SAVE") : nullptr) {
     if (FILE* f = fopen(sf, "w")) {
       for (size_t oi = 0; oi < m->tc_plans.size(); ++oi) {
         SbConvTcPlan* plan = m->tc_plans[oi];
