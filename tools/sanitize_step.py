@@ -30,7 +30,8 @@ print("variant", os.environ.get("SB_FORCE_VARIANT"), "conv01", os.environ.get("S
 
 if __name__ == "__main__":
     quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
-    combos = ([("0", "1", "0"), ("2", "0", "0"), ("3", "0", "2")] if quick else
+    new = len(sys.argv) > 1 and sys.argv[1] == "new"      # what changed since the last committed sanitizer logs
+    combos = [("3", "0", "0"), ("7", "0", "0"), ("9", "1", "0"), (None, "1", "0"), (None, "0", "2"), ("3", "0", "2")] if new else ([("0", "1", "0"), ("2", "0", "0"), ("3", "0", "2")] if quick else
               [(str(v), "1" if v % 2 == 0 else "0", "0") for v in range(10)] + [(None, "1", "0"), (None, "0", "2"), ("3", "0", "2"), ("7", "0", "2")])
     for v, c, prec in combos:
         env = dict(os.environ, SB_FORCE_CONV01=c, SB_SAN_PRECISION=prec)
