@@ -1310,13 +1310,13 @@ template <int NT, int KCH>   // n-tiles of 8 output channels (C_out <= 8 * NT); 
 __global__ void __launch_bounds__(256) k_head_1x1(const __half* __restrict__ in, int in_Ctot, int in_coff, int Cin,
                                                   const __half* __restrict__ w /*[Cout_pad][Cin]*/, const float* __restrict__ bias,
                                                   float* __restrict__ out, int out_Ctot, int out_coff, int Cout, int relu,
-                                                  size_t npix) {
+                                                  size_t npix, int n_ring) {
   extern __shared__ __align__(16) uint8_t hsm[];
   const int wpitch = Cin + 8;                              // halves per weight row (+16 B: conflict-free fragment loads)
-  const int apitch = KCH + 8;                              // halves per staged pixel row
+  constexpr int apitch = KCH + 8;                          // halves per staged pixel row
   __half* s_w = reinterpret_cast<__half*>(hsm);            // [8 * NT][wpitch]
-  __half* s_a = s_w + (size_t)8 * NT * wpitch;             // [8 warps][16][apitch]
-  float* s_out = reinterpret_cast<float*>(s_a + (size_t)8 * 16 * apitch);     // [8 warps][16][8 * NT + 1]
+  __half* s_a = s_w + (size_t)8 * NT * wpitch;             // [8 warps][n_ring][16][apitch]
+  float* s_out = reinterpret_cast<float*>(s_a + (size_t)8 * n_ring * 16 * apitch);     // [8 warps][16][8 * NT + 1]
   float* s_bias = s_out + 8 * 16 * (8 * NT + 1);
   for (int t = threadIdx.x; t < 8 * NT * (Cin / 8); t += 256) {
     const int r = t / (Cin / 8), c8 = t % (Cin / 8);
@@ -1327,51 +1327,86 @@ __global__ void __launch_bounds__(256) k_head_1x1(const __half* __restrict__ in,
   griddep_wait();                      // weights / bias above are static; the feature map comes from the previous kernel
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
   float* so = s_out + warp * 16 * (8 * NT + 1);
-  __half* sa = s_a + (size_t)warp * 16 * apitch;
-  const uint32_t sa_ld = smem_u32(sa + (size_t)(lane & 15) * apitch + (lane >> 4) * 8);     // ldmatrix.x4 row address of this lane
+  __half* ring = s_a + (size_t)warp * n_ring * 16 * apitch;
   constexpr int c8n = KCH / 8;                             // 16-byte pieces per staged row
   constexpr int c8sh = KCH == 128 ? 4 : (KCH == 64 ? 3 : (KCH == 32 ? 2 : 1));
-  constexpr int LI = c8n / 2;                              // 16-byte loads per lane and pass
+  constexpr int LI = c8n / 2;                              // 16-byte copies per lane and item
   const size_t n_tiles = (npix + 15) / 16;
-  for (size_t tile = (size_t)blockIdx.x * 8 + warp; tile < n_tiles; tile += (size_t)gridDim.x * 8) {
-    float acc[NT][4];
-#pragma unroll
-    for (int n = 0; n < NT; ++n) { acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f; }
-    const __half* src = in + tile * 16 * in_Ctot + in_coff;
-    const int rows = (int)min((size_t)16, npix - tile * 16);
-    for (int k0 = 0; k0 < Cin; k0 += KCH) {
-      // 16 pixels x KCH channels, 16 bytes per lane and load: a warp-wide load covers whole 128-byte lines.  ALL loads of
-      // the pass are issued before the first shared-memory store (the second cut looped load -> store and had one 512-byte
-      // load in flight per warp: 43 % of its stall samples sat on that store, 1.8 TB/s); no integer division in the tile
-      // loop (that cut also spent 57 % of its issue slots, mostly on t / Cout and t / c8n; ncu, profiles/r02_head_kernel.md)
-      uint4 v[LI];
-#pragma unroll
-      for (int i = 0; i < LI; ++i) {
-        const int t = lane + 32 * i, r = t >> c8sh, c8 = t & (c8n - 1);
-        v[i] = make_uint4(0u, 0u, 0u, 0u);
-        if (r < rows) v[i] = __ldg(reinterpret_cast<const uint4*>(src + (size_t)r * in_Ctot + k0 + 8 * c8));
-      }
+  const int n_pass = Cin / KCH;
+  // This warp's work items, in order: (tile, pass) with tile = first + j * stride.  Each item is 16 pixels x KCH channels
+  // copied global -> shared with cp.async (16 bytes per lane and copy: a warp-wide copy covers whole 128-byte lines), one
+  // commit group per item, n_ring - 1 items in flight while one is consumed: the copies never pass through registers, so
+  // the bytes in flight per SM are bounded by shared memory, not by the register file (the previous cut staged through
+  // registers: 2 KB per warp in flight, 2.2 TB/s at ~3 us of loaded DRAM latency).
+  const size_t first = (size_t)blockIdx.x * 8 + warp, stride = (size_t)gridDim.x * 8;
+  const size_t my_tiles = first < n_tiles ? (n_tiles - 1 - first) / stride + 1 : 0;
+  const size_t n_items = my_tiles * (size_t)n_pass;
+  auto issue = [&](size_t item) {
+    if (item < n_items) {
+      const size_t tile = first + (item / n_pass) * stride;
+      const int k0 = (int)(item % n_pass) * KCH;
+      const int rows = (int)min((size_t)16, npix - tile * 16);
+      const __half* src = in + tile * 16 * in_Ctot + in_coff + k0;
+      const uint32_t dst0 = smem_u32(ring + (size_t)(item % n_ring) * 16 * apitch);
 #pragma unroll
       for (int i = 0; i < LI; ++i) {
         const int t = lane + 32 * i, r = t >> c8sh, c8 = t & (c8n - 1);
-        *reinterpret_cast<uint4*>(sa + (size_t)r * apitch + 8 * c8) = v[i];
+        const int rs = r < rows ? r : rows - 1;              // rows past the last pixel re-read it (never stored)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + (uint32_t)(r * apitch + 8 * c8) * 2u),
+                     "l"(src + (size_t)rs * in_Ctot + 8 * c8) : "memory");
       }
-      __syncwarp();
-      for (int k = 0; k < KCH; k += 16) {
-        uint32_t ra0, ra1, ra2, ra3;
-        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(ra0), "=r"(ra1), "=r"(ra2), "=r"(ra3) : "r"(sa_ld + 2u * (uint32_t)k));
-#pragma unroll
-        for (int n = 0; n < NT; ++n) {
-          const __half* wb = s_w + (size_t)(8 * n + g) * wpitch + k0 + k + 2 * tq;
-          const uint32_t rb0 = *reinterpret_cast<const uint32_t*>(wb), rb1 = *reinterpret_cast<const uint32_t*>(wb + 8);
-          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-                       : "+f"(acc[n][0]), "+f"(acc[n][1]), "+f"(acc[n][2]), "+f"(acc[n][3])
-                       : "r"(ra0), "r"(ra1), "r"(ra2), "r"(ra3), "r"(rb0), "r"(rb1));
-        }
-      }
-      __syncwarp();
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");     // one group per slot of the schedule, empty past the end
+  };
+  for (int j = 0; j < n_ring - 1; ++j) issue((size_t)j);
+  float acc[NT][4];
+  // a head that owns its buffer (out_Ctot == Cout) stores a tile as ONE run of 16 * Cout floats: lane l writes elements
+  // l, l + 32, ... of the run; their (row, channel) positions in the staging tile are the same for every tile
+  constexpr int NST = (16 * 8 * NT + 31) / 32;
+  int st_off[NST];
+#pragma unroll
+  for (int k = 0; k < NST; ++k) {
+    const int e = lane + 32 * k;
+    st_off[k] = (e / Cout) * (8 * NT + 1) + e % Cout;
+  }
+  const bool linear = out_Ctot == Cout;
+  for (size_t item = 0; item < n_items; ++item) {
+    issue(item + (size_t)(n_ring - 1));
+    // groups complete in order: all but the newest n_ring - 1 are done -> item `item` has landed
+    switch (n_ring) {
+      case 2: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+      case 3: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+      case 4: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+      case 5: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+      case 6: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+      case 7: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+      default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
+    }
+    __syncwarp();
+    const int pass = (int)(item % n_pass), k0 = pass * KCH;
+    const size_t tile = first + (item / n_pass) * stride;
+    if (pass == 0) {
+#pragma unroll
+      for (int n = 0; n < NT; ++n) { acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f; }
+    }
+    const uint32_t sa_ld = smem_u32(ring + (size_t)(item % n_ring) * 16 * apitch + (size_t)(lane & 15) * apitch + (lane >> 4) * 8);
+#pragma unroll
+    for (int k = 0; k < KCH; k += 16) {
+      uint32_t ra0, ra1, ra2, ra3;
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(ra0), "=r"(ra1), "=r"(ra2), "=r"(ra3) : "r"(sa_ld + 2u * (uint32_t)k));
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+        const __half* wb = s_w + (size_t)(8 * n + g) * wpitch + k0 + k + 2 * tq;
+        const uint32_t rb0 = *reinterpret_cast<const uint32_t*>(wb), rb1 = *reinterpret_cast<const uint32_t*>(wb + 8);
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                     : "+f"(acc[n][0]), "+f"(acc[n][1]), "+f"(acc[n][2]), "+f"(acc[n][3])
+                     : "r"(ra0), "r"(ra1), "r"(ra2), "r"(ra3), "r"(rb0), "r"(rb1));
+      }
+    }
+    __syncwarp();                                          // the slot may be refilled by the next issue()
+    if (pass != n_pass - 1) continue;
+    const int rows = (int)min((size_t)16, npix - tile * 16);
 #pragma unroll
     for (int n = 0; n < NT; ++n) {
       const int c = 8 * n + 2 * tq;
@@ -1382,7 +1417,12 @@ __global__ void __launch_bounds__(256) k_head_1x1(const __half* __restrict__ in,
     }
     __syncwarp();
     float* ob = out + tile * 16 * out_Ctot + out_coff;
-    if (NT <= 2) {                                        // two pixel rows per warp store: lanes 0-15 / 16-31 hold the channels of a row
+    if (linear) {                                         // whole 128-byte lines per warp store
+      const int n_el = rows * Cout;
+#pragma unroll
+      for (int k = 0; k < NST; ++k)
+        if (lane + 32 * k < n_el) ob[lane + 32 * k] = so[st_off[k]];
+    } else if (NT <= 2) {                                 // two pixel rows per warp store: lanes 0-15 / 16-31 hold the channels of a row
       const int rr = lane >> 4, cc = lane & 15;
       if (cc < Cout) {
 #pragma unroll
@@ -1396,6 +1436,7 @@ __global__ void __launch_bounds__(256) k_head_1x1(const __half* __restrict__ in,
     }
     __syncwarp();
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 struct TcLaunch {
@@ -2597,10 +2638,17 @@ static int head_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
   const int nt = (op.out_C() + 7) / 8;
   const size_t npix = (size_t)B * ob.H * ob.W;
   const int kch = std::min(op.in_C(), 128);
-  const size_t smem = (size_t)8 * nt * (op.in_C() + 8) * 2 + (size_t)8 * 16 * (kch + 8) * 2 + (size_t)8 * 16 * (8 * nt + 1) * 4 + (size_t)8 * nt * 4;
+  // per-warp ring of n_ring staged items (16 pixels x kch channels each): as deep as shared memory allows with two blocks per SM,
+  // else one block per SM (128-channel passes)
+  const size_t fixed = (size_t)8 * nt * (op.in_C() + 8) * 2 + (size_t)8 * 16 * (8 * nt + 1) * 4 + (size_t)8 * nt * 4;
+  const size_t stage = (size_t)8 * 16 * (kch + 8) * 2;
+  int n_ring = (int)std::min<size_t>(8, (110 * 1024 - fixed) / stage);
+  if (n_ring < 4) n_ring = (int)std::min<size_t>(8, (200 * 1024 - fixed) / stage);
+  n_ring = std::max(2, n_ring);
+  const size_t smem = fixed + (size_t)n_ring * stage;
   const float* bias = op.b_off() >= 0 ? m->weights_dev + op.b_off() : nullptr;
   const int relu = (op.flags() & SB_OPF_RELU) ? 1 : 0;
-  const int grid = (int)std::min<size_t>((npix + 127) / 128, (size_t)h->sm_count * 8);
+  const int grid = (int)std::min<size_t>((npix + 127) / 128, (size_t)h->sm_count * 2);
 #define SB_HEAD_LAUNCH(NT, KC)                                                                                                  \
   {                                                                                                                             \
     static bool attr = false;                                                                                                   \
@@ -2611,7 +2659,7 @@ static int head_launch(sb_handle_s* h, SbModel* m, const SbOp& op, SbConvTcPlan*
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;        \
     cfg.attrs = at; cfg.numAttrs = pdl_on() ? 1 : 0;                                                                            \
     cudaLaunchKernelEx(&cfg, k_head_1x1<NT, KC>, (const __half*)ib.dev, ib.C, op.in_coff(), op.in_C(), (const __half*)plan->w16, bias,        \
-                       (float*)ob.dev, ob.C, op.out_coff(), op.out_C(), relu, npix);                                            \
+                       (float*)ob.dev, ob.C, op.out_coff(), op.out_C(), relu, npix, n_ring);                                    \
   }
 #define SB_HEAD_CASE(NT)                                                                                                        \
   case NT:                                                                                                                      \

@@ -24,4 +24,4 @@ SB_TUNE_LOAD=$O/tune.txt timeout 400 ncu --set full --clock-control none --impor
 echo "top rc=$?"
 timeout 120 ncu -i $O/${PFX}_top_kernel.ncu-rep --page details > $O/${PFX}_top_kernel_details.txt 2>/dev/null
 rm -f $O/${PFX}_step_full.ncu-rep
-timeout 600 python -m pytest tests/test_gpu_zz_full_size.py -m gpu -q > $O/pytest_full.log 2>&1; echo "pytest rc=$?"; tail -2 $O/pytest_full.log
+timeout 600 python -m pytest tests/test_gpu_zz_full_size.py tests/test_gpu_model.py tests/test_gpu_split_precision.py -m gpu -q -k "full or c4 or forward or bottomup or split" > $O/pytest_full.log 2>&1; echo "pytest rc=$?"; tail -2 $O/pytest_full.log
