@@ -256,13 +256,29 @@ def spec_from_config(model_cfg: dict, skeleton_nodes=None, skeleton_edges=None):
         heads.append(dict(name="PartAffinityFieldsHead", channels=2 * len(edges), output_stride=paf["output_stride"]))
         if cm.get("offset_refinement"):
             heads.append(dict(name="OffsetRefinementHead", channels=2 * len(part_names), output_stride=cm["output_stride"]))
+    elif htype == "multi_class_bottomup":                                   # model.py:219-256
+        cm, cls_cfg = hcfg["confmaps"], hcfg["class_maps"]
+        part_names = cm.get("part_names") or skeleton_nodes
+        classes = cls_cfg.get("classes")
+        if part_names is None:
+            raise ValueError("Skeleton must be provided when the head configuration is incomplete.")
+        if classes is None:
+            raise ValueError("Classes must be provided when the head configuration is incomplete.")
+        heads.append(dict(name="MultiInstanceConfmapsHead", channels=len(part_names), output_stride=cm["output_stride"]))
+        # ClassMapsHead: 1x1 conv + sigmoid (heads.py:336-338); the sigmoid is applied by the inference layer
+        heads.append(dict(name="ClassMapsHead", channels=len(classes), output_stride=cls_cfg["output_stride"], activation="sigmoid"))
+        if cm.get("offset_refinement"):
+            heads.append(dict(name="OffsetRefinementHead", channels=2 * len(part_names), output_stride=cm["output_stride"]))
     else:
         raise ValueError(f"Head type '{htype}' is outside the scope of this build.")
     bcfg = dict(bcfg)
     bcfg["output_stride"] = heads[0]["output_stride"]     # model.py:301
-    return dict(backbone=bname, backbone_cfg=bcfg, head_type=htype, heads=heads,
+    spec = dict(backbone=bname, backbone_cfg=bcfg, head_type=htype, heads=heads,
                 part_names=list(part_names) if part_names else None,
                 edges=[tuple(e) for e in edges] if edges else None)
+    if htype == "multi_class_bottomup":
+        spec["classes"] = list(hcfg["class_maps"]["classes"])
+    return spec
 
 
 class CompiledModel:

@@ -679,19 +679,91 @@ class BottomUpInferenceModel(InferenceModel):
 
 
 # ------------------------------------------------------------------------------------------
+class BottomUpMultiClassInferenceLayer(InferenceLayer):
+    """sleap/nn/inference.py:3351-3589: network (confidence maps + class maps) -> local peaks -> identity grouping by the
+    class-map probability at each peak (sleap_b200.nn.identity.classify_peaks_from_maps).  The network and the peak
+    finder run on the device; the grouping is host logic in the reference too (TensorFlow ops around a SciPy callback)."""
+
+    def __init__(self, keras_model, input_scale=1.0, pad_to_stride=1, cm_output_stride=None, class_maps_output_stride=None,
+                 peak_threshold=0.2, refinement="integral", integral_patch_size=5, return_confmaps=False,
+                 return_class_maps=False, **kwargs):
+        super().__init__(keras_model, input_scale=input_scale, pad_to_stride=pad_to_stride, **kwargs)
+        heads = keras_model.cm.head_buffers
+        if "MultiInstanceConfmapsHead" not in heads:
+            raise ValueError("Index of the confidence maps output tensor must be specified if not named 'MultiInstanceConfmapsHead'.")
+        if "ClassMapsHead" not in heads:
+            raise ValueError("Index of the class maps output tensor must be specified if not named 'ClassMapsHead'.")
+        self.has_offsets = "OffsetRefinementHead" in heads
+        self.cm_output_stride = cm_output_stride or keras_model.cm.head_strides["MultiInstanceConfmapsHead"]
+        self.class_maps_output_stride = class_maps_output_stride or keras_model.cm.head_strides["ClassMapsHead"]
+        self.peak_threshold = peak_threshold
+        self.refinement = refinement
+        self.integral_patch_size = integral_patch_size
+        self.return_confmaps = return_confmaps
+        self.return_class_maps = return_class_maps
+
+    def forward_pass(self, data):
+        """:3462-3490 (the class maps come out of a linear 1x1 head; their sigmoid, heads.py:336-338, is applied here)."""
+        imgs = self._prep(_images_of(data))
+        names = ["MultiInstanceConfmapsHead", "ClassMapsHead"] + (["OffsetRefinementHead"] if self.has_offsets else [])
+        outs = self.keras_model.forward(imgs, names)
+        cms, class_maps = outs[0], outs[1]
+        class_maps = (np.float32(1) / (np.float32(1) + np.exp(-class_maps, dtype=np.float32))).astype(np.float32)
+        return cms, class_maps, (outs[2] if self.has_offsets else None)
+
+    def find_peaks(self, cms, offsets):
+        """:3492-3528."""
+        h = self.keras_model.handle
+        if offsets is None:
+            peaks, vals, s_inds, c_inds = peak_finding.find_local_peaks(cms, threshold=self.peak_threshold, refinement=self.refinement,
+                                                                        integral_patch_size=self.integral_patch_size, handle=h)
+        else:
+            peaks, vals, s_inds, c_inds = peak_finding.find_local_peaks_with_offsets(cms, offsets, threshold=self.peak_threshold, handle=h)
+        return (peaks * np.float32(self.cm_output_stride)).astype(np.float32), vals, s_inds, c_inds
+
+    def call(self, data):
+        """:3530-3589."""
+        from sleap_b200.nn import identity
+        cms, class_maps, offsets = self.forward_pass(data)
+        peaks, peak_vals, s_inds, c_inds = self.find_peaks(cms, offsets)
+        peaks = (peaks / np.float32(self.class_maps_output_stride)).astype(np.float32)
+        inst, inst_vals, inst_scores = identity.classify_peaks_from_maps(class_maps, peaks, peak_vals, s_inds, c_inds,
+                                                                         n_channels=cms.shape[3])
+        inst = (inst * np.float32(self.class_maps_output_stride)).astype(np.float32)
+        if self.input_scale != 1.0:
+            inst = (inst / np.float32(self.input_scale) + np.float32(0.5)).astype(np.float32)
+        out = {"instance_peaks": inst, "instance_peak_vals": inst_vals, "instance_scores": inst_scores}
+        if self.return_confmaps:
+            out["confmaps"] = cms
+        if self.return_class_maps:
+            out["class_maps"] = class_maps
+        return out
+
+
+class BottomUpMultiClassInferenceModel(InferenceModel):
+    """sleap/nn/inference.py:3592-3635."""
+
+    def __init__(self, inference_layer: BottomUpMultiClassInferenceLayer):
+        self.inference_layer = inference_layer
+
+    def call(self, example):
+        return self.inference_layer.call(example)
+
+
 class PredictedInstance:
     """Array contract of ``sleap.PredictedInstance.from_numpy`` (sleap/instance.py:1164)."""
 
-    def __init__(self, points, point_confidences, instance_score, skeleton=None, track=None):
+    def __init__(self, points, point_confidences, instance_score, skeleton=None, track=None, tracking_score=0.0):
         self.points = np.asarray(points)
         self.point_confidences = np.asarray(point_confidences)
         self.score = float(instance_score)
         self.skeleton = skeleton
         self.track = track
+        self.tracking_score = float(tracking_score)
 
     @classmethod
-    def from_numpy(cls, points, point_confidences, instance_score, skeleton=None, track=None):
-        return cls(points, point_confidences, instance_score, skeleton, track)
+    def from_numpy(cls, points, point_confidences, instance_score, skeleton=None, track=None, tracking_score=0.0):
+        return cls(points, point_confidences, instance_score, skeleton, track, tracking_score)
 
     def numpy(self):
         return self.points
@@ -743,6 +815,9 @@ class Predictor:
                                                         max_instances=max_instances, **kw)
         if "multi_instance" in cfgs:
             return BottomUpPredictor.from_trained_models(cfgs["multi_instance"], max_instances=max_instances, **kw)
+        if "multi_class_bottomup" in cfgs:
+            mk = {k: kw[k] for k in ("peak_threshold", "integral_refinement", "integral_patch_size", "batch_size", "precision", "handle")}
+            return BottomUpMultiClassPredictor.from_trained_models(cfgs["multi_class_bottomup"], **mk)
         raise ValueError("Could not create predictor from model paths:" + "\n".join(model_paths))
 
     # -- shared helpers ---------------------------------------------------------------------
@@ -940,7 +1015,8 @@ class Predictor:
         """Skeleton of the loaded model(s): node names (+ edges for bottom-up models), as the reference takes them
         from the training config (:1547-1560, :2562-2580, :3230-3240)."""
         from sleap_b200.io.labels import Skeleton
-        for m in (getattr(self, "bottomup_model", None), getattr(self, "confmap_model", None), getattr(self, "centroid_model", None)):
+        for m in (getattr(self, "bottomup_model", None), getattr(self, "confmap_model", None), getattr(self, "centroid_model", None),
+                  getattr(self, "model", None)):
             if m is not None and m.spec.get("part_names"):
                 return Skeleton(m.spec["part_names"], m.spec.get("edges") or [])
         raise ValueError("the loaded model carries no part names")
@@ -1163,6 +1239,57 @@ class BottomUpPredictor(Predictor):
                    integral_refinement=integral_refinement, integral_patch_size=integral_patch_size,
                    max_instances=max_instances, max_peaks_per_sample=max_peaks_per_sample, max_node_peaks=max_node_peaks,
                    max_instances_per_frame=max_instances_per_frame)
+
+
+class BottomUpMultiClassPredictor(Predictor):
+    """sleap/nn/inference.py:3638-3860: bottom-up identity models (confidence maps + class maps).  Instances come out one per
+    class, in class order; each gets the ``Track`` named after its class (:3781-3790), ``score`` = mean point confidence and
+    ``tracking_score`` = mean class probability (:3818-3826)."""
+
+    def __init__(self, model, classes, peak_threshold=0.2, batch_size=4, integral_refinement=True, integral_patch_size=5, tracks=None):
+        super().__init__(batch_size)
+        self.model = model
+        self.classes = list(classes)
+        self.peak_threshold = peak_threshold
+        self.integral_refinement = integral_refinement
+        self.integral_patch_size = integral_patch_size
+        self.tracks = tracks
+        self._initialize_inference_model()
+
+    def _initialize_inference_model(self):
+        """:3682-3697."""
+        m = self.model
+        self.inference_model = BottomUpMultiClassInferenceModel(BottomUpMultiClassInferenceLayer(
+            keras_model=m, input_scale=m.input_scale, pad_to_stride=m.cm.max_stride, peak_threshold=self.peak_threshold,
+            refinement="integral" if self.integral_refinement else "local", integral_patch_size=self.integral_patch_size,
+            cm_output_stride=m.cm.head_strides["MultiInstanceConfmapsHead"],
+            class_maps_output_stride=m.cm.head_strides["ClassMapsHead"]))
+
+    @classmethod
+    def from_trained_models(cls, model_path, batch_size=4, peak_threshold=0.2, integral_refinement=True, integral_patch_size=5,
+                            resize_input_layer=True, precision=PRECISION_FP16, handle=None, **_):
+        """:3699-3745."""
+        _, spec, model = cls._load(model_path, precision, handle)
+        return cls(model, spec["classes"], peak_threshold=peak_threshold, batch_size=batch_size,
+                   integral_refinement=integral_refinement, integral_patch_size=integral_patch_size)
+
+    def _frames_from_example(self, ex):
+        """:3781-3838."""
+        from sleap_b200.nn.tracking import Track
+        tracks = self.tracks
+        if tracks is None:
+            tracks = self.tracks = [Track(spawned_on=0, name=n) for n in self.classes]
+        out = []
+        for i in range(len(ex["instance_peaks"])):
+            insts = []
+            for j in range(ex["instance_peaks"].shape[1]):
+                pts, confs = ex["instance_peaks"][i, j], ex["instance_peak_vals"][i, j]
+                if np.all(np.isnan(pts)):
+                    continue
+                insts.append(PredictedInstance.from_numpy(pts, confs, float(np.nanmean(confs)), track=tracks[j] if j < len(tracks) else None,
+                                                          tracking_score=float(np.nanmean(ex["instance_scores"][i, j]))))
+            out.append(LabeledFrame(int(ex["video_ind"][i]), int(ex["frame_ind"][i]), insts))
+        return out
 
 
 def load_model(model_path, batch_size=4, peak_threshold=0.2, refinement="integral", **kwargs):

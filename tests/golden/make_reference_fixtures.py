@@ -36,6 +36,7 @@ MODELS = {
     "minimal_instance.centered_instance": "minimal_instance.UNet.centered_instance",
     "minimal_robot.single_instance": "minimal_robot.UNet.single_instance",
     "minimal_instance.centered_instance_with_scaling": "minimal_instance.UNet.centered_instance_with_scaling",
+    "min_tracks_2node.bottomup_multiclass": "min_tracks_2node.UNet.bottomup_multiclass",
 }
 
 
@@ -61,6 +62,19 @@ def gt_points(slp_path):
             rows.append(xy)
         out.append(np.stack(rows))
     return np.stack(out), [int(fr["frame_idx"]) for fr in frames], json.loads(f["videos_json"].read()[0])
+
+
+def gt_tracks(slp_path, n_frames):
+    """Track name of every instance of the first ``n_frames`` labeled frames (instances table column ``track``,
+    ``tracks_json`` rows ``[spawned_on, name]``; sleap/io/format/hdf5.py:250-262)."""
+    f = h5lite.File(slp_path)
+    frames, inst = f["frames"].read(), f["instances"].read()
+    names = [json.loads(t)[1] for t in f["tracks_json"].read()]
+    out = []
+    for fr in frames[:n_frames]:
+        out.append([names[int(inst[i]["track"])] if int(inst[i]["track"]) >= 0 else "" for i in
+                    range(int(fr["instance_id_start"]), int(fr["instance_id_end"]))])
+    return out
 
 
 def read_frames(path, idxs, grayscale):
@@ -96,6 +110,26 @@ def main():
     np.savez_compressed(os.path.join(HERE, "frames_robot.npz"), images=frames, points_gt=pts, frame_idx=np.asarray(idxs),
                         video_json=np.asarray(json.dumps(vid)))
     print("robot", frames.shape, pts.shape, idxs, vid)
+
+    # identity (multi-class) models: fixture min_tracks_2node_labels = tests/data/tracks/clip.2node.slp over clip.mp4
+    # (tests/fixtures/datasets.py:94-97); the reference's predictor tests use labeled frame 0 only (test_inference.py:809-852)
+    slp = os.path.join(REF, "tracks", "clip.2node.slp")
+    f = h5lite.File(slp)
+    fr0 = f["frames"].read()[:1]
+    inst, ptab = f["instances"].read(), f["points"].read()
+    rows = []
+    for i in range(int(fr0[0]["instance_id_start"]), int(fr0[0]["instance_id_end"])):
+        p = ptab[int(inst[i]["point_id_start"]):int(inst[i]["point_id_end"])]
+        xy = np.stack([p["x"], p["y"]], -1).astype(np.float32)
+        xy[p["visible"] == 0] = np.nan
+        rows.append(xy)
+    vid = json.loads(f["videos_json"].read()[0])
+    idxs = [int(fr0[0]["frame_idx"])]
+    gray = bool(vid["backend"].get("grayscale"))
+    frames = read_frames(os.path.join(REF, "tracks", "clip.mp4"), idxs, gray)
+    np.savez_compressed(os.path.join(HERE, "frames_tracks_2node.npz"), images=frames, points_gt=np.stack(rows)[None], frame_idx=np.asarray(idxs),
+                        track_names=np.asarray(gt_tracks(slp, 1)), video_json=np.asarray(json.dumps(vid)))
+    print("tracks_2node", frames.shape, np.stack(rows).shape, idxs, gt_tracks(slp, 1), vid)
 
 
 if __name__ == "__main__":

@@ -153,3 +153,29 @@ def test_topdown_centered_instance_with_scaling(precision):
     out = both.predict(imgs)
     assert len(out) == 1 and len(out[0].instances) == 2
     _matched(gt, np.concatenate([i.numpy() for i in out[0].instances]), 2.0)
+
+
+@pytest.mark.parametrize("precision", [1, 0, 2])
+def test_bottomup_multiclass_trained_model(precision):
+    """tests/nn/test_inference.py:809-852 through ``Predictor.from_model_paths`` -> ``BottomUpMultiClassPredictor``: the
+    reference's trained identity model; two instances on the tracks named after their classes, points within 2 % of the
+    ground truth; nothing above a 1.5 threshold.  Device maps / peaks, host-side identity grouping (as in the reference)."""
+    import os
+    from sleap_b200.nn.inference import BottomUpMultiClassPredictor, Predictor
+    z = np.load(os.path.join(rm.GOLDEN, "frames_tracks_2node.npz"))
+    imgs, gt, names = z["images"], z["points_gt"][0], [str(n) for n in z["track_names"][0]]
+    pred = Predictor.from_model_paths([rm.model_dir("min_tracks_2node.bottomup_multiclass")], peak_threshold=0.7,
+                                      integral_refinement=False, precision=precision)
+    assert isinstance(pred, BottomUpMultiClassPredictor)
+    out = pred.inference_model.predict_on_batch(imgs)
+    assert out["instance_peaks"].shape == (1, 2, 2, 2) and out["instance_scores"].shape == (1, 2, 2)
+    frames = pred.predict(imgs)
+    assert len(frames) == 1 and len(frames[0].instances) == 2
+    got = sorted(frames[0].instances, key=lambda i: i.track.name)
+    assert [i.track.name for i in got] == sorted(names)
+    for inst in got:
+        assert_allclose(inst.numpy(), gt[names.index(inst.track.name)], rtol=0.02)
+        assert 0.9 < inst.tracking_score <= 1.0 and 0.7 < inst.score < 1.2
+    hi = Predictor.from_model_paths([rm.model_dir("min_tracks_2node.bottomup_multiclass")], peak_threshold=1.5,
+                                    integral_refinement=False, precision=precision).predict(imgs)
+    assert len(hi) == 1 and len(hi[0].instances) == 0

@@ -140,3 +140,30 @@ def test_oracle_centered_instance_with_scaling():
     pts, vals = oinf.find_instance_peaks_layer(cc["crops"], cc["crop_offsets"], spec, w, in_ch, input_scale=scale, pad_stride=1,
                                                resize_input_image=False)
     _matched(gt[0].reshape(-1, 2), pts.reshape(-1, 2), 1.5)
+
+
+def test_bottomup_multiclass_oracle():
+    """tests/nn/test_inference.py:809-852 (test_bottomup_multiclass_predictor / _high_threshold) on the CPU restatement:
+    the reference's trained identity model (confidence maps + sigmoid class maps), frame 0 of its ``min_tracks_2node``
+    labels; two instances, each on the track of its class, points within 2 % of the ground truth."""
+    from oracle import convnet, peak_finding as opf, preprocess as opre
+    from sleap_b200.nn import identity
+    cfg, spec, w, in_ch = rm.load_fixture_model("min_tracks_2node.bottomup_multiclass")
+    assert spec["head_type"] == "multi_class_bottomup" and spec["classes"] == ["female", "male"]
+    z = np.load(os.path.join(rm.GOLDEN, "frames_tracks_2node.npz"))
+    imgs, gt, names = z["images"], z["points_gt"][0], [str(n) for n in z["track_names"][0]]
+    scale = float(cfg["data"]["preprocessing"]["input_scaling"])
+    x = opre.preprocess(imgs, ensure_gray=(in_ch == 1), input_scale=scale, pad_stride=spec["backbone_cfg"]["max_stride"])
+    cms, cls = convnet.model_forward(x, spec, w)
+    with np.errstate(over="ignore"):
+        cls = (1.0 / (1.0 + np.exp(-cls))).astype(np.float32)
+    cs, ks = spec["heads"][0]["output_stride"], spec["heads"][1]["output_stride"]
+    for thr, want in ((0.7, 2), (1.5, 0)):
+        p, v, si, ci = opf.find_local_peaks(cms, thr, "local", 5)
+        p = ((p * np.float32(cs)).astype(np.float32) / np.float32(ks)).astype(np.float32)
+        pts, pv, pr = identity.classify_peaks_from_maps(cls, p, v, si, ci, n_channels=cms.shape[3])
+        pts = (pts * np.float32(ks)) / np.float32(scale) + np.float32(0.5)
+        found = [j for j in range(pts.shape[1]) if not np.isnan(pts[0, j]).all()]
+        assert len(found) == want
+        for j in found:
+            assert_allclose(pts[0, j], gt[names.index(spec["classes"][j])], rtol=0.02)
