@@ -708,7 +708,8 @@ class BottomUpMultiClassInferenceLayer(InferenceLayer):
         names = ["MultiInstanceConfmapsHead", "ClassMapsHead"] + (["OffsetRefinementHead"] if self.has_offsets else [])
         outs = self.keras_model.forward(imgs, names)
         cms, class_maps = outs[0], outs[1]
-        class_maps = (np.float32(1) / (np.float32(1) + np.exp(-class_maps, dtype=np.float32))).astype(np.float32)
+        with np.errstate(over="ignore"):         # exp(+large) = inf -> 1 / inf = 0: the limit the sigmoid has there
+            class_maps = (np.float32(1) / (np.float32(1) + np.exp(-class_maps, dtype=np.float32))).astype(np.float32)
         return cms, class_maps, (outs[2] if self.has_offsets else None)
 
     def find_peaks(self, cms, offsets):
