@@ -249,6 +249,19 @@ def model_forward(images_nhwc, spec, weights, n_threads=None):
                     raise ValueError(f"Could not find a feature activation for output at stride {h['output_stride']}.")
                 feat = cands[0]
             p = weights[h["name"]]
+            if h.get("vector"):
+                # ClassVectorsHead.make_head (sleap/nn/heads.py:431-460): GlobalMaxPool2D (or Flatten in NHWC order) ->
+                # (Dense + ReLU) x num_fc_layers -> Dense + softmax
+                f = feat.permute(0, 2, 3, 1).contiguous().numpy().astype(np.float32)
+                v = f.max(axis=(1, 2)) if h.get("global_pool", True) else f.reshape(len(f), -1)
+                for i in range(int(h.get("num_fc_layers", 1))):
+                    d = weights[f"pre_classification{i}_fc"]
+                    v = np.maximum(v @ np.asarray(d["kernel"], np.float32) + np.asarray(d["bias"], np.float32), np.float32(0))
+                z = v @ np.asarray(p["kernel"], np.float32) + np.asarray(p["bias"], np.float32)
+                z = z - z.max(axis=1, keepdims=True)
+                e = np.exp(z)
+                res.append((e / e.sum(axis=1, keepdims=True)).astype(np.float32))
+                continue
             y = conv2d_same(feat, p["kernel"], p.get("bias"), 1)
             res.append(y.permute(0, 2, 3, 1).contiguous().numpy())
     return res

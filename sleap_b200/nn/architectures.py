@@ -256,6 +256,22 @@ def spec_from_config(model_cfg: dict, skeleton_nodes=None, skeleton_edges=None):
         heads.append(dict(name="PartAffinityFieldsHead", channels=2 * len(edges), output_stride=paf["output_stride"]))
         if cm.get("offset_refinement"):
             heads.append(dict(name="OffsetRefinementHead", channels=2 * len(part_names), output_stride=cm["output_stride"]))
+    elif htype == "multi_class_topdown":                                    # model.py:258-296
+        cm, cv = hcfg["confmaps"], hcfg["class_vectors"]
+        part_names = cm.get("part_names") or skeleton_nodes
+        classes = cv.get("classes")
+        if part_names is None:
+            raise ValueError("Skeleton must be provided when the head configuration is incomplete.")
+        if classes is None:
+            raise ValueError("Classes must be provided when the head configuration is incomplete.")
+        heads.append(dict(name="CenteredInstanceConfmapsHead", channels=len(part_names), output_stride=cm["output_stride"]))
+        # ClassVectorsHead (heads.py:431-460): global max pool / flatten -> Dense + ReLU x num_fc_layers -> Dense + softmax.
+        # Not a convolution: the engine exposes the feature map it taps ("vector" head), the few dense layers run on the host
+        heads.append(dict(name="ClassVectorsHead", channels=len(classes), output_stride=cv["output_stride"], vector=True,
+                          num_fc_layers=int(cv.get("num_fc_layers", 1)), num_fc_units=int(cv.get("num_fc_units", 64)),
+                          global_pool=bool(cv.get("global_pool", True))))
+        if cm.get("offset_refinement"):
+            heads.append(dict(name="OffsetRefinementHead", channels=2 * len(part_names), output_stride=cm["output_stride"]))
     elif htype == "multi_class_bottomup":                                   # model.py:219-256
         cm, cls_cfg = hcfg["confmaps"], hcfg["class_maps"]
         part_names = cm.get("part_names") or skeleton_nodes
@@ -278,6 +294,8 @@ def spec_from_config(model_cfg: dict, skeleton_nodes=None, skeleton_edges=None):
                 edges=[tuple(e) for e in edges] if edges else None)
     if htype == "multi_class_bottomup":
         spec["classes"] = list(hcfg["class_maps"]["classes"])
+    if htype == "multi_class_topdown":
+        spec["classes"] = list(hcfg["class_vectors"]["classes"])
     return spec
 
 
@@ -291,6 +309,7 @@ class CompiledModel:
         self.input_buffer = 0
         self.head_buffers: Dict[str, int] = {}
         self.head_strides: Dict[str, int] = {}
+        self.vector_taps: Dict[str, dict] = {}    # "vector" heads: the feature map they read (buffer, channel offset, C, planes)
         self.input_channels = 1
         self.max_stride = 1
         self.spec = None
@@ -367,7 +386,7 @@ def compile_model(spec: dict, input_channels: int, input_scale: float = 1.0, pad
         max_stride = spec["backbone_cfg"].get("max_stride", 64)
     out_stride = outs[-1].stride
     # heads on the LAST stack only (inference.py:2885-2888)
-    head_t = {}
+    head_t, vec_t = {}, {}
     for hd in spec["heads"]:
         if hd["output_stride"] == out_stride:
             feat = outs[-1]
@@ -375,6 +394,9 @@ def compile_model(spec: dict, input_channels: int, input_scale: float = 1.0, pad
             feat = next((t for t in mids[-1] if t.stride == hd["output_stride"]), None)
             if feat is None:
                 raise ValueError(f"Could not find a feature activation for output at stride {hd['output_stride']}.")
+        if hd.get("vector"):
+            vec_t[hd["name"]] = feat
+            continue
         head_t[hd["name"]] = g.conv(feat, hd["channels"], 1, hd["name"], relu=False, f32_out=True)
 
     # ---- placement: concat parts become slices of the concat buffer ----
@@ -492,8 +514,13 @@ def compile_model(spec: dict, input_channels: int, input_scale: float = 1.0, pad
             pass
     cm.flops_per_pixel = flops
     for hd in spec["heads"]:
-        cm.head_buffers[hd["name"]] = head_t[hd["name"]].buf
         cm.head_strides[hd["name"]] = hd["output_stride"]
+        if hd["name"] in vec_t:
+            t = vec_t[hd["name"]]
+            cm.vector_taps[hd["name"]] = dict(buf=t.buf, coff=t.coff, C=t.C, planes=3 if (split and not t.f32) else 1,
+                                              buf_C=bufs[t.buf][0], f32=bool(t.f32))
+            continue
+        cm.head_buffers[hd["name"]] = head_t[hd["name"]].buf
     return cm
 
 

@@ -751,6 +751,102 @@ class BottomUpMultiClassInferenceModel(InferenceModel):
         return self.inference_layer.call(example)
 
 
+class TopDownMultiClassFindPeaks(InferenceLayer):
+    """sleap/nn/inference.py:3863-4136: centered-instance confidence maps + class vectors on crops -> global peaks ->
+    one instance per class and sample (``identity.classify_peaks_from_vectors``).  Confidence maps and the class-vector
+    head's feature map come from one device pass; the head's dense layers and the grouping run on the host."""
+
+    HEAD = "CenteredInstanceConfmapsHead"
+
+    def __init__(self, keras_model, input_scale=1.0, output_stride=None, peak_threshold=0.2, refinement="local",
+                 integral_patch_size=5, return_confmaps=False, return_class_vectors=False, optimal_grouping=True,
+                 max_crops_per_call=64, **kwargs):
+        super().__init__(keras_model, input_scale=input_scale, pad_to_stride=1, **kwargs)
+        if self.HEAD not in keras_model.cm.head_buffers:
+            raise ValueError(f"Index of the confidence maps output tensor must be specified if not named '{self.HEAD}'.")
+        if "ClassVectorsHead" not in keras_model.cm.vector_taps:
+            raise ValueError("Index of the classifier output tensor must be specified if not named 'ClassVectorsHead'.")
+        self.has_offsets = "OffsetRefinementHead" in keras_model.cm.head_buffers
+        self.output_stride = output_stride or keras_model.cm.head_strides[self.HEAD]
+        self.peak_threshold = peak_threshold
+        self.refinement = refinement
+        self.integral_patch_size = integral_patch_size
+        self.return_confmaps = return_confmaps
+        self.return_class_vectors = return_class_vectors
+        self.optimal_grouping = optimal_grouping
+        self.max_crops_per_call = max_crops_per_call
+
+    def call(self, inputs):
+        from sleap_b200.nn import identity
+        if isinstance(inputs, dict):
+            crops = inputs["crops"]
+        else:
+            crops, inputs = inputs, {}
+        crops = self._prep(crops)
+        n = crops.shape[0]
+        if "crop_sample_inds" in inputs:
+            samples, sinds = int(inputs["samples"]), np.asarray(inputs["crop_sample_inds"], np.int32)
+        else:
+            samples, sinds = n, np.arange(n, dtype=np.int32)
+        m = self.keras_model
+        n_nodes = next(h["channels"] for h in m.spec["heads"] if h["name"] == self.HEAD)
+        n_classes = next(h["channels"] for h in m.spec["heads"] if h["name"] == "ClassVectorsHead")
+        pts = np.zeros((n, n_nodes, 2), np.float32)
+        vals = np.zeros((n, n_nodes), np.float32)
+        probs = np.zeros((n, n_classes), np.float32)
+        names = [self.HEAD, "ClassVectorsHead"] + (["OffsetRefinementHead"] if self.has_offsets else [])
+        all_cms = []
+        for i in range(0, n, self.max_crops_per_call):
+            sl = slice(i, min(n, i + self.max_crops_per_call))
+            outs = m.forward(np.ascontiguousarray(crops[sl]), names)
+            cms, probs[sl] = outs[0], outs[1]
+            if self.has_offsets:
+                pts[sl], vals[sl] = peak_finding.find_global_peaks_with_offsets(cms, outs[2], threshold=self.peak_threshold, handle=m.handle)
+            else:
+                pts[sl], vals[sl] = peak_finding.find_global_peaks(cms, threshold=self.peak_threshold, refinement=self.refinement,
+                                                                   integral_patch_size=self.integral_patch_size, handle=m.handle)
+            if self.return_confmaps:
+                all_cms.append(cms)
+        pts = (pts * np.float32(self.output_stride)).astype(np.float32)                      # :4076-4082
+        if self.input_scale != 1.0:
+            pts = (pts / np.float32(self.input_scale) + np.float32(0.5)).astype(np.float32)
+        if inputs.get("crop_offsets") is not None:
+            pts = (pts + f32(inputs["crop_offsets"]).reshape(n, 1, 2)).astype(np.float32)     # :4084-4088
+        if self.optimal_grouping:
+            points, point_vals, class_probs = identity.classify_peaks_from_vectors(pts, vals, probs, sinds, samples)
+            out = {"instance_peaks": points, "instance_peak_vals": point_vals, "instance_scores": class_probs}
+        else:
+            out = {"instance_peaks": pts, "instance_peak_vals": vals, "instance_scores": probs}
+        for k in ("centroids", "centroid_vals"):
+            if k in inputs:
+                out[k] = inputs[k]
+        if self.return_confmaps:
+            cms = np.concatenate(all_cms) if all_cms else np.zeros((0,), np.float32)
+            out["instance_confmaps"] = [cms[sinds == s_] for s_ in range(samples)]
+        if self.return_class_vectors and self.optimal_grouping:
+            out["class_vectors"] = probs
+        return out
+
+
+class TopDownMultiClassInferenceModel(InferenceModel):
+    """sleap/nn/inference.py:4139-4210: centroid stage (model or ground truth) -> TopDownMultiClassFindPeaks."""
+
+    def __init__(self, centroid_crop, instance_peaks: TopDownMultiClassFindPeaks):
+        self.centroid_crop = centroid_crop
+        self.instance_peaks = instance_peaks
+
+    def call(self, example):
+        if isinstance(example, np.ndarray):
+            example = dict(image=example)
+        crop_out = self.centroid_crop.call(example)
+        out = self.instance_peaks.call(crop_out)
+        res = {k: out[k] for k in ("instance_peaks", "instance_peak_vals", "instance_scores")}
+        if "centroids" in out:
+            res["centroids"], _ = _ragged_to_dense(out["centroids"], (2,))
+            res["centroid_vals"], _ = _ragged_to_dense(out["centroid_vals"], ())
+        return res
+
+
 class PredictedInstance:
     """Array contract of ``sleap.PredictedInstance.from_numpy`` (sleap/instance.py:1164)."""
 
@@ -810,6 +906,10 @@ class Predictor:
         kw.update(caps)
         if "single_instance" in cfgs:
             return SingleInstancePredictor.from_trained_models(cfgs["single_instance"], **kw)
+        if "multi_class_topdown" in cfgs:
+            mk = {k: kw[k] for k in ("peak_threshold", "integral_refinement", "integral_patch_size", "batch_size", "precision", "handle")}
+            return TopDownMultiClassPredictor.from_trained_models(centroid_model_path=cfgs.get("centroid"),
+                                                                  confmap_model_path=cfgs["multi_class_topdown"], **mk)
         if "centroid" in cfgs or "centered_instance" in cfgs:
             return TopDownPredictor.from_trained_models(centroid_model_path=cfgs.get("centroid"),
                                                         confmap_model_path=cfgs.get("centered_instance"),
@@ -1276,21 +1376,95 @@ class BottomUpMultiClassPredictor(Predictor):
 
     def _frames_from_example(self, ex):
         """:3781-3838."""
-        from sleap_b200.nn.tracking import Track
-        tracks = self.tracks
-        if tracks is None:
-            tracks = self.tracks = [Track(spawned_on=0, name=n) for n in self.classes]
-        out = []
-        for i in range(len(ex["instance_peaks"])):
-            insts = []
-            for j in range(ex["instance_peaks"].shape[1]):
-                pts, confs = ex["instance_peaks"][i, j], ex["instance_peak_vals"][i, j]
-                if np.all(np.isnan(pts)):
-                    continue
-                insts.append(PredictedInstance.from_numpy(pts, confs, float(np.nanmean(confs)), track=tracks[j] if j < len(tracks) else None,
-                                                          tracking_score=float(np.nanmean(ex["instance_scores"][i, j]))))
-            out.append(LabeledFrame(int(ex["video_ind"][i]), int(ex["frame_ind"][i]), insts))
-        return out
+        return _multiclass_frames(self, ex)
+
+
+def _multiclass_frames(predictor, ex):
+    """Shared by the two identity predictors (:3781-3838, :4506-4566): instance j of a frame belongs to class j and gets
+    the ``Track`` named after it; ``score`` = mean point confidence, ``tracking_score`` = mean class probability."""
+    from sleap_b200.nn.tracking import Track
+    tracks = predictor.tracks
+    if tracks is None:
+        tracks = predictor.tracks = [Track(spawned_on=0, name=n) for n in predictor.classes]
+    out = []
+    for i in range(len(ex["instance_peaks"])):
+        insts = []
+        for j in range(ex["instance_peaks"].shape[1]):
+            pts, confs = ex["instance_peaks"][i, j], ex["instance_peak_vals"][i, j]
+            if np.all(np.isnan(pts)):
+                continue
+            insts.append(PredictedInstance.from_numpy(pts, confs, float(np.nanmean(confs)), track=tracks[j] if j < len(tracks) else None,
+                                                      tracking_score=float(np.nanmean(ex["instance_scores"][i, j]))))
+        out.append(LabeledFrame(int(ex["video_ind"][i]), int(ex["frame_ind"][i]), insts))
+    return out
+
+
+class TopDownMultiClassPredictor(Predictor):
+    """sleap/nn/inference.py:4213-4605: top-down identity models -- a centroid model (or ground-truth centroids from a
+    labels provider) and a centered-instance model with a class-vector head; one instance per class and frame."""
+
+    def __init__(self, centroid_model=None, confmap_model=None, crop_size=160, peak_threshold=0.2, integral_refinement=True,
+                 integral_patch_size=5, batch_size=4, max_instances=None, max_peaks_per_sample=256, tracks=None):
+        super().__init__(batch_size)
+        if confmap_model is None:
+            raise ValueError("The topdown multi-class confidence map model must be provided.")
+        self.centroid_model, self.confmap_model = centroid_model, confmap_model
+        self.classes = list(confmap_model.spec["classes"])
+        self.anchor_part = None
+        self.crop_size = crop_size
+        self.peak_threshold = peak_threshold
+        self.integral_refinement = integral_refinement
+        self.integral_patch_size = integral_patch_size
+        self.max_instances = max_instances
+        self.max_peaks_per_sample = max_peaks_per_sample
+        self.tracks = tracks
+        self._initialize_inference_model()
+
+    def _initialize_inference_model(self):
+        """:4263-4318."""
+        ref = "integral" if self.integral_refinement else "local"
+        cm, im = self.centroid_model, self.confmap_model
+        iscale = float(getattr(im, "config_input_scale", im.input_scale))
+        if im.input_scale != 1.0:
+            raise ValueError("top-down instance models must be built without a resize op (resize_input_image=False)")
+        if cm is None:
+            cc = CentroidCropGroundTruth(crop_size=self.crop_size, handle=im.handle)
+            cc.input_scale = iscale
+        else:
+            cc = CentroidCrop(keras_model=cm, crop_size=self.crop_size, input_scale=cm.input_scale, pad_to_stride=cm.cm.max_stride,
+                              peak_threshold=self.peak_threshold, refinement=ref, integral_patch_size=self.integral_patch_size,
+                              max_instances=self.max_instances, return_crops=True, max_peaks_per_sample=self.max_peaks_per_sample)
+            cc.precrop_resize = iscale
+        fp = TopDownMultiClassFindPeaks(keras_model=im, input_scale=iscale, peak_threshold=self.peak_threshold, refinement=ref,
+                                        integral_patch_size=self.integral_patch_size)
+        self.inference_model = TopDownMultiClassInferenceModel(cc, fp)
+
+    @property
+    def uses_ground_truth(self):
+        return self.centroid_model is None
+
+    @classmethod
+    def from_trained_models(cls, centroid_model_path=None, confmap_model_path=None, batch_size=4, peak_threshold=0.2,
+                            integral_refinement=True, integral_patch_size=5, resize_input_layer=True, max_instances=None,
+                            precision=PRECISION_FP16, handle=None, max_peaks_per_sample=256, **_):
+        """:4320-4401."""
+        if confmap_model_path is None:
+            raise ValueError("The topdown multi-class confidence map model must be provided.")
+        cmodel, anchor = None, None
+        if centroid_model_path is not None:
+            ccfg, _, cmodel = cls._load(centroid_model_path, precision, handle)
+            anchor = ccfg["data"]["instance_cropping"].get("center_on_part")
+        icfg, _, imodel = cls._load(confmap_model_path, precision, handle, resize_in_graph=False)
+        crop = icfg["data"]["instance_cropping"]["crop_size"]
+        anchor = icfg["data"]["instance_cropping"].get("center_on_part") if anchor is None else anchor
+        obj = cls(cmodel, imodel, crop, peak_threshold, integral_refinement, integral_patch_size, batch_size, max_instances,
+                  max_peaks_per_sample)
+        obj.anchor_part = anchor
+        return obj
+
+    def _frames_from_example(self, ex):
+        """:4506-4566."""
+        return _multiclass_frames(self, ex)
 
 
 def load_model(model_path, batch_size=4, peak_threshold=0.2, refinement="integral", **kwargs):

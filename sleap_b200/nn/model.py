@@ -26,6 +26,9 @@ class DeviceModel:
         self.input_scale = float(input_scale)
         self.cm = arch.compile_model(spec, input_channels, input_scale, pad_to_stride, split=(precision == PRECISION_SPLIT))
         blob = self.cm.pack_weights(weights)
+        # dense layers of "vector" heads stay on the host (heads.py:431-460)
+        self.dense_weights = {k: {kk: np.asarray(vv, np.float32) for kk, vv in v.items()} for k, v in weights.items()
+                              if k.startswith("pre_classification") or k in self.cm.vector_taps}
         ops = self.cm.ops_array()
         mid = c_int(-1)
         self.handle.call("sb_load_model", ptr(ops), ops.shape[0], ptr(blob), int(blob.size), int(precision),
@@ -61,18 +64,50 @@ class DeviceModel:
         B, H, W, C = images.shape
         if self.configured_for is None or self.configured_for[0] < B or self.configured_for[1:] != (H, W, C):
             self.configure(B, H, W, C)
-        head_names = head_names or [h["name"] for h in self.spec["heads"]]
+        head_names = head_names or [h["name"] for h in self.spec["heads"] if not h.get("vector")]
         nh, nw = self.net_hw(H, W)
         outs, ids = [], []
         for n in head_names:
             st = self.cm.head_strides[n]
+            if n in self.cm.vector_taps:          # "vector" head: fetch the feature map it taps, dense layers on the host
+                outs.append(np.zeros((B, nh // st, nw // st, self.cm.vector_taps[n]["buf_C"]), np.float32))
+                ids.append(self.cm.vector_taps[n]["buf"])
+                continue
             ch = next(h["channels"] for h in self.spec["heads"] if h["name"] == n)
             outs.append(np.zeros((B, nh // st, nw // st, ch), np.float32))
             ids.append(self.cm.head_buffers[n])
         ids_a = np.asarray(ids, np.int32)
         ptrs = (c_void_p * len(outs))(*[o.ctypes.data for o in outs])
         self.handle.call("sb_model_forward", self.model_id, ptr(images), int(is_u8), B, len(outs), ptr(ids_a), ptrs)
+        for i, n in enumerate(head_names):
+            if n in self.cm.vector_taps:
+                outs[i] = self._class_vectors(outs[i], n)
         return outs
+
+    def _class_vectors(self, buf, name):
+        tap = self.cm.vector_taps[name]
+        c0, Cl = tap["coff"], tap["C"]
+        if tap["planes"] == 3:                    # precision 2: [lo | hi | hi] planes -> lo + hi
+            feat = buf[..., c0:c0 + Cl] + buf[..., c0 + Cl:c0 + 2 * Cl]
+        else:
+            feat = buf[..., c0:c0 + Cl]
+        head = next(h for h in self.spec["heads"] if h["name"] == name)
+        return class_vectors_from_features(feat, head, self.dense_weights)
+
+
+def class_vectors_from_features(feat, head, weights):
+    """``ClassVectorsHead.make_head`` (sleap/nn/heads.py:431-460) on a feature map ``feat`` (N, H, W, C) float32: global max
+    pool (or Keras Flatten in H, W, C order), ``num_fc_layers`` x (Dense + ReLU), Dense + softmax -> (N, n_classes)."""
+    x = np.asarray(feat, np.float32)
+    x = x.max(axis=(1, 2)) if head.get("global_pool", True) else x.reshape(len(x), -1)
+    for i in range(int(head.get("num_fc_layers", 1))):
+        p = weights[f"pre_classification{i}_fc"]
+        x = np.maximum(x @ np.asarray(p["kernel"], np.float32) + np.asarray(p["bias"], np.float32), np.float32(0))
+    p = weights[head["name"]]
+    z = x @ np.asarray(p["kernel"], np.float32) + np.asarray(p["bias"], np.float32)
+    z = z - z.max(axis=1, keepdims=True)
+    e = np.exp(z, dtype=np.float32)
+    return (e / e.sum(axis=1, keepdims=True)).astype(np.float32)
 
 
 class FrameResizer:

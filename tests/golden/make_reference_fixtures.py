@@ -37,6 +37,7 @@ MODELS = {
     "minimal_robot.single_instance": "minimal_robot.UNet.single_instance",
     "minimal_instance.centered_instance_with_scaling": "minimal_instance.UNet.centered_instance_with_scaling",
     "min_tracks_2node.bottomup_multiclass": "min_tracks_2node.UNet.bottomup_multiclass",
+    "min_tracks_2node.topdown_multiclass": "min_tracks_2node.UNet.topdown_multiclass",
 }
 
 

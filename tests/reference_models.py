@@ -53,3 +53,16 @@ def labels_minimal_instance():
     lab = Labels(lfs, [json.loads(str(z["video_json"]))], [sk])
     lab.set_video(0, Video.from_numpy(z["images"]))
     return lab
+
+
+def labels_tracks_2node():
+    """Frame 0 of the reference's ``min_tracks_2node_labels`` fixture (tests/fixtures/datasets.py:94-97: clip.2node.slp,
+    skeleton head-thorax, two tracked flies), rebuilt from the committed frame + ground-truth points."""
+    from sleap_b200.io.labels import Instance, LabeledFrame, Labels, Skeleton
+    from sleap_b200.io.video import Video
+    z = np.load(os.path.join(GOLDEN, "frames_tracks_2node.npz"))
+    sk = Skeleton(["head", "thorax"], [("head", "thorax")])
+    lfs = [LabeledFrame(0, int(fi), [Instance(p, sk) for p in pts]) for fi, pts in zip(z["frame_idx"], z["points_gt"])]
+    lab = Labels(lfs, [json.loads(str(z["video_json"]))], [sk])
+    lab.set_video(0, Video.from_numpy(z["images"]))
+    return lab

@@ -179,3 +179,37 @@ def test_bottomup_multiclass_trained_model(precision):
     hi = Predictor.from_model_paths([rm.model_dir("min_tracks_2node.bottomup_multiclass")], peak_threshold=1.5,
                                     integral_refinement=False, precision=precision).predict(imgs)
     assert len(hi) == 1 and len(hi[0].instances) == 0
+
+
+@pytest.mark.parametrize("precision", [1, 0, 2])
+def test_topdown_multiclass_trained_model(precision):
+    """tests/nn/test_inference.py:855-894 through ``TopDownMultiClassPredictor.from_trained_models(confmap_model_path=...)``
+    on a ``Labels`` input (ground-truth centroids, device crops): confidence maps and the class-vector head's feature map
+    from one device pass, dense layers + grouping on the host; two instances on the tracks of their classes, points within
+    2 % of the ground truth; nothing above a 1.5 threshold; class probabilities agree with the oracle network."""
+    import os
+    from oracle import convnet, preprocess as opre
+    from sleap_b200.nn.inference import Predictor, TopDownMultiClassPredictor
+    z = np.load(os.path.join(rm.GOLDEN, "frames_tracks_2node.npz"))
+    gt, names = z["points_gt"][0], [str(n) for n in z["track_names"][0]]
+    labels = rm.labels_tracks_2node()
+    d = rm.model_dir("min_tracks_2node.topdown_multiclass")
+    pred = TopDownMultiClassPredictor.from_trained_models(confmap_model_path=d, peak_threshold=0.7, integral_refinement=False,
+                                                          precision=precision)
+    assert isinstance(Predictor.from_model_paths([d], precision=precision), TopDownMultiClassPredictor)
+    frames = pred.predict(labels)
+    assert len(frames) == 1 and len(frames[0].instances) == 2
+    got = sorted(frames[0].instances, key=lambda i: i.track.name)
+    assert [i.track.name for i in got] == sorted(names)
+    for inst in got:
+        assert_allclose(inst.numpy(), gt[names.index(inst.track.name)], rtol=0.02)
+        assert inst.tracking_score > 0.99
+    # class probabilities of the device path (feature map tapped on the device, dense layers on the host) vs the oracle network
+    cfg, spec, w, in_ch = rm.load_fixture_model("min_tracks_2node.topdown_multiclass")
+    cc = oinf.centroid_crop_ground_truth_layer(z["images"], [gt[:, 1, :]], cfg["data"]["instance_cropping"]["crop_size"], 1.0)
+    want = convnet.model_forward(opre.preprocess(cc["crops"], ensure_gray=True, input_scale=1.0, pad_stride=16), spec, w)[1]
+    have = pred.confmap_model.forward(cc["crops"], ["ClassVectorsHead"])[0]
+    assert_allclose(have, want, atol={0: 2e-2, 1: 1e-4, 2: 1e-4}[precision])
+    hi = TopDownMultiClassPredictor.from_trained_models(confmap_model_path=d, peak_threshold=1.5, integral_refinement=False,
+                                                        precision=precision).predict(labels)
+    assert len(hi) == 1 and len(hi[0].instances) == 0

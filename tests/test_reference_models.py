@@ -167,3 +167,31 @@ def test_bottomup_multiclass_oracle():
         assert len(found) == want
         for j in found:
             assert_allclose(pts[0, j], gt[names.index(spec["classes"][j])], rtol=0.02)
+
+
+def test_topdown_multiclass_oracle():
+    """tests/nn/test_inference.py:855-894 (test_topdown_multiclass_predictor / _high_threshold) on the CPU restatement:
+    ground-truth centroids (anchor part thorax) -> 128-px crops -> the reference's trained centered-instance + class-vector
+    model (ClassVectorsHead = global max pool + 3 x Dense(64) + softmax on the stride-16 encoder output) -> global peaks ->
+    classify_peaks_from_vectors; both flies on the track of their class, points within 2 % of the ground truth."""
+    from oracle import convnet, peak_finding as opf, preprocess as opre
+    from sleap_b200.nn import identity
+    cfg, spec, w, in_ch = rm.load_fixture_model("min_tracks_2node.topdown_multiclass")
+    assert spec["head_type"] == "multi_class_topdown" and spec["classes"] == ["female", "male"]
+    assert spec["heads"][1]["vector"] and spec["heads"][1]["num_fc_layers"] == 3 and spec["heads"][1]["output_stride"] == 16
+    z = np.load(os.path.join(rm.GOLDEN, "frames_tracks_2node.npz"))
+    imgs, gt, names = z["images"], z["points_gt"][0], [str(n) for n in z["track_names"][0]]
+    crop = cfg["data"]["instance_cropping"]["crop_size"]
+    cc = oinf.centroid_crop_ground_truth_layer(imgs, [gt[:, 1, :]], crop, 1.0)          # anchor = thorax = node 1
+    x = opre.preprocess(cc["crops"], ensure_gray=(in_ch == 1), input_scale=1.0, pad_stride=spec["backbone_cfg"]["max_stride"])
+    cms, probs = convnet.model_forward(x, spec, w)
+    assert probs.shape == (2, 2) and np.allclose(probs.sum(1), 1.0, atol=1e-6)
+    for thr, want in ((0.7, 2), (1.5, 0)):
+        pts, vals = opf.find_global_peaks(cms, thr, "local", 5)
+        pts = (pts * np.float32(spec["heads"][0]["output_stride"]) + cc["crop_offsets"][:, None, :]).astype(np.float32)
+        P, V, C = identity.classify_peaks_from_vectors(pts, vals, probs, cc["crop_sample_inds"], 1)
+        found = [j for j in range(P.shape[1]) if not np.isnan(P[0, j]).all()]
+        assert len(found) == want
+        for j in found:
+            assert_allclose(P[0, j], gt[names.index(spec["classes"][j])], rtol=0.02)
+            assert C[0, j] > 0.99
