@@ -530,12 +530,10 @@ class Tracker:
                              max_tracking: bool = False, oks_errors=None, oks_score_weighting: bool = False,
                              oks_normalization: str = "all", img_scale: float = 1.0, of_window_size: int = 21,
                              of_max_levels: int = 3, save_shifted_instances: bool = False, kf_init_frame_count: int = 0,
-                             **kwargs) -> "Tracker":
+                             kf_node_indices: Optional[list] = None, **kwargs) -> "Tracker":
         max_tracking = max_tracking if max_tracks else False
         if max_tracking and tracker in ("simple", "flow"):          # :882-884
             tracker += "maxtracks"
-        if kf_init_frame_count:
-            raise ValueError("the Kalman-filter tracker (kf_init_frame_count > 0) is not part of this build.")
         if tracker.lower() == "none":
             return cls(track_window=track_window, similarity_function=None, matching_function=None, candidate_maker=None)
         if tracker not in CANDIDATE_MAKERS:
@@ -556,9 +554,25 @@ class Tracker:
         pre_cull = None
         if target_instance_count and pre_cull_to_target:
             pre_cull = lambda insts: cull_frame_instances(insts, target_instance_count, pre_cull_iou_threshold)
-        return cls(track_window=track_window, similarity_function=sim, matching_function=MATCHERS[match], candidate_maker=maker,
-                   max_tracks=max_tracks, max_tracking=max_tracking, min_new_track_points=min_new_track_points,
-                   robust_best_instance=robust, pre_cull_function=pre_cull, target_instance_count=target_instance_count)
+        tracker_obj = cls(track_window=track_window, similarity_function=sim, matching_function=MATCHERS[match], candidate_maker=maker,
+                          max_tracks=max_tracks, max_tracking=max_tracking, min_new_track_points=min_new_track_points,
+                          robust_best_instance=robust, pre_cull_function=pre_cull, target_instance_count=target_instance_count)
+        # Kalman filters on top of the regular tracker (:955-991; sleap_b200/nn/kalman.py)
+        if (max_tracks or target_instance_count) and kf_init_frame_count:
+            if not kf_node_indices:
+                raise ValueError("Kalman filter requires node indices for instance tracking.")
+            if tracker in ("flow", "flowmaxtracks"):
+                raise ValueError("Kalman filter requires simple tracker for initial tracking.")
+            if similarity == "normalized_instance":
+                raise ValueError("Kalman filter does not support normalized_instance_similarity.")
+            from sleap_b200.nn.kalman import KalmanTracker
+            return KalmanTracker.make_tracker(init_tracker=tracker_obj, init_frame_count=int(kf_init_frame_count),
+                                              node_indices=[int(i) for i in kf_node_indices],
+                                              instance_count=int(target_instance_count or max_tracks),
+                                              instance_iou_threshold=pre_cull_iou_threshold)
+        if kf_init_frame_count and not (max_tracks or target_instance_count):
+            raise ValueError("Kalman filter requires max tracks or target instance count.")
+        return tracker_obj
 
 
 def run_tracker(frames: list, tracker: Tracker, images=None) -> list:
