@@ -200,6 +200,45 @@ def cull_instances(frames: list, instance_count: int, iou_threshold: Optional[fl
         cull_frame_instances(lf.instances, instance_count, iou_threshold)
 
 
+def connect_single_track_breaks(frames: list, instance_count: int) -> list:
+    """sleap/nn/tracker/components.py:417-466: whenever exactly one track disappears and exactly one new track appears
+    between a frame and the last frame that had ``instance_count`` tracks, the new track is merged into the lost one
+    (for the rest of the video).  Modifies the frames in place."""
+    if not frames:
+        return frames
+    fix_track_map = {}
+    last_good = {inst.track for inst in frames[0].instances}
+    for lf in frames:
+        frame_tracks = {inst.track for inst in lf.instances}
+        if frame_tracks & set(fix_track_map):
+            for inst in lf.instances:
+                if inst.track in fix_track_map and fix_track_map[inst.track] not in frame_tracks:
+                    inst.track = fix_track_map[inst.track]
+                    frame_tracks = {i.track for i in lf.instances}
+        extra, missing = frame_tracks - last_good, last_good - frame_tracks
+        if len(extra) == 1 and len(missing) == 1:
+            for inst in lf.instances:
+                if inst.track in extra:
+                    old, new = inst.track, missing.pop()
+                    fix_track_map[old] = new
+                    inst.track = new
+                    break
+        elif len(frame_tracks) == instance_count:
+            last_good = frame_tracks
+    return frames
+
+
+class TrackCleaner:
+    """tracking.py:1513-1539: cull each frame to ``instance_count`` instances, then join single track breaks."""
+
+    def __init__(self, instance_count: int, iou_threshold: Optional[float] = None):
+        self.instance_count, self.iou_threshold = instance_count, iou_threshold
+
+    def run(self, frames: list):
+        cull_instances(frames, self.instance_count, self.iou_threshold)
+        connect_single_track_breaks(frames, self.instance_count)
+
+
 # ---- matches of one frame ---------------------------------------------------------------------------
 class Match:
     def __init__(self, track, instance, score=None, is_first_choice=False):
@@ -515,8 +554,17 @@ class Tracker:
             self.track_matching_queue.append((t, tracked, keep_img))
         return tracked
 
+    cleaner: Optional["TrackCleaner"] = None          # deprecated --clean_instance_count path (:924-927)
+    post_connect_single_breaks: bool = False
+
     def final_pass(self, frames: list):
-        """Post-processing hook of the reference (track cleaning / single-break joining): nothing here."""
+        """:816-835: post-processing after the last frame -- the (deprecated) cleaner, or the single-break joining."""
+        if self.cleaner is not None:
+            self.cleaner.run(frames)
+        elif (self.target_instance_count or self.max_tracks) and self.post_connect_single_breaks:
+            if not self.target_instance_count:
+                self.target_instance_count = self.max_tracks
+            connect_single_track_breaks(frames, self.target_instance_count)
 
     def get_name(self) -> str:
         return f"{type(self.candidate_maker).__name__}.{getattr(self.similarity_function, '__name__', 'none')}." \
@@ -530,7 +578,8 @@ class Tracker:
                              max_tracking: bool = False, oks_errors=None, oks_score_weighting: bool = False,
                              oks_normalization: str = "all", img_scale: float = 1.0, of_window_size: int = 21,
                              of_max_levels: int = 3, save_shifted_instances: bool = False, kf_init_frame_count: int = 0,
-                             kf_node_indices: Optional[list] = None, **kwargs) -> "Tracker":
+                             kf_node_indices: Optional[list] = None, post_connect_single_breaks: bool = False,
+                             clean_instance_count: int = 0, clean_iou_threshold: Optional[float] = None, **kwargs) -> "Tracker":
         max_tracking = max_tracking if max_tracks else False
         if max_tracking and tracker in ("simple", "flow"):          # :882-884
             tracker += "maxtracks"
@@ -557,6 +606,9 @@ class Tracker:
         tracker_obj = cls(track_window=track_window, similarity_function=sim, matching_function=MATCHERS[match], candidate_maker=maker,
                           max_tracks=max_tracks, max_tracking=max_tracking, min_new_track_points=min_new_track_points,
                           robust_best_instance=robust, pre_cull_function=pre_cull, target_instance_count=target_instance_count)
+        tracker_obj.post_connect_single_breaks = bool(post_connect_single_breaks)
+        if clean_instance_count:
+            tracker_obj.cleaner = TrackCleaner(instance_count=int(clean_instance_count), iou_threshold=clean_iou_threshold)
         # Kalman filters on top of the regular tracker (:955-991; sleap_b200/nn/kalman.py)
         if (max_tracks or target_instance_count) and kf_init_frame_count:
             if not kf_node_indices:

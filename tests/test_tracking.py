@@ -145,3 +145,31 @@ def test_flow_tracker_keeps_identities_across_a_jump(tracker, save):
     simple = T.run_tracker([LabeledFrame(0, f.frame_idx, [PredictedInstance.from_numpy(i.numpy(), [1, 1, 1], 1.0) for i in f.instances])
                             for f in frames], T.Tracker.make_tracker_by_name(tracker="simple", similarity="instance", match="hungarian"))
     assert len({i.track.name for lf in simple for i in lf.instances}) >= 2
+
+
+def test_connect_single_track_breaks_and_final_pass():
+    """sleap/nn/tracker/components.py:417-466 through ``Tracker.final_pass`` (tracking.py:816-835): a track that is lost while
+    exactly one new track appears is continued under the old identity for the rest of the video; two simultaneous
+    changes are left alone; the option is off by default."""
+    from sleap_b200.nn.tracking import Track, Tracker, connect_single_track_breaks
+
+    class I:
+        def __init__(self, track):
+            self.track = track
+
+    class F:
+        def __init__(self, idx, tracks):
+            self.frame_idx, self.instances = idx, [I(t) for t in tracks]
+
+    a, b, c, d, e = (Track(0, n) for n in "abcde")
+    frames = [F(0, [a, b]), F(1, [a, b]), F(2, [a, c]), F(3, [a, c]), F(4, [c, a]), F(5, [d, e])]
+    connect_single_track_breaks(frames, 2)
+    assert [[i.track.name for i in f.instances] for f in frames[:5]] == [["a", "b"], ["a", "b"], ["a", "b"], ["a", "b"], ["b", "a"]]
+    assert [i.track.name for i in frames[5].instances] == ["d", "e"]          # two lost, two new: ambiguous, untouched
+    frames = [F(0, [a, b]), F(1, [a, c])]
+    t = Tracker.make_tracker_by_name(tracker="simple", target_instance_count=2)
+    t.final_pass(frames)
+    assert [i.track.name for i in frames[1].instances] == ["a", "c"]          # post_connect_single_breaks defaults to False
+    t = Tracker.make_tracker_by_name(tracker="simple", max_tracking=True, max_tracks=2, post_connect_single_breaks=True)
+    t.final_pass(frames)
+    assert [i.track.name for i in frames[1].instances] == ["a", "b"] and t.target_instance_count == 2
