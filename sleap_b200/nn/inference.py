@@ -1154,6 +1154,8 @@ class Predictor:
         finally:
             q.put(None)
             t.join()
+        if self.tracker is not None:                                 # :2702-2703, :3345-3346
+            self.tracker.final_pass(frames)
         return frames
 
     def _frames_from_example(self, ex):
