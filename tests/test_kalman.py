@@ -125,3 +125,54 @@ def test_kalman_tracker_keeps_identities_through_a_crossing():
             assert inst.track is ids[who], (t, who)
     assert tr.init_done and ids["a"] is not ids["b"]
     assert set(tr.kalman_tracker.tracks) == {ids["a"], ids["b"]}
+
+
+def test_kalman_tracker_culls_and_resets_after_a_gap():
+    """The pre-cull keeps the ``instance_count`` best instances before matching (a low-score spurious detection never gets a
+    track); when BOTH filters have gone unmatched for more than ``reset_gap_size`` frames their identities are replaced by
+    fresh tracks whose spawn frame is set at their first match (kalman.py:150-160, 236-242)."""
+    rng = np.random.default_rng(3)
+    shape = np.array([[0.0, 0.0], [6.0, 0.0]])
+    tr = Tracker.make_tracker_by_name(tracker="simple", similarity="centroid", match="greedy", track_window=5, target_instance_count=2,
+                                      pre_cull_to_target=True, kf_init_frame_count=6, kf_node_indices=[0, 1])
+
+    def frame(t, jump=0.0):
+        a = shape + np.array([20.0 + 2.0 * t + jump, 30.0])
+        b = shape + np.array([20.0 + 2.0 * t + jump, 120.0])
+        return a, b
+
+    first = {}
+    for t in range(20):
+        a, b = frame(t)
+        out = tr.track([_Inst(a + rng.normal(0, 0.2, a.shape)), _Inst(b + rng.normal(0, 0.2, b.shape)),
+                        _Inst(shape + np.array([300.0, 300.0]), score=0.05)], t=t)
+        assert len(out) == 2 and all(i.score > 0.5 for i in out)          # the spurious detection was culled
+        for i in out:
+            first.setdefault("a" if abs(i.numpy()[0, 1] - 30.0) < 10 else "b", i.track)
+    assert tr.init_done
+    assert set(tr.kalman_tracker.tracks) == {first["a"], first["b"]}
+
+
+def test_kalman_tracker_replaces_identities_after_a_gap():
+    """kalman.py:236-242: when more than one filter has gone unmatched for more than ``reset_gap_size`` frames (here two of three
+    animals leave the field of view while the third keeps being tracked), those filters continue under fresh tracks whose
+    spawn frame is set at their first match (:150-160, :228-232)."""
+    shape = np.array([[0.0, 0.0], [6.0, 0.0]])
+    tr = Tracker.make_tracker_by_name(tracker="simple", similarity="centroid", match="greedy", track_window=5, target_instance_count=3,
+                                      kf_init_frame_count=6, kf_node_indices=[0, 1])
+    pos = lambda t: [shape + np.array([20.0 + 2.0 * t, y]) for y in (30.0, 120.0, 210.0)]
+    for t in range(15):
+        out = tr.track([_Inst(p) for p in pos(t)], t=t)
+    assert tr.init_done and len(tr.kalman_tracker.tracks) == 3
+    by_y = {round(float(i.numpy()[0, 1])): i.track for i in out}
+    stay, gone = by_y[30], {by_y[120], by_y[210]}
+    for t in range(15, 23):                                        # only the first animal is visible
+        out = tr.track([_Inst(pos(t)[0])], t=t)
+        assert out[0].track is stay
+    now = set(tr.kalman_tracker.tracks)
+    assert stay in now and not (now & gone) and len(now) == 3      # the two lost identities were replaced ...
+    assert all(t_.spawned_on == -1 for t_ in now if t_ is not stay)
+    out = tr.track([_Inst(p) for p in pos(23)], t=23)              # ... and are picked up again by the same (coasting) filters
+    tracks = {round(float(i.numpy()[0, 1])): i.track for i in out}
+    assert tracks[30] is stay and tracks[120] in now and tracks[210] in now and tracks[120] is not tracks[210]
+    assert tracks[120].spawned_on == 23 and tracks[210].spawned_on == 23
